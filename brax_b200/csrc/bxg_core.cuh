@@ -1,0 +1,892 @@
+// bxg_core.cuh -- the fused generalized physics step, one lane-group per env.
+//
+// Execution model: G lanes (16 or 32) cooperate on one environment whose whole
+// working state lives in a shared-memory slab (layout: bxg_model.h Dims::s_*).
+// The algorithm is written ONCE against a tiny executor interface X:
+//
+//   ex.lanes(f)    run f(lane) on every lane of the group, then group barrier
+//   ex.sum/max(p)  group all-reduce over a per-lane value
+//
+// DevExec (bxg_kernels.cu) maps it to __syncwarp / shuffles on sm_100a.
+// HostExec (tests/simt/) runs the lanes as a loop so that kernel LOGIC can be
+// checked against the oracle on a machine without a GPU; it is test-only code
+// and is never reachable from the product library.
+//
+// Reference statements restated here (paths relative to the brax tree):
+//   pipeline.step        brax/generalized/pipeline.py:64-94      substep()
+//   actuator.to_tau      brax/actuator.py:23-57                  dyn_forces()
+//   dynamics.forward     brax/generalized/dynamics.py:137-236    dyn_forces()
+//   constraint.force     brax/generalized/constraint.py:194-240  con_force()
+//   jaxopt PG            (third party; see oracle/bxg_oracle.c)   con_force()
+//   integrator.integrate brax/generalized/integrator.py:46-84    integrate()
+//   kinematics.forward   brax/kinematics.py:31-108               kinematics()
+//   dynamics.transform_com  generalized/dynamics.py:27-134       transform_com()
+//   mass.matrix          brax/generalized/mass.py:27-83          mass_matrix()
+//   math.inv_approximate brax/math.py:278-305                    minv_newton_schulz()
+//   constraint.jacobian  brax/generalized/constraint.py:101-191  con_jacobian()
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "bxg_model.h"
+
+#if defined(__CUDACC__)
+#define BXG_HD __host__ __device__ __forceinline__
+#else
+#define BXG_HD inline
+#endif
+
+namespace bxg {
+
+// ------------------------------------------------------------------ algebra
+struct V3 { float x, y, z; };
+struct Q4 { float w, x, y, z; };
+
+BXG_HD V3 ld3(const float* p) { return V3{p[0], p[1], p[2]}; }
+BXG_HD void st3(float* p, V3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+BXG_HD Q4 ld4(const float* p) { return Q4{p[0], p[1], p[2], p[3]}; }
+BXG_HD void st4(float* p, Q4 q) { p[0] = q.w; p[1] = q.x; p[2] = q.y; p[3] = q.z; }
+BXG_HD V3 operator+(V3 a, V3 b) { return V3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+BXG_HD V3 operator-(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+BXG_HD V3 operator*(V3 a, float s) { return V3{a.x * s, a.y * s, a.z * s}; }
+BXG_HD float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+BXG_HD V3 cross(V3 a, V3 b) { return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+
+// math.rotate (brax/math.py:25-41)
+BXG_HD V3 rotate(V3 v, Q4 q) {
+  V3 u{q.x, q.y, q.z};
+  float s = q.w, d = dot(u, v), k = s * s - dot(u, u);
+  V3 c = cross(u, v);
+  V3 r{2.f * (d * u.x) + k * v.x, 2.f * (d * u.y) + k * v.y, 2.f * (d * u.z) + k * v.z};
+  float s2 = 2.f * s;
+  return V3{r.x + s2 * c.x, r.y + s2 * c.y, r.z + s2 * c.z};
+}
+// math.quat_mul (brax/math.py:86-101)
+BXG_HD Q4 qmul(Q4 u, Q4 v) {
+  return Q4{u.w * v.w - u.x * v.x - u.y * v.y - u.z * v.z,
+            u.w * v.x + u.x * v.w + u.y * v.z - u.z * v.y,
+            u.w * v.y - u.x * v.z + u.y * v.w + u.z * v.x,
+            u.w * v.z + u.x * v.y - u.y * v.x + u.z * v.w};
+}
+// math.normalize on a quaternion incl. safe_norm's all-close-to-zero rule
+// (brax/math.py:308-345)
+BXG_HD Q4 qnormalize(Q4 q) {
+  bool zero = fabsf(q.w) <= 1e-8f && fabsf(q.x) <= 1e-8f && fabsf(q.y) <= 1e-8f && fabsf(q.z) <= 1e-8f;
+  float n = zero ? 0.f : sqrtf(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+  float d = n + 1e-6f * (n == 0.f ? 1.f : 0.f);
+  return Q4{q.w / d, q.x / d, q.y / d, q.z / d};
+}
+// normalize(quat_rot_axis(axis, angle)) (brax/math.py:133-147)
+BXG_HD Q4 axis_quat(V3 axis, float angle) {
+  float sn, cs;
+  sincosf(angle * 0.5f, &sn, &cs);
+  return qnormalize(Q4{cs, axis.x * sn, axis.y * sn, axis.z * sn});
+}
+// Transform.do(Transform) (brax/base.py:557-562)
+BXG_HD void tf_do(V3 ap, Q4 ar, V3 bp, Q4 br, V3* op, Q4* orr) {
+  *op = ap + rotate(bp, ar);
+  *orr = qmul(ar, br);
+}
+// Inertia.mul(Motion) -> Force (brax/base.py:297-302); im row-major 3x3
+BXG_HD void inertia_mul(V3 ipos, const float* im, float mass, V3 mang, V3 mvel, V3* fang, V3* fvel) {
+  V3 c1 = cross(ipos, mvel), c2 = cross(ipos, mang);
+  fang->x = (im[0] * mang.x + im[1] * mang.y + im[2] * mang.z) + c1.x;
+  fang->y = (im[3] * mang.x + im[4] * mang.y + im[5] * mang.z) + c1.y;
+  fang->z = (im[6] * mang.x + im[7] * mang.y + im[8] * mang.z) + c1.z;
+  *fvel = mvel * mass - c2;
+}
+
+struct Ctx {
+  const Dims* D;
+  const float* mf;  // model blob viewed as float
+  const int* mi;    // model blob viewed as int32
+  float* s;         // this env's slab
+};
+
+struct Stats { int pg_iters, pg_trials, ns_accepts, ns_cold; };
+
+// constraint._imp_aref (brax/generalized/constraint.py:29-65)
+BXG_HD void imp_aref(const float* prm, float pos, float vel, float* imp_out, float* aref_out) {
+  float timeconst = prm[0], dampratio = prm[1], dmin = prm[2], dmax = prm[3], width = prm[4], mid = prm[5], power = prm[6];
+  float imp_x = fabsf(pos) / width;
+  float imp_a = (1.0f / powf(mid, power - 1.f)) * powf(imp_x, power);
+  float imp_b = 1.f - (1.0f / powf(1.f - mid, power - 1.f)) * powf(1.f - imp_x, power);
+  float imp_y = imp_x < mid ? imp_a : imp_b;
+  float imp = dmin + imp_y * (dmax - dmin);
+  imp = fmaxf(dmin, fminf(imp, dmax));
+  if (imp_x > 1.0f) imp = dmax;
+  float b = 2.f / (dmax * timeconst);
+  float k = 1.f / (dmax * dmax * timeconst * timeconst * dampratio * dampratio);
+  if (dampratio <= 0.f) b = -dampratio / dmax;
+  if (timeconst <= 0.f) k = -timeconst / (dmax * dmax);
+  *imp_out = imp;
+  *aref_out = -b * vel - k * imp * pos;
+}
+
+// ------------------------------------------------ forces: tau, passive, RNE
+template <class X>
+BXG_HD void dyn_forces(X& ex, const Ctx& c) {
+  const Dims& D = *c.D; const float* mf = c.mf; const int* mi = c.mi; float* s = c.s;
+  const int L = D.L, nv = D.nv;
+  // actuator.to_tau (lanes <-> dofs)
+  ex.lanes([&](int lane) {
+    for (int d = lane; d < nv; d += X::G) {
+      float tau = 0.f;
+      for (int k = mi[D.m_dof_act_start + d]; k < mi[D.m_dof_act_start + d + 1]; ++k) {
+        int a = mi[D.m_dof_act_list + k];
+        float qv = s[D.s_q + mi[D.m_act_qid + a]], qdv = s[D.s_qd + mi[D.m_act_did + a]];
+        float ctrl = fmaxf(mf[D.m_act_clo + a], fminf(s[D.s_act + a], mf[D.m_act_chi + a]));
+        float gear = mf[D.m_act_gear + a];
+        float bias = gear * (qv * mf[D.m_act_bq + a] + qdv * mf[D.m_act_bqd + a]);
+        float f = mf[D.m_act_gain + a] * ctrl + bias;
+        f = fmaxf(mf[D.m_act_flo + a], fminf(f, mf[D.m_act_fhi + a]));
+        tau += f * gear;
+      }
+      s[D.s_tau + d] = tau;
+    }
+  });
+  // RNE forward scan: cdd, then cfrc_flat (lanes <-> links, one tree level at a time)
+  for (int lvl = 0; lvl <= D.max_depth; ++lvl) {
+    ex.lanes([&](int l) {
+      if (l >= L || mi[D.m_link_depth + l] != lvl) return;
+      int p = mi[D.m_link_parent + l], da = mi[D.m_link_dadr + l], nd = mi[D.m_link_ndof + l];
+      nd = nd == 0 ? 6 : nd;
+      V3 ca = p >= 0 ? ld3(s + D.s_t_ang + 3 * p) : V3{0.f, 0.f, 0.f};
+      V3 cv = p >= 0 ? ld3(s + D.s_t_vel + 3 * p) : V3{-D.gx, -D.gy, -D.gz};
+      for (int k = 0; k < nd; ++k) {
+        float qd = s[D.s_qd + da + k];
+        ca = ca + ld3(s + D.s_cdofd_ang + 3 * (da + k)) * qd;
+        cv = cv + ld3(s + D.s_cdofd_vel + 3 * (da + k)) * qd;
+      }
+      st3(s + D.s_t_ang + 3 * l, ca); st3(s + D.s_t_vel + 3 * l, cv);
+      // cfrc = cinr.mul(cdd) + cd.cross(cinr.mul(cd))
+      V3 ip = ld3(s + D.s_cinr_pos + 3 * l); const float* im = s + D.s_cinr_i + 9 * l; float mass = s[D.s_cinr_mass + l];
+      V3 cda = ld3(s + D.s_cd_ang + 3 * l), cdv = ld3(s + D.s_cd_vel + 3 * l);
+      V3 fa, fv, ga, gv;
+      inertia_mul(ip, im, mass, ca, cv, &fa, &fv);
+      inertia_mul(ip, im, mass, cda, cdv, &ga, &gv);
+      V3 c1 = cross(cda, gv), c2 = cross(cda, ga), c3 = cross(cdv, gv);
+      st3(s + D.s_f_vel + 3 * l, fv + c1);
+      st3(s + D.s_f_ang + 3 * l, fa + (c2 + c3));
+    });
+  }
+  // RNE backward scan: accumulate children (descending index order)
+  for (int lvl = D.max_depth - 1; lvl >= 0; --lvl) {
+    ex.lanes([&](int l) {
+      if (l >= L || mi[D.m_link_depth + l] != lvl) return;
+      V3 fa = ld3(s + D.s_f_ang + 3 * l), fv = ld3(s + D.s_f_vel + 3 * l);
+      for (int k = mi[D.m_child_start + l]; k < mi[D.m_child_start + l + 1]; ++k) {
+        int ch = mi[D.m_child_list + k];
+        fa = fa + ld3(s + D.s_f_ang + 3 * ch); fv = fv + ld3(s + D.s_f_vel + 3 * ch);
+      }
+      st3(s + D.s_f_ang + 3 * l, fa); st3(s + D.s_f_vel + 3 * l, fv);
+    });
+  }
+  // qf_smooth = passive - bias + tau (lanes <-> dofs)
+  ex.lanes([&](int lane) {
+    for (int d = lane; d < nv; d += X::G) {
+      int l = mi[D.m_dof_link + d], qi = mi[D.m_dof_qidx + d];
+      float bias = dot(ld3(s + D.s_cdof_vel + 3 * d), ld3(s + D.s_f_vel + 3 * l)) +
+                   dot(ld3(s + D.s_cdof_ang + 3 * d), ld3(s + D.s_f_ang + 3 * l));
+      float qd = s[D.s_qd + d];
+      float passive = qi < 0 ? 0.f : -s[D.s_q + qi] * mf[D.m_stiff + d];
+      passive = passive - mf[D.m_damp + d] * qd;
+      s[D.s_qfs + d] = (passive - bias) + s[D.s_tau + d];
+    }
+  });
+}
+
+// --------------------------------------- constraint.force + projected gradient
+template <class X>
+BXG_HD void con_force(X& ex, const Ctx& c, Stats* st) {
+  const Dims& D = *c.D; float* s = c.s;
+  const int nv = D.nv, nc = D.nc, nvp = D.nvp, ncp = D.ncp;
+  if (nc == 0) {
+    ex.lanes([&](int lane) { for (int d = lane; d < nv; d += X::G) s[D.s_qfc + d] = 0.f; });
+    return;
+  }
+  float* J = s + D.s_J; float* Mi = s + D.s_Minv;
+  float* JM = s + D.s_scr; float* A = s + D.s_scr + nc * nvp;
+  float* b = s + D.s_b; float* x = s + D.s_px; float* y = s + D.s_py; float* g = s + D.s_pg;
+  float* res = s + D.s_pres; float* xn = s + D.s_pxn;
+  // A = J Minv J^T + diag, b = J Minv qf_smooth - aref   (lanes <-> rows)
+  ex.lanes([&](int lane) {
+    for (int i = lane; i < nc; i += X::G) {
+      for (int j = 0; j < nv; ++j) {
+        float acc = 0.f;
+        for (int k = 0; k < nv; ++k) acc += J[i * nvp + k] * Mi[k * nvp + j];
+        JM[i * nvp + j] = acc;
+      }
+      for (int j = 0; j < nc; ++j) {
+        float acc = 0.f;
+        for (int k = 0; k < nv; ++k) acc += JM[i * nvp + k] * J[j * nvp + k];
+        A[i * ncp + j] = acc + (i == j ? s[D.s_diag + i] : 0.f);
+      }
+      float acc = 0.f;
+      for (int k = 0; k < nv; ++k) acc += JM[i * nvp + k] * s[D.s_qfs + k];
+      b[i] = acc - s[D.s_aref + i];
+      x[i] = 0.f; y[i] = 0.f;
+    }
+  });
+  float t = 1.f, stepsize = 1.f, error = INFINITY;
+  const float tol = 1e-3f, eps = 1.1920929e-07f;
+  int it = 0;
+  while (it < D.solver_iterations && (it == 0 || error > tol)) {
+    ex.lanes([&](int lane) {
+      for (int i = lane; i < nc; i += X::G) {
+        float acc = 0.f;
+        for (int j = 0; j < nc; ++j) acc += A[i * ncp + j] * y[j];
+        res[i] = acc + b[i];
+      }
+    });
+    float fy = 0.f;
+    for (int i = 0; i < nc; ++i) fy += 0.5f * (res[i] * res[i]);
+    ex.lanes([&](int lane) {
+      for (int j = lane; j < nc; j += X::G) {
+        float acc = 0.f;
+        for (int i = 0; i < nc; ++i) acc += A[i * ncp + j] * res[i];
+        g[j] = acc;
+      }
+    });
+    float sz = stepsize;
+    for (int ls = 0;; ++ls) {
+      ex.lanes([&](int lane) { for (int i = lane; i < nc; i += X::G) xn[i] = fmaxf(y[i] - sz * g[i], 0.f); });
+      ex.lanes([&](int lane) {
+        for (int i = lane; i < nc; i += X::G) {
+          float acc = 0.f;
+          for (int j = 0; j < nc; ++j) acc += A[i * ncp + j] * xn[j];
+          res[i] = acc + b[i];
+        }
+      });
+      float sqdist = 0.f, vd = 0.f, fn = 0.f;
+      for (int i = 0; i < nc; ++i) { float dlt = xn[i] - y[i]; sqdist += dlt * dlt; }
+      for (int i = 0; i < nc; ++i) { float dlt = xn[i] - y[i]; vd += dlt * g[i]; }
+      for (int i = 0; i < nc; ++i) fn += 0.5f * (res[i] * res[i]);
+      st->pg_trials++;
+      float fun_decrease = sz * (fn - fy);
+      float condition = sz * vd + 0.5f * sqdist;
+      if (!(fun_decrease > condition + eps) || ls >= D.solver_maxls) break;
+      sz = sz * 0.5f;
+    }
+    stepsize = sz <= 1e-6f ? 1.f : sz / 0.5f;
+    float tn = 0.5f * (1.f + sqrtf(1.f + 4.f * (t * t)));
+    float mom = (t - 1.f) / tn;
+    // res now holds A x+ + b: reuse it for the error gradient
+    ex.lanes([&](int lane) {
+      for (int j = lane; j < nc; j += X::G) {
+        float acc = 0.f;
+        for (int i = 0; i < nc; ++i) acc += A[i * ncp + j] * res[i];
+        g[j] = acc;
+        float dlt = xn[j] - x[j];
+        y[j] = xn[j] + mom * dlt;
+        x[j] = xn[j];
+      }
+    });
+    float err2 = 0.f;
+    for (int i = 0; i < nc; ++i) { float dlt = fmaxf(xn[i] - g[i], 0.f) - xn[i]; err2 += dlt * dlt; }
+    error = sqrtf(err2);
+    t = tn;
+    ++it;
+    st->pg_iters++;
+    ex.sync();
+  }
+  // qf_constraint = J^T x
+  ex.lanes([&](int lane) {
+    for (int j = lane; j < nv; j += X::G) {
+      float acc = 0.f;
+      for (int i = 0; i < nc; ++i) acc += J[i * nvp + j] * x[i];
+      s[D.s_qfc + j] = acc;
+    }
+  });
+}
+
+// SPD inverse by Cholesky: dst = src^-1, Lm is an nv x nvp scratch.
+// Used by init (mass.py:103-104), integrate's implicit-damping branch
+// (integrator.py:58-60) and BXG_MINV_CHOLESKY.
+template <class X>
+BXG_HD void spd_inverse(X& ex, const Ctx& c, const float* src, float* dst, float* Lm, const float* add_diag, float diag_scale) {
+  const Dims& D = *c.D;
+  const int n = D.nv, nvp = D.nvp;
+  for (int j = 0; j < n; ++j) {
+    ex.lanes([&](int lane) {
+      float sd = src[j * nvp + j] + (add_diag ? add_diag[j] * diag_scale : 0.f);
+      for (int k = 0; k < j; ++k) sd -= Lm[j * nvp + k] * Lm[j * nvp + k];
+      float dg = sqrtf(sd);
+      for (int i = j + lane; i < n; i += X::G) {
+        if (i == j) { Lm[j * nvp + j] = dg; continue; }
+        float tt = src[i * nvp + j];
+        for (int k = 0; k < j; ++k) tt -= Lm[i * nvp + k] * Lm[j * nvp + k];
+        Lm[i * nvp + j] = tt / dg;
+      }
+    });
+  }
+  ex.lanes([&](int lane) {
+    for (int col = lane; col < n; col += X::G) {
+      for (int i = 0; i < n; ++i) {
+        float tt = i == col ? 1.f : 0.f;
+        for (int k = 0; k < i; ++k) tt -= Lm[i * nvp + k] * dst[k * nvp + col];
+        dst[i * nvp + col] = tt / Lm[i * nvp + i];
+      }
+      for (int i = n - 1; i >= 0; --i) {
+        float tt = dst[i * nvp + col];
+        for (int k = i + 1; k < n; ++k) tt -= Lm[k * nvp + i] * dst[k * nvp + col];
+        dst[i * nvp + col] = tt / Lm[i * nvp + i];
+      }
+    }
+  });
+}
+
+// ------------------------------------------------------ integrator.integrate
+template <class X>
+BXG_HD void integrate(X& ex, const Ctx& c) {
+  const Dims& D = *c.D; const float* mf = c.mf; const int* mi = c.mi; float* s = c.s;
+  const int nv = D.nv, nvp = D.nvp, L = D.L;
+  const float dt = D.dt;
+  const float* Mi = s + D.s_Minv;
+  if (D.ns_iters == 0) {
+    float* tmp = s + D.s_scr;  // dst
+    spd_inverse(ex, c, s + D.s_M, tmp, s + D.s_scr + nv * nvp, mf + D.m_damp, dt);
+    Mi = tmp;
+  }
+  ex.lanes([&](int lane) {
+    for (int i = lane; i < nv; i += X::G) {
+      float acc = 0.f;
+      for (int j = 0; j < nv; ++j) acc += Mi[i * nvp + j] * (s[D.s_qfs + j] + s[D.s_qfc + j]);
+      s[D.s_qdd + i] = acc;
+    }
+  });
+  ex.lanes([&](int lane) {
+    for (int i = lane; i < nv; i += X::G) s[D.s_qd + i] = s[D.s_qd + i] + s[D.s_qdd + i] * dt;
+  });
+  ex.lanes([&](int l) {
+    if (l >= L) return;
+    int qa = mi[D.m_link_qadr + l], da = mi[D.m_link_dadr + l], nd = mi[D.m_link_ndof + l];
+    if (nd == 0) {
+      Q4 rot = ld4(s + D.s_q + qa + 3);
+      V3 ang = ld3(s + D.s_qd + da + 3);
+      float ang_norm = sqrtf(ang.x * ang.x + ang.y * ang.y + ang.z * ang.z) + 1e-8f;
+      V3 axis{ang.x / ang_norm, ang.y / ang_norm, ang.z / ang_norm};
+      float sn, cs;
+      sincosf((dt * ang_norm) * 0.5f, &sn, &cs);
+      Q4 nr = qmul(rot, Q4{cs, axis.x * sn, axis.y * sn, axis.z * sn});
+      float n = sqrtf(nr.w * nr.w + nr.x * nr.x + nr.y * nr.y + nr.z * nr.z);
+      st4(s + D.s_q + qa + 3, Q4{nr.w / n, nr.x / n, nr.y / n, nr.z / n});
+      for (int i = 0; i < 3; ++i) s[D.s_q + qa + i] = s[D.s_q + qa + i] + s[D.s_qd + da + i] * dt;
+    } else {
+      for (int k = 0; k < nd; ++k) s[D.s_q + qa + k] = s[D.s_q + qa + k] + s[D.s_qd + da + k] * dt;
+    }
+  });
+}
+
+// -------------------------------------------------------- kinematics.forward
+template <class X>
+BXG_HD void kinematics(X& ex, const Ctx& c) {
+  const Dims& D = *c.D; const float* mf = c.mf; const int* mi = c.mi; float* s = c.s;
+  const int L = D.L;
+  float* jpos = s + D.s_f_ang; float* jrot = s + D.s_j_rot; float* jdang = s + D.s_t_ang; float* jdvel = s + D.s_t_vel;
+  ex.lanes([&](int l) {
+    if (l >= L) return;
+    int qa = mi[D.m_link_qadr + l], da = mi[D.m_link_dadr + l], nd = mi[D.m_link_ndof + l];
+    V3 p, a, v; Q4 r;
+    if (nd == 0) {
+      p = ld3(s + D.s_q + qa); r = ld4(s + D.s_q + qa + 3);
+      v = ld3(s + D.s_qd + da); a = ld3(s + D.s_qd + da + 3);
+    } else {
+      p = V3{0, 0, 0}; a = p; v = p; r = Q4{1, 0, 0, 0};
+      for (int k = 0; k < nd; ++k) {
+        int d = da + k; float qk = s[D.s_q + qa + k], qdk = s[D.s_qd + d];
+        V3 mang = ld3(mf + D.m_dof_ang + 3 * d), mvel = ld3(mf + D.m_dof_vel + 3 * d);
+        Q4 sr = axis_quat(mang, qk);
+        V3 sp = mvel * qk, sa = mang * qdk, sv = mvel * qdk;
+        if (k == 0) { p = sp; r = sr; a = sa; v = sv; }
+        else {
+          V3 np_; Q4 nr;
+          tf_do(p, r, sp, sr, &np_, &nr);
+          a = a + rotate(sa, sr);
+          v = v + rotate(sv + cross(sp, sa), sr);
+          p = np_; r = nr;
+        }
+      }
+    }
+    V3 jp = ld3(mf + D.m_joint_pos + 3 * l);
+    V3 anc = rotate(jp, r);
+    p = (p + jp) - anc;
+    V3 tp; Q4 tr;
+    tf_do(ld3(mf + D.m_tf_pos + 3 * l), ld4(mf + D.m_tf_rot + 4 * l), p, r, &tp, &tr);
+    st3(jpos + 3 * l, tp); st4(jrot + 4 * l, tr); st3(jdang + 3 * l, a); st3(jdvel + 3 * l, v);
+  });
+  for (int lvl = 0; lvl <= D.max_depth; ++lvl) {
+    ex.lanes([&](int l) {
+      if (l >= L || mi[D.m_link_depth + l] != lvl) return;
+      int p = mi[D.m_link_parent + l];
+      V3 jp = ld3(jpos + 3 * l), ja = ld3(jdang + 3 * l), jv = ld3(jdvel + 3 * l); Q4 jr = ld4(jrot + 4 * l);
+      if (p < 0) {
+        st3(s + D.s_x_pos + 3 * l, jp); st4(s + D.s_x_rot + 4 * l, jr);
+        st3(s + D.s_xd_ang + 3 * l, rotate(ja, jr)); st3(s + D.s_xd_vel + 3 * l, jv);
+      } else {
+        V3 pp = ld3(s + D.s_x_pos + 3 * p); Q4 pr = ld4(s + D.s_x_rot + 4 * p);
+        V3 pa = ld3(s + D.s_xd_ang + 3 * p), pv = ld3(s + D.s_xd_vel + 3 * p);
+        V3 xp; Q4 xr;
+        tf_do(pp, pr, jp, jr, &xp, &xr);
+        V3 vel = (pv + cross(pa, xp - pp)) + rotate(jv, pr);
+        V3 ang = pa + rotate(ja, xr);
+        st3(s + D.s_x_pos + 3 * l, xp); st4(s + D.s_x_rot + 4 * l, xr);
+        st3(s + D.s_xd_ang + 3 * l, ang); st3(s + D.s_xd_vel + 3 * l, vel);
+      }
+    });
+  }
+  ex.lanes([&](int l) {
+    if (l >= L) return;
+    st4(s + D.s_x_rot + 4 * l, qnormalize(ld4(s + D.s_x_rot + 4 * l)));
+  });
+}
+
+// ---------------------------------------------------- dynamics.transform_com
+template <class X>
+BXG_HD void transform_com(X& ex, const Ctx& c) {
+  const Dims& D = *c.D; const float* mf = c.mf; const int* mi = c.mi; float* s = c.s;
+  const int L = D.L;
+  float* xi_pos = s + D.s_t_ang;
+  ex.lanes([&](int l) {
+    if (l >= L) return;
+    V3 xp; Q4 xr;
+    tf_do(ld3(s + D.s_x_pos + 3 * l), ld4(s + D.s_x_rot + 4 * l), ld3(mf + D.m_in_pos + 3 * l), ld4(mf + D.m_in_rot + 4 * l), &xp, &xr);
+    st3(xi_pos + 3 * l, xp); st4(s + D.s_cinr_rot + 4 * l, xr);
+  });
+  ex.lanes([&](int l) {
+    if (l >= L) return;
+    // root_com: mass-weighted mean over the links of this tree (index order)
+    int root = mi[D.m_link_root + l];
+    V3 msum{0, 0, 0}; float mtot = 0.f;
+    for (int k = 0; k < L; ++k) {
+      if (mi[D.m_link_root + k] != root) continue;
+      float mk = mf[D.m_in_mass + k];
+      msum = msum + ld3(xi_pos + 3 * k) * mk; mtot += mk;
+    }
+    V3 com{msum.x / mtot, msum.y / mtot, msum.z / mtot};
+    st3(s + D.s_root_com + 3 * l, com);
+    // cinr = Transform(x_i.pos - com, x_i.rot).do(inertia)  (base.py:588-594)
+    float mass = mf[D.m_in_mass + l];
+    V3 p = ld3(xi_pos + 3 * l) - com;
+    Q4 q = ld4(s + D.s_cinr_rot + 4 * l);
+    float R[9];
+    {
+      float dq = q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z, sc = 2.f / dq;
+      float xs = q.x * sc, ys = q.y * sc, zs = q.z * sc;
+      float wx = q.w * xs, wy = q.w * ys, wz = q.w * zs, xx = q.x * xs, xy = q.x * ys, xz = q.x * zs;
+      float yy = q.y * ys, yz = q.y * zs, zz = q.z * zs;
+      R[0] = 1.f - (yy + zz); R[1] = xy - wz; R[2] = xz + wy;
+      R[3] = xy + wz; R[4] = 1.f - (xx + zz); R[5] = yz - wx;
+      R[6] = xz - wy; R[7] = yz + wx; R[8] = 1.f - (xx + yy);
+    }
+    const float* I0 = mf + D.m_in_i + 9 * l;
+    float T[9];
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) {
+      float acc = 0.f;
+      for (int k = 0; k < 3; ++k) acc += R[3 * a + k] * I0[3 * k + b];
+      T[3 * a + b] = acc;
+    }
+    float h[9] = {0.f, -p.z, p.y, p.z, 0.f, -p.x, -p.y, p.x, 0.f};
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) {
+      float acc = 0.f, hh = 0.f;
+      for (int k = 0; k < 3; ++k) acc += T[3 * a + k] * R[3 * b + k];
+      for (int k = 0; k < 3; ++k) hh += h[3 * a + k] * h[3 * b + k];
+      s[D.s_cinr_i + 9 * l + 3 * a + b] = acc + hh * mass;
+    }
+    st3(s + D.s_cinr_pos + 3 * l, p * mass);
+    s[D.s_cinr_mass + l] = mass;
+    // joint frame j = parent.do(link.transform).do(link.joint)  (dynamics.py:47-52)
+    int nd = mi[D.m_link_ndof + l], qa = mi[D.m_link_qadr + l], da = mi[D.m_link_dadr + l];
+    int pi = nd == 0 ? l : mi[D.m_link_parent + l];
+    V3 pp = pi >= 0 ? ld3(s + D.s_x_pos + 3 * pi) : V3{0, 0, 0};
+    Q4 pr = pi >= 0 ? ld4(s + D.s_x_rot + 4 * pi) : Q4{1, 0, 0, 0};
+    V3 tp, jpv; Q4 tr, jrq;
+    tf_do(pp, pr, ld3(mf + D.m_tf_pos + 3 * l), ld4(mf + D.m_tf_rot + 4 * l), &tp, &tr);
+    tf_do(tp, tr, ld3(mf + D.m_joint_pos + 3 * l), Q4{1, 0, 0, 0}, &jpv, &jrq);
+    V3 off = com - jpv;
+    // cdof (dynamics.py:55-89)
+    if (nd == 0) {
+      for (int k = 0; k < 6; ++k) {
+        V3 a = rotate(ld3(mf + D.m_dof_ang + 3 * (da + k)), jrq);
+        V3 v = ld3(mf + D.m_dof_vel + 3 * (da + k)) - cross(off, a);
+        st3(s + D.s_cdof_ang + 3 * (da + k), a); st3(s + D.s_cdof_vel + 3 * (da + k), v);
+      }
+    } else {
+      V3 lp{0, 0, 0}; Q4 lr{1, 0, 0, 0};
+      for (int k = 0; k < nd; ++k) {
+        int d = da + k;
+        V3 mang = ld3(mf + D.m_dof_ang + 3 * d), mvel = ld3(mf + D.m_dof_vel + 3 * d);
+        V3 a = rotate(mang, lr);
+        V3 v = rotate(mvel, lr) + cross(lp, a);
+        float qk = s[D.s_q + qa + k];
+        V3 np_; Q4 nr;
+        tf_do(lp, lr, mvel * qk, axis_quat(mang, qk), &np_, &nr);
+        lp = np_; lr = nr;
+        V3 aw = rotate(a, jrq);
+        st3(s + D.s_cdof_ang + 3 * d, aw); st3(s + D.s_cdof_vel + 3 * d, v - cross(off, aw));
+      }
+    }
+  });
+  // cd forward scan (dynamics.py:92-103)
+  for (int lvl = 0; lvl <= D.max_depth; ++lvl) {
+    ex.lanes([&](int l) {
+      if (l >= L || mi[D.m_link_depth + l] != lvl) return;
+      int p = mi[D.m_link_parent + l], da = mi[D.m_link_dadr + l], nd = mi[D.m_link_ndof + l];
+      nd = nd == 0 ? 6 : nd;
+      V3 ca = p >= 0 ? ld3(s + D.s_cd_ang + 3 * p) : V3{0, 0, 0};
+      V3 cv = p >= 0 ? ld3(s + D.s_cd_vel + 3 * p) : V3{0, 0, 0};
+      for (int k = 0; k < nd; ++k) {
+        float qd = s[D.s_qd + da + k];
+        ca = ca + ld3(s + D.s_cdof_ang + 3 * (da + k)) * qd;
+        cv = cv + ld3(s + D.s_cdof_vel + 3 * (da + k)) * qd;
+      }
+      st3(s + D.s_cd_ang + 3 * l, ca); st3(s + D.s_cd_vel + 3 * l, cv);
+    });
+  }
+  // cdofd (dynamics.py:106-130)
+  ex.lanes([&](int l) {
+    if (l >= L) return;
+    int p = mi[D.m_link_parent + l], da = mi[D.m_link_dadr + l], nd = mi[D.m_link_ndof + l];
+    if (nd == 0) {
+      V3 ca{0, 0, 0}, cv{0, 0, 0};
+      for (int k = 0; k < 3; ++k) {
+        float qd = s[D.s_qd + da + k];
+        ca = ca + ld3(s + D.s_cdof_ang + 3 * (da + k)) * qd;
+        cv = cv + ld3(s + D.s_cdof_vel + 3 * (da + k)) * qd;
+      }
+      for (int k = 0; k < 6; ++k) {
+        V3 da_ = ld3(s + D.s_cdof_ang + 3 * (da + k)), dv_ = ld3(s + D.s_cdof_vel + 3 * (da + k));
+        V3 vel = cross(ca, dv_) + cross(cv, da_), ang = cross(ca, da_);
+        if (k < 3) { vel = V3{0, 0, 0}; ang = vel; }
+        st3(s + D.s_cdofd_ang + 3 * (da + k), ang); st3(s + D.s_cdofd_vel + 3 * (da + k), vel);
+      }
+    } else {
+      V3 ca = p >= 0 ? ld3(s + D.s_cd_ang + 3 * p) : V3{0, 0, 0};
+      V3 cv = p >= 0 ? ld3(s + D.s_cd_vel + 3 * p) : V3{0, 0, 0};
+      for (int k = 0; k < nd; ++k) {
+        int d = da + k;
+        V3 da_ = ld3(s + D.s_cdof_ang + 3 * d), dv_ = ld3(s + D.s_cdof_vel + 3 * d);
+        st3(s + D.s_cdofd_vel + 3 * d, cross(ca, dv_) + cross(cv, da_));
+        st3(s + D.s_cdofd_ang + 3 * d, cross(ca, da_));
+        float qd = s[D.s_qd + d];
+        ca = ca + da_ * qd; cv = cv + dv_ * qd;
+      }
+    }
+  });
+}
+
+// --------------------------------------------------------------- mass.matrix
+template <class X>
+BXG_HD void mass_matrix(X& ex, const Ctx& c) {
+  const Dims& D = *c.D; const float* mf = c.mf; const int* mi = c.mi; float* s = c.s;
+  const int L = D.L, nv = D.nv, nvp = D.nvp;
+  float* M = s + D.s_M;
+  ex.lanes([&](int lane) {
+    if (lane < L) {
+      for (int i = 0; i < 3; ++i) s[D.s_crb_pos + 3 * lane + i] = s[D.s_cinr_pos + 3 * lane + i];
+      for (int i = 0; i < 9; ++i) s[D.s_crb_i + 9 * lane + i] = s[D.s_cinr_i + 9 * lane + i];
+      s[D.s_crb_mass + lane] = s[D.s_cinr_mass + lane];
+    }
+    for (int i = lane; i < nv * nvp; i += X::G) M[i] = 0.f;
+  });
+  for (int lvl = D.max_depth - 1; lvl >= 0; --lvl) {
+    ex.lanes([&](int l) {
+      if (l >= L || mi[D.m_link_depth + l] != lvl) return;
+      for (int k = mi[D.m_child_start + l]; k < mi[D.m_child_start + l + 1]; ++k) {
+        int ch = mi[D.m_child_list + k];
+        for (int i = 0; i < 3; ++i) s[D.s_crb_pos + 3 * l + i] += s[D.s_crb_pos + 3 * ch + i];
+        for (int i = 0; i < 9; ++i) s[D.s_crb_i + 9 * l + i] += s[D.s_crb_i + 9 * ch + i];
+        s[D.s_crb_mass + l] += s[D.s_crb_mass + ch];
+      }
+    });
+  }
+  ex.lanes([&](int lane) {
+    for (int i = lane; i < nv; i += X::G) {
+      int li = mi[D.m_dof_link + i];
+      V3 fa, fv;
+      inertia_mul(ld3(s + D.s_crb_pos + 3 * li), s + D.s_crb_i + 9 * li, s[D.s_crb_mass + li],
+                  ld3(s + D.s_cdof_ang + 3 * i), ld3(s + D.s_cdof_vel + 3 * i), &fa, &fv);
+      uint32_t lo = (uint32_t)mi[D.m_dof_anc_lo + i], hi = (uint32_t)mi[D.m_dof_anc_hi + i];
+      for (int j = 0; j <= i; ++j) {
+        uint32_t bit = j < 32 ? (lo >> j) & 1u : (hi >> (j - 32)) & 1u;
+        if (!bit) continue;
+        float v = dot(ld3(s + D.s_cdof_vel + 3 * j), fv) + dot(ld3(s + D.s_cdof_ang + 3 * j), fa);
+        if (i == j) v += mf[D.m_arm + i];
+        M[i * nvp + j] = v;
+        M[j * nvp + i] = v;
+      }
+    }
+  });
+}
+
+// ------------------------------------------------------ math.inv_approximate
+template <class X>
+BXG_HD void minv_newton_schulz(X& ex, const Ctx& c, Stats* st) {
+  const Dims& D = *c.D; float* s = c.s;
+  const int n = D.nv, nvp = D.nvp;
+  const float* M = s + D.s_M;
+  float* Xc = s + D.s_Minv;          // current estimate
+  float* Xn = s + D.s_scr;           // candidate
+  float* RB = s + D.s_scr + n * nvp;  // residual r, then I + r in place
+  typename X::LaneF p_sum, p_max;
+  // r0 = I - M X
+  ex.lanes([&](int lane) {
+    float ss = 0.f, mx = 0.f;
+    for (int i = lane; i < n; i += X::G) {
+      for (int j = 0; j < n; ++j) {
+        float acc = 0.f;
+        for (int k = 0; k < n; ++k) acc += M[i * nvp + k] * Xc[k * nvp + j];
+        float r = (i == j ? 1.f : 0.f) - acc;
+        RB[i * nvp + j] = r;
+        ss += r * r; mx = fmaxf(mx, fabsf(r));
+      }
+    }
+    p_sum(lane) = ss; p_max(lane) = mx;
+  });
+  float ss = ex.sum(p_sum), mx = ex.max(p_max);
+  float nrm0 = mx <= 1e-8f ? 0.f : sqrtf(ss);
+  if (nrm0 > 1.f) {
+    ex.lanes([&](int lane) {
+      float tr = 0.f;
+      for (int i = lane; i < n; i += X::G) for (int k = 0; k < n; ++k) tr += M[i * nvp + k] * M[i * nvp + k];
+      p_sum(lane) = tr;
+    });
+    float tr = ex.sum(p_sum);
+    ex.lanes([&](int lane) {
+      for (int i = lane; i < n; i += X::G) for (int j = 0; j < n; ++j) Xc[i * nvp + j] = 0.5f * M[j * nvp + i] / tr;
+    });
+    st->ns_cold++;
+  }
+  float err = 1.f;
+  for (int it = 0; it < D.ns_iters; ++it) {
+    // RB <- I + r ; Xn = Xc (I + r)
+    ex.lanes([&](int lane) { for (int i = lane; i < n; i += X::G) RB[i * nvp + i] = 1.f + RB[i * nvp + i]; });
+    ex.lanes([&](int lane) {
+      for (int i = lane; i < n; i += X::G) {
+        for (int j = 0; j < n; ++j) {
+          float acc = 0.f;
+          for (int k = 0; k < n; ++k) acc += Xc[i * nvp + k] * RB[k * nvp + j];
+          Xn[i * nvp + j] = acc;
+        }
+      }
+    });
+    // r' = I - M Xn
+    ex.lanes([&](int lane) {
+      float s2 = 0.f, m2 = 0.f;
+      for (int i = lane; i < n; i += X::G) {
+        for (int j = 0; j < n; ++j) {
+          float acc = 0.f;
+          for (int k = 0; k < n; ++k) acc += M[i * nvp + k] * Xn[k * nvp + j];
+          float r = (i == j ? 1.f : 0.f) - acc;
+          RB[i * nvp + j] = r;
+          s2 += r * r; m2 = fmaxf(m2, fabsf(r));
+        }
+      }
+      p_sum(lane) = s2; p_max(lane) = m2;
+    });
+    float s2 = ex.sum(p_sum), m2 = ex.max(p_max);
+    float err_next = m2 <= 1e-8f ? 0.f : sqrtf(s2);
+    if (err_next < err) {
+      ex.lanes([&](int lane) { for (int i = lane; i < n * nvp; i += X::G) Xc[i] = Xn[i]; });
+      st->ns_accepts++;
+    }
+    err = err_next;
+  }
+}
+
+// ------------------------------------------------------- constraint.jacobian
+template <class X>
+BXG_HD void con_jacobian(X& ex, const Ctx& c) {
+  const Dims& D = *c.D; const float* mf = c.mf; const int* mi = c.mi; float* s = c.s;
+  const int nv = D.nv, nvp = D.nvp;
+  float* J = s + D.s_J;
+  for (int cc = 0; cc < D.ncon; ++cc) {
+    int lb = mi[D.m_con_lb + cc];
+    // contact.get, plane-sphere (contact.py:28-67 + mjx): every lane redundantly
+    V3 n = ld3(mf + D.m_con_frame + 9 * cc), t1 = ld3(mf + D.m_con_frame + 9 * cc + 3), t2 = ld3(mf + D.m_con_frame + 9 * cc + 6);
+    float rad = mf[D.m_con_rad + cc], mu = mf[D.m_con_mu + cc];
+    V3 sp = ld3(s + D.s_x_pos + 3 * lb) + rotate(ld3(mf + D.m_con_spos + 3 * cc), ld4(s + D.s_x_rot + 4 * lb));
+    float dist = dot(sp - ld3(mf + D.m_con_ppos + 3 * cc), n) - rad;
+    V3 pos = sp - n * (rad + 0.5f * dist);
+    bool active = dist < 0.f;
+    V3 off = pos - ld3(s + D.s_root_com + 3 * lb);
+    uint32_t lo = (uint32_t)mi[D.m_con_anc_lo + cc], hi = (uint32_t)mi[D.m_con_anc_hi + cc];
+    V3 dir[4];
+    for (int k = 0; k < 4; ++k) {
+      V3 tt = k < 2 ? t1 : t2; float f = (k & 1) ? mu : -mu;
+      dir[k] = V3{(-tt.x) * f + n.x, (-tt.y) * f + n.y, (-tt.z) * f + n.z};
+    }
+    ex.lanes([&](int lane) {
+      if (lane == 0) s[D.s_dist + cc] = dist;
+      for (int d = lane; d < nv; d += X::G) {
+        uint32_t bit = d < 32 ? (lo >> d) & 1u : (hi >> (d - 32)) & 1u;
+        float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+        if (active && bit) {
+          V3 a = ld3(s + D.s_cdof_ang + 3 * d), v = ld3(s + D.s_cdof_vel + 3 * d);
+          V3 df = v - cross(off, a);
+          r0 = dot(df, dir[0]); r1 = dot(df, dir[1]); r2 = dot(df, dir[2]); r3 = dot(df, dir[3]);
+        }
+        J[(4 * cc + 0) * nvp + d] = r0; J[(4 * cc + 1) * nvp + d] = r1;
+        J[(4 * cc + 2) * nvp + d] = r2; J[(4 * cc + 3) * nvp + d] = r3;
+      }
+    });
+    ex.lanes([&](int lane) {
+      if (lane >= 4) return;
+      int row = 4 * cc + lane;
+      float diag = 0.f, aref = 0.f;
+      if (active) {
+        float vel = 0.f;
+        for (int d = 0; d < nv; ++d) vel += J[row * nvp + d] * s[D.s_qd + d];
+        float imp;
+        imp_aref(mf + D.m_con_sp + 7 * cc, dist, vel, &imp, &aref);
+        float tw = mf[D.m_link_invw + lb];  // link_a is the world: contributes 0
+        diag = (tw + mu * mu * tw) * (2.f * mu * mu * (1.f - imp) / (imp + 1e-8f));
+      }
+      s[D.s_diag + row] = diag; s[D.s_aref + row] = aref;
+    });
+  }
+  if (D.nlim > 0) {
+    ex.lanes([&](int lane) {
+      for (int r = lane; r < D.nlim; r += X::G) {
+        int d = mi[D.m_lim_dof + r], row = 4 * D.ncon + r;
+        float q = s[D.s_q + mi[D.m_dof_qidx + d]];
+        float pos_min = q - mf[D.m_lim_lo + d], pos_max = mf[D.m_lim_hi + d] - q;
+        float pos = fminf(fminf(pos_min, pos_max), 0.f);
+        bool active = pos < 0.f;
+        float side = active ? (pos_min < pos_max ? 1.f : -1.f) : 0.f;
+        float diag = 0.f, aref = 0.f;
+        if (active) {
+          float imp;
+          imp_aref(mf + D.m_dof_sp + 7 * d, pos, side * s[D.s_qd + d], &imp, &aref);
+          diag = mf[D.m_dof_invw + d] * (1.f - imp) / (imp + 1e-8f);
+        }
+        J[row * nvp + d] = side;
+        s[D.s_diag + row] = diag; s[D.s_aref + row] = aref;
+      }
+    });
+  }
+}
+
+// ------------------------------------------------------------------ pipeline
+template <class X>
+BXG_HD void update_position_terms(X& ex, const Ctx& c, Stats* st, bool exact_inverse) {
+  kinematics(ex, c);
+  transform_com(ex, c);
+  mass_matrix(ex, c);
+  if (exact_inverse) spd_inverse(ex, c, c.s + c.D->s_M, c.s + c.D->s_Minv, c.s + c.D->s_scr, nullptr, 0.f);
+  else minv_newton_schulz(ex, c, st);
+  con_jacobian(ex, c);
+}
+
+// pipeline.step (pipeline.py:78-94)
+template <class X>
+BXG_HD void substep(X& ex, const Ctx& c, Stats* st) {
+  dyn_forces(ex, c);
+  con_force(ex, c, st);
+  integrate(ex, c);
+  update_position_terms(ex, c, st, c.D->ns_iters == 0 || c.D->minv_mode == BXG_MINV_CHOLESKY);
+}
+
+// pipeline.init (pipeline.py:51-61); q, qd already in the slab
+template <class X>
+BXG_HD void init_env(X& ex, const Ctx& c, Stats* st) {
+  const Dims& D = *c.D; float* s = c.s;
+  ex.lanes([&](int lane) {
+    for (int i = lane; i < D.nv; i += X::G) { s[D.s_qfs + i] = 0.f; s[D.s_qfc + i] = 0.f; s[D.s_qdd + i] = 0.f; }
+    for (int i = lane; i < (D.nc > 0 ? D.nc : 1) * D.nvp; i += X::G) s[D.s_J + i] = 0.f;
+  });
+  update_position_terms(ex, c, st, true);
+}
+
+// ------------------------------------------------------- global <-> slab I/O
+template <class X, class F>
+BXG_HD void io_vec(X& ex, int n, F f) {
+  ex.lanes([&](int lane) { for (int i = lane; i < n; i += X::G) f(i); });
+}
+
+// Loads the State leaves pipeline.step reads.
+template <class X>
+BXG_HD void load_env(X& ex, const Ctx& c, const BxgState& g, const float* act, int64_t e) {
+  const Dims& D = *c.D; float* s = c.s;
+  const int L = D.L, nv = D.nv, nq = D.nq, nc = D.nc, nvp = D.nvp;
+  ex.lanes([&](int lane) {
+    const int G = X::G;
+    for (int i = lane; i < nq; i += G) s[D.s_q + i] = g.q[e * nq + i];
+    for (int i = lane; i < nv; i += G) s[D.s_qd + i] = g.qd[e * nv + i];
+    for (int i = lane; i < D.nu; i += G) s[D.s_act + i] = act[e * D.nu + i];
+    for (int i = lane; i < L * 3; i += G) {
+      s[D.s_cinr_pos + i] = g.cinr_pos[e * L * 3 + i];
+      s[D.s_cd_ang + i] = g.cd_ang[e * L * 3 + i]; s[D.s_cd_vel + i] = g.cd_vel[e * L * 3 + i];
+    }
+    for (int i = lane; i < L * 9; i += G) s[D.s_cinr_i + i] = g.cinr_i[e * L * 9 + i];
+    for (int i = lane; i < L; i += G) s[D.s_cinr_mass + i] = g.cinr_mass[e * L + i];
+    for (int i = lane; i < nv * 3; i += G) {
+      s[D.s_cdof_ang + i] = g.cdof_ang[e * nv * 3 + i]; s[D.s_cdof_vel + i] = g.cdof_vel[e * nv * 3 + i];
+      s[D.s_cdofd_ang + i] = g.cdofd_ang[e * nv * 3 + i]; s[D.s_cdofd_vel + i] = g.cdofd_vel[e * nv * 3 + i];
+    }
+    for (int i = lane; i < nv * nv; i += G) {
+      int r = i / nv, cc = i - r * nv;
+      s[D.s_Minv + r * nvp + cc] = g.mass_mx_inv[e * nv * nv + i];
+      if (D.ns_iters == 0) s[D.s_M + r * nvp + cc] = g.mass_mx[e * nv * nv + i];
+    }
+    for (int i = lane; i < nc * nv; i += G) {
+      int r = i / nv, cc = i - r * nv;
+      s[D.s_J + r * nvp + cc] = g.con_jac[e * nc * nv + i];
+    }
+    for (int i = lane; i < nc; i += G) { s[D.s_diag + i] = g.con_diag[e * nc + i]; s[D.s_aref + i] = g.con_aref[e * nc + i]; }
+  });
+}
+
+template <class X>
+BXG_HD void load_env_qqd(X& ex, const Ctx& c, const float* q, const float* qd, int64_t e) {
+  const Dims& D = *c.D; float* s = c.s;
+  ex.lanes([&](int lane) {
+    for (int i = lane; i < D.nq; i += X::G) s[D.s_q + i] = q[e * D.nq + i];
+    for (int i = lane; i < D.nv; i += X::G) s[D.s_qd + i] = qd[e * D.nv + i];
+  });
+}
+
+template <class X>
+BXG_HD void store_env(X& ex, const Ctx& c, const BxgState& g, int64_t e, const BxgDiag* dg, const Stats& st) {
+  const Dims& D = *c.D; const float* s = c.s;
+  const int L = D.L, nv = D.nv, nq = D.nq, nc = D.nc, nvp = D.nvp;
+  ex.lanes([&](int lane) {
+    const int G = X::G;
+    for (int i = lane; i < nq; i += G) g.q[e * nq + i] = s[D.s_q + i];
+    for (int i = lane; i < nv; i += G) {
+      g.qd[e * nv + i] = s[D.s_qd + i];
+      g.qf_smooth[e * nv + i] = s[D.s_qfs + i]; g.qf_constraint[e * nv + i] = s[D.s_qfc + i]; g.qdd[e * nv + i] = s[D.s_qdd + i];
+    }
+    for (int i = lane; i < L * 3; i += G) {
+      g.x_pos[e * L * 3 + i] = s[D.s_x_pos + i]; g.xd_ang[e * L * 3 + i] = s[D.s_xd_ang + i]; g.xd_vel[e * L * 3 + i] = s[D.s_xd_vel + i];
+      g.root_com[e * L * 3 + i] = s[D.s_root_com + i]; g.cinr_pos[e * L * 3 + i] = s[D.s_cinr_pos + i];
+      g.cd_ang[e * L * 3 + i] = s[D.s_cd_ang + i]; g.cd_vel[e * L * 3 + i] = s[D.s_cd_vel + i];
+    }
+    for (int i = lane; i < L * 4; i += G) { g.x_rot[e * L * 4 + i] = s[D.s_x_rot + i]; g.cinr_rot[e * L * 4 + i] = s[D.s_cinr_rot + i]; }
+    for (int i = lane; i < L * 9; i += G) g.cinr_i[e * L * 9 + i] = s[D.s_cinr_i + i];
+    for (int i = lane; i < L; i += G) g.cinr_mass[e * L + i] = s[D.s_cinr_mass + i];
+    for (int i = lane; i < nv * 3; i += G) {
+      g.cdof_ang[e * nv * 3 + i] = s[D.s_cdof_ang + i]; g.cdof_vel[e * nv * 3 + i] = s[D.s_cdof_vel + i];
+      g.cdofd_ang[e * nv * 3 + i] = s[D.s_cdofd_ang + i]; g.cdofd_vel[e * nv * 3 + i] = s[D.s_cdofd_vel + i];
+    }
+    for (int i = lane; i < nv * nv; i += G) {
+      int r = i / nv, cc = i - r * nv;
+      g.mass_mx[e * nv * nv + i] = s[D.s_M + r * nvp + cc];
+      g.mass_mx_inv[e * nv * nv + i] = s[D.s_Minv + r * nvp + cc];
+    }
+    for (int i = lane; i < nc * nv; i += G) {
+      int r = i / nv, cc = i - r * nv;
+      g.con_jac[e * nc * nv + i] = s[D.s_J + r * nvp + cc];
+    }
+    for (int i = lane; i < nc; i += G) { g.con_diag[e * nc + i] = s[D.s_diag + i]; g.con_aref[e * nc + i] = s[D.s_aref + i]; }
+    if (dg) {
+      if (dg->con_dist) for (int i = lane; i < D.ncon; i += G) dg->con_dist[e * D.ncon + i] = s[D.s_dist + i];
+      if (dg->stats && lane == 0) {
+        int32_t* o = dg->stats + e * 4;
+        o[0] += st.pg_iters; o[1] += st.pg_trials; o[2] += st.ns_accepts; o[3] += st.ns_cold;
+      }
+    }
+  });
+}
+
+}  // namespace bxg

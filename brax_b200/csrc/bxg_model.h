@@ -1,0 +1,217 @@
+// bxg_model.h -- host-side packing of BxgModelDesc into the flat "model blob"
+// the kernel stages into shared memory, plus the per-env shared-memory layout.
+//
+// This is the compile-time half of the reference's `scan.tree` /
+// `scan.link_types` (brax/scan.py:53-193): tree levels, child lists, ancestor
+// masks and dof->link maps are derived once per model here, so the kernel never
+// walks the tree by pointer chasing.
+#pragma once
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/bxg.h"
+
+namespace bxg {
+
+// All offsets are in 4-byte words.  m_* index the model blob, s_* index the
+// per-env shared-memory slab.
+struct Dims {
+  int L, nq, nv, nu, ncon, nlim, nc;
+  int nvp;        // row stride of nv x nv and nc x nv matrices in smem (odd)
+  int ncp;        // row stride of the nc x nc matrix in smem (odd)
+  int max_depth;  // deepest tree level
+  int solver_iterations, solver_maxls, ns_iters, minv_mode;
+  float dt, gx, gy, gz;
+  // ---- model blob ----
+  int m_link_parent, m_link_ndof, m_link_qadr, m_link_dadr, m_link_depth, m_link_root;
+  int m_child_start, m_child_list;       // CSR, children in DEscending index order
+  int m_dof_link, m_dof_qidx;            // dof -> link, dof -> q index
+  int m_dof_anc_lo, m_dof_anc_hi;        // bitmask over dofs j<=i whose link is ancestor-or-self
+  int m_dof_act_start, m_dof_act_list;   // CSR actuators per dof
+  int m_lim_dof;                         // [nlim] dof of each limit row
+  int m_tf_pos, m_tf_rot, m_joint_pos, m_in_pos, m_in_rot, m_in_i, m_in_mass, m_link_invw;
+  int m_dof_ang, m_dof_vel, m_arm, m_stiff, m_damp, m_lim_lo, m_lim_hi, m_dof_invw, m_dof_sp;
+  int m_act_qid, m_act_did, m_act_gain, m_act_gear, m_act_clo, m_act_chi, m_act_flo, m_act_fhi, m_act_bq, m_act_bqd;
+  int m_con_la, m_con_lb, m_con_ppos, m_con_frame, m_con_spos, m_con_rad, m_con_mu, m_con_sp;  // sp: [ncon,7]
+  int m_con_anc_lo, m_con_anc_hi;        // [ncon] bitmask of dofs that move link_b
+  int model_words;
+  // ---- per-env slab ----
+  int s_q, s_qd, s_act, s_tau, s_qfs, s_qfc, s_qdd;
+  int s_x_pos, s_x_rot, s_xd_ang, s_xd_vel, s_root_com;
+  int s_cinr_pos, s_cinr_rot, s_cinr_i, s_cinr_mass;
+  int s_cd_ang, s_cd_vel, s_cdof_ang, s_cdof_vel, s_cdofd_ang, s_cdofd_vel;
+  int s_t_ang, s_t_vel;        // [L,3] x2 temps: cdd (RNE) / xi_pos (com)
+  int s_f_ang, s_f_vel;        // [L,3] x2 temps: cfrc (RNE) / joint frame pos
+  int s_j_rot;                 // [L,4] joint frame rot
+  int s_crb_pos, s_crb_i, s_crb_mass;
+  int s_M, s_Minv, s_scr;      // s_scr: 2*nv*nvp (N-S) or nc*nvp + nc*ncp (constraint solve)
+  int s_J, s_diag, s_aref, s_b, s_px, s_py, s_pg, s_pres, s_pxn;
+  int s_dist;                  // [ncon]
+  int s_red;                   // [8] scalars
+  int env_words;
+};
+
+inline int odd_up(int n) { return n | 1; }
+
+struct PackedModel {
+  Dims d;
+  std::vector<uint32_t> blob;
+};
+
+// Returns empty string on success, else an error message.
+inline std::string pack_model(const BxgModelDesc& m, PackedModel* out) {
+  Dims& d = out->d;
+  std::vector<uint32_t>& b = out->blob;
+  b.clear();
+  if (m.abi_version != BXG_ABI_VERSION) return "abi_version mismatch";
+  if (m.num_links < 1 || m.nv < 1 || m.nq < 1) return "empty model";
+  if (m.num_links > 32) return "num_links > 32 not supported";
+  if (m.nv > 64) return "nv > 64 not supported";
+  const int L = m.num_links;
+  d.L = L; d.nq = m.nq; d.nv = m.nv; d.nu = m.nu; d.ncon = m.ncon;
+  int nonfree = 0, nq = 0, nv = 0;
+  std::vector<int> qadr(L), dadr(L), depth(L), root(L);
+  for (int l = 0; l < L; ++l) {
+    int nd = m.link_ndof[l];
+    if (nd < 0 || nd > 3) return "link_ndof must be 0 (free) or 1..3";
+    int p = m.link_parent[l];
+    if (p >= l || p < -1) return "link_parents must be depth-first ordered";
+    if (nd == 0 && p != -1) return "free joints must be roots";
+    qadr[l] = nq; dadr[l] = nv;
+    nq += nd == 0 ? 7 : nd; nv += nd == 0 ? 6 : nd;
+    nonfree += nd;
+    depth[l] = p < 0 ? 0 : depth[p] + 1;
+    root[l] = p < 0 ? l : root[p];
+  }
+  if (nq != m.nq || nv != m.nv) return "nq/nv inconsistent with link_ndof";
+  d.nlim = m.has_limit ? nonfree : 0;
+  d.nc = 4 * m.ncon + d.nlim;
+  if (d.nc > 64) return "more than 64 constraint rows not supported";
+  d.nvp = odd_up(m.nv); d.ncp = odd_up(d.nc > 0 ? d.nc : 1);
+  d.max_depth = 0;
+  for (int l = 0; l < L; ++l) d.max_depth = depth[l] > d.max_depth ? depth[l] : d.max_depth;
+  d.solver_iterations = m.solver_iterations; d.solver_maxls = m.solver_maxls;
+  d.ns_iters = m.matrix_inv_iterations; d.minv_mode = m.minv_mode;
+  d.dt = m.dt; d.gx = m.gravity[0]; d.gy = m.gravity[1]; d.gz = m.gravity[2];
+
+  auto put_i = [&](const std::vector<int>& v) { int o = (int)b.size(); for (int x : v) b.push_back((uint32_t)x); return o; };
+  auto put_f = [&](const float* p, int n) {
+    int o = (int)b.size();
+    for (int i = 0; i < n; ++i) { union { float f; uint32_t u; } c; c.f = p ? p[i] : 0.f; b.push_back(c.u); }
+    return o;
+  };
+  auto put_ip = [&](const int32_t* p, int n) { int o = (int)b.size(); for (int i = 0; i < n; ++i) b.push_back((uint32_t)p[i]); return o; };
+
+  d.m_link_parent = put_ip(m.link_parent, L);
+  d.m_link_ndof = put_ip(m.link_ndof, L);
+  d.m_link_qadr = put_i(qadr); d.m_link_dadr = put_i(dadr);
+  d.m_link_depth = put_i(depth); d.m_link_root = put_i(root);
+  std::vector<int> cstart(L + 1, 0), clist;
+  for (int l = 0; l < L; ++l) {
+    cstart[l] = (int)clist.size();
+    for (int c = L - 1; c > l; --c) if (m.link_parent[c] == l) clist.push_back(c);
+  }
+  cstart[L] = (int)clist.size();
+  if (clist.empty()) clist.push_back(0);
+  d.m_child_start = put_i(cstart); d.m_child_list = put_i(clist);
+
+  std::vector<int> dof_link(m.nv), dof_q(m.nv);
+  for (int l = 0; l < L; ++l) {
+    int w = m.link_ndof[l] == 0 ? 6 : m.link_ndof[l];
+    for (int k = 0; k < w; ++k) { dof_link[dadr[l] + k] = l; dof_q[dadr[l] + k] = m.link_ndof[l] == 0 ? -1 : qadr[l] + k; }
+  }
+  d.m_dof_link = put_i(dof_link); d.m_dof_qidx = put_i(dof_q);
+  auto is_anc = [&](int anc, int l) { while (l >= 0) { if (l == anc) return true; l = m.link_parent[l]; } return false; };
+  std::vector<int> alo(m.nv), ahi(m.nv);
+  for (int i = 0; i < m.nv; ++i) {
+    uint64_t mask = 0;
+    for (int j = 0; j <= i; ++j) if (is_anc(dof_link[j], dof_link[i])) mask |= (uint64_t)1 << j;
+    alo[i] = (int)(uint32_t)(mask & 0xffffffffu); ahi[i] = (int)(uint32_t)(mask >> 32);
+  }
+  d.m_dof_anc_lo = put_i(alo); d.m_dof_anc_hi = put_i(ahi);
+  std::vector<int> astart(m.nv + 1, 0), alist;
+  for (int dd = 0; dd < m.nv; ++dd) {
+    astart[dd] = (int)alist.size();
+    for (int a = 0; a < m.nu; ++a) {
+      if (m.act_qd_id[a] < 0 || m.act_qd_id[a] >= m.nv || m.act_q_id[a] < 0 || m.act_q_id[a] >= m.nq) return "actuator index out of range";
+      if (m.act_qd_id[a] == dd) alist.push_back(a);
+    }
+  }
+  astart[m.nv] = (int)alist.size();
+  if (alist.empty()) alist.push_back(0);
+  d.m_dof_act_start = put_i(astart); d.m_dof_act_list = put_i(alist);
+  std::vector<int> lim_dof;
+  for (int i = 0; i < m.nv; ++i) if (dof_q[i] >= 0) lim_dof.push_back(i);
+  if (lim_dof.empty()) lim_dof.push_back(0);
+  d.m_lim_dof = put_i(lim_dof);
+
+  d.m_tf_pos = put_f(m.link_tf_pos, L * 3); d.m_tf_rot = put_f(m.link_tf_rot, L * 4);
+  d.m_joint_pos = put_f(m.link_joint_pos, L * 3);
+  d.m_in_pos = put_f(m.inertia_pos, L * 3); d.m_in_rot = put_f(m.inertia_rot, L * 4);
+  d.m_in_i = put_f(m.inertia_i, L * 9); d.m_in_mass = put_f(m.inertia_mass, L);
+  d.m_link_invw = put_f(m.link_invweight, L);
+  d.m_dof_ang = put_f(m.dof_ang, m.nv * 3); d.m_dof_vel = put_f(m.dof_vel, m.nv * 3);
+  d.m_arm = put_f(m.dof_armature, m.nv); d.m_stiff = put_f(m.dof_stiffness, m.nv);
+  d.m_damp = put_f(m.dof_damping, m.nv);
+  d.m_lim_lo = put_f(m.has_limit ? m.dof_limit_lo : nullptr, m.nv);
+  d.m_lim_hi = put_f(m.has_limit ? m.dof_limit_hi : nullptr, m.nv);
+  d.m_dof_invw = put_f(m.dof_invweight, m.nv); d.m_dof_sp = put_f(m.dof_solver_params, m.nv * 7);
+  int nu1 = m.nu > 0 ? m.nu : 0;
+  d.m_act_qid = put_ip(m.act_q_id, nu1); d.m_act_did = put_ip(m.act_qd_id, nu1);
+  d.m_act_gain = put_f(m.act_gain, nu1); d.m_act_gear = put_f(m.act_gear, nu1);
+  d.m_act_clo = put_f(m.act_ctrl_lo, nu1); d.m_act_chi = put_f(m.act_ctrl_hi, nu1);
+  d.m_act_flo = put_f(m.act_force_lo, nu1); d.m_act_fhi = put_f(m.act_force_hi, nu1);
+  d.m_act_bq = put_f(m.act_bias_q, nu1); d.m_act_bqd = put_f(m.act_bias_qd, nu1);
+  for (int c = 0; c < m.ncon; ++c) {
+    if (m.con_link_b[c] < 0 || m.con_link_b[c] >= L) return "con_link_b out of range";
+    if (m.con_link_a[c] != -1) return "plane must be attached to the world (link_a == -1)";
+  }
+  d.m_con_la = put_ip(m.con_link_a, m.ncon); d.m_con_lb = put_ip(m.con_link_b, m.ncon);
+  d.m_con_ppos = put_f(m.con_plane_pos, m.ncon * 3); d.m_con_frame = put_f(m.con_frame, m.ncon * 9);
+  d.m_con_spos = put_f(m.con_sphere_pos, m.ncon * 3); d.m_con_rad = put_f(m.con_radius, m.ncon);
+  d.m_con_mu = put_f(m.con_friction, m.ncon);
+  std::vector<float> sp(m.ncon * 7 + 1, 0.f);
+  for (int c = 0; c < m.ncon; ++c) {
+    sp[c * 7 + 0] = m.con_solref[c * 2]; sp[c * 7 + 1] = m.con_solref[c * 2 + 1];
+    for (int k = 0; k < 5; ++k) sp[c * 7 + 2 + k] = m.con_solimp[c * 5 + k];
+  }
+  d.m_con_sp = put_f(sp.data(), m.ncon * 7);
+  std::vector<int> clo(m.ncon > 0 ? m.ncon : 1, 0), chi(m.ncon > 0 ? m.ncon : 1, 0);
+  for (int c = 0; c < m.ncon; ++c) {
+    uint64_t mask = 0;
+    for (int j = 0; j < m.nv; ++j) if (is_anc(dof_link[j], m.con_link_b[c])) mask |= (uint64_t)1 << j;
+    clo[c] = (int)(uint32_t)(mask & 0xffffffffu); chi[c] = (int)(uint32_t)(mask >> 32);
+  }
+  d.m_con_anc_lo = put_i(clo); d.m_con_anc_hi = put_i(chi);
+  while (b.size() % 4) b.push_back(0);
+  d.model_words = (int)b.size();
+
+  // ---- per-env slab ----
+  int o = 0;
+  auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
+  const int nvv = m.nv, nc = d.nc, ncz = nc > 0 ? nc : 1;
+  d.s_q = take(m.nq); d.s_qd = take(nvv); d.s_act = take(m.nu > 0 ? m.nu : 1);
+  d.s_tau = take(nvv); d.s_qfs = take(nvv); d.s_qfc = take(nvv); d.s_qdd = take(nvv);
+  d.s_x_pos = take(L * 3); d.s_x_rot = take(L * 4); d.s_xd_ang = take(L * 3); d.s_xd_vel = take(L * 3);
+  d.s_root_com = take(L * 3);
+  d.s_cinr_pos = take(L * 3); d.s_cinr_rot = take(L * 4); d.s_cinr_i = take(L * 9); d.s_cinr_mass = take(L);
+  d.s_cd_ang = take(L * 3); d.s_cd_vel = take(L * 3);
+  d.s_cdof_ang = take(nvv * 3); d.s_cdof_vel = take(nvv * 3);
+  d.s_cdofd_ang = take(nvv * 3); d.s_cdofd_vel = take(nvv * 3);
+  d.s_t_ang = take(L * 3); d.s_t_vel = take(L * 3); d.s_f_ang = take(L * 3); d.s_f_vel = take(L * 3);
+  d.s_j_rot = take(L * 4);
+  d.s_crb_pos = take(L * 3); d.s_crb_i = take(L * 9); d.s_crb_mass = take(L);
+  d.s_M = take(nvv * d.nvp); d.s_Minv = take(nvv * d.nvp);
+  int scr_ns = 2 * nvv * d.nvp, scr_pg = ncz * d.nvp + ncz * d.ncp;
+  d.s_scr = take(scr_ns > scr_pg ? scr_ns : scr_pg);
+  d.s_J = take(ncz * d.nvp); d.s_diag = take(ncz); d.s_aref = take(ncz); d.s_b = take(ncz);
+  d.s_px = take(ncz); d.s_py = take(ncz); d.s_pg = take(ncz); d.s_pres = take(ncz); d.s_pxn = take(ncz);
+  d.s_dist = take(m.ncon > 0 ? m.ncon : 1);
+  d.s_red = take(8);
+  d.env_words = o;
+  return "";
+}
+
+}  // namespace bxg

@@ -1,0 +1,274 @@
+"""ctypes binding of the C ABI in include/bxg.h (libbxg.so, built in-tree).
+
+PyTorch is used only for device memory and streams: every State leaf is a
+torch CUDA tensor whose `data_ptr()` is handed to the library.  There is no CPU
+fallback -- if the shared library or a CUDA device is missing, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libbxg.so')
+
+MINV_NEWTON_SCHULZ = 0
+MINV_CHOLESKY = 1
+STEP_DIAGNOSTICS = 1
+
+STATE_FIELDS = (
+    'q', 'qd', 'x_pos', 'x_rot', 'xd_ang', 'xd_vel', 'root_com',
+    'cinr_pos', 'cinr_rot', 'cinr_i', 'cinr_mass', 'cd_ang', 'cd_vel',
+    'cdof_ang', 'cdof_vel', 'cdofd_ang', 'cdofd_vel',
+    'mass_mx', 'mass_mx_inv', 'con_jac', 'con_diag', 'con_aref',
+    'qf_smooth', 'qf_constraint', 'qdd')
+
+_i32, _f32 = ctypes.c_int32, ctypes.c_float
+_pi, _pf = ctypes.POINTER(_i32), ctypes.POINTER(_f32)
+
+
+class ModelDesc(ctypes.Structure):
+  """Mirror of BxgModelDesc (include/bxg.h)."""
+  _fields_ = [
+      ('abi_version', _i32), ('num_links', _i32), ('nq', _i32), ('nv', _i32), ('nu', _i32),
+      ('ncon', _i32), ('has_limit', _i32),
+      ('solver_iterations', _i32), ('solver_maxls', _i32), ('matrix_inv_iterations', _i32),
+      ('minv_mode', _i32), ('dt', _f32), ('gravity', _f32 * 3),
+      ('link_parent', _pi), ('link_ndof', _pi),
+      ('link_tf_pos', _pf), ('link_tf_rot', _pf), ('link_joint_pos', _pf),
+      ('inertia_pos', _pf), ('inertia_rot', _pf), ('inertia_i', _pf), ('inertia_mass', _pf),
+      ('link_invweight', _pf),
+      ('dof_ang', _pf), ('dof_vel', _pf), ('dof_armature', _pf), ('dof_stiffness', _pf),
+      ('dof_damping', _pf), ('dof_limit_lo', _pf), ('dof_limit_hi', _pf), ('dof_invweight', _pf),
+      ('dof_solver_params', _pf),
+      ('act_q_id', _pi), ('act_qd_id', _pi), ('act_gain', _pf), ('act_gear', _pf),
+      ('act_ctrl_lo', _pf), ('act_ctrl_hi', _pf), ('act_force_lo', _pf), ('act_force_hi', _pf),
+      ('act_bias_q', _pf), ('act_bias_qd', _pf),
+      ('con_link_a', _pi), ('con_link_b', _pi), ('con_plane_pos', _pf), ('con_frame', _pf),
+      ('con_sphere_pos', _pf), ('con_radius', _pf), ('con_friction', _pf),
+      ('con_solref', _pf), ('con_solimp', _pf),
+  ]
+
+
+class StateC(ctypes.Structure):
+  _fields_ = [(f, ctypes.c_void_p) for f in STATE_FIELDS]
+
+
+class DiagC(ctypes.Structure):
+  _fields_ = [('con_dist', ctypes.c_void_p), ('stats', ctypes.c_void_p)]
+
+
+def make_desc(sys, minv_mode: int = MINV_NEWTON_SCHULZ) -> Tuple[ModelDesc, list]:
+  """System -> BxgModelDesc.  Returns (desc, keepalive arrays)."""
+  keep = []
+
+  def fp(a):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(-1))
+    if a.size == 0:
+      a = np.zeros(1, np.float32)
+    keep.append(a)
+    return a.ctypes.data_as(_pf)
+
+  def ip(a):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.int32).reshape(-1))
+    if a.size == 0:
+      a = np.zeros(1, np.int32)
+    keep.append(a)
+    return a.ctypes.data_as(_pi)
+
+  cp = sys.contact_pairs()
+  d = ModelDesc()
+  d.abi_version = 1
+  d.num_links, d.nq, d.nv, d.nu = sys.num_links(), sys.nq, sys.nv, sys.nu
+  d.ncon = len(cp.geom1)
+  d.has_limit = 0 if sys.dof.limit is None else 1
+  d.solver_iterations = int(sys.solver_iterations)
+  d.solver_maxls = int(sys.solver_maxls)
+  d.matrix_inv_iterations = int(sys.matrix_inv_iterations)
+  d.minv_mode = int(minv_mode)
+  d.dt = float(sys.opt.timestep)
+  for i in range(3):
+    d.gravity[i] = float(sys.gravity[i])
+  d.link_parent = ip(sys.link_parents)
+  d.link_ndof = ip([0 if t == 'f' else int(t) for t in sys.link_types])
+  d.link_tf_pos = fp(sys.link.transform.pos); d.link_tf_rot = fp(sys.link.transform.rot)
+  d.link_joint_pos = fp(sys.link.joint.pos)
+  d.inertia_pos = fp(sys.link.inertia.transform.pos); d.inertia_rot = fp(sys.link.inertia.transform.rot)
+  d.inertia_i = fp(sys.link.inertia.i); d.inertia_mass = fp(sys.link.inertia.mass)
+  d.link_invweight = fp(sys.link.invweight)
+  d.dof_ang = fp(sys.dof.motion.ang); d.dof_vel = fp(sys.dof.motion.vel)
+  d.dof_armature = fp(sys.dof.armature); d.dof_stiffness = fp(sys.dof.stiffness)
+  d.dof_damping = fp(sys.dof.damping)
+  if sys.dof.limit is not None:
+    d.dof_limit_lo = fp(sys.dof.limit[0]); d.dof_limit_hi = fp(sys.dof.limit[1])
+  d.dof_invweight = fp(sys.dof.invweight); d.dof_solver_params = fp(sys.dof.solver_params)
+  a = sys.actuator
+  d.act_q_id = ip(a.q_id); d.act_qd_id = ip(a.qd_id)
+  d.act_gain = fp(a.gain); d.act_gear = fp(a.gear)
+  cr = np.asarray(a.ctrl_range, np.float32).reshape(-1, 2)
+  fr = np.asarray(a.force_range, np.float32).reshape(-1, 2)
+  d.act_ctrl_lo = fp(cr[:, 0]); d.act_ctrl_hi = fp(cr[:, 1])
+  d.act_force_lo = fp(fr[:, 0]); d.act_force_hi = fp(fr[:, 1])
+  d.act_bias_q = fp(a.bias_q); d.act_bias_qd = fp(a.bias_qd)
+  d.con_link_a = ip(cp.link_a); d.con_link_b = ip(cp.link_b)
+  d.con_plane_pos = fp(cp.plane_pos); d.con_frame = fp(cp.frame)
+  d.con_sphere_pos = fp(cp.sphere_pos); d.con_radius = fp(cp.radius)
+  d.con_friction = fp(cp.friction); d.con_solref = fp(cp.solref); d.con_solimp = fp(cp.solimp)
+  return d, keep
+
+
+def num_constraints(sys) -> int:
+  ncon = len(sys.contact_pairs().geom1)
+  nlim = 0
+  if sys.dof.limit is not None:
+    nlim = sum(int(t) for t in sys.link_types if t != 'f')
+  return 4 * ncon + nlim
+
+
+def state_shapes(sys) -> Dict[str, tuple]:
+  L, nq, nv, nc = sys.num_links(), sys.nq, sys.nv, num_constraints(sys)
+  return {
+      'q': (nq,), 'qd': (nv,), 'x_pos': (L, 3), 'x_rot': (L, 4), 'xd_ang': (L, 3), 'xd_vel': (L, 3),
+      'root_com': (L, 3), 'cinr_pos': (L, 3), 'cinr_rot': (L, 4), 'cinr_i': (L, 3, 3), 'cinr_mass': (L,),
+      'cd_ang': (L, 3), 'cd_vel': (L, 3), 'cdof_ang': (nv, 3), 'cdof_vel': (nv, 3),
+      'cdofd_ang': (nv, 3), 'cdofd_vel': (nv, 3), 'mass_mx': (nv, nv), 'mass_mx_inv': (nv, nv),
+      'con_jac': (nc, nv), 'con_diag': (nc,), 'con_aref': (nc,),
+      'qf_smooth': (nv,), 'qf_constraint': (nv,), 'qdd': (nv,)}
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def lib() -> ctypes.CDLL:
+  """Loads libbxg.so.  Raises (loudly) if the extension has not been built."""
+  global _lib
+  with _lib_lock:
+    if _lib is None:
+      if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f'{LIB_PATH} is missing: build it with `python -c "import '
+            '__graft_entry__ as g; g.build()"`. There is no CPU fallback.')
+      l = ctypes.CDLL(LIB_PATH)
+      l.bxg_last_error.restype = ctypes.c_char_p
+      l.bxg_launch_count.restype = ctypes.c_int64
+      l.bxg_model_create.argtypes = [ctypes.POINTER(ModelDesc), ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+      l.bxg_model_destroy.argtypes = [ctypes.c_void_p]
+      l.bxg_model_num_constraints.argtypes = [ctypes.c_void_p]
+      l.bxg_init.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                             ctypes.POINTER(StateC), ctypes.c_void_p]
+      l.bxg_step.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(StateC),
+                             ctypes.c_void_p, ctypes.POINTER(StateC), ctypes.c_int32,
+                             ctypes.POINTER(DiagC), ctypes.c_void_p]
+      if l.bxg_abi_version() != 1:
+        raise RuntimeError('libbxg.so ABI version mismatch')
+      _lib = l
+    return _lib
+
+
+def launch_count() -> int:
+  return int(lib().bxg_launch_count())
+
+
+def _check(rc: int, what: str):
+  if rc != 0:
+    msg = lib().bxg_last_error().decode('utf-8', 'replace')
+    raise RuntimeError(f'{what} failed (code {rc}): {msg}')
+
+
+class NativeModel:
+  """A System uploaded to one CUDA device (BxgModel handle)."""
+
+  def __init__(self, sys, device: int, minv_mode: int = MINV_NEWTON_SCHULZ):
+    import torch
+    if not torch.cuda.is_available():
+      raise RuntimeError('no CUDA device: brax_b200 has no CPU fallback')
+    self.sys = sys
+    self.device = int(device)
+    self.minv_mode = minv_mode
+    self.shapes = state_shapes(sys)
+    self.nc = num_constraints(sys)
+    self.ncon = len(sys.contact_pairs().geom1)
+    desc, keep = make_desc(sys, minv_mode)
+    h = ctypes.c_void_p()
+    _check(lib().bxg_model_create(ctypes.byref(desc), self.device, ctypes.byref(h)), 'bxg_model_create')
+    self._h = h
+    del keep
+
+  def __del__(self):
+    h, self._h = getattr(self, '_h', None), None
+    if h is not None and _lib is not None:
+      _lib.bxg_model_destroy(h)
+
+  # -- buffers ---------------------------------------------------------------
+  def alloc(self, n: int) -> Dict[str, 'torch.Tensor']:
+    import torch
+    dev = torch.device('cuda', self.device)
+    return {k: torch.empty((n,) + s, dtype=torch.float32, device=dev) for k, s in self.shapes.items()}
+
+  @staticmethod
+  def _cstate(bufs) -> StateC:
+    cs = StateC()
+    for f in STATE_FIELDS:
+      t = bufs[f]
+      assert t.is_cuda and t.is_contiguous() and t.dtype.is_floating_point and t.element_size() == 4, f
+      setattr(cs, f, t.data_ptr())
+    return cs
+
+  # -- calls -----------------------------------------------------------------
+  def init(self, q, qd, out: Optional[dict] = None) -> dict:
+    import torch
+    n = q.shape[0]
+    assert q.shape == (n, self.sys.nq) and qd.shape == (n, self.sys.nv), (q.shape, qd.shape)
+    q = q.contiguous().float(); qd = qd.contiguous().float()
+    out = self.alloc(n) if out is None else out
+    cs = self._cstate(out)
+    stream = torch.cuda.current_stream(q.device).cuda_stream
+    _check(lib().bxg_init(self._h, n, q.data_ptr(), qd.data_ptr(), ctypes.byref(cs), stream), 'bxg_init')
+    return out
+
+  def step(self, bufs: dict, act, n_frames: int = 1, out: Optional[dict] = None,
+           diag: Optional[dict] = None) -> dict:
+    import torch
+    n = bufs['q'].shape[0]
+    if self.sys.nu:
+      assert act is not None and act.shape == (n, self.sys.nu), None if act is None else act.shape
+      act = act.contiguous().float()
+      act_ptr = act.data_ptr()
+    else:
+      act_ptr = None
+    out = self.alloc(n) if out is None else out
+    cin, cout = self._cstate(bufs), self._cstate(out)
+    flags, dg = 0, None
+    if diag is not None:
+      flags = STEP_DIAGNOSTICS
+      dg = DiagC()
+      dg.con_dist = diag['con_dist'].data_ptr() if self.ncon else None
+      dg.stats = diag['stats'].data_ptr()
+    stream = torch.cuda.current_stream(bufs['q'].device).cuda_stream
+    _check(lib().bxg_step(self._h, n, int(n_frames), ctypes.byref(cin), act_ptr, ctypes.byref(cout),
+                          flags, ctypes.byref(dg) if dg is not None else None, stream), 'bxg_step')
+    return out
+
+  def alloc_diag(self, n: int) -> dict:
+    import torch
+    dev = torch.device('cuda', self.device)
+    return {'con_dist': torch.zeros((n, max(self.ncon, 1)), dtype=torch.float32, device=dev),
+            'stats': torch.zeros((n, 4), dtype=torch.int32, device=dev)}
+
+
+_models: Dict[Tuple[int, int, int], NativeModel] = {}
+
+
+def model_for(sys, device: int, minv_mode: int = MINV_NEWTON_SCHULZ) -> NativeModel:
+  """Per-(System object, device, mode) cache of uploaded models."""
+  key = (id(sys), int(device), int(minv_mode))
+  m = _models.get(key)
+  if m is None or m.sys is not sys:
+    m = NativeModel(sys, device, minv_mode)
+    _models[key] = m
+  return m

@@ -1,0 +1,184 @@
+/*
+ * bxg.h -- C ABI of the B200-native `generalized` physics step.
+ *
+ * Drop-in boundary for google/brax 0.14.2's generalized pipeline.  The
+ * reference has no FFI for this path: the seam is a Python module with two
+ * functions selected by a backend string (brax/envs/base.py:104-114),
+ *
+ *   generalized.pipeline.init(sys, q, qd, ...)  -> State   pipeline.py:32-61
+ *   generalized.pipeline.step(sys, state, act)  -> State   pipeline.py:64-94
+ *
+ * called under vmap over envs (envs/wrappers/training.py:66-72) and looped
+ * n_frames times with one action (envs/base.py:128-137).  The entry points
+ * below are what a JAX-FFI / ctypes binding for that seam binds: the batch
+ * axis and the n_frames loop are inside the call.
+ *
+ * Conventions
+ *   - every `float*` / `int32_t*` in BxgState and in the call arguments is a
+ *     DEVICE pointer to a dense env-major array [n_env, ...] (fp32), caller
+ *     allocated; BxgModelDesc pointers are HOST pointers, copied at create time
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*),
+ *     never allocate, never synchronise, are CUDA-graph capturable and
+ *     re-entrant across models/devices
+ *   - return 0 on success, non-zero BXG_E_* otherwise; bxg_last_error() gives
+ *     a thread-local message.  There is no CPU fallback: without a CUDA device
+ *     every compute entry point returns BXG_E_CUDA.
+ */
+#ifndef BXG_H_
+#define BXG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BXG_ABI_VERSION 1
+
+enum {
+  BXG_OK = 0,
+  BXG_E_INVALID = 1,      /* bad argument / unsupported model            */
+  BXG_E_CUDA = 2,         /* CUDA runtime error (incl. no device)        */
+  BXG_E_UNSUPPORTED = 3   /* model outside the kernel's compiled limits  */
+};
+
+/* bxg_step flags */
+enum {
+  BXG_STEP_DEFAULT = 0,
+  /* also write the per-contact penetration distance and solver statistics */
+  BXG_STEP_DIAGNOSTICS = 1
+};
+
+/* How mass_mx_inv is produced inside step (reference mass.py:86-106).
+ * NEWTON_SCHULZ is the reference algorithm (math.py:278-305): warm-started
+ * from the incoming mass_mx_inv, `matrix_inv_iterations` iterations.       */
+enum {
+  BXG_MINV_NEWTON_SCHULZ = 0,
+  BXG_MINV_CHOLESKY = 1   /* exact SPD inverse every substep (north_star) */
+};
+
+/* Model constants = the fields of brax.base.System the path reads
+ * (brax/base.py:415-540).  Host pointers. */
+typedef struct BxgModelDesc {
+  int32_t abi_version;           /* BXG_ABI_VERSION */
+  int32_t num_links, nq, nv, nu; /* len(link_types), q_size, qd_size, act_size */
+  int32_t ncon;                  /* static contact count (mjx.make_data(sys).ncon) */
+  int32_t has_limit;             /* sys.dof.limit is not None */
+  int32_t solver_iterations, solver_maxls, matrix_inv_iterations;
+  int32_t minv_mode;             /* BXG_MINV_* */
+  float dt;                      /* sys.opt.timestep */
+  float gravity[3];              /* sys.gravity */
+  /* links [num_links] */
+  const int32_t* link_parent;    /* sys.link_parents (-1 = root) */
+  const int32_t* link_ndof;      /* 0 = free joint ('f'), else 1..3 */
+  const float* link_tf_pos;      /* [L,3] sys.link.transform.pos */
+  const float* link_tf_rot;      /* [L,4] sys.link.transform.rot */
+  const float* link_joint_pos;   /* [L,3] sys.link.joint.pos */
+  const float* inertia_pos;      /* [L,3] sys.link.inertia.transform.pos */
+  const float* inertia_rot;      /* [L,4] sys.link.inertia.transform.rot */
+  const float* inertia_i;        /* [L,3,3] sys.link.inertia.i */
+  const float* inertia_mass;     /* [L] */
+  const float* link_invweight;   /* [L] */
+  /* dofs [nv] */
+  const float* dof_ang;          /* [nv,3] sys.dof.motion.ang */
+  const float* dof_vel;          /* [nv,3] sys.dof.motion.vel */
+  const float* dof_armature;
+  const float* dof_stiffness;
+  const float* dof_damping;
+  const float* dof_limit_lo;     /* may be NULL when !has_limit */
+  const float* dof_limit_hi;
+  const float* dof_invweight;
+  const float* dof_solver_params; /* [nv,7] */
+  /* actuators [nu] */
+  const int32_t* act_q_id;
+  const int32_t* act_qd_id;
+  const float* act_gain;
+  const float* act_gear;
+  const float* act_ctrl_lo;
+  const float* act_ctrl_hi;
+  const float* act_force_lo;
+  const float* act_force_hi;
+  const float* act_bias_q;
+  const float* act_bias_qd;
+  /* plane-sphere contacts [ncon] (brax/contact.py:28-67 + mjx collision) */
+  const int32_t* con_link_a;     /* plane link (-1 = world) */
+  const int32_t* con_link_b;     /* sphere link */
+  const float* con_plane_pos;    /* [ncon,3] world */
+  const float* con_frame;        /* [ncon,3,3] rows normal,t1,t2 */
+  const float* con_sphere_pos;   /* [ncon,3] in link_b frame */
+  const float* con_radius;
+  const float* con_friction;     /* sliding friction mu */
+  const float* con_solref;       /* [ncon,2] */
+  const float* con_solimp;       /* [ncon,5] */
+} BxgModelDesc;
+
+/* The generalized State (brax/generalized/base.py:25-92 + brax/base.py:396-412)
+ * as one dense fp32 array per leaf, env-major.  nc = 4*ncon + nlim where nlim
+ * is the number of non-free dofs when has_limit, else 0. */
+typedef struct BxgState {
+  float* q;             /* [n, nq] */
+  float* qd;            /* [n, nv] */
+  float* x_pos;         /* [n, L, 3] */
+  float* x_rot;         /* [n, L, 4] */
+  float* xd_ang;        /* [n, L, 3] */
+  float* xd_vel;        /* [n, L, 3] */
+  float* root_com;      /* [n, L, 3] */
+  float* cinr_pos;      /* [n, L, 3]   cinr.transform.pos */
+  float* cinr_rot;      /* [n, L, 4]   cinr.transform.rot */
+  float* cinr_i;        /* [n, L, 3, 3] */
+  float* cinr_mass;     /* [n, L] */
+  float* cd_ang;        /* [n, L, 3] */
+  float* cd_vel;        /* [n, L, 3] */
+  float* cdof_ang;      /* [n, nv, 3] */
+  float* cdof_vel;      /* [n, nv, 3] */
+  float* cdofd_ang;     /* [n, nv, 3] */
+  float* cdofd_vel;     /* [n, nv, 3] */
+  float* mass_mx;       /* [n, nv, nv] */
+  float* mass_mx_inv;   /* [n, nv, nv] */
+  float* con_jac;       /* [n, nc, nv] */
+  float* con_diag;      /* [n, nc] */
+  float* con_aref;      /* [n, nc] */
+  float* qf_smooth;     /* [n, nv] */
+  float* qf_constraint; /* [n, nv] */
+  float* qdd;           /* [n, nv] */
+} BxgState;
+
+/* Optional outputs written when BXG_STEP_DIAGNOSTICS is set (may be NULL). */
+typedef struct BxgDiag {
+  float* con_dist;      /* [n, ncon]  contact.dist after the last substep   */
+  int32_t* stats;       /* [n, 4]  accumulated: pg iterations, line-search
+                           evaluations, Newton-Schulz accepts, cold starts  */
+} BxgDiag;
+
+typedef struct BxgModel BxgModel;
+
+int bxg_abi_version(void);
+const char* bxg_last_error(void);
+
+/* Uploads model constants to `device` (cuda ordinal).  Replaces the implicit
+ * capture of `sys` by jit in the reference (envs/base.py:126,133). */
+int bxg_model_create(const BxgModelDesc* desc, int device, BxgModel** out);
+void bxg_model_destroy(BxgModel* model);
+/* nc for this model (rows of con_jac). */
+int bxg_model_num_constraints(const BxgModel* model);
+
+/* generalized.pipeline.init over a batch (pipeline.py:32-61):
+ * q [n,nq], qd [n,nv] -> every leaf of `out`. */
+int bxg_init(const BxgModel* model, int64_t n_env, const float* q,
+             const float* qd, const BxgState* out, void* stream);
+
+/* n_frames x generalized.pipeline.step with one action per env
+ * (pipeline.py:64-94 looped as envs/base.py:128-137).  `in` and `out` may
+ * alias field by field (in-place update).  act [n,nu] (NULL iff nu == 0). */
+int bxg_step(const BxgModel* model, int64_t n_env, int32_t n_frames,
+             const BxgState* in, const float* act, const BxgState* out,
+             int32_t flags, const BxgDiag* diag, void* stream);
+
+/* Number of kernel launches issued by this library so far in this process
+ * (bench.py reports the delta over the timed region as gpu_launches). */
+int64_t bxg_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BXG_H_ */

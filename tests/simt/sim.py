@@ -1,0 +1,71 @@
+"""TEST-ONLY front-end of tests/simt/bxg_sim.cpp (host emulation of the kernel's
+lane-group execution; see the header of that file).  Not a CPU fallback."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+from brax_b200 import native
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, 'libbxg_sim.so')
+_SRC = os.path.join(_HERE, 'bxg_sim.cpp')
+_CSRC = os.path.join(os.path.dirname(os.path.dirname(_HERE)), 'brax_b200', 'csrc')
+
+
+def build(force=False):
+  deps = [_SRC] + [os.path.join(_CSRC, f) for f in ('bxg_core.cuh', 'bxg_model.h')]
+  if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps):
+    return
+  subprocess.run(['g++', '-O2', '-ffp-contract=off', '-fPIC', '-shared', '-std=c++17', _SRC, '-o', _SO], check=True)
+
+
+class Sim:
+  def __init__(self, sys, G=None, reverse=False, minv_mode=native.MINV_NEWTON_SCHULZ):
+    build()
+    self.lib = ctypes.CDLL(_SO)
+    self.sys = sys
+    self.desc, self._keep = native.make_desc(sys, minv_mode)
+    if G is None:
+      G = 16 if (sys.num_links() <= 16 and sys.nv <= 16) else 32
+    self.G, self.reverse = G, int(reverse)
+    self.shapes = native.state_shapes(sys)
+    self.ncon = len(sys.contact_pairs().geom1)
+
+  def alloc(self, n):
+    return {k: np.zeros((n,) + s, np.float32) for k, s in self.shapes.items()}
+
+  @staticmethod
+  def _cstate(b):
+    cs = native.StateC()
+    for f in native.STATE_FIELDS:
+      assert b[f].dtype == np.float32 and b[f].flags['C_CONTIGUOUS'], f
+      setattr(cs, f, b[f].ctypes.data)
+    return cs
+
+  def init(self, q, qd):
+    q = np.ascontiguousarray(np.atleast_2d(q), np.float32); qd = np.ascontiguousarray(np.atleast_2d(qd), np.float32)
+    n = q.shape[0]
+    out = self.alloc(n)
+    cs = self._cstate(out)
+    rc = self.lib.sim_init(ctypes.byref(self.desc), self.G, self.reverse, ctypes.c_int64(n),
+                           q.ctypes.data_as(ctypes.c_void_p), qd.ctypes.data_as(ctypes.c_void_p), ctypes.byref(cs))
+    assert rc == 0, rc
+    return out
+
+  def step(self, st, act, n_frames=1, diag=False):
+    n = st['q'].shape[0]
+    act = np.ascontiguousarray(np.atleast_2d(act), np.float32)
+    out = self.alloc(n)
+    cin, cout = self._cstate(st), self._cstate(out)
+    dg = native.DiagC()
+    con_dist = np.zeros((n, max(self.ncon, 1)), np.float32); stats = np.zeros((n, 4), np.int32)
+    dg.con_dist = con_dist.ctypes.data; dg.stats = stats.ctypes.data
+    rc = self.lib.sim_step(ctypes.byref(self.desc), self.G, self.reverse, ctypes.c_int64(n), int(n_frames),
+                           ctypes.byref(cin), act.ctypes.data_as(ctypes.c_void_p), ctypes.byref(cout),
+                           1 if diag else 0, ctypes.byref(dg))
+    assert rc == 0, rc
+    if diag:
+      out['con_dist'] = con_dist; out['stats'] = stats
+    return out

@@ -1,0 +1,33 @@
+"""Regenerates the compiled model constants shipped with the package.
+
+Run in the build container (needs /root/reference for the MJCF sources):
+    python tools/gen_assets.py
+Writes brax_b200/assets/{ant,humanoid}.json and the small pendulum fixtures
+under tests/golden/ that the known-answer tests use.  The XML files themselves
+are not copied into this repository; only the numbers the hot path consumes.
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from brax_b200.io import mjcf, model_json  # noqa: E402
+
+REF = '/root/reference/brax'
+ASSETS = {
+    'ant': f'{REF}/envs/assets/ant.xml',
+    'humanoid': f'{REF}/envs/assets/humanoid.xml',
+}
+FIXTURES = ['triple_pendulum', 'single_pendulum_motor', 'single_pendulum_position',
+            'single_pendulum_velocity', 'single_pendulum_position_frclimit',
+            'double_pendulum', 'single_pendulum', 'triple_pendulum_motor']
+
+if __name__ == '__main__':
+  for name, path in ASSETS.items():
+    out = os.path.join(ROOT, 'brax_b200', 'assets', f'{name}.json')
+    model_json.save(mjcf.load(path), out)
+    print('wrote', out)
+  for name in FIXTURES:
+    out = os.path.join(ROOT, 'tests', 'golden', f'{name}.json')
+    model_json.save(mjcf.load(f'{REF}/test_data/{name}.xml'), out)
+    print('wrote', out)
