@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the generalized physics step (BASELINE.json).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+
+One "step" = one env-step (n_frames = 5 physics substeps, one action) over the
+whole env batch of this rank.  Prints ONE JSON line (rank 0).  Under torchrun
+each rank owns a contiguous shard of the env batch on its own GPU; there is no
+collective on the step path (scaling = weak: per-GPU envs fixed).
+
+Workloads (BASELINE.json `configs`):
+  humanoid_8192  configs[1]  Humanoid, 8192 envs/GPU            (default at N=1)
+  ant_1m         configs[2]  Ant, 1,048,576 envs/GPU
+  humanoid_512k  configs[3]  Humanoid, 524,288 envs/GPU, randomised falls
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    'humanoid_8192': ('humanoid', 8192),
+    'ant_1m': ('ant', 1 << 20),
+    'humanoid_512k': ('humanoid', 1 << 19),
+    'ant_1024': ('ant', 1024),
+}
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # non-tensor FMA peak at max clock
+
+
+def peaks():
+  p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(p):
+    with open(p) as f:
+      d = json.load(f)
+    return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+  return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+  """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+  Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+       'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+       'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, gpu_index):
+    self.gpu, self.rows, self.proc = gpu_index, [], None
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(
+          ['nvidia-smi', '-i', str(self.gpu), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100'],
+          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.t = threading.Thread(target=self._read, daemon=True)
+      self.t.start()
+    except Exception:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.rows.append([c.strip() for c in line.split(',')])
+
+  def stop(self):
+    if self.proc is None:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+    time.sleep(0.15)
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=2)
+    except Exception:
+      self.proc.kill()
+    sm, mx, reasons = [], [], set()
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    for r in self.rows:
+      try:
+        sm.append(float(r[1])); mx.append(float(r[2]))
+        for nme, v in zip(names, r[5:9]):
+          if v.lower().startswith('active'):
+            reasons.add(nme)
+      except Exception:
+        pass
+    sm.sort()
+    return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+            'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def cpu_port_throughput(model, n_frames, seconds_target=12.0, seed=0):
+  """Times the C oracle (a port, NOT the JAX reference) on the host cores on a
+  bounded sample of the same workload.  Returns (env_steps_per_s, cores, sample)."""
+  import numpy as np
+  import torch
+  from brax_b200 import workloads
+  from oracle import oracle as O
+  cores = os.cpu_count() or 1
+  sys_, q, qd = workloads.reset(model, 0, 64 * cores, seed, 'cpu')
+  o = O.Oracle(sys_, np.float32)
+  st = o.init(q.numpy(), qd.numpy())
+  n = q.shape[0]
+  act = workloads.action(model, 0, n, seed, 0, 'cpu').numpy()
+  o.step(st, act, n_frames)  # warm-up
+  t0 = time.perf_counter(); o.step(st, act, n_frames); dt1 = time.perf_counter() - t0
+  reps = max(1, min(200, int(seconds_target / max(dt1, 1e-6))))
+  t0 = time.perf_counter()
+  for k in range(reps):
+    act = workloads.action(model, 0, n, seed, 1 + k, 'cpu').numpy()
+    o.step(st, act, n_frames)
+  dt = time.perf_counter() - t0
+  return n * reps / dt, cores, f'{model}: {n} envs x {reps} env-steps, C oracle -O2 + OpenMP'
+
+
+def run_reference(args, rank, world):
+  """--impl reference: the reference's CPU implementation of the path.  JAX /
+  jaxopt / mujoco are not installable here, so this arm times the
+  oracle port on all host threads, bounded sample per step."""
+  if rank != 0:
+    return
+  model, n_env = WORKLOADS[args.workload]
+  import numpy as np
+  from brax_b200 import workloads
+  from oracle import oracle as O
+  cores = os.cpu_count() or 1
+  n = 32 * cores
+  sys_, q, qd = workloads.reset(model, 0, n, 0, 'cpu')
+  o = O.Oracle(sys_, np.float32)
+  st = o.init(q.numpy(), qd.numpy())
+  nf = workloads.N_FRAMES[model]
+  for w in range(args.warmup):
+    o.step(st, workloads.action(model, 0, n, 0, w, 'cpu').numpy(), nf)
+  acts = [workloads.action(model, 0, n, 0, 100 + k, 'cpu').numpy() for k in range(args.steps)]
+  t0 = time.perf_counter()
+  for k in range(args.steps):
+    o.step(st, acts[k], nf)
+  dt = time.perf_counter() - t0
+  val = n * args.steps / dt
+  sample = f'{n} envs x {args.steps} env-steps of {args.workload} per run (bounded sample)'
+  line = {
+      'impl': 'reference', 'metric': 'env-steps/sec', 'value': val, 'unit': 'env-steps/s', 'n_gpus': args.gpus,
+      'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
+      'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+      'config': {'workload': args.workload, 'model': model, 'envs_per_gpu': n_env, 'n_frames': nf,
+                 'note': 'CPU restatement (C oracle port), not JAX: jax/jaxopt/mujoco unavailable offline'},
+      'cpu_baseline': {'value': val, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+      'e2e': {'value': val, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+  }
+  print(json.dumps(line), flush=True)
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=20)
+  ap.add_argument('--warmup', type=int, default=3)
+  ap.add_argument('--workload', default='humanoid_8192', choices=sorted(WORKLOADS))
+  ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+  ap.add_argument('--envs', type=int, default=0, help='override envs per GPU')
+  ap.add_argument('--minv', default='newton_schulz', choices=['newton_schulz', 'cholesky'])
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--no-extra', action='store_true', help='skip the secondary workload lines')
+  args = ap.parse_args()
+  args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+
+  rank = int(os.environ.get('RANK', '0'))
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+
+  if args.impl == 'reference':
+    run_reference(args, rank, world)
+    return
+
+  import torch
+  import torch.distributed as dist
+  from brax_b200 import native, workloads
+
+  if not torch.cuda.is_available():
+    raise SystemExit('bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')
+  torch.cuda.set_device(local_rank)
+  dev = torch.device('cuda', local_rank)
+  if world > 1:
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    dist.init_process_group('nccl', device_id=dev)
+
+  def barrier():
+    if world > 1:
+      dist.barrier(device_ids=[local_rank])
+    torch.cuda.synchronize()
+
+  def max_over_ranks(x):
+    if world > 1:
+      t = torch.tensor([x], dtype=torch.float64, device=dev)
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+      return float(t.item())
+    return x
+
+  minv = native.MINV_NEWTON_SCHULZ if args.minv == 'newton_schulz' else native.MINV_CHOLESKY
+  hbm_peak, peak_src = peaks()
+  flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+  def measure(workload, steps, warmup, with_clocks):
+    model, n_env = WORKLOADS[workload]
+    if args.envs:
+      n_env = args.envs
+    nf = workloads.N_FRAMES[model]
+    begin = rank * n_env  # weak scaling: every rank has n_env envs; ids are global
+    sys_, q, qd = workloads.reset(model, begin, n_env, 0, dev)
+    nm = native.model_for(sys_, local_rank, minv)
+    a, b = nm.init(q, qd), nm.alloc(n_env)
+    acts = [workloads.action(model, begin, n_env, 0, k, dev) for k in range(min(steps + warmup, 8))]
+    state_bytes = sum(t.numel() * 4 for t in a.values())
+    flush = state_bytes < (512 << 20)
+    for w in range(warmup):
+      nm.step(a, acts[w % len(acts)], nf, out=b); a, b = b, a
+    sampler = ClockSampler(local_rank) if with_clocks else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    barrier()
+    if sampler:
+      sampler.start()
+    l0 = native.launch_count()
+    t0 = time.perf_counter()
+    for k in range(steps):
+      if flush:
+        flush_buf.fill_(k & 0xff)
+      ev[k][0].record()
+      nm.step(a, acts[(warmup + k) % len(acts)], nf, out=b)
+      ev[k][1].record()
+      a, b = b, a
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = native.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    kern_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
+    dev_ms_total = ev[0][0].elapsed_time(ev[-1][1])  # first start -> last end, on-device
+    dev_ms_total = max_over_ranks(dev_ms_total)
+    kern_avg_ms = max_over_ranks(sum(kern_ms) / len(kern_ms))
+    assert all(torch.isfinite(t).all() for t in (a['q'], a['qd'])), 'non-finite state in bench rollout'
+    total_envs = n_env * world
+    return {
+        'model': model, 'n_env': n_env, 'nf': nf, 'value': total_envs * steps / (dev_ms_total * 1e-3),
+        'ms_per_step': dev_ms_total / steps, 'kern_avg_ms': kern_avg_ms, 'wall_ms_per_step': 1e3 * wall / steps,
+        'launches': launches, 'clocks': clocks, 'flush': flush, 'nm': nm, 'state': a, 'spare': b, 'acts': acts,
+        'begin': begin,
+    }
+
+  def measure_e2e(r, steps):
+    """Same metric through the public call with HOST buffers: per step, H2D copy of
+    the actions from pinned memory, the step, D2H read of q and qd."""
+    nm, a, b = r['nm'], r['state'], r['spare']
+    n_env, nf, model = r['n_env'], r['nf'], r['model']
+    sys_ = nm.sys
+    h_act = [t.cpu().pin_memory() for t in r['acts']]
+    d_act = torch.empty_like(r['acts'][0])
+    h_q = torch.empty((n_env, sys_.nq), dtype=torch.float32).pin_memory()
+    h_qd = torch.empty((n_env, sys_.nv), dtype=torch.float32).pin_memory()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(steps):
+      d_act.copy_(h_act[k % len(h_act)], non_blocking=True)
+      nm.step(a, d_act, nf, out=b)
+      a, b = b, a
+      h_q.copy_(a['q'], non_blocking=True); h_qd.copy_(a['qd'], non_blocking=True)
+      torch.cuda.current_stream().synchronize()  # the caller consumes the result every step
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    return {'value': n_env * world * steps / (ms * 1e-3), 'unit': 'env-steps/s',
+            'h2d_bytes_per_step': n_env * sys_.nu * 4, 'd2h_bytes_per_step': n_env * (sys_.nq + sys_.nv) * 4}
+
+  r = measure(args.workload, args.steps, args.warmup, with_clocks=True)
+  e2e = measure_e2e(r, args.steps)
+  model = r['model']
+  algo_bytes = workloads.ALGO_BYTES[model] * r['n_env']          # per launch (= per rank per step)
+  achieved = algo_bytes / (r['kern_avg_ms'] * 1e-3) / 1e9
+  traffic = None
+  tp = os.path.join(ROOT, 'profiles', 'traffic.json')
+  if os.path.exists(tp):
+    with open(tp) as f:
+      tj = json.load(f)
+    if args.workload in tj:
+      traffic = tj[args.workload]['dram_bytes_per_env_step'] * r['n_env']
+
+  line = {
+      'metric': 'env-steps/sec', 'value': r['value'], 'unit': 'env-steps/s', 'n_gpus': world,
+      'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': r['ms_per_step'],
+      'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+      'config': {'workload': args.workload, 'model': model, 'envs_per_gpu': r['n_env'], 'n_frames': r['nf'],
+                 'minv': args.minv, 'parallelism': f'env-shard x{world}, no collective',
+                 'l2': 'flushed between steps (256 MiB write)' if r['flush'] else 'state >> L2, no flush'},
+      'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
+                   'traffic': traffic, 'peak_source': peak_src,
+                   'algorithmic_bytes_per_env_step': workloads.ALGO_BYTES[model],
+                   'note': 'step is FP32-FMA-bound (SURVEY 8d); see profiles/ for pipe utilisation'},
+      'e2e': e2e, 'gpu_launches': r['launches'], 'clocks': r['clocks'],
+      'kernel_ms': r['kern_avg_ms'], 'wall_ms_per_step': r['wall_ms_per_step'],
+  }
+
+  if not args.no_extra and world == 1:
+    extra = []
+    del r['state'], r['spare']
+    for wl, st_ in (('ant_1m', 5),):
+      if wl == args.workload:
+        continue
+      try:
+        torch.cuda.empty_cache()
+        x = measure(wl, st_, 3, with_clocks=False)
+        ab = workloads.ALGO_BYTES[x['model']] * x['n_env'] / (x['kern_avg_ms'] * 1e-3) / 1e9
+        extra.append({'workload': wl, 'value': x['value'], 'unit': 'env-steps/s', 'ms_per_step': x['ms_per_step'],
+                      'steps': st_, 'roofline_frac_hbm': ab / hbm_peak})
+        del x
+      except Exception as ex:  # report, do not hide
+        extra.append({'workload': wl, 'error': repr(ex)})
+    line['other_workloads'] = extra
+
+  if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    v, cores, sample = cpu_port_throughput(model, workloads.N_FRAMES[model])
+    line['cpu_baseline'] = {'value': v, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample}
+
+  if rank == 0:
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+  main()
