@@ -128,10 +128,16 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 #define BXG_CUDA(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return cuda_fail(e__, #x); } while (0)
 
-bool state_ok(const BxgState* s) {
+// every leaf must be non-null, except the constraint leaves of a model with no
+// constraint rows (their arrays have zero elements)
+bool state_ok(const BxgState* s, int nc) {
   if (!s) return false;
   const float* const* p = reinterpret_cast<const float* const*>(s);
-  for (size_t i = 0; i < sizeof(BxgState) / sizeof(float*); ++i) if (!p[i]) return false;
+  for (size_t i = 0; i < sizeof(BxgState) / sizeof(float*); ++i) {
+    const float* const* f = p + i;
+    bool con_leaf = f == (const float* const*)&s->con_jac || f == (const float* const*)&s->con_diag || f == (const float* const*)&s->con_aref;
+    if (!p[i] && !(con_leaf && nc == 0)) return false;
+  }
   return true;
 }
 }  // namespace
@@ -204,8 +210,9 @@ static int grid_for(const BxgModel* m, int64_t n_env, int blocks_per_sm) {
 }
 
 int bxg_init(const BxgModel* m, int64_t n_env, const float* q, const float* qd, const BxgState* out, void* stream) {
-  if (!m || !q || !qd || !state_ok(out)) return fail(BXG_E_INVALID, "null argument");
+  if (!m) return fail(BXG_E_INVALID, "null model");
   if (n_env <= 0) return n_env == 0 ? BXG_OK : fail(BXG_E_INVALID, "n_env < 0");
+  if (!q || !qd || !state_ok(out, m->pm.d.nc)) return fail(BXG_E_INVALID, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
   int grid = grid_for(m, n_env, m->blocks_per_sm_init);
   if (m->lanes == 16) bxg::init_kernel<16><<<grid, bxg::kThreads, m->smem_bytes, st>>>(m->pm.d, m->d_blob, q, qd, *out, n_env);
@@ -217,10 +224,11 @@ int bxg_init(const BxgModel* m, int64_t n_env, const float* q, const float* qd, 
 
 int bxg_step(const BxgModel* m, int64_t n_env, int32_t n_frames, const BxgState* in, const float* act, const BxgState* out,
              int32_t flags, const BxgDiag* diag, void* stream) {
-  if (!m || !state_ok(in) || !state_ok(out)) return fail(BXG_E_INVALID, "null argument");
-  if (m->pm.d.nu > 0 && !act) return fail(BXG_E_INVALID, "act is NULL but the model has actuators");
+  if (!m) return fail(BXG_E_INVALID, "null model");
   if (n_frames < 0) return fail(BXG_E_INVALID, "n_frames < 0");
   if (n_env <= 0) return n_env == 0 ? BXG_OK : fail(BXG_E_INVALID, "n_env < 0");
+  if (!state_ok(in, m->pm.d.nc) || !state_ok(out, m->pm.d.nc)) return fail(BXG_E_INVALID, "null argument");
+  if (m->pm.d.nu > 0 && !act) return fail(BXG_E_INVALID, "act is NULL but the model has actuators");
   BxgDiag dg{nullptr, nullptr};
   if ((flags & BXG_STEP_DIAGNOSTICS) && diag) dg = *diag;
   cudaStream_t st = (cudaStream_t)stream;
