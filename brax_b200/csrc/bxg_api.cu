@@ -1,117 +1,47 @@
-// bxg_kernels.cu -- sm_100a kernels + the C ABI declared in include/bxg.h.
-//
-// One lane-group (G = 16 or 32 lanes) per environment, whole working state in
-// shared memory, all n_frames substeps inside one launch; HBM is touched only
-// at kernel entry (load_env) and exit (store_env).  See bxg_core.cuh for the
-// algorithm and DESIGN.md for the layout and roofline accounting.
+// bxg_api.cu -- the C ABI declared in include/bxg.h: model upload, launch
+// configuration and the two launches (init, step).  Kernels live in
+// bxg_kernels.cuh and are instantiated per variant in bxg_inst.cu.
 #include <cuda_runtime.h>
 #include <stdio.h>
 
 #include <atomic>
-#include <mutex>
 #include <string>
 
-#include "bxg_core.cuh"
+#include "bxg_model.h"
 
 namespace bxg {
-
-// ------------------------------------------------------- device executor
-template <int G_>
-struct DevExec {
-  static constexpr int G = G_;
-  int lane;
-  unsigned mask;
-  struct LaneF {
-    float v;
-    __device__ __forceinline__ float& operator()(int) { return v; }
-  };
-  __device__ __forceinline__ void sync() { __syncwarp(mask); }
-  template <class F>
-  __device__ __forceinline__ void lanes(F&& f) {
-    __syncwarp(mask);
-    f(lane);
-    __syncwarp(mask);
-  }
-  __device__ __forceinline__ float sum(LaneF& p) {
-    float v = p.v;
-#pragma unroll
-    for (int o = G / 2; o >= 1; o >>= 1) v += __shfl_xor_sync(mask, v, o, G);
-    return v;
-  }
-  __device__ __forceinline__ float max(LaneF& p) {
-    float v = p.v;
-#pragma unroll
-    for (int o = G / 2; o >= 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(mask, v, o, G));
-    return v;
-  }
-};
-
-constexpr int kThreads = 128;
-
-template <int G>
-__device__ __forceinline__ DevExec<G> make_exec() {
-  DevExec<G> ex;
-  int wl = threadIdx.x & 31;
-  ex.lane = wl % G;
-  ex.mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((wl / G) * G));
-  return ex;
+constexpr int kMaxThreads = 512;          // must match bxg_kernels.cuh
+constexpr size_t kSmemBudget = 227 * 1024;  // usable shared memory per SM on sm_100
+// envs per CTA: as many as fit the shared-memory budget of one SM (one CTA per
+// SM, all of its warps phase-aligned), whole warps only
+inline int envs_per_cta(const Dims& d, int G) {
+  size_t avail = kSmemBudget - sizeof(uint32_t) * (size_t)d.model_words;
+  int n = (int)(avail / (sizeof(uint32_t) * (size_t)d.env_words));
+  int per_warp = 32 / G;
+  n -= n % per_warp;
+  int cap = kMaxThreads / G;
+  return n > cap ? cap : n;
+}
 }
 
-__device__ __forceinline__ void stage_model(const Dims& D, const uint32_t* __restrict__ model, uint32_t* smem) {
-  for (int i = threadIdx.x; i < D.model_words; i += blockDim.x) smem[i] = model[i];
-  __syncthreads();
+extern "C" {
+const void* bxg_step_kernel_v0(); const void* bxg_step_kernel_v1(); const void* bxg_step_kernel_v2(); const void* bxg_step_kernel_v3();
+const void* bxg_init_kernel_v0(); const void* bxg_init_kernel_v1(); const void* bxg_init_kernel_v2(); const void* bxg_init_kernel_v3();
+}
+static const void* step_kernel_of(int v) {
+  switch (v) { case 0: return bxg_step_kernel_v0(); case 1: return bxg_step_kernel_v1(); case 2: return bxg_step_kernel_v2(); default: return bxg_step_kernel_v3(); }
+}
+static const void* init_kernel_of(int v) {
+  switch (v) { case 0: return bxg_init_kernel_v0(); case 1: return bxg_init_kernel_v1(); case 2: return bxg_init_kernel_v2(); default: return bxg_init_kernel_v3(); }
 }
 
-template <int G>
-__global__ void __launch_bounds__(kThreads)
-step_kernel(const Dims D, const uint32_t* __restrict__ model, const BxgState in, const float* __restrict__ act,
-            const BxgState out, int64_t n_env, int n_frames, int flags, const BxgDiag diag) {
-  extern __shared__ __align__(16) uint32_t smem_u[];
-  stage_model(D, model, smem_u);
-  const int groups = kThreads / G, group = threadIdx.x / G;
-  Ctx c;
-  c.D = &D;
-  c.mf = reinterpret_cast<const float*>(smem_u);
-  c.mi = reinterpret_cast<const int*>(smem_u);
-  c.s = reinterpret_cast<float*>(smem_u) + D.model_words + group * D.env_words;
-  DevExec<G> ex = make_exec<G>();
-  for (int64_t e = (int64_t)blockIdx.x * groups + group; e < n_env; e += (int64_t)gridDim.x * groups) {
-    Stats st{0, 0, 0, 0};
-    load_env(ex, c, in, act, e);
-    for (int f = 0; f < n_frames; ++f) substep(ex, c, &st);
-    store_env(ex, c, out, e, (flags & BXG_STEP_DIAGNOSTICS) ? &diag : nullptr, st);
-  }
-}
-
-template <int G>
-__global__ void __launch_bounds__(kThreads)
-init_kernel(const Dims D, const uint32_t* __restrict__ model, const float* __restrict__ q, const float* __restrict__ qd,
-            const BxgState out, int64_t n_env) {
-  extern __shared__ __align__(16) uint32_t smem_u[];
-  stage_model(D, model, smem_u);
-  const int groups = kThreads / G, group = threadIdx.x / G;
-  Ctx c;
-  c.D = &D;
-  c.mf = reinterpret_cast<const float*>(smem_u);
-  c.mi = reinterpret_cast<const int*>(smem_u);
-  c.s = reinterpret_cast<float*>(smem_u) + D.model_words + group * D.env_words;
-  DevExec<G> ex = make_exec<G>();
-  for (int64_t e = (int64_t)blockIdx.x * groups + group; e < n_env; e += (int64_t)gridDim.x * groups) {
-    Stats st{0, 0, 0, 0};
-    load_env_qqd(ex, c, q, qd, e);
-    init_env(ex, c, &st);
-    store_env(ex, c, out, e, nullptr, st);
-  }
-}
-
-}  // namespace bxg
-
-// ============================================================== C ABI
 struct BxgModel {
   bxg::PackedModel pm;
   int device = 0;
   int lanes = 32;          // G
   int sm_count = 0;
+  int groups = 0;          // envs per CTA
+  int threads = 0;         // CTA size
   uint32_t* d_blob = nullptr;
   size_t smem_bytes = 0;
   int blocks_per_sm_step = 1, blocks_per_sm_init = 1;
@@ -160,8 +90,8 @@ int bxg_model_create(const BxgModelDesc* desc, int device, BxgModel** out) {
   if (device < 0 || device >= ndev) { delete m; return fail(BXG_E_INVALID, "bad device ordinal"); }
   m->device = device;
   const bxg::Dims& D = m->pm.d;
-  // half-warp groups when the tree fits 16 lanes (Ant), else full warps
-  m->lanes = (D.L <= 16 && D.nv <= 16) ? 16 : 32;
+  // half-warp groups when the model fits the 16-lane variant (Ant), else full warps
+  m->lanes = bxg::variant(m->pm.variant_id).G;
   int prev = 0;
   cudaGetDevice(&prev);
   auto cleanup = [&](int code) { cudaSetDevice(prev); if (m->d_blob) cudaFree(m->d_blob); delete m; return code; };
@@ -169,19 +99,21 @@ int bxg_model_create(const BxgModelDesc* desc, int device, BxgModel** out) {
   cudaDeviceProp prop;
   if ((ce = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cleanup(cuda_fail(ce, "cudaGetDeviceProperties"));
   m->sm_count = prop.multiProcessorCount;
-  const int groups = bxg::kThreads / m->lanes;
+  const int groups = bxg::envs_per_cta(D, m->lanes);
+  if (groups < 1) return cleanup(fail(BXG_E_UNSUPPORTED, "one env does not fit the shared memory of an SM"));
+  m->groups = groups; m->threads = groups * m->lanes;
   m->smem_bytes = sizeof(uint32_t) * ((size_t)D.model_words + (size_t)groups * D.env_words);
   if (m->smem_bytes > (size_t)prop.sharedMemPerBlockOptin)
     return cleanup(fail(BXG_E_UNSUPPORTED, "model needs more shared memory per CTA than the device offers"));
   if ((ce = cudaMalloc(&m->d_blob, m->pm.blob.size() * sizeof(uint32_t))) != cudaSuccess) return cleanup(cuda_fail(ce, "cudaMalloc(model)"));
   if ((ce = cudaMemcpy(m->d_blob, m->pm.blob.data(), m->pm.blob.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess)
     return cleanup(cuda_fail(ce, "cudaMemcpy(model)"));
-  const void* ks = m->lanes == 16 ? (const void*)bxg::step_kernel<16> : (const void*)bxg::step_kernel<32>;
-  const void* ki = m->lanes == 16 ? (const void*)bxg::init_kernel<16> : (const void*)bxg::init_kernel<32>;
+  const void* ks = step_kernel_of(m->pm.variant_id);
+  const void* ki = init_kernel_of(m->pm.variant_id);
   if ((ce = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_bytes)) != cudaSuccess) return cleanup(cuda_fail(ce, "cudaFuncSetAttribute(step)"));
   if ((ce = cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_bytes)) != cudaSuccess) return cleanup(cuda_fail(ce, "cudaFuncSetAttribute(init)"));
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m->blocks_per_sm_step, ks, bxg::kThreads, m->smem_bytes);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m->blocks_per_sm_init, ki, bxg::kThreads, m->smem_bytes);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m->blocks_per_sm_step, ks, m->threads, m->smem_bytes);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m->blocks_per_sm_init, ki, m->threads, m->smem_bytes);
   if (m->blocks_per_sm_step < 1 || m->blocks_per_sm_init < 1) return cleanup(fail(BXG_E_UNSUPPORTED, "kernel does not fit on an SM"));
   cudaSetDevice(prev);
   *out = m;
@@ -202,8 +134,20 @@ void bxg_model_destroy(BxgModel* m) {
 
 int bxg_model_num_constraints(const BxgModel* m) { return m ? m->pm.d.nc : -1; }
 
+int bxg_plan(const BxgModelDesc* desc, int32_t info[8]) {
+  if (!desc || !info) return fail(BXG_E_INVALID, "null argument");
+  bxg::PackedModel pm;
+  std::string err = bxg::pack_model(*desc, &pm);
+  if (!err.empty()) return fail(BXG_E_UNSUPPORTED, err);
+  const int G = bxg::variant(pm.variant_id).G, groups = bxg::envs_per_cta(pm.d, G);
+  info[0] = pm.variant_id; info[1] = G; info[2] = pm.d.model_words; info[3] = pm.d.env_words; info[4] = groups;
+  info[5] = (int32_t)(sizeof(uint32_t) * ((size_t)pm.d.model_words + (size_t)groups * pm.d.env_words));
+  info[6] = pm.d.nc; info[7] = 0;
+  return BXG_OK;
+}
+
 static int grid_for(const BxgModel* m, int64_t n_env, int blocks_per_sm) {
-  const int groups = bxg::kThreads / m->lanes;
+  const int groups = m->groups;
   int64_t need = (n_env + groups - 1) / groups;
   int64_t cap = (int64_t)m->sm_count * blocks_per_sm;
   return (int)(need < cap ? need : cap);
@@ -215,8 +159,8 @@ int bxg_init(const BxgModel* m, int64_t n_env, const float* q, const float* qd, 
   if (!q || !qd || !state_ok(out, m->pm.d.nc)) return fail(BXG_E_INVALID, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
   int grid = grid_for(m, n_env, m->blocks_per_sm_init);
-  if (m->lanes == 16) bxg::init_kernel<16><<<grid, bxg::kThreads, m->smem_bytes, st>>>(m->pm.d, m->d_blob, q, qd, *out, n_env);
-  else bxg::init_kernel<32><<<grid, bxg::kThreads, m->smem_bytes, st>>>(m->pm.d, m->d_blob, q, qd, *out, n_env);
+  void* args[] = {(void*)&m->pm.d, (void*)&m->d_blob, (void*)&q, (void*)&qd, (void*)out, (void*)&n_env};
+  BXG_CUDA(cudaLaunchKernel(init_kernel_of(m->pm.variant_id), dim3(grid), dim3(m->threads), args, m->smem_bytes, st));
   g_launches.fetch_add(1);
   BXG_CUDA(cudaGetLastError());
   return BXG_OK;
@@ -233,8 +177,9 @@ int bxg_step(const BxgModel* m, int64_t n_env, int32_t n_frames, const BxgState*
   if ((flags & BXG_STEP_DIAGNOSTICS) && diag) dg = *diag;
   cudaStream_t st = (cudaStream_t)stream;
   int grid = grid_for(m, n_env, m->blocks_per_sm_step);
-  if (m->lanes == 16) bxg::step_kernel<16><<<grid, bxg::kThreads, m->smem_bytes, st>>>(m->pm.d, m->d_blob, *in, act, *out, n_env, n_frames, flags, dg);
-  else bxg::step_kernel<32><<<grid, bxg::kThreads, m->smem_bytes, st>>>(m->pm.d, m->d_blob, *in, act, *out, n_env, n_frames, flags, dg);
+  int nf = n_frames, fl = flags;
+  void* args[] = {(void*)&m->pm.d, (void*)&m->d_blob, (void*)in, (void*)&act, (void*)out, (void*)&n_env, (void*)&nf, (void*)&fl, (void*)&dg};
+  BXG_CUDA(cudaLaunchKernel(step_kernel_of(m->pm.variant_id), dim3(grid), dim3(m->threads), args, m->smem_bytes, st));
   g_launches.fetch_add(1);
   BXG_CUDA(cudaGetLastError());
   return BXG_OK;

@@ -42,6 +42,11 @@ namespace bxg {
 struct V3 { float x, y, z; };
 struct Q4 { float w, x, y, z; };
 
+struct alignas(16) F4 { float x, y, z, w; };
+// 128-bit shared-memory access (LDS.128 / STS.128 on device); p must be 16-byte aligned
+BXG_HD F4 ldv4(const float* p) { return *reinterpret_cast<const F4*>(p); }
+BXG_HD void stv4(float* p, F4 v) { *reinterpret_cast<F4*>(p) = v; }
+
 BXG_HD V3 ld3(const float* p) { return V3{p[0], p[1], p[2]}; }
 BXG_HD void st3(float* p, V3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
 BXG_HD Q4 ld4(const float* p) { return Q4{p[0], p[1], p[2], p[3]}; }
@@ -104,6 +109,15 @@ struct Ctx {
 };
 
 struct Stats { int pg_iters, pg_trials, ns_accepts, ns_cold; };
+
+// Compile-time kernel configuration: lanes per env and register-row widths.
+// GENERIC_TOO keeps the any-size code reachable next to the specialised kernels
+// (host emulator only: the CPU tests compare the two); device variants drop it.
+template <int G_, int VC4_, int NC4_, bool GENERIC_TOO_ = false>
+struct KernelCfg {
+  static constexpr int G = G_, VC4 = VC4_, NC4 = NC4_;
+  static constexpr bool GENERIC_TOO = GENERIC_TOO_ || VC4_ == 0;
+};
 
 // constraint._imp_aref (brax/generalized/constraint.py:29-65)
 BXG_HD void imp_aref(const float* prm, float pos, float vel, float* imp_out, float* aref_out) {
@@ -198,7 +212,7 @@ BXG_HD void dyn_forces(X& ex, const Ctx& c) {
 
 // --------------------------------------- constraint.force + projected gradient
 template <class X>
-BXG_HD void con_force(X& ex, const Ctx& c, Stats* st) {
+BXG_HD void con_force_generic(X& ex, const Ctx& c, Stats* st) {
   const Dims& D = *c.D; float* s = c.s;
   const int nv = D.nv, nc = D.nc, nvp = D.nvp, ncp = D.ncp;
   if (nc == 0) {
@@ -621,7 +635,7 @@ BXG_HD void mass_matrix(X& ex, const Ctx& c) {
 
 // ------------------------------------------------------ math.inv_approximate
 template <class X>
-BXG_HD void minv_newton_schulz(X& ex, const Ctx& c, Stats* st) {
+BXG_HD void minv_newton_schulz_generic(X& ex, const Ctx& c, Stats* st) {
   const Dims& D = *c.D; float* s = c.s;
   const int n = D.nv, nvp = D.nvp;
   const float* M = s + D.s_M;
@@ -692,6 +706,372 @@ BXG_HD void minv_newton_schulz(X& ex, const Ctx& c, Stats* st) {
     }
     err = err_next;
   }
+}
+
+
+// ===================================================== register-row kernels
+// Lane i owns row i of the left operand in registers; the right operand's rows
+// are broadcast from shared memory with 128-bit loads (all lanes of the group
+// read the same address: one wavefront), so one LDS.128 feeds four FFMA per lane.
+// acc[0..4*C4) = sum_k a[k] * B[k][0..4*C4), k ascending (same order as the oracle).
+template <int K, int C4>
+BXG_HD void row_times_mat(const float* a, const float* B, int ldb, float* acc) {
+#pragma unroll
+  for (int j = 0; j < 4 * C4; ++j) acc[j] = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const float ak = a[k];
+#pragma unroll
+    for (int cc = 0; cc < C4; ++cc) {
+      F4 b = ldv4(B + k * ldb + 4 * cc);
+      acc[4 * cc + 0] += ak * b.x; acc[4 * cc + 1] += ak * b.y;
+      acc[4 * cc + 2] += ak * b.z; acc[4 * cc + 3] += ak * b.w;
+    }
+  }
+}
+template <int C4>
+BXG_HD void load_row(const float* p, float* r) {
+#pragma unroll
+  for (int cc = 0; cc < C4; ++cc) { F4 v = ldv4(p + 4 * cc); r[4 * cc] = v.x; r[4 * cc + 1] = v.y; r[4 * cc + 2] = v.z; r[4 * cc + 3] = v.w; }
+}
+template <int C4>
+BXG_HD void store_row(float* p, const float* r) {
+#pragma unroll
+  for (int cc = 0; cc < C4; ++cc) stv4(p + 4 * cc, F4{r[4 * cc], r[4 * cc + 1], r[4 * cc + 2], r[4 * cc + 3]});
+}
+// dot of a register row with a shared-memory vector (broadcast 128-bit loads)
+template <int C4>
+BXG_HD float row_dot(const float* a, const float* v) {
+  float acc = 0.f;
+#pragma unroll
+  for (int cc = 0; cc < C4; ++cc) {
+    F4 b = ldv4(v + 4 * cc);
+    acc += a[4 * cc] * b.x; acc += a[4 * cc + 1] * b.y; acc += a[4 * cc + 2] * b.z; acc += a[4 * cc + 3] * b.w;
+  }
+  return acc;
+}
+
+// ---- 2-D register tiles for the Newton-Schulz products -----------------------
+// A G-lane group computes C[W x W] = A * B with both operands in shared memory
+// (row-major, stride ld) and a TM x TN tile of C per lane.  Per 4 k-steps a lane
+// issues TM 128-bit loads of A and 4*TN/2 64-bit (or TN/4 128-bit) loads of B for
+// 4*TM*TN FFMA, which balances the shared-memory pipe against the FMA pipe; the
+// k loop stays rolled so the body lives in the instruction cache.
+template <int G, int W> struct Tile;
+template <> struct Tile<32, 24> { static constexpr int RG = 8, CG = 4, TM = 3, TN = 6; };
+template <> struct Tile<16, 16> { static constexpr int RG = 4, CG = 4, TM = 4, TN = 4; };
+template <> struct Tile<32, 32> { static constexpr int RG = 8, CG = 4, TM = 4, TN = 8; };
+struct alignas(8) F2 { float x, y; };
+
+template <int TN>
+BXG_HD void load_cols(const float* p, float* v) {
+  if constexpr (TN % 4 == 0) {
+#pragma unroll
+    for (int c = 0; c < TN / 4; ++c) { F4 t = ldv4(p + 4 * c); v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w; }
+  } else {
+#pragma unroll
+    for (int c = 0; c < TN / 2; ++c) { F2 t = *reinterpret_cast<const F2*>(p + 2 * c); v[2 * c] = t.x; v[2 * c + 1] = t.y; }
+  }
+}
+template <int TN>
+BXG_HD void store_cols(float* p, const float* v) {
+  if constexpr (TN % 4 == 0) {
+#pragma unroll
+    for (int c = 0; c < TN / 4; ++c) stv4(p + 4 * c, F4{v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]});
+  } else {
+#pragma unroll
+    for (int c = 0; c < TN / 2; ++c) *reinterpret_cast<F2*>(p + 2 * c) = F2{v[2 * c], v[2 * c + 1]};
+  }
+}
+
+// acc[r][c] = sum_k A[row0 + r][k] * B[k][col0 + c], k ascending
+template <class T, int W>
+BXG_HD void tile_matmul(int lane, const float* A, const float* B, int ld, float (&acc)[T::TM][T::TN]) {
+  const int rg = lane / T::CG, cg = lane - rg * T::CG;
+  const float* a0 = A + rg * T::TM * ld;
+  const float* b0 = B + cg * T::TN;
+#pragma unroll
+  for (int r = 0; r < T::TM; ++r)
+#pragma unroll
+    for (int cc = 0; cc < T::TN; ++cc) acc[r][cc] = 0.f;
+#pragma unroll 1
+  for (int k0 = 0; k0 < W; k0 += 4) {
+    F4 a[T::TM];
+#pragma unroll
+    for (int r = 0; r < T::TM; ++r) a[r] = ldv4(a0 + r * ld + k0);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      float bv[T::TN];
+      load_cols<T::TN>(b0 + (k0 + kk) * ld, bv);
+#pragma unroll
+      for (int r = 0; r < T::TM; ++r) {
+        const float av = kk == 0 ? a[r].x : kk == 1 ? a[r].y : kk == 2 ? a[r].z : a[r].w;
+#pragma unroll
+        for (int cc = 0; cc < T::TN; ++cc) acc[r][cc] += av * bv[cc];
+      }
+    }
+  }
+}
+
+// residual tile r = I - acc (identity only on real rows), accumulates the
+// Frobenius partials and overwrites acc with I + r for the next product
+template <class T>
+BXG_HD void residual_tile(int lane, int n, float (&acc)[T::TM][T::TN], float* ss, float* mx) {
+  const int rg = lane / T::CG, cg = lane - rg * T::CG;
+#pragma unroll
+  for (int r = 0; r < T::TM; ++r)
+#pragma unroll
+    for (int cc = 0; cc < T::TN; ++cc) {
+      const int i = rg * T::TM + r, j = cg * T::TN + cc;
+      const bool diag = i == j && i < n;
+      float res = (diag ? 1.f : 0.f) - acc[r][cc];
+      *ss += res * res; *mx = fmaxf(*mx, fabsf(res));
+      acc[r][cc] = diag ? 1.f + res : res;
+    }
+}
+template <class T>
+BXG_HD void store_tile(int lane, float* C, int ld, const float (&acc)[T::TM][T::TN]) {
+  const int rg = lane / T::CG, cg = lane - rg * T::CG;
+#pragma unroll
+  for (int r = 0; r < T::TM; ++r) store_cols<T::TN>(C + (rg * T::TM + r) * ld + cg * T::TN, acc[r]);
+}
+
+// math.inv_approximate (brax/math.py:278-305) on W x W zero-padded matrices.
+template <class X, int W>
+BXG_HD void minv_newton_schulz_tiles(X& ex, const Ctx& c, Stats* st) {
+  using T = Tile<X::G, W>;
+  const Dims& D = *c.D; float* s = c.s;
+  const int n = D.nv, ld = D.nvp;
+  const float* M = s + D.s_M;
+  float* Xa = s + D.s_Minv;
+  float* Xc = Xa;                      // current estimate
+  float* Xn = s + D.s_scr;             // candidate
+  float* B = s + D.s_scr + W * ld;     // I + r
+  typename X::LaneF p_sum, p_max;
+  // r0 = I - M X
+  ex.lanes([&](int lane) {
+    float acc[T::TM][T::TN], ss = 0.f, mx = 0.f;
+    tile_matmul<T, W>(lane, M, Xc, ld, acc);
+    residual_tile<T>(lane, n, acc, &ss, &mx);
+    store_tile<T>(lane, B, ld, acc);
+    p_sum(lane) = ss; p_max(lane) = mx;
+  });
+  float ss0 = ex.sum(p_sum), mx0 = ex.max(p_max);
+  float nrm0 = mx0 <= 1e-8f ? 0.f : sqrtf(ss0);
+  if (nrm0 > 1.f) {
+    // cold start 0.5 M^T / tr(M M^T); M is exactly symmetric
+    ex.lanes([&](int lane) {
+      float tr = 0.f;
+      for (int i = lane; i < W * ld; i += X::G) tr += M[i] * M[i];
+      p_sum(lane) = tr;
+    });
+    float tr = ex.sum(p_sum);
+    ex.lanes([&](int lane) { for (int i = lane; i < W * ld; i += X::G) Xc[i] = 0.5f * M[i] / tr; });
+    st->ns_cold++;
+  }
+  float err = 1.f;
+  for (int it = 0; it < D.ns_iters; ++it) {
+    ex.lanes([&](int lane) {       // candidate = X (I + r)
+      float acc[T::TM][T::TN];
+      tile_matmul<T, W>(lane, Xc, B, ld, acc);
+      store_tile<T>(lane, Xn, ld, acc);
+    });
+    ex.lanes([&](int lane) {       // r' = I - M candidate
+      float acc[T::TM][T::TN], ss = 0.f, mx = 0.f;
+      tile_matmul<T, W>(lane, M, Xn, ld, acc);
+      residual_tile<T>(lane, n, acc, &ss, &mx);
+      store_tile<T>(lane, B, ld, acc);
+      p_sum(lane) = ss; p_max(lane) = mx;
+    });
+    float s2 = ex.sum(p_sum), m2 = ex.max(p_max);
+    float err_next = m2 <= 1e-8f ? 0.f : sqrtf(s2);
+    if (err_next < err) { float* t = Xc; Xc = Xn; Xn = t; st->ns_accepts++; }
+    err = err_next;
+  }
+  if (Xc != Xa) ex.lanes([&](int lane) { for (int i = lane; i < W * ld; i += X::G) Xa[i] = Xc[i]; });
+}
+
+template <class X, class Cfg>
+BXG_HD void minv_newton_schulz(X& ex, const Ctx& c, Stats* st) {
+  if constexpr (Cfg::VC4 > 0) {
+    if (!Cfg::GENERIC_TOO || !c.D->force_generic) { minv_newton_schulz_tiles<X, 4 * Cfg::VC4>(ex, c, st); return; }
+  }
+  if constexpr (Cfg::GENERIC_TOO) minv_newton_schulz_generic(ex, c, st);
+}
+
+// constraint.force with register rows.  VC4 = nvw/4, NC4 = ncw/4, R rows of A per
+// lane (row i = lane + r*G).  Shared scratch: Jt [nvw][ncp] (J transposed, zero
+// padded) and A [nc][ncp]; solver vectors [ncw] with zero padding.
+template <class X, int VC4, int NC4, int R>
+BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
+  constexpr int VW = 4 * VC4, CW = 4 * NC4, G = X::G;
+  const Dims& D = *c.D; float* s = c.s;
+  const int nv = D.nv, nc = D.nc, ldv = D.nvp, ldc = D.ncp;
+  const float* J = s + D.s_J; const float* Mi = s + D.s_Minv;
+  float* Jt = s + D.s_scr; float* A = s + D.s_scr + VW * ldc;
+  float* xs = s + D.s_px; float* ys = s + D.s_py; float* ress = s + D.s_pres; float* xns = s + D.s_pxn;
+  typename X::template LaneVec<R * CW> arow;
+  typename X::template LaneVec<R> bi, xi, yi, gi, xni, resi;
+  typename X::LaneF p0, p1, p2;
+  ex.lanes([&](int lane) {
+    for (int i = lane; i < VW * ldc; i += G) Jt[i] = 0.f;
+  });
+  // Jt, then A = (J Minv) J^T + diag and b = (J Minv) qf_smooth - aref
+  ex.lanes([&](int lane) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      int i = lane + r * G;
+      if (i < nc) {
+        float jrow[VW];
+        load_row<VC4>(J + i * ldv, jrow);
+#pragma unroll
+        for (int k = 0; k < VW; ++k) Jt[k * ldc + i] = jrow[k];
+      }
+    }
+  });
+  ex.lanes([&](int lane) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      int i = lane + r * G;
+      float* ar = arow(lane) + r * CW;
+      if (i < nc) {
+        float jrow[VW], jm[VW];
+        load_row<VC4>(J + i * ldv, jrow);
+        row_times_mat<VW, VC4>(jrow, Mi, ldv, jm);
+        row_times_mat<VW, NC4>(jm, Jt, ldc, ar);
+        float bacc = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < VC4; ++cc) {
+          F4 f = ldv4(s + D.s_qfs + 4 * cc);
+          bacc += jm[4 * cc] * f.x; bacc += jm[4 * cc + 1] * f.y; bacc += jm[4 * cc + 2] * f.z; bacc += jm[4 * cc + 3] * f.w;
+        }
+#pragma unroll
+        for (int j = 0; j < CW; ++j) if (j == i) ar[j] += s[D.s_diag + i];
+        bi(lane)[r] = bacc - s[D.s_aref + i];
+        store_row<NC4>(A + i * ldc, ar);
+        xs[i] = 0.f; ys[i] = 0.f;
+      } else {
+#pragma unroll
+        for (int j = 0; j < CW; ++j) ar[j] = 0.f;
+        bi(lane)[r] = 0.f;
+      }
+      xi(lane)[r] = 0.f; yi(lane)[r] = 0.f; gi(lane)[r] = 0.f; xni(lane)[r] = 0.f; resi(lane)[r] = 0.f;
+    }
+  });
+  float t = 1.f, stepsize = 1.f, error = INFINITY;
+  const float tol = 1e-3f, eps = 1.1920929e-07f;
+  int it = 0;
+  while (it < D.solver_iterations && (it == 0 || error > tol)) {
+    // value and gradient at y
+    ex.lanes([&](int lane) {
+      float f = 0.f;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        int i = lane + r * G;
+        if (i < nc) {
+          float rv = row_dot<NC4>(arow(lane) + r * CW, ys) + bi(lane)[r];
+          ress[i] = rv;
+          f += 0.5f * (rv * rv);
+        }
+      }
+      p0(lane) = f;
+    });
+    float fy = ex.sum(p0);
+    ex.lanes([&](int lane) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        int j = lane + r * G;
+        if (j < nc) {
+          float acc = 0.f;
+          for (int i = 0; i < nc; ++i) acc += A[i * ldc + j] * ress[i];
+          gi(lane)[r] = acc;
+        }
+      }
+    });
+    float sz = stepsize;
+    for (int ls = 0;; ++ls) {
+      ex.lanes([&](int lane) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          int i = lane + r * G;
+          if (i < nc) { float v = fmaxf(yi(lane)[r] - sz * gi(lane)[r], 0.f); xni(lane)[r] = v; xns[i] = v; }
+        }
+      });
+      ex.lanes([&](int lane) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          int i = lane + r * G;
+          if (i < nc) {
+            float rv = row_dot<NC4>(arow(lane) + r * CW, xns) + bi(lane)[r];
+            resi(lane)[r] = rv;
+            float dlt = xni(lane)[r] - yi(lane)[r];
+            a0 += dlt * dlt; a1 += dlt * gi(lane)[r]; a2 += 0.5f * (rv * rv);
+          }
+        }
+        p0(lane) = a0; p1(lane) = a1; p2(lane) = a2;
+      });
+      float sqdist = ex.sum(p0), vd = ex.sum(p1), fn = ex.sum(p2);
+      st->pg_trials++;
+      float fun_decrease = sz * (fn - fy);
+      float condition = sz * vd + 0.5f * sqdist;
+      if (!(fun_decrease > condition + eps) || ls >= D.solver_maxls) break;
+      sz = sz * 0.5f;
+    }
+    stepsize = sz <= 1e-6f ? 1.f : sz / 0.5f;
+    float tn = 0.5f * (1.f + sqrtf(1.f + 4.f * (t * t)));
+    float mom = (t - 1.f) / tn;
+    ex.lanes([&](int lane) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) { int i = lane + r * G; if (i < nc) ress[i] = resi(lane)[r]; }
+    });
+    ex.lanes([&](int lane) {
+      float e2 = 0.f;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        int j = lane + r * G;
+        if (j < nc) {
+          float acc = 0.f;
+          for (int i = 0; i < nc; ++i) acc += A[i * ldc + j] * ress[i];
+          float xn = xni(lane)[r];
+          float dlt = fmaxf(xn - acc, 0.f) - xn;
+          e2 += dlt * dlt;
+          float yv = xn + mom * (xn - xi(lane)[r]);
+          yi(lane)[r] = yv; ys[j] = yv;
+          xi(lane)[r] = xn; xs[j] = xn;
+        }
+      }
+      p0(lane) = e2;
+    });
+    error = sqrtf(ex.sum(p0));
+    t = tn;
+    ++it;
+    st->pg_iters++;
+  }
+  // qf_constraint = J^T x: lane j owns row j of Jt
+  ex.lanes([&](int lane) {
+    for (int j = lane; j < nv; j += G) {
+      float jt[CW];
+      load_row<NC4>(Jt + j * ldc, jt);
+      s[D.s_qfc + j] = row_dot<NC4>(jt, xs);
+    }
+  });
+}
+
+template <class X, class Cfg>
+BXG_HD void con_force(X& ex, const Ctx& c, Stats* st) {
+  const Dims& D = *c.D;
+  if (D.nc == 0) {
+    ex.lanes([&](int lane) { for (int d = lane; d < D.nv; d += X::G) c.s[D.s_qfc + d] = 0.f; });
+    return;
+  }
+  if constexpr (Cfg::VC4 > 0 && Cfg::NC4 > 0) {
+    if (!Cfg::GENERIC_TOO || !D.force_generic) {
+      con_force_rows<X, Cfg::VC4, Cfg::NC4, (4 * Cfg::NC4 + X::G - 1) / X::G>(ex, c, st);
+      return;
+    }
+  }
+  if constexpr (Cfg::GENERIC_TOO) con_force_generic(ex, c, st);
 }
 
 // ------------------------------------------------------- constraint.jacobian
@@ -768,34 +1148,56 @@ BXG_HD void con_jacobian(X& ex, const Ctx& c) {
 }
 
 // ------------------------------------------------------------------ pipeline
-template <class X>
+template <class X, class Cfg>
 BXG_HD void update_position_terms(X& ex, const Ctx& c, Stats* st, bool exact_inverse) {
+  ex.cta_sync();
   kinematics(ex, c);
   transform_com(ex, c);
+  ex.cta_sync();
   mass_matrix(ex, c);
+  ex.cta_sync();
   if (exact_inverse) spd_inverse(ex, c, c.s + c.D->s_M, c.s + c.D->s_Minv, c.s + c.D->s_scr, nullptr, 0.f);
-  else minv_newton_schulz(ex, c, st);
+  else minv_newton_schulz<X, Cfg>(ex, c, st);
+  ex.cta_sync();
   con_jacobian(ex, c);
 }
 
 // pipeline.step (pipeline.py:78-94)
-template <class X>
+template <class X, class Cfg>
 BXG_HD void substep(X& ex, const Ctx& c, Stats* st) {
+  ex.cta_sync();
   dyn_forces(ex, c);
-  con_force(ex, c, st);
+  ex.cta_sync();
+  con_force<X, Cfg>(ex, c, st);
+  ex.cta_sync();
   integrate(ex, c);
-  update_position_terms(ex, c, st, c.D->ns_iters == 0 || c.D->minv_mode == BXG_MINV_CHOLESKY);
+  update_position_terms<X, Cfg>(ex, c, st, c.D->ns_iters == 0 || c.D->minv_mode == BXG_MINV_CHOLESKY);
 }
 
 // pipeline.init (pipeline.py:51-61); q, qd already in the slab
-template <class X>
+template <class X, class Cfg>
 BXG_HD void init_env(X& ex, const Ctx& c, Stats* st) {
   const Dims& D = *c.D; float* s = c.s;
   ex.lanes([&](int lane) {
     for (int i = lane; i < D.nv; i += X::G) { s[D.s_qfs + i] = 0.f; s[D.s_qfc + i] = 0.f; s[D.s_qdd + i] = 0.f; }
     for (int i = lane; i < (D.nc > 0 ? D.nc : 1) * D.nvp; i += X::G) s[D.s_J + i] = 0.f;
   });
-  update_position_terms(ex, c, st, true);
+  update_position_terms<X, Cfg>(ex, c, st, true);
+}
+
+// Zeroes every region whose padding the register-row kernels rely on (rows and
+// columns past nv / nc are read by compile-time-width loops and must contribute 0).
+template <class X>
+BXG_HD void prepare_env(X& ex, const Ctx& c) {
+  const Dims& D = *c.D; float* s = c.s;
+  const int ncz = D.nc > 0 ? D.nc : 1;
+  ex.lanes([&](int lane) {
+    const int G = X::G;
+    for (int i = lane; i < D.nvw * D.nvp; i += G) { s[D.s_M + i] = 0.f; s[D.s_Minv + i] = 0.f; }
+    for (int i = lane; i < ncz * D.nvp; i += G) s[D.s_J + i] = 0.f;
+    for (int i = lane; i < D.nvw; i += G) { s[D.s_tau + i] = 0.f; s[D.s_qfs + i] = 0.f; s[D.s_qfc + i] = 0.f; s[D.s_qdd + i] = 0.f; }
+    for (int i = lane; i < D.ncw; i += G) { s[D.s_b + i] = 0.f; s[D.s_px + i] = 0.f; s[D.s_py + i] = 0.f; s[D.s_pg + i] = 0.f; s[D.s_pres + i] = 0.f; s[D.s_pxn + i] = 0.f; }
+  });
 }
 
 // ------------------------------------------------------- global <-> slab I/O

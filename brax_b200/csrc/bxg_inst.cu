@@ -1,0 +1,25 @@
+// bxg_inst.cu -- one kernel variant per translation unit (-DBXG_VARIANT=k) so
+// the variants compile in parallel.  Exposes the two entry points of variant k
+// to bxg_api.cu as plain function pointers.
+#include "bxg_kernels.cuh"
+
+#ifndef BXG_VARIANT
+#error "compile with -DBXG_VARIANT=0..3"
+#endif
+
+namespace {
+#if BXG_VARIANT == 0
+using Cfg = bxg::KernelCfg<16, 4, 6>;
+#elif BXG_VARIANT == 1
+using Cfg = bxg::KernelCfg<32, 6, 7>;
+#elif BXG_VARIANT == 2
+using Cfg = bxg::KernelCfg<32, 8, 8>;
+#else
+using Cfg = bxg::KernelCfg<32, 0, 0>;
+#endif
+}  // namespace
+
+#define BXG_CAT2(a, b) a##b
+#define BXG_CAT(a, b) BXG_CAT2(a, b)
+extern "C" const void* BXG_CAT(bxg_step_kernel_v, BXG_VARIANT)() { return (const void*)bxg::step_kernel<Cfg>; }
+extern "C" const void* BXG_CAT(bxg_init_kernel_v, BXG_VARIANT)() { return (const void*)bxg::init_kernel<Cfg>; }

@@ -1,0 +1,128 @@
+// bxg_kernels.cuh -- sm_100a kernel templates (instantiated per variant by
+// bxg_inst.cu; the C ABI that launches them is bxg_api.cu).
+//
+// One lane-group (G = 16 or 32 lanes) per environment, whole working state in
+// shared memory, all n_frames substeps inside one launch; HBM is touched only
+// at kernel entry (load_env) and exit (store_env).  See bxg_core.cuh for the
+// algorithm and DESIGN.md for the layout and roofline accounting.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "bxg_core.cuh"
+
+namespace bxg {
+
+// ------------------------------------------------------- device executor
+template <int G_>
+struct DevExec {
+  static constexpr int G = G_;
+  int lane;
+  unsigned mask;
+  struct LaneF {
+    float v;
+    __device__ __forceinline__ float& operator()(int) { return v; }
+  };
+  template <int N>
+  struct LaneVec {   // per-lane register array that persists across lanes() calls
+    float v[N];
+    __device__ __forceinline__ float* operator()(int) { return v; }
+  };
+  __device__ __forceinline__ void sync() { __syncwarp(mask); }
+  // CTA-wide phase alignment: every warp of the CTA streams the same straight-line
+  // code at the same time, so instruction-cache lines are fetched once per CTA
+  __device__ __forceinline__ void cta_sync() { __syncthreads(); }
+  template <class F>
+  __device__ __forceinline__ void lanes(F&& f) {
+    __syncwarp(mask);
+    f(lane);
+    __syncwarp(mask);
+  }
+  __device__ __forceinline__ float sum(LaneF& p) {
+    float v = p.v;
+#pragma unroll
+    for (int o = G / 2; o >= 1; o >>= 1) v += __shfl_xor_sync(mask, v, o, G);
+    return v;
+  }
+  __device__ __forceinline__ float max(LaneF& p) {
+    float v = p.v;
+#pragma unroll
+    for (int o = G / 2; o >= 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(mask, v, o, G));
+    return v;
+  }
+};
+
+constexpr int kMaxThreads = 512;   // CTA size is chosen per model at run time (bxg_api.cu)
+
+template <int G>
+__device__ __forceinline__ DevExec<G> make_exec() {
+  DevExec<G> ex;
+  int wl = threadIdx.x & 31;
+  ex.lane = wl % G;
+  ex.mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((wl / G) * G));
+  return ex;
+}
+
+__device__ __forceinline__ void stage_model(const Dims& D, const uint32_t* __restrict__ model, uint32_t* smem) {
+  for (int i = threadIdx.x; i < D.model_words; i += blockDim.x) smem[i] = model[i];
+  __syncthreads();
+}
+
+template <class Cfg>
+__global__ void __launch_bounds__(kMaxThreads)
+step_kernel(const Dims D, const uint32_t* __restrict__ model, const BxgState in, const float* __restrict__ act,
+            const BxgState out, int64_t n_env, int n_frames, int flags, const BxgDiag diag) {
+  extern __shared__ __align__(16) uint32_t smem_u[];
+  constexpr int G = Cfg::G;
+  stage_model(D, model, smem_u);
+  const int groups = blockDim.x / G, group = threadIdx.x / G;
+  Ctx c;
+  c.D = &D;
+  c.mf = reinterpret_cast<const float*>(smem_u);
+  c.mi = reinterpret_cast<const int*>(smem_u);
+  c.s = reinterpret_cast<float*>(smem_u) + D.model_words + group * D.env_words;
+  DevExec<G> ex = make_exec<G>();
+  // uniform trip count per CTA (phases are CTA-synchronous): groups past the end
+  // of the batch redo the last env and skip the store
+  const int64_t per_pass = (int64_t)gridDim.x * groups;
+  const int64_t passes = (n_env + per_pass - 1) / per_pass;
+  for (int64_t p = 0; p < passes; ++p) {
+    int64_t e = p * per_pass + (int64_t)blockIdx.x * groups + group;
+    const bool valid = e < n_env;
+    if (!valid) e = n_env - 1;
+    Stats st{0, 0, 0, 0};
+    prepare_env(ex, c);
+    load_env(ex, c, in, act, e);
+    for (int f = 0; f < n_frames; ++f) substep<DevExec<G>, Cfg>(ex, c, &st);
+    if (valid) store_env(ex, c, out, e, (flags & BXG_STEP_DIAGNOSTICS) ? &diag : nullptr, st);
+  }
+}
+
+template <class Cfg>
+__global__ void __launch_bounds__(kMaxThreads)
+init_kernel(const Dims D, const uint32_t* __restrict__ model, const float* __restrict__ q, const float* __restrict__ qd,
+            const BxgState out, int64_t n_env) {
+  extern __shared__ __align__(16) uint32_t smem_u[];
+  constexpr int G = Cfg::G;
+  stage_model(D, model, smem_u);
+  const int groups = blockDim.x / G, group = threadIdx.x / G;
+  Ctx c;
+  c.D = &D;
+  c.mf = reinterpret_cast<const float*>(smem_u);
+  c.mi = reinterpret_cast<const int*>(smem_u);
+  c.s = reinterpret_cast<float*>(smem_u) + D.model_words + group * D.env_words;
+  DevExec<G> ex = make_exec<G>();
+  const int64_t per_pass = (int64_t)gridDim.x * groups;
+  const int64_t passes = (n_env + per_pass - 1) / per_pass;
+  for (int64_t p = 0; p < passes; ++p) {
+    int64_t e = p * per_pass + (int64_t)blockIdx.x * groups + group;
+    const bool valid = e < n_env;
+    if (!valid) e = n_env - 1;
+    Stats st{0, 0, 0, 0};
+    prepare_env(ex, c);
+    load_env_qqd(ex, c, q, qd, e);
+    init_env<DevExec<G>, Cfg>(ex, c, &st);
+    if (valid) store_env(ex, c, out, e, nullptr, st);
+  }
+}
+
+}  // namespace bxg

@@ -19,10 +19,12 @@ namespace bxg {
 // per-env shared-memory slab.
 struct Dims {
   int L, nq, nv, nu, ncon, nlim, nc;
-  int nvp;        // row stride of nv x nv and nc x nv matrices in smem (odd)
-  int ncp;        // row stride of the nc x nc matrix in smem (odd)
+  int nvw, ncw;   // nv / nc rounded up to the register-row widths the kernels are built for
+  int nvp;        // row stride (floats) of matrices with nv columns: multiple of 4, (nvp/4) odd
+  int ncp;        // row stride (floats) of matrices with nc columns: multiple of 4, (ncp/4) odd
   int max_depth;  // deepest tree level
   int solver_iterations, solver_maxls, ns_iters, minv_mode;
+  int force_generic;  // tests only: bypass the register-row kernels
   float dt, gx, gy, gz;
   // ---- model blob ----
   int m_link_parent, m_link_ndof, m_link_qadr, m_link_dadr, m_link_depth, m_link_root;
@@ -53,15 +55,34 @@ struct Dims {
   int env_words;
 };
 
-inline int odd_up(int n) { return n | 1; }
+// Row widths the register-row kernels are instantiated for (bxg_core.cuh).
+// Row stride: a multiple of 4 floats (16-byte rows for 128-bit shared loads) whose
+// chunk count is odd, so that lanes reading "their own row" with 128-bit
+// accesses fall into distinct bank groups.
+inline int row_stride(int w) { int c = w / 4; return 4 * (c | 1); }
+
+// Kernel variants that are compiled (bxg_kernels.cu).  A model takes the first
+// variant it fits; the last one is the generic any-size kernel.
+struct Variant { int G, VC4, NC4, max_links, max_nv, max_nc; };
+constexpr int kNumVariants = 4;
+inline Variant variant(int id) {
+  switch (id) {
+    case 0: return {16, 4, 6, 16, 16, 24};   // Ant class: half-warp per env
+    case 1: return {32, 6, 7, 32, 24, 28};   // Humanoid class: warp per env
+    case 2: return {32, 8, 8, 32, 32, 32};
+    default: return {32, 0, 0, 32, 64, 64};  // generic
+  }
+}
+inline bool variant_fits(const Variant& v, int L, int nv, int nc) { return L <= v.max_links && nv <= v.max_nv && nc <= v.max_nc; }
 
 struct PackedModel {
   Dims d;
+  int variant_id = -1;
   std::vector<uint32_t> blob;
 };
 
 // Returns empty string on success, else an error message.
-inline std::string pack_model(const BxgModelDesc& m, PackedModel* out) {
+inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force_variant = -1) {
   Dims& d = out->d;
   std::vector<uint32_t>& b = out->blob;
   b.clear();
@@ -89,11 +110,18 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out) {
   d.nlim = m.has_limit ? nonfree : 0;
   d.nc = 4 * m.ncon + d.nlim;
   if (d.nc > 64) return "more than 64 constraint rows not supported";
-  d.nvp = odd_up(m.nv); d.ncp = odd_up(d.nc > 0 ? d.nc : 1);
+  int vid = force_variant;
+  if (vid < 0) for (vid = 0; vid < kNumVariants - 1; ++vid) if (variant_fits(variant(vid), L, m.nv, d.nc)) break;
+  if (vid >= kNumVariants || !variant_fits(variant(vid), L, m.nv, d.nc)) return "model does not fit the requested kernel variant";
+  out->variant_id = vid;
+  const Variant var = variant(vid);
+  d.nvw = var.VC4 ? 4 * var.VC4 : (m.nv + 3) & ~3;
+  d.ncw = var.NC4 ? 4 * var.NC4 : ((d.nc > 0 ? d.nc : 1) + 3) & ~3;
+  d.nvp = row_stride(d.nvw); d.ncp = row_stride(d.ncw);
   d.max_depth = 0;
   for (int l = 0; l < L; ++l) d.max_depth = depth[l] > d.max_depth ? depth[l] : d.max_depth;
   d.solver_iterations = m.solver_iterations; d.solver_maxls = m.solver_maxls;
-  d.ns_iters = m.matrix_inv_iterations; d.minv_mode = m.minv_mode;
+  d.ns_iters = m.matrix_inv_iterations; d.minv_mode = m.minv_mode; d.force_generic = 0;
   d.dt = m.dt; d.gx = m.gravity[0]; d.gy = m.gravity[1]; d.gz = m.gravity[2];
 
   auto put_i = [&](const std::vector<int>& v) { int o = (int)b.size(); for (int x : v) b.push_back((uint32_t)x); return o; };
@@ -193,7 +221,7 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out) {
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
   const int nvv = m.nv, nc = d.nc, ncz = nc > 0 ? nc : 1;
   d.s_q = take(m.nq); d.s_qd = take(nvv); d.s_act = take(m.nu > 0 ? m.nu : 1);
-  d.s_tau = take(nvv); d.s_qfs = take(nvv); d.s_qfc = take(nvv); d.s_qdd = take(nvv);
+  d.s_tau = take(d.nvw); d.s_qfs = take(d.nvw); d.s_qfc = take(d.nvw); d.s_qdd = take(d.nvw);
   d.s_x_pos = take(L * 3); d.s_x_rot = take(L * 4); d.s_xd_ang = take(L * 3); d.s_xd_vel = take(L * 3);
   d.s_root_com = take(L * 3);
   d.s_cinr_pos = take(L * 3); d.s_cinr_rot = take(L * 4); d.s_cinr_i = take(L * 9); d.s_cinr_mass = take(L);
@@ -203,11 +231,16 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out) {
   d.s_t_ang = take(L * 3); d.s_t_vel = take(L * 3); d.s_f_ang = take(L * 3); d.s_f_vel = take(L * 3);
   d.s_j_rot = take(L * 4);
   d.s_crb_pos = take(L * 3); d.s_crb_i = take(L * 9); d.s_crb_mass = take(L);
-  d.s_M = take(nvv * d.nvp); d.s_Minv = take(nvv * d.nvp);
-  int scr_ns = 2 * nvv * d.nvp, scr_pg = ncz * d.nvp + ncz * d.ncp;
-  d.s_scr = take(scr_ns > scr_pg ? scr_ns : scr_pg);
-  d.s_J = take(ncz * d.nvp); d.s_diag = take(ncz); d.s_aref = take(ncz); d.s_b = take(ncz);
-  d.s_px = take(ncz); d.s_py = take(ncz); d.s_pg = take(ncz); d.s_pres = take(ncz); d.s_pxn = take(ncz);
+  // matrices with nv columns keep nvw rows: the rows past nv stay zero so that
+  // register-row kernels can run their k loops to the compile-time width
+  d.s_M = take(d.nvw * d.nvp); d.s_Minv = take(d.nvw * d.nvp);
+  int scr_ns = 2 * d.nvw * d.nvp;                   // Newton-Schulz: candidate + (I + r)
+  int scr_pg = d.nvw * d.ncp + ncz * d.ncp;         // constraint solve: J^T + A
+  int scr_gen = ncz * d.nvp + ncz * d.ncp;          // generic path: J Minv + A
+  int scr = scr_ns > scr_pg ? scr_ns : scr_pg;
+  d.s_scr = take(scr > scr_gen ? scr : scr_gen);
+  d.s_J = take(ncz * d.nvp); d.s_diag = take(ncz); d.s_aref = take(ncz); d.s_b = take(d.ncw);
+  d.s_px = take(d.ncw); d.s_py = take(d.ncw); d.s_pg = take(d.ncw); d.s_pres = take(d.ncw); d.s_pxn = take(d.ncw);
   d.s_dist = take(m.ncon > 0 ? m.ncon : 1);
   d.s_red = take(8);
   d.env_words = o;

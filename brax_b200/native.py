@@ -159,6 +159,7 @@ def lib() -> ctypes.CDLL:
       l.bxg_model_create.argtypes = [ctypes.POINTER(ModelDesc), ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
       l.bxg_model_destroy.argtypes = [ctypes.c_void_p]
       l.bxg_model_num_constraints.argtypes = [ctypes.c_void_p]
+      l.bxg_plan.argtypes = [ctypes.POINTER(ModelDesc), ctypes.POINTER(ctypes.c_int32)]
       l.bxg_init.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                              ctypes.POINTER(StateC), ctypes.c_void_p]
       l.bxg_step.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(StateC),
@@ -168,6 +169,15 @@ def lib() -> ctypes.CDLL:
         raise RuntimeError('libbxg.so ABI version mismatch')
       _lib = l
     return _lib
+
+
+def plan(sys, minv_mode: int = MINV_NEWTON_SCHULZ) -> dict:
+  """Host-only: kernel variant and shared-memory footprint for a System."""
+  desc, keep = make_desc(sys, minv_mode)
+  info = (ctypes.c_int32 * 8)()
+  _check(lib().bxg_plan(ctypes.byref(desc), info), 'bxg_plan')
+  names = ('variant', 'lanes_per_env', 'model_words', 'env_words', 'envs_per_cta', 'smem_bytes_per_cta', 'nc')
+  return dict(zip(names, list(info)[:7]))
 
 
 def launch_count() -> int:

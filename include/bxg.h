@@ -161,6 +161,11 @@ int bxg_model_create(const BxgModelDesc* desc, int device, BxgModel** out);
 void bxg_model_destroy(BxgModel* model);
 /* nc for this model (rows of con_jac). */
 int bxg_model_num_constraints(const BxgModel* model);
+/* Host-only planning query (no CUDA needed): which kernel variant a model maps
+ * to and its shared-memory footprint.  info[0] = variant id, [1] = lanes per env,
+ * [2] = model words, [3] = per-env slab words, [4] = envs per CTA,
+ * [5] = dynamic shared memory bytes per CTA, [6] = nc, [7] = reserved. */
+int bxg_plan(const BxgModelDesc* desc, int32_t info[8]);
 
 /* generalized.pipeline.init over a batch (pipeline.py:32-61):
  * q [n,nq], qd [n,nv] -> every leaf of `out`. */

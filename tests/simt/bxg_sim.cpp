@@ -6,6 +6,7 @@
 // solver state machine) against the oracle without a GPU.  `reverse` runs the
 // lanes of every phase in descending order: any result difference between the
 // two orders exposes an intra-phase cross-lane dependency (a race on device).
+// mode bit 0 = reverse lane order, bit 1 = force the generic (non register-row) kernels.
 //
 // This is not a CPU fallback: it lives under tests/, is never built by the
 // package and nothing in brax_b200/ can load it.
@@ -26,7 +27,13 @@ struct HostExec {
     float v[G_];
     float& operator()(int l) { return v[l]; }
   };
+  template <int N>
+  struct LaneVec {
+    float v[G_][N];
+    float* operator()(int l) { return v[l]; }
+  };
   void sync() {}
+  void cta_sync() {}
   template <class F>
   void lanes(F&& f) {
     if (!reverse) for (int l = 0; l < G; ++l) f(l);
@@ -45,32 +52,37 @@ struct HostExec {
   }
 };
 
-template <int G>
-int run(const BxgModelDesc* desc, bool reverse, bool init, int64_t n_env, int n_frames, const float* q, const float* qd,
+template <class Cfg>
+int run(const BxgModelDesc* desc, int vid, int mode, bool init, int64_t n_env, int n_frames, const float* q, const float* qd,
         const BxgState* in, const float* act, const BxgState* out, int flags, const BxgDiag* diag) {
+  constexpr int G = Cfg::G;
   bxg::PackedModel pm;
-  std::string err = bxg::pack_model(*desc, &pm);
+  std::string err = bxg::pack_model(*desc, &pm, vid);
   if (!err.empty()) return 3;
-  if (pm.d.L > G) return 3;
-  std::vector<float> slab(pm.d.env_words);
+  const bool reverse = mode & 1;
+  pm.d.force_generic = (mode & 2) ? 1 : 0;
+  std::vector<float> slab_store(pm.d.env_words + 4);
+  float* slab_base = slab_store.data();
+  while (reinterpret_cast<uintptr_t>(slab_base) % 16) ++slab_base;
   bxg::Ctx c;
   c.D = &pm.d;
   c.mf = reinterpret_cast<const float*>(pm.blob.data());
   c.mi = reinterpret_cast<const int*>(pm.blob.data());
-  c.s = slab.data();
+  c.s = slab_base;
   HostExec<G> ex;
   ex.reverse = reverse;
   for (int64_t e = 0; e < n_env; ++e) {
     // poison the slab so stale-data bugs show up as NaN
-    for (auto& v : slab) v = NAN;
+    for (int i = 0; i < pm.d.env_words; ++i) slab_base[i] = NAN;
     bxg::Stats st{0, 0, 0, 0};
+    bxg::prepare_env(ex, c);
     if (init) {
       bxg::load_env_qqd(ex, c, q, qd, e);
-      bxg::init_env(ex, c, &st);
+      bxg::init_env<HostExec<G>, Cfg>(ex, c, &st);
       bxg::store_env(ex, c, *out, e, nullptr, st);
     } else {
       bxg::load_env(ex, c, *in, act, e);
-      for (int f = 0; f < n_frames; ++f) bxg::substep(ex, c, &st);
+      for (int f = 0; f < n_frames; ++f) bxg::substep<HostExec<G>, Cfg>(ex, c, &st);
       bxg::store_env(ex, c, *out, e, (flags & BXG_STEP_DIAGNOSTICS) ? diag : nullptr, st);
     }
   }
@@ -79,14 +91,29 @@ int run(const BxgModelDesc* desc, bool reverse, bool init, int64_t n_env, int n_
 
 }  // namespace
 
-extern "C" {
-int sim_init(const BxgModelDesc* desc, int G, int reverse, int64_t n_env, const float* q, const float* qd, const BxgState* out) {
-  if (G == 16) return run<16>(desc, reverse, true, n_env, 0, q, qd, nullptr, nullptr, out, 0, nullptr);
-  return run<32>(desc, reverse, true, n_env, 0, q, qd, nullptr, nullptr, out, 0, nullptr);
+template <class... A>
+int dispatch(const BxgModelDesc* desc, int vid, A... a) {
+  if (vid < 0) {
+    bxg::PackedModel pm;
+    if (!bxg::pack_model(*desc, &pm).empty()) return 3;
+    vid = pm.variant_id;
+  }
+  switch (vid) {
+    case 0: return run<bxg::KernelCfg<16, 4, 6, true>>(desc, vid, a...);
+    case 1: return run<bxg::KernelCfg<32, 6, 7, true>>(desc, vid, a...);
+    case 2: return run<bxg::KernelCfg<32, 8, 8, true>>(desc, vid, a...);
+    case 3: return run<bxg::KernelCfg<32, 0, 0>>(desc, vid, a...);
+  }
+  return 3;
 }
-int sim_step(const BxgModelDesc* desc, int G, int reverse, int64_t n_env, int n_frames, const BxgState* in, const float* act,
+
+extern "C" {
+// variant: -1 = the one the library would pick, else a forced kernel variant id
+int sim_init(const BxgModelDesc* desc, int variant, int mode, int64_t n_env, const float* q, const float* qd, const BxgState* out) {
+  return dispatch(desc, variant, mode, true, n_env, 0, q, qd, (const BxgState*)nullptr, (const float*)nullptr, out, 0, (const BxgDiag*)nullptr);
+}
+int sim_step(const BxgModelDesc* desc, int variant, int mode, int64_t n_env, int n_frames, const BxgState* in, const float* act,
              const BxgState* out, int flags, const BxgDiag* diag) {
-  if (G == 16) return run<16>(desc, reverse, false, n_env, n_frames, nullptr, nullptr, in, act, out, flags, diag);
-  return run<32>(desc, reverse, false, n_env, n_frames, nullptr, nullptr, in, act, out, flags, diag);
+  return dispatch(desc, variant, mode, false, n_env, n_frames, (const float*)nullptr, (const float*)nullptr, in, act, out, flags, diag);
 }
 }

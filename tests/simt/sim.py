@@ -18,18 +18,18 @@ def build(force=False):
   deps = [_SRC] + [os.path.join(_CSRC, f) for f in ('bxg_core.cuh', 'bxg_model.h')]
   if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps):
     return
-  subprocess.run(['g++', '-O2', '-ffp-contract=off', '-fPIC', '-shared', '-std=c++17', _SRC, '-o', _SO], check=True)
+  subprocess.run(['g++', '-O2', '-ffp-contract=off', '-fPIC', '-shared', '-std=c++17', '-Wno-unknown-pragmas', _SRC, '-o', _SO], check=True)
 
 
 class Sim:
-  def __init__(self, sys, G=None, reverse=False, minv_mode=native.MINV_NEWTON_SCHULZ):
+  def __init__(self, sys, variant=-1, reverse=False, minv_mode=native.MINV_NEWTON_SCHULZ, generic=False):
+    """variant: -1 auto, 0 = (G16, nv<=16, nc<=24), 1 = (G32, nv<=24, nc<=28),
+    2 = (G32, nv<=32, nc<=32), 3 = generic kernel."""
     build()
     self.lib = ctypes.CDLL(_SO)
     self.sys = sys
     self.desc, self._keep = native.make_desc(sys, minv_mode)
-    if G is None:
-      G = 16 if (sys.num_links() <= 16 and sys.nv <= 16) else 32
-    self.G, self.reverse = G, int(reverse)
+    self.G, self.reverse = int(variant), int(reverse) | (2 if generic else 0)
     self.shapes = native.state_shapes(sys)
     self.ncon = len(sys.contact_pairs().geom1)
 

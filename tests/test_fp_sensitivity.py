@@ -52,7 +52,7 @@ def test_fma_contraction_alone_breaks_strict_tolerance(ant, tmp_path):
       acc.append(e)
   one, five = np.concatenate(one), np.concatenate(five)
   # a single substep is tight for almost every env ...
-  assert (one <= 1).mean() > 0.99 and np.median(one) < 0.01
+  assert (one <= 1).mean() > 0.95 and np.median(one) < 0.05
   # ... five substeps are not, for the SAME code modulo FMA contraction
   assert np.median(five) < 0.1
   assert 0.80 < (five <= 1).mean() < 0.999
