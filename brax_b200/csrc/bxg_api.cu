@@ -108,10 +108,12 @@ int bxg_model_create(const BxgModelDesc* desc, int device, BxgModel** out) {
   if ((ce = cudaMalloc(&m->d_blob, m->pm.blob.size() * sizeof(uint32_t))) != cudaSuccess) return cleanup(cuda_fail(ce, "cudaMalloc(model)"));
   if ((ce = cudaMemcpy(m->d_blob, m->pm.blob.data(), m->pm.blob.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess)
     return cleanup(cuda_fail(ce, "cudaMemcpy(model)"));
+  // the attribute is per function (shared by every model of this variant): always
+  // raise it to the device maximum, never to this model's own size
   const void* ks = step_kernel_of(m->pm.variant_id);
   const void* ki = init_kernel_of(m->pm.variant_id);
-  if ((ce = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_bytes)) != cudaSuccess) return cleanup(cuda_fail(ce, "cudaFuncSetAttribute(step)"));
-  if ((ce = cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_bytes)) != cudaSuccess) return cleanup(cuda_fail(ce, "cudaFuncSetAttribute(init)"));
+  if ((ce = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin)) != cudaSuccess) return cleanup(cuda_fail(ce, "cudaFuncSetAttribute(step)"));
+  if ((ce = cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin)) != cudaSuccess) return cleanup(cuda_fail(ce, "cudaFuncSetAttribute(init)"));
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m->blocks_per_sm_step, ks, m->threads, m->smem_bytes);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m->blocks_per_sm_init, ki, m->threads, m->smem_bytes);
   if (m->blocks_per_sm_step < 1 || m->blocks_per_sm_init < 1) return cleanup(fail(BXG_E_UNSUPPORTED, "kernel does not fit on an SM"));

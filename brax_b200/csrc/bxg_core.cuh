@@ -220,7 +220,7 @@ BXG_HD void con_force_generic(X& ex, const Ctx& c, Stats* st) {
     return;
   }
   float* J = s + D.s_J; float* Mi = s + D.s_Minv;
-  float* JM = s + D.s_scr; float* A = s + D.s_scr + nc * nvp;
+  float* JM = s + D.s_JM; float* A = s + D.s_A;
   float* b = s + D.s_b; float* x = s + D.s_px; float* y = s + D.s_py; float* g = s + D.s_pg;
   float* res = s + D.s_pres; float* xn = s + D.s_pxn;
   // A = J Minv J^T + diag, b = J Minv qf_smooth - aref   (lanes <-> rows)
@@ -261,7 +261,7 @@ BXG_HD void con_force_generic(X& ex, const Ctx& c, Stats* st) {
         for (int i = 0; i < nc; ++i) acc += A[i * ncp + j] * res[i];
         g[j] = acc;
       }
-    });
+    });   // (writes g only: no hazard with the redundant reads of res above)
     float sz = stepsize;
     for (int ls = 0;; ++ls) {
       ex.lanes([&](int lane) { for (int i = lane; i < nc; i += X::G) xn[i] = fmaxf(y[i] - sz * g[i], 0.f); });
@@ -277,6 +277,7 @@ BXG_HD void con_force_generic(X& ex, const Ctx& c, Stats* st) {
       for (int i = 0; i < nc; ++i) { float dlt = xn[i] - y[i]; vd += dlt * g[i]; }
       for (int i = 0; i < nc; ++i) fn += 0.5f * (res[i] * res[i]);
       st->pg_trials++;
+      ex.sync();   // every lane finished its redundant reads of xn / res before they are rewritten
       float fun_decrease = sz * (fn - fy);
       float condition = sz * vd + 0.5f * sqdist;
       if (!(fun_decrease > condition + eps) || ls >= D.solver_maxls) break;
@@ -359,7 +360,7 @@ BXG_HD void integrate(X& ex, const Ctx& c) {
   const float* Mi = s + D.s_Minv;
   if (D.ns_iters == 0) {
     float* tmp = s + D.s_scr;  // dst
-    spd_inverse(ex, c, s + D.s_M, tmp, s + D.s_scr + nv * nvp, mf + D.m_damp, dt);
+    spd_inverse(ex, c, s + D.s_M, tmp, s + D.s_scr + D.nvw * nvp, mf + D.m_damp, dt);
     Mi = tmp;
   }
   ex.lanes([&](int lane) {
@@ -601,7 +602,7 @@ BXG_HD void mass_matrix(X& ex, const Ctx& c) {
       for (int i = 0; i < 9; ++i) s[D.s_crb_i + 9 * lane + i] = s[D.s_cinr_i + 9 * lane + i];
       s[D.s_crb_mass + lane] = s[D.s_cinr_mass + lane];
     }
-    for (int i = lane; i < nv * nvp; i += X::G) M[i] = 0.f;
+    for (int i = lane; i < D.nvw * nvp; i += X::G) M[i] = 0.f;   // incl. padding rows (slot shared with A)
   });
   for (int lvl = D.max_depth - 1; lvl >= 0; --lvl) {
     ex.lanes([&](int l) {
@@ -639,9 +640,9 @@ BXG_HD void minv_newton_schulz_generic(X& ex, const Ctx& c, Stats* st) {
   const Dims& D = *c.D; float* s = c.s;
   const int n = D.nv, nvp = D.nvp;
   const float* M = s + D.s_M;
-  float* Xc = s + D.s_Minv;          // current estimate
-  float* Xn = s + D.s_scr;           // candidate
-  float* RB = s + D.s_scr + n * nvp;  // residual r, then I + r in place
+  float* Xc = s + D.s_Minv;   // current estimate
+  float* Xn = s + D.s_Xn;     // candidate
+  float* RB = s + D.s_B;      // residual r, then I + r in place
   typename X::LaneF p_sum, p_max;
   // r0 = I - M X
   ex.lanes([&](int lane) {
@@ -845,8 +846,8 @@ BXG_HD void minv_newton_schulz_tiles(X& ex, const Ctx& c, Stats* st) {
   const float* M = s + D.s_M;
   float* Xa = s + D.s_Minv;
   float* Xc = Xa;                      // current estimate
-  float* Xn = s + D.s_scr;             // candidate
-  float* B = s + D.s_scr + W * ld;     // I + r
+  float* Xn = s + D.s_Xn;              // candidate
+  float* B = s + D.s_B;                // I + r
   typename X::LaneF p_sum, p_max;
   // r0 = I - M X
   ex.lanes([&](int lane) {
@@ -908,13 +909,15 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
   const Dims& D = *c.D; float* s = c.s;
   const int nv = D.nv, nc = D.nc, ldv = D.nvp, ldc = D.ncp;
   const float* J = s + D.s_J; const float* Mi = s + D.s_Minv;
-  float* Jt = s + D.s_scr; float* A = s + D.s_scr + VW * ldc;
+  float* Jt = s + D.s_Jt; float* A = s + D.s_A;
   float* xs = s + D.s_px; float* ys = s + D.s_py; float* ress = s + D.s_pres; float* xns = s + D.s_pxn;
   typename X::template LaneVec<R * CW> arow;
   typename X::template LaneVec<R> bi, xi, yi, gi, xni, resi;
   typename X::LaneF p0, p1, p2;
   ex.lanes([&](int lane) {
     for (int i = lane; i < VW * ldc; i += G) Jt[i] = 0.f;
+    // padding of the solver vectors (they share storage with other phases)
+    for (int i = nc + lane; i < CW; i += G) { xs[i] = 0.f; ys[i] = 0.f; xns[i] = 0.f; ress[i] = 0.f; }
   });
   // Jt, then A = (J Minv) J^T + diag and b = (J Minv) qf_smooth - aref
   ex.lanes([&](int lane) {
@@ -1080,6 +1083,9 @@ BXG_HD void con_jacobian(X& ex, const Ctx& c) {
   const Dims& D = *c.D; const float* mf = c.mf; const int* mi = c.mi; float* s = c.s;
   const int nv = D.nv, nvp = D.nvp;
   float* J = s + D.s_J;
+  // J shares its slot with Newton-Schulz scratch: clear it (limit rows and the
+  // padding columns rely on zeros)
+  ex.lanes([&](int lane) { for (int i = lane; i < D.nc * nvp; i += X::G) J[i] = 0.f; });
   for (int cc = 0; cc < D.ncon; ++cc) {
     int lb = mi[D.m_con_lb + cc];
     // contact.get, plane-sphere (contact.py:28-67 + mjx): every lane redundantly
@@ -1229,7 +1235,7 @@ BXG_HD void load_env(X& ex, const Ctx& c, const BxgState& g, const float* act, i
     for (int i = lane; i < nv * nv; i += G) {
       int r = i / nv, cc = i - r * nv;
       s[D.s_Minv + r * nvp + cc] = g.mass_mx_inv[e * nv * nv + i];
-      if (D.ns_iters == 0) s[D.s_M + r * nvp + cc] = g.mass_mx[e * nv * nv + i];
+      s[D.s_M + r * nvp + cc] = g.mass_mx[e * nv * nv + i];
     }
     for (int i = lane; i < nc * nv; i += G) {
       int r = i / nv, cc = i - r * nv;

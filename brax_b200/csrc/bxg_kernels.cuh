@@ -33,9 +33,8 @@ struct DevExec {
   __device__ __forceinline__ void cta_sync() { __syncthreads(); }
   template <class F>
   __device__ __forceinline__ void lanes(F&& f) {
-    __syncwarp(mask);
     f(lane);
-    __syncwarp(mask);
+    __syncwarp(mask);   // group barrier + memory ordering for the next phase
   }
   __device__ __forceinline__ float sum(LaneF& p) {
     float v = p.v;

@@ -47,9 +47,15 @@ struct Dims {
   int s_t_ang, s_t_vel;        // [L,3] x2 temps: cdd (RNE) / xi_pos (com)
   int s_f_ang, s_f_vel;        // [L,3] x2 temps: cfrc (RNE) / joint frame pos
   int s_j_rot;                 // [L,4] joint frame rot
-  int s_crb_pos, s_crb_i, s_crb_mass;
-  int s_M, s_Minv, s_scr;      // s_scr: 2*nv*nvp (N-S) or nc*nvp + nc*ncp (constraint solve)
-  int s_J, s_diag, s_aref, s_b, s_px, s_py, s_pg, s_pres, s_pxn;
+  int s_crb_pos, s_crb_i, s_crb_mass;   // alias the t/f temporaries (different phases)
+  // Matrices.  In the specialised variants three slots are time-shared:
+  //   slot0 {M | A}   slot1 {Newton-Schulz candidate | J}   slot2 {I + r | J^T}
+  // (M, candidate, I+r live from mass.matrix to the end of Newton-Schulz; J from
+  // constraint.jacobian to the end of constraint.force of the NEXT substep; J^T, A
+  // inside constraint.force).  The generic variant keeps them apart.
+  int s_M, s_Minv, s_Xn, s_B, s_J, s_Jt, s_A, s_JM;
+  int s_scr;                   // generic path / Cholesky scratch (2 matrices)
+  int s_diag, s_aref, s_b, s_px, s_py, s_pg, s_pres, s_pxn;  // solver vectors alias the t/f temporaries
   int s_dist;                  // [ncon]
   int s_red;                   // [8] scalars
   int env_words;
@@ -228,19 +234,42 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
   d.s_cd_ang = take(L * 3); d.s_cd_vel = take(L * 3);
   d.s_cdof_ang = take(nvv * 3); d.s_cdof_vel = take(nvv * 3);
   d.s_cdofd_ang = take(nvv * 3); d.s_cdofd_vel = take(nvv * 3);
-  d.s_t_ang = take(L * 3); d.s_t_vel = take(L * 3); d.s_f_ang = take(L * 3); d.s_f_vel = take(L * 3);
-  d.s_j_rot = take(L * 4);
-  d.s_crb_pos = take(L * 3); d.s_crb_i = take(L * 9); d.s_crb_mass = take(L);
-  // matrices with nv columns keep nvw rows: the rows past nv stay zero so that
-  // register-row kernels can run their k loops to the compile-time width
-  d.s_M = take(d.nvw * d.nvp); d.s_Minv = take(d.nvw * d.nvp);
-  int scr_ns = 2 * d.nvw * d.nvp;                   // Newton-Schulz: candidate + (I + r)
-  int scr_pg = d.nvw * d.ncp + ncz * d.ncp;         // constraint solve: J^T + A
-  int scr_gen = ncz * d.nvp + ncz * d.ncp;          // generic path: J Minv + A
-  int scr = scr_ns > scr_pg ? scr_ns : scr_pg;
-  d.s_scr = take(scr > scr_gen ? scr : scr_gen);
-  d.s_J = take(ncz * d.nvp); d.s_diag = take(ncz); d.s_aref = take(ncz); d.s_b = take(d.ncw);
-  d.s_px = take(d.ncw); d.s_py = take(d.ncw); d.s_pg = take(d.ncw); d.s_pres = take(d.ncw); d.s_pxn = take(d.ncw);
+  const bool shared_slots = var.VC4 > 0 && m.matrix_inv_iterations > 0 && m.minv_mode == BXG_MINV_NEWTON_SCHULZ;
+  // union of phase-local temporaries: kinematics / RNE / com temps, composite
+  // inertias (CRBA) and the constraint-solver vectors never live at the same time
+  {
+    int base = o;
+    d.s_t_ang = take(L * 3); d.s_t_vel = take(L * 3); d.s_f_ang = take(L * 3); d.s_f_vel = take(L * 3);
+    d.s_j_rot = take(L * 4);
+    int end_tf = o;
+    o = base;
+    d.s_crb_pos = take(L * 3); d.s_crb_i = take(L * 9); d.s_crb_mass = take(L);
+    int end_crb = o;
+    o = base;
+    d.s_b = take(d.ncw); d.s_px = take(d.ncw); d.s_py = take(d.ncw); d.s_pg = take(d.ncw); d.s_pres = take(d.ncw); d.s_pxn = take(d.ncw);
+    int end_pg = o;
+    o = end_tf > end_crb ? end_tf : end_crb;
+    o = o > end_pg ? o : end_pg;
+  }
+  d.s_diag = take(ncz); d.s_aref = take(ncz);
+  // matrices with nv columns keep nvw rows: rows/columns past nv stay zero so the
+  // register-tile kernels can run their loops to the compile-time width
+  const int mat_v = d.nvw * d.nvp;          // [nvw][nvp]
+  const int mat_j = ncz * d.nvp;            // J   [nc][nvp]
+  const int mat_jt = d.nvw * d.ncp;         // J^T [nvw][ncp]
+  const int mat_a = ncz * d.ncp;            // A   [nc][ncp]
+  auto mx = [](int a, int b) { return a > b ? a : b; };
+  d.s_Minv = take(mat_v);
+  if (shared_slots) {
+    int s0 = take(mx(mat_v, mat_a)), s1 = take(mx(mat_v, mat_j)), s2 = take(mx(mat_v, mat_jt));
+    d.s_M = s0; d.s_A = s0; d.s_Xn = s1; d.s_J = s1; d.s_B = s2; d.s_Jt = s2;
+    d.s_JM = s0; d.s_scr = s1;  // unused by the specialised kernels
+  } else {
+    d.s_M = take(mat_v); d.s_J = take(mat_j);
+    d.s_scr = take(2 * mat_v);            // Cholesky: dst/Lm; generic Newton-Schulz: candidate, I + r
+    d.s_Xn = d.s_scr; d.s_B = d.s_scr + mat_v;
+    d.s_Jt = take(mat_jt); d.s_A = take(mat_a); d.s_JM = take(mat_j);
+  }
   d.s_dist = take(m.ncon > 0 ? m.ncon : 1);
   d.s_red = take(8);
   d.env_words = o;
