@@ -161,7 +161,8 @@ int bxg_init(const BxgModel* m, int64_t n_env, const float* q, const float* qd, 
   if (!q || !qd || !state_ok(out, m->pm.d.nc)) return fail(BXG_E_INVALID, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
   int grid = grid_for(m, n_env, m->blocks_per_sm_init);
-  void* args[] = {(void*)&m->pm.d, (void*)&m->d_blob, (void*)&q, (void*)&qd, (void*)out, (void*)&n_env};
+  BxgEnvSpec env{}; float* obs = nullptr;
+  void* args[] = {(void*)&m->pm.d, (void*)&m->d_blob, (void*)&q, (void*)&qd, (void*)out, (void*)&n_env, (void*)&env, (void*)&obs};
   BXG_CUDA(cudaLaunchKernel(init_kernel_of(m->pm.variant_id), dim3(grid), dim3(m->threads), args, m->smem_bytes, st));
   g_launches.fetch_add(1);
   BXG_CUDA(cudaGetLastError());
@@ -180,7 +181,57 @@ int bxg_step(const BxgModel* m, int64_t n_env, int32_t n_frames, const BxgState*
   cudaStream_t st = (cudaStream_t)stream;
   int grid = grid_for(m, n_env, m->blocks_per_sm_step);
   int nf = n_frames, fl = flags;
-  void* args[] = {(void*)&m->pm.d, (void*)&m->d_blob, (void*)in, (void*)&act, (void*)out, (void*)&n_env, (void*)&nf, (void*)&fl, (void*)&dg};
+  BxgEnvSpec env{}; BxgEnvIO eio{}; BxgState first{};
+  void* args[] = {(void*)&m->pm.d, (void*)&m->d_blob, (void*)in, (void*)&act, (void*)out, (void*)&n_env, (void*)&nf, (void*)&fl, (void*)&dg,
+                  (void*)&env, (void*)&eio, (void*)&first};
+  BXG_CUDA(cudaLaunchKernel(step_kernel_of(m->pm.variant_id), dim3(grid), dim3(m->threads), args, m->smem_bytes, st));
+  g_launches.fetch_add(1);
+  BXG_CUDA(cudaGetLastError());
+  return BXG_OK;
+}
+
+int bxg_env_obs_size(const BxgModel* m, const BxgEnvSpec* spec) {
+  if (!m || !spec) return -1;
+  const bxg::Dims& d = m->pm.d;
+  int base = (d.nq - spec->obs_skip) + d.nv;
+  return spec->kind == BXG_ENV_COM_VELOCITY ? base + 16 * d.L + d.nv : base;
+}
+
+int bxg_env_reset(const BxgModel* m, const BxgEnvSpec* spec, int64_t n_env, const float* q, const float* qd,
+                  const BxgState* out, float* obs, void* stream) {
+  if (!m || !spec) return fail(BXG_E_INVALID, "null argument");
+  if (spec->kind != BXG_ENV_ROOT_VELOCITY && spec->kind != BXG_ENV_COM_VELOCITY) return fail(BXG_E_INVALID, "unknown env kind");
+  if (n_env <= 0) return n_env == 0 ? BXG_OK : fail(BXG_E_INVALID, "n_env < 0");
+  if (!q || !qd || !obs || !state_ok(out, m->pm.d.nc)) return fail(BXG_E_INVALID, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = grid_for(m, n_env, m->blocks_per_sm_init);
+  BxgEnvSpec env = *spec;
+  void* args[] = {(void*)&m->pm.d, (void*)&m->d_blob, (void*)&q, (void*)&qd, (void*)out, (void*)&n_env, (void*)&env, (void*)&obs};
+  BXG_CUDA(cudaLaunchKernel(init_kernel_of(m->pm.variant_id), dim3(grid), dim3(m->threads), args, m->smem_bytes, st));
+  g_launches.fetch_add(1);
+  BXG_CUDA(cudaGetLastError());
+  return BXG_OK;
+}
+
+int bxg_env_step(const BxgModel* m, const BxgEnvSpec* spec, int64_t n_env, int32_t n_frames, const BxgState* in,
+                 const float* action, const BxgState* out, const BxgEnvIO* io, void* stream) {
+  if (!m || !spec || !io) return fail(BXG_E_INVALID, "null argument");
+  if (spec->kind != BXG_ENV_ROOT_VELOCITY && spec->kind != BXG_ENV_COM_VELOCITY) return fail(BXG_E_INVALID, "unknown env kind");
+  if (spec->obs_skip < 0 || spec->obs_skip > m->pm.d.nq || !(spec->env_dt > 0.f)) return fail(BXG_E_INVALID, "bad env spec");
+  if (n_frames < 1) return fail(BXG_E_INVALID, "n_frames < 1");
+  if (n_env <= 0) return n_env == 0 ? BXG_OK : fail(BXG_E_INVALID, "n_env < 0");
+  if (!state_ok(in, m->pm.d.nc) || !state_ok(out, m->pm.d.nc)) return fail(BXG_E_INVALID, "null state leaf");
+  if (!io->obs || !io->reward || !io->done || !io->metrics) return fail(BXG_E_INVALID, "null env output");
+  if (io->first_state && (!state_ok(io->first_state, m->pm.d.nc) || !io->first_obs)) return fail(BXG_E_INVALID, "null first_state leaf");
+  if (m->pm.d.nu > 0 && !action) return fail(BXG_E_INVALID, "action is NULL but the model has actuators");
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = grid_for(m, n_env, m->blocks_per_sm_step);
+  int nf = n_frames, fl = 0;
+  BxgDiag dg{nullptr, nullptr};
+  BxgEnvSpec env = *spec; BxgEnvIO eio = *io; BxgState first{};
+  if (io->first_state) first = *io->first_state;
+  void* args[] = {(void*)&m->pm.d, (void*)&m->d_blob, (void*)in, (void*)&action, (void*)out, (void*)&n_env, (void*)&nf, (void*)&fl, (void*)&dg,
+                  (void*)&env, (void*)&eio, (void*)&first};
   BXG_CUDA(cudaLaunchKernel(step_kernel_of(m->pm.variant_id), dim3(grid), dim3(m->threads), args, m->smem_bytes, st));
   g_launches.fetch_add(1);
   BXG_CUDA(cudaGetLastError());

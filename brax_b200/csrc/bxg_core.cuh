@@ -138,11 +138,11 @@ BXG_HD void imp_aref(const float* prm, float pos, float vel, float* imp_out, flo
 }
 
 // ------------------------------------------------ forces: tau, passive, RNE
+// actuator.to_tau (brax/actuator.py:23-57), lanes <-> dofs, into s_tau
 template <class X>
-BXG_HD void dyn_forces(X& ex, const Ctx& c) {
+BXG_HD void actuator_tau(X& ex, const Ctx& c) {
   const Dims& D = *c.D; const float* mf = c.mf; const int* mi = c.mi; float* s = c.s;
-  const int L = D.L, nv = D.nv;
-  // actuator.to_tau (lanes <-> dofs)
+  const int nv = D.nv;
   ex.lanes([&](int lane) {
     for (int d = lane; d < nv; d += X::G) {
       float tau = 0.f;
@@ -159,6 +159,13 @@ BXG_HD void dyn_forces(X& ex, const Ctx& c) {
       s[D.s_tau + d] = tau;
     }
   });
+}
+
+template <class X>
+BXG_HD void dyn_forces(X& ex, const Ctx& c) {
+  const Dims& D = *c.D; const float* mf = c.mf; const int* mi = c.mi; float* s = c.s;
+  const int L = D.L, nv = D.nv;
+  actuator_tau(ex, c);
   // RNE forward scan: cdd, then cfrc_flat (lanes <-> links, one tree level at a time)
   for (int lvl = 0; lvl <= D.max_depth; ++lvl) {
     ex.lanes([&](int l) {
@@ -791,6 +798,38 @@ BXG_HD void tile_matmul(int lane, const float* A, const float* B, int ld, float 
   const int rg = lane / T::CG, cg = lane - rg * T::CG;
   const float* a0 = A + rg * T::TM * ld;
   const float* b0 = B + cg * T::TN;
+#if defined(__CUDA_ARCH__)
+  // sm_100a packed FP32: one FFMA2 = two fused multiply-adds per lane (same
+  // rounding as two scalar FFMA), halving the issue slots of the inner product
+  float2 acc2[T::TM][T::TN / 2];
+#pragma unroll
+  for (int r = 0; r < T::TM; ++r)
+#pragma unroll
+    for (int cc = 0; cc < T::TN / 2; ++cc) acc2[r][cc] = make_float2(0.f, 0.f);
+#pragma unroll 1
+  for (int k0 = 0; k0 < W; k0 += 4) {
+    F4 a[T::TM];
+#pragma unroll
+    for (int r = 0; r < T::TM; ++r) a[r] = ldv4(a0 + r * ld + k0);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      float bv[T::TN];
+      load_cols<T::TN>(b0 + (k0 + kk) * ld, bv);
+#pragma unroll
+      for (int r = 0; r < T::TM; ++r) {
+        const float av = kk == 0 ? a[r].x : kk == 1 ? a[r].y : kk == 2 ? a[r].z : a[r].w;
+        const float2 av2 = make_float2(av, av);
+#pragma unroll
+        for (int cc = 0; cc < T::TN / 2; ++cc)
+          acc2[r][cc] = __ffma2_rn(av2, make_float2(bv[2 * cc], bv[2 * cc + 1]), acc2[r][cc]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < T::TM; ++r)
+#pragma unroll
+    for (int cc = 0; cc < T::TN / 2; ++cc) { acc[r][2 * cc] = acc2[r][cc].x; acc[r][2 * cc + 1] = acc2[r][cc].y; }
+#else
 #pragma unroll
   for (int r = 0; r < T::TM; ++r)
 #pragma unroll
@@ -812,6 +851,7 @@ BXG_HD void tile_matmul(int lane, const float* A, const float* B, int ld, float 
       }
     }
   }
+#endif
 }
 
 // residual tile r = I - acc (identity only on real rows), accumulates the
@@ -1203,6 +1243,166 @@ BXG_HD void prepare_env(X& ex, const Ctx& c) {
     for (int i = lane; i < ncz * D.nvp; i += G) s[D.s_J + i] = 0.f;
     for (int i = lane; i < D.nvw; i += G) { s[D.s_tau + i] = 0.f; s[D.s_qfs + i] = 0.f; s[D.s_qfc + i] = 0.f; s[D.s_qdd + i] = 0.f; }
     for (int i = lane; i < D.ncw; i += G) { s[D.s_b + i] = 0.f; s[D.s_px + i] = 0.f; s[D.s_py + i] = 0.f; s[D.s_pg + i] = 0.f; s[D.s_pres + i] = 0.f; s[D.s_pxn + i] = 0.f; }
+  });
+}
+
+// ============================================================ env epilogue
+// What the reference envs compute around pipeline_step, evaluated while the
+// post-step state is still in the slab.  `before` holds what must be captured
+// from the pre-step state: position of link 0 (Ant) or the centre of mass
+// (Humanoid), stored in s_red[0..2] by env_prologue.
+BXG_HD int env_obs_size(const Dims& D, const BxgEnvSpec& sp) {
+  int base = (D.nq - sp.obs_skip) + D.nv;
+  return sp.kind == BXG_ENV_COM_VELOCITY ? base + 10 * D.L + 6 * D.L + D.nv : base;
+}
+
+// whole-model centre of mass from link poses in s_x_pos / s_x_rot
+// (envs/humanoid.py:339-354 `_com`); every lane computes it redundantly
+BXG_HD V3 env_com(const Ctx& c) {
+  const Dims& D = *c.D; const float* mf = c.mf; const float* s = c.s;
+  V3 msum{0, 0, 0}; float mtot = 0.f;
+  for (int l = 0; l < D.L; ++l) {
+    float m = mf[D.m_in_mass + l];
+    V3 xi = ld3(s + D.s_x_pos + 3 * l) + rotate(ld3(mf + D.m_in_pos + 3 * l), ld4(s + D.s_x_rot + 4 * l));
+    msum = msum + xi * m; mtot += m;
+  }
+  return V3{msum.x / mtot, msum.y / mtot, msum.z / mtot};
+}
+
+// captures the pre-step reference point and rescales the action (Humanoid)
+template <class X>
+BXG_HD void env_prologue(X& ex, const Ctx& c, const BxgEnvSpec& sp, const BxgState& g, int64_t e) {
+  const Dims& D = *c.D; const float* mf = c.mf; float* s = c.s;
+  const int L = D.L;
+  ex.lanes([&](int lane) {
+    for (int i = lane; i < L * 3; i += X::G) s[D.s_x_pos + i] = g.x_pos[e * L * 3 + i];
+    for (int i = lane; i < L * 4; i += X::G) s[D.s_x_rot + i] = g.x_rot[e * L * 4 + i];
+    if (sp.kind == BXG_ENV_COM_VELOCITY) {
+      // action = (a + 1) * (hi - lo) * 0.5 + lo   (envs/humanoid.py:260-262)
+      for (int a = lane; a < D.nu; a += X::G) {
+        float lo = mf[D.m_act_clo + a], hi = mf[D.m_act_chi + a];
+        s[D.s_act + a] = (s[D.s_act + a] + 1.f) * (hi - lo) * 0.5f + lo;
+      }
+    }
+  });
+  V3 ref = sp.kind == BXG_ENV_COM_VELOCITY ? env_com(c) : ld3(s + D.s_x_pos);
+  ex.lanes([&](int lane) { if (lane == 0) st3(s + D.s_red, ref); });
+}
+
+// _get_obs (envs/ant.py:271-279, envs/humanoid.py:301-337) from the slab; for the
+// COM kind s_tau must already hold actuator.to_tau at the current q, qd
+template <class X>
+BXG_HD void env_write_obs(X& ex, const Ctx& c, const BxgEnvSpec& sp, float* o) {
+  const Dims& D = *c.D; const float* mf = c.mf; float* s = c.s;
+  const int L = D.L, nv = D.nv, nq = D.nq;
+  ex.lanes([&](int lane) {
+    const int G = X::G;
+    const int np = nq - sp.obs_skip;
+    for (int i = lane; i < np; i += G) o[i] = s[D.s_q + sp.obs_skip + i];
+    for (int i = lane; i < nv; i += G) o[np + i] = s[D.s_qd + i];
+    if (sp.kind == BXG_ENV_COM_VELOCITY) {
+      float mass_sum = 0.f;
+      for (int l = 0; l < L; ++l) mass_sum += mf[D.m_in_mass + l];
+      float* oi = o + np + nv; float* ov = oi + 10 * L; float* of = ov + 6 * L;
+      // com_inertia = [cinr.i (9), mass]: x_i - com is what transform_com used (one tree)
+      for (int i = lane; i < L * 10; i += G) { int l = i / 10, k = i - 10 * l; oi[i] = k < 9 ? s[D.s_cinr_i + 9 * l + k] : mf[D.m_in_mass + l]; }
+      // com_velocity = [m * (xd.vel - (x_i - x) x xd.ang) / mass_sum, xd.ang]  (humanoid.py:316-323)
+      for (int l = lane; l < L; l += G) {
+        V3 xp = ld3(s + D.s_x_pos + 3 * l);
+        V3 off = (xp + rotate(ld3(mf + D.m_in_pos + 3 * l), ld4(s + D.s_x_rot + 4 * l))) - xp;
+        V3 ang = ld3(s + D.s_xd_ang + 3 * l);
+        V3 v = ld3(s + D.s_xd_vel + 3 * l) - cross(off, ang);
+        float m = mf[D.m_in_mass + l];
+        ov[6 * l + 0] = m * v.x / mass_sum; ov[6 * l + 1] = m * v.y / mass_sum; ov[6 * l + 2] = m * v.z / mass_sum;
+        ov[6 * l + 3] = ang.x; ov[6 * l + 4] = ang.y; ov[6 * l + 5] = ang.z;
+      }
+      for (int i = lane; i < nv; i += G) of[i] = s[D.s_tau + i];
+    }
+  });
+}
+
+// observation of a freshly initialised state: action = zeros (humanoid.py:241)
+template <class X>
+BXG_HD void env_reset_obs(X& ex, const Ctx& c, const BxgEnvSpec& sp, float* o) {
+  const Dims& D = *c.D; float* s = c.s;
+  ex.lanes([&](int lane) { for (int a = lane; a < D.nu; a += X::G) s[D.s_act + a] = 0.f; });
+  if (sp.kind == BXG_ENV_COM_VELOCITY) actuator_tau(ex, c);
+  env_write_obs(ex, c, sp, o);
+}
+
+template <class X>
+BXG_HD void env_epilogue(X& ex, const Ctx& c, const BxgEnvSpec& sp, const BxgEnvIO& io, int64_t e, bool valid, bool* done_out) {
+  const Dims& D = *c.D; const float* mf = c.mf; float* s = c.s;
+  const int L = D.L, nv = D.nv, nq = D.nq;
+  const bool com_kind = sp.kind == BXG_ENV_COM_VELOCITY;
+  if (com_kind) actuator_tau(ex, c);   // qfrc_actuator at the post-step q, qd (humanoid.py:325-327)
+  // ---- reward / done / metrics: every lane redundantly (uniform scalars) ----
+  V3 before = ld3(s + D.s_red);
+  V3 after = com_kind ? env_com(c) : ld3(s + D.s_x_pos);
+  V3 vel{(after.x - before.x) / sp.env_dt, (after.y - before.y) / sp.env_dt, (after.z - before.z) / sp.env_dt};
+  float forward_reward = com_kind ? sp.forward_reward_weight * vel.x : vel.x;
+  float z = s[D.s_x_pos + 2];
+  float is_healthy = z < sp.healthy_z_min ? 0.f : 1.f;
+  if (z > sp.healthy_z_max) is_healthy = 0.f;
+  float healthy_reward = sp.terminate_when_unhealthy ? sp.healthy_reward : sp.healthy_reward * is_healthy;
+  float sq = 0.f;
+  for (int a = 0; a < D.nu; ++a) sq += s[D.s_act + a] * s[D.s_act + a];
+  float ctrl_cost = sp.ctrl_cost_weight * sq;
+  float reward = com_kind ? (forward_reward + healthy_reward) - ctrl_cost : ((forward_reward + healthy_reward) - ctrl_cost) - 0.f;
+  float done = sp.terminate_when_unhealthy ? 1.f - is_healthy : 0.f;
+  // EpisodeWrapper (wrappers/training.py:98-135) after AutoResetWrapper's step reset (:141-146)
+  float trunc = 0.f;
+  if (io.steps && valid) {
+    float steps = io.done[e] != 0.f ? 0.f : io.steps[e];
+    steps += 1.f;
+    if (sp.episode_length > 0 && steps >= (float)sp.episode_length) { trunc = 1.f - done; done = 1.f; }
+    ex.lanes([&](int lane) { if (lane == 0) { io.steps[e] = steps; if (io.truncation) io.truncation[e] = trunc; } });
+  }
+  *done_out = done != 0.f;
+  if (!valid) return;
+  const int osz = env_obs_size(D, sp);
+  const bool use_first = *done_out && io.first_state != nullptr;
+  ex.lanes([&](int lane) {
+    const int G = X::G;
+    if (lane == 0) {
+      io.reward[e] = reward; io.done[e] = done;
+      float* m = io.metrics + e * BXG_ENV_NUM_METRICS;
+      float dist;
+      if (com_kind) {
+        dist = sqrtf(after.x * after.x + after.y * after.y + after.z * after.z);
+        m[0] = forward_reward; m[1] = forward_reward; m[2] = -ctrl_cost; m[3] = healthy_reward;
+        m[4] = after.x; m[5] = after.y; m[6] = dist; m[7] = vel.x; m[8] = vel.y; m[9] = 0.f;
+      } else {
+        bool zero = fabsf(after.x) <= 1e-8f && fabsf(after.y) <= 1e-8f && fabsf(after.z) <= 1e-8f;  // math.safe_norm
+        dist = zero ? 0.f : sqrtf(after.x * after.x + after.y * after.y + after.z * after.z);
+        m[0] = forward_reward; m[1] = healthy_reward; m[2] = -ctrl_cost; m[3] = -0.f;
+        m[4] = after.x; m[5] = after.y; m[6] = dist; m[7] = vel.x; m[8] = vel.y; m[9] = forward_reward;
+      }
+    }
+    if (use_first) {   // AutoResetWrapper: obs = where(done, first_obs, obs)
+      float* o = io.obs + e * osz;
+      for (int i = lane; i < osz; i += G) o[i] = io.first_obs[e * osz + i];
+    }
+  });
+  if (!use_first) env_write_obs(ex, c, sp, io.obs + e * osz);
+}
+
+// AutoResetWrapper for the pipeline state: copy first_state's leaves for a done env
+template <class X>
+BXG_HD void store_first_state(X& ex, const Ctx& c, const BxgState& g, const BxgState& f, int64_t e) {
+  const Dims& D = *c.D;
+  const int L = D.L, nv = D.nv, nq = D.nq, nc = D.nc;
+  ex.lanes([&](int lane) {
+    const int G = X::G;
+    auto cp = [&](float* dst, const float* src, int n) { for (int i = lane; i < n; i += G) dst[e * n + i] = src[e * n + i]; };
+    cp(g.q, f.q, nq); cp(g.qd, f.qd, nv); cp(g.x_pos, f.x_pos, L * 3); cp(g.x_rot, f.x_rot, L * 4);
+    cp(g.xd_ang, f.xd_ang, L * 3); cp(g.xd_vel, f.xd_vel, L * 3); cp(g.root_com, f.root_com, L * 3);
+    cp(g.cinr_pos, f.cinr_pos, L * 3); cp(g.cinr_rot, f.cinr_rot, L * 4); cp(g.cinr_i, f.cinr_i, L * 9); cp(g.cinr_mass, f.cinr_mass, L);
+    cp(g.cd_ang, f.cd_ang, L * 3); cp(g.cd_vel, f.cd_vel, L * 3); cp(g.cdof_ang, f.cdof_ang, nv * 3); cp(g.cdof_vel, f.cdof_vel, nv * 3);
+    cp(g.cdofd_ang, f.cdofd_ang, nv * 3); cp(g.cdofd_vel, f.cdofd_vel, nv * 3);
+    cp(g.mass_mx, f.mass_mx, nv * nv); cp(g.mass_mx_inv, f.mass_mx_inv, nv * nv);
+    cp(g.con_jac, f.con_jac, nc * nv); cp(g.con_diag, f.con_diag, nc); cp(g.con_aref, f.con_aref, nc);
+    cp(g.qf_smooth, f.qf_smooth, nv); cp(g.qf_constraint, f.qf_constraint, nv); cp(g.qdd, f.qdd, nv);
   });
 }
 

@@ -69,7 +69,8 @@ __device__ __forceinline__ void stage_model(const Dims& D, const uint32_t* __res
 template <class Cfg>
 __global__ void __launch_bounds__(kMaxThreads)
 step_kernel(const Dims D, const uint32_t* __restrict__ model, const BxgState in, const float* __restrict__ act,
-            const BxgState out, int64_t n_env, int n_frames, int flags, const BxgDiag diag) {
+            const BxgState out, int64_t n_env, int n_frames, int flags, const BxgDiag diag,
+            const BxgEnvSpec env, const BxgEnvIO eio, const BxgState first) {
   extern __shared__ __align__(16) uint32_t smem_u[];
   constexpr int G = Cfg::G;
   stage_model(D, model, smem_u);
@@ -91,15 +92,21 @@ step_kernel(const Dims D, const uint32_t* __restrict__ model, const BxgState in,
     Stats st{0, 0, 0, 0};
     prepare_env(ex, c);
     load_env(ex, c, in, act, e);
+    if (env.kind) env_prologue(ex, c, env, in, e);
     for (int f = 0; f < n_frames; ++f) substep<DevExec<G>, Cfg>(ex, c, &st);
-    if (valid) store_env(ex, c, out, e, (flags & BXG_STEP_DIAGNOSTICS) ? &diag : nullptr, st);
+    bool done = false;
+    if (env.kind) env_epilogue(ex, c, env, eio, e, valid, &done);
+    if (valid) {
+      if (done && eio.first_state) store_first_state(ex, c, out, first, e);   // AutoResetWrapper
+      else store_env(ex, c, out, e, (flags & BXG_STEP_DIAGNOSTICS) ? &diag : nullptr, st);
+    }
   }
 }
 
 template <class Cfg>
 __global__ void __launch_bounds__(kMaxThreads)
 init_kernel(const Dims D, const uint32_t* __restrict__ model, const float* __restrict__ q, const float* __restrict__ qd,
-            const BxgState out, int64_t n_env) {
+            const BxgState out, int64_t n_env, const BxgEnvSpec env, float* __restrict__ obs) {
   extern __shared__ __align__(16) uint32_t smem_u[];
   constexpr int G = Cfg::G;
   stage_model(D, model, smem_u);
@@ -120,6 +127,7 @@ init_kernel(const Dims D, const uint32_t* __restrict__ model, const float* __res
     prepare_env(ex, c);
     load_env_qqd(ex, c, q, qd, e);
     init_env<DevExec<G>, Cfg>(ex, c, &st);
+    if (env.kind && valid) env_reset_obs(ex, c, env, obs + e * env_obs_size(D, env));
     if (valid) store_env(ex, c, out, e, nullptr, st);
   }
 }

@@ -1,0 +1,22 @@
+"""Environments in scope (reference `brax/envs/__init__.py:35-107`): ant, humanoid."""
+from typing import Optional
+
+from brax_b200.envs.ant import Ant
+from brax_b200.envs.base import FusedEnv, State
+from brax_b200.envs.humanoid import Humanoid
+
+_envs = {'ant': Ant, 'humanoid': Humanoid}
+
+
+def get_environment(env_name: str, **kwargs) -> FusedEnv:
+  """Returns an environment from the registry (reference envs/__init__.py:51-63)."""
+  return _envs[env_name](**kwargs)
+
+
+def create(env_name: str, episode_length: int = 1000, action_repeat: int = 1, auto_reset: bool = True,
+           batch_size: Optional[int] = None, **kwargs) -> FusedEnv:
+  """reference envs/__init__.py:76-107.  The Episode / Vmap / AutoReset wrappers
+  are not separate objects here: their arithmetic is fused into the step kernel."""
+  if action_repeat != 1:
+    raise NotImplementedError('action_repeat != 1 is not fused; loop env.step instead')
+  return _envs[env_name](episode_length=episode_length, auto_reset=auto_reset, batch_size=batch_size, **kwargs)

@@ -1,0 +1,121 @@
+"""Environment interface (reference `brax/envs/base.py:33-165`), natively batched.
+
+`State` has the reference fields.  `FusedEnv.step` is one CUDA launch: the
+n_frames physics substeps, the env's obs / reward / done / metrics and -- when
+wrapped -- the EpisodeWrapper / AutoResetWrapper arithmetic
+(`brax/envs/wrappers/training.py:75-158`) all happen while the env's state is in
+shared memory.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import Any, Dict, Optional
+
+import numpy as np
+import torch
+
+from brax_b200 import base, native, sharding
+from brax_b200.generalized.base import State as PipelineState
+
+
+@dataclasses.dataclass(frozen=True)
+class State(base.Base):
+  """Environment state for training and inference (reference envs/base.py:33-43)."""
+  pipeline_state: Optional[PipelineState]
+  obs: Any
+  reward: Any
+  done: Any
+  metrics: Dict[str, Any] = dataclasses.field(default_factory=dict)
+  info: Dict[str, Any] = dataclasses.field(default_factory=dict)
+
+
+class FusedEnv:
+  """A brax-style env whose step runs fused on the GPU.
+
+  Subclasses set `sys`, `spec` (native.EnvSpecC), `metric_names`, `n_frames`
+  and implement `_reset_q_qd(env_begin, n, seed, device)`.
+  """
+
+  backend = 'generalized'
+
+  def __init__(self, sys: base.System, spec: native.EnvSpecC, metric_names, n_frames: int,
+               episode_length: Optional[int] = None, auto_reset: bool = False,
+               batch_size: Optional[int] = None, device=None, env_id_offset: int = 0):
+    self.sys = sys
+    self.spec = spec
+    self.metric_names = tuple(metric_names)
+    self._n_frames = int(n_frames)
+    self.episode_length = episode_length
+    self.auto_reset = auto_reset
+    self.batch_size = batch_size
+    self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    self.env_id_offset = int(env_id_offset)   # global id of env 0 (sharding across ranks)
+    spec.episode_length = int(episode_length) if episode_length else 0
+    spec.env_dt = float(np.float32(sys.opt.timestep) * np.float32(self._n_frames))
+
+  # -- reference properties ---------------------------------------------------
+  @property
+  def dt(self) -> float:
+    return float(self.spec.env_dt)
+
+  @property
+  def n_frames(self) -> int:
+    return self._n_frames
+
+  @property
+  def action_size(self) -> int:
+    return self.sys.act_size()
+
+  @property
+  def observation_size(self) -> int:
+    return self._model().env_obs_size(self.spec)
+
+  @property
+  def unwrapped(self) -> 'FusedEnv':
+    return self
+
+  def _model(self) -> native.NativeModel:
+    return native.model_for(self.sys, self.device.index or 0)
+
+  # -- API --------------------------------------------------------------------
+  def reset(self, rng) -> State:
+    """rng: an int seed.  Env e draws its noise from (seed, global env id)."""
+    n = self.batch_size or 1
+    seed = int(rng)
+    q, qd = self._reset_q_qd(self.env_id_offset, n, seed, self.device)
+    bufs, obs = self._model().env_reset(self.spec, q, qd)
+    zeros = lambda: torch.zeros(n, dtype=torch.float32, device=self.device)
+    metrics = {k: zeros() for k in self.metric_names}
+    info: Dict[str, Any] = {}
+    if self.episode_length:
+      info['steps'] = zeros(); info['truncation'] = zeros()
+    if self.auto_reset:
+      info['first_pipeline_state'] = PipelineState.from_flat(bufs)
+      info['first_obs'] = obs
+    return State(PipelineState.from_flat({k: v.clone() for k, v in bufs.items()}) if self.auto_reset
+                 else PipelineState.from_flat(bufs), obs.clone() if self.auto_reset else obs, zeros(), zeros(), metrics, info)
+
+  def step(self, state: State, action: torch.Tensor) -> State:
+    n = state.obs.shape[0]
+    model = self._model()
+    io = {
+        'obs': torch.empty_like(state.obs), 'reward': torch.empty(n, dtype=torch.float32, device=self.device),
+        'done': state.done.clone(),   # previous done in, new done out
+        'metrics': torch.empty((n, native.ENV_NUM_METRICS), dtype=torch.float32, device=self.device),
+        'steps': state.info['steps'].clone() if 'steps' in state.info else None,
+        'truncation': torch.empty(n, dtype=torch.float32, device=self.device) if 'steps' in state.info else None,
+    }
+    first = first_obs = None
+    if 'first_pipeline_state' in state.info:
+      first = {k: v.contiguous() for k, v in state.info['first_pipeline_state'].to_flat().items()}
+      first_obs = state.info['first_obs'].contiguous()
+    bufs = {k: v.contiguous() for k, v in state.pipeline_state.to_flat().items()}
+    out = model.env_step(self.spec, bufs, action, self._n_frames, io, first=first, first_obs=first_obs)
+    metrics = {k: io['metrics'][:, i] for i, k in enumerate(self.metric_names)}
+    info = dict(state.info)
+    if io['steps'] is not None:
+      info['steps'] = io['steps']; info['truncation'] = io['truncation']
+    return State(PipelineState.from_flat(out), io['obs'], io['reward'], io['done'], metrics, info)
+
+  def _reset_q_qd(self, env_begin, n, seed, device):
+    raise NotImplementedError

@@ -62,6 +62,25 @@ class DiagC(ctypes.Structure):
   _fields_ = [('con_dist', ctypes.c_void_p), ('stats', ctypes.c_void_p)]
 
 
+ENV_ROOT_VELOCITY = 1
+ENV_COM_VELOCITY = 2
+ENV_NUM_METRICS = 10
+
+
+class EnvSpecC(ctypes.Structure):
+  """Mirror of BxgEnvSpec (include/bxg.h)."""
+  _fields_ = [('kind', _i32), ('obs_skip', _i32), ('terminate_when_unhealthy', _i32), ('episode_length', _i32),
+              ('forward_reward_weight', _f32), ('ctrl_cost_weight', _f32), ('healthy_reward', _f32),
+              ('healthy_z_min', _f32), ('healthy_z_max', _f32), ('env_dt', _f32)]
+
+
+class EnvIOC(ctypes.Structure):
+  """Mirror of BxgEnvIO (include/bxg.h)."""
+  _fields_ = [('obs', ctypes.c_void_p), ('reward', ctypes.c_void_p), ('done', ctypes.c_void_p),
+              ('metrics', ctypes.c_void_p), ('steps', ctypes.c_void_p), ('truncation', ctypes.c_void_p),
+              ('first_state', ctypes.POINTER(StateC)), ('first_obs', ctypes.c_void_p)]
+
+
 def make_desc(sys, minv_mode: int = MINV_NEWTON_SCHULZ) -> Tuple[ModelDesc, list]:
   """System -> BxgModelDesc.  Returns (desc, keepalive arrays)."""
   keep = []
@@ -165,6 +184,12 @@ def lib() -> ctypes.CDLL:
       l.bxg_step.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(StateC),
                              ctypes.c_void_p, ctypes.POINTER(StateC), ctypes.c_int32,
                              ctypes.POINTER(DiagC), ctypes.c_void_p]
+      l.bxg_env_obs_size.argtypes = [ctypes.c_void_p, ctypes.POINTER(EnvSpecC)]
+      l.bxg_env_reset.argtypes = [ctypes.c_void_p, ctypes.POINTER(EnvSpecC), ctypes.c_int64, ctypes.c_void_p,
+                                  ctypes.c_void_p, ctypes.POINTER(StateC), ctypes.c_void_p, ctypes.c_void_p]
+      l.bxg_env_step.argtypes = [ctypes.c_void_p, ctypes.POINTER(EnvSpecC), ctypes.c_int64, ctypes.c_int32,
+                                 ctypes.POINTER(StateC), ctypes.c_void_p, ctypes.POINTER(StateC),
+                                 ctypes.POINTER(EnvIOC), ctypes.c_void_p]
       if l.bxg_abi_version() != 1:
         raise RuntimeError('libbxg.so ABI version mismatch')
       _lib = l
@@ -262,6 +287,50 @@ class NativeModel:
     stream = torch.cuda.current_stream(bufs['q'].device).cuda_stream
     _check(lib().bxg_step(self._h, n, int(n_frames), ctypes.byref(cin), act_ptr, ctypes.byref(cout),
                           flags, ctypes.byref(dg) if dg is not None else None, stream), 'bxg_step')
+    return out
+
+  # -- fused env calls ---------------------------------------------------------
+  def env_obs_size(self, spec: EnvSpecC) -> int:
+    return int(lib().bxg_env_obs_size(self._h, ctypes.byref(spec)))
+
+  def env_reset(self, spec: EnvSpecC, q, qd):
+    """pipeline.init + observation of the fresh state.  Returns (state bufs, obs)."""
+    import torch
+    n = q.shape[0]
+    q = q.contiguous().float(); qd = qd.contiguous().float()
+    out = self.alloc(n)
+    obs = torch.empty((n, self.env_obs_size(spec)), dtype=torch.float32, device=q.device)
+    cs = self._cstate(out)
+    stream = torch.cuda.current_stream(q.device).cuda_stream
+    _check(lib().bxg_env_reset(self._h, ctypes.byref(spec), n, q.data_ptr(), qd.data_ptr(), ctypes.byref(cs),
+                               obs.data_ptr(), stream), 'bxg_env_reset')
+    return out, obs
+
+  def env_step(self, spec: EnvSpecC, bufs: dict, action, n_frames: int, io: dict, out: Optional[dict] = None,
+               first: Optional[dict] = None, first_obs=None) -> dict:
+    """AutoReset(Episode(env)).step over the batch.  `io` holds the per-env arrays
+    obs, reward, done, metrics (+ optional steps, truncation), updated in place."""
+    import torch
+    n = bufs['q'].shape[0]
+    action = action.contiguous().float()
+    assert action.shape == (n, self.sys.nu), action.shape
+    out = self.alloc(n) if out is None else out
+    cin, cout = self._cstate(bufs), self._cstate(out)
+    eio = EnvIOC()
+    for k in ('obs', 'reward', 'done', 'metrics'):
+      t = io[k]
+      assert t.is_cuda and t.is_contiguous() and t.dtype == torch.float32, k
+      setattr(eio, k, t.data_ptr())
+    eio.steps = io['steps'].data_ptr() if io.get('steps') is not None else None
+    eio.truncation = io['truncation'].data_ptr() if io.get('truncation') is not None else None
+    cfirst = None
+    if first is not None:
+      cfirst = self._cstate(first)
+      eio.first_state = ctypes.pointer(cfirst)
+      eio.first_obs = first_obs.data_ptr()
+    stream = torch.cuda.current_stream(action.device).cuda_stream
+    _check(lib().bxg_env_step(self._h, ctypes.byref(spec), n, int(n_frames), ctypes.byref(cin), action.data_ptr(),
+                              ctypes.byref(cout), ctypes.byref(eio), stream), 'bxg_env_step')
     return out
 
   def alloc_diag(self, n: int) -> dict:

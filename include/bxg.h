@@ -150,6 +150,48 @@ typedef struct BxgDiag {
                            evaluations, Newton-Schulz accepts, cold starts  */
 } BxgDiag;
 
+/* ---- environment step ---------------------------------
+ * The env arithmetic the reference does around pipeline_step, fused after the
+ * last substep while the state is still in shared memory:
+ *   envs/ant.py:233-279, envs/humanoid.py:256-354   obs / reward / done / metrics
+ *   envs/wrappers/training.py:75-158                 EpisodeWrapper + AutoResetWrapper
+ */
+enum {
+  BXG_ENV_ROOT_VELOCITY = 1,  /* Ant:      velocity of link 0, obs = [q[skip:], qd]          */
+  BXG_ENV_COM_VELOCITY = 2    /* Humanoid: velocity of the centre of mass, obs = [q[skip:],
+                                 qd, com_inertia, com_velocity, qfrc_actuator]; the action is
+                                 rescaled from [-1,1] to the ctrl range first                */
+};
+#define BXG_ENV_NUM_METRICS 10
+
+typedef struct BxgEnvSpec {
+  int32_t kind;                      /* BXG_ENV_* */
+  int32_t obs_skip;                  /* 2 when exclude_current_positions_from_observation */
+  int32_t terminate_when_unhealthy;
+  int32_t episode_length;            /* EpisodeWrapper; <= 0 disables truncation */
+  float forward_reward_weight;       /* 1.0 for Ant */
+  float ctrl_cost_weight;
+  float healthy_reward;
+  float healthy_z_min, healthy_z_max;
+  float env_dt;                      /* sys.opt.timestep * n_frames */
+} BxgEnvSpec;
+
+/* Per-env arrays, device pointers.  metrics order:
+ *  ROOT_VELOCITY: reward_forward, reward_survive, reward_ctrl, reward_contact, x_position,
+ *                 y_position, distance_from_origin, x_velocity, y_velocity, forward_reward
+ *  COM_VELOCITY:  forward_reward, reward_linvel, reward_quadctrl, reward_alive, x_position,
+ *                 y_position, distance_from_origin, x_velocity, y_velocity, (unused)        */
+typedef struct BxgEnvIO {
+  float* obs;                 /* [n, obs_size] out */
+  float* reward;              /* [n] out */
+  float* done;                /* [n] in (previous done, resets `steps`) / out */
+  float* metrics;             /* [n, BXG_ENV_NUM_METRICS] out */
+  float* steps;               /* [n] in/out  info['steps'];      may be NULL */
+  float* truncation;          /* [n] out     info['truncation']; may be NULL */
+  const BxgState* first_state; /* AutoResetWrapper source; NULL disables auto-reset */
+  const float* first_obs;      /* [n, obs_size] */
+} BxgEnvIO;
+
 typedef struct BxgModel BxgModel;
 
 int bxg_abi_version(void);
@@ -178,6 +220,20 @@ int bxg_init(const BxgModel* model, int64_t n_env, const float* q,
 int bxg_step(const BxgModel* model, int64_t n_env, int32_t n_frames,
              const BxgState* in, const float* act, const BxgState* out,
              int32_t flags, const BxgDiag* diag, void* stream);
+
+/* One wrapped env.step for every env: AutoReset(Episode(env)).step(state, action)
+ * with action_repeat = 1 (envs/wrappers/training.py:98-158 around envs/ant.py:233 /
+ * envs/humanoid.py:256).  `action` is the raw policy action [n, nu]. */
+int bxg_env_step(const BxgModel* model, const BxgEnvSpec* spec, int64_t n_env,
+                 int32_t n_frames, const BxgState* in, const float* action,
+                 const BxgState* out, const BxgEnvIO* io, void* stream);
+/* Length of one observation vector for this model / env kind. */
+int bxg_env_obs_size(const BxgModel* model, const BxgEnvSpec* spec);
+/* Env.reset (envs/ant.py:205-231, envs/humanoid.py:227-254) without the RNG:
+ * pipeline.init(q, qd) plus the observation of the fresh state (zero action). */
+int bxg_env_reset(const BxgModel* model, const BxgEnvSpec* spec, int64_t n_env,
+                  const float* q, const float* qd, const BxgState* out, float* obs,
+                  void* stream);
 
 /* Number of kernel launches issued by this library so far in this process
  * (bench.py reports the delta over the timed region as gpu_launches). */

@@ -1,0 +1,146 @@
+"""NumPy restatement of the reference envs around the physics oracle.
+
+TEST INFRASTRUCTURE ONLY (see oracle/bxg_oracle.c header).  Follows, statement
+by statement, float32:
+  brax/envs/ant.py:233-279            Ant.step / _get_obs
+  brax/envs/humanoid.py:256-354       Humanoid.step / _get_obs / _com
+  brax/envs/wrappers/training.py:98-158  EpisodeWrapper.step, AutoResetWrapper.step
+  brax/actuator.py:23-57              to_tau (for Humanoid's qfrc_actuator)
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from oracle import oracle as O
+
+f32 = np.float32
+
+
+def _rotate(v, q):
+  s, u = q[..., 0:1], q[..., 1:]
+  r = f32(2) * (np.sum(u * v, -1, keepdims=True) * u) + (s * s - np.sum(u * u, -1, keepdims=True)) * v
+  return r + f32(2) * s * np.cross(u, v)
+
+
+class EnvOracle:
+  def __init__(self, sys, kind, *, forward_reward_weight=1.0, ctrl_cost_weight, healthy_reward,
+               terminate_when_unhealthy=True, healthy_z_range, exclude_current_positions=True,
+               n_frames=5, episode_length=None, auto_reset=False):
+    self.sys, self.kind = sys, kind
+    self.o = O.Oracle(sys, np.float32)
+    self.w_fwd, self.w_ctrl, self.h_rew = f32(forward_reward_weight), f32(ctrl_cost_weight), f32(healthy_reward)
+    self.term = terminate_when_unhealthy
+    self.zmin, self.zmax = f32(healthy_z_range[0]), f32(healthy_z_range[1])
+    self.skip = 2 if exclude_current_positions else 0
+    self.n_frames = n_frames
+    self.dt = f32(sys.opt.timestep) * f32(n_frames)
+    self.episode_length, self.auto_reset = episode_length, auto_reset
+    self.mass = np.asarray(sys.link.inertia.mass, f32)
+    self.ipos = np.asarray(sys.link.inertia.transform.pos, f32)
+
+  # -- helpers ---------------------------------------------------------------
+  def _com(self, st):
+    x_i = st['x_pos'] + _rotate(self.ipos[None], st['x_rot'])
+    mass_sum = f32(0)
+    for m in self.mass:
+      mass_sum = f32(mass_sum + m)
+    acc = np.zeros((st['x_pos'].shape[0], 3), f32)
+    for l in range(len(self.mass)):
+      acc = (acc + self.mass[l] * x_i[:, l]).astype(f32)
+    return (acc / mass_sum).astype(f32), mass_sum, x_i
+
+  def _to_tau(self, act, q, qd):
+    a = self.sys.actuator
+    n = q.shape[0]
+    tau = np.zeros((n, self.sys.nv), f32)
+    if self.sys.nu == 0:
+      return tau
+    qv, qdv = q[:, np.asarray(a.q_id)], qd[:, np.asarray(a.qd_id)]
+    act = np.clip(act, a.ctrl_range[:, 0], a.ctrl_range[:, 1]).astype(f32)
+    bias = (a.gear * (qv * a.bias_q + qdv * a.bias_qd)).astype(f32)
+    force = (a.gain * act + bias).astype(f32)
+    force = np.clip(force, a.force_range[:, 0], a.force_range[:, 1]).astype(f32)
+    force = (force * a.gear).astype(f32)
+    np.add.at(tau, (slice(None), np.asarray(a.qd_id)), force)
+    return tau
+
+  def obs(self, st, action):
+    q, qd = st['q'][:, self.skip:], st['qd']
+    if self.kind == 'ant':
+      return np.concatenate([q, qd], 1).astype(f32)
+    n, L = q.shape[0], len(self.mass)
+    com, mass_sum, x_i = self._com(st)
+    com_inertia = np.concatenate([st['cinr_i'].reshape(n, L, 9), np.broadcast_to(self.mass[None, :, None], (n, L, 1))], 2)
+    off = (x_i - st['x_pos']).astype(f32)
+    vel = (st['xd_vel'] - np.cross(off, st['xd_ang'])).astype(f32)
+    com_vel = (self.mass[None, :, None] * vel / mass_sum).astype(f32)
+    com_velocity = np.concatenate([com_vel, st['xd_ang']], 2)
+    tau = self._to_tau(action, st['q'], st['qd'])
+    return np.concatenate([q, qd, com_inertia.reshape(n, -1), com_velocity.reshape(n, -1), tau], 1).astype(f32)
+
+  # -- env API ---------------------------------------------------------------
+  def reset(self, q, qd):
+    st = self.o.init(q, qd)
+    n = st['q'].shape[0]
+    ob = self.obs(st, np.zeros((n, self.sys.nu), f32))
+    env = {'ps': st, 'obs': ob, 'reward': np.zeros(n, f32), 'done': np.zeros(n, f32), 'metrics': {},
+           'steps': np.zeros(n, f32), 'truncation': np.zeros(n, f32)}
+    if self.auto_reset:
+      env['first_ps'] = {k: v.copy() for k, v in st.items()}
+      env['first_obs'] = ob.copy()
+    return env
+
+  def _env_step(self, ps0, action):
+    """Ant.step / Humanoid.step on pipeline states (no wrappers)."""
+    action = np.asarray(action, f32)
+    if self.kind == 'humanoid':
+      lo, hi = self.sys.actuator.ctrl_range[:, 0], self.sys.actuator.ctrl_range[:, 1]
+      action = ((action + f32(1)) * (hi - lo) * f32(0.5) + lo).astype(f32)
+    ps = {k: v.copy() for k, v in ps0.items()}
+    if self.kind == 'humanoid':
+      before, _, _ = self._com(ps0)
+    else:
+      before = ps0['x_pos'][:, 0].copy()
+    self.o.step(ps, action, self.n_frames)
+    after = self._com(ps)[0] if self.kind == 'humanoid' else ps['x_pos'][:, 0]
+    velocity = ((after - before) / self.dt).astype(f32)
+    forward = (self.w_fwd * velocity[:, 0]).astype(f32) if self.kind == 'humanoid' else velocity[:, 0]
+    z = ps['x_pos'][:, 0, 2]
+    healthy = np.where(z < self.zmin, f32(0), f32(1)).astype(f32)
+    healthy = np.where(z > self.zmax, f32(0), healthy).astype(f32)
+    h_rew = np.full_like(healthy, self.h_rew) if self.term else (self.h_rew * healthy).astype(f32)
+    sq = np.zeros(action.shape[0], f32)
+    for a in range(action.shape[1]):
+      sq = (sq + action[:, a] * action[:, a]).astype(f32)
+    ctrl = (self.w_ctrl * sq).astype(f32)
+    reward = ((forward + h_rew).astype(f32) - ctrl).astype(f32)
+    done = (f32(1) - healthy).astype(f32) if self.term else np.zeros_like(healthy)
+    dist = np.sqrt(np.sum(after.astype(f32) ** 2, -1)).astype(f32)
+    if self.kind == 'ant':
+      m = {'reward_forward': forward, 'reward_survive': h_rew, 'reward_ctrl': -ctrl, 'reward_contact': np.zeros_like(ctrl),
+           'x_position': after[:, 0], 'y_position': after[:, 1], 'distance_from_origin': dist,
+           'x_velocity': velocity[:, 0], 'y_velocity': velocity[:, 1], 'forward_reward': forward}
+    else:
+      m = {'forward_reward': forward, 'reward_linvel': forward, 'reward_quadctrl': -ctrl, 'reward_alive': h_rew,
+           'x_position': after[:, 0], 'y_position': after[:, 1], 'distance_from_origin': dist,
+           'x_velocity': velocity[:, 0], 'y_velocity': velocity[:, 1]}
+    return ps, self.obs(ps, action), reward, done, m
+
+  def step(self, env, action):
+    """AutoReset(Episode(env)).step with action_repeat = 1."""
+    steps = np.where(env['done'] != 0, f32(0), env['steps']).astype(f32) if self.episode_length else env['steps']
+    ps, ob, reward, done, m = self._env_step(env['ps'], action)
+    trunc = np.zeros_like(done)
+    if self.episode_length:
+      steps = (steps + f32(1)).astype(f32)
+      over = steps >= self.episode_length
+      trunc = np.where(over, f32(1) - done, f32(0)).astype(f32)
+      done = np.where(over, f32(1), done).astype(f32)
+    out = dict(env)
+    if self.auto_reset:
+      d = done != 0
+      ps = {k: (np.where(d.reshape((-1,) + (1,) * (v.ndim - 1)), env['first_ps'][k], v) if k in env['first_ps'] and v.dtype != np.int32 else v)
+            for k, v in ps.items()}
+      ob = np.where(d[:, None], env['first_obs'], ob)
+    out.update(ps=ps, obs=ob, reward=reward, done=done, metrics=m, steps=steps, truncation=trunc)
+    return out

@@ -54,7 +54,8 @@ struct HostExec {
 
 template <class Cfg>
 int run(const BxgModelDesc* desc, int vid, int mode, bool init, int64_t n_env, int n_frames, const float* q, const float* qd,
-        const BxgState* in, const float* act, const BxgState* out, int flags, const BxgDiag* diag) {
+        const BxgState* in, const float* act, const BxgState* out, int flags, const BxgDiag* diag,
+        const BxgEnvSpec* env = nullptr, const BxgEnvIO* eio = nullptr) {
   constexpr int G = Cfg::G;
   bxg::PackedModel pm;
   std::string err = bxg::pack_model(*desc, &pm, vid);
@@ -79,11 +80,16 @@ int run(const BxgModelDesc* desc, int vid, int mode, bool init, int64_t n_env, i
     if (init) {
       bxg::load_env_qqd(ex, c, q, qd, e);
       bxg::init_env<HostExec<G>, Cfg>(ex, c, &st);
+      if (env) bxg::env_reset_obs(ex, c, *env, eio->obs + e * bxg::env_obs_size(pm.d, *env));
       bxg::store_env(ex, c, *out, e, nullptr, st);
     } else {
       bxg::load_env(ex, c, *in, act, e);
+      if (env) bxg::env_prologue(ex, c, *env, *in, e);
       for (int f = 0; f < n_frames; ++f) bxg::substep<HostExec<G>, Cfg>(ex, c, &st);
-      bxg::store_env(ex, c, *out, e, (flags & BXG_STEP_DIAGNOSTICS) ? diag : nullptr, st);
+      bool done = false;
+      if (env) bxg::env_epilogue(ex, c, *env, *eio, e, true, &done);
+      if (done && eio && eio->first_state) bxg::store_first_state(ex, c, *out, *eio->first_state, e);
+      else bxg::store_env(ex, c, *out, e, (flags & BXG_STEP_DIAGNOSTICS) ? diag : nullptr, st);
     }
   }
   return 0;
@@ -110,10 +116,23 @@ int dispatch(const BxgModelDesc* desc, int vid, A... a) {
 extern "C" {
 // variant: -1 = the one the library would pick, else a forced kernel variant id
 int sim_init(const BxgModelDesc* desc, int variant, int mode, int64_t n_env, const float* q, const float* qd, const BxgState* out) {
-  return dispatch(desc, variant, mode, true, n_env, 0, q, qd, (const BxgState*)nullptr, (const float*)nullptr, out, 0, (const BxgDiag*)nullptr);
+  return dispatch(desc, variant, mode, true, n_env, 0, q, qd, (const BxgState*)nullptr, (const float*)nullptr, out, 0, (const BxgDiag*)nullptr,
+                  (const BxgEnvSpec*)nullptr, (const BxgEnvIO*)nullptr);
 }
 int sim_step(const BxgModelDesc* desc, int variant, int mode, int64_t n_env, int n_frames, const BxgState* in, const float* act,
              const BxgState* out, int flags, const BxgDiag* diag) {
-  return dispatch(desc, variant, mode, false, n_env, n_frames, (const float*)nullptr, (const float*)nullptr, in, act, out, flags, diag);
+  return dispatch(desc, variant, mode, false, n_env, n_frames, (const float*)nullptr, (const float*)nullptr, in, act, out, flags, diag,
+                  (const BxgEnvSpec*)nullptr, (const BxgEnvIO*)nullptr);
+}
+int sim_env_reset(const BxgModelDesc* desc, int variant, int mode, const BxgEnvSpec* spec, int64_t n_env, const float* q,
+                  const float* qd, const BxgState* out, float* obs) {
+  BxgEnvIO io{}; io.obs = obs;
+  return dispatch(desc, variant, mode, true, n_env, 0, q, qd, (const BxgState*)nullptr, (const float*)nullptr, out, 0,
+                  (const BxgDiag*)nullptr, spec, (const BxgEnvIO*)&io);
+}
+int sim_env_step(const BxgModelDesc* desc, int variant, int mode, const BxgEnvSpec* spec, int64_t n_env, int n_frames,
+                 const BxgState* in, const float* action, const BxgState* out, const BxgEnvIO* io) {
+  return dispatch(desc, variant, mode, false, n_env, n_frames, (const float*)nullptr, (const float*)nullptr, in, action, out, 0,
+                  (const BxgDiag*)nullptr, spec, io);
 }
 }

@@ -69,3 +69,51 @@ class Sim:
     if diag:
       out['con_dist'] = con_dist; out['stats'] = stats
     return out
+
+
+class SimEnv:
+  """Host-emulated fused env step (bxg_env_reset / bxg_env_step semantics)."""
+
+  def __init__(self, env, variant=-1, reverse=False):
+    """env: a brax_b200.envs FusedEnv-like object exposing .sys, .spec, .n_frames (no CUDA is touched)."""
+    self.sim = Sim(env.sys, variant=variant, reverse=reverse)
+    self.spec, self.n_frames = env.spec, env.n_frames
+    self.sys = env.sys
+    L, nq, nv = env.sys.num_links(), env.sys.nq, env.sys.nv
+    base = nq - env.spec.obs_skip + nv
+    self.obs_size = base + 16 * L + nv if env.spec.kind == native.ENV_COM_VELOCITY else base
+
+  def reset(self, q, qd):
+    q = np.ascontiguousarray(q, np.float32); qd = np.ascontiguousarray(qd, np.float32)
+    n = q.shape[0]
+    out = self.sim.alloc(n)
+    obs = np.zeros((n, self.obs_size), np.float32)
+    cs = Sim._cstate(out)
+    rc = self.sim.lib.sim_env_reset(ctypes.byref(self.sim.desc), self.sim.G, self.sim.reverse, ctypes.byref(self.spec),
+                                    ctypes.c_int64(n), q.ctypes.data_as(ctypes.c_void_p), qd.ctypes.data_as(ctypes.c_void_p),
+                                    ctypes.byref(cs), obs.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0, rc
+    return out, obs
+
+  def step(self, st, action, done, steps, first=None, first_obs=None):
+    n = st['q'].shape[0]
+    action = np.ascontiguousarray(action, np.float32)
+    out = self.sim.alloc(n)
+    io = {'obs': np.zeros((n, self.obs_size), np.float32), 'reward': np.zeros(n, np.float32),
+          'done': np.ascontiguousarray(done, np.float32).copy(), 'metrics': np.zeros((n, native.ENV_NUM_METRICS), np.float32),
+          'steps': np.ascontiguousarray(steps, np.float32).copy(), 'truncation': np.zeros(n, np.float32)}
+    eio = native.EnvIOC()
+    for k, v in io.items():
+      setattr(eio, k, v.ctypes.data)
+    keep = None
+    if first is not None:
+      keep = Sim._cstate(first)
+      eio.first_state = ctypes.pointer(keep)
+      first_obs = np.ascontiguousarray(first_obs, np.float32)
+      eio.first_obs = first_obs.ctypes.data
+    cin, cout = Sim._cstate(st), Sim._cstate(out)
+    rc = self.sim.lib.sim_env_step(ctypes.byref(self.sim.desc), self.sim.G, self.sim.reverse, ctypes.byref(self.spec),
+                                   ctypes.c_int64(n), int(self.n_frames), ctypes.byref(cin),
+                                   action.ctypes.data_as(ctypes.c_void_p), ctypes.byref(cout), ctypes.byref(eio))
+    assert rc == 0, rc
+    return out, io

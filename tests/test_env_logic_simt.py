@@ -1,0 +1,107 @@
+"""Env epilogue logic (obs / reward / done / metrics / episode + auto-reset) on the
+CPU: the kernel source through the host lane-group emulator vs the NumPy
+restatement of the reference envs (oracle/env_oracle.py)."""
+import numpy as np
+import pytest
+
+from oracle.env_oracle import EnvOracle
+from tests.simt.sim import SimEnv
+
+
+class _EnvStub:
+  """What SimEnv needs from an env, built without touching CUDA."""
+
+  def __init__(self, name, episode_length=None):
+    from brax_b200 import envs_assets, native
+    self.sys = envs_assets.load(name)
+    sp = native.EnvSpecC()
+    if name == 'ant':
+      sp.kind, sp.forward_reward_weight, sp.ctrl_cost_weight, sp.healthy_reward = native.ENV_ROOT_VELOCITY, 1.0, 0.5, 1.0
+      sp.healthy_z_min, sp.healthy_z_max = 0.2, 1.0
+    else:
+      sp.kind, sp.forward_reward_weight, sp.ctrl_cost_weight, sp.healthy_reward = native.ENV_COM_VELOCITY, 1.25, 0.1, 5.0
+      sp.healthy_z_min, sp.healthy_z_max = 1.0, 2.0
+    sp.obs_skip, sp.terminate_when_unhealthy = 2, 1
+    sp.episode_length = episode_length or 0
+    self.n_frames = 5
+    sp.env_dt = float(np.float32(self.sys.opt.timestep) * np.float32(5))
+    self.spec = sp
+
+
+def _oracle(name, sys, **kw):
+  if name == 'ant':
+    return EnvOracle(sys, 'ant', ctrl_cost_weight=0.5, healthy_reward=1.0, healthy_z_range=(0.2, 1.0), **kw)
+  return EnvOracle(sys, 'humanoid', forward_reward_weight=1.25, ctrl_cost_weight=0.1, healthy_reward=5.0,
+                   healthy_z_range=(1.0, 2.0), **kw)
+
+
+@pytest.mark.parametrize('name', ['ant', 'humanoid'])
+def test_reset_obs_and_step_outputs(name):
+  from brax_b200 import workloads
+  stub = _EnvStub(name, episode_length=1000)
+  n = 8
+  _, q, qd = workloads.reset(name, 0, n, 0, 'cpu')
+  q, qd = q.numpy(), qd.numpy()
+  sim, orc = SimEnv(stub), _oracle(name, stub.sys, episode_length=1000)
+  st, obs = sim.reset(q, qd)
+  env = orc.reset(q, qd)
+  np.testing.assert_allclose(obs, env['obs'], rtol=1e-5, atol=1e-6)
+  done, steps = np.zeros(n, np.float32), np.zeros(n, np.float32)
+  rng = np.random.default_rng(0)
+  for k in range(4):
+    act = rng.uniform(-1, 1, (n, stub.sys.nu)).astype(np.float32)
+    # one-step map from the oracle's pipeline state (physics sensitivity: test_fp_sensitivity.py)
+    st_in = {f: env['ps'][f].copy() for f in st}
+    out, io = sim.step(st_in, act, env['done'], env['steps'])
+    env = orc.step(env, act)
+    e = np.abs(out['q'] - env['ps']['q']).max(1)
+    ok = e < 1e-4     # envs whose solver took the same branch
+    assert ok.mean() >= 0.75
+    np.testing.assert_allclose(io['obs'][ok], env['obs'][ok], rtol=2e-3, atol=2e-3)
+    np.testing.assert_allclose(io['reward'][ok], env['reward'][ok], rtol=1e-3, atol=5e-3)
+    np.testing.assert_array_equal(io['done'][ok], env['done'][ok])
+    np.testing.assert_array_equal(io['steps'], env['steps'])
+    names = list(env['metrics'])
+    for i, nm in enumerate(names):
+      np.testing.assert_allclose(io['metrics'][ok, i], env['metrics'][nm][ok], rtol=1e-3, atol=5e-3, err_msg=nm)
+
+
+def test_episode_truncation_and_auto_reset():
+  """episode_length = 3: step 3 sets done with truncation = 1 - done_env, the pipeline state
+  and obs snap back to the first state, and `steps` restarts on the following step."""
+  from brax_b200 import workloads
+  stub = _EnvStub('ant', episode_length=3)
+  n = 4
+  _, q, qd = workloads.reset('ant', 0, n, 0, 'cpu')
+  sim, orc = SimEnv(stub), _oracle('ant', stub.sys, episode_length=3, auto_reset=True)
+  st, obs = sim.reset(q.numpy(), qd.numpy())
+  first, first_obs = {k: v.copy() for k, v in st.items()}, obs.copy()
+  env = orc.reset(q.numpy(), qd.numpy())
+  done, steps = np.zeros(n, np.float32), np.zeros(n, np.float32)
+  act = np.zeros((n, 8), np.float32)
+  for k in range(5):
+    st, io = sim.step(st, act, done, steps, first=first, first_obs=first_obs)
+    env = orc.step(env, act)
+    done, steps = io['done'], io['steps']
+    np.testing.assert_array_equal(steps, env['steps'])
+    np.testing.assert_array_equal(done, env['done'])
+    np.testing.assert_array_equal(io['truncation'], env['truncation'])
+    if k == 2:
+      assert (done == 1).all() and (io['truncation'] == 1).all() and (steps == 3).all()
+      for f in ('q', 'qd', 'mass_mx_inv', 'con_jac', 'x_pos'):
+        np.testing.assert_array_equal(st[f], first[f])
+      np.testing.assert_array_equal(io['obs'], first_obs)
+    if k == 3:
+      assert (steps == 1).all() and (done == 0).all()
+
+
+def test_unhealthy_env_terminates():
+  from brax_b200 import workloads
+  stub = _EnvStub('ant')
+  _, q, qd = workloads.reset('ant', 0, 2, 0, 'cpu')
+  q = q.numpy(); q[1, 2] = 3.0          # far above healthy_z_range -> done
+  sim = SimEnv(stub)
+  st, _ = sim.reset(q, qd.numpy())
+  _, io = sim.step(st, np.zeros((2, 8), np.float32), np.zeros(2, np.float32), np.zeros(2, np.float32))
+  assert io['done'][0] == 0 and io['done'][1] == 1
+  assert io['metrics'][0, 1] == 1.0     # reward_survive

@@ -1,0 +1,88 @@
+"""Fused env step on the GPU (brax_b200.envs) vs the NumPy restatement of the
+reference envs + wrappers (oracle/env_oracle.py)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle(name, sys, **kw):
+  from oracle.env_oracle import EnvOracle
+  if name == 'ant':
+    return EnvOracle(sys, 'ant', ctrl_cost_weight=0.5, healthy_reward=1.0, healthy_z_range=(0.2, 1.0), **kw)
+  return EnvOracle(sys, 'humanoid', forward_reward_weight=1.25, ctrl_cost_weight=0.1, healthy_reward=5.0,
+                   healthy_z_range=(1.0, 2.0), **kw)
+
+
+def _state_from_oracle(torch, env_state_cls, ps_cls, o_env, dev, first=None):
+  from oracle import oracle as O
+  ps = ps_cls.from_flat({k: torch.as_tensor(o_env['ps'][k], device=dev) for k in O.STATE_FIELDS})
+  info = {'steps': torch.as_tensor(o_env['steps'], device=dev), 'truncation': torch.as_tensor(o_env['truncation'], device=dev)}
+  if first is not None:
+    info.update(first)
+  return env_state_cls(ps, torch.as_tensor(o_env['obs'], device=dev), torch.as_tensor(o_env['reward'], device=dev),
+                       torch.as_tensor(o_env['done'], device=dev), {}, info)
+
+
+@pytest.mark.parametrize('name', ['ant', 'humanoid'])
+def test_env_reset_and_step_match_reference_restatement(name):
+  import torch
+  from brax_b200 import envs
+  from brax_b200.envs.base import State
+  from brax_b200.generalized.base import State as PS
+  n = 64
+  env = envs.create(name, episode_length=1000, auto_reset=True, batch_size=n)
+  assert env.action_size == env.sys.nu and env.observation_size == (27 if name == 'ant' else 244)
+  st = env.reset(0)
+  dev = st.obs.device
+  orc = _oracle(name, env.sys, episode_length=1000, auto_reset=True)
+  o_env = orc.reset(st.pipeline_state.q.cpu().numpy(), st.pipeline_state.qd.cpu().numpy())
+  np.testing.assert_allclose(st.obs.cpu().numpy(), o_env['obs'], rtol=1e-5, atol=1e-5)
+  first = {'first_pipeline_state': st.info['first_pipeline_state'], 'first_obs': st.info['first_obs']}
+  gen = torch.Generator(device='cpu').manual_seed(0)
+  within = []
+  for k in range(6):
+    act = (torch.rand((n, env.action_size), generator=gen) * 2 - 1).to(dev)
+    s_in = _state_from_oracle(torch, State, PS, o_env, dev, first)      # one-step map from the oracle's state
+    s_out = env.step(s_in, act)
+    o_env = orc.step(o_env, act.cpu().numpy())
+    e = np.abs(s_out.pipeline_state.q.cpu().numpy() - o_env['ps']['q']).max(1)
+    ok = e < 1e-4
+    within.append(ok.mean())
+    np.testing.assert_allclose(s_out.obs.cpu().numpy()[ok], o_env['obs'][ok], rtol=2e-3, atol=2e-3)
+    np.testing.assert_allclose(s_out.reward.cpu().numpy()[ok], o_env['reward'][ok], rtol=1e-3, atol=5e-3)
+    np.testing.assert_array_equal(s_out.done.cpu().numpy()[ok], o_env['done'][ok])
+    np.testing.assert_array_equal(s_out.info['steps'].cpu().numpy(), o_env['steps'])
+    for nm, v in s_out.metrics.items():
+      np.testing.assert_allclose(v.cpu().numpy()[ok], o_env['metrics'][nm][ok], rtol=1e-3, atol=5e-3, err_msg=nm)
+  assert np.mean(within) >= 0.8
+
+
+def test_auto_reset_on_gpu():
+  import torch
+  from brax_b200 import envs
+  n = 32
+  env = envs.create('ant', episode_length=3, auto_reset=True, batch_size=n)
+  st = env.reset(1)
+  first_q = st.info['first_pipeline_state'].q.clone()
+  act = torch.zeros((n, 8), device=st.obs.device)
+  for k in range(4):
+    st = env.step(st, act)
+    if k == 2:
+      assert (st.done == 1).all() and (st.info['truncation'] == 1).all()
+      assert torch.equal(st.pipeline_state.q, first_q) and torch.equal(st.obs, st.info['first_obs'])
+  assert (st.info['steps'] == 1).all() and (st.done == 0).all()
+
+
+def test_env_step_equals_pipeline_step_plus_obs():
+  """The fused env step leaves exactly the pipeline state pipeline.step produces."""
+  import torch
+  from brax_b200 import envs
+  from brax_b200.generalized import pipeline
+  env = envs.get_environment('ant', batch_size=50)
+  st = env.reset(3)
+  act = torch.rand((50, 8), device=st.obs.device) * 2 - 1
+  ps = pipeline.step(env.sys, st.pipeline_state, act, n_frames=5)
+  st2 = env.step(st, act)
+  assert torch.equal(st2.pipeline_state.q, ps.q) and torch.equal(st2.pipeline_state.mass_mx_inv, ps.mass_mx_inv)
+  assert torch.equal(st2.obs, torch.cat([ps.q[:, 2:], ps.qd], 1))
