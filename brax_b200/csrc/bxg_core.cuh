@@ -940,9 +940,37 @@ BXG_HD void minv_newton_schulz(X& ex, const Ctx& c, Stats* st) {
   if constexpr (Cfg::GENERIC_TOO) minv_newton_schulz_generic(ex, c, st);
 }
 
-// constraint.force with register rows.  VC4 = nvw/4, NC4 = ncw/4, R rows of A per
-// lane (row i = lane + r*G).  Shared scratch: Jt [nvw][ncp] (J transposed, zero
-// padded) and A [nc][ncp]; solver vectors [ncw] with zero padding.
+// dot of a register row with a shared-memory vector, first `chunks` float4 chunks
+template <int C4>
+BXG_HD float row_dot_n(const float* a, const float* v, int chunks) {
+  float acc = 0.f;
+#pragma unroll
+  for (int cc = 0; cc < C4; ++cc) {
+    if (cc < chunks) {
+      F4 b = ldv4(v + 4 * cc);
+      acc += a[4 * cc] * b.x; acc += a[4 * cc + 1] * b.y; acc += a[4 * cc + 2] * b.z; acc += a[4 * cc + 3] * b.w;
+    }
+  }
+  return acc;
+}
+// index of the n-th (0-based) set bit of m
+BXG_HD int nth_set_bit(uint32_t m, int n) {
+  for (int k = 0; k < n; ++k) m &= m - 1u;
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)m) - 1;
+#else
+  return __builtin_ffs((int)m) - 1;
+#endif
+}
+
+// constraint.force on the ACTIVE rows only.  Rows the jacobian masked out
+// (inactive contact pyramids, joints inside their limits: constraint.py:124-131,174)
+// are identically zero in J, diag and aref, so they contribute exact zeros to A,
+// b, the objective, the gradient and J^T x and their x stays 0: dropping them
+// leaves every sum unchanged.  The na active rows are compacted to rows
+// 0..na-1 (lane p owns compact rows p and p+G): A = (J Minv) J^T + diag is built
+// with the row of A in registers, FISTA + backtracking line search as in
+// jaxopt.ProjectedGradient (see oracle/bxg_oracle.c).  VC4 = nvw/4, NC4 = ncw/4.
 template <class X, int VC4, int NC4, int R>
 BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
   constexpr int VW = 4 * VC4, CW = 4 * NC4, G = X::G;
@@ -954,30 +982,59 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
   typename X::template LaneVec<R * CW> arow;
   typename X::template LaneVec<R> bi, xi, yi, gi, xni, resi;
   typename X::LaneF p0, p1, p2;
+  // ---- active set ---------------------------------------------------------
+  uint32_t am = 0;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    ex.lanes([&](int lane) {
+      int i = lane + r * G;
+      float flag = 0.f;
+      if (i < nc) {
+        bool nz = s[D.s_diag + i] != 0.f || s[D.s_aref + i] != 0.f;
+        for (int k = 0; k < nv && !nz; ++k) nz = J[i * ldv + k] != 0.f;
+        flag = nz ? 1.f : 0.f;
+      }
+      p0(lane) = flag;
+    });
+    am |= ex.ballot(p0) << (r * G);
+  }
+#if defined(__CUDA_ARCH__)
+  const int na = __popc(am);
+#else
+  const int na = __builtin_popcount(am);
+#endif
+  if (na == 0) {   // nothing active: the solver would return x = 0 after one trivial iteration
+    ex.lanes([&](int lane) { for (int d = lane; d < nv; d += G) s[D.s_qfc + d] = 0.f; });
+    st->pg_iters++; st->pg_trials++;
+    return;
+  }
+  const int nch = (na + 3) >> 2;           // float4 chunks that hold active columns
   ex.lanes([&](int lane) {
     for (int i = lane; i < VW * ldc; i += G) Jt[i] = 0.f;
-    // padding of the solver vectors (they share storage with other phases)
-    for (int i = nc + lane; i < CW; i += G) { xs[i] = 0.f; ys[i] = 0.f; xns[i] = 0.f; ress[i] = 0.f; }
+    for (int i = lane; i < CW; i += G) { xs[i] = 0.f; ys[i] = 0.f; xns[i] = 0.f; ress[i] = 0.f; }
   });
-  // Jt, then A = (J Minv) J^T + diag and b = (J Minv) qf_smooth - aref
+  // J^T over the active rows: Jt[k][p] = J[orig(p)][k]
   ex.lanes([&](int lane) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      int i = lane + r * G;
-      if (i < nc) {
+      int p = lane + r * G;
+      if (p < na) {
+        int i = nth_set_bit(am, p);
         float jrow[VW];
         load_row<VC4>(J + i * ldv, jrow);
 #pragma unroll
-        for (int k = 0; k < VW; ++k) Jt[k * ldc + i] = jrow[k];
+        for (int k = 0; k < VW; ++k) Jt[k * ldc + p] = jrow[k];
       }
     }
   });
+  // A = (J Minv) J^T + diag, b = (J Minv) qf_smooth - aref on the compact rows
   ex.lanes([&](int lane) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      int i = lane + r * G;
+      int p = lane + r * G;
       float* ar = arow(lane) + r * CW;
-      if (i < nc) {
+      if (p < na) {
+        int i = nth_set_bit(am, p);
         float jrow[VW], jm[VW];
         load_row<VC4>(J + i * ldv, jrow);
         row_times_mat<VW, VC4>(jrow, Mi, ldv, jm);
@@ -988,11 +1045,11 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
           F4 f = ldv4(s + D.s_qfs + 4 * cc);
           bacc += jm[4 * cc] * f.x; bacc += jm[4 * cc + 1] * f.y; bacc += jm[4 * cc + 2] * f.z; bacc += jm[4 * cc + 3] * f.w;
         }
+        const float dg = s[D.s_diag + i];
 #pragma unroll
-        for (int j = 0; j < CW; ++j) if (j == i) ar[j] += s[D.s_diag + i];
+        for (int j = 0; j < CW; ++j) if (j == p) ar[j] += dg;
         bi(lane)[r] = bacc - s[D.s_aref + i];
-        store_row<NC4>(A + i * ldc, ar);
-        xs[i] = 0.f; ys[i] = 0.f;
+        store_row<NC4>(A + p * ldc, ar);
       } else {
 #pragma unroll
         for (int j = 0; j < CW; ++j) ar[j] = 0.f;
@@ -1010,10 +1067,10 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
       float f = 0.f;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        int i = lane + r * G;
-        if (i < nc) {
-          float rv = row_dot<NC4>(arow(lane) + r * CW, ys) + bi(lane)[r];
-          ress[i] = rv;
+        int p = lane + r * G;
+        if (p < na) {
+          float rv = row_dot_n<NC4>(arow(lane) + r * CW, ys, nch) + bi(lane)[r];
+          ress[p] = rv;
           f += 0.5f * (rv * rv);
         }
       }
@@ -1024,9 +1081,9 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         int j = lane + r * G;
-        if (j < nc) {
+        if (j < na) {
           float acc = 0.f;
-          for (int i = 0; i < nc; ++i) acc += A[i * ldc + j] * ress[i];
+          for (int i = 0; i < na; ++i) acc += A[i * ldc + j] * ress[i];
           gi(lane)[r] = acc;
         }
       }
@@ -1036,17 +1093,17 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
       ex.lanes([&](int lane) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          int i = lane + r * G;
-          if (i < nc) { float v = fmaxf(yi(lane)[r] - sz * gi(lane)[r], 0.f); xni(lane)[r] = v; xns[i] = v; }
+          int p = lane + r * G;
+          if (p < na) { float v = fmaxf(yi(lane)[r] - sz * gi(lane)[r], 0.f); xni(lane)[r] = v; xns[p] = v; }
         }
       });
       ex.lanes([&](int lane) {
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          int i = lane + r * G;
-          if (i < nc) {
-            float rv = row_dot<NC4>(arow(lane) + r * CW, xns) + bi(lane)[r];
+          int p = lane + r * G;
+          if (p < na) {
+            float rv = row_dot_n<NC4>(arow(lane) + r * CW, xns, nch) + bi(lane)[r];
             resi(lane)[r] = rv;
             float dlt = xni(lane)[r] - yi(lane)[r];
             a0 += dlt * dlt; a1 += dlt * gi(lane)[r]; a2 += 0.5f * (rv * rv);
@@ -1066,16 +1123,16 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
     float mom = (t - 1.f) / tn;
     ex.lanes([&](int lane) {
 #pragma unroll
-      for (int r = 0; r < R; ++r) { int i = lane + r * G; if (i < nc) ress[i] = resi(lane)[r]; }
+      for (int r = 0; r < R; ++r) { int p = lane + r * G; if (p < na) ress[p] = resi(lane)[r]; }
     });
     ex.lanes([&](int lane) {
       float e2 = 0.f;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         int j = lane + r * G;
-        if (j < nc) {
+        if (j < na) {
           float acc = 0.f;
-          for (int i = 0; i < nc; ++i) acc += A[i * ldc + j] * ress[i];
+          for (int i = 0; i < na; ++i) acc += A[i * ldc + j] * ress[i];
           float xn = xni(lane)[r];
           float dlt = fmaxf(xn - acc, 0.f) - xn;
           e2 += dlt * dlt;
@@ -1096,7 +1153,7 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
     for (int j = lane; j < nv; j += G) {
       float jt[CW];
       load_row<NC4>(Jt + j * ldc, jt);
-      s[D.s_qfc + j] = row_dot<NC4>(jt, xs);
+      s[D.s_qfc + j] = row_dot_n<NC4>(jt, xs, nch);
     }
   });
 }

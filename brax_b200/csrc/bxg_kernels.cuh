@@ -42,6 +42,12 @@ struct DevExec {
     for (int o = G / 2; o >= 1; o >>= 1) v += __shfl_xor_sync(mask, v, o, G);
     return v;
   }
+  // bit l of the result = (lane l of this group holds a non-zero value)
+  __device__ __forceinline__ uint32_t ballot(LaneF& p) {
+    uint32_t b = __ballot_sync(mask, p.v != 0.f);
+    if (G == 32) return b;
+    return (b >> ((threadIdx.x & 31) / G * G)) & ((1u << G) - 1u);
+  }
   __device__ __forceinline__ float max(LaneF& p) {
     float v = p.v;
 #pragma unroll

@@ -45,6 +45,11 @@ struct HostExec {
     for (int o = G / 2; o >= 1; o >>= 1) { for (int l = 0; l < G; ++l) b[l] = a[l] + a[l ^ o]; memcpy(a, b, sizeof a); }
     return a[0];
   }
+  uint32_t ballot(LaneF& p) {
+    uint32_t b = 0;
+    for (int l = 0; l < G; ++l) if (p.v[l] != 0.f) b |= 1u << l;
+    return b;
+  }
   float max(LaneF& p) {
     float m = p.v[0];
     for (int l = 1; l < G; ++l) m = fmaxf(m, p.v[l]);

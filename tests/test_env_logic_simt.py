@@ -54,8 +54,9 @@ def test_reset_obs_and_step_outputs(name):
     st_in = {f: env['ps'][f].copy() for f in st}
     out, io = sim.step(st_in, act, env['done'], env['steps'])
     env = orc.step(env, act)
-    e = np.abs(out['q'] - env['ps']['q']).max(1)
-    ok = e < 1e-4     # envs whose solver took the same branch
+    e = np.maximum((np.abs(out['q'] - env['ps']['q']) / (1e-5 + 1e-4 * np.abs(env['ps']['q']))).max(1),
+                   (np.abs(out['qd'] - env['ps']['qd']) / (1e-5 + 1e-4 * np.abs(env['ps']['qd']))).max(1))
+    ok = e <= 1.0     # envs inside the stated physics tolerance (same solver branch)
     assert ok.mean() >= 0.75
     np.testing.assert_allclose(io['obs'][ok], env['obs'][ok], rtol=2e-3, atol=2e-3)
     np.testing.assert_allclose(io['reward'][ok], env['reward'][ok], rtol=1e-3, atol=5e-3)

@@ -46,8 +46,10 @@ def test_env_reset_and_step_match_reference_restatement(name):
     s_in = _state_from_oracle(torch, State, PS, o_env, dev, first)      # one-step map from the oracle's state
     s_out = env.step(s_in, act)
     o_env = orc.step(o_env, act.cpu().numpy())
-    e = np.abs(s_out.pipeline_state.q.cpu().numpy() - o_env['ps']['q']).max(1)
-    ok = e < 1e-4
+    gq, gqd = s_out.pipeline_state.q.cpu().numpy(), s_out.pipeline_state.qd.cpu().numpy()
+    e = np.maximum((np.abs(gq - o_env['ps']['q']) / (1e-5 + 1e-4 * np.abs(o_env['ps']['q']))).max(1),
+                   (np.abs(gqd - o_env['ps']['qd']) / (1e-5 + 1e-4 * np.abs(o_env['ps']['qd']))).max(1))
+    ok = e <= 1.0   # envs inside the stated physics tolerance (same solver branch)
     within.append(ok.mean())
     np.testing.assert_allclose(s_out.obs.cpu().numpy()[ok], o_env['obs'][ok], rtol=2e-3, atol=2e-3)
     np.testing.assert_allclose(s_out.reward.cpu().numpy()[ok], o_env['reward'][ok], rtol=1e-3, atol=5e-3)
