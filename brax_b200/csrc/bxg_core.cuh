@@ -123,8 +123,16 @@ struct KernelCfg {
 BXG_HD void imp_aref(const float* prm, float pos, float vel, float* imp_out, float* aref_out) {
   float timeconst = prm[0], dampratio = prm[1], dmin = prm[2], dmax = prm[3], width = prm[4], mid = prm[5], power = prm[6];
   float imp_x = fabsf(pos) / width;
-  float imp_a = (1.0f / powf(mid, power - 1.f)) * powf(imp_x, power);
-  float imp_b = 1.f - (1.0f / powf(1.f - mid, power - 1.f)) * powf(1.f - imp_x, power);
+  float imp_a, imp_b;
+  if (power == 2.f) {
+    // x^2 and mid^1 are exact operations: no transcendental needed (MuJoCo's
+    // default solimp power; XLA's simplifier lowers pow(x, 2) to x * x as well)
+    imp_a = (1.0f / mid) * (imp_x * imp_x);
+    imp_b = 1.f - (1.0f / (1.f - mid)) * ((1.f - imp_x) * (1.f - imp_x));
+  } else {
+    imp_a = (1.0f / powf(mid, power - 1.f)) * powf(imp_x, power);
+    imp_b = 1.f - (1.0f / powf(1.f - mid, power - 1.f)) * powf(1.f - imp_x, power);
+  }
   float imp_y = imp_x < mid ? imp_a : imp_b;
   float imp = dmin + imp_y * (dmax - dmin);
   imp = fmaxf(dmin, fminf(imp, dmax));

@@ -1,0 +1,21 @@
+"""Small rollout for compute-sanitizer (memcheck / racecheck / initcheck):
+  compute-sanitizer --tool racecheck python tools/sanitize.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from brax_b200 import envs, workloads
+from brax_b200.generalized import pipeline
+
+dev = torch.device('cuda', 0)
+for model in ('ant', 'humanoid'):
+  sys_, q, qd = workloads.reset(model, 0, 37, 0, dev)
+  st = pipeline.init(sys_, q, qd)
+  for k in range(2):
+    st = pipeline.step(sys_, st, workloads.action(model, 0, 37, 0, k, dev), n_frames=5)
+  env = envs.create(model, episode_length=2, auto_reset=True, batch_size=21)
+  es = env.reset(0)
+  for k in range(3):
+    es = env.step(es, torch.zeros((21, env.action_size), device=dev))
+  torch.cuda.synchronize()
+  assert torch.isfinite(st.q).all() and torch.isfinite(es.obs).all()
+print('sanitize rollout ok')
