@@ -3,6 +3,7 @@
 // bxg_kernels.cuh and are instantiated per variant in bxg_inst.cu.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <string>
@@ -84,6 +85,7 @@ int bxg_model_create(const BxgModelDesc* desc, int device, BxgModel** out) {
   BxgModel* m = new BxgModel();
   std::string err = bxg::pack_model(*desc, &m->pm);
   if (!err.empty()) { delete m; return fail(BXG_E_UNSUPPORTED, err); }
+  if (const char* sl = getenv("BXG_SYNC_LEVEL")) m->pm.d.sync_level = atoi(sl);   // tuning knob
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
   if (ce != cudaSuccess || ndev == 0) { delete m; return fail(BXG_E_CUDA, "no CUDA device: this library has no CPU fallback"); }

@@ -1261,26 +1261,29 @@ BXG_HD void con_jacobian(X& ex, const Ctx& c) {
 // ------------------------------------------------------------------ pipeline
 template <class X, class Cfg>
 BXG_HD void update_position_terms(X& ex, const Ctx& c, Stats* st, bool exact_inverse) {
-  ex.cta_sync();
+  const int sl = c.D->sync_level;
   kinematics(ex, c);
   transform_com(ex, c);
-  ex.cta_sync();
+  if (sl & 8) ex.cta_sync();
   mass_matrix(ex, c);
-  ex.cta_sync();
+  if (sl & 16) ex.cta_sync();
   if (exact_inverse) spd_inverse(ex, c, c.s + c.D->s_M, c.s + c.D->s_Minv, c.s + c.D->s_scr, nullptr, 0.f);
   else minv_newton_schulz<X, Cfg>(ex, c, st);
-  ex.cta_sync();
+  if (sl & 2) ex.cta_sync();
   con_jacobian(ex, c);
 }
 
 // pipeline.step (pipeline.py:78-94)
 template <class X, class Cfg>
 BXG_HD void substep(X& ex, const Ctx& c, Stats* st) {
-  ex.cta_sync();
+  // CTA-wide phase alignment keeps the warps of a CTA on the same straight-line
+  // code (instruction-cache locality); sync_level trades that against barrier waits
+  const int sl = c.D->sync_level;
+  if (sl & 4) ex.cta_sync();
   dyn_forces(ex, c);
-  ex.cta_sync();
+  if (sl & 32) ex.cta_sync();
   con_force<X, Cfg>(ex, c, st);
-  ex.cta_sync();
+  if (sl & 1) ex.cta_sync();
   integrate(ex, c);
   update_position_terms<X, Cfg>(ex, c, st, c.D->ns_iters == 0 || c.D->minv_mode == BXG_MINV_CHOLESKY);
 }

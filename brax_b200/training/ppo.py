@@ -1,0 +1,187 @@
+"""PPO on the fused B200 env step (BASELINE config 5).
+
+The physics + env arithmetic is the hand-written kernel (one launch per env
+step for the whole batch); policy / value networks, GAE and Adam are ordinary
+PyTorch, as in the PyTorch agent the reference ships
+(`notebooks/training_torch.ipynb:94-480`): tanh-squashed diagonal Gaussian policy
+`[obs, 64, 64, 2*act]`, value `[obs, 64, 64, 1]`, running observation
+normalisation, clipped surrogate, entropy bonus.  Hyper-parameter names follow
+`brax/training/agents/ppo/train.py:176-230`.
+
+Multi-GPU: one process per GPU, env batch sharded by global env id (no
+collective in the rollout), gradients averaged with an NCCL all-reduce per
+minibatch -- the `lax.pmean` of `training/gradients.py:32`.
+"""
+from __future__ import annotations
+
+import math
+import time
+from typing import Callable, Dict, Optional
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from brax_b200 import envs
+
+
+class Agent(nn.Module):
+  def __init__(self, obs_size: int, act_size: int, hidden=(64, 64), entropy_cost=1e-2, discounting=0.97,
+               reward_scaling=10.0, lambda_=0.95, epsilon=0.3):
+    super().__init__()
+    def mlp(sizes):
+      layers = []
+      for i in range(len(sizes) - 1):
+        layers += [nn.Linear(sizes[i], sizes[i + 1]), nn.SiLU()]
+      return nn.Sequential(*layers[:-1])
+    self.policy = mlp([obs_size, *hidden, 2 * act_size])
+    self.value = mlp([obs_size, *hidden, 1])
+    self.register_buffer('num_steps', torch.zeros(()))
+    self.register_buffer('running_mean', torch.zeros(obs_size))
+    self.register_buffer('running_var', torch.zeros(obs_size))
+    self.entropy_cost, self.discounting, self.reward_scaling = entropy_cost, discounting, reward_scaling
+    self.lambda_, self.epsilon = lambda_, epsilon
+
+  @torch.no_grad()
+  def update_normalization(self, obs):
+    n = obs.shape[0] * obs.shape[1]
+    flat = obs.reshape(n, -1)
+    total = self.num_steps + n
+    delta = flat - self.running_mean
+    self.running_mean += delta.sum(0) / total
+    self.running_var += (delta * (flat - self.running_mean)).sum(0)
+    self.num_steps.copy_(total)
+
+  def normalize(self, obs):
+    var = self.running_var / (self.num_steps + 1.0)
+    return torch.clip((obs - self.running_mean) / (var.sqrt() + 1e-6), -5, 5)
+
+  @staticmethod
+  def dist_create(logits):
+    loc, scale = torch.chunk(logits, 2, dim=-1)
+    return loc, torch.nn.functional.softplus(scale) + 0.001
+
+  @staticmethod
+  def dist_log_prob(loc, scale, pre_tanh):
+    lp = -0.5 * ((pre_tanh - loc) / scale) ** 2 - 0.5 * math.log(2 * math.pi) - torch.log(scale)
+    lp = lp - 2 * (math.log(2) - pre_tanh - torch.nn.functional.softplus(-2 * pre_tanh))
+    return lp.sum(-1)
+
+  @staticmethod
+  def dist_entropy(loc, scale):
+    ent = 0.5 + 0.5 * math.log(2 * math.pi) + torch.log(scale)
+    sample = loc + scale * torch.randn_like(loc)
+    ent = ent + 2 * (math.log(2) - sample - torch.nn.functional.softplus(-2 * sample))
+    return ent.sum(-1)
+
+  @torch.no_grad()
+  def act(self, obs):
+    logits = self.policy(self.normalize(obs))
+    loc, scale = self.dist_create(logits)
+    pre = loc + scale * torch.randn_like(loc)
+    return torch.tanh(pre), logits, pre
+
+  @torch.no_grad()
+  def gae(self, truncation, termination, reward, values, bootstrap):
+    mask = 1.0 - truncation
+    values_t1 = torch.cat([values[1:], bootstrap[None]], 0)
+    deltas = (reward + self.discounting * (1 - termination) * values_t1 - values) * mask
+    acc = torch.zeros_like(bootstrap)
+    out = []
+    for t in range(deltas.shape[0] - 1, -1, -1):
+      acc = deltas[t] + self.discounting * (1 - termination[t]) * mask[t] * self.lambda_ * acc
+      out.append(acc)
+    vs = torch.stack(out[::-1]) + values
+    vs_t1 = torch.cat([vs[1:], bootstrap[None]], 0)
+    adv = (reward + self.discounting * (1 - termination) * vs_t1 - values) * mask
+    return vs, adv
+
+  def loss(self, td: Dict[str, torch.Tensor]):
+    obs = self.normalize(td['obs'])                       # [T+1, B, obs]
+    values = self.value(obs).squeeze(-1)
+    logits = self.policy(obs[:-1])
+    loc, scale = self.dist_create(logits)
+    beh_loc, beh_scale = self.dist_create(td['logits'])
+    lp = self.dist_log_prob(loc, scale, td['pre'])
+    blp = self.dist_log_prob(beh_loc, beh_scale, td['pre'])
+    reward = td['reward'] * self.reward_scaling
+    termination = td['done'] * (1 - td['truncation'])
+    vs, adv = self.gae(td['truncation'], termination, reward, values[:-1].detach(), values[-1].detach())
+    rho = torch.exp(lp - blp)
+    policy_loss = -torch.minimum(rho * adv, rho.clip(1 - self.epsilon, 1 + self.epsilon) * adv).mean()
+    v_loss = 0.25 * ((vs - values[:-1]) ** 2).mean()
+    ent_loss = -self.entropy_cost * self.dist_entropy(loc, scale).mean()
+    return policy_loss + v_loss + ent_loss
+
+
+def train(env_name: str = 'ant', num_envs: int = 2048, episode_length: int = 1000, num_timesteps: int = 1_000_000,
+          unroll_length: int = 5, batch_size: int = 1024, num_minibatches: int = 32, num_update_epochs: int = 4,
+          reward_scaling: float = 10.0, entropy_cost: float = 1e-2, discounting: float = 0.97, learning_rate: float = 3e-4,
+          seed: int = 0, device=None, progress_fn: Optional[Callable[[int, Dict[str, float]], None]] = None):
+  """Returns (agent, metrics).  metrics['sps'] = env-steps/sec including policy
+  inference and learning (the figure BASELINE config 5 asks for)."""
+  world = dist.get_world_size() if dist.is_initialized() else 1
+  rank = dist.get_rank() if dist.is_initialized() else 0
+  device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+  env = envs.create(env_name, episode_length=episode_length, auto_reset=True, batch_size=num_envs, device=device,
+                    env_id_offset=rank * num_envs)
+  torch.manual_seed(seed + rank)
+  agent = Agent(env.observation_size, env.action_size, entropy_cost=entropy_cost, discounting=discounting,
+                reward_scaling=reward_scaling).to(device)
+  if world > 1:
+    for p in agent.parameters():
+      dist.broadcast(p.data, 0)
+  opt = torch.optim.Adam(agent.parameters(), lr=learning_rate)
+  state = env.reset(seed)
+  # one training step consumes batch_size * num_minibatches trajectories of unroll_length steps
+  traj_per_step = batch_size * num_minibatches
+  rollouts_per_step = max(1, traj_per_step // num_envs)
+  steps_per_train_step = rollouts_per_step * num_envs * unroll_length * world
+  total, it = 0, 0
+  ep_reward = torch.zeros(num_envs, device=device)
+  finished_sum, finished_n = 0.0, 0
+  torch.cuda.synchronize()
+  t0 = time.perf_counter()
+  metrics: Dict[str, float] = {}
+  while total < num_timesteps:
+    obs_l, logit_l, pre_l, rew_l, done_l, trunc_l = [], [], [], [], [], []
+    for _ in range(rollouts_per_step):
+      o, lg, pr, rw, dn, tr = [state.obs], [], [], [], [], []
+      for _ in range(unroll_length):
+        action, logits, pre = agent.act(state.obs)
+        state = env.step(state, action)
+        o.append(state.obs); lg.append(logits); pr.append(pre)
+        rw.append(state.reward); dn.append(state.done); tr.append(state.info['truncation'])
+        ep_reward += state.reward
+        d = state.done > 0
+        if d.any():
+          finished_sum += float(ep_reward[d].sum()); finished_n += int(d.sum())
+          ep_reward = torch.where(d, torch.zeros_like(ep_reward), ep_reward)
+      obs_l.append(torch.stack(o)); logit_l.append(torch.stack(lg)); pre_l.append(torch.stack(pr))
+      rew_l.append(torch.stack(rw)); done_l.append(torch.stack(dn)); trunc_l.append(torch.stack(tr))
+    td = {'obs': torch.cat(obs_l, 1), 'logits': torch.cat(logit_l, 1), 'pre': torch.cat(pre_l, 1),
+          'reward': torch.cat(rew_l, 1), 'done': torch.cat(done_l, 1), 'truncation': torch.cat(trunc_l, 1)}
+    agent.update_normalization(td['obs'][:-1])
+    n_traj = td['reward'].shape[1]
+    for _ in range(num_update_epochs):
+      perm = torch.randperm(n_traj, device=device)
+      for mb in perm.chunk(num_minibatches):
+        loss = agent.loss({k: v[:, mb] for k, v in td.items()})
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if world > 1:   # lax.pmean(grad) of the reference, over NCCL
+          flat = torch.cat([p.grad.reshape(-1) for p in agent.parameters()])
+          dist.all_reduce(flat); flat /= world
+          off = 0
+          for p in agent.parameters():
+            p.grad.copy_(flat[off:off + p.numel()].view_as(p)); off += p.numel()
+        opt.step()
+    total += steps_per_train_step
+    it += 1
+    torch.cuda.synchronize()
+    metrics = {'sps': total / (time.perf_counter() - t0), 'loss': float(loss.detach()),
+               'episode_reward': finished_sum / max(finished_n, 1), 'env_steps': total, 'iterations': it}
+    if progress_fn and rank == 0:
+      progress_fn(total, metrics)
+    finished_sum, finished_n = 0.0, 0
+  return agent, metrics
