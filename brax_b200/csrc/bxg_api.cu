@@ -85,7 +85,8 @@ int bxg_model_create(const BxgModelDesc* desc, int device, BxgModel** out) {
   BxgModel* m = new BxgModel();
   std::string err = bxg::pack_model(*desc, &m->pm);
   if (!err.empty()) { delete m; return fail(BXG_E_UNSUPPORTED, err); }
-  if (const char* sl = getenv("BXG_SYNC_LEVEL")) m->pm.d.sync_level = atoi(sl);   // tuning knob
+  if (const char* sl = getenv("BXG_SYNC_LEVEL")) m->pm.d.sync_level = atoi(sl);   // tuning knobs
+  if (const char* pg = getenv("BXG_PHASE_GROUPS")) m->pm.d.phase_groups = atoi(pg);
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
   if (ce != cudaSuccess || ndev == 0) { delete m; return fail(BXG_E_CUDA, "no CUDA device: this library has no CPU fallback"); }

@@ -32,8 +32,10 @@
 
 #if defined(__CUDACC__)
 #define BXG_HD __host__ __device__ __forceinline__
+#define BXG_HD_NOINLINE static __host__ __device__ __noinline__   // one copy: keeps the per-substep code footprint small
 #else
 #define BXG_HD inline
+#define BXG_HD_NOINLINE inline
 #endif
 
 namespace bxg {
@@ -120,7 +122,7 @@ struct KernelCfg {
 };
 
 // constraint._imp_aref (brax/generalized/constraint.py:29-65)
-BXG_HD void imp_aref(const float* prm, float pos, float vel, float* imp_out, float* aref_out) {
+BXG_HD_NOINLINE void imp_aref(const float* prm, float pos, float vel, float* imp_out, float* aref_out) {
   float timeconst = prm[0], dampratio = prm[1], dmin = prm[2], dmax = prm[3], width = prm[4], mid = prm[5], power = prm[6];
   float imp_x = fabsf(pos) / width;
   float imp_a, imp_b;
@@ -745,6 +747,27 @@ BXG_HD void row_times_mat(const float* a, const float* B, int ldb, float* acc) {
     }
   }
 }
+// Same product with the left row read from shared memory (own row, 128-bit
+// chunks) and the k loop rolled: small code, no register-resident left operand.
+template <int K, int C4>
+BXG_HD void smem_row_times_mat(const float* arow_sm, const float* B, int ldb, float* acc) {
+#pragma unroll
+  for (int j = 0; j < 4 * C4; ++j) acc[j] = 0.f;
+#pragma unroll 1
+  for (int k0 = 0; k0 < K; k0 += 4) {
+    const F4 a4 = ldv4(arow_sm + k0);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const float ak = kk == 0 ? a4.x : kk == 1 ? a4.y : kk == 2 ? a4.z : a4.w;
+#pragma unroll
+      for (int cc = 0; cc < C4; ++cc) {
+        F4 b = ldv4(B + (k0 + kk) * ldb + 4 * cc);
+        acc[4 * cc + 0] += ak * b.x; acc[4 * cc + 1] += ak * b.y;
+        acc[4 * cc + 2] += ak * b.z; acc[4 * cc + 3] += ak * b.w;
+      }
+    }
+  }
+}
 template <int C4>
 BXG_HD void load_row(const float* p, float* r) {
 #pragma unroll
@@ -1043,16 +1066,16 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
       float* ar = arow(lane) + r * CW;
       if (p < na) {
         int i = nth_set_bit(am, p);
-        float jrow[VW], jm[VW];
-        load_row<VC4>(J + i * ldv, jrow);
-        row_times_mat<VW, VC4>(jrow, Mi, ldv, jm);
-        row_times_mat<VW, NC4>(jm, Jt, ldc, ar);
+        float jm[VW];
+        smem_row_times_mat<VW, VC4>(J + i * ldv, Mi, ldv, jm);        // (J Minv)[i, :]
+        store_row<VC4>(A + p * ldc, jm);                               // park it in this lane's own row of A
         float bacc = 0.f;
 #pragma unroll
         for (int cc = 0; cc < VC4; ++cc) {
           F4 f = ldv4(s + D.s_qfs + 4 * cc);
           bacc += jm[4 * cc] * f.x; bacc += jm[4 * cc + 1] * f.y; bacc += jm[4 * cc + 2] * f.z; bacc += jm[4 * cc + 3] * f.w;
         }
+        smem_row_times_mat<VW, NC4>(A + p * ldc, Jt, ldc, ar);         // A[p, :] = (J Minv)[i, :] J^T
         const float dg = s[D.s_diag + i];
 #pragma unroll
         for (int j = 0; j < CW; ++j) if (j == p) ar[j] += dg;

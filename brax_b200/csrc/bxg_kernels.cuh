@@ -18,6 +18,7 @@ struct DevExec {
   static constexpr int G = G_;
   int lane;
   unsigned mask;
+  int bar_id, bar_threads;   // named barrier of this warp's phase group
   struct LaneF {
     float v;
     __device__ __forceinline__ float& operator()(int) { return v; }
@@ -30,7 +31,9 @@ struct DevExec {
   __device__ __forceinline__ void sync() { __syncwarp(mask); }
   // CTA-wide phase alignment: every warp of the CTA streams the same straight-line
   // code at the same time, so instruction-cache lines are fetched once per CTA
-  __device__ __forceinline__ void cta_sync() { __syncthreads(); }
+  __device__ __forceinline__ void cta_sync() {
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
+  }
   template <class F>
   __device__ __forceinline__ void lanes(F&& f) {
     f(lane);
@@ -59,8 +62,19 @@ struct DevExec {
 constexpr int kMaxThreads = 512;   // CTA size is chosen per model at run time (bxg_api.cu)
 
 template <int G>
-__device__ __forceinline__ DevExec<G> make_exec() {
+__device__ __forceinline__ DevExec<G> make_exec(int phase_groups) {
   DevExec<G> ex;
+  // the warps of a CTA are split into `phase_groups` groups that align their
+  // phases independently (named barriers 1..): within a group the warps share
+  // instruction-cache lines, across groups FMA-bound and latency-bound phases overlap
+  {
+    const int nw = blockDim.x >> 5, w = threadIdx.x >> 5;
+    int pg = phase_groups < 1 ? 1 : (phase_groups > nw ? nw : phase_groups);
+    const int base = nw / pg, rem = nw % pg;      // first `rem` groups have base + 1 warps
+    int g = 0, start = 0;
+    for (; g < pg; ++g) { int sz = base + (g < rem ? 1 : 0); if (w < start + sz) { ex.bar_threads = sz * 32; break; } start += sz; }
+    ex.bar_id = 1 + g;
+  }
   int wl = threadIdx.x & 31;
   ex.lane = wl % G;
   ex.mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((wl / G) * G));
@@ -86,7 +100,7 @@ step_kernel(const Dims D, const uint32_t* __restrict__ model, const BxgState in,
   c.mf = reinterpret_cast<const float*>(smem_u);
   c.mi = reinterpret_cast<const int*>(smem_u);
   c.s = reinterpret_cast<float*>(smem_u) + D.model_words + group * D.env_words;
-  DevExec<G> ex = make_exec<G>();
+  DevExec<G> ex = make_exec<G>(D.phase_groups);
   // uniform trip count per CTA (phases are CTA-synchronous): groups past the end
   // of the batch redo the last env and skip the store
   const int64_t per_pass = (int64_t)gridDim.x * groups;
@@ -122,7 +136,7 @@ init_kernel(const Dims D, const uint32_t* __restrict__ model, const float* __res
   c.mf = reinterpret_cast<const float*>(smem_u);
   c.mi = reinterpret_cast<const int*>(smem_u);
   c.s = reinterpret_cast<float*>(smem_u) + D.model_words + group * D.env_words;
-  DevExec<G> ex = make_exec<G>();
+  DevExec<G> ex = make_exec<G>(D.phase_groups);
   const int64_t per_pass = (int64_t)gridDim.x * groups;
   const int64_t passes = (n_env + per_pass - 1) / per_pass;
   for (int64_t p = 0; p < passes; ++p) {

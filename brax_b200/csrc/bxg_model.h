@@ -25,6 +25,7 @@ struct Dims {
   int max_depth;  // deepest tree level
   int solver_iterations, solver_maxls, ns_iters, minv_mode;
   int force_generic;  // tests only: bypass the register-row kernels
+  int phase_groups;   // warps of a CTA align their phases in this many independent groups
   int sync_level;     // bit mask of CTA-wide phase alignments per substep: 1 after constraint.force, 2 after
                       // Newton-Schulz, 4 before dynamics, 8 before mass.matrix, 16 before N-S, 32 before constraint.force
   float dt, gx, gy, gz;
@@ -129,7 +130,7 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
   d.max_depth = 0;
   for (int l = 0; l < L; ++l) d.max_depth = depth[l] > d.max_depth ? depth[l] : d.max_depth;
   d.solver_iterations = m.solver_iterations; d.solver_maxls = m.solver_maxls;
-  d.ns_iters = m.matrix_inv_iterations; d.minv_mode = m.minv_mode; d.force_generic = 0; d.sync_level = 1;
+  d.ns_iters = m.matrix_inv_iterations; d.minv_mode = m.minv_mode; d.force_generic = 0; d.sync_level = 1; d.phase_groups = 1;
   d.dt = m.dt; d.gx = m.gravity[0]; d.gy = m.gravity[1]; d.gz = m.gravity[2];
 
   auto put_i = [&](const std::vector<int>& v) { int o = (int)b.size(); for (int x : v) b.push_back((uint32_t)x); return o; };

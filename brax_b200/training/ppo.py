@@ -139,7 +139,7 @@ def train(env_name: str = 'ant', num_envs: int = 2048, episode_length: int = 100
   steps_per_train_step = rollouts_per_step * num_envs * unroll_length * world
   total, it = 0, 0
   ep_reward = torch.zeros(num_envs, device=device)
-  finished_sum, finished_n = 0.0, 0
+  finished_sum = torch.zeros((), device=device); finished_n = torch.zeros((), device=device)   # no host sync in the rollout
   torch.cuda.synchronize()
   t0 = time.perf_counter()
   metrics: Dict[str, float] = {}
@@ -153,10 +153,8 @@ def train(env_name: str = 'ant', num_envs: int = 2048, episode_length: int = 100
         o.append(state.obs); lg.append(logits); pr.append(pre)
         rw.append(state.reward); dn.append(state.done); tr.append(state.info['truncation'])
         ep_reward += state.reward
-        d = state.done > 0
-        if d.any():
-          finished_sum += float(ep_reward[d].sum()); finished_n += int(d.sum())
-          ep_reward = torch.where(d, torch.zeros_like(ep_reward), ep_reward)
+        finished_sum += (ep_reward * state.done).sum(); finished_n += state.done.sum()
+        ep_reward = ep_reward * (1 - state.done)
       obs_l.append(torch.stack(o)); logit_l.append(torch.stack(lg)); pre_l.append(torch.stack(pr))
       rew_l.append(torch.stack(rw)); done_l.append(torch.stack(dn)); trunc_l.append(torch.stack(tr))
     td = {'obs': torch.cat(obs_l, 1), 'logits': torch.cat(logit_l, 1), 'pre': torch.cat(pre_l, 1),
@@ -180,8 +178,8 @@ def train(env_name: str = 'ant', num_envs: int = 2048, episode_length: int = 100
     it += 1
     torch.cuda.synchronize()
     metrics = {'sps': total / (time.perf_counter() - t0), 'loss': float(loss.detach()),
-               'episode_reward': finished_sum / max(finished_n, 1), 'env_steps': total, 'iterations': it}
+               'episode_reward': float(finished_sum) / max(float(finished_n), 1.0), 'env_steps': total, 'iterations': it}
     if progress_fn and rank == 0:
       progress_fn(total, metrics)
-    finished_sum, finished_n = 0.0, 0
+    finished_sum.zero_(); finished_n.zero_()
   return agent, metrics
