@@ -798,6 +798,7 @@ BXG_HD float row_dot(const float* a, const float* v) {
 // k loop stays rolled so the body lives in the instruction cache.
 template <int G, int W> struct Tile;
 template <> struct Tile<32, 24> { static constexpr int RG = 8, CG = 4, TM = 3, TN = 6; };
+template <> struct Tile<16, 24> { static constexpr int RG = 4, CG = 4, TM = 6, TN = 6; };
 template <> struct Tile<16, 16> { static constexpr int RG = 4, CG = 4, TM = 4, TN = 4; };
 template <> struct Tile<32, 32> { static constexpr int RG = 8, CG = 4, TM = 4, TN = 8; };
 struct alignas(8) F2 { float x, y; };
