@@ -284,6 +284,15 @@ def main():
     if args.workload in tj:
       traffic = tj[args.workload]['dram_bytes_per_env_step'] * r['n_env']
 
+  # algorithmic FLOPs per env-step at the reference iteration counts: Newton-Schulz
+  # (2*iters + 1 products of 2 nv^3), A = J Minv J^T, ~6.6 matvecs per solver iteration, O(L) terms
+  sysm = r['nm'].sys
+  nv_, nc_ = sysm.nv, native.num_constraints(sysm)
+  per_sub = ((2 * sysm.matrix_inv_iterations + 1) * 2 * nv_ ** 3 + 2 * nc_ * nv_ ** 2 + 2 * nc_ ** 2 * nv_
+             + sysm.solver_iterations * 6.6 * 2 * nc_ ** 2 + 20e3)
+  flops_per_env_step = per_sub * r['nf']
+  fp32_tflops = flops_per_env_step * r['n_env'] / (r['kern_avg_ms'] * 1e-3) / 1e12
+
   line = {
       'metric': 'env-steps/sec', 'value': r['value'], 'unit': 'env-steps/s', 'n_gpus': world,
       'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': r['ms_per_step'],
@@ -295,6 +304,9 @@ def main():
                    'traffic': traffic, 'peak_source': peak_src,
                    'algorithmic_bytes_per_env_step': workloads.ALGO_BYTES[model],
                    'note': 'step is FP32-FMA-bound (SURVEY 8d); see profiles/ for pipe utilisation'},
+      'fp32': {'achieved': fp32_tflops, 'peak': FP32_PEAK_TFLOPS, 'unit': 'TFLOP/s', 'frac': fp32_tflops / FP32_PEAK_TFLOPS,
+               'flops_per_env_step': flops_per_env_step,
+               'note': 'non-tensor FP32 FMA peak at max clock; the dense work is fp32 by the parity requirement'},
       'e2e': e2e, 'gpu_launches': r['launches'], 'clocks': r['clocks'],
       'kernel_ms': r['kern_avg_ms'], 'wall_ms_per_step': r['wall_ms_per_step'],
   }
