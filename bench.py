@@ -11,7 +11,7 @@ collective on the step path (scaling = weak: per-GPU envs fixed).
 Workloads (BASELINE.json `configs`):
   humanoid_8192  configs[1]  Humanoid, 8192 envs/GPU            (default at N=1)
   ant_1m         configs[2]  Ant, 1,048,576 envs/GPU
-  humanoid_512k  configs[3]  Humanoid, 524,288 envs/GPU, randomised falls
+  humanoid_512k  configs[3]  Humanoid, 524,288 envs/GPU (4 M over 8 GPUs), randomised falls
 """
 import argparse
 import json
@@ -28,7 +28,7 @@ if ROOT not in sys.path:
 WORKLOADS = {
     'humanoid_8192': ('humanoid', 8192),
     'ant_1m': ('ant', 1 << 20),
-    'humanoid_512k': ('humanoid', 1 << 19),
+    'humanoid_512k': ('humanoid_falls', 1 << 19),
     'ant_1024': ('ant', 1024),
 }
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # non-tensor FMA peak at max clock

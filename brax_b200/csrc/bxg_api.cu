@@ -61,6 +61,15 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 // every leaf must be non-null, except the constraint leaves of a model with no
 // constraint rows (their arrays have zero elements)
+// launches must go to the model's device whatever the caller's current device is
+struct DeviceGuard {
+  int prev = -1; bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
 bool state_ok(const BxgState* s, int nc) {
   if (!s) return false;
   const float* const* p = reinterpret_cast<const float* const*>(s);
@@ -163,6 +172,7 @@ int bxg_init(const BxgModel* m, int64_t n_env, const float* q, const float* qd, 
   if (n_env <= 0) return n_env == 0 ? BXG_OK : fail(BXG_E_INVALID, "n_env < 0");
   if (!q || !qd || !state_ok(out, m->pm.d.nc)) return fail(BXG_E_INVALID, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
+  DeviceGuard guard(m->device);
   int grid = grid_for(m, n_env, m->blocks_per_sm_init);
   BxgEnvSpec env{}; float* obs = nullptr;
   void* args[] = {(void*)&m->pm.d, (void*)&m->d_blob, (void*)&q, (void*)&qd, (void*)out, (void*)&n_env, (void*)&env, (void*)&obs};
@@ -182,6 +192,7 @@ int bxg_step(const BxgModel* m, int64_t n_env, int32_t n_frames, const BxgState*
   BxgDiag dg{nullptr, nullptr};
   if ((flags & BXG_STEP_DIAGNOSTICS) && diag) dg = *diag;
   cudaStream_t st = (cudaStream_t)stream;
+  DeviceGuard guard(m->device);
   int grid = grid_for(m, n_env, m->blocks_per_sm_step);
   int nf = n_frames, fl = flags;
   BxgEnvSpec env{}; BxgEnvIO eio{}; BxgState first{};
@@ -207,6 +218,7 @@ int bxg_env_reset(const BxgModel* m, const BxgEnvSpec* spec, int64_t n_env, cons
   if (n_env <= 0) return n_env == 0 ? BXG_OK : fail(BXG_E_INVALID, "n_env < 0");
   if (!q || !qd || !obs || !state_ok(out, m->pm.d.nc)) return fail(BXG_E_INVALID, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
+  DeviceGuard guard(m->device);
   int grid = grid_for(m, n_env, m->blocks_per_sm_init);
   BxgEnvSpec env = *spec;
   void* args[] = {(void*)&m->pm.d, (void*)&m->d_blob, (void*)&q, (void*)&qd, (void*)out, (void*)&n_env, (void*)&env, (void*)&obs};
@@ -228,6 +240,7 @@ int bxg_env_step(const BxgModel* m, const BxgEnvSpec* spec, int64_t n_env, int32
   if (io->first_state && (!state_ok(io->first_state, m->pm.d.nc) || !io->first_obs)) return fail(BXG_E_INVALID, "null first_state leaf");
   if (m->pm.d.nu > 0 && !action) return fail(BXG_E_INVALID, "action is NULL but the model has actuators");
   cudaStream_t st = (cudaStream_t)stream;
+  DeviceGuard guard(m->device);
   int grid = grid_for(m, n_env, m->blocks_per_sm_step);
   int nf = n_frames, fl = 0;
   BxgDiag dg{nullptr, nullptr};
