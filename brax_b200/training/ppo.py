@@ -117,7 +117,7 @@ class Agent(nn.Module):
 def train(env_name: str = 'ant', num_envs: int = 2048, episode_length: int = 1000, num_timesteps: int = 1_000_000,
           unroll_length: int = 5, batch_size: int = 1024, num_minibatches: int = 32, num_update_epochs: int = 4,
           reward_scaling: float = 10.0, entropy_cost: float = 1e-2, discounting: float = 0.97, learning_rate: float = 3e-4,
-          seed: int = 0, device=None, progress_fn: Optional[Callable[[int, Dict[str, float]], None]] = None):
+          seed: int = 0, device=None, use_cuda_graph: bool = True, progress_fn: Optional[Callable[[int, Dict[str, float]], None]] = None):
   """Returns (agent, metrics).  metrics['sps'] = env-steps/sec including policy
   inference and learning (the figure BASELINE config 5 asks for)."""
   world = dist.get_world_size() if dist.is_initialized() else 1
@@ -131,7 +131,8 @@ def train(env_name: str = 'ant', num_envs: int = 2048, episode_length: int = 100
   if world > 1:
     for p in agent.parameters():
       dist.broadcast(p.data, 0)
-  opt = torch.optim.Adam(agent.parameters(), lr=learning_rate)
+  opt = torch.optim.Adam(agent.parameters(), lr=learning_rate, capturable=use_cuda_graph)
+  sgd_graph = static_mb = static_loss = None
   state = env.reset(seed)
   # one training step consumes batch_size * num_minibatches trajectories of unroll_length steps
   traj_per_step = batch_size * num_minibatches
@@ -161,9 +162,38 @@ def train(env_name: str = 'ant', num_envs: int = 2048, episode_length: int = 100
           'reward': torch.cat(rew_l, 1), 'done': torch.cat(done_l, 1), 'truncation': torch.cat(trunc_l, 1)}
     agent.update_normalization(td['obs'][:-1])
     n_traj = td['reward'].shape[1]
+    mb_size = n_traj // num_minibatches
+    if use_cuda_graph and sgd_graph is None and world == 1:
+      # capture one minibatch update (loss, backward, Adam) into a CUDA graph: the
+      # learner is launch-bound (small MLPs), replay removes the per-op overhead
+      static_mb = {k: torch.empty_like(v[:, :mb_size]) for k, v in td.items()}
+      static_loss = torch.zeros((), device=device)
+      side = torch.cuda.Stream()
+      side.wait_stream(torch.cuda.current_stream())
+      with torch.cuda.stream(side):
+        for _ in range(3):   # warm-up outside capture (allocations, cuBLAS handles)
+          for k, v in td.items():
+            static_mb[k].copy_(v[:, :mb_size])
+          opt.zero_grad(set_to_none=True)
+          agent.loss(static_mb).backward()
+          opt.step()
+      torch.cuda.current_stream().wait_stream(side)
+      sgd_graph = torch.cuda.CUDAGraph()
+      opt.zero_grad(set_to_none=True)
+      with torch.cuda.graph(sgd_graph):
+        l_ = agent.loss(static_mb)
+        l_.backward()
+        opt.step()
+        static_loss.copy_(l_.detach())
     for _ in range(num_update_epochs):
       perm = torch.randperm(n_traj, device=device)
-      for mb in perm.chunk(num_minibatches):
+      for mb in perm[:mb_size * num_minibatches].view(num_minibatches, mb_size):
+        if sgd_graph is not None:
+          for k, v in td.items():
+            torch.index_select(v, 1, mb, out=static_mb[k])
+          sgd_graph.replay()
+          loss = static_loss
+          continue
         loss = agent.loss({k: v[:, mb] for k, v in td.items()})
         opt.zero_grad(set_to_none=True)
         loss.backward()

@@ -297,3 +297,37 @@ def test_full_size_properties_humanoid_8192():
   for k in range(3):
     half = pipeline.step(sys_, half, workloads.action('humanoid', n // 2, n // 2, 0, k, dev), n_frames=5)
   assert torch.equal(half.q, st.q[n // 2:])
+
+
+@pytest.mark.parametrize('n_legs', [3, 5, 7])
+def test_other_kernel_variants_on_gpu(n_legs):
+  """Synthetic multi-leg models reach the kernel variants Ant / Humanoid do not
+  (5 legs: 32-lane 4x8-tile variant; 7 legs: generic any-size kernel)."""
+  from brax_b200.generalized import pipeline
+  from brax_b200.io import mjcf
+  from oracle import oracle as O
+  from tests.synthetic_models import centipede_xml
+  torch = _torch()
+  dev = torch.device('cuda', 0)
+  sys_ = mjcf.loads(centipede_xml(n_legs))
+  rng = np.random.default_rng(0)
+  n = 96
+  q = (np.asarray(sys_.init_q)[None] + rng.uniform(-0.05, 0.05, (n, sys_.nq))).astype(np.float32)
+  q[:, 2] = 0.2 + 0.1 * rng.uniform(size=n)
+  qd = (0.1 * rng.standard_normal((n, sys_.nv))).astype(np.float32)
+  o = O.Oracle(sys_)
+  ref = o.init(q, qd)
+  got = _flat_np(pipeline.init(sys_, torch.as_tensor(q, device=dev), torch.as_tensor(qd, device=dev)))
+  for k in O.STATE_FIELDS:
+    scale = max(1.0, float(np.abs(ref[k]).max()))
+    np.testing.assert_allclose(got[k], ref[k], rtol=1e-4, atol=2e-5 * scale, err_msg=k)
+  errs = []
+  for k in range(10):
+    act = rng.uniform(-1, 1, (n, sys_.nu)).astype(np.float32)
+    st_in = _to_state(torch, ref, dev)
+    out = _flat_np(pipeline.step(sys_, st_in, torch.as_tensor(act, device=dev), n_frames=1))
+    o.step(ref, act, 1)
+    errs.append(_env_err(out, ref))
+    o.step(ref, act, 4)
+  errs = np.concatenate(errs)
+  assert np.median(errs) <= 0.1 and (errs <= 1.0).mean() >= 0.9, (np.median(errs), (errs <= 1.0).mean())
