@@ -929,7 +929,8 @@ BXG_HD void minv_newton_schulz_tiles(X& ex, const Ctx& c, Stats* st) {
     store_tile<T>(lane, B, ld, acc);
     p_sum(lane) = ss; p_max(lane) = mx;
   });
-  float ss0 = ex.sum(p_sum), mx0 = ex.max(p_max);
+  float ss0, mx0;
+  ex.sum_max(p_sum, p_max, &ss0, &mx0);
   float nrm0 = mx0 <= 1e-8f ? 0.f : sqrtf(ss0);
   if (nrm0 > 1.f) {
     // cold start 0.5 M^T / tr(M M^T); M is exactly symmetric
@@ -956,7 +957,8 @@ BXG_HD void minv_newton_schulz_tiles(X& ex, const Ctx& c, Stats* st) {
       store_tile<T>(lane, B, ld, acc);
       p_sum(lane) = ss; p_max(lane) = mx;
     });
-    float s2 = ex.sum(p_sum), m2 = ex.max(p_max);
+    float s2, m2;
+    ex.sum_max(p_sum, p_max, &s2, &m2);
     float err_next = m2 <= 1e-8f ? 0.f : sqrtf(s2);
     if (err_next < err) { float* t = Xc; Xc = Xn; Xn = t; st->ns_accepts++; }
     err = err_next;
@@ -1143,7 +1145,8 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
         }
         p0(lane) = a0; p1(lane) = a1; p2(lane) = a2;
       });
-      float sqdist = ex.sum(p0), vd = ex.sum(p1), fn = ex.sum(p2);
+      float sqdist, vd, fn;
+      ex.sum3(p0, p1, p2, &sqdist, &vd, &fn);
       st->pg_trials++;
       float fun_decrease = sz * (fn - fy);
       float condition = sz * vd + 0.5f * sqdist;

@@ -45,6 +45,26 @@ struct DevExec {
     for (int o = G / 2; o >= 1; o >>= 1) v += __shfl_xor_sync(mask, v, o, G);
     return v;
   }
+  // sum and max in one butterfly (two independent shuffle chains interleave)
+  __device__ __forceinline__ void sum_max(LaneF& ps, LaneF& pm, float* s_out, float* m_out) {
+    float a = ps.v, b = pm.v;
+#pragma unroll
+    for (int o = G / 2; o >= 1; o >>= 1) {
+      float a2 = __shfl_xor_sync(mask, a, o, G), b2 = __shfl_xor_sync(mask, b, o, G);
+      a += a2; b = fmaxf(b, b2);
+    }
+    *s_out = a; *m_out = b;
+  }
+  // three sums in one butterfly
+  __device__ __forceinline__ void sum3(LaneF& p0, LaneF& p1, LaneF& p2, float* o0, float* o1, float* o2) {
+    float a = p0.v, b = p1.v, c = p2.v;
+#pragma unroll
+    for (int o = G / 2; o >= 1; o >>= 1) {
+      float a2 = __shfl_xor_sync(mask, a, o, G), b2 = __shfl_xor_sync(mask, b, o, G), c2 = __shfl_xor_sync(mask, c, o, G);
+      a += a2; b += b2; c += c2;
+    }
+    *o0 = a; *o1 = b; *o2 = c;
+  }
   // bit l of the result = (lane l of this group holds a non-zero value)
   __device__ __forceinline__ uint32_t ballot(LaneF& p) {
     uint32_t b = __ballot_sync(mask, p.v != 0.f);

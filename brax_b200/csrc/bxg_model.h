@@ -275,6 +275,9 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
   }
   d.s_dist = take(m.ncon > 0 ? m.ncon : 1);
   d.s_red = take(8);
+  // half-warp variants put two envs in one warp: offset their slabs by 16 banks so that the
+  // two envs' broadcast row loads (64 B each) never share a bank
+  if (var.G == 16) while (o % 32 != 16) o += 4;
   d.env_words = o;
   return "";
 }

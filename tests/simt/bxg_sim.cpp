@@ -45,6 +45,8 @@ struct HostExec {
     for (int o = G / 2; o >= 1; o >>= 1) { for (int l = 0; l < G; ++l) b[l] = a[l] + a[l ^ o]; memcpy(a, b, sizeof a); }
     return a[0];
   }
+  void sum_max(LaneF& ps, LaneF& pm, float* s_out, float* m_out) { *s_out = sum(ps); *m_out = max(pm); }
+  void sum3(LaneF& p0, LaneF& p1, LaneF& p2, float* o0, float* o1, float* o2) { *o0 = sum(p0); *o1 = sum(p1); *o2 = sum(p2); }
   uint32_t ballot(LaneF& p) {
     uint32_t b = 0;
     for (int l = 0; l < G; ++l) if (p.v[l] != 0.f) b |= 1u << l;
