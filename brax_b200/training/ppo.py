@@ -141,23 +141,59 @@ def train(env_name: str = 'ant', num_envs: int = 2048, episode_length: int = 100
   total, it = 0, 0
   ep_reward = torch.zeros(num_envs, device=device)
   finished_sum = torch.zeros((), device=device); finished_n = torch.zeros((), device=device)   # no host sync in the rollout
+  metrics: Dict[str, float] = {}
+  # ---- rollout of `unroll_length` env steps; optionally one CUDA graph ----------------------------
+  from brax_b200.base import tree_map
+
+  def unroll(st, ep_rew, fsum, fnum):
+    o, lg, pr, rw, dn, tr = [st.obs], [], [], [], [], []
+    for _ in range(unroll_length):
+      action, logits, pre = agent.act(st.obs)
+      st = env.step(st, action)
+      o.append(st.obs); lg.append(logits); pr.append(pre)
+      rw.append(st.reward); dn.append(st.done); tr.append(st.info['truncation'])
+      ep_rew = ep_rew + st.reward
+      fsum = fsum + (ep_rew * st.done).sum(); fnum = fnum + st.done.sum()
+      ep_rew = ep_rew * (1 - st.done)
+    return st, ep_rew, fsum, fnum, (torch.stack(o), torch.stack(lg), torch.stack(pr), torch.stack(rw), torch.stack(dn), torch.stack(tr))
+
+  rollout_graph = None
+  if use_cuda_graph and world == 1:
+    # static state buffers: the graph reads them, steps, and writes the final state back in place
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+      for _ in range(2):   # warm-up (model upload, allocator, cuBLAS)
+        unroll(state, ep_reward, finished_sum, finished_n)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    static_state = state
+    rollout_graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(rollout_graph):
+      st2, er2, fs2, fn2, static_traj = unroll(static_state, ep_reward, finished_sum, finished_n)
+      # write the carried values back into the static inputs
+      def write_back(dst, src):
+        if isinstance(dst, torch.Tensor) and dst.data_ptr() != src.data_ptr():
+          dst.copy_(src)
+        return dst
+      tree_map(write_back, static_state.pipeline_state, st2.pipeline_state)
+      static_state.obs.copy_(st2.obs); static_state.reward.copy_(st2.reward); static_state.done.copy_(st2.done)
+      for k in ('steps', 'truncation'):
+        static_state.info[k].copy_(st2.info[k])
+      ep_reward.copy_(er2); finished_sum.copy_(fs2); finished_n.copy_(fn2)
+
   torch.cuda.synchronize()
   t0 = time.perf_counter()
-  metrics: Dict[str, float] = {}
   while total < num_timesteps:
     obs_l, logit_l, pre_l, rew_l, done_l, trunc_l = [], [], [], [], [], []
     for _ in range(rollouts_per_step):
-      o, lg, pr, rw, dn, tr = [state.obs], [], [], [], [], []
-      for _ in range(unroll_length):
-        action, logits, pre = agent.act(state.obs)
-        state = env.step(state, action)
-        o.append(state.obs); lg.append(logits); pr.append(pre)
-        rw.append(state.reward); dn.append(state.done); tr.append(state.info['truncation'])
-        ep_reward += state.reward
-        finished_sum += (ep_reward * state.done).sum(); finished_n += state.done.sum()
-        ep_reward = ep_reward * (1 - state.done)
-      obs_l.append(torch.stack(o)); logit_l.append(torch.stack(lg)); pre_l.append(torch.stack(pr))
-      rew_l.append(torch.stack(rw)); done_l.append(torch.stack(dn)); trunc_l.append(torch.stack(tr))
+      if rollout_graph is not None:
+        rollout_graph.replay()
+        traj = [t.clone() for t in static_traj]
+      else:
+        state, ep_reward, finished_sum, finished_n, traj = unroll(state, ep_reward, finished_sum, finished_n)
+      obs_l.append(traj[0]); logit_l.append(traj[1]); pre_l.append(traj[2])
+      rew_l.append(traj[3]); done_l.append(traj[4]); trunc_l.append(traj[5])
     td = {'obs': torch.cat(obs_l, 1), 'logits': torch.cat(logit_l, 1), 'pre': torch.cat(pre_l, 1),
           'reward': torch.cat(rew_l, 1), 'done': torch.cat(done_l, 1), 'truncation': torch.cat(trunc_l, 1)}
     agent.update_normalization(td['obs'][:-1])
