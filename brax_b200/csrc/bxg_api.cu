@@ -160,11 +160,29 @@ int bxg_plan(const BxgModelDesc* desc, int32_t info[8]) {
   return BXG_OK;
 }
 
-static int grid_for(const BxgModel* m, int64_t n_env, int blocks_per_sm) {
-  const int groups = m->groups;
-  int64_t need = (n_env + groups - 1) / groups;
-  int64_t cap = (int64_t)m->sm_count * blocks_per_sm;
-  return (int)(need < cap ? need : cap);
+// Launch shape for a batch.  The kernel is persistent (one CTA per SM, `passes`
+// sweeps over the batch).  With the largest CTA that fits an SM, small or awkward
+// batch sizes leave SMs idle or pay for a nearly empty last pass, so the number of
+// envs per CTA is chosen per call: minimise passes * (cost of one pass), where a
+// pass with e of e_max envs resident costs about (e_max + e) -- at least half of a
+// full pass is latency that more resident warps hide.
+struct LaunchShape { int grid, threads; size_t smem; };
+static LaunchShape launch_shape(const BxgModel* m, int64_t n_env) {
+  const int per_warp = 32 / m->lanes;
+  int best = m->groups; double best_cost = 1e300;
+  for (int e = per_warp; e <= m->groups; e += per_warp) {
+    int64_t ctas = (n_env + e - 1) / e;
+    int64_t grid = ctas < m->sm_count ? ctas : m->sm_count;
+    int64_t passes = (n_env + grid * e - 1) / (grid * e);
+    double cost = (double)passes * (1.0 * m->groups + e);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = e; }
+  }
+  int64_t ctas = (n_env + best - 1) / best;
+  LaunchShape ls;
+  ls.grid = (int)(ctas < m->sm_count ? ctas : m->sm_count);
+  ls.threads = best * m->lanes;
+  ls.smem = sizeof(uint32_t) * ((size_t)m->pm.d.model_words + (size_t)best * m->pm.d.env_words);
+  return ls;
 }
 
 int bxg_init(const BxgModel* m, int64_t n_env, const float* q, const float* qd, const BxgState* out, void* stream) {
@@ -173,10 +191,10 @@ int bxg_init(const BxgModel* m, int64_t n_env, const float* q, const float* qd, 
   if (!q || !qd || !state_ok(out, m->pm.d.nc)) return fail(BXG_E_INVALID, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
   DeviceGuard guard(m->device);
-  int grid = grid_for(m, n_env, m->blocks_per_sm_init);
+  LaunchShape ls = launch_shape(m, n_env);
   BxgEnvSpec env{}; float* obs = nullptr;
   void* args[] = {(void*)&m->pm.d, (void*)&m->d_blob, (void*)&q, (void*)&qd, (void*)out, (void*)&n_env, (void*)&env, (void*)&obs};
-  BXG_CUDA(cudaLaunchKernel(init_kernel_of(m->pm.variant_id), dim3(grid), dim3(m->threads), args, m->smem_bytes, st));
+  BXG_CUDA(cudaLaunchKernel(init_kernel_of(m->pm.variant_id), dim3(ls.grid), dim3(ls.threads), args, ls.smem, st));
   g_launches.fetch_add(1);
   BXG_CUDA(cudaGetLastError());
   return BXG_OK;
@@ -193,12 +211,12 @@ int bxg_step(const BxgModel* m, int64_t n_env, int32_t n_frames, const BxgState*
   if ((flags & BXG_STEP_DIAGNOSTICS) && diag) dg = *diag;
   cudaStream_t st = (cudaStream_t)stream;
   DeviceGuard guard(m->device);
-  int grid = grid_for(m, n_env, m->blocks_per_sm_step);
+  LaunchShape ls = launch_shape(m, n_env);
   int nf = n_frames, fl = flags;
   BxgEnvSpec env{}; BxgEnvIO eio{}; BxgState first{};
   void* args[] = {(void*)&m->pm.d, (void*)&m->d_blob, (void*)in, (void*)&act, (void*)out, (void*)&n_env, (void*)&nf, (void*)&fl, (void*)&dg,
                   (void*)&env, (void*)&eio, (void*)&first};
-  BXG_CUDA(cudaLaunchKernel(step_kernel_of(m->pm.variant_id), dim3(grid), dim3(m->threads), args, m->smem_bytes, st));
+  BXG_CUDA(cudaLaunchKernel(step_kernel_of(m->pm.variant_id), dim3(ls.grid), dim3(ls.threads), args, ls.smem, st));
   g_launches.fetch_add(1);
   BXG_CUDA(cudaGetLastError());
   return BXG_OK;
@@ -219,10 +237,10 @@ int bxg_env_reset(const BxgModel* m, const BxgEnvSpec* spec, int64_t n_env, cons
   if (!q || !qd || !obs || !state_ok(out, m->pm.d.nc)) return fail(BXG_E_INVALID, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
   DeviceGuard guard(m->device);
-  int grid = grid_for(m, n_env, m->blocks_per_sm_init);
+  LaunchShape ls = launch_shape(m, n_env);
   BxgEnvSpec env = *spec;
   void* args[] = {(void*)&m->pm.d, (void*)&m->d_blob, (void*)&q, (void*)&qd, (void*)out, (void*)&n_env, (void*)&env, (void*)&obs};
-  BXG_CUDA(cudaLaunchKernel(init_kernel_of(m->pm.variant_id), dim3(grid), dim3(m->threads), args, m->smem_bytes, st));
+  BXG_CUDA(cudaLaunchKernel(init_kernel_of(m->pm.variant_id), dim3(ls.grid), dim3(ls.threads), args, ls.smem, st));
   g_launches.fetch_add(1);
   BXG_CUDA(cudaGetLastError());
   return BXG_OK;
@@ -241,14 +259,14 @@ int bxg_env_step(const BxgModel* m, const BxgEnvSpec* spec, int64_t n_env, int32
   if (m->pm.d.nu > 0 && !action) return fail(BXG_E_INVALID, "action is NULL but the model has actuators");
   cudaStream_t st = (cudaStream_t)stream;
   DeviceGuard guard(m->device);
-  int grid = grid_for(m, n_env, m->blocks_per_sm_step);
+  LaunchShape ls = launch_shape(m, n_env);
   int nf = n_frames, fl = 0;
   BxgDiag dg{nullptr, nullptr};
   BxgEnvSpec env = *spec; BxgEnvIO eio = *io; BxgState first{};
   if (io->first_state) first = *io->first_state;
   void* args[] = {(void*)&m->pm.d, (void*)&m->d_blob, (void*)in, (void*)&action, (void*)out, (void*)&n_env, (void*)&nf, (void*)&fl, (void*)&dg,
                   (void*)&env, (void*)&eio, (void*)&first};
-  BXG_CUDA(cudaLaunchKernel(step_kernel_of(m->pm.variant_id), dim3(grid), dim3(m->threads), args, m->smem_bytes, st));
+  BXG_CUDA(cudaLaunchKernel(step_kernel_of(m->pm.variant_id), dim3(ls.grid), dim3(ls.threads), args, ls.smem, st));
   g_launches.fetch_add(1);
   BXG_CUDA(cudaGetLastError());
   return BXG_OK;

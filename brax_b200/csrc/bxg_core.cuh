@@ -838,7 +838,7 @@ BXG_HD void tile_matmul(int lane, const float* A, const float* B, int ld, float 
   for (int r = 0; r < T::TM; ++r)
 #pragma unroll
     for (int cc = 0; cc < T::TN / 2; ++cc) acc2[r][cc] = make_float2(0.f, 0.f);
-#pragma unroll 1
+#pragma unroll 2
   for (int k0 = 0; k0 < W; k0 += 4) {
     F4 a[T::TM];
 #pragma unroll
