@@ -96,10 +96,26 @@ def step(
 
 
 def _contact_debug(model, bufs):
-  # distances are produced by the step kernel's diagnostics; after init they are
-  # recomputed by a zero-frame step (loads and stores the state untouched)
+  """debug=True after init: plane-sphere penetration distances of the fresh state
+  (brax/contact.py:28-67 + mjx plane-sphere).  Debug-only host-side torch ops; the
+  step kernel produces the same quantity itself (BXG_STEP_DIAGNOSTICS)."""
+  import numpy as np
   n = bufs['q'].shape[0]
   diag = model.alloc_diag(n)
+  cp = model.sys.contact_pairs()
+  if len(cp.geom1) == 0:
+    return diag
+  dev = bufs['q'].device
+  lb = torch.as_tensor(np.asarray(cp.link_b, np.int64), device=dev)
+  pos, rot = bufs['x_pos'][:, lb], bufs['x_rot'][:, lb]          # [n, ncon, 3|4]
+  v = torch.as_tensor(np.asarray(cp.sphere_pos, np.float32), device=dev)[None].expand_as(pos)
+  s_, u = rot[..., :1], rot[..., 1:]
+  r = 2 * ((u * v).sum(-1, keepdim=True) * u) + (s_ * s_ - (u * u).sum(-1, keepdim=True)) * v + 2 * s_ * torch.cross(u, v, dim=-1)
+  sp = pos + r
+  nrm = torch.as_tensor(np.asarray(cp.plane_normal, np.float32), device=dev)[None]
+  pp = torch.as_tensor(np.asarray(cp.plane_pos, np.float32), device=dev)[None]
+  rad = torch.as_tensor(np.asarray(cp.radius, np.float32), device=dev)[None]
+  diag['con_dist'] = (((sp - pp) * nrm).sum(-1) - rad).contiguous()
   return diag
 
 

@@ -340,14 +340,17 @@ class NativeModel:
             'stats': torch.zeros((n, 4), dtype=torch.int32, device=dev)}
 
 
-_models: Dict[Tuple[int, int, int], NativeModel] = {}
-
-
 def model_for(sys, device: int, minv_mode: int = MINV_NEWTON_SCHULZ) -> NativeModel:
-  """Per-(System object, device, mode) cache of uploaded models."""
-  key = (id(sys), int(device), int(minv_mode))
-  m = _models.get(key)
-  if m is None or m.sys is not sys:
+  """Per-(System object, device, mode) cache of uploaded models.  The cache lives
+  on the System object itself, so it is released with it and a `sys.replace(...)`
+  copy (different constants) never sees a stale upload."""
+  cache = getattr(sys, '_bxg_models', None)
+  if cache is None:
+    cache = {}
+    object.__setattr__(sys, '_bxg_models', cache)   # System is a frozen dataclass
+  key = (int(device), int(minv_mode))
+  m = cache.get(key)
+  if m is None:
     m = NativeModel(sys, device, minv_mode)
-    _models[key] = m
+    cache[key] = m
   return m

@@ -331,3 +331,15 @@ def test_other_kernel_variants_on_gpu(n_legs):
     o.step(ref, act, 4)
   errs = np.concatenate(errs)
   assert np.median(errs) <= 0.1 and (errs <= 1.0).mean() >= 0.9, (np.median(errs), (errs <= 1.0).mean())
+
+
+def test_debug_contact_after_init_matches_step_diagnostics():
+  from brax_b200 import workloads
+  from brax_b200.generalized import pipeline
+  torch, dev, sys_, q, qd = _inputs('ant', 33)
+  q = q.clone(); q[:, 2] = 0.3                          # feet near the floor
+  st = pipeline.init(sys_, q, qd, debug=True)
+  # a zero-force comparison: the distances of the init state equal the oracle's
+  from oracle import oracle as O
+  ref = O.Oracle(sys_).init(q.cpu().numpy(), qd.cpu().numpy())
+  np.testing.assert_allclose(st.contact['con_dist'].cpu().numpy(), ref['con_dist'], rtol=1e-5, atol=1e-6)
