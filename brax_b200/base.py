@@ -187,11 +187,17 @@ class ContactPairs:
   """Static collision-pair table derived from the geoms (world link = -1).
 
   Restates what `mjx.make_data(sys).ncon` / `mjx.collision` enumerate for the
-  supported pair type (plane-sphere): contype/conaffinity filter, same-body and
-  parent-child exclusion, pairs emitted in (geom1 < geom2) order.
+  supported pair types: contype/conaffinity filter, same-body and parent-child
+  exclusion.  plane-sphere gives one contact per pair; plane-capsule gives two
+  (the capsule's end spheres, +axis first), emitted after the plane-sphere group
+  (mjx groups contacts by geom-type pair).  For capsules `frame` is only the
+  fallback: the tangent follows the capsule axis at run time.
   """
   geom1: np.ndarray        # (ncon,) plane geom
-  geom2: np.ndarray        # (ncon,) sphere geom
+  geom2: np.ndarray        # (ncon,) sphere / capsule geom
+  kind: np.ndarray         # (ncon,) 0 = plane-sphere, 1 = plane-capsule end point
+  geom_quat: np.ndarray    # (ncon,4) capsule orientation in link_b frame
+  half_len: np.ndarray     # (ncon,) signed half length: end point = centre + axis * half_len
   link_a: np.ndarray       # (ncon,) link of geom1 (-1 = world)
   link_b: np.ndarray       # (ncon,) link of geom2
   plane_pos: np.ndarray    # (ncon,3) world
@@ -310,7 +316,7 @@ class System(Base):
   def contact_pairs(self) -> ContactPairs:
     """Enumerates colliding geom pairs (see ContactPairs)."""
     ng = 0 if self.geom_type is None else len(self.geom_type)
-    rows = []
+    rows, caps = [], []
     for g1 in range(ng):
       for g2 in range(g1 + 1, ng):
         b1, b2 = int(self.geom_bodyid[g1]), int(self.geom_bodyid[g2])
@@ -326,13 +332,19 @@ class System(Base):
             self.link_parents[l1] == l2 or self.link_parents[l2] == l1):
           continue
         t1, t2 = int(self.geom_type[g1]), int(self.geom_type[g2])
-        if (t1, t2) != (0, 2):
+        if (t1, t2) not in ((0, 2), (0, 3)):
           raise NotImplementedError(
-              f'collision pair type ({t1},{t2}) not supported: only '
-              'plane-sphere (SURVEY.md section 8 a-11)')
+              f'collision pair type ({t1},{t2}) not supported: only plane-sphere and '
+              'plane-capsule (SURVEY.md section 8 a-11 / f-3)')
         if l1 != -1:
           raise NotImplementedError('planes must be attached to the world')
-        rows.append((g1, g2, l1, l2))
+        if t2 == 2:
+          rows.append((g1, g2, l1, l2, 0, 0.0))
+        else:
+          half = float(self.geom_size[g2][1])
+          caps.append((g1, g2, l1, l2, 1, half))
+          caps.append((g1, g2, l1, l2, 1, -half))
+    rows = rows + caps
     n = len(rows)
     f64 = np.float64
 
@@ -351,6 +363,8 @@ class System(Base):
       return np.stack([a, b, np.cross(a, b)])
 
     cp = dict(
+        kind=np.zeros(n, np.int32), geom_quat=np.tile(np.array([1, 0, 0, 0], np.float32), (n, 1)),
+        half_len=np.zeros(n, np.float32),
         geom1=np.zeros(n, np.int32), geom2=np.zeros(n, np.int32),
         link_a=np.zeros(n, np.int32), link_b=np.zeros(n, np.int32),
         plane_pos=np.zeros((n, 3), np.float32),
@@ -359,7 +373,9 @@ class System(Base):
         sphere_pos=np.zeros((n, 3), np.float32), radius=np.zeros(n, np.float32),
         friction=np.zeros(n, np.float32), solref=np.zeros((n, 2), np.float32),
         solimp=np.zeros((n, 5), np.float32))
-    for k, (g1, g2, l1, l2) in enumerate(rows):
+    for k, (g1, g2, l1, l2, kind, half) in enumerate(rows):
+      cp['kind'][k], cp['half_len'][k] = kind, half
+      cp['geom_quat'][k] = self.geom_quat[g2]
       nrm = quat_to_mat(np.asarray(self.geom_quat[g1], f64))[:, 2]
       cp['geom1'][k], cp['geom2'][k] = g1, g2
       cp['link_a'][k], cp['link_b'][k] = l1, l2

@@ -104,6 +104,28 @@ def _mat2q(m):
   return _qnorm(q)
 
 
+def _orientation(a: Dict[str, str], deg: bool) -> np.ndarray:
+  """quat | axisangle | euler (xyz, intrinsic) -> unit quaternion (MJCF orientation attributes)."""
+  if 'quat' in a:
+    return _qnorm(_vec(a['quat'], [1, 0, 0, 0]))
+  if 'axisangle' in a:
+    v = _vec(a['axisangle'], [0, 0, 1, 0])
+    ang = np.deg2rad(v[3]) if deg else v[3]
+    ax = v[:3] / np.linalg.norm(v[:3])
+    return np.concatenate([[_math.cos(ang / 2)], ax * _math.sin(ang / 2)])
+  if 'euler' in a:
+    e = _vec(a['euler'], [0, 0, 0])
+    e = np.deg2rad(e) if deg else e
+    q = np.array([1.0, 0, 0, 0])
+    for k in range(3):   # default eulerseq "xyz", intrinsic rotations
+      ax = np.eye(3)[k]
+      q = _qmul(q, np.concatenate([[_math.cos(e[k] / 2)], ax * _math.sin(e[k] / 2)]))
+    return _qnorm(q)
+  if 'xyaxes' in a or 'zaxis' in a:
+    raise NotImplementedError('xyaxes / zaxis orientations are not supported')
+  return np.array([1.0, 0, 0, 0])
+
+
 def _z_to(vec):
   """Quaternion rotating +z onto `vec` (MuJoCo mjuu_z2quat convention)."""
   v = vec / np.linalg.norm(vec)
@@ -254,7 +276,7 @@ class _Body:
                'iquat', 'inertia', 'mass')
 
 
-def _parse_geom(a: Dict[str, str], density_default=1000.0) -> _Geom:
+def _parse_geom(a: Dict[str, str], density_default=1000.0, deg: bool = True) -> _Geom:
   g = _Geom()
   g.name = a.get('name', '')
   tname = a.get('type', 'sphere')
@@ -264,9 +286,7 @@ def _parse_geom(a: Dict[str, str], density_default=1000.0) -> _Geom:
   size = _vec(a.get('size'), [0, 0, 0])
   size = np.concatenate([size, np.zeros(3 - len(size))]) if len(size) < 3 else size[:3]
   g.pos = _vec(a.get('pos'), [0, 0, 0])
-  g.quat = _qnorm(_vec(a.get('quat'), [1, 0, 0, 0]))
-  if 'euler' in a or 'axisangle' in a or 'xyaxes' in a or 'zaxis' in a:
-    raise NotImplementedError('geom orientation must be given as quat/fromto')
+  g.quat = _orientation(a, deg)
   if a.get('fromto'):
     if g.type not in (GEOM_CAPSULE, GEOM_CYLINDER, GEOM_BOX, GEOM_ELLIPSOID):
       raise NotImplementedError('fromto only for capsule/cylinder/box/ellipsoid')
@@ -507,7 +527,7 @@ def loads(xml: str) -> base.System:
   bodies: List[_Body] = []
   world_geoms: List[_Geom] = []
   for ge in world.findall('geom'):
-    g = _parse_geom(defaults.resolve(ge, 'geom', ge.attrib.get('class')))
+    g = _parse_geom(defaults.resolve(ge, 'geom', ge.attrib.get('class')), deg=deg)
     g.body = -1
     world_geoms.append(g)
 
@@ -517,9 +537,7 @@ def loads(xml: str) -> base.System:
       b = _Body()
       b.name = be.attrib.get('name', '')
       b.pos = _vec(be.attrib.get('pos'), [0, 0, 0])
-      b.quat = _qnorm(_vec(be.attrib.get('quat'), [1, 0, 0, 0]))
-      if 'euler' in be.attrib or 'axisangle' in be.attrib:
-        raise NotImplementedError('body orientation must be given as quat')
+      b.quat = _orientation(be.attrib, deg)
       b.parent = parent
       b.joints, b.geoms = [], []
       for je in list(be):
@@ -529,7 +547,7 @@ def loads(xml: str) -> base.System:
             a = dict(je.attrib)
           b.joints.append(_parse_joint(a, je.tag, deg))
       for ge in be.findall('geom'):
-        g = _parse_geom(defaults.resolve(ge, 'geom', ge.attrib.get('class', cc)))
+        g = _parse_geom(defaults.resolve(ge, 'geom', ge.attrib.get('class', cc)), deg=deg)
         b.geoms.append(g)
       if be.find('inertial') is not None:
         raise NotImplementedError('explicit <inertial> is not supported')
@@ -543,6 +561,12 @@ def loads(xml: str) -> base.System:
   walk(world, -1, None)
   if not bodies:
     raise ValueError('model has no bodies')
+  total = float(comp.get('settotalmass', -1))
+  if total > 0:   # compiler settotalmass: rescale every body's mass and inertia
+    scale = total / sum(b.mass for b in bodies)
+    for b in bodies:
+      b.mass *= scale
+      b.inertia = b.inertia * scale
   for b in bodies:
     if not b.joints:
       raise NotImplementedError('static non-world bodies are not supported')

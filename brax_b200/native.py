@@ -100,6 +100,8 @@ def make_desc(sys, minv_mode: int = MINV_NEWTON_SCHULZ) -> Tuple[ModelDesc, list
     return a.ctypes.data_as(_pi)
 
   cp = sys.contact_pairs()
+  if np.any(np.asarray(cp.kind) != 0):
+    raise NotImplementedError('plane-capsule contacts are not supported by this kernel build')
   d = ModelDesc()
   d.abi_version = 1
   d.num_links, d.nq, d.nv, d.nu = sys.num_links(), sys.nq, sys.nv, sys.nu
