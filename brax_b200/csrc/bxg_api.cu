@@ -11,29 +11,30 @@
 #include "bxg_model.h"
 
 namespace bxg {
-constexpr int kMaxThreads = 512;          // must match bxg_kernels.cuh
 constexpr size_t kSmemBudget = 227 * 1024;  // usable shared memory per SM on sm_100
 // envs per CTA: as many as fit the shared-memory budget of one SM (one CTA per
 // SM, all of its warps phase-aligned), whole warps only
-inline int envs_per_cta(const Dims& d, int G) {
+inline int envs_per_cta(const Dims& d, const Variant& var) {
+  const int G = var.G;
   size_t avail = kSmemBudget - sizeof(uint32_t) * (size_t)d.model_words;
   int n = (int)(avail / (sizeof(uint32_t) * (size_t)d.env_words));
   int per_warp = 32 / G;
   n -= n % per_warp;
-  int cap = kMaxThreads / G;
+  int cap = variant_max_threads(var.G, var.VC4) / G;
+  if (const char* e = getenv("BXG_MAX_ENVS_PER_CTA")) { int v = atoi(e); if (v >= per_warp && v < cap) cap = v - v % per_warp; }   // tuning knob
   return n > cap ? cap : n;
 }
 }
 
 extern "C" {
-const void* bxg_step_kernel_v0(); const void* bxg_step_kernel_v1(); const void* bxg_step_kernel_v2(); const void* bxg_step_kernel_v3();
-const void* bxg_init_kernel_v0(); const void* bxg_init_kernel_v1(); const void* bxg_init_kernel_v2(); const void* bxg_init_kernel_v3();
+const void* bxg_step_kernel_v0(); const void* bxg_step_kernel_v1(); const void* bxg_step_kernel_v2(); const void* bxg_step_kernel_v3(); const void* bxg_step_kernel_v4();
+const void* bxg_init_kernel_v0(); const void* bxg_init_kernel_v1(); const void* bxg_init_kernel_v2(); const void* bxg_init_kernel_v3(); const void* bxg_init_kernel_v4();
 }
 static const void* step_kernel_of(int v) {
-  switch (v) { case 0: return bxg_step_kernel_v0(); case 1: return bxg_step_kernel_v1(); case 2: return bxg_step_kernel_v2(); default: return bxg_step_kernel_v3(); }
+  switch (v) { case 0: return bxg_step_kernel_v0(); case 1: return bxg_step_kernel_v1(); case 2: return bxg_step_kernel_v2(); case 4: return bxg_step_kernel_v4(); default: return bxg_step_kernel_v3(); }
 }
 static const void* init_kernel_of(int v) {
-  switch (v) { case 0: return bxg_init_kernel_v0(); case 1: return bxg_init_kernel_v1(); case 2: return bxg_init_kernel_v2(); default: return bxg_init_kernel_v3(); }
+  switch (v) { case 0: return bxg_init_kernel_v0(); case 1: return bxg_init_kernel_v1(); case 2: return bxg_init_kernel_v2(); case 4: return bxg_init_kernel_v4(); default: return bxg_init_kernel_v3(); }
 }
 
 struct BxgModel {
@@ -92,7 +93,9 @@ int bxg_model_create(const BxgModelDesc* desc, int device, BxgModel** out) {
   if (!desc || !out) return fail(BXG_E_INVALID, "null argument");
   *out = nullptr;
   BxgModel* m = new BxgModel();
-  std::string err = bxg::pack_model(*desc, &m->pm);
+  int force_variant = -1;
+  if (const char* fv = getenv("BXG_FORCE_VARIANT")) force_variant = atoi(fv);   // tuning knob (e.g. 4: Humanoid class on half-warps)
+  std::string err = bxg::pack_model(*desc, &m->pm, force_variant);
   if (!err.empty()) { delete m; return fail(BXG_E_UNSUPPORTED, err); }
   if (const char* sl = getenv("BXG_SYNC_LEVEL")) m->pm.d.sync_level = atoi(sl);   // tuning knobs
   if (const char* pg = getenv("BXG_PHASE_GROUPS")) m->pm.d.phase_groups = atoi(pg);
@@ -111,7 +114,7 @@ int bxg_model_create(const BxgModelDesc* desc, int device, BxgModel** out) {
   cudaDeviceProp prop;
   if ((ce = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cleanup(cuda_fail(ce, "cudaGetDeviceProperties"));
   m->sm_count = prop.multiProcessorCount;
-  const int groups = bxg::envs_per_cta(D, m->lanes);
+  const int groups = bxg::envs_per_cta(D, bxg::variant(m->pm.variant_id));
   if (groups < 1) return cleanup(fail(BXG_E_UNSUPPORTED, "one env does not fit the shared memory of an SM"));
   m->groups = groups; m->threads = groups * m->lanes;
   m->smem_bytes = sizeof(uint32_t) * ((size_t)D.model_words + (size_t)groups * D.env_words);
@@ -153,7 +156,7 @@ int bxg_plan(const BxgModelDesc* desc, int32_t info[8]) {
   bxg::PackedModel pm;
   std::string err = bxg::pack_model(*desc, &pm);
   if (!err.empty()) return fail(BXG_E_UNSUPPORTED, err);
-  const int G = bxg::variant(pm.variant_id).G, groups = bxg::envs_per_cta(pm.d, G);
+  const int G = bxg::variant(pm.variant_id).G, groups = bxg::envs_per_cta(pm.d, bxg::variant(pm.variant_id));
   info[0] = pm.variant_id; info[1] = G; info[2] = pm.d.model_words; info[3] = pm.d.env_words; info[4] = groups;
   info[5] = (int32_t)(sizeof(uint32_t) * ((size_t)pm.d.model_words + (size_t)groups * pm.d.env_words));
   info[6] = pm.d.nc; info[7] = 0;

@@ -118,6 +118,7 @@ struct Stats { int pg_iters, pg_trials, ns_accepts, ns_cold; };
 template <int G_, int VC4_, int NC4_, bool GENERIC_TOO_ = false>
 struct KernelCfg {
   static constexpr int G = G_, VC4 = VC4_, NC4 = NC4_;
+  static constexpr int MAX_THREADS = variant_max_threads(G_, VC4_);
   static constexpr bool GENERIC_TOO = GENERIC_TOO_ || VC4_ == 0;
 };
 
@@ -236,7 +237,7 @@ BXG_HD void con_force_generic(X& ex, const Ctx& c, Stats* st) {
     ex.lanes([&](int lane) { for (int d = lane; d < nv; d += X::G) s[D.s_qfc + d] = 0.f; });
     return;
   }
-  float* J = s + D.s_J; float* Mi = s + D.s_Minv;
+  float* J = s + D.s_J; float* Mi = s + D.s_Minv; const int jld = D.jld;
   float* JM = s + D.s_JM; float* A = s + D.s_A;
   float* b = s + D.s_b; float* x = s + D.s_px; float* y = s + D.s_py; float* g = s + D.s_pg;
   float* res = s + D.s_pres; float* xn = s + D.s_pxn;
@@ -245,16 +246,16 @@ BXG_HD void con_force_generic(X& ex, const Ctx& c, Stats* st) {
     for (int i = lane; i < nc; i += X::G) {
       for (int j = 0; j < nv; ++j) {
         float acc = 0.f;
-        for (int k = 0; k < nv; ++k) acc += J[i * nvp + k] * Mi[k * nvp + j];
-        JM[i * nvp + j] = acc;
+        for (int k = 0; k < nv; ++k) acc += J[i * jld + k] * Mi[k * nvp + j];
+        JM[i * jld + j] = acc;
       }
       for (int j = 0; j < nc; ++j) {
         float acc = 0.f;
-        for (int k = 0; k < nv; ++k) acc += JM[i * nvp + k] * J[j * nvp + k];
+        for (int k = 0; k < nv; ++k) acc += JM[i * jld + k] * J[j * jld + k];
         A[i * ncp + j] = acc + (i == j ? s[D.s_diag + i] : 0.f);
       }
       float acc = 0.f;
-      for (int k = 0; k < nv; ++k) acc += JM[i * nvp + k] * s[D.s_qfs + k];
+      for (int k = 0; k < nv; ++k) acc += JM[i * jld + k] * s[D.s_qfs + k];
       b[i] = acc - s[D.s_aref + i];
       x[i] = 0.f; y[i] = 0.f;
     }
@@ -326,7 +327,7 @@ BXG_HD void con_force_generic(X& ex, const Ctx& c, Stats* st) {
   ex.lanes([&](int lane) {
     for (int j = lane; j < nv; j += X::G) {
       float acc = 0.f;
-      for (int i = 0; i < nc; ++i) acc += J[i * nvp + j] * x[i];
+      for (int i = 0; i < nc; ++i) acc += J[i * jld + j] * x[i];
       s[D.s_qfc + j] = acc;
     }
   });
@@ -824,9 +825,9 @@ BXG_HD void store_cols(float* p, const float* v) {
   }
 }
 
-// acc[r][c] = sum_k A[row0 + r][k] * B[k][col0 + c], k ascending
+// acc[r * TN + c] = sum_k A[row0 + r][k] * B[k][col0 + c], k ascending
 template <class T, int W>
-BXG_HD void tile_matmul(int lane, const float* A, const float* B, int ld, float (&acc)[T::TM][T::TN]) {
+BXG_HD void tile_matmul(int lane, const float* A, const float* B, int ld, float* acc) {
   const int rg = lane / T::CG, cg = lane - rg * T::CG;
   const float* a0 = A + rg * T::TM * ld;
   const float* b0 = B + cg * T::TN;
@@ -860,12 +861,12 @@ BXG_HD void tile_matmul(int lane, const float* A, const float* B, int ld, float 
 #pragma unroll
   for (int r = 0; r < T::TM; ++r)
 #pragma unroll
-    for (int cc = 0; cc < T::TN / 2; ++cc) { acc[r][2 * cc] = acc2[r][cc].x; acc[r][2 * cc + 1] = acc2[r][cc].y; }
+    for (int cc = 0; cc < T::TN / 2; ++cc) { acc[r * T::TN + 2 * cc] = acc2[r][cc].x; acc[r * T::TN + 2 * cc + 1] = acc2[r][cc].y; }
 #else
 #pragma unroll
   for (int r = 0; r < T::TM; ++r)
 #pragma unroll
-    for (int cc = 0; cc < T::TN; ++cc) acc[r][cc] = 0.f;
+    for (int cc = 0; cc < T::TN; ++cc) acc[r * T::TN + cc] = 0.f;
 #pragma unroll 1
   for (int k0 = 0; k0 < W; k0 += 4) {
     F4 a[T::TM];
@@ -879,7 +880,7 @@ BXG_HD void tile_matmul(int lane, const float* A, const float* B, int ld, float 
       for (int r = 0; r < T::TM; ++r) {
         const float av = kk == 0 ? a[r].x : kk == 1 ? a[r].y : kk == 2 ? a[r].z : a[r].w;
 #pragma unroll
-        for (int cc = 0; cc < T::TN; ++cc) acc[r][cc] += av * bv[cc];
+        for (int cc = 0; cc < T::TN; ++cc) acc[r * T::TN + cc] += av * bv[cc];
       }
     }
   }
@@ -889,7 +890,7 @@ BXG_HD void tile_matmul(int lane, const float* A, const float* B, int ld, float 
 // residual tile r = I - acc (identity only on real rows), accumulates the
 // Frobenius partials and overwrites acc with I + r for the next product
 template <class T>
-BXG_HD void residual_tile(int lane, int n, float (&acc)[T::TM][T::TN], float* ss, float* mx) {
+BXG_HD void residual_tile(int lane, int n, float* acc, float* ss, float* mx) {
   const int rg = lane / T::CG, cg = lane - rg * T::CG;
 #pragma unroll
   for (int r = 0; r < T::TM; ++r)
@@ -897,19 +898,24 @@ BXG_HD void residual_tile(int lane, int n, float (&acc)[T::TM][T::TN], float* ss
     for (int cc = 0; cc < T::TN; ++cc) {
       const int i = rg * T::TM + r, j = cg * T::TN + cc;
       const bool diag = i == j && i < n;
-      float res = (diag ? 1.f : 0.f) - acc[r][cc];
+      float res = (diag ? 1.f : 0.f) - acc[r * T::TN + cc];
       *ss += res * res; *mx = fmaxf(*mx, fabsf(res));
-      acc[r][cc] = diag ? 1.f + res : res;
+      acc[r * T::TN + cc] = diag ? 1.f + res : res;
     }
 }
 template <class T>
-BXG_HD void store_tile(int lane, float* C, int ld, const float (&acc)[T::TM][T::TN]) {
+BXG_HD void store_tile(int lane, float* C, int ld, const float* acc) {
   const int rg = lane / T::CG, cg = lane - rg * T::CG;
 #pragma unroll
-  for (int r = 0; r < T::TM; ++r) store_cols<T::TN>(C + (rg * T::TM + r) * ld + cg * T::TN, acc[r]);
+  for (int r = 0; r < T::TM; ++r) store_cols<T::TN>(C + (rg * T::TM + r) * ld + cg * T::TN, acc + r * T::TN);
 }
 
 // math.inv_approximate (brax/math.py:278-305) on W x W zero-padded matrices.
+// Shared memory holds M, the current estimate X and ONE more buffer Q.  A product's
+// result tile waits in registers until every lane has finished reading the operand
+// it replaces: the candidate X (I + r) overwrites I + r (dead once the product is
+// formed: the next residual is computed from M and the candidate), and the next
+// I + r' overwrites whichever of X / candidate lost the comparison.
 template <class X, int W>
 BXG_HD void minv_newton_schulz_tiles(X& ex, const Ctx& c, Stats* st) {
   using T = Tile<X::G, W>;
@@ -918,15 +924,15 @@ BXG_HD void minv_newton_schulz_tiles(X& ex, const Ctx& c, Stats* st) {
   const float* M = s + D.s_M;
   float* Xa = s + D.s_Minv;
   float* Xc = Xa;                      // current estimate
-  float* Xn = s + D.s_Xn;              // candidate
-  float* B = s + D.s_B;                // I + r
+  float* Q = s + D.s_B;                // I + r, then the candidate
   typename X::LaneF p_sum, p_max;
+  typename X::template LaneVec<T::TM * T::TN> tile;
   // r0 = I - M X
   ex.lanes([&](int lane) {
-    float acc[T::TM][T::TN], ss = 0.f, mx = 0.f;
+    float* acc = tile(lane); float ss = 0.f, mx = 0.f;
     tile_matmul<T, W>(lane, M, Xc, ld, acc);
     residual_tile<T>(lane, n, acc, &ss, &mx);
-    store_tile<T>(lane, B, ld, acc);
+    store_tile<T>(lane, Q, ld, acc);
     p_sum(lane) = ss; p_max(lane) = mx;
   });
   float ss0, mx0;
@@ -945,22 +951,21 @@ BXG_HD void minv_newton_schulz_tiles(X& ex, const Ctx& c, Stats* st) {
   }
   float err = 1.f;
   for (int it = 0; it < D.ns_iters; ++it) {
-    ex.lanes([&](int lane) {       // candidate = X (I + r)
-      float acc[T::TM][T::TN];
-      tile_matmul<T, W>(lane, Xc, B, ld, acc);
-      store_tile<T>(lane, Xn, ld, acc);
-    });
+    ex.lanes([&](int lane) { tile_matmul<T, W>(lane, Xc, Q, ld, tile(lane)); });   // candidate = X (I + r)
+    ex.lanes([&](int lane) { store_tile<T>(lane, Q, ld, tile(lane)); });           // ... replaces I + r
     ex.lanes([&](int lane) {       // r' = I - M candidate
-      float acc[T::TM][T::TN], ss = 0.f, mx = 0.f;
-      tile_matmul<T, W>(lane, M, Xn, ld, acc);
+      float* acc = tile(lane); float ss = 0.f, mx = 0.f;
+      tile_matmul<T, W>(lane, M, Q, ld, acc);
       residual_tile<T>(lane, n, acc, &ss, &mx);
-      store_tile<T>(lane, B, ld, acc);
       p_sum(lane) = ss; p_max(lane) = mx;
     });
     float s2, m2;
     ex.sum_max(p_sum, p_max, &s2, &m2);
     float err_next = m2 <= 1e-8f ? 0.f : sqrtf(s2);
-    if (err_next < err) { float* t = Xc; Xc = Xn; Xn = t; st->ns_accepts++; }
+    const bool accept = err_next < err;
+    float* dst = accept ? Xc : Q;     // I + r' replaces the loser
+    ex.lanes([&](int lane) { store_tile<T>(lane, dst, ld, tile(lane)); });
+    if (accept) { float* t = Xc; Xc = Q; Q = t; st->ns_accepts++; }
     err = err_next;
   }
   if (Xc != Xa) ex.lanes([&](int lane) { for (int i = lane; i < W * ld; i += X::G) Xa[i] = Xc[i]; });
@@ -1003,16 +1008,18 @@ BXG_HD int nth_set_bit(uint32_t m, int n) {
 // b, the objective, the gradient and J^T x and their x stays 0: dropping them
 // leaves every sum unchanged.  The na active rows are compacted to rows
 // 0..na-1 (lane p owns compact rows p and p+G): A = (J Minv) J^T + diag is built
-// with the row of A in registers, FISTA + backtracking line search as in
+// row by row against the active rows of J (no transposed copy), the row of A then
+// stays in registers for FISTA + backtracking line search as in
 // jaxopt.ProjectedGradient (see oracle/bxg_oracle.c).  VC4 = nvw/4, NC4 = ncw/4.
 template <class X, int VC4, int NC4, int R>
 BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
   constexpr int VW = 4 * VC4, CW = 4 * NC4, G = X::G;
   const Dims& D = *c.D; float* s = c.s;
-  const int nv = D.nv, nc = D.nc, ldv = D.nvp, ldc = D.ncp;
+  const int nv = D.nv, nc = D.nc, ldv = D.nvp, ldj = D.jld, ldc = D.ncp;
   const float* J = s + D.s_J; const float* Mi = s + D.s_Minv;
-  float* Jt = s + D.s_Jt; float* A = s + D.s_A;
+  float* A = s + D.s_A;
   float* xs = s + D.s_px; float* ys = s + D.s_py; float* ress = s + D.s_pres; float* xns = s + D.s_pxn;
+  int* orig = reinterpret_cast<int*>(s + D.s_pg);   // compact row -> row of J
   typename X::template LaneVec<R * CW> arow;
   typename X::template LaneVec<R> bi, xi, yi, gi, xni, resi;
   typename X::LaneF p0, p1, p2;
@@ -1025,7 +1032,7 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
       float flag = 0.f;
       if (i < nc) {
         bool nz = s[D.s_diag + i] != 0.f || s[D.s_aref + i] != 0.f;
-        for (int k = 0; k < nv && !nz; ++k) nz = J[i * ldv + k] != 0.f;
+        for (int k = 0; k < nv && !nz; ++k) nz = J[i * ldj + k] != 0.f;
         flag = nz ? 1.f : 0.f;
       }
       p0(lane) = flag;
@@ -1044,50 +1051,57 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
   }
   const int nch = (na + 3) >> 2;           // float4 chunks that hold active columns
   ex.lanes([&](int lane) {
-    for (int i = lane; i < VW * ldc; i += G) Jt[i] = 0.f;
     for (int i = lane; i < CW; i += G) { xs[i] = 0.f; ys[i] = 0.f; xns[i] = 0.f; ress[i] = 0.f; }
-  });
-  // J^T over the active rows: Jt[k][p] = J[orig(p)][k]
-  ex.lanes([&](int lane) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      int p = lane + r * G;
-      if (p < na) {
-        int i = nth_set_bit(am, p);
-        float jrow[VW];
-        load_row<VC4>(J + i * ldv, jrow);
-#pragma unroll
-        for (int k = 0; k < VW; ++k) Jt[k * ldc + p] = jrow[k];
-      }
-    }
+    for (int r = 0; r < R; ++r) { int p = lane + r * G; if (p < CW) orig[p] = p < na ? nth_set_bit(am, p) : -1; }
   });
-  // A = (J Minv) J^T + diag, b = (J Minv) qf_smooth - aref on the compact rows
+  // b = (J Minv) qf_smooth - aref;  A[p, q] = (J Minv)[orig p, :] . J[orig q, :] + diag,
+  // four active columns at a time (rows of J are broadcast 128-bit loads feeding four
+  // independent k-ascending chains).  The row goes to shared memory for the column
+  // reads of the gradient and stays in registers for the row products.
   ex.lanes([&](int lane) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       int p = lane + r * G;
       float* ar = arow(lane) + r * CW;
+#pragma unroll
+      for (int j = 0; j < CW; ++j) ar[j] = 0.f;
+      bi(lane)[r] = 0.f;
       if (p < na) {
-        int i = nth_set_bit(am, p);
+        const int i = orig[p];
         float jm[VW];
-        smem_row_times_mat<VW, VC4>(J + i * ldv, Mi, ldv, jm);        // (J Minv)[i, :]
-        store_row<VC4>(A + p * ldc, jm);                               // park it in this lane's own row of A
+        smem_row_times_mat<VW, VC4>(J + i * ldj, Mi, ldv, jm);        // (J Minv)[i, :]
         float bacc = 0.f;
 #pragma unroll
         for (int cc = 0; cc < VC4; ++cc) {
           F4 f = ldv4(s + D.s_qfs + 4 * cc);
           bacc += jm[4 * cc] * f.x; bacc += jm[4 * cc + 1] * f.y; bacc += jm[4 * cc + 2] * f.z; bacc += jm[4 * cc + 3] * f.w;
         }
-        smem_row_times_mat<VW, NC4>(A + p * ldc, Jt, ldc, ar);         // A[p, :] = (J Minv)[i, :] J^T
-        const float dg = s[D.s_diag + i];
-#pragma unroll
-        for (int j = 0; j < CW; ++j) if (j == p) ar[j] += dg;
         bi(lane)[r] = bacc - s[D.s_aref + i];
-        store_row<NC4>(A + p * ldc, ar);
-      } else {
+        const float dg = s[D.s_diag + i];
+        float* arow_sm = A + p * ldc;
+#pragma unroll 1
+        for (int qc = 0; qc < nch; ++qc) {
+          float a4[4];
 #pragma unroll
-        for (int j = 0; j < CW; ++j) ar[j] = 0.f;
-        bi(lane)[r] = 0.f;
+          for (int u = 0; u < 4; ++u) {
+            const int q = 4 * qc + u, iq = orig[q];
+            const float* jq = J + (iq < 0 ? i : iq) * ldj;
+            float acc = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < VC4; ++cc) {
+              F4 b = ldv4(jq + 4 * cc);
+              acc += jm[4 * cc] * b.x; acc += jm[4 * cc + 1] * b.y; acc += jm[4 * cc + 2] * b.z; acc += jm[4 * cc + 3] * b.w;
+            }
+            if (q == p) acc += dg;
+            a4[u] = iq < 0 ? 0.f : acc;
+          }
+          stv4(arow_sm + 4 * qc, F4{a4[0], a4[1], a4[2], a4[3]});
+        }
+#pragma unroll
+        for (int cc = 0; cc < NC4; ++cc) {
+          if (cc < nch) { F4 v = ldv4(arow_sm + 4 * cc); ar[4 * cc] = v.x; ar[4 * cc + 1] = v.y; ar[4 * cc + 2] = v.z; ar[4 * cc + 3] = v.w; }
+        }
       }
       xi(lane)[r] = 0.f; yi(lane)[r] = 0.f; gi(lane)[r] = 0.f; xni(lane)[r] = 0.f; resi(lane)[r] = 0.f;
     }
@@ -1183,12 +1197,12 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
     ++it;
     st->pg_iters++;
   }
-  // qf_constraint = J^T x: lane j owns row j of Jt
+  // qf_constraint = J^T x over the active rows (lanes read consecutive columns of J)
   ex.lanes([&](int lane) {
     for (int j = lane; j < nv; j += G) {
-      float jt[CW];
-      load_row<NC4>(Jt + j * ldc, jt);
-      s[D.s_qfc + j] = row_dot_n<NC4>(jt, xs, nch);
+      float acc = 0.f;
+      for (int p = 0; p < na; ++p) acc += J[orig[p] * ldj + j] * xs[p];
+      s[D.s_qfc + j] = acc;
     }
   });
 }
@@ -1213,7 +1227,7 @@ BXG_HD void con_force(X& ex, const Ctx& c, Stats* st) {
 template <class X>
 BXG_HD void con_jacobian(X& ex, const Ctx& c) {
   const Dims& D = *c.D; const float* mf = c.mf; const int* mi = c.mi; float* s = c.s;
-  const int nv = D.nv, nvp = D.nvp;
+  const int nv = D.nv, nvp = D.jld;
   float* J = s + D.s_J;
   // J shares its slot with Newton-Schulz scratch: clear it (limit rows and the
   // padding columns rely on zeros)
@@ -1321,7 +1335,7 @@ BXG_HD void init_env(X& ex, const Ctx& c, Stats* st) {
   const Dims& D = *c.D; float* s = c.s;
   ex.lanes([&](int lane) {
     for (int i = lane; i < D.nv; i += X::G) { s[D.s_qfs + i] = 0.f; s[D.s_qfc + i] = 0.f; s[D.s_qdd + i] = 0.f; }
-    for (int i = lane; i < (D.nc > 0 ? D.nc : 1) * D.nvp; i += X::G) s[D.s_J + i] = 0.f;
+    for (int i = lane; i < (D.nc > 0 ? D.nc : 1) * D.jld; i += X::G) s[D.s_J + i] = 0.f;
   });
   update_position_terms<X, Cfg>(ex, c, st, true);
 }
@@ -1335,8 +1349,9 @@ BXG_HD void prepare_env(X& ex, const Ctx& c) {
   ex.lanes([&](int lane) {
     const int G = X::G;
     for (int i = lane; i < D.nvw * D.nvp; i += G) { s[D.s_M + i] = 0.f; s[D.s_Minv + i] = 0.f; }
-    for (int i = lane; i < ncz * D.nvp; i += G) s[D.s_J + i] = 0.f;
-    for (int i = lane; i < D.nvw; i += G) { s[D.s_tau + i] = 0.f; s[D.s_qfs + i] = 0.f; s[D.s_qfc + i] = 0.f; s[D.s_qdd + i] = 0.f; }
+    for (int i = lane; i < ncz * D.jld; i += G) s[D.s_J + i] = 0.f;
+    for (int i = lane; i < D.nvw; i += G) s[D.s_qfs + i] = 0.f;   // read 128 bits at a time: the padding must be zero
+    for (int i = lane; i < D.nv; i += G) { s[D.s_qfc + i] = 0.f; s[D.s_qdd + i] = 0.f; }
     for (int i = lane; i < D.ncw; i += G) { s[D.s_b + i] = 0.f; s[D.s_px + i] = 0.f; s[D.s_py + i] = 0.f; s[D.s_pg + i] = 0.f; s[D.s_pres + i] = 0.f; s[D.s_pxn + i] = 0.f; }
   });
 }
@@ -1534,7 +1549,7 @@ BXG_HD void load_env(X& ex, const Ctx& c, const BxgState& g, const float* act, i
     }
     for (int i = lane; i < nc * nv; i += G) {
       int r = i / nv, cc = i - r * nv;
-      s[D.s_J + r * nvp + cc] = g.con_jac[e * nc * nv + i];
+      s[D.s_J + r * D.jld + cc] = g.con_jac[e * nc * nv + i];
     }
     for (int i = lane; i < nc; i += G) { s[D.s_diag + i] = g.con_diag[e * nc + i]; s[D.s_aref + i] = g.con_aref[e * nc + i]; }
   });
@@ -1579,7 +1594,7 @@ BXG_HD void store_env(X& ex, const Ctx& c, const BxgState& g, int64_t e, const B
     }
     for (int i = lane; i < nc * nv; i += G) {
       int r = i / nv, cc = i - r * nv;
-      g.con_jac[e * nc * nv + i] = s[D.s_J + r * nvp + cc];
+      g.con_jac[e * nc * nv + i] = s[D.s_J + r * D.jld + cc];
     }
     for (int i = lane; i < nc; i += G) { g.con_diag[e * nc + i] = s[D.s_diag + i]; g.con_aref[e * nc + i] = s[D.s_aref + i]; }
     if (dg) {

@@ -79,7 +79,6 @@ struct DevExec {
   }
 };
 
-constexpr int kMaxThreads = 512;   // CTA size is chosen per model at run time (bxg_api.cu)
 
 template <int G>
 __device__ __forceinline__ DevExec<G> make_exec(int phase_groups) {
@@ -107,7 +106,7 @@ __device__ __forceinline__ void stage_model(const Dims& D, const uint32_t* __res
 }
 
 template <class Cfg>
-__global__ void __launch_bounds__(kMaxThreads)
+__global__ void __launch_bounds__(Cfg::MAX_THREADS)
 step_kernel(const Dims D, const uint32_t* __restrict__ model, const BxgState in, const float* __restrict__ act,
             const BxgState out, int64_t n_env, int n_frames, int flags, const BxgDiag diag,
             const BxgEnvSpec env, const BxgEnvIO eio, const BxgState first) {
@@ -144,7 +143,7 @@ step_kernel(const Dims D, const uint32_t* __restrict__ model, const BxgState in,
 }
 
 template <class Cfg>
-__global__ void __launch_bounds__(kMaxThreads)
+__global__ void __launch_bounds__(Cfg::MAX_THREADS)
 init_kernel(const Dims D, const uint32_t* __restrict__ model, const float* __restrict__ q, const float* __restrict__ qd,
             const BxgState out, int64_t n_env, const BxgEnvSpec env, float* __restrict__ obs) {
   extern __shared__ __align__(16) uint32_t smem_u[];

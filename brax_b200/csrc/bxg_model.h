@@ -20,8 +20,9 @@ namespace bxg {
 struct Dims {
   int L, nq, nv, nu, ncon, nlim, nc;
   int nvw, ncw;   // nv / nc rounded up to the register-row widths the kernels are built for
-  int nvp;        // row stride (floats) of matrices with nv columns: multiple of 4, (nvp/4) odd
-  int ncp;        // row stride (floats) of matrices with nc columns: multiple of 4, (ncp/4) odd
+  int nvp;        // row stride (floats) of M, Minv and the Newton-Schulz buffer (see mat_stride)
+  int jld;        // row stride (floats) of J: nvw (rows 16-byte aligned)
+  int ncp;        // row stride (floats) of A: ncw
   int max_depth;  // deepest tree level
   int solver_iterations, solver_maxls, ns_iters, minv_mode;
   int force_generic;  // tests only: bypass the register-row kernels
@@ -51,14 +52,16 @@ struct Dims {
   int s_f_ang, s_f_vel;        // [L,3] x2 temps: cfrc (RNE) / joint frame pos
   int s_j_rot;                 // [L,4] joint frame rot
   int s_crb_pos, s_crb_i, s_crb_mass;   // alias the t/f temporaries (different phases)
-  // Matrices.  In the specialised variants three slots are time-shared:
-  //   slot0 {M | A}   slot1 {Newton-Schulz candidate | J}   slot2 {I + r | J^T}
-  // (M, candidate, I+r live from mass.matrix to the end of Newton-Schulz; J from
-  // constraint.jacobian to the end of constraint.force of the NEXT substep; J^T, A
+  // Matrices.  In the specialised variants Minv has its own slot and two more are
+  // time-shared:   slot0 {M | A}   slot1 {Newton-Schulz ping-pong buffer | J}
+  // (M lives from mass.matrix to the end of Newton-Schulz, and after the last
+  // substep until store_env; the Newton-Schulz buffer holds I + r and the candidate
+  // in turn and trades places with Minv's slot when a candidate is accepted; J lives
+  // from constraint.jacobian to the end of constraint.force of the NEXT substep; A
   // inside constraint.force).  The generic variant keeps them apart.
-  int s_M, s_Minv, s_Xn, s_B, s_J, s_Jt, s_A, s_JM;
+  int s_M, s_Minv, s_Xn, s_B, s_J, s_A, s_JM;
   int s_scr;                   // generic path / Cholesky scratch (2 matrices)
-  int s_diag, s_aref, s_b, s_px, s_py, s_pg, s_pres, s_pxn;  // solver vectors alias the t/f temporaries
+  int s_diag, s_aref, s_b, s_px, s_py, s_pg, s_pres, s_pxn;  // solver vectors (b..pxn) alias the t/f temporaries
   int s_dist;                  // [ncon]
   int s_red;                   // [8] scalars
   int env_words;
@@ -73,15 +76,28 @@ inline int row_stride(int w) { int c = w / 4; return 4 * (c | 1); }
 // Kernel variants that are compiled (bxg_kernels.cu).  A model takes the first
 // variant it fits; the last one is the generic any-size kernel.
 struct Variant { int G, VC4, NC4, max_links, max_nv, max_nc; };
-constexpr int kNumVariants = 4;
+constexpr int kNumVariants = 4;     // auto-selected; ids past it are reachable only by forcing them
+constexpr int kNumVariantsAll = 5;
 inline Variant variant(int id) {
   switch (id) {
     case 0: return {16, 4, 6, 16, 16, 24};   // Ant class: half-warp per env
-    case 1: return {32, 6, 7, 32, 24, 28};   // Humanoid class: warp per env (a half-warp variant measured 7% slower)
+    case 1: return {32, 6, 7, 32, 24, 28};   // Humanoid class: warp per env
     case 2: return {32, 8, 8, 32, 32, 32};
+    case 4: return {16, 6, 7, 16, 24, 28};   // Humanoid class on a half-warp (6x6 tiles); forced only
     default: return {32, 0, 0, 32, 64, 64};  // generic
   }
 }
+// Row stride of the nv-column matrices.  The register-tile products read TM rows per
+// lane row-group: the stride must keep the row-groups of one 128-bit load phase (8
+// lanes) in distinct banks.  24 floats does for the 24-wide variants (rows 3 or 6
+// apart: 72 / 144 floats); the 16- and 32-wide ones need the odd chunk count.
+inline int mat_stride(const Variant& v, int w) { return v.VC4 == 6 ? w : row_stride(w); }
+// Largest CTA a variant is launched with (its __launch_bounds__): half-warp variants
+// fill an SM's shared memory with fewer threads and can keep more registers each.
+#ifndef BXG_G32_MAXT
+#define BXG_G32_MAXT 608
+#endif
+constexpr int variant_max_threads(int G, int VC4) { return G == 16 ? (VC4 == 6 ? 320 : 416) : BXG_G32_MAXT; }
 inline bool variant_fits(const Variant& v, int L, int nv, int nc) { return L <= v.max_links && nv <= v.max_nv && nc <= v.max_nc; }
 
 struct PackedModel {
@@ -121,12 +137,12 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
   if (d.nc > 64) return "more than 64 constraint rows not supported";
   int vid = force_variant;
   if (vid < 0) for (vid = 0; vid < kNumVariants - 1; ++vid) if (variant_fits(variant(vid), L, m.nv, d.nc)) break;
-  if (vid >= kNumVariants || !variant_fits(variant(vid), L, m.nv, d.nc)) return "model does not fit the requested kernel variant";
+  if (vid >= kNumVariantsAll || !variant_fits(variant(vid), L, m.nv, d.nc)) return "model does not fit the requested kernel variant";
   out->variant_id = vid;
   const Variant var = variant(vid);
   d.nvw = var.VC4 ? 4 * var.VC4 : (m.nv + 3) & ~3;
   d.ncw = var.NC4 ? 4 * var.NC4 : ((d.nc > 0 ? d.nc : 1) + 3) & ~3;
-  d.nvp = row_stride(d.nvw); d.ncp = row_stride(d.ncw);
+  d.nvp = mat_stride(var, d.nvw); d.jld = d.nvw; d.ncp = d.ncw;
   d.max_depth = 0;
   for (int l = 0; l < L; ++l) d.max_depth = depth[l] > d.max_depth ? depth[l] : d.max_depth;
   d.solver_iterations = m.solver_iterations; d.solver_maxls = m.solver_maxls;
@@ -226,27 +242,38 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
   d.model_words = (int)b.size();
 
   // ---- per-env slab ----
+  // Only what is read with 128-bit loads is 16-byte aligned and padded (matrices, qf_smooth,
+  // the solver vectors); everything else is packed to its exact size: shared memory per env
+  // decides how many envs an SM holds, and throughput follows that number.
   int o = 0;
-  auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
+  auto take = [&](int n) { o = (o + 3) & ~3; int r = o; o += n; return r; };   // aligned start
+  auto take1 = [&](int n) { int r = o; o += n; return r; };                     // packed
   const int nvv = m.nv, nc = d.nc, ncz = nc > 0 ? nc : 1;
-  d.s_q = take(m.nq); d.s_qd = take(nvv); d.s_act = take(m.nu > 0 ? m.nu : 1);
-  d.s_tau = take(d.nvw); d.s_qfs = take(d.nvw); d.s_qfc = take(d.nvw); d.s_qdd = take(d.nvw);
-  d.s_x_pos = take(L * 3); d.s_x_rot = take(L * 4); d.s_xd_ang = take(L * 3); d.s_xd_vel = take(L * 3);
-  d.s_root_com = take(L * 3);
-  d.s_cinr_pos = take(L * 3); d.s_cinr_rot = take(L * 4); d.s_cinr_i = take(L * 9); d.s_cinr_mass = take(L);
-  d.s_cd_ang = take(L * 3); d.s_cd_vel = take(L * 3);
-  d.s_cdof_ang = take(nvv * 3); d.s_cdof_vel = take(nvv * 3);
-  d.s_cdofd_ang = take(nvv * 3); d.s_cdofd_vel = take(nvv * 3);
+  d.s_q = take1(m.nq); d.s_qd = take1(nvv); d.s_act = take1(m.nu > 0 ? m.nu : 1);
+  d.s_qfc = take1(nvv); d.s_qdd = take1(nvv);
+  d.s_x_pos = take1(L * 3); d.s_x_rot = take1(L * 4); d.s_xd_ang = take1(L * 3); d.s_xd_vel = take1(L * 3);
+  d.s_root_com = take1(L * 3);
+  d.s_cinr_pos = take1(L * 3); d.s_cinr_rot = take1(L * 4); d.s_cinr_i = take1(L * 9); d.s_cinr_mass = take1(L);
+  d.s_cd_ang = take1(L * 3); d.s_cd_vel = take1(L * 3);
+  d.s_cdof_ang = take1(nvv * 3); d.s_cdof_vel = take1(nvv * 3);
+  d.s_cdofd_ang = take1(nvv * 3); d.s_cdofd_vel = take1(nvv * 3);
+  d.s_diag = take1(ncz); d.s_aref = take1(ncz);
+  d.s_qfs = take(d.nvw);
   const bool shared_slots = var.VC4 > 0 && m.matrix_inv_iterations > 0 && m.minv_mode == BXG_MINV_NEWTON_SCHULZ;
   // union of phase-local temporaries: kinematics / RNE / com temps, composite
-  // inertias (CRBA) and the constraint-solver vectors never live at the same time
+  // inertias (CRBA) and the constraint-solver vectors never live at the same time.
+  // tau (actuator.to_tau) lives from the start of dynamics to qf_smooth and, for the
+  // COM-kind env, from the epilogue's actuator pass to the observation: it takes the
+  // place of the joint-frame rotations, which only kinematics uses.
   {
+    o = (o + 3) & ~3;
     int base = o;
-    d.s_t_ang = take(L * 3); d.s_t_vel = take(L * 3); d.s_f_ang = take(L * 3); d.s_f_vel = take(L * 3);
-    d.s_j_rot = take(L * 4);
+    d.s_t_ang = take1(L * 3); d.s_t_vel = take1(L * 3); d.s_f_ang = take1(L * 3); d.s_f_vel = take1(L * 3);
+    d.s_j_rot = take1(L * 4 > nvv ? L * 4 : nvv);
+    d.s_tau = d.s_j_rot;
     int end_tf = o;
     o = base;
-    d.s_crb_pos = take(L * 3); d.s_crb_i = take(L * 9); d.s_crb_mass = take(L);
+    d.s_crb_pos = take1(L * 3); d.s_crb_i = take1(L * 9); d.s_crb_mass = take1(L);
     int end_crb = o;
     o = base;
     d.s_b = take(d.ncw); d.s_px = take(d.ncw); d.s_py = take(d.ncw); d.s_pg = take(d.ncw); d.s_pres = take(d.ncw); d.s_pxn = take(d.ncw);
@@ -254,27 +281,26 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
     o = end_tf > end_crb ? end_tf : end_crb;
     o = o > end_pg ? o : end_pg;
   }
-  d.s_diag = take(ncz); d.s_aref = take(ncz);
   // matrices with nv columns keep nvw rows: rows/columns past nv stay zero so the
   // register-tile kernels can run their loops to the compile-time width
   const int mat_v = d.nvw * d.nvp;          // [nvw][nvp]
-  const int mat_j = ncz * d.nvp;            // J   [nc][nvp]
-  const int mat_jt = d.nvw * d.ncp;         // J^T [nvw][ncp]
+  const int mat_j = ncz * d.jld;            // J   [nc][jld]
   const int mat_a = ncz * d.ncp;            // A   [nc][ncp]
   auto mx = [](int a, int b) { return a > b ? a : b; };
   d.s_Minv = take(mat_v);
   if (shared_slots) {
-    int s0 = take(mx(mat_v, mat_a)), s1 = take(mx(mat_v, mat_j)), s2 = take(mx(mat_v, mat_jt));
-    d.s_M = s0; d.s_A = s0; d.s_Xn = s1; d.s_J = s1; d.s_B = s2; d.s_Jt = s2;
+    int s0 = take(mx(mat_v, mat_a)), s1 = take(mx(mat_v, mat_j));
+    d.s_M = s0; d.s_A = s0; d.s_Xn = s1; d.s_B = s1; d.s_J = s1;
     d.s_JM = s0; d.s_scr = s1;  // unused by the specialised kernels
   } else {
     d.s_M = take(mat_v); d.s_J = take(mat_j);
     d.s_scr = take(2 * mat_v);            // Cholesky: dst/Lm; generic Newton-Schulz: candidate, I + r
     d.s_Xn = d.s_scr; d.s_B = d.s_scr + mat_v;
-    d.s_Jt = take(mat_jt); d.s_A = take(mat_a); d.s_JM = take(mat_j);
+    d.s_A = take(mat_a); d.s_JM = take(mat_j);
   }
-  d.s_dist = take(m.ncon > 0 ? m.ncon : 1);
-  d.s_red = take(8);
+  d.s_dist = take1(m.ncon > 0 ? m.ncon : 1);
+  d.s_red = take1(8);
+  o = (o + 3) & ~3;
   // half-warp variants put two envs in one warp: offset their slabs by 16 banks so that the
   // two envs' broadcast row loads (64 B each) never share a bank
   if (var.G == 16) while (o % 32 != 16) o += 4;

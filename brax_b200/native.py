@@ -170,11 +170,12 @@ def lib() -> ctypes.CDLL:
   global _lib
   with _lib_lock:
     if _lib is None:
-      if not os.path.exists(LIB_PATH):
+      path = os.environ.get('BXG_LIB', LIB_PATH)   # tuning: an alternative build of the same library
+      if not os.path.exists(path):
         raise RuntimeError(
-            f'{LIB_PATH} is missing: build it with `python -c "import '
+            f'{path} is missing: build it with `python -c "import '
             '__graft_entry__ as g; g.build()"`. There is no CPU fallback.')
-      l = ctypes.CDLL(LIB_PATH)
+      l = ctypes.CDLL(path)
       l.bxg_last_error.restype = ctypes.c_char_p
       l.bxg_launch_count.restype = ctypes.c_int64
       l.bxg_model_create.argtypes = [ctypes.POINTER(ModelDesc), ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]

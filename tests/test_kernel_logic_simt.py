@@ -39,7 +39,7 @@ def test_ant_generic_kernels_bit_exact_vs_oracle(ant):
       assert np.array_equal(a['con_dist'], b['con_dist'])
 
 
-@pytest.mark.parametrize('model,G', [('ant', 0), ('ant', 1), ('ant', 2), ('humanoid', 1), ('humanoid', 2), ('humanoid', 3)])
+@pytest.mark.parametrize('model,G', [('ant', 0), ('ant', 1), ('ant', 2), ('ant', 4), ('humanoid', 1), ('humanoid', 2), ('humanoid', 3), ('humanoid', 4)])
 def test_register_row_kernels_match_oracle(model, G, ant, humanoid):
   """The register-row kernels (Newton-Schulz, constraint solve) replace sequential
   sums by group reductions, so they agree with the oracle to rounding, not to the
@@ -95,15 +95,15 @@ def test_humanoid_matches_oracle(humanoid):
     o.step(b, act, 4)
 
 
-@pytest.mark.parametrize('model', ['ant', 'humanoid'])
-def test_no_intra_phase_lane_dependency(model, ant, humanoid):
+@pytest.mark.parametrize('model,variant', [('ant', -1), ('humanoid', -1), ('humanoid', 4)])
+def test_no_intra_phase_lane_dependency(model, variant, ant, humanoid):
   """Forward vs reverse lane order inside every phase must give identical bits:
   a difference would be a shared-memory race on the device.  The emulator also
   poisons the slab with NaN per env, so stale reads would surface here."""
   s = {'ant': ant, 'humanoid': humanoid}[model]
   n = 4
   q, qd = _inputs(s, model, n)
-  fw, rv = Sim(s), Sim(s, reverse=True)
+  fw, rv = Sim(s, variant=variant), Sim(s, variant=variant, reverse=True)
   a, b = fw.init(q, qd), rv.init(q, qd)
   for k in range(5):
     act = _acts(model, n, k)
