@@ -38,6 +38,13 @@
 #define BXG_HD_NOINLINE inline
 #endif
 
+// k-loop unroll of the register-tile product (in blocks of 4 k-steps)
+#ifndef BXG_TILE_UNROLL
+#define BXG_TILE_UNROLL 2
+#endif
+#define BXG_PRAGMA_(x) _Pragma(#x)
+#define BXG_PRAGMA_UNROLL(n) BXG_PRAGMA_(unroll n)
+
 namespace bxg {
 
 // ------------------------------------------------------------------ algebra
@@ -191,7 +198,13 @@ BXG_HD void dyn_forces(X& ex, const Ctx& c) {
         cv = cv + ld3(s + D.s_cdofd_vel + 3 * (da + k)) * qd;
       }
       st3(s + D.s_t_ang + 3 * l, ca); st3(s + D.s_t_vel + 3 * l, cv);
-      // cfrc = cinr.mul(cdd) + cd.cross(cinr.mul(cd))
+    });
+  }
+  // cfrc = cinr.mul(cdd) + cd.cross(cinr.mul(cd)): no dependency between links, one pass
+  {
+    ex.lanes([&](int l) {
+      if (l >= L) return;
+      V3 ca = ld3(s + D.s_t_ang + 3 * l), cv = ld3(s + D.s_t_vel + 3 * l);
       V3 ip = ld3(s + D.s_cinr_pos + 3 * l); const float* im = s + D.s_cinr_i + 9 * l; float mass = s[D.s_cinr_mass + l];
       V3 cda = ld3(s + D.s_cd_ang + 3 * l), cdv = ld3(s + D.s_cd_vel + 3 * l);
       V3 fa, fv, ga, gv;
@@ -620,7 +633,7 @@ BXG_HD void mass_matrix(X& ex, const Ctx& c) {
       for (int i = 0; i < 9; ++i) s[D.s_crb_i + 9 * lane + i] = s[D.s_cinr_i + 9 * lane + i];
       s[D.s_crb_mass + lane] = s[D.s_cinr_mass + lane];
     }
-    for (int i = lane; i < D.nvw * nvp; i += X::G) M[i] = 0.f;   // incl. padding rows (slot shared with A)
+    for (int i = 4 * lane; i < D.nvw * nvp; i += 4 * X::G) stv4(M + i, F4{0.f, 0.f, 0.f, 0.f});   // incl. padding rows (slot shared with A)
   });
   for (int lvl = D.max_depth - 1; lvl >= 0; --lvl) {
     ex.lanes([&](int l) {
@@ -633,21 +646,25 @@ BXG_HD void mass_matrix(X& ex, const Ctx& c) {
       }
     });
   }
+  // f[i] = crb[link(i)] * cdof[i] per dof, parked in the Newton-Schulz buffer (J is dead
+  // between constraint.force and constraint.jacobian); then one lane per non-zero (i, j <= i)
+  float* fbuf = s + D.s_B;
   ex.lanes([&](int lane) {
     for (int i = lane; i < nv; i += X::G) {
       int li = mi[D.m_dof_link + i];
       V3 fa, fv;
       inertia_mul(ld3(s + D.s_crb_pos + 3 * li), s + D.s_crb_i + 9 * li, s[D.s_crb_mass + li],
                   ld3(s + D.s_cdof_ang + 3 * i), ld3(s + D.s_cdof_vel + 3 * i), &fa, &fv);
-      uint32_t lo = (uint32_t)mi[D.m_dof_anc_lo + i], hi = (uint32_t)mi[D.m_dof_anc_hi + i];
-      for (int j = 0; j <= i; ++j) {
-        uint32_t bit = j < 32 ? (lo >> j) & 1u : (hi >> (j - 32)) & 1u;
-        if (!bit) continue;
-        float v = dot(ld3(s + D.s_cdof_vel + 3 * j), fv) + dot(ld3(s + D.s_cdof_ang + 3 * j), fa);
-        if (i == j) v += mf[D.m_arm + i];
-        M[i * nvp + j] = v;
-        M[j * nvp + i] = v;
-      }
+      st3(fbuf + 6 * i, fv); st3(fbuf + 6 * i + 3, fa);
+    }
+  });
+  ex.lanes([&](int lane) {
+    for (int p = lane; p < D.n_mm_pairs; p += X::G) {
+      const int ij = mi[D.m_mm_pairs + p], i = ij & 255, j = ij >> 8;
+      float v = dot(ld3(s + D.s_cdof_vel + 3 * j), ld3(fbuf + 6 * i)) + dot(ld3(s + D.s_cdof_ang + 3 * j), ld3(fbuf + 6 * i + 3));
+      if (i == j) v += mf[D.m_arm + i];
+      M[i * nvp + j] = v;
+      M[j * nvp + i] = v;
     }
   });
 }
@@ -825,12 +842,12 @@ BXG_HD void store_cols(float* p, const float* v) {
   }
 }
 
-// acc[r * TN + c] = sum_k A[row0 + r][k] * B[k][col0 + c], k ascending
-template <class T, int W>
+// acc[r * TN + c] = sum_k A[row0 + r][k] * B[k][col0 + c], k ascending; NEG accumulates
+// the negated products instead (rounding is symmetric: exactly -(A B), no extra operation)
+template <class T, int W, bool NEG = false>
 BXG_HD void tile_matmul(int lane, const float* A, const float* B, int ld, float* acc) {
   const int rg = lane / T::CG, cg = lane - rg * T::CG;
   const float* a0 = A + rg * T::TM * ld;
-  const float* b0 = B + cg * T::TN;
 #if defined(__CUDA_ARCH__)
   // sm_100a packed FP32: one FFMA2 = two fused multiply-adds per lane (same
   // rounding as two scalar FFMA), halving the issue slots of the inner product
@@ -839,7 +856,7 @@ BXG_HD void tile_matmul(int lane, const float* A, const float* B, int ld, float*
   for (int r = 0; r < T::TM; ++r)
 #pragma unroll
     for (int cc = 0; cc < T::TN / 2; ++cc) acc2[r][cc] = make_float2(0.f, 0.f);
-#pragma unroll 2
+  BXG_PRAGMA_UNROLL(BXG_TILE_UNROLL)
   for (int k0 = 0; k0 < W; k0 += 4) {
     F4 a[T::TM];
 #pragma unroll
@@ -847,10 +864,11 @@ BXG_HD void tile_matmul(int lane, const float* A, const float* B, int ld, float*
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       float bv[T::TN];
-      load_cols<T::TN>(b0 + (k0 + kk) * ld, bv);
+      load_cols<T::TN>(B + (k0 + kk) * ld + cg * T::TN, bv);
 #pragma unroll
       for (int r = 0; r < T::TM; ++r) {
-        const float av = kk == 0 ? a[r].x : kk == 1 ? a[r].y : kk == 2 ? a[r].z : a[r].w;
+        const float ap = kk == 0 ? a[r].x : kk == 1 ? a[r].y : kk == 2 ? a[r].z : a[r].w;
+        const float av = NEG ? -ap : ap;
         const float2 av2 = make_float2(av, av);
 #pragma unroll
         for (int cc = 0; cc < T::TN / 2; ++cc)
@@ -875,10 +893,11 @@ BXG_HD void tile_matmul(int lane, const float* A, const float* B, int ld, float*
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       float bv[T::TN];
-      load_cols<T::TN>(b0 + (k0 + kk) * ld, bv);
+      load_cols<T::TN>(B + (k0 + kk) * ld + cg * T::TN, bv);
 #pragma unroll
       for (int r = 0; r < T::TM; ++r) {
-        const float av = kk == 0 ? a[r].x : kk == 1 ? a[r].y : kk == 2 ? a[r].z : a[r].w;
+        const float ap = kk == 0 ? a[r].x : kk == 1 ? a[r].y : kk == 2 ? a[r].z : a[r].w;
+        const float av = NEG ? -ap : ap;
 #pragma unroll
         for (int cc = 0; cc < T::TN; ++cc) acc[r * T::TN + cc] += av * bv[cc];
       }
@@ -887,21 +906,37 @@ BXG_HD void tile_matmul(int lane, const float* A, const float* B, int ld, float*
 #endif
 }
 
-// residual tile r = I - acc (identity only on real rows), accumulates the
-// Frobenius partials and overwrites acc with I + r for the next product
+// Residual tile.  In: acc = -(M X) (tile_matmul<NEG>), i.e. already r = I - M X away
+// from the diagonal.  The few lanes whose tile crosses the diagonal add the identity
+// (real rows only); every lane accumulates the Frobenius partials; out: acc = I + r
+// for the next product.
+// calls f(element) for the tile elements of this lane that lie on the diagonal of real rows.
+// The tile's diagonal offset delta = row0 - col0 is a multiple of gcd(TM, TN): only those
+// offsets are compiled (two for the 3x6 tile, one for the square ones).
+constexpr int tile_gcd(int a, int b) { return b == 0 ? a : tile_gcd(b, a % b); }
+template <class T, class F>
+BXG_HD void tile_diagonal(int lane, int n, F f) {
+  constexpr int S = tile_gcd(T::TM, T::TN);
+  const int rg = lane / T::CG, cg = lane - rg * T::CG;
+  const int row0 = rg * T::TM, delta = row0 - cg * T::TN;     // diagonal elements: cc = r + delta
+  if (delta > -T::TM && delta < T::TN) {
+#pragma unroll
+    for (int dlt = -((T::TM - 1) / S) * S; dlt < T::TN; dlt += S) {
+      if (delta == dlt) {
+#pragma unroll
+        for (int r = 0; r < T::TM; ++r) {
+          if (r + dlt >= 0 && r + dlt < T::TN) { if (row0 + r < n) f(r * T::TN + r + dlt); }
+        }
+      }
+    }
+  }
+}
 template <class T>
 BXG_HD void residual_tile(int lane, int n, float* acc, float* ss, float* mx) {
-  const int rg = lane / T::CG, cg = lane - rg * T::CG;
+  tile_diagonal<T>(lane, n, [&](int e) { acc[e] = 1.f + acc[e]; });     // r = I - M X
 #pragma unroll
-  for (int r = 0; r < T::TM; ++r)
-#pragma unroll
-    for (int cc = 0; cc < T::TN; ++cc) {
-      const int i = rg * T::TM + r, j = cg * T::TN + cc;
-      const bool diag = i == j && i < n;
-      float res = (diag ? 1.f : 0.f) - acc[r * T::TN + cc];
-      *ss += res * res; *mx = fmaxf(*mx, fabsf(res));
-      acc[r * T::TN + cc] = diag ? 1.f + res : res;
-    }
+  for (int e = 0; e < T::TM * T::TN; ++e) { *ss += acc[e] * acc[e]; *mx = fmaxf(*mx, fabsf(acc[e])); }
+  tile_diagonal<T>(lane, n, [&](int e) { acc[e] = 1.f + acc[e]; });     // I + r
 }
 template <class T>
 BXG_HD void store_tile(int lane, float* C, int ld, const float* acc) {
@@ -930,7 +965,7 @@ BXG_HD void minv_newton_schulz_tiles(X& ex, const Ctx& c, Stats* st) {
   // r0 = I - M X
   ex.lanes([&](int lane) {
     float* acc = tile(lane); float ss = 0.f, mx = 0.f;
-    tile_matmul<T, W>(lane, M, Xc, ld, acc);
+    tile_matmul<T, W, true>(lane, M, Xc, ld, acc);
     residual_tile<T>(lane, n, acc, &ss, &mx);
     store_tile<T>(lane, Q, ld, acc);
     p_sum(lane) = ss; p_max(lane) = mx;
@@ -945,8 +980,20 @@ BXG_HD void minv_newton_schulz_tiles(X& ex, const Ctx& c, Stats* st) {
       for (int i = lane; i < W * ld; i += X::G) tr += M[i] * M[i];
       p_sum(lane) = tr;
     });
-    float tr = ex.sum(p_sum);
-    ex.lanes([&](int lane) { for (int i = lane; i < W * ld; i += X::G) Xc[i] = 0.5f * M[i] / tr; });
+    const float tr = ex.sum(p_sum);
+    // x / tr with one shared reciprocal: q = x * (1/tr) corrected by its own remainder
+    // (the correctly rounded quotient whenever 1/tr is; three operations per element
+    // instead of a division sequence each)
+    const float rinv = 1.f / tr;
+    ex.lanes([&](int lane) {
+      for (int i = 4 * lane; i < W * ld; i += 4 * X::G) {
+        F4 m = ldv4(M + i);
+        float x[4] = {0.5f * m.x, 0.5f * m.y, 0.5f * m.z, 0.5f * m.w}, q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { q[u] = x[u] * rinv; q[u] = fmaf(fmaf(-tr, q[u], x[u]), rinv, q[u]); }
+        stv4(Xc + i, F4{q[0], q[1], q[2], q[3]});
+      }
+    });
     st->ns_cold++;
   }
   float err = 1.f;
@@ -955,7 +1002,7 @@ BXG_HD void minv_newton_schulz_tiles(X& ex, const Ctx& c, Stats* st) {
     ex.lanes([&](int lane) { store_tile<T>(lane, Q, ld, tile(lane)); });           // ... replaces I + r
     ex.lanes([&](int lane) {       // r' = I - M candidate
       float* acc = tile(lane); float ss = 0.f, mx = 0.f;
-      tile_matmul<T, W>(lane, M, Q, ld, acc);
+      tile_matmul<T, W, true>(lane, M, Q, ld, acc);
       residual_tile<T>(lane, n, acc, &ss, &mx);
       p_sum(lane) = ss; p_max(lane) = mx;
     });
@@ -1029,13 +1076,7 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
   for (int r = 0; r < R; ++r) {
     ex.lanes([&](int lane) {
       int i = lane + r * G;
-      float flag = 0.f;
-      if (i < nc) {
-        bool nz = s[D.s_diag + i] != 0.f || s[D.s_aref + i] != 0.f;
-        for (int k = 0; k < nv && !nz; ++k) nz = J[i * ldj + k] != 0.f;
-        flag = nz ? 1.f : 0.f;
-      }
-      p0(lane) = flag;
+      p0(lane) = i < nc ? s[D.s_rowact + i] : 0.f;   // set by constraint.jacobian (load_env for the incoming state)
     });
     am |= ex.ballot(p0) << (r * G);
   }
@@ -1274,7 +1315,7 @@ BXG_HD void con_jacobian(X& ex, const Ctx& c) {
         float tw = mf[D.m_link_invw + lb];  // link_a is the world: contributes 0
         diag = (tw + mu * mu * tw) * (2.f * mu * mu * (1.f - imp) / (imp + 1e-8f));
       }
-      s[D.s_diag + row] = diag; s[D.s_aref + row] = aref;
+      s[D.s_diag + row] = diag; s[D.s_aref + row] = aref; s[D.s_rowact + row] = active ? 1.f : 0.f;
     });
   }
   if (D.nlim > 0) {
@@ -1293,7 +1334,7 @@ BXG_HD void con_jacobian(X& ex, const Ctx& c) {
           diag = mf[D.m_dof_invw + d] * (1.f - imp) / (imp + 1e-8f);
         }
         J[row * nvp + d] = side;
-        s[D.s_diag + row] = diag; s[D.s_aref + row] = aref;
+        s[D.s_diag + row] = diag; s[D.s_aref + row] = aref; s[D.s_rowact + row] = active ? 1.f : 0.f;
       }
     });
   }
@@ -1552,6 +1593,16 @@ BXG_HD void load_env(X& ex, const Ctx& c, const BxgState& g, const float* act, i
       s[D.s_J + r * D.jld + cc] = g.con_jac[e * nc * nv + i];
     }
     for (int i = lane; i < nc; i += G) { s[D.s_diag + i] = g.con_diag[e * nc + i]; s[D.s_aref + i] = g.con_aref[e * nc + i]; }
+  });
+  // active rows of the incoming jacobian: anything non-zero in the row (lane i starts its scan
+  // at column i so that the lanes of a group read different banks)
+  ex.lanes([&](int lane) {
+    const int G = X::G, jld = D.jld;
+    for (int i = lane; i < nc; i += G) {
+      bool nz = s[D.s_diag + i] != 0.f || s[D.s_aref + i] != 0.f;
+      for (int k = 0; k < jld && !nz; ++k) { int kk = k + i; kk = kk >= jld ? kk - jld : kk; kk = kk >= jld ? kk - jld : kk; nz = s[D.s_J + i * jld + kk] != 0.f; }
+      s[D.s_rowact + i] = nz ? 1.f : 0.f;
+    }
   });
 }
 

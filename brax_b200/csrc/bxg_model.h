@@ -35,6 +35,7 @@ struct Dims {
   int m_child_start, m_child_list;       // CSR, children in DEscending index order
   int m_dof_link, m_dof_qidx;            // dof -> link, dof -> q index
   int m_dof_anc_lo, m_dof_anc_hi;        // bitmask over dofs j<=i whose link is ancestor-or-self
+  int m_mm_pairs, n_mm_pairs;            // the same relation as a list of (i | j << 8): the non-zeros of the lower triangle of M
   int m_dof_act_start, m_dof_act_list;   // CSR actuators per dof
   int m_lim_dof;                         // [nlim] dof of each limit row
   int m_tf_pos, m_tf_rot, m_joint_pos, m_in_pos, m_in_rot, m_in_i, m_in_mass, m_link_invw;
@@ -63,6 +64,7 @@ struct Dims {
   int s_scr;                   // generic path / Cholesky scratch (2 matrices)
   int s_diag, s_aref, s_b, s_px, s_py, s_pg, s_pres, s_pxn;  // solver vectors (b..pxn) alias the t/f temporaries
   int s_dist;                  // [ncon]
+  int s_rowact;                // [nc] 1.0 where the constraint row is active (else J, diag, aref of the row are all zero)
   int s_red;                   // [8] scalars
   int env_words;
 };
@@ -184,6 +186,11 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
     alo[i] = (int)(uint32_t)(mask & 0xffffffffu); ahi[i] = (int)(uint32_t)(mask >> 32);
   }
   d.m_dof_anc_lo = put_i(alo); d.m_dof_anc_hi = put_i(ahi);
+  std::vector<int> pairs;
+  for (int i = 0; i < m.nv; ++i)
+    for (int j = 0; j <= i; ++j) if (is_anc(dof_link[j], dof_link[i])) pairs.push_back(i | (j << 8));
+  d.n_mm_pairs = (int)pairs.size();
+  d.m_mm_pairs = put_i(pairs);
   std::vector<int> astart(m.nv + 1, 0), alist;
   for (int dd = 0; dd < m.nv; ++dd) {
     astart[dd] = (int)alist.size();
@@ -299,6 +306,7 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
     d.s_A = take(mat_a); d.s_JM = take(mat_j);
   }
   d.s_dist = take1(m.ncon > 0 ? m.ncon : 1);
+  d.s_rowact = take1(ncz);
   d.s_red = take1(8);
   o = (o + 3) & ~3;
   // half-warp variants put two envs in one warp: offset their slabs by 16 banks so that the

@@ -24,7 +24,7 @@ def main():
   rows = list(csv.reader(io.StringIO(out)))
   hdr, cur, per_line = None, None, {}
   for r in rows:
-    if len(r) >= 2 and r[0] == 'File Path':
+    if len(r) >= 2 and r[0] in ('File Path', 'File Name'):
       cur = r[1].split('/')[-1]
     elif len(r) > 2 and r[0] == 'Line No':
       hdr = r
@@ -34,10 +34,15 @@ def main():
       inst, samp = int(d['Instructions Executed'] or 0), int(d['# Samples'] or 0)
       a, b, _ = per_line.get(key, (0, 0, ''))
       per_line[key] = (a + inst, b + samp, r[1])
-  src = open(os.path.join(ROOT, 'brax_b200', 'csrc', 'bxg_core.cuh')).read().split('\n')
+  # function starts from the source of the captured build: pass the git revision as 3rd
+  # argument when the tree has moved on since the capture
+  if len(sys.argv) > 3:
+    text = subprocess.run(['git', 'show', f'{sys.argv[3]}:brax_b200/csrc/bxg_core.cuh'], capture_output=True, text=True, cwd=ROOT).stdout
+  else:
+    text = open(os.path.join(ROOT, 'brax_b200', 'csrc', 'bxg_core.cuh')).read()
   funcs = []
-  for i, l in enumerate(src, 1):
-    m = re.match(r'BXG_HD [\w\s\*:<>]*?(\w+)\(', l)
+  for i, l in enumerate(text.split('\n'), 1):
+    m = re.match(r'BXG_HD(?:_NOINLINE)? [\w\s\*:<>]*?(\w+)\(', l)
     if m:
       funcs.append((i, m.group(1)))
 

@@ -3,15 +3,14 @@
 Each entry: label, workload, environment overrides."""
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+def _lib(name):
+  return {'BXG_LIB': os.path.join(ROOT, 'brax_b200', f'libbxg_{name}.so')}
+
+
 CONFIGS = [
     ('hum_default', 'humanoid_8192', {}),
-    ('hum_14envs', 'humanoid_8192', {'BXG_MAX_ENVS_PER_CTA': '14'}),
-    ('hum_v4', 'humanoid_8192', {'BXG_FORCE_VARIANT': '4'}),
     ('hum512k_default', 'humanoid_512k', {}),
-    ('hum512k_16envs', 'humanoid_512k', {'BXG_MAX_ENVS_PER_CTA': '16'}),
-    ('hum512k_14envs', 'humanoid_512k', {'BXG_MAX_ENVS_PER_CTA': '14'}),
     ('ant_default', 'ant_1m', {}),
-    ('ant_24envs', 'ant_1m', {'BXG_MAX_ENVS_PER_CTA': '24'}),
 ]
 out_path = sys.argv[1]
 only = sys.argv[2] if len(sys.argv) > 2 else ''
