@@ -1264,6 +1264,28 @@ BXG_HD void con_force(X& ex, const Ctx& c, Stats* st) {
   if constexpr (Cfg::GENERIC_TOO) con_force_generic(ex, c, st);
 }
 
+// One end of a capsule against a plane (mjx plane_capsule, restated in
+// oracle/bxg_oracle.c): the end sphere's centre is the geom centre moved along the
+// capsule axis (third column of the geom's world rotation, brax/contact.py:48-53 with
+// math.quat_to_3x3), and the contact frame's first tangent follows the axis projected
+// into the plane (falls back to y or z when the capsule stands upright).
+BXG_HD void capsule_end(Q4 link_rot, Q4 geom_quat, float half_len, V3 n, V3* centre, V3* t1, V3* t2) {
+  Q4 q = qmul(link_rot, geom_quat);
+  float dq = q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z, sc = 2.f / dq;
+  float xs = q.x * sc, ys = q.y * sc, zs = q.z * sc;
+  V3 axis{q.x * zs + q.w * ys, q.y * zs - q.w * xs, 1.f - (q.x * xs + q.y * ys)};
+  *centre = *centre + axis * half_len;
+  float na = dot(n, axis);
+  V3 b{axis.x - n.x * na, axis.y - n.y * na, axis.z - n.z * na};
+  bool zero = fabsf(b.x) <= 1e-8f && fabsf(b.y) <= 1e-8f && fabsf(b.z) <= 1e-8f;     // math.safe_norm
+  float bn = zero ? 0.f : sqrtf(b.x * b.x + b.y * b.y + b.z * b.z);
+  float d = bn + 1e-6f * (bn == 0.f ? 1.f : 0.f);
+  b = V3{b.x / d, b.y / d, b.z / d};
+  if (bn < 0.5f) b = (-0.5f < n.y && n.y < 0.5f) ? V3{0.f, 1.f, 0.f} : V3{0.f, 0.f, 1.f};
+  *t1 = b;
+  *t2 = cross(n, b);
+}
+
 // ------------------------------------------------------- constraint.jacobian
 template <class X>
 BXG_HD void con_jacobian(X& ex, const Ctx& c) {
@@ -1275,10 +1297,11 @@ BXG_HD void con_jacobian(X& ex, const Ctx& c) {
   ex.lanes([&](int lane) { for (int i = lane; i < D.nc * nvp; i += X::G) J[i] = 0.f; });
   for (int cc = 0; cc < D.ncon; ++cc) {
     int lb = mi[D.m_con_lb + cc];
-    // contact.get, plane-sphere (contact.py:28-67 + mjx): every lane redundantly
+    // contact.get, plane-sphere / plane-capsule (contact.py:28-67 + mjx): every lane redundantly
     V3 n = ld3(mf + D.m_con_frame + 9 * cc), t1 = ld3(mf + D.m_con_frame + 9 * cc + 3), t2 = ld3(mf + D.m_con_frame + 9 * cc + 6);
     float rad = mf[D.m_con_rad + cc], mu = mf[D.m_con_mu + cc];
     V3 sp = ld3(s + D.s_x_pos + 3 * lb) + rotate(ld3(mf + D.m_con_spos + 3 * cc), ld4(s + D.s_x_rot + 4 * lb));
+    if (mi[D.m_con_kind + cc] == BXG_CON_PLANE_CAPSULE_END) capsule_end(ld4(s + D.s_x_rot + 4 * lb), ld4(mf + D.m_con_gquat + 4 * cc), mf[D.m_con_half + cc], n, &sp, &t1, &t2);
     float dist = dot(sp - ld3(mf + D.m_con_ppos + 3 * cc), n) - rad;
     V3 pos = sp - n * (rad + 0.5f * dist);
     bool active = dist < 0.f;

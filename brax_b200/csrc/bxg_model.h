@@ -42,6 +42,7 @@ struct Dims {
   int m_dof_ang, m_dof_vel, m_arm, m_stiff, m_damp, m_lim_lo, m_lim_hi, m_dof_invw, m_dof_sp;
   int m_act_qid, m_act_did, m_act_gain, m_act_gear, m_act_clo, m_act_chi, m_act_flo, m_act_fhi, m_act_bq, m_act_bqd;
   int m_con_la, m_con_lb, m_con_ppos, m_con_frame, m_con_spos, m_con_rad, m_con_mu, m_con_sp;  // sp: [ncon,7]
+  int m_con_kind, m_con_gquat, m_con_half;   // plane-capsule end points: kind 1, geom quaternion [ncon,4], signed half length
   int m_con_anc_lo, m_con_anc_hi;        // [ncon] bitmask of dofs that move link_b
   int model_words;
   // ---- per-env slab ----
@@ -238,6 +239,18 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
     for (int k = 0; k < 5; ++k) sp[c * 7 + 2 + k] = m.con_solimp[c * 5 + k];
   }
   d.m_con_sp = put_f(sp.data(), m.ncon * 7);
+  {
+    std::vector<int> kind(m.ncon > 0 ? m.ncon : 1, 0);
+    std::vector<float> gq((m.ncon > 0 ? m.ncon : 1) * 4, 0.f), half(m.ncon > 0 ? m.ncon : 1, 0.f);
+    for (int c = 0; c < m.ncon; ++c) {
+      kind[c] = m.con_kind ? m.con_kind[c] : BXG_CON_PLANE_SPHERE;
+      if (kind[c] != BXG_CON_PLANE_SPHERE && kind[c] != BXG_CON_PLANE_CAPSULE_END) return "unknown contact kind";
+      if (kind[c] == BXG_CON_PLANE_CAPSULE_END && (!m.con_geom_quat || !m.con_half_len)) return "capsule contact without con_geom_quat / con_half_len";
+      gq[4 * c] = 1.f;
+      if (kind[c] == BXG_CON_PLANE_CAPSULE_END) { for (int k = 0; k < 4; ++k) gq[4 * c + k] = m.con_geom_quat[4 * c + k]; half[c] = m.con_half_len[c]; }
+    }
+    d.m_con_kind = put_i(kind); d.m_con_gquat = put_f(gq.data(), (int)gq.size()); d.m_con_half = put_f(half.data(), (int)half.size());
+  }
   std::vector<int> clo(m.ncon > 0 ? m.ncon : 1, 0), chi(m.ncon > 0 ? m.ncon : 1, 0);
   for (int c = 0; c < m.ncon; ++c) {
     uint64_t mask = 0;

@@ -357,6 +357,8 @@ def _parse_joint(a: Dict[str, str], tag: str, deg: bool) -> _Joint:
     j.stiffness = float(a.get('stiffness', 0.0))
   j.solref = _vec(a.get('solreflimit'), _DEFAULT_SOLREF)
   j.solimp = _vec(a.get('solimplimit'), _DEFAULT_SOLIMP)
+  if len(j.solimp) < 5:   # a partial solimp keeps MuJoCo's defaults for the rest
+    j.solimp = np.concatenate([j.solimp, np.array(_DEFAULT_SOLIMP)[len(j.solimp):]])
   return j
 
 

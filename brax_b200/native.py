@@ -51,6 +51,7 @@ class ModelDesc(ctypes.Structure):
       ('con_link_a', _pi), ('con_link_b', _pi), ('con_plane_pos', _pf), ('con_frame', _pf),
       ('con_sphere_pos', _pf), ('con_radius', _pf), ('con_friction', _pf),
       ('con_solref', _pf), ('con_solimp', _pf),
+      ('con_kind', _pi), ('con_geom_quat', _pf), ('con_half_len', _pf),
   ]
 
 
@@ -100,10 +101,8 @@ def make_desc(sys, minv_mode: int = MINV_NEWTON_SCHULZ) -> Tuple[ModelDesc, list
     return a.ctypes.data_as(_pi)
 
   cp = sys.contact_pairs()
-  if np.any(np.asarray(cp.kind) != 0):
-    raise NotImplementedError('plane-capsule contacts are not supported by this kernel build')
   d = ModelDesc()
-  d.abi_version = 1
+  d.abi_version = 2
   d.num_links, d.nq, d.nv, d.nu = sys.num_links(), sys.nq, sys.nv, sys.nu
   d.ncon = len(cp.geom1)
   d.has_limit = 0 if sys.dof.limit is None else 1
@@ -139,6 +138,7 @@ def make_desc(sys, minv_mode: int = MINV_NEWTON_SCHULZ) -> Tuple[ModelDesc, list
   d.con_plane_pos = fp(cp.plane_pos); d.con_frame = fp(cp.frame)
   d.con_sphere_pos = fp(cp.sphere_pos); d.con_radius = fp(cp.radius)
   d.con_friction = fp(cp.friction); d.con_solref = fp(cp.solref); d.con_solimp = fp(cp.solimp)
+  d.con_kind = ip(cp.kind); d.con_geom_quat = fp(cp.geom_quat); d.con_half_len = fp(cp.half_len)
   return d, keep
 
 
@@ -193,7 +193,7 @@ def lib() -> ctypes.CDLL:
       l.bxg_env_step.argtypes = [ctypes.c_void_p, ctypes.POINTER(EnvSpecC), ctypes.c_int64, ctypes.c_int32,
                                  ctypes.POINTER(StateC), ctypes.c_void_p, ctypes.POINTER(StateC),
                                  ctypes.POINTER(EnvIOC), ctypes.c_void_p]
-      if l.bxg_abi_version() != 1:
+      if l.bxg_abi_version() != 2:
         raise RuntimeError('libbxg.so ABI version mismatch')
       _lib = l
     return _lib

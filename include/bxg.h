@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BXG_ABI_VERSION 1
+#define BXG_ABI_VERSION 2
 
 enum {
   BXG_OK = 0,
@@ -56,6 +56,9 @@ enum {
   BXG_MINV_NEWTON_SCHULZ = 0,
   BXG_MINV_CHOLESKY = 1   /* exact SPD inverse every substep (north_star) */
 };
+
+#define BXG_CON_PLANE_SPHERE 0
+#define BXG_CON_PLANE_CAPSULE_END 1
 
 /* Model constants = the fields of brax.base.System the path reads
  * (brax/base.py:415-540).  Host pointers. */
@@ -100,16 +103,20 @@ typedef struct BxgModelDesc {
   const float* act_force_hi;
   const float* act_bias_q;
   const float* act_bias_qd;
-  /* plane-sphere contacts [ncon] (brax/contact.py:28-67 + mjx collision) */
+  /* plane-sphere / plane-capsule contacts [ncon] (brax/contact.py:28-67 + mjx collision).
+   * A capsule contributes two contacts (its end spheres, +axis first). */
   const int32_t* con_link_a;     /* plane link (-1 = world) */
-  const int32_t* con_link_b;     /* sphere link */
+  const int32_t* con_link_b;     /* sphere / capsule link */
   const float* con_plane_pos;    /* [ncon,3] world */
-  const float* con_frame;        /* [ncon,3,3] rows normal,t1,t2 */
-  const float* con_sphere_pos;   /* [ncon,3] in link_b frame */
+  const float* con_frame;        /* [ncon,3,3] rows normal,t1,t2 (capsules: t1, t2 follow the axis at run time) */
+  const float* con_sphere_pos;   /* [ncon,3] geom centre in link_b frame */
   const float* con_radius;
   const float* con_friction;     /* sliding friction mu */
   const float* con_solref;       /* [ncon,2] */
   const float* con_solimp;       /* [ncon,5] */
+  const int32_t* con_kind;       /* [ncon] BXG_CON_*; NULL = all plane-sphere */
+  const float* con_geom_quat;    /* [ncon,4] capsule orientation in link_b frame (kind 1) */
+  const float* con_half_len;     /* [ncon] signed half length: end point = centre + axis * half_len (kind 1) */
 } BxgModelDesc;
 
 /* The generalized State (brax/generalized/base.py:25-92 + brax/base.py:396-412)

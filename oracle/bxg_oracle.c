@@ -78,6 +78,9 @@ typedef struct {
   int32_t con_link_a[MAXCON], con_link_b[MAXCON];
   real con_plane_pos[MAXCON][3], con_frame[MAXCON][9], con_sphere_pos[MAXCON][3];
   real con_radius[MAXCON], con_friction[MAXCON], con_solref[MAXCON][2], con_solimp[MAXCON][5];
+  int32_t con_kind[MAXCON];          /* 0 plane-sphere, 1 one end of a plane-capsule pair */
+  real con_geom_quat[MAXCON][4];     /* capsule orientation in link_b frame */
+  real con_half_len[MAXCON];         /* signed: end point = centre + axis * half_len */
 } OrcModel;
 
 /* per-environment working state (reference generalized/base.py:25-92) */
@@ -488,13 +491,43 @@ static void imp_aref(const real* prm, real pos, real vel, real* imp_out, real* a
   *aref_out = -b * vel - k * imp * pos;
 }
 
-/* contact.get restricted to plane-sphere, brax/contact.py:28-67 + mjx */
-static void contact_get(const OrcModel* m, const Env* e, int c, real* dist, real* pos) {
+/* contact.get for plane-sphere and plane-capsule pairs, brax/contact.py:28-67 + mjx.
+ * mujoco-mjx is not under /root/reference (unpinned dependency, pyproject.toml:45);
+ * restated from its published source, mjx/_src/collision_primitive.py:
+ *   _plane_sphere: dist = (c - p).n - r;  pos = c - n (r + dist/2)
+ *   plane_sphere:  frame = make_frame(n)  (constant per pair: precomputed on the host)
+ *   plane_capsule: axis = cap.mat[:, 2]; b = normalize(axis - n (n.axis)), with the
+ *                  fallback b = y if |n_y| < 0.5 else z when |b| < 0.5;
+ *                  frame = [n, b, n x b]; two contacts, the end spheres at
+ *                  cap.pos + axis * half and cap.pos - axis * half (in that order).
+ * geom pose as brax/contact.py:48-53: pos = x.pos + rotate(geom_pos, x.rot),
+ * mat = quat_to_3x3(x.rot * geom_quat).  No reference test pins plane-capsule numbers
+ * (parity unpinned for this pair type). */
+static void contact_get(const OrcModel* m, const Env* e, int c, real* dist, real* pos, real* frame) {
   int lb = m->con_link_b[c];
   real t[3], sp[3], d[3];
   rotate(m->con_sphere_pos[c], e->x_rot[lb], t);
-  for (int i = 0; i < 3; i++) { sp[i] = e->x_pos[lb][i] + t[i]; d[i] = sp[i] - m->con_plane_pos[c][i]; }
+  for (int i = 0; i < 3; i++) sp[i] = e->x_pos[lb][i] + t[i];
   const real* n = m->con_frame[c];
+  for (int i = 0; i < 9; i++) frame[i] = m->con_frame[c][i];
+  if (m->con_kind[c] == 1) {
+    real q[4], mat[9], axis[3], b[3];
+    quat_mul(e->x_rot[lb], m->con_geom_quat[c], q);
+    quat_to_3x3(q, mat);
+    axis[0] = mat[2]; axis[1] = mat[5]; axis[2] = mat[8];
+    for (int i = 0; i < 3; i++) sp[i] = sp[i] + axis[i] * m->con_half_len[c];
+    real na = dot3(n, axis);
+    for (int i = 0; i < 3; i++) b[i] = axis[i] - n[i] * na;
+    real bn = safe_norm(b, 3);
+    normalize(b, 3);
+    if (bn < (real)0.5) {
+      int use_y = (real)-0.5 < n[1] && n[1] < (real)0.5;
+      b[0] = 0; b[1] = use_y ? 1 : 0; b[2] = use_y ? 0 : 1;
+    }
+    for (int i = 0; i < 3; i++) frame[3 + i] = b[i];
+    cross3(n, b, frame + 6);
+  }
+  for (int i = 0; i < 3; i++) d[i] = sp[i] - m->con_plane_pos[c][i];
   *dist = dot3(d, n) - m->con_radius[c];
   for (int i = 0; i < 3; i++) pos[i] = sp[i] - n[i] * (m->con_radius[c] + (real)0.5 * *dist);
 }
@@ -516,12 +549,12 @@ static void point_jac_vel(const OrcModel* m, const Env* e, const real* pos, int 
 static void con_jacobian(const OrcModel* m, Env* e) {
   int nv = m->nv, row = 0;
   for (int c = 0; c < m->ncon; c++) {
-    real dist, pos[3], ja[MAXV][3], jb[MAXV][3];
-    contact_get(m, e, c, &dist, pos);
+    real dist, pos[3], fr[9], ja[MAXV][3], jb[MAXV][3];
+    contact_get(m, e, c, &dist, pos, fr);
     e->con_dist[c] = dist;
     point_jac_vel(m, e, pos, m->con_link_a[c], ja);
     point_jac_vel(m, e, pos, m->con_link_b[c], jb);
-    const real* fr = m->con_frame[c]; real mu = m->con_friction[c];
+    real mu = m->con_friction[c];
     int la = m->con_link_a[c], lb = m->con_link_b[c];
     real active = dist < 0 ? (real)1 : (real)0;
     real prm[7] = {m->con_solref[c][0], m->con_solref[c][1], m->con_solimp[c][0], m->con_solimp[c][1], m->con_solimp[c][2], m->con_solimp[c][3], m->con_solimp[c][4]};
@@ -860,7 +893,7 @@ int orc_contact(const OrcModel* m, const real* q, real* dist, real* pos) {
   Env* e = (Env*)calloc(1, sizeof(Env));
   CP(e->q, q, m->nq);
   kin_forward(m, e);
-  for (int c = 0; c < m->ncon; c++) contact_get(m, e, c, dist + c, pos + 3 * c);
+  for (int c = 0; c < m->ncon; c++) { real fr[9]; contact_get(m, e, c, dist + c, pos + 3 * c, fr); }
   free(e);
   return 0;
 }

@@ -65,6 +65,7 @@ def _model_struct(ct):
       ('con_plane_pos', ct * (MAXCON * 3)), ('con_frame', ct * (MAXCON * 9)), ('con_sphere_pos', ct * (MAXCON * 3)),
       ('con_radius', ct * MAXCON), ('con_friction', ct * MAXCON), ('con_solref', ct * (MAXCON * 2)),
       ('con_solimp', ct * (MAXCON * 5)),
+      ('con_kind', i32 * MAXCON), ('con_geom_quat', ct * (MAXCON * 4)), ('con_half_len', ct * MAXCON),
   ]
 
 
@@ -158,6 +159,7 @@ class Oracle:
       put('con_plane_pos', cp.plane_pos); put('con_frame', cp.frame)
       put('con_sphere_pos', cp.sphere_pos); put('con_radius', cp.radius)
       put('con_friction', cp.friction); put('con_solref', cp.solref); put('con_solimp', cp.solimp)
+      put('con_kind', cp.kind); put('con_geom_quat', cp.geom_quat); put('con_half_len', cp.half_len)
 
   # ---------------------------------------------------------------- state
   def shapes(self) -> Dict[str, tuple]:

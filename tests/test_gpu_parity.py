@@ -343,3 +343,51 @@ def test_debug_contact_after_init_matches_step_diagnostics():
   from oracle import oracle as O
   ref = O.Oracle(sys_).init(q.cpu().numpy(), qd.cpu().numpy())
   np.testing.assert_allclose(st.contact['con_dist'].cpu().numpy(), ref['con_dist'], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('model,drop', [('hopper', 0.05), ('walker2d', 0.1), ('halfcheetah', 0.45)])
+def test_capsule_models_single_substep_map(model, drop):
+  """Plane-capsule contacts on the GPU: init and one-substep maps from
+  the oracle's state for Hopper (half-warp variant), Walker2d and HalfCheetah (generic
+  kernel), with contacts active; same criteria as the Ant / Humanoid single-substep test."""
+  from brax_b200 import envs_assets
+  from brax_b200.generalized import pipeline
+  from oracle import oracle as O
+  torch = _torch()
+  dev = torch.device('cuda', 0)
+  sys_ = envs_assets.load(model)
+  n, steps = 128, 20
+  rng = np.random.default_rng(0)
+  q = (np.asarray(sys_.init_q)[None] + rng.uniform(-0.1, 0.1, (n, sys_.nq))).astype(np.float32)
+  q[:, 1] -= drop * rng.uniform(0.5, 1.0, n).astype(np.float32)
+  qd = (0.1 * rng.standard_normal((n, sys_.nv))).astype(np.float32)
+  o = O.Oracle(sys_)
+  ref = o.init(q, qd)
+  got = _flat_np(pipeline.init(sys_, torch.as_tensor(q, device=dev), torch.as_tensor(qd, device=dev)))
+  for k in O.STATE_FIELDS:
+    scale = max(1.0, float(np.abs(ref[k]).max()))
+    np.testing.assert_allclose(got[k], ref[k], rtol=1e-4, atol=2e-5 * scale, err_msg=f'{model}.{k}')
+  inside, total, active, mask_mismatch = 0, 0, 0, 0
+  for k in range(steps):
+    act = torch.as_tensor(rng.uniform(-1, 1, (n, sys_.nu)).astype(np.float32), device=dev)
+    st_in = _to_state(torch, ref, dev)
+    prev = ref['stats'].copy()
+    got_state = pipeline.step(sys_, st_in, act, debug=True, n_frames=1)
+    got = _flat_np(got_state)
+    o.step(ref, act.cpu().numpy(), 1)
+    e = _env_err(got, ref)
+    d = ref['stats'] - prev
+    gs = got_state.contact['stats'].cpu().numpy()
+    same = (d[:, 0] == gs[:, 0]) & (d[:, 1] == gs[:, 1])
+    if same.any():
+      assert np.percentile(e[same], 95) <= 1.0, (model, k, np.percentile(e[same], 95))
+    dist_got = got_state.contact['con_dist'].cpu().numpy()
+    differ = (dist_got < 0) != (ref['con_dist'] < 0)
+    mask_mismatch += int(np.sum(differ & (np.abs(ref['con_dist']) > 1e-6)))
+    inside += int((e <= 1.0).sum()); total += n
+    active += int((ref['con_dist'] < 0).sum())
+    o.step(ref, act.cpu().numpy(), 4)
+  assert mask_mismatch == 0
+  assert active > 0
+  assert inside / total >= 0.9, inside / total
+  _report(f'capsule_{model}', {'envs_inside_tolerance': inside / total, 'active_contacts': active, 'substeps': steps, 'n_env': n})

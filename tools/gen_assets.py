@@ -2,7 +2,7 @@
 
 Run in the build container (needs /root/reference for the MJCF sources):
     python tools/gen_assets.py
-Writes brax_b200/assets/{ant,humanoid}.json and the small pendulum fixtures
+Writes brax_b200/assets/{ant,humanoid,halfcheetah,hopper,walker2d}.json and the small pendulum fixtures
 under tests/golden/ that the known-answer tests use.  The XML files themselves
 are not copied into this repository; only the numbers the hot path consumes.
 """
@@ -17,6 +17,10 @@ REF = '/root/reference/brax'
 ASSETS = {
     'ant': f'{REF}/envs/assets/ant.xml',
     'humanoid': f'{REF}/envs/assets/humanoid.xml',
+    # plane-capsule models
+    'halfcheetah': f'{REF}/envs/assets/half_cheetah.xml',
+    'hopper': f'{REF}/envs/assets/hopper.xml',
+    'walker2d': f'{REF}/envs/assets/walker2d.xml',
 }
 FIXTURES = ['triple_pendulum', 'single_pendulum_motor', 'single_pendulum_position',
             'single_pendulum_velocity', 'single_pendulum_position_frclimit',
