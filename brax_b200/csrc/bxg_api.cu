@@ -127,8 +127,14 @@ int bxg_model_create(const BxgModelDesc* desc, int device, BxgModel** out) {
   // raise it to the device maximum, never to this model's own size
   const void* ks = step_kernel_of(m->pm.variant_id);
   const void* ki = init_kernel_of(m->pm.variant_id);
-  if ((ce = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin)) != cudaSuccess) return cleanup(cuda_fail(ce, "cudaFuncSetAttribute(step)"));
-  if ((ce = cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin)) != cudaSuccess) return cleanup(cuda_fail(ce, "cudaFuncSetAttribute(init)"));
+  // (dynamic + the kernel's few bytes of static shared memory must fit the opt-in limit)
+  for (const void* k : {ks, ki}) {
+    cudaFuncAttributes fa;
+    if ((ce = cudaFuncGetAttributes(&fa, k)) != cudaSuccess) return cleanup(cuda_fail(ce, "cudaFuncGetAttributes"));
+    const int dyn_max = (int)prop.sharedMemPerBlockOptin - (int)fa.sharedSizeBytes;
+    if ((int)m->smem_bytes > dyn_max) return cleanup(fail(BXG_E_UNSUPPORTED, "model needs more shared memory per CTA than the device offers"));
+    if ((ce = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max)) != cudaSuccess) return cleanup(cuda_fail(ce, "cudaFuncSetAttribute(max dynamic shared memory)"));
+  }
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m->blocks_per_sm_step, ks, m->threads, m->smem_bytes);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m->blocks_per_sm_init, ki, m->threads, m->smem_bytes);
   if (m->blocks_per_sm_step < 1 || m->blocks_per_sm_init < 1) return cleanup(fail(BXG_E_UNSUPPORTED, "kernel does not fit on an SM"));

@@ -1365,8 +1365,8 @@ BXG_HD void con_jacobian(X& ex, const Ctx& c) {
 
 // ------------------------------------------------------------------ pipeline
 template <class X, class Cfg>
-BXG_HD void update_position_terms(X& ex, const Ctx& c, Stats* st, bool exact_inverse) {
-  const int sl = c.D->sync_level;
+BXG_HD void update_position_terms(X& ex, const Ctx& c, Stats* st, bool exact_inverse, bool in_step) {
+  const int sl = in_step ? c.D->sync_level : 0;
   kinematics(ex, c);
   transform_com(ex, c);
   if (sl & 8) ex.cta_sync();
@@ -1390,7 +1390,7 @@ BXG_HD void substep(X& ex, const Ctx& c, Stats* st) {
   con_force<X, Cfg>(ex, c, st);
   if (sl & 1) ex.cta_sync();
   integrate(ex, c);
-  update_position_terms<X, Cfg>(ex, c, st, c.D->ns_iters == 0 || c.D->minv_mode == BXG_MINV_CHOLESKY);
+  update_position_terms<X, Cfg>(ex, c, st, c.D->ns_iters == 0 || c.D->minv_mode == BXG_MINV_CHOLESKY, true);
 }
 
 // pipeline.init (pipeline.py:51-61); q, qd already in the slab
@@ -1401,7 +1401,7 @@ BXG_HD void init_env(X& ex, const Ctx& c, Stats* st) {
     for (int i = lane; i < D.nv; i += X::G) { s[D.s_qfs + i] = 0.f; s[D.s_qfc + i] = 0.f; s[D.s_qdd + i] = 0.f; }
     for (int i = lane; i < (D.nc > 0 ? D.nc : 1) * D.jld; i += X::G) s[D.s_J + i] = 0.f;
   });
-  update_position_terms<X, Cfg>(ex, c, st, true);
+  update_position_terms<X, Cfg>(ex, c, st, true, false);
 }
 
 // Zeroes every region whose padding the register-row kernels rely on (rows and

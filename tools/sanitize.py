@@ -18,4 +18,15 @@ for model in ('ant', 'humanoid'):
     es = env.step(es, torch.zeros((21, env.action_size), device=dev))
   torch.cuda.synchronize()
   assert torch.isfinite(st.q).all() and torch.isfinite(es.obs).all()
+from brax_b200 import envs_assets
+import numpy as np
+for model in ('hopper', 'halfcheetah'):   # plane-capsule contacts: half-warp variant and the generic kernel
+  sys_ = envs_assets.load(model)
+  q = torch.as_tensor(np.asarray(sys_.init_q, np.float32), device=dev)[None].repeat(29, 1).contiguous()
+  q[:, 1] -= 0.3 if model == 'halfcheetah' else 0.04
+  st = pipeline.init(sys_, q, torch.zeros((29, sys_.nv), device=dev))
+  for k in range(2):
+    st = pipeline.step(sys_, st, torch.zeros((29, sys_.nu), device=dev), n_frames=5)
+  torch.cuda.synchronize()
+  assert torch.isfinite(st.q).all()
 print('sanitize rollout ok')

@@ -8,9 +8,15 @@ def _lib(name):
 
 
 CONFIGS = [
-    ('hum_default', 'humanoid_8192', {}),
-    ('hum512k_default', 'humanoid_512k', {}),
-    ('ant_default', 'ant_1m', {}),
+    ('hum_sl1', 'humanoid_8192', {}),
+    ('hum_split', 'humanoid_8192', {'BXG_SYNC_LEVEL': '192'}),
+    ('hum_sl0', 'humanoid_8192', {'BXG_SYNC_LEVEL': '0'}),
+    ('hum_sl3', 'humanoid_8192', {'BXG_SYNC_LEVEL': '3'}),
+    ('hum512k_sl1', 'humanoid_512k', {}),
+    ('hum512k_split', 'humanoid_512k', {'BXG_SYNC_LEVEL': '192'}),
+    ('ant_sl1', 'ant_1m', {}),
+    ('ant_split', 'ant_1m', {'BXG_SYNC_LEVEL': '192'}),
+    ('ant_sl0', 'ant_1m', {'BXG_SYNC_LEVEL': '0'}),
 ]
 out_path = sys.argv[1]
 only = sys.argv[2] if len(sys.argv) > 2 else ''
@@ -20,7 +26,7 @@ for label, wl, env in CONFIGS:
     continue
   e = dict(os.environ); e.update(env)
   p = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--workload', wl, '--steps', '10', '--warmup', '3',
-                      '--no-cpu-baseline', '--no-extra'], env=e, capture_output=True, text=True, timeout=600)
+                      '--no-cpu-baseline', '--no-extra'], env=e, capture_output=True, text=True, timeout=150)
   line = None
   for l in p.stdout.splitlines():
     if l.startswith('{'):
