@@ -1514,7 +1514,7 @@ BXG_HD void env_epilogue(X& ex, const Ctx& c, const BxgEnvSpec& sp, const BxgEnv
   V3 before = ld3(s + D.s_red);
   V3 after = com_kind ? env_com(c) : ld3(s + D.s_x_pos);
   V3 vel{(after.x - before.x) / sp.env_dt, (after.y - before.y) / sp.env_dt, (after.z - before.z) / sp.env_dt};
-  float forward_reward = com_kind ? sp.forward_reward_weight * vel.x : vel.x;
+  float forward_reward = sp.forward_reward_weight * vel.x;   // Ant has no weight (envs/ant.py:240): its spec carries 1.0, exact
   float z = s[D.s_x_pos + 2];
   float is_healthy = z < sp.healthy_z_min ? 0.f : 1.f;
   if (z > sp.healthy_z_max) is_healthy = 0.f;

@@ -1,11 +1,12 @@
-"""Environments in scope (reference `brax/envs/__init__.py:35-107`): ant, humanoid."""
+"""Environments in scope (reference `brax/envs/__init__.py:35-107`): ant, humanoid, halfcheetah."""
 from typing import Optional
 
 from brax_b200.envs.ant import Ant
 from brax_b200.envs.base import FusedEnv, State
+from brax_b200.envs.half_cheetah import Halfcheetah
 from brax_b200.envs.humanoid import Humanoid
 
-_envs = {'ant': Ant, 'humanoid': Humanoid}
+_envs = {'ant': Ant, 'humanoid': Humanoid, 'halfcheetah': Halfcheetah}
 
 
 def get_environment(env_name: str, **kwargs) -> FusedEnv:

@@ -40,10 +40,12 @@ class FusedEnv:
 
   def __init__(self, sys: base.System, spec: native.EnvSpecC, metric_names, n_frames: int,
                episode_length: Optional[int] = None, auto_reset: bool = False,
-               batch_size: Optional[int] = None, device=None, env_id_offset: int = 0):
+               batch_size: Optional[int] = None, device=None, env_id_offset: int = 0, metric_slots=None):
     self.sys = sys
     self.spec = spec
     self.metric_names = tuple(metric_names)
+    # slot of each metric in the kernel's per-env metrics row (default: in order)
+    self._metric_slots = dict(metric_slots) if metric_slots else {k: i for i, k in enumerate(self.metric_names)}
     self._n_frames = int(n_frames)
     self.episode_length = episode_length
     self.auto_reset = auto_reset
@@ -111,7 +113,7 @@ class FusedEnv:
       first_obs = state.info['first_obs'].contiguous()
     bufs = {k: v.contiguous() for k, v in state.pipeline_state.to_flat().items()}
     out = model.env_step(self.spec, bufs, action, self._n_frames, io, first=first, first_obs=first_obs)
-    metrics = {k: io['metrics'][:, i] for i, k in enumerate(self.metric_names)}
+    metrics = {k: io['metrics'][:, self._metric_slots[k]] for k in self.metric_names}
     info = dict(state.info)
     if io['steps'] is not None:
       info['steps'] = io['steps']; info['truncation'] = io['truncation']

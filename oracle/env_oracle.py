@@ -4,6 +4,7 @@ TEST INFRASTRUCTURE ONLY (see oracle/bxg_oracle.c header).  Follows, statement
 by statement, float32:
   brax/envs/ant.py:233-279            Ant.step / _get_obs
   brax/envs/humanoid.py:256-354       Humanoid.step / _get_obs / _com
+  brax/envs/half_cheetah.py:178-212   Halfcheetah.step / _get_obs
   brax/envs/wrappers/training.py:98-158  EpisodeWrapper.step, AutoResetWrapper.step
   brax/actuator.py:23-57              to_tau (for Humanoid's qfrc_actuator)
 """
@@ -24,14 +25,14 @@ def _rotate(v, q):
 
 class EnvOracle:
   def __init__(self, sys, kind, *, forward_reward_weight=1.0, ctrl_cost_weight, healthy_reward,
-               terminate_when_unhealthy=True, healthy_z_range, exclude_current_positions=True,
+               terminate_when_unhealthy=True, healthy_z_range=(-np.inf, np.inf), exclude_current_positions=True,
                n_frames=5, episode_length=None, auto_reset=False):
     self.sys, self.kind = sys, kind
     self.o = O.Oracle(sys, np.float32)
     self.w_fwd, self.w_ctrl, self.h_rew = f32(forward_reward_weight), f32(ctrl_cost_weight), f32(healthy_reward)
     self.term = terminate_when_unhealthy
     self.zmin, self.zmax = f32(healthy_z_range[0]), f32(healthy_z_range[1])
-    self.skip = 2 if exclude_current_positions else 0
+    self.skip = (1 if kind == 'halfcheetah' else 2) if exclude_current_positions else 0
     self.n_frames = n_frames
     self.dt = f32(sys.opt.timestep) * f32(n_frames)
     self.episode_length, self.auto_reset = episode_length, auto_reset
@@ -66,7 +67,7 @@ class EnvOracle:
 
   def obs(self, st, action):
     q, qd = st['q'][:, self.skip:], st['qd']
-    if self.kind == 'ant':
+    if self.kind in ('ant', 'halfcheetah'):
       return np.concatenate([q, qd], 1).astype(f32)
     n, L = q.shape[0], len(self.mass)
     com, mass_sum, x_i = self._com(st)
@@ -104,7 +105,7 @@ class EnvOracle:
     self.o.step(ps, action, self.n_frames)
     after = self._com(ps)[0] if self.kind == 'humanoid' else ps['x_pos'][:, 0]
     velocity = ((after - before) / self.dt).astype(f32)
-    forward = (self.w_fwd * velocity[:, 0]).astype(f32) if self.kind == 'humanoid' else velocity[:, 0]
+    forward = velocity[:, 0] if self.kind == 'ant' else (self.w_fwd * velocity[:, 0]).astype(f32)
     z = ps['x_pos'][:, 0, 2]
     healthy = np.where(z < self.zmin, f32(0), f32(1)).astype(f32)
     healthy = np.where(z > self.zmax, f32(0), healthy).astype(f32)
@@ -116,7 +117,10 @@ class EnvOracle:
     reward = ((forward + h_rew).astype(f32) - ctrl).astype(f32)
     done = (f32(1) - healthy).astype(f32) if self.term else np.zeros_like(healthy)
     dist = np.sqrt(np.sum(after.astype(f32) ** 2, -1)).astype(f32)
-    if self.kind == 'ant':
+    if self.kind == 'halfcheetah':   # reward = forward_reward - ctrl_cost; done is never set (half_cheetah.py:189-199)
+      reward = (forward - ctrl).astype(f32)
+      m = {'x_position': after[:, 0], 'x_velocity': velocity[:, 0], 'reward_ctrl': -ctrl, 'reward_run': forward}
+    elif self.kind == 'ant':
       m = {'reward_forward': forward, 'reward_survive': h_rew, 'reward_ctrl': -ctrl, 'reward_contact': np.zeros_like(ctrl),
            'x_position': after[:, 0], 'y_position': after[:, 1], 'distance_from_origin': dist,
            'x_velocity': velocity[:, 0], 'y_velocity': velocity[:, 1], 'forward_reward': forward}

@@ -18,10 +18,13 @@ class _EnvStub:
     if name == 'ant':
       sp.kind, sp.forward_reward_weight, sp.ctrl_cost_weight, sp.healthy_reward = native.ENV_ROOT_VELOCITY, 1.0, 0.5, 1.0
       sp.healthy_z_min, sp.healthy_z_max = 0.2, 1.0
+    elif name == 'halfcheetah':
+      sp.kind, sp.forward_reward_weight, sp.ctrl_cost_weight, sp.healthy_reward = native.ENV_ROOT_VELOCITY, 1.0, 0.1, 0.0
+      sp.healthy_z_min, sp.healthy_z_max = -3.0e38, 3.0e38
     else:
       sp.kind, sp.forward_reward_weight, sp.ctrl_cost_weight, sp.healthy_reward = native.ENV_COM_VELOCITY, 1.25, 0.1, 5.0
       sp.healthy_z_min, sp.healthy_z_max = 1.0, 2.0
-    sp.obs_skip, sp.terminate_when_unhealthy = 2, 1
+    sp.obs_skip, sp.terminate_when_unhealthy = (1, 0) if name == 'halfcheetah' else (2, 1)
     sp.episode_length = episode_length or 0
     self.n_frames = 5
     sp.env_dt = float(np.float32(self.sys.opt.timestep) * np.float32(5))
@@ -31,17 +34,29 @@ class _EnvStub:
 def _oracle(name, sys, **kw):
   if name == 'ant':
     return EnvOracle(sys, 'ant', ctrl_cost_weight=0.5, healthy_reward=1.0, healthy_z_range=(0.2, 1.0), **kw)
+  if name == 'halfcheetah':
+    return EnvOracle(sys, 'halfcheetah', forward_reward_weight=1.0, ctrl_cost_weight=0.1, healthy_reward=0.0,
+                     terminate_when_unhealthy=False, **kw)
   return EnvOracle(sys, 'humanoid', forward_reward_weight=1.25, ctrl_cost_weight=0.1, healthy_reward=5.0,
                    healthy_z_range=(1.0, 2.0), **kw)
 
 
-@pytest.mark.parametrize('name', ['ant', 'humanoid'])
+_SLOTS = {'halfcheetah': {'reward_run': 0, 'reward_ctrl': 2, 'x_position': 4, 'x_velocity': 7}}
+
+
+@pytest.mark.parametrize('name', ['ant', 'humanoid', 'halfcheetah'])
 def test_reset_obs_and_step_outputs(name):
   from brax_b200 import workloads
   stub = _EnvStub(name, episode_length=1000)
   n = 8
-  _, q, qd = workloads.reset(name, 0, n, 0, 'cpu')
-  q, qd = q.numpy(), qd.numpy()
+  if name == 'halfcheetah':   # reset as half_cheetah.py:157-163, dropped towards the floor so that the capsules touch
+    rng0 = np.random.default_rng(3)
+    q = (np.asarray(stub.sys.init_q)[None] + rng0.uniform(-0.1, 0.1, (n, stub.sys.nq))).astype(np.float32)
+    q[:, 1] -= 0.3
+    qd = (0.1 * rng0.standard_normal((n, stub.sys.nv))).astype(np.float32)
+  else:
+    _, q, qd = workloads.reset(name, 0, n, 0, 'cpu')
+    q, qd = q.numpy(), qd.numpy()
   sim, orc = SimEnv(stub), _oracle(name, stub.sys, episode_length=1000)
   st, obs = sim.reset(q, qd)
   env = orc.reset(q, qd)
@@ -64,7 +79,8 @@ def test_reset_obs_and_step_outputs(name):
     np.testing.assert_array_equal(io['steps'], env['steps'])
     names = list(env['metrics'])
     for i, nm in enumerate(names):
-      np.testing.assert_allclose(io['metrics'][ok, i], env['metrics'][nm][ok], rtol=1e-3, atol=5e-3, err_msg=nm)
+      slot = _SLOTS.get(name, {}).get(nm, i)
+      np.testing.assert_allclose(io['metrics'][ok, slot], env['metrics'][nm][ok], rtol=1e-3, atol=5e-3, err_msg=nm)
 
 
 def test_episode_truncation_and_auto_reset():

@@ -10,6 +10,9 @@ def _oracle(name, sys, **kw):
   from oracle.env_oracle import EnvOracle
   if name == 'ant':
     return EnvOracle(sys, 'ant', ctrl_cost_weight=0.5, healthy_reward=1.0, healthy_z_range=(0.2, 1.0), **kw)
+  if name == 'halfcheetah':
+    return EnvOracle(sys, 'halfcheetah', forward_reward_weight=1.0, ctrl_cost_weight=0.1, healthy_reward=0.0,
+                     terminate_when_unhealthy=False, **kw)
   return EnvOracle(sys, 'humanoid', forward_reward_weight=1.25, ctrl_cost_weight=0.1, healthy_reward=5.0,
                    healthy_z_range=(1.0, 2.0), **kw)
 
@@ -24,7 +27,7 @@ def _state_from_oracle(torch, env_state_cls, ps_cls, o_env, dev, first=None):
                        torch.as_tensor(o_env['done'], device=dev), {}, info)
 
 
-@pytest.mark.parametrize('name', ['ant', 'humanoid'])
+@pytest.mark.parametrize('name', ['ant', 'humanoid', 'halfcheetah'])
 def test_env_reset_and_step_match_reference_restatement(name):
   import torch
   from brax_b200 import envs
@@ -32,7 +35,7 @@ def test_env_reset_and_step_match_reference_restatement(name):
   from brax_b200.generalized.base import State as PS
   n = 64
   env = envs.create(name, episode_length=1000, auto_reset=True, batch_size=n)
-  assert env.action_size == env.sys.nu and env.observation_size == (27 if name == 'ant' else 244)
+  assert env.action_size == env.sys.nu and env.observation_size == {'ant': 27, 'humanoid': 244, 'halfcheetah': 17}[name]
   st = env.reset(0)
   dev = st.obs.device
   orc = _oracle(name, env.sys, episode_length=1000, auto_reset=True)
