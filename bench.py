@@ -55,7 +55,7 @@ class ClockSampler:
   def start(self):
     try:
       self.proc = subprocess.Popen(
-          ['nvidia-smi', '-i', str(self.gpu), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100'],
+          ['nvidia-smi', '-i', str(self.gpu), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '20'],
           stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
       self.t = threading.Thread(target=self._read, daemon=True)
       self.t.start()
@@ -154,7 +154,7 @@ def run_reference(args, rank, world):
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
-  ap.add_argument('--steps', type=int, default=20)
+  ap.add_argument('--steps', type=int, default=100)
   ap.add_argument('--warmup', type=int, default=3)
   ap.add_argument('--workload', default='humanoid_8192', choices=sorted(WORKLOADS))
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
@@ -277,6 +277,7 @@ def main():
   r = measure(args.workload, args.steps, args.warmup, with_clocks=True)
   e2e = measure_e2e(r, args.steps)
   model = r['model']
+  plan = native.plan(r['nm'].sys, minv)
   algo_bytes = workloads.ALGO_BYTES[model] * r['n_env']          # per launch (= per rank per step)
   achieved = algo_bytes / (r['kern_avg_ms'] * 1e-3) / 1e9
   traffic = None
@@ -302,11 +303,13 @@ def main():
       'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
       'config': {'workload': args.workload, 'model': model, 'envs_per_gpu': r['n_env'], 'n_frames': r['nf'],
                  'minv': args.minv, 'parallelism': f'env-shard x{world}, no collective',
+                 'launch': {k: plan[k] for k in ('variant', 'lanes_per_env', 'envs_per_cta', 'smem_bytes_per_cta')},
                  'l2': 'flushed between steps (256 MiB write)' if r['flush'] else 'state >> L2, no flush'},
       'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
                    'traffic': traffic, 'peak_source': peak_src,
                    'algorithmic_bytes_per_env_step': workloads.ALGO_BYTES[model],
-                   'note': 'step is FP32-FMA-bound (SURVEY 8d); see profiles/ for pipe utilisation'},
+                   'note': 'the step is bound on-chip (shared-memory wavefronts of the Newton-Schulz products, then '
+                           'FP32 FMA), not by HBM (SURVEY 8d); see profiles/ for pipe utilisation'},
       'fp32': {'achieved': fp32_tflops, 'peak': FP32_PEAK_TFLOPS, 'unit': 'TFLOP/s', 'frac': fp32_tflops / FP32_PEAK_TFLOPS,
                'flops_per_env_step': flops_per_env_step,
                'note': 'non-tensor FP32 FMA peak at max clock; the dense work is fp32 by the parity requirement'},
