@@ -7,15 +7,27 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg
  * may build, load or call this file.  The product (brax_b200/) never does.
  *
- * PARITY STATUS: "parity unpinned" for the whole-step numerics -- the real
- * reference (JAX + jaxopt + mujoco.mjx) cannot be imported in this environment
- * and its own tests are differential tests against a live MuJoCo engine
- * (SURVEY.md F2/F6).  What IS pinned: the embedded known answers the reference
- * tests carry (tests/test_oracle_known_answers.py) and physics invariants
- * (tests/test_oracle_invariants.py).  Two pieces are restated from the
- * published algorithms of third-party packages that are not in
- * /root/reference: jaxopt.ProjectedGradient (unpinned version; FISTA +
- * backtracking line search) and mujoco.mjx plane-sphere collision.
+ * PARITY STATUS: pinned against outputs of the reference's own source for
+ * everything that lives in /root/reference; "parity unpinned" for the three
+ * third-party pieces that do not.
+ *   PINNED  tests/golden/ref_*.npz are written by tools/gen_reference_golden.py,
+ *           which imports brax.generalized.pipeline (and brax.envs + the training
+ *           wrappers) UNMODIFIED from /root/reference and runs them on NumPy
+ *           float64 through small stand-ins for jax / flax (tools/refshim/).
+ *           tests/test_reference_golden.py: this oracle reproduces every State
+ *           leaf after init and after every step to 1e-9 (Ant, Humanoid,
+ *           HalfCheetah, Hopper, a motorised pendulum; contacts and joint limits
+ *           active).  Also pinned: the known answers embedded in the reference's
+ *           tests (tests/test_oracle_known_answers.py) and physics invariants
+ *           (tests/test_oracle_invariants.py).
+ *   UNPINNED (restated from the published algorithms of packages that are not
+ *           installable here, identically in the stand-ins and in this file, so
+ *           the golden files cannot tell a shared misreading): jaxopt.
+ *           ProjectedGradient (unpinned version; FISTA + backtracking line
+ *           search), the mujoco.mjx plane-sphere / plane-capsule colliders, and
+ *           MuJoCo's model compiler (brax_b200/io/mjcf.py produces the System
+ *           constants both sides consume).  The real JAX float32 execution
+ *           (XLA op ordering) is not reproducible here either.
  *
  * Build twice: -DORC_REAL=float (parity) and -DORC_REAL=double (sanity).
  *

@@ -1,7 +1,8 @@
 """NumPy restatement of the reference envs around the physics oracle.
 
-TEST INFRASTRUCTURE ONLY (see oracle/bxg_oracle.c header).  Follows, statement
-by statement, float32:
+TEST INFRASTRUCTURE ONLY (see oracle/bxg_oracle.c header).  Pinned against the
+reference's own envs + training wrappers run on NumPy (tests/golden/ref_env_*.npz,
+tests/test_reference_golden.py).  Follows, statement by statement, float32:
   brax/envs/ant.py:233-279            Ant.step / _get_obs
   brax/envs/humanoid.py:256-354       Humanoid.step / _get_obs / _com
   brax/envs/half_cheetah.py:178-212   Halfcheetah.step / _get_obs

@@ -4,8 +4,9 @@ TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
 bench.py's cpu_baseline / --impl reference legs.  The product package
 (brax_b200/) must never import this module.
 
-Parity status: see the header of bxg_oracle.c ("parity unpinned" for
-whole-step numerics; known answers + invariants pinned in tests/).
+Parity status: see the header of bxg_oracle.c (pinned to 1e-9 against the reference's own
+source run on NumPy, tests/test_reference_golden.py; "parity unpinned" only for jaxopt's
+solver, the mjx colliders and MuJoCo's model compiler, which are not installable here).
 """
 from __future__ import annotations
 

