@@ -241,7 +241,7 @@ int bxg_env_obs_size(const BxgModel* m, const BxgEnvSpec* spec) {
 int bxg_env_reset(const BxgModel* m, const BxgEnvSpec* spec, int64_t n_env, const float* q, const float* qd,
                   const BxgState* out, float* obs, void* stream) {
   if (!m || !spec) return fail(BXG_E_INVALID, "null argument");
-  if (spec->kind != BXG_ENV_ROOT_VELOCITY && spec->kind != BXG_ENV_COM_VELOCITY) return fail(BXG_E_INVALID, "unknown env kind");
+  if (spec->kind != BXG_ENV_ROOT_VELOCITY && spec->kind != BXG_ENV_COM_VELOCITY && spec->kind != BXG_ENV_PLANAR) return fail(BXG_E_INVALID, "unknown env kind");
   if (n_env <= 0) return n_env == 0 ? BXG_OK : fail(BXG_E_INVALID, "n_env < 0");
   if (!q || !qd || !obs || !state_ok(out, m->pm.d.nc)) return fail(BXG_E_INVALID, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -258,8 +258,9 @@ int bxg_env_reset(const BxgModel* m, const BxgEnvSpec* spec, int64_t n_env, cons
 int bxg_env_step(const BxgModel* m, const BxgEnvSpec* spec, int64_t n_env, int32_t n_frames, const BxgState* in,
                  const float* action, const BxgState* out, const BxgEnvIO* io, void* stream) {
   if (!m || !spec || !io) return fail(BXG_E_INVALID, "null argument");
-  if (spec->kind != BXG_ENV_ROOT_VELOCITY && spec->kind != BXG_ENV_COM_VELOCITY) return fail(BXG_E_INVALID, "unknown env kind");
+  if (spec->kind != BXG_ENV_ROOT_VELOCITY && spec->kind != BXG_ENV_COM_VELOCITY && spec->kind != BXG_ENV_PLANAR) return fail(BXG_E_INVALID, "unknown env kind");
   if (spec->obs_skip < 0 || spec->obs_skip > m->pm.d.nq || !(spec->env_dt > 0.f)) return fail(BXG_E_INVALID, "bad env spec");
+  if (spec->kind == BXG_ENV_PLANAR && m->pm.d.nq < 3) return fail(BXG_E_INVALID, "planar env kind needs q = [x, z, angle, ...]");
   if (n_frames < 1) return fail(BXG_E_INVALID, "n_frames < 1");
   if (n_env <= 0) return n_env == 0 ? BXG_OK : fail(BXG_E_INVALID, "n_env < 0");
   if (!state_ok(in, m->pm.d.nc) || !state_ok(out, m->pm.d.nc)) return fail(BXG_E_INVALID, "null state leaf");

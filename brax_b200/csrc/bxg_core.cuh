@@ -1472,8 +1472,14 @@ BXG_HD void env_write_obs(X& ex, const Ctx& c, const BxgEnvSpec& sp, float* o) {
   ex.lanes([&](int lane) {
     const int G = X::G;
     const int np = nq - sp.obs_skip;
-    for (int i = lane; i < np; i += G) o[i] = s[D.s_q + sp.obs_skip + i];
-    for (int i = lane; i < nv; i += G) o[np + i] = s[D.s_qd + i];
+    if (sp.kind == BXG_ENV_PLANAR) {
+      // position = q.at[1].set(x.pos[0, 2]); velocity = clip(qd, -10, 10)  (envs/hopper.py:266-276, walker2d.py:263-273)
+      for (int i = lane; i < np; i += G) o[i] = sp.obs_skip + i == 1 ? s[D.s_x_pos + 2] : s[D.s_q + sp.obs_skip + i];
+      for (int i = lane; i < nv; i += G) o[np + i] = fmaxf(-10.f, fminf(s[D.s_qd + i], 10.f));
+    } else {
+      for (int i = lane; i < np; i += G) o[i] = s[D.s_q + sp.obs_skip + i];
+      for (int i = lane; i < nv; i += G) o[np + i] = s[D.s_qd + i];
+    }
     if (sp.kind == BXG_ENV_COM_VELOCITY) {
       float mass_sum = 0.f;
       for (int l = 0; l < L; ++l) mass_sum += mf[D.m_in_mass + l];
@@ -1518,6 +1524,15 @@ BXG_HD void env_epilogue(X& ex, const Ctx& c, const BxgEnvSpec& sp, const BxgEnv
   float z = s[D.s_x_pos + 2];
   float is_healthy = z < sp.healthy_z_min ? 0.f : 1.f;
   if (z > sp.healthy_z_max) is_healthy = 0.f;
+  if (sp.kind == BXG_ENV_PLANAR) {
+    // strict ranges on z, the root angle q[2] and every entry of [q[2:], qd]
+    // (envs/hopper.py:233-244; walker2d.py:215-219 is the same test without the state range)
+    const float angle = s[D.s_q + 2];
+    bool ok = sp.healthy_z_min < z && z < sp.healthy_z_max && sp.healthy_angle_min < angle && angle < sp.healthy_angle_max;
+    for (int i = 2; i < nq; ++i) ok = ok && sp.healthy_state_min < s[D.s_q + i] && s[D.s_q + i] < sp.healthy_state_max;
+    for (int i = 0; i < nv; ++i) ok = ok && sp.healthy_state_min < s[D.s_qd + i] && s[D.s_qd + i] < sp.healthy_state_max;
+    is_healthy = ok ? 1.f : 0.f;
+  }
   float healthy_reward = sp.terminate_when_unhealthy ? sp.healthy_reward : sp.healthy_reward * is_healthy;
   float sq = 0.f;
   for (int a = 0; a < D.nu; ++a) sq += s[D.s_act + a] * s[D.s_act + a];

@@ -1,12 +1,13 @@
-"""Environments in scope (reference `brax/envs/__init__.py:35-107`): ant, humanoid, halfcheetah."""
+"""Environments in scope (reference `brax/envs/__init__.py:35-107`): ant, humanoid, halfcheetah, hopper, walker2d."""
 from typing import Optional
 
 from brax_b200.envs.ant import Ant
 from brax_b200.envs.base import FusedEnv, State
 from brax_b200.envs.half_cheetah import Halfcheetah
+from brax_b200.envs.hopper import Hopper, Walker2d
 from brax_b200.envs.humanoid import Humanoid
 
-_envs = {'ant': Ant, 'humanoid': Humanoid, 'halfcheetah': Halfcheetah}
+_envs = {'ant': Ant, 'humanoid': Humanoid, 'halfcheetah': Halfcheetah, 'hopper': Hopper, 'walker2d': Walker2d}
 
 
 def get_environment(env_name: str, **kwargs) -> FusedEnv:

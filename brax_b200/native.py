@@ -65,6 +65,7 @@ class DiagC(ctypes.Structure):
 
 ENV_ROOT_VELOCITY = 1
 ENV_COM_VELOCITY = 2
+ENV_PLANAR = 3
 ENV_NUM_METRICS = 10
 
 
@@ -72,7 +73,9 @@ class EnvSpecC(ctypes.Structure):
   """Mirror of BxgEnvSpec (include/bxg.h)."""
   _fields_ = [('kind', _i32), ('obs_skip', _i32), ('terminate_when_unhealthy', _i32), ('episode_length', _i32),
               ('forward_reward_weight', _f32), ('ctrl_cost_weight', _f32), ('healthy_reward', _f32),
-              ('healthy_z_min', _f32), ('healthy_z_max', _f32), ('env_dt', _f32)]
+              ('healthy_z_min', _f32), ('healthy_z_max', _f32), ('env_dt', _f32),
+              ('healthy_angle_min', _f32), ('healthy_angle_max', _f32),
+              ('healthy_state_min', _f32), ('healthy_state_max', _f32)]
 
 
 class EnvIOC(ctypes.Structure):

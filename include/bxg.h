@@ -165,6 +165,8 @@ typedef struct BxgDiag {
  */
 enum {
   BXG_ENV_ROOT_VELOCITY = 1,  /* Ant:      velocity of link 0, obs = [q[skip:], qd]          */
+  BXG_ENV_PLANAR = 3,         /* Hopper / Walker2d: velocity of link 0; healthy = z, angle q[2] and state ranges
+                                 (strict); obs = [q[skip:] with q[1] := z of link 0, clip(qd, -10, 10)]          */
   BXG_ENV_COM_VELOCITY = 2    /* Humanoid: velocity of the centre of mass, obs = [q[skip:],
                                  qd, com_inertia, com_velocity, qfrc_actuator]; the action is
                                  rescaled from [-1,1] to the ctrl range first                */
@@ -181,11 +183,14 @@ typedef struct BxgEnvSpec {
   float healthy_reward;
   float healthy_z_min, healthy_z_max;
   float env_dt;                      /* sys.opt.timestep * n_frames */
+  float healthy_angle_min, healthy_angle_max;   /* BXG_ENV_PLANAR: range of q[2] */
+  float healthy_state_min, healthy_state_max;   /* BXG_ENV_PLANAR: range of every entry of [q[2:], qd] */
 } BxgEnvSpec;
 
 /* Per-env arrays, device pointers.  metrics order:
  *  ROOT_VELOCITY: reward_forward, reward_survive, reward_ctrl, reward_contact, x_position,
  *                 y_position, distance_from_origin, x_velocity, y_velocity, forward_reward
+ *  PLANAR:        reward_forward, reward_healthy, reward_ctrl, -, x_position, -, -, x_velocity, -, -
  *  COM_VELOCITY:  forward_reward, reward_linvel, reward_quadctrl, reward_alive, x_position,
  *                 y_position, distance_from_origin, x_velocity, y_velocity, (unused)        */
 typedef struct BxgEnvIO {

@@ -6,6 +6,8 @@ tests/test_reference_golden.py).  Follows, statement by statement, float32:
   brax/envs/ant.py:233-279            Ant.step / _get_obs
   brax/envs/humanoid.py:256-354       Humanoid.step / _get_obs / _com
   brax/envs/half_cheetah.py:178-212   Halfcheetah.step / _get_obs
+  brax/envs/hopper.py:219-276         Hopper.step / _get_obs
+  brax/envs/walker2d.py:200-273       Walker2d.step / _get_obs
   brax/envs/wrappers/training.py:98-158  EpisodeWrapper.step, AutoResetWrapper.step
   brax/actuator.py:23-57              to_tau (for Humanoid's qfrc_actuator)
 """
@@ -27,13 +29,17 @@ def _rotate(v, q):
 class EnvOracle:
   def __init__(self, sys, kind, *, forward_reward_weight=1.0, ctrl_cost_weight, healthy_reward,
                terminate_when_unhealthy=True, healthy_z_range=(-np.inf, np.inf), exclude_current_positions=True,
-               n_frames=5, episode_length=None, auto_reset=False):
+               n_frames=5, episode_length=None, auto_reset=False,
+               healthy_angle_range=(-np.inf, np.inf), healthy_state_range=(-np.inf, np.inf)):
     self.sys, self.kind = sys, kind
     self.o = O.Oracle(sys, np.float32)
     self.w_fwd, self.w_ctrl, self.h_rew = f32(forward_reward_weight), f32(ctrl_cost_weight), f32(healthy_reward)
     self.term = terminate_when_unhealthy
     self.zmin, self.zmax = f32(healthy_z_range[0]), f32(healthy_z_range[1])
-    self.skip = (1 if kind == 'halfcheetah' else 2) if exclude_current_positions else 0
+    self.planar = kind in ('hopper', 'walker2d')
+    self.skip = (1 if kind == 'halfcheetah' or self.planar else 2) if exclude_current_positions else 0
+    self.amin, self.amax = f32(healthy_angle_range[0]), f32(healthy_angle_range[1])
+    self.smin, self.smax = f32(healthy_state_range[0]), f32(healthy_state_range[1])
     self.n_frames = n_frames
     self.dt = f32(sys.opt.timestep) * f32(n_frames)
     self.episode_length, self.auto_reset = episode_length, auto_reset
@@ -67,6 +73,9 @@ class EnvOracle:
     return tau
 
   def obs(self, st, action):
+    if self.planar:   # position = q.at[1].set(x.pos[0, 2]); velocity = clip(qd, -10, 10)
+      pos = st['q'].copy(); pos[:, 1] = st['x_pos'][:, 0, 2]
+      return np.concatenate([pos[:, self.skip:], np.clip(st['qd'], f32(-10), f32(10))], 1).astype(f32)
     q, qd = st['q'][:, self.skip:], st['qd']
     if self.kind in ('ant', 'halfcheetah'):
       return np.concatenate([q, qd], 1).astype(f32)
@@ -110,6 +119,12 @@ class EnvOracle:
     z = ps['x_pos'][:, 0, 2]
     healthy = np.where(z < self.zmin, f32(0), f32(1)).astype(f32)
     healthy = np.where(z > self.zmax, f32(0), healthy).astype(f32)
+    if self.planar:   # strict ranges on z, angle = q[2] and the state vector [q[2:], qd]
+      angle = ps['q'][:, 2]
+      sv = np.concatenate([ps['q'][:, 2:], ps['qd']], 1)
+      ok = (self.zmin < z) & (z < self.zmax) & (self.amin < angle) & (angle < self.amax)
+      ok &= np.all((self.smin < sv) & (sv < self.smax), axis=1)
+      healthy = ok.astype(f32)
     h_rew = np.full_like(healthy, self.h_rew) if self.term else (self.h_rew * healthy).astype(f32)
     sq = np.zeros(action.shape[0], f32)
     for a in range(action.shape[1]):
@@ -121,6 +136,8 @@ class EnvOracle:
     if self.kind == 'halfcheetah':   # reward = forward_reward - ctrl_cost; done is never set (half_cheetah.py:189-199)
       reward = (forward - ctrl).astype(f32)
       m = {'x_position': after[:, 0], 'x_velocity': velocity[:, 0], 'reward_ctrl': -ctrl, 'reward_run': forward}
+    elif self.planar:
+      m = {'reward_forward': forward, 'reward_ctrl': -ctrl, 'reward_healthy': h_rew, 'x_position': after[:, 0], 'x_velocity': velocity[:, 0]}
     elif self.kind == 'ant':
       m = {'reward_forward': forward, 'reward_survive': h_rew, 'reward_ctrl': -ctrl, 'reward_contact': np.zeros_like(ctrl),
            'x_position': after[:, 0], 'y_position': after[:, 1], 'distance_from_origin': dist,

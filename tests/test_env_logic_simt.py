@@ -21,19 +21,30 @@ class _EnvStub:
     elif name == 'halfcheetah':
       sp.kind, sp.forward_reward_weight, sp.ctrl_cost_weight, sp.healthy_reward = native.ENV_ROOT_VELOCITY, 1.0, 0.1, 0.0
       sp.healthy_z_min, sp.healthy_z_max = -3.0e38, 3.0e38
+    elif name in ('hopper', 'walker2d'):
+      sp.kind, sp.forward_reward_weight, sp.ctrl_cost_weight, sp.healthy_reward = native.ENV_PLANAR, 1.0, 1e-3, 1.0
+      sp.healthy_z_min, sp.healthy_z_max = (0.7, 3.0e38) if name == 'hopper' else (0.8, 2.0)
+      sp.healthy_angle_min, sp.healthy_angle_max = (-0.2, 0.2) if name == 'hopper' else (-1.0, 1.0)
+      sp.healthy_state_min, sp.healthy_state_max = (-100.0, 100.0) if name == 'hopper' else (-3.0e38, 3.0e38)
     else:
       sp.kind, sp.forward_reward_weight, sp.ctrl_cost_weight, sp.healthy_reward = native.ENV_COM_VELOCITY, 1.25, 0.1, 5.0
       sp.healthy_z_min, sp.healthy_z_max = 1.0, 2.0
-    sp.obs_skip, sp.terminate_when_unhealthy = (1, 0) if name == 'halfcheetah' else (2, 1)
+    sp.obs_skip, sp.terminate_when_unhealthy = {'halfcheetah': (1, 0), 'hopper': (1, 1), 'walker2d': (1, 1)}.get(name, (2, 1))
     sp.episode_length = episode_length or 0
-    self.n_frames = 5
-    sp.env_dt = float(np.float32(self.sys.opt.timestep) * np.float32(5))
+    self.n_frames = 4 if name in ('hopper', 'walker2d') else 5
+    sp.env_dt = float(np.float32(self.sys.opt.timestep) * np.float32(self.n_frames))
     self.spec = sp
 
 
 def _oracle(name, sys, **kw):
   if name == 'ant':
     return EnvOracle(sys, 'ant', ctrl_cost_weight=0.5, healthy_reward=1.0, healthy_z_range=(0.2, 1.0), **kw)
+  if name == 'hopper':
+    return EnvOracle(sys, 'hopper', forward_reward_weight=1.0, ctrl_cost_weight=1e-3, healthy_reward=1.0, n_frames=4,
+                     healthy_z_range=(0.7, np.inf), healthy_angle_range=(-0.2, 0.2), healthy_state_range=(-100.0, 100.0), **kw)
+  if name == 'walker2d':
+    return EnvOracle(sys, 'walker2d', forward_reward_weight=1.0, ctrl_cost_weight=1e-3, healthy_reward=1.0, n_frames=4,
+                     healthy_z_range=(0.8, 2.0), healthy_angle_range=(-1.0, 1.0), **kw)
   if name == 'halfcheetah':
     return EnvOracle(sys, 'halfcheetah', forward_reward_weight=1.0, ctrl_cost_weight=0.1, healthy_reward=0.0,
                      terminate_when_unhealthy=False, **kw)
@@ -41,19 +52,24 @@ def _oracle(name, sys, **kw):
                    healthy_z_range=(1.0, 2.0), **kw)
 
 
-_SLOTS = {'halfcheetah': {'reward_run': 0, 'reward_ctrl': 2, 'x_position': 4, 'x_velocity': 7}}
+_PLANAR_SLOTS = {'reward_forward': 0, 'reward_healthy': 1, 'reward_ctrl': 2, 'x_position': 4, 'x_velocity': 7}
+_SLOTS = {'halfcheetah': {'reward_run': 0, 'reward_ctrl': 2, 'x_position': 4, 'x_velocity': 7},
+          'hopper': _PLANAR_SLOTS, 'walker2d': _PLANAR_SLOTS}
 
 
-@pytest.mark.parametrize('name', ['ant', 'humanoid', 'halfcheetah'])
+@pytest.mark.parametrize('name', ['ant', 'humanoid', 'halfcheetah', 'hopper', 'walker2d'])
 def test_reset_obs_and_step_outputs(name):
   from brax_b200 import workloads
   stub = _EnvStub(name, episode_length=1000)
   n = 8
-  if name == 'halfcheetah':   # reset as half_cheetah.py:157-163, dropped towards the floor so that the capsules touch
+  if name in ('halfcheetah', 'hopper', 'walker2d'):   # reset noise as the reference envs, dropped towards the floor so that the capsules touch
     rng0 = np.random.default_rng(3)
-    q = (np.asarray(stub.sys.init_q)[None] + rng0.uniform(-0.1, 0.1, (n, stub.sys.nq))).astype(np.float32)
-    q[:, 1] -= 0.3
-    qd = (0.1 * rng0.standard_normal((n, stub.sys.nv))).astype(np.float32)
+    noise = 0.1 if name == 'halfcheetah' else 5e-3
+    q = (np.asarray(stub.sys.init_q)[None] + rng0.uniform(-noise, noise, (n, stub.sys.nq))).astype(np.float32)
+    q[:, 1] -= {'halfcheetah': 0.3, 'hopper': 0.03, 'walker2d': 0.03}[name]
+    if name == 'hopper':
+      q[0, 2] = 0.5      # root angle outside (-0.2, 0.2): unhealthy, terminates
+    qd = (noise * rng0.standard_normal((n, stub.sys.nv))).astype(np.float32)
   else:
     _, q, qd = workloads.reset(name, 0, n, 0, 'cpu')
     q, qd = q.numpy(), qd.numpy()

@@ -10,6 +10,12 @@ def _oracle(name, sys, **kw):
   from oracle.env_oracle import EnvOracle
   if name == 'ant':
     return EnvOracle(sys, 'ant', ctrl_cost_weight=0.5, healthy_reward=1.0, healthy_z_range=(0.2, 1.0), **kw)
+  if name == 'hopper':
+    return EnvOracle(sys, 'hopper', forward_reward_weight=1.0, ctrl_cost_weight=1e-3, healthy_reward=1.0, n_frames=4,
+                     healthy_z_range=(0.7, np.inf), healthy_angle_range=(-0.2, 0.2), healthy_state_range=(-100.0, 100.0), **kw)
+  if name == 'walker2d':
+    return EnvOracle(sys, 'walker2d', forward_reward_weight=1.0, ctrl_cost_weight=1e-3, healthy_reward=1.0, n_frames=4,
+                     healthy_z_range=(0.8, 2.0), healthy_angle_range=(-1.0, 1.0), **kw)
   if name == 'halfcheetah':
     return EnvOracle(sys, 'halfcheetah', forward_reward_weight=1.0, ctrl_cost_weight=0.1, healthy_reward=0.0,
                      terminate_when_unhealthy=False, **kw)
@@ -27,7 +33,7 @@ def _state_from_oracle(torch, env_state_cls, ps_cls, o_env, dev, first=None):
                        torch.as_tensor(o_env['done'], device=dev), {}, info)
 
 
-@pytest.mark.parametrize('name', ['ant', 'humanoid', 'halfcheetah'])
+@pytest.mark.parametrize('name', ['ant', 'humanoid', 'halfcheetah', 'hopper', 'walker2d'])
 def test_env_reset_and_step_match_reference_restatement(name):
   import torch
   from brax_b200 import envs
@@ -35,7 +41,7 @@ def test_env_reset_and_step_match_reference_restatement(name):
   from brax_b200.generalized.base import State as PS
   n = 64
   env = envs.create(name, episode_length=1000, auto_reset=True, batch_size=n)
-  assert env.action_size == env.sys.nu and env.observation_size == {'ant': 27, 'humanoid': 244, 'halfcheetah': 17}[name]
+  assert env.action_size == env.sys.nu and env.observation_size == {'ant': 27, 'humanoid': 244, 'halfcheetah': 17, 'hopper': 11, 'walker2d': 17}[name]
   st = env.reset(0)
   dev = st.obs.device
   orc = _oracle(name, env.sys, episode_length=1000, auto_reset=True)

@@ -81,6 +81,10 @@ ENVS = {
     'humanoid': dict(kind='humanoid', forward_reward_weight=1.25, ctrl_cost_weight=0.1, healthy_reward=5.0, healthy_z_range=(1.0, 2.0)),
     'halfcheetah': dict(kind='halfcheetah', forward_reward_weight=1.0, ctrl_cost_weight=0.1, healthy_reward=0.0,
                         terminate_when_unhealthy=False),
+    'hopper': dict(kind='hopper', forward_reward_weight=1.0, ctrl_cost_weight=1e-3, healthy_reward=1.0, n_frames=4,
+                   healthy_z_range=(0.7, np.inf), healthy_angle_range=(-0.2, 0.2), healthy_state_range=(-100.0, 100.0)),
+    'walker2d': dict(kind='walker2d', forward_reward_weight=1.0, ctrl_cost_weight=1e-3, healthy_reward=1.0, n_frames=4,
+                     healthy_z_range=(0.8, 2.0), healthy_angle_range=(-1.0, 1.0)),
 }
 
 

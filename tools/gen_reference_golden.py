@@ -122,7 +122,8 @@ def load(name):
   return model_json.load(os.path.join(ROOT, 'tests', 'golden', f'{name}.json'))
 
 
-ENV_XML = {'ant.xml': 'ant', 'humanoid.xml': 'humanoid', 'half_cheetah.xml': 'halfcheetah'}
+ENV_XML = {'ant.xml': 'ant', 'humanoid.xml': 'humanoid', 'half_cheetah.xml': 'halfcheetah', 'hopper.xml': 'hopper',
+           'walker2d.xml': 'walker2d'}
 
 
 def _mjcf_load(path):
@@ -137,16 +138,22 @@ def env_golden():
   import jax
   mjcf_stub.load = _mjcf_load
   from brax.envs import ant as ref_ant, half_cheetah as ref_hc, humanoid as ref_hum   # the reference
+  from brax.envs import hopper as ref_hop, walker2d as ref_walk                       # the reference
   from brax.envs.wrappers import training as ref_wrap                                 # the reference
   assert ref_wrap.__file__.startswith('/root/reference/')
-  cases = {'ant': (ref_ant.Ant, 4, 7, 5), 'humanoid': (ref_hum.Humanoid, 3, 6, 4), 'halfcheetah': (ref_hc.Halfcheetah, 3, 5, 3)}
+  cases = {'ant': (ref_ant.Ant, 4, 7, 5), 'humanoid': (ref_hum.Humanoid, 3, 6, 4), 'halfcheetah': (ref_hc.Halfcheetah, 3, 5, 3),
+           'hopper': (ref_hop.Hopper, 4, 6, 4), 'walker2d': (ref_walk.Walker2d, 3, 5, 4)}
   for name, (cls, n, steps, ep_len) in cases.items():
     env = ref_wrap.wrap(cls(backend='generalized'), episode_length=ep_len, action_repeat=1)
     rng = np.random.default_rng(7)
     st = env.reset(jax.random.split(jax.random.PRNGKey(3), n))
-    if name == 'ant':       # one env starts outside the healthy z range: terminates on the first step
-      q = np.asarray(st.pipeline_state.q).copy(); q[0, 2] = 1.3
-      inner = env.env.env.env     # AutoReset -> Episode -> Vmap -> Ant
+    if name in ('ant', 'hopper'):   # one env starts unhealthy (Ant: z too high; Hopper: root angle out of range): terminates at once
+      q = np.asarray(st.pipeline_state.q).copy()
+      if name == 'ant':
+        q[0, 2] = 1.3
+      else:
+        q[0, 2] = 0.5
+      inner = env.env.env.env     # AutoReset -> Episode -> Vmap -> the env
       ps = jax.vmap(inner.pipeline_init)(jp.array(q), st.pipeline_state.qd)
       obs = jax.vmap(inner._get_obs)(ps)
       st = st.replace(pipeline_state=ps, obs=obs)
