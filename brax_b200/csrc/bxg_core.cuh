@@ -1621,14 +1621,21 @@ BXG_HD void load_env(X& ex, const Ctx& c, const BxgState& g, const float* act, i
       s[D.s_cdof_ang + i] = g.cdof_ang[e * nv * 3 + i]; s[D.s_cdof_vel + i] = g.cdof_vel[e * nv * 3 + i];
       s[D.s_cdofd_ang + i] = g.cdofd_ang[e * nv * 3 + i]; s[D.s_cdofd_vel + i] = g.cdofd_vel[e * nv * 3 + i];
     }
-    for (int i = lane; i < nv * nv; i += G) {
-      int r = i / nv, cc = i - r * nv;
-      s[D.s_Minv + r * nvp + cc] = g.mass_mx_inv[e * nv * nv + i];
-      s[D.s_M + r * nvp + cc] = g.mass_mx[e * nv * nv + i];
-    }
-    for (int i = lane; i < nc * nv; i += G) {
-      int r = i / nv, cc = i - r * nv;
-      s[D.s_J + r * D.jld + cc] = g.con_jac[e * nc * nv + i];
+    // matrices: flat, fully coalesced reads; (row, column) of the re-strided shared-memory copy
+    // advance incrementally (no integer division by nv)
+    {
+      const int dq = G / nv, dr = G - dq * nv;    // i += G  <=>  (r, cc) += (dq, dr) with one carry
+      int r = lane / nv, cc = lane - r * nv;
+      for (int i = lane; i < nv * nv; i += G) {
+        s[D.s_Minv + r * nvp + cc] = g.mass_mx_inv[e * nv * nv + i];
+        s[D.s_M + r * nvp + cc] = g.mass_mx[e * nv * nv + i];
+        r += dq; cc += dr; if (cc >= nv) { cc -= nv; ++r; }
+      }
+      r = lane / nv; cc = lane - r * nv;
+      for (int i = lane; i < nc * nv; i += G) {
+        s[D.s_J + r * D.jld + cc] = g.con_jac[e * nc * nv + i];
+        r += dq; cc += dr; if (cc >= nv) { cc -= nv; ++r; }
+      }
     }
     for (int i = lane; i < nc; i += G) { s[D.s_diag + i] = g.con_diag[e * nc + i]; s[D.s_aref + i] = g.con_aref[e * nc + i]; }
   });
@@ -1676,14 +1683,19 @@ BXG_HD void store_env(X& ex, const Ctx& c, const BxgState& g, int64_t e, const B
       g.cdof_ang[e * nv * 3 + i] = s[D.s_cdof_ang + i]; g.cdof_vel[e * nv * 3 + i] = s[D.s_cdof_vel + i];
       g.cdofd_ang[e * nv * 3 + i] = s[D.s_cdofd_ang + i]; g.cdofd_vel[e * nv * 3 + i] = s[D.s_cdofd_vel + i];
     }
-    for (int i = lane; i < nv * nv; i += G) {
-      int r = i / nv, cc = i - r * nv;
-      g.mass_mx[e * nv * nv + i] = s[D.s_M + r * nvp + cc];
-      g.mass_mx_inv[e * nv * nv + i] = s[D.s_Minv + r * nvp + cc];
-    }
-    for (int i = lane; i < nc * nv; i += G) {
-      int r = i / nv, cc = i - r * nv;
-      g.con_jac[e * nc * nv + i] = s[D.s_J + r * D.jld + cc];
+    {
+      const int dq = G / nv, dr = G - dq * nv;
+      int r = lane / nv, cc = lane - r * nv;
+      for (int i = lane; i < nv * nv; i += G) {
+        g.mass_mx[e * nv * nv + i] = s[D.s_M + r * nvp + cc];
+        g.mass_mx_inv[e * nv * nv + i] = s[D.s_Minv + r * nvp + cc];
+        r += dq; cc += dr; if (cc >= nv) { cc -= nv; ++r; }
+      }
+      r = lane / nv; cc = lane - r * nv;
+      for (int i = lane; i < nc * nv; i += G) {
+        g.con_jac[e * nc * nv + i] = s[D.s_J + r * D.jld + cc];
+        r += dq; cc += dr; if (cc >= nv) { cc -= nv; ++r; }
+      }
     }
     for (int i = lane; i < nc; i += G) { g.con_diag[e * nc + i] = s[D.s_diag + i]; g.con_aref[e * nc + i] = s[D.s_aref + i]; }
     if (dg) {

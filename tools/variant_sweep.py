@@ -8,15 +8,9 @@ def _lib(name):
 
 
 CONFIGS = [
-    ('hum_sl1', 'humanoid_8192', {}),
-    ('hum_split', 'humanoid_8192', {'BXG_SYNC_LEVEL': '192'}),
-    ('hum_sl0', 'humanoid_8192', {'BXG_SYNC_LEVEL': '0'}),
-    ('hum_sl3', 'humanoid_8192', {'BXG_SYNC_LEVEL': '3'}),
-    ('hum512k_sl1', 'humanoid_512k', {}),
-    ('hum512k_split', 'humanoid_512k', {'BXG_SYNC_LEVEL': '192'}),
-    ('ant_sl1', 'ant_1m', {}),
-    ('ant_split', 'ant_1m', {'BXG_SYNC_LEVEL': '192'}),
-    ('ant_sl0', 'ant_1m', {'BXG_SYNC_LEVEL': '0'}),
+    ('hum_default', 'humanoid_8192', {}),
+    ('hum512k_default', 'humanoid_512k', {}),
+    ('ant_default', 'ant_1m', {}),
 ]
 out_path = sys.argv[1]
 only = sys.argv[2] if len(sys.argv) > 2 else ''
