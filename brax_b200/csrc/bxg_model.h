@@ -34,14 +34,13 @@ struct Dims {
   int m_link_parent, m_link_ndof, m_link_qadr, m_link_dadr, m_link_depth, m_link_root;
   int m_child_start, m_child_list;       // CSR, children in DEscending index order
   int m_dof_link, m_dof_qidx;            // dof -> link, dof -> q index
-  int m_dof_anc_lo, m_dof_anc_hi;        // bitmask over dofs j<=i whose link is ancestor-or-self
-  int m_mm_pairs, n_mm_pairs;            // the same relation as a list of (i | j << 8): the non-zeros of the lower triangle of M
+  int m_mm_pairs, n_mm_pairs;            // (i | j << 8) for dofs j <= i whose link is ancestor-or-self of dof i's link: the non-zeros of the lower triangle of M
   int m_dof_act_start, m_dof_act_list;   // CSR actuators per dof
   int m_lim_dof;                         // [nlim] dof of each limit row
   int m_tf_pos, m_tf_rot, m_joint_pos, m_in_pos, m_in_rot, m_in_i, m_in_mass, m_link_invw;
   int m_dof_ang, m_dof_vel, m_arm, m_stiff, m_damp, m_lim_lo, m_lim_hi, m_dof_invw, m_dof_sp;
   int m_act_qid, m_act_did, m_act_gain, m_act_gear, m_act_clo, m_act_chi, m_act_flo, m_act_fhi, m_act_bq, m_act_bqd;
-  int m_con_la, m_con_lb, m_con_ppos, m_con_frame, m_con_spos, m_con_rad, m_con_mu, m_con_sp;  // sp: [ncon,7]
+  int m_con_lb, m_con_ppos, m_con_frame, m_con_spos, m_con_rad, m_con_mu, m_con_sp;  // sp: [ncon,7]
   int m_con_kind, m_con_gquat, m_con_half;   // plane-capsule end points: kind 1, geom quaternion [ncon,4], signed half length
   int m_con_anc_lo, m_con_anc_hi;        // [ncon] bitmask of dofs that move link_b
   int model_words;
@@ -180,13 +179,6 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
   }
   d.m_dof_link = put_i(dof_link); d.m_dof_qidx = put_i(dof_q);
   auto is_anc = [&](int anc, int l) { while (l >= 0) { if (l == anc) return true; l = m.link_parent[l]; } return false; };
-  std::vector<int> alo(m.nv), ahi(m.nv);
-  for (int i = 0; i < m.nv; ++i) {
-    uint64_t mask = 0;
-    for (int j = 0; j <= i; ++j) if (is_anc(dof_link[j], dof_link[i])) mask |= (uint64_t)1 << j;
-    alo[i] = (int)(uint32_t)(mask & 0xffffffffu); ahi[i] = (int)(uint32_t)(mask >> 32);
-  }
-  d.m_dof_anc_lo = put_i(alo); d.m_dof_anc_hi = put_i(ahi);
   std::vector<int> pairs;
   for (int i = 0; i < m.nv; ++i)
     for (int j = 0; j <= i; ++j) if (is_anc(dof_link[j], dof_link[i])) pairs.push_back(i | (j << 8));
@@ -229,7 +221,7 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
     if (m.con_link_b[c] < 0 || m.con_link_b[c] >= L) return "con_link_b out of range";
     if (m.con_link_a[c] != -1) return "plane must be attached to the world (link_a == -1)";
   }
-  d.m_con_la = put_ip(m.con_link_a, m.ncon); d.m_con_lb = put_ip(m.con_link_b, m.ncon);
+  d.m_con_lb = put_ip(m.con_link_b, m.ncon);
   d.m_con_ppos = put_f(m.con_plane_pos, m.ncon * 3); d.m_con_frame = put_f(m.con_frame, m.ncon * 9);
   d.m_con_spos = put_f(m.con_sphere_pos, m.ncon * 3); d.m_con_rad = put_f(m.con_radius, m.ncon);
   d.m_con_mu = put_f(m.con_friction, m.ncon);
