@@ -9,8 +9,11 @@ def _lib(name):
 
 CONFIGS = [
     ('hum_default', 'humanoid_8192', {}),
+    ('hum_ks', 'humanoid_8192', _lib('ks')),
+    ('hum_ks_u3', 'humanoid_8192', _lib('ks_u3')),
+    ('hum_ks_u6', 'humanoid_8192', _lib('ks_u6')),
     ('hum512k_default', 'humanoid_512k', {}),
-    ('ant_default', 'ant_1m', {}),
+    ('hum512k_ks', 'humanoid_512k', _lib('ks')),
 ]
 out_path = sys.argv[1]
 only = sys.argv[2] if len(sys.argv) > 2 else ''
