@@ -42,6 +42,10 @@
 #ifndef BXG_TILE_UNROLL
 #define BXG_TILE_UNROLL 2
 #endif
+// explicit software pipeline in the tile product of the half-warp 16-wide variant (unroll of its k-block loop)
+#ifndef BXG_PIPE16_UNROLL
+#define BXG_PIPE16_UNROLL 1
+#endif
 #define BXG_PRAGMA_(x) _Pragma(#x)
 #define BXG_PRAGMA_UNROLL(n) BXG_PRAGMA_(unroll n)
 
@@ -815,10 +819,12 @@ BXG_HD float row_dot(const float* a, const float* v) {
 // 4*TM*TN FFMA, which balances the shared-memory pipe against the FMA pipe; the
 // k loop stays rolled so the body lives in the instruction cache.
 template <int G, int W> struct Tile;
-template <> struct Tile<32, 24> { static constexpr int RG = 8, CG = 4, TM = 3, TN = 6; };
-template <> struct Tile<16, 24> { static constexpr int RG = 4, CG = 4, TM = 6, TN = 6; };
-template <> struct Tile<16, 16> { static constexpr int RG = 4, CG = 4, TM = 4, TN = 4; };
-template <> struct Tile<32, 32> { static constexpr int RG = 8, CG = 4, TM = 4, TN = 8; };
+// PIPE: request the operands of the next k-block before the FMAs of the current one, explicitly.  Pays where
+// registers allow (4x4 tiles: Ant +2.4 %); with the 3x6 tiles at 96 registers it costs 5 % (profiles/r01_sweep_r1i.json)
+template <> struct Tile<32, 24> { static constexpr int RG = 8, CG = 4, TM = 3, TN = 6; static constexpr bool PIPE = false; };
+template <> struct Tile<16, 24> { static constexpr int RG = 4, CG = 4, TM = 6, TN = 6; static constexpr bool PIPE = false; };
+template <> struct Tile<16, 16> { static constexpr int RG = 4, CG = 4, TM = 4, TN = 4; static constexpr bool PIPE = true; };
+template <> struct Tile<32, 32> { static constexpr int RG = 8, CG = 4, TM = 4, TN = 8; static constexpr bool PIPE = false; };
 struct alignas(8) F2 { float x, y; };
 
 template <int TN>
@@ -856,6 +862,42 @@ BXG_HD void tile_matmul(int lane, const float* A, const float* B, int ld, float*
   for (int r = 0; r < T::TM; ++r)
 #pragma unroll
     for (int cc = 0; cc < T::TN / 2; ++cc) acc2[r][cc] = make_float2(0.f, 0.f);
+  if constexpr (T::PIPE) {
+  // explicit software pipeline: the operands of k-block k0 + 4 are requested before the FMAs of block k0
+  F4 a_nxt[T::TM]; float b_nxt[4][T::TN];
+#pragma unroll
+  for (int r = 0; r < T::TM; ++r) a_nxt[r] = ldv4(a0 + r * ld);
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) load_cols<T::TN>(B + kk * ld + cg * T::TN, b_nxt[kk]);
+  BXG_PRAGMA_UNROLL(BXG_PIPE16_UNROLL)
+  for (int k0 = 0; k0 < W; k0 += 4) {
+    F4 a[T::TM]; float bv[4][T::TN];
+#pragma unroll
+    for (int r = 0; r < T::TM; ++r) a[r] = a_nxt[r];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+      for (int cc = 0; cc < T::TN; ++cc) bv[kk][cc] = b_nxt[kk][cc];
+    if (k0 + 4 < W) {
+#pragma unroll
+      for (int r = 0; r < T::TM; ++r) a_nxt[r] = ldv4(a0 + r * ld + k0 + 4);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) load_cols<T::TN>(B + (k0 + 4 + kk) * ld + cg * T::TN, b_nxt[kk]);
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int r = 0; r < T::TM; ++r) {
+        const float ap = kk == 0 ? a[r].x : kk == 1 ? a[r].y : kk == 2 ? a[r].z : a[r].w;
+        const float av = NEG ? -ap : ap;
+        const float2 av2 = make_float2(av, av);
+#pragma unroll
+        for (int cc = 0; cc < T::TN / 2; ++cc)
+          acc2[r][cc] = __ffma2_rn(av2, make_float2(bv[kk][2 * cc], bv[kk][2 * cc + 1]), acc2[r][cc]);
+      }
+    }
+  }
+  } else {
   BXG_PRAGMA_UNROLL(BXG_TILE_UNROLL)
   for (int k0 = 0; k0 < W; k0 += 4) {
     F4 a[T::TM];
@@ -875,6 +917,7 @@ BXG_HD void tile_matmul(int lane, const float* A, const float* B, int ld, float*
           acc2[r][cc] = __ffma2_rn(av2, make_float2(bv[2 * cc], bv[2 * cc + 1]), acc2[r][cc]);
       }
     }
+  }
   }
 #pragma unroll
   for (int r = 0; r < T::TM; ++r)

@@ -9,11 +9,9 @@ def _lib(name):
 
 CONFIGS = [
     ('hum_default', 'humanoid_8192', {}),
-    ('hum_ks', 'humanoid_8192', _lib('ks')),
-    ('hum_ks_u3', 'humanoid_8192', _lib('ks_u3')),
-    ('hum_ks_u6', 'humanoid_8192', _lib('ks_u6')),
-    ('hum512k_default', 'humanoid_512k', {}),
-    ('hum512k_ks', 'humanoid_512k', _lib('ks')),
+    ('ant_default_pipe_u1', 'ant_1m', {}),
+    ('ant_pipe_u2', 'ant_1m', _lib('p16u2')),
+    ('ant_pipe_u4', 'ant_1m', _lib('p16u4')),
 ]
 out_path = sys.argv[1]
 only = sys.argv[2] if len(sys.argv) > 2 else ''
