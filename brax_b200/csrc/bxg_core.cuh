@@ -1215,6 +1215,7 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
         int j = lane + r * G;
         if (j < na) {
           float acc = 0.f;
+#pragma unroll 4
           for (int i = 0; i < na; ++i) acc += A[i * ldc + j] * ress[i];
           gi(lane)[r] = acc;
         }
@@ -1265,6 +1266,7 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
         int j = lane + r * G;
         if (j < na) {
           float acc = 0.f;
+#pragma unroll 4
           for (int i = 0; i < na; ++i) acc += A[i * ldc + j] * ress[i];
           float xn = xni(lane)[r];
           float dlt = fmaxf(xn - acc, 0.f) - xn;
@@ -1285,6 +1287,7 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
   ex.lanes([&](int lane) {
     for (int j = lane; j < nv; j += G) {
       float acc = 0.f;
+#pragma unroll 4
       for (int p = 0; p < na; ++p) acc += J[orig[p] * ldj + j] * xs[p];
       s[D.s_qfc + j] = acc;
     }

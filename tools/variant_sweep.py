@@ -9,9 +9,8 @@ def _lib(name):
 
 CONFIGS = [
     ('hum_default', 'humanoid_8192', {}),
-    ('ant_default_pipe_u1', 'ant_1m', {}),
-    ('ant_pipe_u2', 'ant_1m', _lib('p16u2')),
-    ('ant_pipe_u4', 'ant_1m', _lib('p16u4')),
+    ('hum512k_default', 'humanoid_512k', {}),
+    ('ant_default', 'ant_1m', {}),
 ]
 out_path = sys.argv[1]
 only = sys.argv[2] if len(sys.argv) > 2 else ''
