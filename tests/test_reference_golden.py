@@ -17,14 +17,16 @@ import pytest
 from oracle import oracle as O
 from tests.conftest import ROOT
 
-MODELS = ['ant', 'humanoid', 'halfcheetah', 'hopper', 'triple_pendulum_motor']
+MODELS = ['ant', 'humanoid', 'halfcheetah', 'hopper', 'walker2d', 'triple_pendulum_motor', 'inverted_pendulum',
+          'inverted_double_pendulum', 'reacher', 'swimmer']
+ASSETS = ('ant', 'humanoid', 'halfcheetah', 'hopper', 'walker2d')
 
 
 def _load(name):
   from brax_b200 import envs_assets
   from brax_b200.io import model_json
   g = np.load(os.path.join(ROOT, 'tests', 'golden', f'ref_{name}.npz'))
-  if name == 'triple_pendulum_motor':
+  if name not in ASSETS:
     return model_json.load(os.path.join(ROOT, 'tests', 'golden', f'{name}.json')), g
   return envs_assets.load(name), g
 
@@ -59,7 +61,7 @@ def test_every_step_is_a_one_step_map_of_the_reference_state(name):
     for f in O.STATE_FIELDS:
       _close(st[f], g[f'step{k}_{f}'].reshape(st[f].shape), f'{name} step {k} {f}', rtol=1e-8, atol=1e-8)
     active += int((g[f'step{k}_con_diag'] != 0).sum())
-  if name != 'triple_pendulum_motor':
+  if name in ASSETS:
     assert active > 0      # contact / limit rows were exercised
 
 

@@ -26,6 +26,9 @@ FIXTURES = ['triple_pendulum', 'single_pendulum_motor', 'single_pendulum_positio
             'single_pendulum_velocity', 'single_pendulum_position_frclimit',
             'double_pendulum', 'single_pendulum', 'triple_pendulum_motor']
 
+# further reference env models used only as parity fixtures (slide joints, 2-dof links, no contacts)
+ENV_FIXTURES = ['inverted_pendulum', 'inverted_double_pendulum', 'reacher', 'swimmer']
+
 if __name__ == '__main__':
   for name, path in ASSETS.items():
     out = os.path.join(ROOT, 'brax_b200', 'assets', f'{name}.json')
@@ -34,4 +37,8 @@ if __name__ == '__main__':
   for name in FIXTURES:
     out = os.path.join(ROOT, 'tests', 'golden', f'{name}.json')
     model_json.save(mjcf.load(f'{REF}/test_data/{name}.xml'), out)
+    print('wrote', out)
+  for name in ENV_FIXTURES:
+    out = os.path.join(ROOT, 'tests', 'golden', f'{name}.json')
+    model_json.save(mjcf.load(f'{REF}/envs/assets/{name}.xml'), out)
     print('wrote', out)

@@ -95,7 +95,8 @@ LEAVES = {   # our flat State field -> accessor on the reference State
 
 # model -> (envs, steps, how far to drop the root towards the floor so that contacts are active)
 CASES = {'ant': (3, 6, 0.0), 'humanoid': (2, 6, 0.0), 'halfcheetah': (2, 5, 0.35), 'hopper': (2, 5, 0.04),
-         'triple_pendulum_motor': (2, 4, 0.0)}
+         'walker2d': (2, 5, 0.05), 'triple_pendulum_motor': (2, 4, 0.0), 'inverted_pendulum': (2, 4, 0.0),
+         'inverted_double_pendulum': (2, 4, 0.0), 'reacher': (2, 4, 0.0), 'swimmer': (2, 4, 0.0)}
 
 
 def inputs(s, name, n, steps, drop, seed=0):
