@@ -44,15 +44,51 @@ def peaks():
 
 
 class ClockSampler:
-  """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+  """Samples SM clocks / throttle reasons of one GPU during the timed region: NVML in a thread
+  (every 5 ms, no start-up latency), nvidia-smi as a fallback."""
   Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
        'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
   def __init__(self, gpu_index):
-    self.gpu, self.rows, self.proc = gpu_index, [], None
+    self.gpu, self.rows, self.proc, self.nvml = gpu_index, [], None, None
+    self.sm, self.reasons, self.max_mhz, self._stop = [], set(), None, False
+
+  def _nvml_loop(self):
+    n = self.nvml
+    names = {getattr(n, 'nvmlClocksEventReasonHwSlowdown', 0x8): 'hw_slowdown',
+             getattr(n, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40): 'hw_thermal_slowdown',
+             getattr(n, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20): 'sw_thermal_slowdown',
+             getattr(n, 'nvmlClocksEventReasonSwPowerCap', 0x4): 'sw_power_cap'}
+    get_reasons = getattr(n, 'nvmlDeviceGetCurrentClocksEventReasons', None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+    while not self._stop:
+      try:
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+        bits = int(get_reasons(self.h))
+        for bit, nme in names.items():
+          if bits & bit:
+            self.reasons.add(nme)
+      except Exception:
+        pass
+      time.sleep(0.005)
 
   def start(self):
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+      vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+      idx = self.gpu
+      if vis and all(t.strip().isdigit() for t in vis.split(',')):
+        idx = int(vis.split(',')[self.gpu])
+      self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+      self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+      self.nvml = pynvml
+      self.t = threading.Thread(target=self._nvml_loop, daemon=True)
+      self.t.start()
+      return
+    except Exception:
+      self.nvml = None
     try:
       self.proc = subprocess.Popen(
           ['nvidia-smi', '-i', str(self.gpu), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '20'],
@@ -67,6 +103,12 @@ class ClockSampler:
       self.rows.append([c.strip() for c in line.split(',')])
 
   def stop(self):
+    if self.nvml is not None:
+      self._stop = True
+      self.t.join(timeout=1)
+      sm = sorted(self.sm)
+      return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': self.max_mhz, 'samples': len(sm),
+              'reasons': sorted(self.reasons), 'source': 'nvml'}
     if self.proc is None:
       return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
     time.sleep(0.15)
@@ -87,7 +129,7 @@ class ClockSampler:
         pass
     sm.sort()
     return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-            'samples': len(sm), 'reasons': sorted(reasons)}
+            'samples': len(sm), 'reasons': sorted(reasons), 'source': 'nvidia-smi'}
 
 
 def cpu_port_throughput(model, n_frames, seconds_target=12.0, seed=0):
