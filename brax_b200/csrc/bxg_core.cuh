@@ -825,6 +825,7 @@ template <> struct Tile<32, 24> { static constexpr int RG = 8, CG = 4, TM = 3, T
 template <> struct Tile<16, 24> { static constexpr int RG = 4, CG = 4, TM = 6, TN = 6; static constexpr bool PIPE = false; };
 template <> struct Tile<16, 16> { static constexpr int RG = 4, CG = 4, TM = 4, TN = 4; static constexpr bool PIPE = true; };
 template <> struct Tile<32, 32> { static constexpr int RG = 8, CG = 4, TM = 4, TN = 8; static constexpr bool PIPE = false; };
+template <> struct Tile<32, 16> { static constexpr int RG = 8, CG = 4, TM = 2, TN = 4; static constexpr bool PIPE = true; };
 struct alignas(8) F2 { float x, y; };
 
 template <int TN>
@@ -1083,13 +1084,22 @@ BXG_HD float row_dot_n(const float* a, const float* v, int chunks) {
   return acc;
 }
 // index of the n-th (0-based) set bit of m
-BXG_HD int nth_set_bit(uint32_t m, int n) {
-  for (int k = 0; k < n; ++k) m &= m - 1u;
+BXG_HD int nth_set_bit(uint64_t m, int n) {
+  for (int k = 0; k < n; ++k) m &= m - 1ull;
 #if defined(__CUDA_ARCH__)
-  return __ffs((int)m) - 1;
+  return __ffsll((long long)m) - 1;
 #else
-  return __builtin_ffs((int)m) - 1;
+  return __builtin_ffsll((long long)m) - 1;
 #endif
+}
+// dot of a row of A kept in shared memory (128-bit loads of the lane's own row) with a vector
+BXG_HD float smem_row_dot(const float* arow_sm, const float* v, int chunks) {
+  float acc = 0.f;
+  for (int cc = 0; cc < chunks; ++cc) {
+    F4 a = ldv4(arow_sm + 4 * cc), b = ldv4(v + 4 * cc);
+    acc += a.x * b.x; acc += a.y * b.y; acc += a.z * b.z; acc += a.w * b.w;
+  }
+  return acc;
 }
 
 // constraint.force on the ACTIVE rows only.  Rows the jacobian masked out
@@ -1101,32 +1111,35 @@ BXG_HD int nth_set_bit(uint32_t m, int n) {
 // row by row against the active rows of J (no transposed copy), the row of A then
 // stays in registers for FISTA + backtracking line search as in
 // jaxopt.ProjectedGradient (see oracle/bxg_oracle.c).  VC4 = nvw/4, NC4 = ncw/4.
+// Wide variants (more than 56 row registers per lane) read their row of A from shared
+// memory instead (AREG false).
 template <class X, int VC4, int NC4, int R>
 BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
   constexpr int VW = 4 * VC4, CW = 4 * NC4, G = X::G;
+  constexpr bool AREG = R * CW <= 56;
   const Dims& D = *c.D; float* s = c.s;
   const int nv = D.nv, nc = D.nc, ldv = D.nvp, ldj = D.jld, ldc = D.ncp;
   const float* J = s + D.s_J; const float* Mi = s + D.s_Minv;
   float* A = s + D.s_A;
   float* xs = s + D.s_px; float* ys = s + D.s_py; float* ress = s + D.s_pres; float* xns = s + D.s_pxn;
   int* orig = reinterpret_cast<int*>(s + D.s_pg);   // compact row -> row of J
-  typename X::template LaneVec<R * CW> arow;
+  typename X::template LaneVec<AREG ? R * CW : 1> arow;
   typename X::template LaneVec<R> bi, xi, yi, gi, xni, resi;
   typename X::LaneF p0, p1, p2;
   // ---- active set ---------------------------------------------------------
-  uint32_t am = 0;
+  uint64_t am = 0;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     ex.lanes([&](int lane) {
       int i = lane + r * G;
       p0(lane) = i < nc ? s[D.s_rowact + i] : 0.f;   // set by constraint.jacobian (load_env for the incoming state)
     });
-    am |= ex.ballot(p0) << (r * G);
+    am |= (uint64_t)ex.ballot(p0) << (r * G);
   }
 #if defined(__CUDA_ARCH__)
-  const int na = __popc(am);
+  const int na = __popcll(am);
 #else
-  const int na = __builtin_popcount(am);
+  const int na = __builtin_popcountll(am);
 #endif
   if (na == 0) {   // nothing active: the solver would return x = 0 after one trivial iteration
     ex.lanes([&](int lane) { for (int d = lane; d < nv; d += G) s[D.s_qfc + d] = 0.f; });
@@ -1147,9 +1160,11 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       int p = lane + r * G;
-      float* ar = arow(lane) + r * CW;
+      float* ar = arow(lane) + (AREG ? r * CW : 0);
+      if constexpr (AREG) {
 #pragma unroll
-      for (int j = 0; j < CW; ++j) ar[j] = 0.f;
+        for (int j = 0; j < CW; ++j) ar[j] = 0.f;
+      }
       bi(lane)[r] = 0.f;
       if (p < na) {
         const int i = orig[p];
@@ -1182,9 +1197,11 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
           }
           stv4(arow_sm + 4 * qc, F4{a4[0], a4[1], a4[2], a4[3]});
         }
+        if constexpr (AREG) {
 #pragma unroll
-        for (int cc = 0; cc < NC4; ++cc) {
-          if (cc < nch) { F4 v = ldv4(arow_sm + 4 * cc); ar[4 * cc] = v.x; ar[4 * cc + 1] = v.y; ar[4 * cc + 2] = v.z; ar[4 * cc + 3] = v.w; }
+          for (int cc = 0; cc < NC4; ++cc) {
+            if (cc < nch) { F4 v = ldv4(arow_sm + 4 * cc); ar[4 * cc] = v.x; ar[4 * cc + 1] = v.y; ar[4 * cc + 2] = v.z; ar[4 * cc + 3] = v.w; }
+          }
         }
       }
       xi(lane)[r] = 0.f; yi(lane)[r] = 0.f; gi(lane)[r] = 0.f; xni(lane)[r] = 0.f; resi(lane)[r] = 0.f;
@@ -1201,7 +1218,7 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
       for (int r = 0; r < R; ++r) {
         int p = lane + r * G;
         if (p < na) {
-          float rv = row_dot_n<NC4>(arow(lane) + r * CW, ys, nch) + bi(lane)[r];
+          float rv = (AREG ? row_dot_n<NC4>(arow(lane) + (AREG ? r * CW : 0), ys, nch) : smem_row_dot(A + p * ldc, ys, nch)) + bi(lane)[r];
           ress[p] = rv;
           f += 0.5f * (rv * rv);
         }
@@ -1236,7 +1253,7 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
         for (int r = 0; r < R; ++r) {
           int p = lane + r * G;
           if (p < na) {
-            float rv = row_dot_n<NC4>(arow(lane) + r * CW, xns, nch) + bi(lane)[r];
+            float rv = (AREG ? row_dot_n<NC4>(arow(lane) + (AREG ? r * CW : 0), xns, nch) : smem_row_dot(A + p * ldc, xns, nch)) + bi(lane)[r];
             resi(lane)[r] = rv;
             float dlt = xni(lane)[r] - yi(lane)[r];
             a0 += dlt * dlt; a1 += dlt * gi(lane)[r]; a2 += 0.5f * (rv * rv);

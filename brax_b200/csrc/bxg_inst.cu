@@ -4,7 +4,7 @@
 #include "bxg_kernels.cuh"
 
 #ifndef BXG_VARIANT
-#error "compile with -DBXG_VARIANT=0..4"
+#error "compile with -DBXG_VARIANT=0..5"
 #endif
 
 namespace {
@@ -16,6 +16,8 @@ using Cfg = bxg::KernelCfg<32, 6, 7>;
 using Cfg = bxg::KernelCfg<32, 8, 8>;
 #elif BXG_VARIANT == 4
 using Cfg = bxg::KernelCfg<16, 6, 7>;
+#elif BXG_VARIANT == 5
+using Cfg = bxg::KernelCfg<32, 4, 16>;
 #else
 using Cfg = bxg::KernelCfg<32, 0, 0>;
 #endif

@@ -78,14 +78,16 @@ inline int row_stride(int w) { int c = w / 4; return 4 * (c | 1); }
 // Kernel variants that are compiled (bxg_kernels.cu).  A model takes the first
 // variant it fits; the last one is the generic any-size kernel.
 struct Variant { int G, VC4, NC4, max_links, max_nv, max_nc; };
-constexpr int kNumVariants = 4;     // auto-selected; ids past it are reachable only by forcing them
-constexpr int kNumVariantsAll = 5;
+constexpr int kNumVariantsAll = 6;
+// order in which a model is offered to the variants (first fit); 3 is the generic kernel, 4 is forced only
+constexpr int kAutoOrder[] = {0, 1, 2, 5, 3};
 inline Variant variant(int id) {
   switch (id) {
     case 0: return {16, 4, 6, 16, 16, 24};   // Ant class: half-warp per env
     case 1: return {32, 6, 7, 32, 24, 28};   // Humanoid class: warp per env
     case 2: return {32, 8, 8, 32, 32, 32};
     case 4: return {16, 6, 7, 16, 24, 28};   // Humanoid class on a half-warp (6x6 tiles); forced only
+    case 5: return {32, 4, 16, 32, 16, 64};  // few dofs, many constraint rows (Walker2d, HalfCheetah): rows of A stay in shared memory
     default: return {32, 0, 0, 32, 64, 64};  // generic
   }
 }
@@ -138,13 +140,18 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
   d.nc = 4 * m.ncon + d.nlim;
   if (d.nc > 64) return "more than 64 constraint rows not supported";
   int vid = force_variant;
-  if (vid < 0) for (vid = 0; vid < kNumVariants - 1; ++vid) if (variant_fits(variant(vid), L, m.nv, d.nc)) break;
+  if (vid < 0) {
+    for (int k : kAutoOrder) { vid = k; if (variant_fits(variant(k), L, m.nv, d.nc)) break; }
+  }
   if (vid >= kNumVariantsAll || !variant_fits(variant(vid), L, m.nv, d.nc)) return "model does not fit the requested kernel variant";
   out->variant_id = vid;
   const Variant var = variant(vid);
   d.nvw = var.VC4 ? 4 * var.VC4 : (m.nv + 3) & ~3;
   d.ncw = var.NC4 ? 4 * var.NC4 : ((d.nc > 0 ? d.nc : 1) + 3) & ~3;
   d.nvp = mat_stride(var, d.nvw); d.jld = d.nvw; d.ncp = d.ncw;
+  // wide variants keep the rows of A in shared memory only (bxg_core.cuh con_force_rows AREG): their stride
+  // follows the model, not the compiled width
+  if (var.NC4 > 0 && ((4 * var.NC4 + var.G - 1) / var.G) * 4 * var.NC4 > 56) d.ncp = ((d.nc > 0 ? d.nc : 1) + 3) & ~3;
   d.max_depth = 0;
   for (int l = 0; l < L; ++l) d.max_depth = depth[l] > d.max_depth ? depth[l] : d.max_depth;
   d.solver_iterations = m.solver_iterations; d.solver_maxls = m.solver_maxls;

@@ -24,7 +24,7 @@ def build(force=False):
 class Sim:
   def __init__(self, sys, variant=-1, reverse=False, minv_mode=native.MINV_NEWTON_SCHULZ, generic=False):
     """variant: -1 auto, 0 = (G16, nv<=16, nc<=24), 1 = (G32, nv<=24, nc<=28),
-    2 = (G32, nv<=32, nc<=32), 3 = generic kernel."""
+    2 = (G32, nv<=32, nc<=32), 3 = generic kernel, 4 = (G16, nv<=24, nc<=28), 5 = (G32, nv<=16, nc<=64)."""
     build()
     self.lib = ctypes.CDLL(_SO)
     self.sys = sys
