@@ -299,6 +299,32 @@ def test_full_size_properties_humanoid_8192():
   assert torch.equal(half.q, st.q[n // 2:])
 
 
+def test_full_size_properties_ant_1m():
+  """BASELINE configs[2] size (1,048,576 Ant envs on one GPU): size-independent properties."""
+  from brax_b200 import workloads
+  from brax_b200.generalized import pipeline
+  n = 1 << 20
+  torch, dev, sys_, q, qd = _inputs('ant', n)
+  st = pipeline.init(sys_, q, qd)
+  for k in range(2):
+    st = pipeline.step(sys_, st, workloads.action('ant', 0, n, 0, k, dev), n_frames=5)
+  assert torch.isfinite(st.q).all() and torch.isfinite(st.qd).all() and torch.isfinite(st.x.pos).all()
+  assert (st.q[:, 3:7].norm(dim=-1) - 1).abs().max() < 1e-5
+  assert torch.equal(st.mass_mx, st.mass_mx.transpose(1, 2))
+  inactive = st.con_diag == 0
+  assert (st.con_aref[inactive] == 0).all()
+  # the same global env ids in a small batch (another launch shape, another pass structure): same bits
+  lo, m = 777_001, 4099
+  part = pipeline.init(sys_, q[lo:lo + m].contiguous(), qd[lo:lo + m].contiguous())
+  for k in range(2):
+    part = pipeline.step(sys_, part, workloads.action('ant', lo, m, 0, k, dev), n_frames=5)
+  assert torch.equal(part.q, st.q[lo:lo + m]) and torch.equal(part.qd, st.qd[lo:lo + m])
+  # determinism: the same launch twice gives the same bits
+  again = pipeline.step(sys_, part, workloads.action('ant', lo, m, 0, 7, dev), n_frames=5)
+  again2 = pipeline.step(sys_, part, workloads.action('ant', lo, m, 0, 7, dev), n_frames=5)
+  assert torch.equal(again.q, again2.q)
+
+
 @pytest.mark.parametrize('n_legs', [3, 5, 7])
 def test_other_kernel_variants_on_gpu(n_legs):
   """Synthetic multi-leg models reach the kernel variants Ant / Humanoid do not
