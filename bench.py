@@ -243,7 +243,7 @@ def main():
   hbm_peak, peak_src = peaks()
   flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-  def measure(workload, steps, warmup, with_clocks):
+  def measure(workload, steps, warmup, with_clocks, minv=minv):
     model, n_env = WORKLOADS[workload]
     if args.envs:
       n_env = args.envs
@@ -366,14 +366,17 @@ def main():
   if not args.no_extra and world == 1:
     extra = []
     del r['state'], r['spare']
-    for wl, st_ in (('ant_1m', 5),):
-      if wl == args.workload:
+    # the other headline configuration, and the exact-inverse mode (north_star's per-env Cholesky solve: NOT
+    # the reference's Newton-Schulz numerics) on the default workload
+    for wl, st_, mv in (('ant_1m', 5, minv), (args.workload, 10, native.MINV_CHOLESKY)):
+      if wl == args.workload and mv == minv:
         continue
       try:
         torch.cuda.empty_cache()
-        x = measure(wl, st_, 3, with_clocks=False)
+        x = measure(wl, st_, 3, with_clocks=False, minv=mv)
         ab = workloads.ALGO_BYTES[x['model']] * x['n_env'] / (x['kern_avg_ms'] * 1e-3) / 1e9
-        extra.append({'workload': wl, 'value': x['value'], 'unit': 'env-steps/s', 'ms_per_step': x['ms_per_step'],
+        extra.append({'workload': wl, 'minv': 'cholesky' if mv == native.MINV_CHOLESKY else 'newton_schulz',
+                      'value': x['value'], 'unit': 'env-steps/s', 'ms_per_step': x['ms_per_step'],
                       'steps': st_, 'roofline_frac_hbm': ab / hbm_peak})
         del x
       except Exception as ex:  # report, do not hide

@@ -30,6 +30,14 @@ extern "C" {
 const void* bxg_step_kernel_v0(); const void* bxg_step_kernel_v1(); const void* bxg_step_kernel_v2(); const void* bxg_step_kernel_v3(); const void* bxg_step_kernel_v4(); const void* bxg_step_kernel_v5();
 const void* bxg_init_kernel_v0(); const void* bxg_init_kernel_v1(); const void* bxg_init_kernel_v2(); const void* bxg_init_kernel_v3(); const void* bxg_init_kernel_v4(); const void* bxg_init_kernel_v5();
 }
+extern "C" {
+const void* bxg_step_chol_kernel_v0(); const void* bxg_step_chol_kernel_v1(); const void* bxg_step_chol_kernel_v2();
+const void* bxg_step_chol_kernel_v3(); const void* bxg_step_chol_kernel_v4(); const void* bxg_step_chol_kernel_v5();
+}
+static const void* step_chol_kernel_of(int v) {
+  switch (v) { case 0: return bxg_step_chol_kernel_v0(); case 1: return bxg_step_chol_kernel_v1(); case 2: return bxg_step_chol_kernel_v2();
+               case 4: return bxg_step_chol_kernel_v4(); case 5: return bxg_step_chol_kernel_v5(); default: return bxg_step_chol_kernel_v3(); }
+}
 static const void* step_kernel_of(int v) {
   switch (v) { case 0: return bxg_step_kernel_v0(); case 1: return bxg_step_kernel_v1(); case 2: return bxg_step_kernel_v2(); case 4: return bxg_step_kernel_v4(); case 5: return bxg_step_kernel_v5(); default: return bxg_step_kernel_v3(); }
 }
@@ -125,7 +133,7 @@ int bxg_model_create(const BxgModelDesc* desc, int device, BxgModel** out) {
     return cleanup(cuda_fail(ce, "cudaMemcpy(model)"));
   // the attribute is per function (shared by every model of this variant): always
   // raise it to the device maximum, never to this model's own size
-  const void* ks = step_kernel_of(m->pm.variant_id);
+  const void* ks = m->pm.d.minv_mode == BXG_MINV_CHOLESKY ? step_chol_kernel_of(m->pm.variant_id) : step_kernel_of(m->pm.variant_id);
   const void* ki = init_kernel_of(m->pm.variant_id);
   // (dynamic + the kernel's few bytes of static shared memory must fit the opt-in limit)
   for (const void* k : {ks, ki}) {
@@ -225,7 +233,7 @@ int bxg_step(const BxgModel* m, int64_t n_env, int32_t n_frames, const BxgState*
   BxgEnvSpec env{}; BxgEnvIO eio{}; BxgState first{};
   void* args[] = {(void*)&m->pm.d, (void*)&m->d_blob, (void*)in, (void*)&act, (void*)out, (void*)&n_env, (void*)&nf, (void*)&fl, (void*)&dg,
                   (void*)&env, (void*)&eio, (void*)&first};
-  BXG_CUDA(cudaLaunchKernel(step_kernel_of(m->pm.variant_id), dim3(ls.grid), dim3(ls.threads), args, ls.smem, st));
+  BXG_CUDA(cudaLaunchKernel(m->pm.d.minv_mode == BXG_MINV_CHOLESKY ? step_chol_kernel_of(m->pm.variant_id) : step_kernel_of(m->pm.variant_id), dim3(ls.grid), dim3(ls.threads), args, ls.smem, st));
   g_launches.fetch_add(1);
   BXG_CUDA(cudaGetLastError());
   return BXG_OK;
@@ -276,7 +284,7 @@ int bxg_env_step(const BxgModel* m, const BxgEnvSpec* spec, int64_t n_env, int32
   if (io->first_state) first = *io->first_state;
   void* args[] = {(void*)&m->pm.d, (void*)&m->d_blob, (void*)in, (void*)&action, (void*)out, (void*)&n_env, (void*)&nf, (void*)&fl, (void*)&dg,
                   (void*)&env, (void*)&eio, (void*)&first};
-  BXG_CUDA(cudaLaunchKernel(step_kernel_of(m->pm.variant_id), dim3(ls.grid), dim3(ls.threads), args, ls.smem, st));
+  BXG_CUDA(cudaLaunchKernel(m->pm.d.minv_mode == BXG_MINV_CHOLESKY ? step_chol_kernel_of(m->pm.variant_id) : step_kernel_of(m->pm.variant_id), dim3(ls.grid), dim3(ls.threads), args, ls.smem, st));
   g_launches.fetch_add(1);
   BXG_CUDA(cudaGetLastError());
   return BXG_OK;

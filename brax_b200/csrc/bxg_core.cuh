@@ -386,6 +386,72 @@ BXG_HD void spd_inverse(X& ex, const Ctx& c, const float* src, float* dst, float
   });
 }
 
+// SPD inverse for the specialised variants: same arithmetic, in the same order, as
+// spd_inverse above, restructured for the lane group.  Factorisation: lane i keeps row i of
+// L in registers; per column j every lane reads row j of L (complete by then) with
+// broadcast 128-bit loads.  L is stored together with its transpose (Lm[j][i] = Lm[i][j]),
+// so that the back substitution reads rows too.  Solve: lane c owns column c of the
+// inverse in registers.  W = nvw.
+template <class X, int W>
+BXG_HD void spd_inverse_rows(X& ex, const Ctx& c, const float* src, float* dst, float* Lm) {
+  const Dims& D = *c.D;
+  const int n = D.nv, ld = D.nvp;
+  typename X::template LaneVec<W> lrow;
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+    if (j < n) {
+      ex.lanes([&](int i) {
+        float lj[W > 1 ? W : 1];
+#pragma unroll
+        for (int k4 = 0; k4 < j; k4 += 4) { F4 t = ldv4(Lm + j * ld + k4); lj[k4] = t.x; if (k4 + 1 < W) lj[k4 + 1] = t.y; if (k4 + 2 < W) lj[k4 + 2] = t.z; if (k4 + 3 < W) lj[k4 + 3] = t.w; }
+        float sd = src[j * ld + j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) sd -= lj[k] * lj[k];
+        const float dg = sqrtf(sd);
+        if (i == j) {
+          lrow(i)[j] = dg; Lm[j * ld + j] = dg;
+        } else if (i > j && i < n) {
+          float tt = src[i * ld + j];
+#pragma unroll
+          for (int k = 0; k < j; ++k) tt -= lrow(i)[k] * lj[k];
+          const float v = tt / dg;
+          lrow(i)[j] = v; Lm[i * ld + j] = v; Lm[j * ld + i] = v;
+        }
+      });
+    }
+  }
+  ex.lanes([&](int col) {
+    if (col >= n) return;
+    float y[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      if (i < n) {
+        float li[W];
+#pragma unroll
+        for (int k4 = 0; k4 <= i; k4 += 4) { F4 t = ldv4(Lm + i * ld + k4); li[k4] = t.x; if (k4 + 1 < W) li[k4 + 1] = t.y; if (k4 + 2 < W) li[k4 + 2] = t.z; if (k4 + 3 < W) li[k4 + 3] = t.w; }
+        float tt = i == col ? 1.f : 0.f;
+#pragma unroll
+        for (int k = 0; k < i; ++k) tt -= li[k] * y[k];
+        y[i] = tt / li[i];
+      }
+    }
+#pragma unroll
+    for (int i = W - 1; i >= 0; --i) {
+      if (i < n) {
+        float li[W];
+#pragma unroll
+        for (int k4 = (i / 4) * 4; k4 < W; k4 += 4) { F4 t = ldv4(Lm + i * ld + k4); li[k4] = t.x; if (k4 + 1 < W) li[k4 + 1] = t.y; if (k4 + 2 < W) li[k4 + 2] = t.z; if (k4 + 3 < W) li[k4 + 3] = t.w; }
+        float tt = y[i];
+#pragma unroll
+        for (int k = i + 1; k < W; ++k) if (k < n) tt -= li[k] * y[k];
+        y[i] = tt / li[i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i) if (i < n) dst[i * ld + col] = y[i];
+  });
+}
+
 // ------------------------------------------------------ integrator.integrate
 template <class X>
 BXG_HD void integrate(X& ex, const Ctx& c) {
@@ -1427,22 +1493,34 @@ BXG_HD void con_jacobian(X& ex, const Ctx& c) {
 }
 
 // ------------------------------------------------------------------ pipeline
-template <class X, class Cfg>
-BXG_HD void update_position_terms(X& ex, const Ctx& c, Stats* st, bool exact_inverse, bool in_step) {
+// INV selects, at compile time, how mass_mx_inv is produced, so that each kernel carries
+// only one of the two code paths:
+//   0  the reference's Newton-Schulz iteration (or its exact solve when matrix_inv_iterations == 0)
+//   1  exact SPD inverse by Cholesky (pipeline.init; BXG_MINV_CHOLESKY steps)
+template <class X, class Cfg, int INV>
+BXG_HD void update_position_terms(X& ex, const Ctx& c, Stats* st, bool in_step) {
   const int sl = in_step ? c.D->sync_level : 0;
   kinematics(ex, c);
   transform_com(ex, c);
   if (sl & 8) ex.cta_sync();
   mass_matrix(ex, c);
   if (sl & 16) ex.cta_sync();
-  if (exact_inverse) spd_inverse(ex, c, c.s + c.D->s_M, c.s + c.D->s_Minv, c.s + c.D->s_scr, nullptr, 0.f);
-  else minv_newton_schulz<X, Cfg>(ex, c, st);
+  if constexpr (INV == 1) {
+    bool done = false;
+    if constexpr (Cfg::VC4 > 0 && 4 * Cfg::VC4 <= X::G) {   // one lane per row / column
+      if (!Cfg::GENERIC_TOO || !c.D->force_generic) { spd_inverse_rows<X, 4 * Cfg::VC4>(ex, c, c.s + c.D->s_M, c.s + c.D->s_Minv, c.s + c.D->s_scr); done = true; }
+    }
+    if (!done) spd_inverse(ex, c, c.s + c.D->s_M, c.s + c.D->s_Minv, c.s + c.D->s_scr, nullptr, 0.f);
+  } else {
+    if (c.D->ns_iters == 0) spd_inverse(ex, c, c.s + c.D->s_M, c.s + c.D->s_Minv, c.s + c.D->s_scr, nullptr, 0.f);
+    else minv_newton_schulz<X, Cfg>(ex, c, st);
+  }
   if (sl & 2) ex.cta_sync();
   con_jacobian(ex, c);
 }
 
 // pipeline.step (pipeline.py:78-94)
-template <class X, class Cfg>
+template <class X, class Cfg, int INV>
 BXG_HD void substep(X& ex, const Ctx& c, Stats* st) {
   // CTA-wide phase alignment keeps the warps of a CTA on the same straight-line
   // code (instruction-cache locality); sync_level trades that against barrier waits
@@ -1453,7 +1531,7 @@ BXG_HD void substep(X& ex, const Ctx& c, Stats* st) {
   con_force<X, Cfg>(ex, c, st);
   if (sl & 1) ex.cta_sync();
   integrate(ex, c);
-  update_position_terms<X, Cfg>(ex, c, st, c.D->ns_iters == 0 || c.D->minv_mode == BXG_MINV_CHOLESKY, true);
+  update_position_terms<X, Cfg, INV>(ex, c, st, true);
 }
 
 // pipeline.init (pipeline.py:51-61); q, qd already in the slab
@@ -1464,7 +1542,7 @@ BXG_HD void init_env(X& ex, const Ctx& c, Stats* st) {
     for (int i = lane; i < D.nv; i += X::G) { s[D.s_qfs + i] = 0.f; s[D.s_qfc + i] = 0.f; s[D.s_qdd + i] = 0.f; }
     for (int i = lane; i < (D.nc > 0 ? D.nc : 1) * D.jld; i += X::G) s[D.s_J + i] = 0.f;
   });
-  update_position_terms<X, Cfg>(ex, c, st, true, false);
+  update_position_terms<X, Cfg, 1>(ex, c, st, false);
 }
 
 // Zeroes every region whose padding the register-row kernels rely on (rows and

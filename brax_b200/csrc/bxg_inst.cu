@@ -25,5 +25,7 @@ using Cfg = bxg::KernelCfg<32, 0, 0>;
 
 #define BXG_CAT2(a, b) a##b
 #define BXG_CAT(a, b) BXG_CAT2(a, b)
-extern "C" const void* BXG_CAT(bxg_step_kernel_v, BXG_VARIANT)() { return (const void*)bxg::step_kernel<Cfg>; }
+// two step kernels per variant: Newton-Schulz (the reference's matrix_inv) and exact Cholesky inverse
+extern "C" const void* BXG_CAT(bxg_step_kernel_v, BXG_VARIANT)() { return (const void*)bxg::step_kernel<Cfg, 0>; }
+extern "C" const void* BXG_CAT(bxg_step_chol_kernel_v, BXG_VARIANT)() { return (const void*)bxg::step_kernel<Cfg, 1>; }
 extern "C" const void* BXG_CAT(bxg_init_kernel_v, BXG_VARIANT)() { return (const void*)bxg::init_kernel<Cfg>; }

@@ -105,7 +105,7 @@ __device__ __forceinline__ void stage_model(const Dims& D, const uint32_t* __res
   __syncthreads();
 }
 
-template <class Cfg>
+template <class Cfg, int INV>
 __global__ void __launch_bounds__(Cfg::MAX_THREADS)
 step_kernel(const Dims D, const uint32_t* __restrict__ model, const BxgState in, const float* __restrict__ act,
             const BxgState out, int64_t n_env, int n_frames, int flags, const BxgDiag diag,
@@ -132,7 +132,7 @@ step_kernel(const Dims D, const uint32_t* __restrict__ model, const BxgState in,
     prepare_env(ex, c);
     load_env(ex, c, in, act, e);
     if (env.kind) env_prologue(ex, c, env, in, e);
-    for (int f = 0; f < n_frames; ++f) substep<DevExec<G>, Cfg>(ex, c, &st);
+    for (int f = 0; f < n_frames; ++f) substep<DevExec<G>, Cfg, INV>(ex, c, &st);
     bool done = false;
     if (env.kind) env_epilogue(ex, c, env, eio, e, valid, &done);
     if (valid) {

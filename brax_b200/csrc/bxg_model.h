@@ -278,7 +278,8 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
   d.s_cdofd_ang = take1(nvv * 3); d.s_cdofd_vel = take1(nvv * 3);
   d.s_diag = take1(ncz); d.s_aref = take1(ncz);
   d.s_qfs = take(d.nvw);
-  const bool shared_slots = var.VC4 > 0 && m.matrix_inv_iterations > 0 && m.minv_mode == BXG_MINV_NEWTON_SCHULZ;
+  // (the Cholesky mode shares them too: its factor lives in the Newton-Schulz buffer's slot)
+  const bool shared_slots = var.VC4 > 0 && m.matrix_inv_iterations > 0;
   // union of phase-local temporaries: kinematics / RNE / com temps, composite
   // inertias (CRBA) and the constraint-solver vectors never live at the same time.
   // tau (actuator.to_tau) lives from the start of dynamics to qf_smooth and, for the

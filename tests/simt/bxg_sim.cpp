@@ -92,7 +92,10 @@ int run(const BxgModelDesc* desc, int vid, int mode, bool init, int64_t n_env, i
     } else {
       bxg::load_env(ex, c, *in, act, e);
       if (env) bxg::env_prologue(ex, c, *env, *in, e);
-      for (int f = 0; f < n_frames; ++f) bxg::substep<HostExec<G>, Cfg>(ex, c, &st);
+      for (int f = 0; f < n_frames; ++f) {
+        if (pm.d.minv_mode == BXG_MINV_CHOLESKY) bxg::substep<HostExec<G>, Cfg, 1>(ex, c, &st);
+        else bxg::substep<HostExec<G>, Cfg, 0>(ex, c, &st);
+      }
       bool done = false;
       if (env) bxg::env_epilogue(ex, c, *env, *eio, e, true, &done);
       if (done && eio && eio->first_state) bxg::store_first_state(ex, c, *out, *eio->first_state, e);
