@@ -3,14 +3,14 @@ float32 oracle vs the float64 oracle on identical inputs.  Trajectories of a
 contact-rich articulated system decorrelate, so besides the
 per-env agreement over time this records ENSEMBLE statistics, which must agree
 between implementations however long the rollout is.
-  python tools/parity_rollout.py [ant|humanoid] [n_env] [n_steps] -> JSON on stdout"""
+  python tests/rollout_report.py [ant|humanoid] [n_env] [n_steps] -> JSON on stdout"""
 import json
 import os
 import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # repo root
 import torch  # noqa: E402
 from brax_b200 import workloads  # noqa: E402
 from brax_b200.generalized import pipeline  # noqa: E402

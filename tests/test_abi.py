@@ -65,3 +65,22 @@ def test_desc_struct_matches_header_layout(ant, humanoid):
   for s in (ant, humanoid):
     d, _ = native.make_desc(s)
     assert d.nv == s.nv and d.ncon == len(s.contact_pairs().geom1)
+
+
+def test_only_test_infrastructure_touches_the_oracle():
+  """oracle/ is test infrastructure: nothing under brax_b200/ or tools/ may import it (only tests/,
+  __graft_entry__.smoke() / build() and bench.py's CPU legs do)."""
+  import re
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  pat = re.compile(r'^\s*(from\s+oracle\b|import\s+oracle\b)', re.M)
+  offenders = []
+  for top in ('brax_b200', 'tools'):
+    for dirpath, _, files in os.walk(os.path.join(root, top)):
+      for f in files:
+        if f.endswith(('.py', '.cu', '.cuh', '.h')):
+          path = os.path.join(dirpath, f)
+          text = open(path, errors='ignore').read()
+          includes_oracle = any('oracle' in l for l in text.split('\n') if l.lstrip().startswith('#include'))
+          if (f.endswith('.py') and pat.search(text)) or includes_oracle:
+            offenders.append(os.path.relpath(path, root))
+  assert not offenders, offenders
