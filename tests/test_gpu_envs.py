@@ -85,6 +85,22 @@ def test_auto_reset_on_gpu():
   assert (st.info['steps'] == 1).all() and (st.done == 0).all()
 
 
+def test_training_wrap_mirrors_the_reference_entry_point():
+  """envs.get_environment + wrappers.training.wrap (reference envs/__init__.py:51-107) give the same
+  fused env as envs.create."""
+  import torch
+  from brax_b200 import envs
+  from brax_b200.envs.wrappers import training
+  n = 16
+  a = envs.create('ant', episode_length=3, auto_reset=True, batch_size=n)
+  b = training.wrap(envs.get_environment('ant', batch_size=n), episode_length=3)
+  sa, sb = a.reset(5), b.reset(5)
+  act = torch.zeros((n, 8), device=sa.obs.device)
+  for _ in range(4):
+    sa, sb = a.step(sa, act), b.step(sb, act)
+  assert torch.equal(sa.obs, sb.obs) and torch.equal(sa.done, sb.done) and torch.equal(sa.info['steps'], sb.info['steps'])
+
+
 def test_env_step_equals_pipeline_step_plus_obs():
   """The fused env step leaves exactly the pipeline state pipeline.step produces."""
   import torch
