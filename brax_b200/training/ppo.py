@@ -132,7 +132,7 @@ def train(env_name: str = 'ant', num_envs: int = 2048, episode_length: int = 100
     for p in agent.parameters():
       dist.broadcast(p.data, 0)
   opt = torch.optim.Adam(agent.parameters(), lr=learning_rate, capturable=use_cuda_graph)
-  sgd_graph = static_mb = static_loss = None
+  sgd_graph = step_graph = static_mb = static_loss = static_flat = None
   state = env.reset(seed)
   # one training step consumes batch_size * num_minibatches trajectories of unroll_length steps
   traj_per_step = batch_size * num_minibatches
@@ -158,7 +158,7 @@ def train(env_name: str = 'ant', num_envs: int = 2048, episode_length: int = 100
     return st, ep_rew, fsum, fnum, (torch.stack(o), torch.stack(lg), torch.stack(pr), torch.stack(rw), torch.stack(dn), torch.stack(tr))
 
   rollout_graph = None
-  if use_cuda_graph and world == 1:
+  if use_cuda_graph:   # (no collective inside the rollout: graphs work the same on every rank)
     # static state buffers: the graph reads them, steps, and writes the final state back in place
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
@@ -199,28 +199,56 @@ def train(env_name: str = 'ant', num_envs: int = 2048, episode_length: int = 100
     agent.update_normalization(td['obs'][:-1])
     n_traj = td['reward'].shape[1]
     mb_size = n_traj // num_minibatches
-    if use_cuda_graph and sgd_graph is None and world == 1:
+    if use_cuda_graph and sgd_graph is None:
       # capture one minibatch update (loss, backward, Adam) into a CUDA graph: the
-      # learner is launch-bound (small MLPs), replay removes the per-op overhead
+      # learner is launch-bound (small MLPs), replay removes the per-op overhead.  With several
+      # ranks the update is two graphs around one NCCL all-reduce of the flattened gradient
+      # (lax.pmean(grad) of the reference): [loss, backward, flatten] -> all_reduce -> [unflatten, Adam].
       static_mb = {k: torch.empty_like(v[:, :mb_size]) for k, v in td.items()}
       static_loss = torch.zeros((), device=device)
+      params = list(agent.parameters())
+      static_flat = torch.zeros(sum(p.numel() for p in params), device=device)
+
+      def scatter_grads():
+        off = 0
+        for p in params:
+          p.grad.copy_(static_flat[off:off + p.numel()].view_as(p)); off += p.numel()
+
       side = torch.cuda.Stream()
       side.wait_stream(torch.cuda.current_stream())
       with torch.cuda.stream(side):
         for _ in range(3):   # warm-up outside capture (allocations, cuBLAS handles)
           for k, v in td.items():
             static_mb[k].copy_(v[:, :mb_size])
-          opt.zero_grad(set_to_none=True)
+          opt.zero_grad(set_to_none=False)
           agent.loss(static_mb).backward()
+          if world > 1:
+            torch.cat([p.grad.reshape(-1) for p in params], out=static_flat)
+            dist.all_reduce(static_flat); static_flat /= world
+            scatter_grads()
           opt.step()
       torch.cuda.current_stream().wait_stream(side)
+      torch.cuda.synchronize()
       sgd_graph = torch.cuda.CUDAGraph()
-      opt.zero_grad(set_to_none=True)
+      opt.zero_grad(set_to_none=world == 1)     # one rank: gradients are (re)created inside the graph
       with torch.cuda.graph(sgd_graph):
+        if world > 1:                            # several ranks: persistent gradients, zeroed in the graph
+          for p in params:
+            p.grad.zero_()
         l_ = agent.loss(static_mb)
         l_.backward()
-        opt.step()
         static_loss.copy_(l_.detach())
+        if world > 1:
+          torch.cat([p.grad.reshape(-1) for p in params], out=static_flat)
+        else:
+          opt.step()
+      step_graph = None
+      if world > 1:
+        step_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(step_graph):
+          static_flat.div_(world)
+          scatter_grads()
+          opt.step()
     for _ in range(num_update_epochs):
       perm = torch.randperm(n_traj, device=device)
       for mb in perm[:mb_size * num_minibatches].view(num_minibatches, mb_size):
@@ -228,6 +256,9 @@ def train(env_name: str = 'ant', num_envs: int = 2048, episode_length: int = 100
           for k, v in td.items():
             torch.index_select(v, 1, mb, out=static_mb[k])
           sgd_graph.replay()
+          if world > 1:
+            dist.all_reduce(static_flat)
+            step_graph.replay()
           loss = static_loss
           continue
         loss = agent.loss({k: v[:, mb] for k, v in td.items()})
