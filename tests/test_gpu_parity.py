@@ -419,7 +419,7 @@ def test_capsule_models_single_substep_map(model, drop):
   _report(f'capsule_{model}', {'envs_inside_tolerance': inside / total, 'active_contacts': active, 'substeps': steps, 'n_env': n})
 
 
-@pytest.mark.parametrize('name', ['ant', 'humanoid', 'halfcheetah', 'hopper'])
+@pytest.mark.parametrize('name', ['ant', 'humanoid', 'halfcheetah', 'hopper', 'walker2d', 'two_trees'])
 def test_cuda_path_against_reference_source_golden(name):
   """The CUDA path directly against golden vectors produced by the reference's own source
   (tests/golden/ref_*.npz, tools/gen_reference_golden.py: brax.generalized.pipeline run
@@ -431,7 +431,12 @@ def test_cuda_path_against_reference_source_golden(name):
   torch = _torch()
   dev = torch.device('cuda', 0)
   g = np.load(os.path.join(ROOT, 'tests', 'golden', f'ref_{name}.npz'))
-  sys_ = envs_assets.load(name)
+  if name == 'two_trees':      # synthetic: two kinematic trees (several free roots) in one System
+    from brax_b200.io import mjcf
+    from tests.synthetic_models import TWO_TREES_XML
+    sys_ = mjcf.loads(TWO_TREES_XML)
+  else:
+    sys_ = envs_assets.load(name)
   f32 = np.float32
   got = _flat_np(pipeline.init(sys_, torch.as_tensor(g['q0'].astype(f32), device=dev), torch.as_tensor(g['qd0'].astype(f32), device=dev)))
   for k in O.STATE_FIELDS:

@@ -18,7 +18,7 @@ from oracle import oracle as O
 from tests.conftest import ROOT
 
 MODELS = ['ant', 'humanoid', 'halfcheetah', 'hopper', 'walker2d', 'triple_pendulum_motor', 'inverted_pendulum',
-          'inverted_double_pendulum', 'reacher', 'swimmer']
+          'inverted_double_pendulum', 'reacher', 'swimmer', 'two_trees']
 ASSETS = ('ant', 'humanoid', 'halfcheetah', 'hopper', 'walker2d')
 
 
@@ -26,6 +26,10 @@ def _load(name):
   from brax_b200 import envs_assets
   from brax_b200.io import model_json
   g = np.load(os.path.join(ROOT, 'tests', 'golden', f'ref_{name}.npz'))
+  if name == 'two_trees':
+    from brax_b200.io import mjcf
+    from tests.synthetic_models import TWO_TREES_XML
+    return mjcf.loads(TWO_TREES_XML), g
   if name not in ASSETS:
     return model_json.load(os.path.join(ROOT, 'tests', 'golden', f'{name}.json')), g
   return envs_assets.load(name), g
@@ -61,7 +65,7 @@ def test_every_step_is_a_one_step_map_of_the_reference_state(name):
     for f in O.STATE_FIELDS:
       _close(st[f], g[f'step{k}_{f}'].reshape(st[f].shape), f'{name} step {k} {f}', rtol=1e-8, atol=1e-8)
     active += int((g[f'step{k}_con_diag'] != 0).sum())
-  if name in ASSETS:
+  if name in ASSETS or name == 'two_trees':
     assert active > 0      # contact / limit rows were exercised
 
 
@@ -130,7 +134,7 @@ def test_env_oracle_matches_reference_envs_and_wrappers(name):
   assert saw_done and saw_trunc
 
 
-@pytest.mark.parametrize('name', ['ant', 'humanoid', 'halfcheetah', 'hopper'])
+@pytest.mark.parametrize('name', ['ant', 'humanoid', 'halfcheetah', 'hopper', 'two_trees'])
 def test_kernel_source_against_reference_source_golden(name):
   """brax_b200/csrc/bxg_core.cuh (float32, through the host lane emulator) directly against the
   reference-source golden (float64): one-step maps inside the stated 1e-4 / 1e-5 tolerance."""

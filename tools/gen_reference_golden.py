@@ -96,7 +96,7 @@ LEAVES = {   # our flat State field -> accessor on the reference State
 # model -> (envs, steps, how far to drop the root towards the floor so that contacts are active)
 CASES = {'ant': (3, 6, 0.0), 'humanoid': (2, 6, 0.0), 'halfcheetah': (2, 5, 0.35), 'hopper': (2, 5, 0.04),
          'walker2d': (2, 5, 0.05), 'triple_pendulum_motor': (2, 4, 0.0), 'inverted_pendulum': (2, 4, 0.0),
-         'inverted_double_pendulum': (2, 4, 0.0), 'reacher': (2, 4, 0.0), 'swimmer': (2, 4, 0.0)}
+         'inverted_double_pendulum': (2, 4, 0.0), 'reacher': (2, 4, 0.0), 'swimmer': (2, 4, 0.0), 'two_trees': (2, 6, 0.0)}
 
 
 def inputs(s, name, n, steps, drop, seed=0):
@@ -107,6 +107,8 @@ def inputs(s, name, n, steps, drop, seed=0):
   if name == 'humanoid':
     q = np.asarray(s.init_q, np.float64)[None] + rng.uniform(-0.01, 0.01, (n, s.nq))
     q[:, 2] = 1.29 + 0.02 * rng.uniform(size=n)       # feet touching (foot spheres reach z = 1.4 - 1.3)
+  if name == 'two_trees':      # both spheres start slightly inside the floor; keep the root quaternions near unit
+    q[:, 2] = 0.24; q[:, 9] = 0.29
   if drop:
     q[:, 1] -= drop
   qd = 0.1 * rng.standard_normal((n, s.nv))
@@ -119,6 +121,10 @@ def inputs(s, name, n, steps, drop, seed=0):
 def load(name):
   if name in ('ant', 'humanoid', 'halfcheetah', 'hopper', 'walker2d'):
     return envs_assets.load(name)
+  if name == 'two_trees':      # our own synthetic model (tests/synthetic_models.py): several free roots
+    from brax_b200.io import mjcf
+    from tests.synthetic_models import TWO_TREES_XML
+    return mjcf.loads(TWO_TREES_XML)
   from brax_b200.io import model_json
   return model_json.load(os.path.join(ROOT, 'tests', 'golden', f'{name}.json'))
 
