@@ -353,7 +353,7 @@ def main():
       'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
                    'traffic': traffic, 'peak_source': peak_src,
                    'algorithmic_bytes_per_env_step': workloads.ALGO_BYTES[model],
-                   'note': 'the step is bound on-chip (Newton-Schulz products: a balanced FMA / shared-memory / issue loop; then '
+                   'note': 'the step is bound on-chip (Newton-Schulz products: issue / register-bandwidth bound at 53% of FMA peak; then '
                            'latency), not by HBM (SURVEY 8d); see profiles/ for pipe utilisation'},
       'fp32': {'achieved': fp32_tflops, 'peak': FP32_PEAK_TFLOPS, 'unit': 'TFLOP/s', 'frac': fp32_tflops / FP32_PEAK_TFLOPS,
                'flops_per_env_step': flops_per_env_step,
