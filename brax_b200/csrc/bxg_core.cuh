@@ -133,28 +133,26 @@ struct KernelCfg {
   static constexpr bool GENERIC_TOO = GENERIC_TOO_ || VC4_ == 0;
 };
 
-// constraint._imp_aref (brax/generalized/constraint.py:29-65)
+// constraint._imp_aref (brax/generalized/constraint.py:29-65); prm as packed by pack_impedance
+// (bxg_model.h): the row-constant quotients are precomputed on the host
 BXG_HD_NOINLINE void imp_aref(const float* prm, float pos, float vel, float* imp_out, float* aref_out) {
-  float timeconst = prm[0], dampratio = prm[1], dmin = prm[2], dmax = prm[3], width = prm[4], mid = prm[5], power = prm[6];
+  const float dmin = prm[0], dmax = prm[1], width = prm[2], mid = prm[3], power = prm[4];
+  const float inv_a = prm[5], inv_b = prm[6], b = prm[7], k = prm[8];
   float imp_x = fabsf(pos) / width;
   float imp_a, imp_b;
   if (power == 2.f) {
-    // x^2 and mid^1 are exact operations: no transcendental needed (MuJoCo's
-    // default solimp power; XLA's simplifier lowers pow(x, 2) to x * x as well)
-    imp_a = (1.0f / mid) * (imp_x * imp_x);
-    imp_b = 1.f - (1.0f / (1.f - mid)) * ((1.f - imp_x) * (1.f - imp_x));
+    // x^2 is an exact operation: no transcendental needed (MuJoCo's default solimp power;
+    // XLA's simplifier lowers pow(x, 2) to x * x as well)
+    imp_a = inv_a * (imp_x * imp_x);
+    imp_b = 1.f - inv_b * ((1.f - imp_x) * (1.f - imp_x));
   } else {
-    imp_a = (1.0f / powf(mid, power - 1.f)) * powf(imp_x, power);
-    imp_b = 1.f - (1.0f / powf(1.f - mid, power - 1.f)) * powf(1.f - imp_x, power);
+    imp_a = inv_a * powf(imp_x, power);
+    imp_b = 1.f - inv_b * powf(1.f - imp_x, power);
   }
   float imp_y = imp_x < mid ? imp_a : imp_b;
   float imp = dmin + imp_y * (dmax - dmin);
   imp = fmaxf(dmin, fminf(imp, dmax));
   if (imp_x > 1.0f) imp = dmax;
-  float b = 2.f / (dmax * timeconst);
-  float k = 1.f / (dmax * dmax * timeconst * timeconst * dampratio * dampratio);
-  if (dampratio <= 0.f) b = -dampratio / dmax;
-  if (timeconst <= 0.f) k = -timeconst / (dmax * dmax);
   *imp_out = imp;
   *aref_out = -b * vel - k * imp * pos;
 }
@@ -1463,7 +1461,7 @@ BXG_HD void con_jacobian(X& ex, const Ctx& c) {
         float vel = 0.f;
         for (int d = 0; d < nv; ++d) vel += J[row * nvp + d] * s[D.s_qd + d];
         float imp;
-        imp_aref(mf + D.m_con_sp + 7 * cc, dist, vel, &imp, &aref);
+        imp_aref(mf + D.m_con_sp + kImpStride * cc, dist, vel, &imp, &aref);
         float tw = mf[D.m_link_invw + lb];  // link_a is the world: contributes 0
         diag = (tw + mu * mu * tw) * (2.f * mu * mu * (1.f - imp) / (imp + 1e-8f));
       }
@@ -1482,7 +1480,7 @@ BXG_HD void con_jacobian(X& ex, const Ctx& c) {
         float diag = 0.f, aref = 0.f;
         if (active) {
           float imp;
-          imp_aref(mf + D.m_dof_sp + 7 * d, pos, side * s[D.s_qd + d], &imp, &aref);
+          imp_aref(mf + D.m_dof_sp + kImpStride * d, pos, side * s[D.s_qd + d], &imp, &aref);
           diag = mf[D.m_dof_invw + d] * (1.f - imp) / (imp + 1e-8f);
         }
         J[row * nvp + d] = side;

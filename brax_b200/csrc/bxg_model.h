@@ -6,6 +6,7 @@
 // masks and dof->link maps are derived once per model here, so the kernel never
 // walks the tree by pointer chasing.
 #pragma once
+#include <math.h>
 #include <stdint.h>
 
 #include <string>
@@ -40,7 +41,7 @@ struct Dims {
   int m_tf_pos, m_tf_rot, m_joint_pos, m_in_pos, m_in_rot, m_in_i, m_in_mass, m_link_invw;
   int m_dof_ang, m_dof_vel, m_arm, m_stiff, m_damp, m_lim_lo, m_lim_hi, m_dof_invw, m_dof_sp;
   int m_act_qid, m_act_did, m_act_gain, m_act_gear, m_act_clo, m_act_chi, m_act_flo, m_act_fhi, m_act_bq, m_act_bqd;
-  int m_con_lb, m_con_ppos, m_con_frame, m_con_spos, m_con_rad, m_con_mu, m_con_sp;  // sp: [ncon,7]
+  int m_con_lb, m_con_ppos, m_con_frame, m_con_spos, m_con_rad, m_con_mu, m_con_sp;  // sp: [ncon, kImpStride]
   int m_con_kind, m_con_gquat, m_con_half;   // plane-capsule end points: kind 1, geom quaternion [ncon,4], signed half length
   int m_con_anc_lo, m_con_anc_hi;        // [ncon] bitmask of dofs that move link_b
   int model_words;
@@ -109,6 +110,24 @@ struct PackedModel {
   int variant_id = -1;
   std::vector<uint32_t> blob;
 };
+
+// Impedance parameters of one constraint row as the kernel reads them: from
+// [timeconst, dampratio, dmin, dmax, width, mid, power] (solref ++ solimp) to
+// [dmin, dmax, width, mid, power, 1/mid^(p-1), 1/(1-mid)^(p-1), b, k].  The last four are the
+// row-constant subexpressions of constraint._imp_aref (constraint.py:40-61), evaluated here in
+// float with the same operations the oracle applies, instead of four divisions per call.
+constexpr int kImpStride = 9;
+inline void pack_impedance(const float* p7, float* o9) {
+  const float tc = p7[0], dr = p7[1], dmin = p7[2], dmax = p7[3], width = p7[4], mid = p7[5], power = p7[6];
+  o9[0] = dmin; o9[1] = dmax; o9[2] = width; o9[3] = mid; o9[4] = power;
+  o9[5] = 1.0f / powf(mid, power - 1.f);
+  o9[6] = 1.0f / powf(1.f - mid, power - 1.f);
+  float b = 2.f / (dmax * tc);
+  float k = 1.f / (dmax * dmax * tc * tc * dr * dr);
+  if (dr <= 0.f) b = -dr / dmax;
+  if (tc <= 0.f) k = -tc / (dmax * dmax);
+  o9[7] = b; o9[8] = k;
+}
 
 // Returns empty string on success, else an error message.
 inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force_variant = -1) {
@@ -217,7 +236,11 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
   d.m_damp = put_f(m.dof_damping, m.nv);
   d.m_lim_lo = put_f(m.has_limit ? m.dof_limit_lo : nullptr, m.nv);
   d.m_lim_hi = put_f(m.has_limit ? m.dof_limit_hi : nullptr, m.nv);
-  d.m_dof_invw = put_f(m.dof_invweight, m.nv); d.m_dof_sp = put_f(m.dof_solver_params, m.nv * 7);
+  d.m_dof_invw = put_f(m.dof_invweight, m.nv); {
+    std::vector<float> dsp(m.nv * kImpStride, 0.f);
+    for (int i = 0; i < m.nv; ++i) pack_impedance(m.dof_solver_params + 7 * i, dsp.data() + kImpStride * i);
+    d.m_dof_sp = put_f(dsp.data(), m.nv * kImpStride);
+  }
   int nu1 = m.nu > 0 ? m.nu : 0;
   d.m_act_qid = put_ip(m.act_q_id, nu1); d.m_act_did = put_ip(m.act_qd_id, nu1);
   d.m_act_gain = put_f(m.act_gain, nu1); d.m_act_gear = put_f(m.act_gear, nu1);
@@ -237,7 +260,11 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
     sp[c * 7 + 0] = m.con_solref[c * 2]; sp[c * 7 + 1] = m.con_solref[c * 2 + 1];
     for (int k = 0; k < 5; ++k) sp[c * 7 + 2 + k] = m.con_solimp[c * 5 + k];
   }
-  d.m_con_sp = put_f(sp.data(), m.ncon * 7);
+  {
+    std::vector<float> csp(m.ncon * kImpStride + 1, 0.f);
+    for (int c = 0; c < m.ncon; ++c) pack_impedance(sp.data() + 7 * c, csp.data() + kImpStride * c);
+    d.m_con_sp = put_f(csp.data(), m.ncon * kImpStride);
+  }
   {
     std::vector<int> kind(m.ncon > 0 ? m.ncon : 1, 0);
     std::vector<float> gq((m.ncon > 0 ? m.ncon : 1) * 4, 0.f), half(m.ncon > 0 ? m.ncon : 1, 0.f);

@@ -50,26 +50,39 @@ __global__ void __launch_bounds__(608) k_probe(float* out, int reps, int ld) {
   for (int rep = 0; rep < reps; ++rep) {
 #pragma unroll 2
     for (int k0 = 0; k0 < W; k0 += 4) {
-      if (MODE != 2) {
+      if (MODE != 2 && MODE != 5) {
 #pragma unroll
         for (int r = 0; r < TM; ++r) a[r] = ldv4(a0 + r * ld + k0);
       }
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
-        if (MODE != 2) load_cols<TN>(B + (k0 + kk) * ld + cg * TN, bv);
+        if (MODE != 2 && MODE != 5) load_cols<TN>(B + (k0 + kk) * ld + cg * TN, bv);
         if (MODE == 1) {
           chk += bv[0] + bv[2] + bv[4] + (kk == 0 ? a[0].x + a[1].x + a[2].x : 0.f);
         } else {
 #pragma unroll
           for (int r = 0; r < TM; ++r) {
             const float av = kk == 0 ? a[r].x : kk == 1 ? a[r].y : kk == 2 ? a[r].z : a[r].w;
-            if (MODE == 3) {
+            if (MODE == 4 || MODE == 5) {
+              // handled below (column-outer order)
+            } else if (MODE == 3) {
 #pragma unroll
               for (int c = 0; c < TN; ++c) accs[r][c] = fmaf(av, bv[c], accs[r][c]);
             } else {
               const float2 av2 = make_float2(av, av);
 #pragma unroll
               for (int c = 0; c < TN / 2; ++c) acc2[r][c] = __ffma2_rn(av2, make_float2(bv[2 * c], bv[2 * c + 1]), acc2[r][c]);
+            }
+          }
+          if (MODE == 4 || MODE == 5) {   // B pair outer, rows inner: consecutive FFMA2 share the 64-bit operand
+#pragma unroll
+            for (int c = 0; c < TN / 2; ++c) {
+              const float2 b2 = make_float2(bv[2 * c], bv[2 * c + 1]);
+#pragma unroll
+              for (int r = 0; r < TM; ++r) {
+                const float av = kk == 0 ? a[r].x : kk == 1 ? a[r].y : kk == 2 ? a[r].z : a[r].w;
+                acc2[r][c] = __ffma2_rn(make_float2(av, av), b2, acc2[r][c]);
+              }
             }
           }
         }
@@ -117,6 +130,8 @@ int main() {
     probe(k_probe<1>, g, "3x6 loads only");
     probe(k_probe<2>, g, "3x6 FFMA2 only (operands in registers)");
     probe(k_probe<3>, g, "3x6 scalar FFMA + loads");
+    probe(k_probe<4>, g, "3x6 FFMA2 + loads, B-pair-outer order");
+    probe(k_probe<5>, g, "3x6 FFMA2 only, B-pair-outer order");
   }
   return 0;
 }
