@@ -11,8 +11,6 @@ CONFIGS = [   # edit per experiment; alternative builds come from tools/build_al
     ('hum_default', 'humanoid_8192', {}),
     ('hum512k_default', 'humanoid_512k', {}),
     ('ant_default', 'ant_1m', {}),
-    ('hum_no_alignment', 'humanoid_8192', {'BXG_SYNC_LEVEL': '0'}),
-    ('hum_half_warp_variant', 'humanoid_8192', {'BXG_FORCE_VARIANT': '4'}),
 ]
 out_path = sys.argv[1]
 only = sys.argv[2] if len(sys.argv) > 2 else ''
