@@ -239,17 +239,26 @@ int bxg_step(const BxgModel* m, int64_t n_env, int32_t n_frames, const BxgState*
   return BXG_OK;
 }
 
+// what the kernel's env code assumes about the model for each env kind
+static const char* env_spec_error(const BxgModel* m, const BxgEnvSpec* spec) {
+  const bxg::Dims& d = m->pm.d;
+  if (spec->kind < BXG_ENV_ROOT_VELOCITY || spec->kind > BXG_ENV_SWIMMER) return "unknown env kind";
+  if (spec->kind == BXG_ENV_CARTPOLE && d.nq < 2) return "cartpole env kind needs q = [x, angle, ...]";
+  if (spec->kind == BXG_ENV_DOUBLE_CARTPOLE && (d.nv < 3 || spec->tip_link < 0 || spec->tip_link >= d.L)) return "double cartpole env kind needs nv >= 3 and a tip link";
+  if (spec->kind == BXG_ENV_REACHER && (d.nq < 2 || spec->tip_link < 0 || spec->tip_link >= d.L || spec->target_link < 0 || spec->target_link >= d.L)) return "reacher env kind needs a tip link and a target link";
+  if (spec->kind == BXG_ENV_SWIMMER && d.nq < 2) return "swimmer env kind needs q = [x, y, ...]";
+  return nullptr;
+}
+
 int bxg_env_obs_size(const BxgModel* m, const BxgEnvSpec* spec) {
   if (!m || !spec) return -1;
-  const bxg::Dims& d = m->pm.d;
-  int base = (d.nq - spec->obs_skip) + d.nv;
-  return spec->kind == BXG_ENV_COM_VELOCITY ? base + 16 * d.L + d.nv : base;
+  return bxg::env_obs_size(m->pm.d, *spec);
 }
 
 int bxg_env_reset(const BxgModel* m, const BxgEnvSpec* spec, int64_t n_env, const float* q, const float* qd,
                   const BxgState* out, float* obs, void* stream) {
   if (!m || !spec) return fail(BXG_E_INVALID, "null argument");
-  if (spec->kind != BXG_ENV_ROOT_VELOCITY && spec->kind != BXG_ENV_COM_VELOCITY && spec->kind != BXG_ENV_PLANAR) return fail(BXG_E_INVALID, "unknown env kind");
+  if (const char* why = env_spec_error(m, spec)) return fail(BXG_E_INVALID, why);
   if (n_env <= 0) return n_env == 0 ? BXG_OK : fail(BXG_E_INVALID, "n_env < 0");
   if (!q || !qd || !obs || !state_ok(out, m->pm.d.nc)) return fail(BXG_E_INVALID, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -266,7 +275,7 @@ int bxg_env_reset(const BxgModel* m, const BxgEnvSpec* spec, int64_t n_env, cons
 int bxg_env_step(const BxgModel* m, const BxgEnvSpec* spec, int64_t n_env, int32_t n_frames, const BxgState* in,
                  const float* action, const BxgState* out, const BxgEnvIO* io, void* stream) {
   if (!m || !spec || !io) return fail(BXG_E_INVALID, "null argument");
-  if (spec->kind != BXG_ENV_ROOT_VELOCITY && spec->kind != BXG_ENV_COM_VELOCITY && spec->kind != BXG_ENV_PLANAR) return fail(BXG_E_INVALID, "unknown env kind");
+  if (const char* why = env_spec_error(m, spec)) return fail(BXG_E_INVALID, why);
   if (spec->obs_skip < 0 || spec->obs_skip > m->pm.d.nq || !(spec->env_dt > 0.f)) return fail(BXG_E_INVALID, "bad env spec");
   if (spec->kind == BXG_ENV_PLANAR && m->pm.d.nq < 3) return fail(BXG_E_INVALID, "planar env kind needs q = [x, z, angle, ...]");
   if (n_frames < 1) return fail(BXG_E_INVALID, "n_frames < 1");

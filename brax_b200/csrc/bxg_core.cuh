@@ -181,10 +181,58 @@ BXG_HD void actuator_tau(X& ex, const Ctx& c) {
   });
 }
 
+// fluid.force (brax/fluid.py:24-91) projected on the dofs as dynamics._passive does
+// (dynamics.py:198-211).  Lanes <-> links: force of each link's inertia box in the world
+// orientation into s_t_ang / s_t_vel, its lever arm x_i.pos - root_com into s_f_ang; then
+// lanes <-> dofs: sum over the links the dof moves of jac . frc, left in s_qfs for the
+// assembly of qf_smooth.  Runs before the RNE passes, which reuse the same temporaries.
 template <class X>
+BXG_HD void fluid_passive(X& ex, const Ctx& c) {
+  const Dims& D = *c.D; const float* mf = c.mf; const int* mi = c.mi; float* s = c.s;
+  const int L = D.L, nv = D.nv;
+  ex.lanes([&](int lane) {
+    for (int l = lane; l < L; l += X::G) {
+      V3 xi_pos; Q4 xi_rot;
+      tf_do(ld3(s + D.s_x_pos + 3 * l), ld4(s + D.s_x_rot + 4 * l), ld3(mf + D.m_in_pos + 3 * l), ld4(mf + D.m_in_rot + 4 * l), &xi_pos, &xi_rot);
+      V3 off = xi_pos - ld3(s + D.s_root_com + 3 * l);
+      Q4 rinv{xi_rot.w, -xi_rot.x, -xi_rot.y, -xi_rot.z};
+      V3 cda = ld3(s + D.s_cd_ang + 3 * l);
+      V3 ang = rotate(cda, rinv);
+      V3 vel = rotate(ld3(s + D.s_cd_vel + 3 * l) - cross(off, cda), rinv);
+      const float* k = mf + D.m_fluid + kFluidStride * l;
+      V3 fa{k[0] * ang.x + k[5] * fabsf(ang.x) * ang.x / 64.0f, k[0] * ang.y + k[6] * fabsf(ang.y) * ang.y / 64.0f,
+            k[0] * ang.z + k[7] * fabsf(ang.z) * ang.z / 64.0f};
+      V3 fv{k[1] * vel.x + k[2] * fabsf(vel.x) * vel.x, k[1] * vel.y + k[3] * fabsf(vel.y) * vel.y,
+            k[1] * vel.z + k[4] * fabsf(vel.z) * vel.z};
+      st3(s + D.s_t_vel + 3 * l, rotate(fv, xi_rot));
+      st3(s + D.s_t_ang + 3 * l, rotate(fa, xi_rot));
+      st3(s + D.s_f_ang + 3 * l, off);
+    }
+  });
+  ex.lanes([&](int lane) {
+    for (int d = lane; d < nv; d += X::G) {
+      const int dl = mi[D.m_dof_link + d];
+      V3 ca = ld3(s + D.s_cdof_ang + 3 * d), cv = ld3(s + D.s_cdof_vel + 3 * d);
+      float acc = 0.f;
+      for (int l = dl; l < L; ++l) {
+        int p = l;
+        while (p > dl) p = mi[D.m_link_parent + p];   // parents precede their children
+        if (p != dl) continue;
+        V3 jv = cv - cross(ld3(s + D.s_f_ang + 3 * l), ca);
+        acc += dot(jv, ld3(s + D.s_t_vel + 3 * l)) + dot(ca, ld3(s + D.s_t_ang + 3 * l));
+      }
+      s[D.s_qfs + d] = acc;
+    }
+  });
+}
+
+template <class X, class Cfg>
 BXG_HD void dyn_forces(X& ex, const Ctx& c) {
   const Dims& D = *c.D; const float* mf = c.mf; const int* mi = c.mi; float* s = c.s;
   const int L = D.L, nv = D.nv;
+  // fluid models always run on the generic variant (bxg_model.h): the specialised ones carry no fluid code
+  constexpr bool kFluidCode = Cfg::VC4 == 0;
+  if constexpr (kFluidCode) { if (D.fluid) fluid_passive(ex, c); }
   actuator_tau(ex, c);
   // RNE forward scan: cdd, then cfrc_flat (lanes <-> links, one tree level at a time)
   for (int lvl = 0; lvl <= D.max_depth; ++lvl) {
@@ -238,6 +286,7 @@ BXG_HD void dyn_forces(X& ex, const Ctx& c) {
       float qd = s[D.s_qd + d];
       float passive = qi < 0 ? 0.f : -s[D.s_q + qi] * mf[D.m_stiff + d];
       passive = passive - mf[D.m_damp + d] * qd;
+      if constexpr (kFluidCode) { if (D.fluid) passive = passive + s[D.s_qfs + d]; }
       s[D.s_qfs + d] = (passive - bias) + s[D.s_tau + d];
     }
   });
@@ -1524,7 +1573,7 @@ BXG_HD void substep(X& ex, const Ctx& c, Stats* st) {
   // code (instruction-cache locality); sync_level trades that against barrier waits
   const int sl = c.D->sync_level;
   if (sl & 4) ex.cta_sync();
-  dyn_forces(ex, c);
+  dyn_forces<X, Cfg>(ex, c);
   if (sl & 32) ex.cta_sync();
   con_force<X, Cfg>(ex, c, st);
   if (sl & 1) ex.cta_sync();
@@ -1564,9 +1613,15 @@ BXG_HD void prepare_env(X& ex, const Ctx& c) {
 // post-step state is still in the slab.  `before` holds what must be captured
 // from the pre-step state: position of link 0 (Ant) or the centre of mass
 // (Humanoid), stored in s_red[0..2] by env_prologue.
-BXG_HD int env_obs_size(const Dims& D, const BxgEnvSpec& sp) {
-  int base = (D.nq - sp.obs_skip) + D.nv;
-  return sp.kind == BXG_ENV_COM_VELOCITY ? base + 10 * D.L + 6 * D.L + D.nv : base;
+// a point fixed in the frame of a link: x.take(link).do(Transform.create(pos=p)).pos
+BXG_HD V3 env_tip(const Ctx& c, const BxgEnvSpec& sp) {
+  const Dims& D = *c.D; const float* s = c.s;
+  return ld3(s + D.s_x_pos + 3 * sp.tip_link) + rotate(V3{sp.tip_pos[0], sp.tip_pos[1], sp.tip_pos[2]}, ld4(s + D.s_x_rot + 4 * sp.tip_link));
+}
+// math.safe_norm (brax/math.py:308-328)
+BXG_HD float env_safe_norm(V3 v) {
+  bool zero = fabsf(v.x) <= 1e-8f && fabsf(v.y) <= 1e-8f && fabsf(v.z) <= 1e-8f;
+  return zero ? 0.f : sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
 }
 
 // whole-model centre of mass from link poses in s_x_pos / s_x_rot
@@ -1590,8 +1645,8 @@ BXG_HD void env_prologue(X& ex, const Ctx& c, const BxgEnvSpec& sp, const BxgSta
   ex.lanes([&](int lane) {
     for (int i = lane; i < L * 3; i += X::G) s[D.s_x_pos + i] = g.x_pos[e * L * 3 + i];
     for (int i = lane; i < L * 4; i += X::G) s[D.s_x_rot + i] = g.x_rot[e * L * 4 + i];
-    if (sp.kind == BXG_ENV_COM_VELOCITY) {
-      // action = (a + 1) * (hi - lo) * 0.5 + lo   (envs/humanoid.py:260-262)
+    if (sp.kind == BXG_ENV_COM_VELOCITY || sp.kind == BXG_ENV_CARTPOLE) {
+      // action = (a + 1) * (hi - lo) * 0.5 + lo   (envs/humanoid.py:260-262, inverted_pendulum.py:134-137)
       for (int a = lane; a < D.nu; a += X::G) {
         float lo = mf[D.m_act_clo + a], hi = mf[D.m_act_chi + a];
         s[D.s_act + a] = (s[D.s_act + a] + 1.f) * (hi - lo) * 0.5f + lo;
@@ -1599,6 +1654,7 @@ BXG_HD void env_prologue(X& ex, const Ctx& c, const BxgEnvSpec& sp, const BxgSta
     }
   });
   V3 ref = sp.kind == BXG_ENV_COM_VELOCITY ? env_com(c) : ld3(s + D.s_x_pos);
+  if (sp.kind == BXG_ENV_SWIMMER) ref = V3{s[D.s_q], s[D.s_q + 1], 0.f};   // pipeline_state0.q[:2] (envs/swimmer.py:165-167)
   ex.lanes([&](int lane) { if (lane == 0) st3(s + D.s_red, ref); });
 }
 
@@ -1611,7 +1667,28 @@ BXG_HD void env_write_obs(X& ex, const Ctx& c, const BxgEnvSpec& sp, float* o) {
   ex.lanes([&](int lane) {
     const int G = X::G;
     const int np = nq - sp.obs_skip;
-    if (sp.kind == BXG_ENV_PLANAR) {
+    if (sp.kind == BXG_ENV_DOUBLE_CARTPOLE) {
+      // [q[:1], sin(q[1:]), cos(q[1:]), clip(qd, -10, 10)]  (envs/inverted_double_pendulum.py:187-195)
+      const int na = nq - 1;
+      for (int i = lane; i < nq; i += G) {
+        if (i == 0) { o[0] = s[D.s_q]; continue; }
+        float sn, cs; sincosf(s[D.s_q + i], &sn, &cs);
+        o[i] = sn; o[na + i] = cs;
+      }
+      for (int i = lane; i < nv; i += G) o[1 + 2 * na + i] = fmaxf(-10.f, fminf(s[D.s_qd + i], 10.f));
+    } else if (sp.kind == BXG_ENV_REACHER) {
+      // [cos(theta), sin(theta), q[2:], tip_vel[:2], tip_pos - target_pos]  (envs/reacher.py:215-239)
+      if (lane == 0) {
+        for (int i = 0; i < 2; ++i) { float sn, cs; sincosf(s[D.s_q + i], &sn, &cs); o[i] = cs; o[2 + i] = sn; }
+        for (int i = 2; i < nq; ++i) o[2 + i] = s[D.s_q + i];
+        // Transform.create(pos=tip).do(xd.take(tip_link)).vel = vel - tip x ang  (identity rotation, base.py:565-570)
+        V3 tp{sp.tip_pos[0], sp.tip_pos[1], sp.tip_pos[2]};
+        V3 tv = ld3(s + D.s_xd_vel + 3 * sp.tip_link) - cross(tp, ld3(s + D.s_xd_ang + 3 * sp.tip_link));
+        V3 tt = env_tip(c, sp) - ld3(s + D.s_x_pos + 3 * sp.target_link);
+        float* t = o + 2 + nq;
+        t[0] = tv.x; t[1] = tv.y; t[2] = tt.x; t[3] = tt.y; t[4] = tt.z;
+      }
+    } else if (sp.kind == BXG_ENV_PLANAR) {
       // position = q.at[1].set(x.pos[0, 2]); velocity = clip(qd, -10, 10)  (envs/hopper.py:266-276, walker2d.py:263-273)
       for (int i = lane; i < np; i += G) o[i] = sp.obs_skip + i == 1 ? s[D.s_x_pos + 2] : s[D.s_q + sp.obs_skip + i];
       for (int i = lane; i < nv; i += G) o[np + i] = fmaxf(-10.f, fminf(s[D.s_qd + i], 10.f));
@@ -1658,6 +1735,7 @@ BXG_HD void env_epilogue(X& ex, const Ctx& c, const BxgEnvSpec& sp, const BxgEnv
   // ---- reward / done / metrics: every lane redundantly (uniform scalars) ----
   V3 before = ld3(s + D.s_red);
   V3 after = com_kind ? env_com(c) : ld3(s + D.s_x_pos);
+  if (sp.kind == BXG_ENV_SWIMMER) after = V3{s[D.s_q], s[D.s_q + 1], 0.f};   // xy_position = q[:2] (envs/swimmer.py:164)
   V3 vel{(after.x - before.x) / sp.env_dt, (after.y - before.y) / sp.env_dt, (after.z - before.z) / sp.env_dt};
   float forward_reward = sp.forward_reward_weight * vel.x;   // Ant has no weight (envs/ant.py:240): its spec carries 1.0, exact
   float z = s[D.s_x_pos + 2];
@@ -1678,6 +1756,31 @@ BXG_HD void env_epilogue(X& ex, const Ctx& c, const BxgEnvSpec& sp, const BxgEnv
   float ctrl_cost = sp.ctrl_cost_weight * sq;
   float reward = com_kind ? (forward_reward + healthy_reward) - ctrl_cost : ((forward_reward + healthy_reward) - ctrl_cost) - 0.f;
   float done = sp.terminate_when_unhealthy ? 1.f - is_healthy : 0.f;
+  // the small classic-control envs: their own reward / done; metrics (if any) in ms[]
+  const bool simple_kind = sp.kind >= BXG_ENV_CARTPOLE;
+  float ms[BXG_ENV_NUM_METRICS] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (sp.kind == BXG_ENV_CARTPOLE) {
+    // reward = 1.0; done = |obs[1]| > 0.2  (envs/inverted_pendulum.py:141-142)
+    reward = 1.0f; done = fabsf(s[D.s_q + 1]) > sp.healthy_angle_max ? 1.f : 0.f;
+  } else if (sp.kind == BXG_ENV_DOUBLE_CARTPOLE) {
+    // envs/inverted_double_pendulum.py:164-177
+    V3 tip = env_tip(c, sp);
+    const float x = tip.x, y = tip.z, v1 = s[D.s_qd + 1], v2 = s[D.s_qd + 2];
+    float dist_penalty = 0.01f * (x * x) + (y - 2.f) * (y - 2.f);
+    float vel_penalty = 1e-3f * (v1 * v1) + 5e-3f * (v2 * v2);
+    done = y <= sp.healthy_z_min ? 1.f : 0.f;
+    reward = ((1.f - done) * sp.healthy_reward - dist_penalty) - vel_penalty;
+  } else if (sp.kind == BXG_ENV_REACHER) {
+    // reward_dist = -safe_norm(obs[-3:]); reward_ctrl = -sum(action^2)  (envs/reacher.py:203-207)
+    V3 tt = env_tip(c, sp) - ld3(s + D.s_x_pos + 3 * sp.target_link);
+    ms[0] = -env_safe_norm(tt); ms[1] = -sq;
+    reward = ms[0] + ms[1]; done = 0.f;
+  } else if (sp.kind == BXG_ENV_SWIMMER) {
+    // envs/swimmer.py:168-183 (jp.linalg.norm, not safe_norm; 'forward_reward' is never updated)
+    reward = forward_reward - ctrl_cost; done = 0.f;
+    ms[0] = forward_reward; ms[2] = -ctrl_cost; ms[4] = after.x; ms[5] = after.y;
+    ms[6] = sqrtf(after.x * after.x + after.y * after.y); ms[7] = vel.x; ms[8] = vel.y;
+  }
   // EpisodeWrapper (wrappers/training.py:98-135) after AutoResetWrapper's step reset (:141-146)
   float trunc = 0.f;
   if (io.steps && valid) {
@@ -1696,7 +1799,9 @@ BXG_HD void env_epilogue(X& ex, const Ctx& c, const BxgEnvSpec& sp, const BxgEnv
       io.reward[e] = reward; io.done[e] = done;
       float* m = io.metrics + e * BXG_ENV_NUM_METRICS;
       float dist;
-      if (com_kind) {
+      if (simple_kind) {
+        for (int i = 0; i < BXG_ENV_NUM_METRICS; ++i) m[i] = ms[i];
+      } else if (com_kind) {
         dist = sqrtf(after.x * after.x + after.y * after.y + after.z * after.z);
         m[0] = forward_reward; m[1] = forward_reward; m[2] = -ctrl_cost; m[3] = healthy_reward;
         m[4] = after.x; m[5] = after.y; m[6] = dist; m[7] = vel.x; m[8] = vel.y; m[9] = 0.f;
@@ -1756,6 +1861,10 @@ BXG_HD void load_env(X& ex, const Ctx& c, const BxgState& g, const float* act, i
     }
     for (int i = lane; i < L * 9; i += G) s[D.s_cinr_i + i] = g.cinr_i[e * L * 9 + i];
     for (int i = lane; i < L; i += G) s[D.s_cinr_mass + i] = g.cinr_mass[e * L + i];
+    if (D.fluid) {   // fluid.force reads x and root_com of the incoming state (dynamics.py:199-206)
+      for (int i = lane; i < L * 3; i += G) { s[D.s_x_pos + i] = g.x_pos[e * L * 3 + i]; s[D.s_root_com + i] = g.root_com[e * L * 3 + i]; }
+      for (int i = lane; i < L * 4; i += G) s[D.s_x_rot + i] = g.x_rot[e * L * 4 + i];
+    }
     for (int i = lane; i < nv * 3; i += G) {
       s[D.s_cdof_ang + i] = g.cdof_ang[e * nv * 3 + i]; s[D.s_cdof_vel + i] = g.cdof_vel[e * nv * 3 + i];
       s[D.s_cdofd_ang + i] = g.cdofd_ang[e * nv * 3 + i]; s[D.s_cdofd_vel + i] = g.cdofd_vel[e * nv * 3 + i];

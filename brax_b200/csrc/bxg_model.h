@@ -31,6 +31,7 @@ struct Dims {
   int sync_level;     // bit mask of CTA-wide phase alignments per substep: 1 after constraint.force, 2 after
                       // Newton-Schulz, 4 before dynamics, 8 before mass.matrix, 16 before N-S, 32 before constraint.force
   float dt, gx, gy, gz;
+  int fluid;          // sys.enable_fluid: fluid forces in dynamics._passive (generic variant only)
   // ---- model blob ----
   int m_link_parent, m_link_ndof, m_link_qadr, m_link_dadr, m_link_depth, m_link_root;
   int m_child_start, m_child_list;       // CSR, children in DEscending index order
@@ -44,6 +45,7 @@ struct Dims {
   int m_con_lb, m_con_ppos, m_con_frame, m_con_spos, m_con_rad, m_con_mu, m_con_sp;  // sp: [ncon, kImpStride]
   int m_con_kind, m_con_gquat, m_con_half;   // plane-capsule end points: kind 1, geom quaternion [ncon,4], signed half length
   int m_con_anc_lo, m_con_anc_hi;        // [ncon] bitmask of dofs that move link_b
+  int m_fluid;                           // [L, 8] per-link fluid constants (pack_fluid), only when `fluid`
   int model_words;
   // ---- per-env slab ----
   int s_q, s_qd, s_act, s_tau, s_qfs, s_qfc, s_qdd;
@@ -129,6 +131,30 @@ inline void pack_impedance(const float* p7, float* o9) {
   o9[7] = b; o9[8] = k;
 }
 
+// Fluid constants of one link (brax/fluid.py:24-53,73-77), evaluated in float with the same
+// operations the oracle applies: [ang_scale, vel_scale, cv[3], ca[3]] with
+// frc.ang = ang_scale * w + ca * |w| * w / 64,  frc.vel = vel_scale * v + cv * |v| * v
+constexpr int kFluidStride = 8;
+inline void pack_fluid(const float* inertia_i9, float mass, float viscosity, float density, float* o8) {
+  const float dg[3] = {inertia_i9[0], inertia_i9[4], inertia_i9[8]};
+  float box[3];
+  for (int i = 0; i < 3; ++i) {
+    float sum = 0.f;
+    for (int j = 0; j < 3; ++j) sum += dg[j] * (i == j ? -1.f : 1.f);
+    sum = 6.f * (sum > 1e-12f ? sum : 1e-12f);
+    box[i] = sqrtf(sum / mass);
+  }
+  const float pi = 3.14159265358979323846f;
+  const float diam = (box[0] + box[1] + box[2]) / 3.f;
+  o8[0] = -pi * (diam * diam * diam) * viscosity;
+  o8[1] = (float)(-3.0 * 3.14159265358979323846) * diam * viscosity;
+  const float bmv[3] = {box[1] * box[2], box[0] * box[2], box[0] * box[1]};
+  const float p2[3] = {box[0] * box[0], box[1] * box[1], box[2] * box[2]};
+  const float p4[3] = {p2[0] * p2[0], p2[1] * p2[1], p2[2] * p2[2]};
+  const float bma[3] = {box[0] * (p4[1] + p4[2]), box[1] * (p4[0] + p4[2]), box[2] * (p4[0] + p4[1])};
+  for (int i = 0; i < 3; ++i) { o8[2 + i] = -0.5f * density * bmv[i]; o8[5 + i] = -1.0f * density * bma[i]; }
+}
+
 // Returns empty string on success, else an error message.
 inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force_variant = -1) {
   Dims& d = out->d;
@@ -159,6 +185,9 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
   d.nc = 4 * m.ncon + d.nlim;
   if (d.nc > 64) return "more than 64 constraint rows not supported";
   int vid = force_variant;
+  d.fluid = m.enable_fluid ? 1 : 0;
+  if (d.fluid && vid >= 0 && variant(vid).VC4 != 0) return "fluid forces are compiled into the generic kernel variant only";
+  if (d.fluid) vid = 3;   // the specialised variants carry no fluid code: they stay exactly as profiled
   if (vid < 0) {
     for (int k : kAutoOrder) { vid = k; if (variant_fits(variant(k), L, m.nv, d.nc)) break; }
   }
@@ -284,6 +313,12 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
     clo[c] = (int)(uint32_t)(mask & 0xffffffffu); chi[c] = (int)(uint32_t)(mask >> 32);
   }
   d.m_con_anc_lo = put_i(clo); d.m_con_anc_hi = put_i(chi);
+  d.m_fluid = (int)b.size();
+  if (d.fluid) {
+    std::vector<float> fl(L * kFluidStride, 0.f);
+    for (int l = 0; l < L; ++l) pack_fluid(m.inertia_i + 9 * l, m.inertia_mass[l], m.viscosity, m.density, fl.data() + kFluidStride * l);
+    d.m_fluid = put_f(fl.data(), L * kFluidStride);
+  }
   while (b.size() % 4) b.push_back(0);
   d.model_words = (int)b.size();
 
@@ -354,6 +389,19 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
   if (var.G == 16) while (o % 32 != 16) o += 4;
   d.env_words = o;
   return "";
+}
+
+// Length of one observation vector (shared by the kernels and the C ABI).
+#if defined(__CUDACC__)
+#define BXG_MODEL_HD __host__ __device__ inline
+#else
+#define BXG_MODEL_HD inline
+#endif
+BXG_MODEL_HD int env_obs_size(const Dims& D, const BxgEnvSpec& sp) {
+  int base = (D.nq - sp.obs_skip) + D.nv;
+  if (sp.kind == BXG_ENV_DOUBLE_CARTPOLE) return 1 + 2 * (D.nq - 1) + D.nv;   // q[0], sin, cos of q[1:], qd
+  if (sp.kind == BXG_ENV_REACHER) return 4 + (D.nq - 2) + 2 + 3;               // cos, sin of q[:2], q[2:], tip_vel[:2], tip - target
+  return sp.kind == BXG_ENV_COM_VELOCITY ? base + 10 * D.L + 6 * D.L + D.nv : base;
 }
 
 }  // namespace bxg

@@ -33,8 +33,8 @@ def _device_index(t: torch.Tensor) -> int:
 
 def _validate(sys: System) -> None:
   """The subset of `mjcf.validate_model` that applies (io/mjcf.py:236-314)."""
-  if sys.enable_fluid:
-    raise NotImplementedError('fluid forces are not implemented in the B200 step')
+  if sys.enable_fluid and sys.num_links() > 32:
+    raise NotImplementedError('fluid forces run on the generic kernel variant: at most 32 links')
 
 
 def init(

@@ -52,6 +52,7 @@ class ModelDesc(ctypes.Structure):
       ('con_sphere_pos', _pf), ('con_radius', _pf), ('con_friction', _pf),
       ('con_solref', _pf), ('con_solimp', _pf),
       ('con_kind', _pi), ('con_geom_quat', _pf), ('con_half_len', _pf),
+      ('enable_fluid', _i32), ('viscosity', _f32), ('density', _f32),
   ]
 
 
@@ -66,6 +67,10 @@ class DiagC(ctypes.Structure):
 ENV_ROOT_VELOCITY = 1
 ENV_COM_VELOCITY = 2
 ENV_PLANAR = 3
+ENV_CARTPOLE = 4
+ENV_DOUBLE_CARTPOLE = 5
+ENV_REACHER = 6
+ENV_SWIMMER = 7
 ENV_NUM_METRICS = 10
 
 
@@ -75,7 +80,8 @@ class EnvSpecC(ctypes.Structure):
               ('forward_reward_weight', _f32), ('ctrl_cost_weight', _f32), ('healthy_reward', _f32),
               ('healthy_z_min', _f32), ('healthy_z_max', _f32), ('env_dt', _f32),
               ('healthy_angle_min', _f32), ('healthy_angle_max', _f32),
-              ('healthy_state_min', _f32), ('healthy_state_max', _f32)]
+              ('healthy_state_min', _f32), ('healthy_state_max', _f32),
+              ('tip_link', _i32), ('target_link', _i32), ('tip_pos', _f32 * 3)]
 
 
 class EnvIOC(ctypes.Structure):
@@ -105,7 +111,7 @@ def make_desc(sys, minv_mode: int = MINV_NEWTON_SCHULZ) -> Tuple[ModelDesc, list
 
   cp = sys.contact_pairs()
   d = ModelDesc()
-  d.abi_version = 2
+  d.abi_version = 3
   d.num_links, d.nq, d.nv, d.nu = sys.num_links(), sys.nq, sys.nv, sys.nu
   d.ncon = len(cp.geom1)
   d.has_limit = 0 if sys.dof.limit is None else 1
@@ -142,6 +148,8 @@ def make_desc(sys, minv_mode: int = MINV_NEWTON_SCHULZ) -> Tuple[ModelDesc, list
   d.con_sphere_pos = fp(cp.sphere_pos); d.con_radius = fp(cp.radius)
   d.con_friction = fp(cp.friction); d.con_solref = fp(cp.solref); d.con_solimp = fp(cp.solimp)
   d.con_kind = ip(cp.kind); d.con_geom_quat = fp(cp.geom_quat); d.con_half_len = fp(cp.half_len)
+  d.enable_fluid = int(bool(sys.enable_fluid))
+  d.viscosity, d.density = float(np.asarray(sys.viscosity)), float(np.asarray(sys.density))
   return d, keep
 
 
@@ -196,7 +204,7 @@ def lib() -> ctypes.CDLL:
       l.bxg_env_step.argtypes = [ctypes.c_void_p, ctypes.POINTER(EnvSpecC), ctypes.c_int64, ctypes.c_int32,
                                  ctypes.POINTER(StateC), ctypes.c_void_p, ctypes.POINTER(StateC),
                                  ctypes.POINTER(EnvIOC), ctypes.c_void_p]
-      if l.bxg_abi_version() != 2:
+      if l.bxg_abi_version() != 3:
         raise RuntimeError('libbxg.so ABI version mismatch')
       _lib = l
     return _lib

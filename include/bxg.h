@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BXG_ABI_VERSION 2
+#define BXG_ABI_VERSION 3
 
 enum {
   BXG_OK = 0,
@@ -117,6 +117,9 @@ typedef struct BxgModelDesc {
   const int32_t* con_kind;       /* [ncon] BXG_CON_*; NULL = all plane-sphere */
   const float* con_geom_quat;    /* [ncon,4] capsule orientation in link_b frame (kind 1) */
   const float* con_half_len;     /* [ncon] signed half length: end point = centre + axis * half_len (kind 1) */
+  /* fluid forces on the links' inertia boxes (brax/fluid.py:24-91, dynamics.py:198-211) */
+  int32_t enable_fluid;          /* sys.enable_fluid = viscosity > 0 or density > 0 (io/mjcf.py:467) */
+  float viscosity, density;      /* sys.viscosity, sys.density */
 } BxgModelDesc;
 
 /* The generalized State (brax/generalized/base.py:25-92 + brax/base.py:396-412)
@@ -167,9 +170,19 @@ enum {
   BXG_ENV_ROOT_VELOCITY = 1,  /* Ant:      velocity of link 0, obs = [q[skip:], qd]          */
   BXG_ENV_PLANAR = 3,         /* Hopper / Walker2d: velocity of link 0; healthy = z, angle q[2] and state ranges
                                  (strict); obs = [q[skip:] with q[1] := z of link 0, clip(qd, -10, 10)]          */
-  BXG_ENV_COM_VELOCITY = 2    /* Humanoid: velocity of the centre of mass, obs = [q[skip:],
+  BXG_ENV_COM_VELOCITY = 2,   /* Humanoid: velocity of the centre of mass, obs = [q[skip:],
                                  qd, com_inertia, com_velocity, qfrc_actuator]; the action is
                                  rescaled from [-1,1] to the ctrl range first                */
+  BXG_ENV_CARTPOLE = 4,       /* InvertedPendulum (envs/inverted_pendulum.py:131-154): action rescaled to the ctrl
+                                 range; obs = [q, qd]; reward = 1; done = |q[1]| > healthy_angle_max */
+  BXG_ENV_DOUBLE_CARTPOLE = 5,/* InvertedDoublePendulum (envs/inverted_double_pendulum.py:161-195): tip = tip_pos in
+                                 the frame of link tip_link; obs = [q[0], sin(q[1:]), cos(q[1:]), clip(qd, -10, 10)];
+                                 done = tip z <= healthy_z_min; reward = (1 - done) * healthy_reward - penalties */
+  BXG_ENV_REACHER = 6,        /* Reacher (envs/reacher.py:199-239): obs = [cos(q[:2]), sin(q[:2]), q[2:], tip_vel[:2],
+                                 tip - target]; tip on link tip_link, target = position of link target_link;
+                                 reward = -|tip - target| - sum(action^2) */
+  BXG_ENV_SWIMMER = 7         /* Swimmer (envs/swimmer.py:157-194): velocity of q[:2]; obs = [q[skip:], qd];
+                                 reward = forward_reward_weight * vx - ctrl_cost_weight * sum(action^2) */
 };
 #define BXG_ENV_NUM_METRICS 10
 
@@ -185,6 +198,8 @@ typedef struct BxgEnvSpec {
   float env_dt;                      /* sys.opt.timestep * n_frames */
   float healthy_angle_min, healthy_angle_max;   /* BXG_ENV_PLANAR: range of q[2] */
   float healthy_state_min, healthy_state_max;   /* BXG_ENV_PLANAR: range of every entry of [q[2:], qd] */
+  int32_t tip_link, target_link;     /* BXG_ENV_DOUBLE_CARTPOLE / BXG_ENV_REACHER */
+  float tip_pos[3];                  /* tip in the frame of tip_link */
 } BxgEnvSpec;
 
 /* Per-env arrays, device pointers.  metrics order:
@@ -192,7 +207,11 @@ typedef struct BxgEnvSpec {
  *                 y_position, distance_from_origin, x_velocity, y_velocity, forward_reward
  *  PLANAR:        reward_forward, reward_healthy, reward_ctrl, -, x_position, -, -, x_velocity, -, -
  *  COM_VELOCITY:  forward_reward, reward_linvel, reward_quadctrl, reward_alive, x_position,
- *                 y_position, distance_from_origin, x_velocity, y_velocity, (unused)        */
+ *                 y_position, distance_from_origin, x_velocity, y_velocity, (unused)
+ *  CARTPOLE, DOUBLE_CARTPOLE: none
+ *  REACHER:       reward_dist, reward_ctrl
+ *  SWIMMER:       reward_fwd, -, reward_ctrl, -, x_position, y_position, distance_from_origin,
+ *                 x_velocity, y_velocity, forward_reward (always 0: swimmer.py never updates it)  */
 typedef struct BxgEnvIO {
   float* obs;                 /* [n, obs_size] out */
   float* reward;              /* [n] out */

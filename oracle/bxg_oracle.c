@@ -93,6 +93,8 @@ typedef struct {
   int32_t con_kind[MAXCON];          /* 0 plane-sphere, 1 one end of a plane-capsule pair */
   real con_geom_quat[MAXCON][4];     /* capsule orientation in link_b frame */
   real con_half_len[MAXCON];         /* signed: end point = centre + axis * half_len */
+  int32_t enable_fluid, pad2;        /* sys.enable_fluid (io/mjcf.py:467) */
+  real viscosity, density;           /* sys.viscosity, sys.density */
 } OrcModel;
 
 /* per-environment working state (reference generalized/base.py:25-92) */
@@ -724,10 +726,63 @@ static void to_tau(const OrcModel* m, const Env* e, const real* act, real* tau) 
   }
 }
 
+/* fluid.force (brax/fluid.py:24-91) as dynamics._passive uses it (dynamics.py:198-211): the
+ * viscous + inertial drag of each link's inertia box, projected on the dofs through the point
+ * jacobian of the link's centre of mass.  out[d] = sum over links of jac[l][d] . frc[l] */
+static void fluid_passive(const OrcModel* m, const Env* e, real* out) {
+  int L = m->num_links, nv = m->nv;
+  const real pi = (real)3.14159265358979323846;
+  for (int d = 0; d < nv; d++) out[d] = 0;
+  for (int l = 0; l < L; l++) {
+    /* x_i = x.do(inertia.transform); offset = x_i.pos - root_com; xd_i = Transform(offset, x_i.rot).do(cd) */
+    real xi_pos[3], xi_rot[4], off[3], rinv[4], c[3], t[3], ang[3], vel[3];
+    tf_do_tf(e->x_pos[l], e->x_rot[l], m->inertia_pos[l], m->inertia_rot[l], xi_pos, xi_rot);
+    for (int i = 0; i < 3; i++) off[i] = xi_pos[i] - e->root_com[l][i];
+    rinv[0] = xi_rot[0]; rinv[1] = -xi_rot[1]; rinv[2] = -xi_rot[2]; rinv[3] = -xi_rot[3];
+    rotate(e->cd_ang[l], rinv, ang);
+    cross3(off, e->cd_ang[l], c);
+    for (int i = 0; i < 3; i++) t[i] = e->cd_vel[l][i] - c[i];
+    rotate(t, rinv, vel);
+    /* box from the diagonal inertia (fluid.py:73-77) */
+    const real* I = m->inertia_i[l];
+    real dg[3] = {I[0], I[4], I[8]}, box[3];
+    for (int i = 0; i < 3; i++) {
+      real sum = 0;
+      for (int j = 0; j < 3; j++) sum += dg[j] * (i == j ? (real)-1 : (real)1);
+      sum = (real)6 * r_max(sum, (real)1e-12);
+      box[i] = r_sqrt(sum / m->inertia_mass[l]);
+    }
+    /* _box_viscosity + _box_density (fluid.py:24-53) */
+    real diam = (box[0] + box[1] + box[2]) / (real)3;
+    real ang_scale = -pi * (diam * diam * diam) * m->viscosity, vel_scale = (real)(-3.0 * 3.14159265358979323846) * diam * m->viscosity;
+    real bmv[3] = {box[1] * box[2], box[0] * box[2], box[0] * box[1]};
+    real p2[3] = {box[0] * box[0], box[1] * box[1], box[2] * box[2]};
+    real p4[3] = {p2[0] * p2[0], p2[1] * p2[1], p2[2] * p2[2]};   /* x ** 4 by repeated squaring */
+    real bma[3] = {box[0] * (p4[1] + p4[2]), box[1] * (p4[0] + p4[2]), box[2] * (p4[0] + p4[1])};
+    real fa[3], fv[3], wa[3], wv[3];
+    for (int i = 0; i < 3; i++) {
+      real dv = (real)-0.5 * m->density * bmv[i] * r_abs(vel[i]) * vel[i];
+      real da = (real)-1.0 * m->density * bma[i] * r_abs(ang[i]) * ang[i] / (real)64.0;
+      fa[i] = ang_scale * ang[i] + da; fv[i] = vel_scale * vel[i] + dv;
+    }
+    /* back to the world orientation: Transform.create(rot=x_i.rot).do(Force), base.py:581-585 */
+    rotate(fv, xi_rot, wv); rotate(fa, xi_rot, wa);
+    /* point jacobian of x_i.pos on link l (constraint.py:68-98), dotted with the force */
+    for (int d = 0; d < nv; d++) {
+      if (!is_ancestor_or_self(m, m->dof_link[d], l)) continue;
+      real jv[3];
+      cross3(off, e->cdof_ang[d], c);
+      for (int i = 0; i < 3; i++) jv[i] = e->cdof_vel[d][i] - c[i];
+      out[d] += dot3(jv, wv) + dot3(e->cdof_ang[d], wa);
+    }
+  }
+}
+
 /* dynamics.forward = passive - inverse(RNE) + tau, dynamics.py:137-236 */
 static void dyn_forward(const OrcModel* m, Env* e, const real* tau) {
   int L = m->num_links, nv = m->nv;
-  real cdd_a[MAXL][3], cdd_v[MAXL][3], cf_a[MAXL][3], cf_v[MAXL][3];
+  real cdd_a[MAXL][3], cdd_v[MAXL][3], cf_a[MAXL][3], cf_v[MAXL][3], fluid[MAXV];
+  if (m->enable_fluid) fluid_passive(m, e, fluid);
   for (int l = 0; l < L; l++) {
     int p = m->link_parent[l], da = m->link_qd_adr[l], nd = m->link_ndof[l] == 0 ? 6 : m->link_ndof[l];
     for (int i = 0; i < 3; i++) { cdd_a[l][i] = p >= 0 ? cdd_a[p][i] : 0; cdd_v[l][i] = p >= 0 ? cdd_v[p][i] : -m->gravity[i]; }
@@ -756,6 +811,7 @@ static void dyn_forward(const OrcModel* m, Env* e, const real* tau) {
     int qi = m->link_q_adr[l] + (d - m->link_qd_adr[l]);
     real passive = is_free ? (real)0 : -e->q[qi] * m->dof_stiffness[d];
     passive = passive - m->dof_damping[d] * e->qd[d];
+    if (m->enable_fluid) passive = passive + fluid[d];
     e->qf_smooth[d] = (passive - bias) + tau[d];
   }
 }

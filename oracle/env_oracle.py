@@ -8,6 +8,10 @@ tests/test_reference_golden.py).  Follows, statement by statement, float32:
   brax/envs/half_cheetah.py:178-212   Halfcheetah.step / _get_obs
   brax/envs/hopper.py:219-276         Hopper.step / _get_obs
   brax/envs/walker2d.py:200-273       Walker2d.step / _get_obs
+  brax/envs/inverted_pendulum.py:131-154         InvertedPendulum.step / _get_obs
+  brax/envs/inverted_double_pendulum.py:161-195  InvertedDoublePendulum.step / _get_obs
+  brax/envs/reacher.py:199-239        Reacher.step / _get_obs
+  brax/envs/swimmer.py:157-194        Swimmer.step / _get_obs
   brax/envs/wrappers/training.py:98-158  EpisodeWrapper.step, AutoResetWrapper.step
   brax/actuator.py:23-57              to_tau (for Humanoid's qfrc_actuator)
 """
@@ -27,7 +31,7 @@ def _rotate(v, q):
 
 
 class EnvOracle:
-  def __init__(self, sys, kind, *, forward_reward_weight=1.0, ctrl_cost_weight, healthy_reward,
+  def __init__(self, sys, kind, *, forward_reward_weight=1.0, ctrl_cost_weight=0.0, healthy_reward=0.0,
                terminate_when_unhealthy=True, healthy_z_range=(-np.inf, np.inf), exclude_current_positions=True,
                n_frames=5, episode_length=None, auto_reset=False,
                healthy_angle_range=(-np.inf, np.inf), healthy_state_range=(-np.inf, np.inf)):
@@ -38,6 +42,9 @@ class EnvOracle:
     self.zmin, self.zmax = f32(healthy_z_range[0]), f32(healthy_z_range[1])
     self.planar = kind in ('hopper', 'walker2d')
     self.skip = (1 if kind == 'halfcheetah' or self.planar else 2) if exclude_current_positions else 0
+    self.classic = kind in ('inverted_pendulum', 'inverted_double_pendulum', 'reacher', 'swimmer')
+    if self.classic and kind != 'swimmer':
+      self.skip = 0
     self.amin, self.amax = f32(healthy_angle_range[0]), f32(healthy_angle_range[1])
     self.smin, self.smax = f32(healthy_state_range[0]), f32(healthy_state_range[1])
     self.n_frames = n_frames
@@ -72,12 +79,24 @@ class EnvOracle:
     np.add.at(tau, (slice(None), np.asarray(a.qd_id)), force)
     return tau
 
+  def _tip(self, st, link, p):
+    return (st['x_pos'][:, link] + _rotate(np.asarray(p, f32)[None], st['x_rot'][:, link])).astype(f32)
+
   def obs(self, st, action):
+    if self.kind == 'inverted_double_pendulum':   # [q[:1], sin(q[1:]), cos(q[1:]), clip(qd, -10, 10)]
+      q = st['q']
+      return np.concatenate([q[:, :1], np.sin(q[:, 1:]), np.cos(q[:, 1:]), np.clip(st['qd'], f32(-10), f32(10))], 1).astype(f32)
+    if self.kind == 'reacher':   # [cos(theta), sin(theta), q[2:], tip_vel[:2], tip_pos - target_pos]
+      theta = st['q'][:, :2]
+      tip = self._tip(st, 1, (0.11, 0, 0))
+      p = np.asarray((0.11, 0, 0), f32)[None]
+      tip_vel = (st['xd_vel'][:, 1] - np.cross(p, st['xd_ang'][:, 1])).astype(f32)
+      return np.concatenate([np.cos(theta), np.sin(theta), st['q'][:, 2:], tip_vel[:, :2], tip - st['x_pos'][:, 2]], 1).astype(f32)
     if self.planar:   # position = q.at[1].set(x.pos[0, 2]); velocity = clip(qd, -10, 10)
       pos = st['q'].copy(); pos[:, 1] = st['x_pos'][:, 0, 2]
       return np.concatenate([pos[:, self.skip:], np.clip(st['qd'], f32(-10), f32(10))], 1).astype(f32)
     q, qd = st['q'][:, self.skip:], st['qd']
-    if self.kind in ('ant', 'halfcheetah'):
+    if self.kind in ('ant', 'halfcheetah', 'inverted_pendulum', 'swimmer'):
       return np.concatenate([q, qd], 1).astype(f32)
     n, L = q.shape[0], len(self.mass)
     com, mass_sum, x_i = self._com(st)
@@ -104,6 +123,8 @@ class EnvOracle:
   def _env_step(self, ps0, action):
     """Ant.step / Humanoid.step on pipeline states (no wrappers)."""
     action = np.asarray(action, f32)
+    if self.classic:
+      return self._classic_step(ps0, action)
     if self.kind == 'humanoid':
       lo, hi = self.sys.actuator.ctrl_range[:, 0], self.sys.actuator.ctrl_range[:, 1]
       action = ((action + f32(1)) * (hi - lo) * f32(0.5) + lo).astype(f32)
@@ -147,6 +168,49 @@ class EnvOracle:
            'x_position': after[:, 0], 'y_position': after[:, 1], 'distance_from_origin': dist,
            'x_velocity': velocity[:, 0], 'y_velocity': velocity[:, 1]}
     return ps, self.obs(ps, action), reward, done, m
+
+  def _classic_step(self, ps0, action):
+    """InvertedPendulum / InvertedDoublePendulum / Reacher / Swimmer .step on pipeline states."""
+    if self.kind == 'inverted_pendulum':
+      lo, hi = self.sys.actuator.ctrl_range[:, 0], self.sys.actuator.ctrl_range[:, 1]
+      action = ((action + f32(1)) * (hi - lo) * f32(0.5) + lo).astype(f32)
+    ps = {k: v.copy() for k, v in ps0.items()}
+    self.o.step(ps, action, self.n_frames)
+    n = action.shape[0]
+    ob = self.obs(ps, action)
+    sq = np.zeros(n, f32)
+    for a in range(action.shape[1]):
+      sq = (sq + action[:, a] * action[:, a]).astype(f32)
+    m = {}
+    if self.kind == 'inverted_pendulum':
+      reward = np.ones(n, f32)
+      done = np.where(np.abs(ob[:, 1]) > f32(0.2), f32(1), f32(0)).astype(f32)
+    elif self.kind == 'inverted_double_pendulum':
+      tip = self._tip(ps, 2, (0, 0, 0.6))
+      x, y = tip[:, 0], tip[:, 2]
+      v1, v2 = ps['qd'][:, 1], ps['qd'][:, 2]
+      dist_penalty = (f32(0.01) * x ** 2 + (y - f32(2)) ** 2).astype(f32)
+      vel_penalty = (f32(1e-3) * v1 ** 2 + f32(5e-3) * v2 ** 2).astype(f32)
+      done = np.where(y <= 1, f32(1), f32(0)).astype(f32)
+      reward = (((f32(1) - done) * f32(10) - dist_penalty) - vel_penalty).astype(f32)
+    elif self.kind == 'reacher':
+      v = ob[:, -3:]
+      zero = np.all(np.abs(v) <= 1e-8, axis=1)           # math.safe_norm
+      norm = np.where(zero, f32(0), np.sqrt(np.sum(np.where(zero[:, None], f32(1), v) ** 2, -1))).astype(f32)
+      m = {'reward_dist': -norm, 'reward_ctrl': -sq}
+      reward = (m['reward_dist'] + m['reward_ctrl']).astype(f32)
+      done = np.zeros(n, f32)
+    else:   # swimmer
+      xy = ps['q'][:, :2]
+      vel = ((xy - ps0['q'][:, :2]) / self.dt).astype(f32)
+      forward = (self.w_fwd * vel[:, 0]).astype(f32)
+      ctrl = (self.w_ctrl * sq).astype(f32)
+      reward = (forward - ctrl).astype(f32)
+      done = np.zeros(n, f32)
+      m = {'reward_fwd': forward, 'reward_ctrl': -ctrl, 'x_position': xy[:, 0], 'y_position': xy[:, 1],
+           'distance_from_origin': np.sqrt(xy[:, 0] ** 2 + xy[:, 1] ** 2).astype(f32), 'x_velocity': vel[:, 0], 'y_velocity': vel[:, 1],
+           'forward_reward': np.zeros(n, f32)}   # swimmer.py never updates it after reset
+    return ps, ob, reward, done, m
 
   def step(self, env, action):
     """AutoReset(Episode(env)).step with action_repeat = 1."""

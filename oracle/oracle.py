@@ -67,6 +67,7 @@ def _model_struct(ct):
       ('con_radius', ct * MAXCON), ('con_friction', ct * MAXCON), ('con_solref', ct * (MAXCON * 2)),
       ('con_solimp', ct * (MAXCON * 5)),
       ('con_kind', i32 * MAXCON), ('con_geom_quat', ct * (MAXCON * 4)), ('con_half_len', ct * MAXCON),
+      ('enable_fluid', i32), ('pad2', i32), ('viscosity', ct), ('density', ct),
   ]
 
 
@@ -115,6 +116,8 @@ class Oracle:
     m.solver_maxls = int(sys.solver_maxls)
     m.matrix_inv_iterations = int(sys.matrix_inv_iterations)
     m.dt = float(sys.opt.timestep)
+    m.enable_fluid = int(bool(sys.enable_fluid))
+    m.viscosity, m.density = float(np.asarray(sys.viscosity)), float(np.asarray(sys.density))
 
     def put(name, arr):
       a = np.asarray(arr).reshape(-1)

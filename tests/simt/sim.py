@@ -82,6 +82,10 @@ class SimEnv:
     L, nq, nv = env.sys.num_links(), env.sys.nq, env.sys.nv
     base = nq - env.spec.obs_skip + nv
     self.obs_size = base + 16 * L + nv if env.spec.kind == native.ENV_COM_VELOCITY else base
+    if env.spec.kind == native.ENV_DOUBLE_CARTPOLE:
+      self.obs_size = 1 + 2 * (nq - 1) + nv
+    if env.spec.kind == native.ENV_REACHER:
+      self.obs_size = 4 + (nq - 2) + 2 + 3
 
   def reset(self, q, qd):
     q = np.ascontiguousarray(q, np.float32); qd = np.ascontiguousarray(qd, np.float32)

@@ -419,7 +419,8 @@ def test_capsule_models_single_substep_map(model, drop):
   _report(f'capsule_{model}', {'envs_inside_tolerance': inside / total, 'active_contacts': active, 'substeps': steps, 'n_env': n})
 
 
-@pytest.mark.parametrize('name', ['ant', 'humanoid', 'halfcheetah', 'hopper', 'walker2d', 'two_trees'])
+@pytest.mark.parametrize('name', ['ant', 'humanoid', 'halfcheetah', 'hopper', 'walker2d', 'two_trees', 'inverted_pendulum',
+                                  'inverted_double_pendulum', 'reacher', 'swimmer'])
 def test_cuda_path_against_reference_source_golden(name):
   """The CUDA path directly against golden vectors produced by the reference's own source
   (tests/golden/ref_*.npz, tools/gen_reference_golden.py: brax.generalized.pipeline run

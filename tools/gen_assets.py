@@ -2,8 +2,8 @@
 
 Run in the build container (needs /root/reference for the MJCF sources):
     python tools/gen_assets.py
-Writes brax_b200/assets/{ant,humanoid,halfcheetah,hopper,walker2d}.json and the small pendulum fixtures
-under tests/golden/ that the known-answer tests use.  The XML files themselves
+Writes brax_b200/assets/{ant,humanoid,halfcheetah,hopper,walker2d,inverted_pendulum,inverted_double_pendulum,
+reacher,swimmer}.json and the small pendulum fixtures under tests/golden/ that the known-answer tests use.  The XML files themselves
 are not copied into this repository; only the numbers the hot path consumes.
 """
 import os
@@ -26,7 +26,8 @@ FIXTURES = ['triple_pendulum', 'single_pendulum_motor', 'single_pendulum_positio
             'single_pendulum_velocity', 'single_pendulum_position_frclimit',
             'double_pendulum', 'single_pendulum', 'triple_pendulum_motor']
 
-# further reference env models used only as parity fixtures (slide joints, 2-dof links, no contacts)
+# the classic-control env models (slide joints, 2-dof links, no contacts; Swimmer: fluid forces): shipped as
+# assets and kept as parity fixtures
 ENV_FIXTURES = ['inverted_pendulum', 'inverted_double_pendulum', 'reacher', 'swimmer']
 
 if __name__ == '__main__':
@@ -40,5 +41,8 @@ if __name__ == '__main__':
     print('wrote', out)
   for name in ENV_FIXTURES:
     out = os.path.join(ROOT, 'tests', 'golden', f'{name}.json')
+    model_json.save(mjcf.load(f'{REF}/envs/assets/{name}.xml'), out)
+    print('wrote', out)
+    out = os.path.join(ROOT, 'brax_b200', 'assets', f'{name}.json')
     model_json.save(mjcf.load(f'{REF}/envs/assets/{name}.xml'), out)
     print('wrote', out)

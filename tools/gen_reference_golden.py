@@ -71,10 +71,10 @@ def reference_system(s):
                     bias_q=F(a.bias_q), bias_qd=F(a.bias_qd))
   ng = 0 if s.geom_bodyid is None else len(s.geom_bodyid)
   return rb.System(
-      gravity=F(s.gravity), viscosity=0.0, density=0.0, link=link, dof=dof, actuator=act, init_q=F(s.init_q),
+      gravity=F(s.gravity), viscosity=F(s.viscosity), density=F(s.density), link=link, dof=dof, actuator=act, init_q=F(s.init_q),
       elasticity=jp.zeros(max(ng, 1)), vel_damping=0.0, ang_damping=0.0, baumgarte_erp=0.0, spring_mass_scale=0.0,
       spring_inertia_scale=0.0, joint_scale_ang=0.0, joint_scale_pos=0.0, collide_scale=0.0,
-      enable_fluid=False, link_names=list(s.link_names), link_types=s.link_types, link_parents=tuple(s.link_parents),
+      enable_fluid=bool(s.enable_fluid), link_names=list(s.link_names), link_types=s.link_types, link_parents=tuple(s.link_parents),
       matrix_inv_iterations=int(s.matrix_inv_iterations), solver_iterations=int(s.solver_iterations),
       solver_maxls=int(s.solver_maxls), mj_model=None,
       nq=s.nq, nv=nv, nu=s.nu, opt=mjx.Option(timestep=float(np.float32(s.opt.timestep))),
@@ -119,7 +119,8 @@ def inputs(s, name, n, steps, drop, seed=0):
 
 
 def load(name):
-  if name in ('ant', 'humanoid', 'halfcheetah', 'hopper', 'walker2d'):
+  if name in ('ant', 'humanoid', 'halfcheetah', 'hopper', 'walker2d', 'inverted_pendulum', 'inverted_double_pendulum',
+              'reacher', 'swimmer'):
     return envs_assets.load(name)
   if name == 'two_trees':      # our own synthetic model (tests/synthetic_models.py): several free roots
     from brax_b200.io import mjcf
@@ -130,36 +131,47 @@ def load(name):
 
 
 ENV_XML = {'ant.xml': 'ant', 'humanoid.xml': 'humanoid', 'half_cheetah.xml': 'halfcheetah', 'hopper.xml': 'hopper',
-           'walker2d.xml': 'walker2d'}
+           'walker2d.xml': 'walker2d', 'inverted_pendulum.xml': 'inverted_pendulum',
+           'inverted_double_pendulum.xml': 'inverted_double_pendulum', 'reacher.xml': 'reacher', 'swimmer.xml': 'swimmer'}
 
 
 def _mjcf_load(path):
   """Stands in for brax.io.mjcf.load (MuJoCo's compiler): our compiled constants for that asset."""
   s = load(ENV_XML[os.path.basename(str(path))])
-  mjx.PAIRS = s.contact_pairs()
+  mjx.PAIRS = s.contact_pairs() if s.geom_bodyid is not None and len(s.contact_pairs().geom1) else None
   return reference_system(s)
 
 
-def env_golden():
+def env_golden(only=None):
   """The reference envs + wrappers, unmodified, on the stand-ins."""
   import jax
   mjcf_stub.load = _mjcf_load
   from brax.envs import ant as ref_ant, half_cheetah as ref_hc, humanoid as ref_hum   # the reference
   from brax.envs import hopper as ref_hop, walker2d as ref_walk                       # the reference
+  from brax.envs import inverted_pendulum as ref_ip, inverted_double_pendulum as ref_idp, reacher as ref_re, swimmer as ref_sw
   from brax.envs.wrappers import training as ref_wrap                                 # the reference
   assert ref_wrap.__file__.startswith('/root/reference/')
   cases = {'ant': (ref_ant.Ant, 4, 7, 5), 'humanoid': (ref_hum.Humanoid, 3, 6, 4), 'halfcheetah': (ref_hc.Halfcheetah, 3, 5, 3),
-           'hopper': (ref_hop.Hopper, 4, 6, 4), 'walker2d': (ref_walk.Walker2d, 3, 5, 4)}
+           'hopper': (ref_hop.Hopper, 4, 6, 4), 'walker2d': (ref_walk.Walker2d, 3, 5, 4),
+           'inverted_pendulum': (ref_ip.InvertedPendulum, 4, 6, 4), 'inverted_double_pendulum': (ref_idp.InvertedDoublePendulum, 4, 6, 4),
+           'reacher': (ref_re.Reacher, 3, 6, 4), 'swimmer': (ref_sw.Swimmer, 3, 6, 4)}
   for name, (cls, n, steps, ep_len) in cases.items():
+    if only is not None and f'env_{name}' not in only:
+      continue
     env = ref_wrap.wrap(cls(backend='generalized'), episode_length=ep_len, action_repeat=1)
     rng = np.random.default_rng(7)
     st = env.reset(jax.random.split(jax.random.PRNGKey(3), n))
-    if name in ('ant', 'hopper'):   # one env starts unhealthy (Ant: z too high; Hopper: root angle out of range): terminates at once
+    if name in ('ant', 'hopper', 'inverted_pendulum', 'inverted_double_pendulum'):
+      # one env starts unhealthy (Ant: z too high; Hopper: root angle out of range; the pendulums: pole(s) tipped over): terminates at once
       q = np.asarray(st.pipeline_state.q).copy()
       if name == 'ant':
         q[0, 2] = 1.3
-      else:
+      elif name == 'hopper':
         q[0, 2] = 0.5
+      elif name == 'inverted_pendulum':
+        q[0, 1] = 0.5
+      else:
+        q[0, 1] = 1.5
       inner = env.env.env.env     # AutoReset -> Episode -> Vmap -> the env
       ps = jax.vmap(inner.pipeline_init)(jp.array(q), st.pipeline_state.qd)
       obs = jax.vmap(inner._get_obs)(ps)
@@ -186,8 +198,11 @@ def env_golden():
 
 
 def main():
-  env_golden()
+  only = set(sys.argv[1].split(',')) if len(sys.argv) > 1 else None   # e.g. `swimmer,env_reacher`
+  env_golden(only)
   for name, (n, steps, drop) in CASES.items():
+    if only is not None and name not in only:
+      continue
     s = load(name)
     mjx.PAIRS = s.contact_pairs() if s.geom_bodyid is not None and len(s.contact_pairs().geom1) else None
     rs = reference_system(s)
