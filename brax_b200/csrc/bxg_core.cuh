@@ -1645,7 +1645,7 @@ BXG_HD void env_prologue(X& ex, const Ctx& c, const BxgEnvSpec& sp, const BxgSta
   ex.lanes([&](int lane) {
     for (int i = lane; i < L * 3; i += X::G) s[D.s_x_pos + i] = g.x_pos[e * L * 3 + i];
     for (int i = lane; i < L * 4; i += X::G) s[D.s_x_rot + i] = g.x_rot[e * L * 4 + i];
-    if (sp.kind == BXG_ENV_COM_VELOCITY || sp.kind == BXG_ENV_CARTPOLE) {
+    if (sp.kind == BXG_ENV_COM_VELOCITY || sp.kind == BXG_ENV_CARTPOLE || sp.kind == BXG_ENV_STANDUP) {
       // action = (a + 1) * (hi - lo) * 0.5 + lo   (envs/humanoid.py:260-262, inverted_pendulum.py:134-137)
       for (int a = lane; a < D.nu; a += X::G) {
         float lo = mf[D.m_act_clo + a], hi = mf[D.m_act_chi + a];
@@ -1696,7 +1696,7 @@ BXG_HD void env_write_obs(X& ex, const Ctx& c, const BxgEnvSpec& sp, float* o) {
       for (int i = lane; i < np; i += G) o[i] = s[D.s_q + sp.obs_skip + i];
       for (int i = lane; i < nv; i += G) o[np + i] = s[D.s_qd + i];
     }
-    if (sp.kind == BXG_ENV_COM_VELOCITY) {
+    if (sp.kind == BXG_ENV_COM_VELOCITY || sp.kind == BXG_ENV_STANDUP) {
       float mass_sum = 0.f;
       for (int l = 0; l < L; ++l) mass_sum += mf[D.m_in_mass + l];
       float* oi = o + np + nv; float* ov = oi + 10 * L; float* of = ov + 6 * L;
@@ -1722,7 +1722,7 @@ template <class X>
 BXG_HD void env_reset_obs(X& ex, const Ctx& c, const BxgEnvSpec& sp, float* o) {
   const Dims& D = *c.D; float* s = c.s;
   ex.lanes([&](int lane) { for (int a = lane; a < D.nu; a += X::G) s[D.s_act + a] = 0.f; });
-  if (sp.kind == BXG_ENV_COM_VELOCITY) actuator_tau(ex, c);
+  if (sp.kind == BXG_ENV_COM_VELOCITY || sp.kind == BXG_ENV_STANDUP) actuator_tau(ex, c);
   env_write_obs(ex, c, sp, o);
 }
 
@@ -1731,7 +1731,7 @@ BXG_HD void env_epilogue(X& ex, const Ctx& c, const BxgEnvSpec& sp, const BxgEnv
   const Dims& D = *c.D; const float* mf = c.mf; float* s = c.s;
   const int L = D.L, nv = D.nv, nq = D.nq;
   const bool com_kind = sp.kind == BXG_ENV_COM_VELOCITY;
-  if (com_kind) actuator_tau(ex, c);   // qfrc_actuator at the post-step q, qd (humanoid.py:325-327)
+  if (com_kind || sp.kind == BXG_ENV_STANDUP) actuator_tau(ex, c);   // qfrc_actuator at the post-step q, qd (humanoid.py:325-327)
   // ---- reward / done / metrics: every lane redundantly (uniform scalars) ----
   V3 before = ld3(s + D.s_red);
   V3 after = com_kind ? env_com(c) : ld3(s + D.s_x_pos);
@@ -1775,6 +1775,11 @@ BXG_HD void env_epilogue(X& ex, const Ctx& c, const BxgEnvSpec& sp, const BxgEnv
     V3 tt = env_tip(c, sp) - ld3(s + D.s_x_pos + 3 * sp.target_link);
     ms[0] = -env_safe_norm(tt); ms[1] = -sq;
     reward = ms[0] + ms[1]; done = 0.f;
+  } else if (sp.kind == BXG_ENV_STANDUP) {
+    // uph_cost = (z - 0) / dt; reward = uph_cost + 1 - 0.01 * sum(action^2)  (envs/humanoidstandup.py:227-236)
+    float uph_cost = (z - 0.f) / sp.env_dt;
+    reward = (uph_cost + sp.healthy_reward) - ctrl_cost; done = 0.f;
+    ms[0] = uph_cost; ms[1] = -ctrl_cost;
   } else if (sp.kind == BXG_ENV_SWIMMER) {
     // envs/swimmer.py:168-183 (jp.linalg.norm, not safe_norm; 'forward_reward' is never updated)
     reward = forward_reward - ctrl_cost; done = 0.f;

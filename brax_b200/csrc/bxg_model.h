@@ -91,7 +91,7 @@ inline Variant variant(int id) {
     case 2: return {32, 8, 8, 32, 32, 32};
     case 4: return {16, 6, 7, 16, 24, 28};   // Humanoid class on a half-warp (6x6 tiles); forced only
     case 5: return {32, 4, 16, 32, 16, 64};  // few dofs, many constraint rows (Walker2d, HalfCheetah): rows of A stay in shared memory
-    default: return {32, 0, 0, 32, 64, 64};  // generic
+    default: return {32, 0, 0, 32, 64, 128}; // generic
   }
 }
 // Row stride of the nv-column matrices.  The register-tile products read TM rows per
@@ -183,7 +183,7 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
   if (nq != m.nq || nv != m.nv) return "nq/nv inconsistent with link_ndof";
   d.nlim = m.has_limit ? nonfree : 0;
   d.nc = 4 * m.ncon + d.nlim;
-  if (d.nc > 64) return "more than 64 constraint rows not supported";
+  if (d.nc > 128) return "more than 128 constraint rows not supported";
   int vid = force_variant;
   d.fluid = m.enable_fluid ? 1 : 0;
   if (d.fluid && vid >= 0 && variant(vid).VC4 != 0) return "fluid forces are compiled into the generic kernel variant only";
@@ -401,7 +401,7 @@ BXG_MODEL_HD int env_obs_size(const Dims& D, const BxgEnvSpec& sp) {
   int base = (D.nq - sp.obs_skip) + D.nv;
   if (sp.kind == BXG_ENV_DOUBLE_CARTPOLE) return 1 + 2 * (D.nq - 1) + D.nv;   // q[0], sin, cos of q[1:], qd
   if (sp.kind == BXG_ENV_REACHER) return 4 + (D.nq - 2) + 2 + 3;               // cos, sin of q[:2], q[2:], tip_vel[:2], tip - target
-  return sp.kind == BXG_ENV_COM_VELOCITY ? base + 10 * D.L + 6 * D.L + D.nv : base;
+  return (sp.kind == BXG_ENV_COM_VELOCITY || sp.kind == BXG_ENV_STANDUP) ? base + 10 * D.L + 6 * D.L + D.nv : base;
 }
 
 }  // namespace bxg

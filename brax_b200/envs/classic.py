@@ -1,5 +1,5 @@
 """The small classic-control envs (reference `brax/envs/{inverted_pendulum, inverted_double_pendulum,
-reacher, swimmer}.py`, backend='generalized').
+reacher, swimmer}.py`, backend='generalized') and HumanoidStandup.
 
 No contacts; slide joints (the carts), a 2-dof link (Reacher's target) and, for Swimmer, the fluid
 forces of `brax/fluid.py` (compiled into the generic kernel variant).  Each env has its own kind in
@@ -134,4 +134,25 @@ class Swimmer(FusedEnv):
     init_q = torch.as_tensor(np.asarray(self.sys.init_q, np.float32), device=device)
     q = init_q[None] + sharding.uniform(env_begin, n, self.sys.nq, seed, 1, -s, s, device)
     qd = sharding.uniform(env_begin, n, self.sys.nv, seed, 2, -s, s, device)
+    return q.contiguous(), qd.contiguous()
+
+
+class HumanoidStandup(FusedEnv):
+  """Reference envs/humanoidstandup.py:180-274: the humanoid starts lying down; reward = torso z / dt + 1
+  - 0.01 * sum(action^2), never done.  15 floor contacts (torso, thighs, feet spheres and the limbs'
+  capsule ends) make 77 constraint rows: the generic kernel variant."""
+
+  def __init__(self, backend='generalized', n_frames=5, **kwargs):
+    _check_backend(backend)
+    spec = _spec(native.ENV_STANDUP)
+    spec.obs_skip = 2
+    spec.ctrl_cost_weight = 0.01
+    spec.healthy_reward = 1.0
+    super().__init__(envs_assets.load('humanoidstandup'), spec, ('reward_linup', 'reward_quadctrl'), n_frames, **kwargs)
+
+  def _reset_q_qd(self, env_begin, n, seed, device):
+    # qpos = init_q + U(-0.01, 0.01); qvel = U(-0.01, 0.01)   (humanoidstandup.py:202-209)
+    init_q = torch.as_tensor(np.asarray(self.sys.init_q, np.float32), device=device)
+    q = init_q[None] + sharding.uniform(env_begin, n, self.sys.nq, seed, 1, -0.01, 0.01, device)
+    qd = sharding.uniform(env_begin, n, self.sys.nv, seed, 2, -0.01, 0.01, device)
     return q.contiguous(), qd.contiguous()

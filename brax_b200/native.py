@@ -71,6 +71,7 @@ ENV_CARTPOLE = 4
 ENV_DOUBLE_CARTPOLE = 5
 ENV_REACHER = 6
 ENV_SWIMMER = 7
+ENV_STANDUP = 8
 ENV_NUM_METRICS = 10
 
 

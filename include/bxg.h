@@ -181,8 +181,11 @@ enum {
   BXG_ENV_REACHER = 6,        /* Reacher (envs/reacher.py:199-239): obs = [cos(q[:2]), sin(q[:2]), q[2:], tip_vel[:2],
                                  tip - target]; tip on link tip_link, target = position of link target_link;
                                  reward = -|tip - target| - sum(action^2) */
-  BXG_ENV_SWIMMER = 7         /* Swimmer (envs/swimmer.py:157-194): velocity of q[:2]; obs = [q[skip:], qd];
+  BXG_ENV_SWIMMER = 7,        /* Swimmer (envs/swimmer.py:157-194): velocity of q[:2]; obs = [q[skip:], qd];
                                  reward = forward_reward_weight * vx - ctrl_cost_weight * sum(action^2) */
+  BXG_ENV_STANDUP = 8         /* HumanoidStandup (envs/humanoidstandup.py:220-274): action rescaled to the ctrl range;
+                                 obs as COM_VELOCITY; reward = z of link 0 / env_dt + healthy_reward
+                                 - ctrl_cost_weight * sum(action^2); never done */
 };
 #define BXG_ENV_NUM_METRICS 10
 
@@ -210,6 +213,7 @@ typedef struct BxgEnvSpec {
  *                 y_position, distance_from_origin, x_velocity, y_velocity, (unused)
  *  CARTPOLE, DOUBLE_CARTPOLE: none
  *  REACHER:       reward_dist, reward_ctrl
+ *  STANDUP:       reward_linup, reward_quadctrl
  *  SWIMMER:       reward_fwd, -, reward_ctrl, -, x_position, y_position, distance_from_origin,
  *                 x_velocity, y_velocity, forward_reward (always 0: swimmer.py never updates it)  */
 typedef struct BxgEnvIO {

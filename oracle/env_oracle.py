@@ -12,6 +12,7 @@ tests/test_reference_golden.py).  Follows, statement by statement, float32:
   brax/envs/inverted_double_pendulum.py:161-195  InvertedDoublePendulum.step / _get_obs
   brax/envs/reacher.py:199-239        Reacher.step / _get_obs
   brax/envs/swimmer.py:157-194        Swimmer.step / _get_obs
+  brax/envs/humanoidstandup.py:220-274  HumanoidStandup.step / _get_obs
   brax/envs/wrappers/training.py:98-158  EpisodeWrapper.step, AutoResetWrapper.step
   brax/actuator.py:23-57              to_tau (for Humanoid's qfrc_actuator)
 """
@@ -125,6 +126,18 @@ class EnvOracle:
     action = np.asarray(action, f32)
     if self.classic:
       return self._classic_step(ps0, action)
+    if self.kind == 'humanoidstandup':
+      lo, hi = self.sys.actuator.ctrl_range[:, 0], self.sys.actuator.ctrl_range[:, 1]
+      action = ((action + f32(1)) * (hi - lo) * f32(0.5) + lo).astype(f32)
+      ps = {k: v.copy() for k, v in ps0.items()}
+      self.o.step(ps, action, self.n_frames)
+      uph = ((ps['x_pos'][:, 0, 2] - f32(0)) / self.dt).astype(f32)
+      sq = np.zeros(action.shape[0], f32)
+      for a in range(action.shape[1]):
+        sq = (sq + action[:, a] * action[:, a]).astype(f32)
+      quad = (f32(0.01) * sq).astype(f32)
+      reward = ((uph + f32(1)).astype(f32) - quad).astype(f32)
+      return ps, self.obs(ps, action), reward, np.zeros_like(reward), {'reward_linup': uph, 'reward_quadctrl': -quad}
     if self.kind == 'humanoid':
       lo, hi = self.sys.actuator.ctrl_range[:, 0], self.sys.actuator.ctrl_range[:, 1]
       action = ((action + f32(1)) * (hi - lo) * f32(0.5) + lo).astype(f32)

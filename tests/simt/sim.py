@@ -81,7 +81,7 @@ class SimEnv:
     self.sys = env.sys
     L, nq, nv = env.sys.num_links(), env.sys.nq, env.sys.nv
     base = nq - env.spec.obs_skip + nv
-    self.obs_size = base + 16 * L + nv if env.spec.kind == native.ENV_COM_VELOCITY else base
+    self.obs_size = base + 16 * L + nv if env.spec.kind in (native.ENV_COM_VELOCITY, native.ENV_STANDUP) else base
     if env.spec.kind == native.ENV_DOUBLE_CARTPOLE:
       self.obs_size = 1 + 2 * (nq - 1) + nv
     if env.spec.kind == native.ENV_REACHER:

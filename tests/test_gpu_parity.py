@@ -420,7 +420,7 @@ def test_capsule_models_single_substep_map(model, drop):
 
 
 @pytest.mark.parametrize('name', ['ant', 'humanoid', 'halfcheetah', 'hopper', 'walker2d', 'two_trees', 'inverted_pendulum',
-                                  'inverted_double_pendulum', 'reacher', 'swimmer'])
+                                  'inverted_double_pendulum', 'reacher', 'swimmer', 'humanoidstandup'])
 def test_cuda_path_against_reference_source_golden(name):
   """The CUDA path directly against golden vectors produced by the reference's own source
   (tests/golden/ref_*.npz, tools/gen_reference_golden.py: brax.generalized.pipeline run

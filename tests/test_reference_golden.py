@@ -17,9 +17,9 @@ import pytest
 from oracle import oracle as O
 from tests.conftest import ROOT
 
-MODELS = ['ant', 'humanoid', 'halfcheetah', 'hopper', 'walker2d', 'triple_pendulum_motor', 'inverted_pendulum',
+MODELS = ['ant', 'humanoid', 'halfcheetah', 'hopper', 'walker2d', 'humanoidstandup', 'triple_pendulum_motor', 'inverted_pendulum',
           'inverted_double_pendulum', 'reacher', 'swimmer', 'two_trees']
-ASSETS = ('ant', 'humanoid', 'halfcheetah', 'hopper', 'walker2d')
+ASSETS = ('ant', 'humanoid', 'halfcheetah', 'hopper', 'walker2d', 'humanoidstandup')
 
 
 def _load(name):
@@ -91,6 +91,7 @@ ENVS = {
                    healthy_z_range=(0.7, np.inf), healthy_angle_range=(-0.2, 0.2), healthy_state_range=(-100.0, 100.0)),
     'walker2d': dict(kind='walker2d', forward_reward_weight=1.0, ctrl_cost_weight=1e-3, healthy_reward=1.0, n_frames=4,
                      healthy_z_range=(0.8, 2.0), healthy_angle_range=(-1.0, 1.0)),
+    'humanoidstandup': dict(kind='humanoidstandup', n_frames=5),
     'inverted_pendulum': dict(kind='inverted_pendulum', n_frames=2),
     'inverted_double_pendulum': dict(kind='inverted_double_pendulum', n_frames=2),
     'reacher': dict(kind='reacher', n_frames=2),
@@ -135,10 +136,10 @@ def test_env_oracle_matches_reference_envs_and_wrappers(name):
     for m, v in env['metrics'].items():
       np.testing.assert_allclose(v, g[p + 'metric_' + m], rtol=2e-3, atol=5e-3, err_msg=f'{name} step {k} {m}')
     saw_done |= bool(g[p + 'done'].any()); saw_trunc |= bool(g[p + 'truncation'].any())
-  assert saw_trunc and (saw_done or name in ('reacher', 'swimmer'))
+  assert saw_trunc and (saw_done or name in ('reacher', 'swimmer', 'humanoidstandup'))
 
 
-@pytest.mark.parametrize('name', ['ant', 'humanoid', 'halfcheetah', 'hopper', 'two_trees', 'swimmer', 'reacher', 'inverted_double_pendulum'])
+@pytest.mark.parametrize('name', ['ant', 'humanoid', 'halfcheetah', 'hopper', 'two_trees', 'swimmer', 'reacher', 'inverted_double_pendulum', 'humanoidstandup'])
 def test_kernel_source_against_reference_source_golden(name):
   """brax_b200/csrc/bxg_core.cuh (float32, through the host lane emulator) directly against the
   reference-source golden (float64): one-step maps inside the stated 1e-4 / 1e-5 tolerance."""

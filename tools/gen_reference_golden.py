@@ -95,7 +95,7 @@ LEAVES = {   # our flat State field -> accessor on the reference State
 
 # model -> (envs, steps, how far to drop the root towards the floor so that contacts are active)
 CASES = {'ant': (3, 6, 0.0), 'humanoid': (2, 6, 0.0), 'halfcheetah': (2, 5, 0.35), 'hopper': (2, 5, 0.04),
-         'walker2d': (2, 5, 0.05), 'triple_pendulum_motor': (2, 4, 0.0), 'inverted_pendulum': (2, 4, 0.0),
+         'walker2d': (2, 5, 0.05), 'humanoidstandup': (2, 4, 0.0), 'triple_pendulum_motor': (2, 4, 0.0), 'inverted_pendulum': (2, 4, 0.0),
          'inverted_double_pendulum': (2, 4, 0.0), 'reacher': (2, 4, 0.0), 'swimmer': (2, 4, 0.0), 'two_trees': (2, 6, 0.0)}
 
 
@@ -104,6 +104,8 @@ def inputs(s, name, n, steps, drop, seed=0):
   q = np.asarray(s.init_q, np.float64)[None] + rng.uniform(-0.1, 0.1, (n, s.nq))
   if name == 'ant':
     q[:, 2] = 0.45 + 0.1 * rng.uniform(size=n)        # feet touching
+  if name == 'humanoidstandup':   # lying on the floor (init_q), small noise as the env's reset
+    q = np.asarray(s.init_q, np.float64)[None] + rng.uniform(-0.01, 0.01, (n, s.nq))
   if name == 'humanoid':
     q = np.asarray(s.init_q, np.float64)[None] + rng.uniform(-0.01, 0.01, (n, s.nq))
     q[:, 2] = 1.29 + 0.02 * rng.uniform(size=n)       # feet touching (foot spheres reach z = 1.4 - 1.3)
@@ -113,13 +115,13 @@ def inputs(s, name, n, steps, drop, seed=0):
     q[:, 1] -= drop
   qd = 0.1 * rng.standard_normal((n, s.nv))
   act = rng.uniform(-1, 1, (steps, n, s.nu))
-  if name == 'humanoid':
+  if name in ('humanoid', 'humanoidstandup'):
     act *= 0.4
   return q.astype(np.float32).astype(np.float64), qd.astype(np.float32).astype(np.float64), act.astype(np.float32).astype(np.float64)
 
 
 def load(name):
-  if name in ('ant', 'humanoid', 'halfcheetah', 'hopper', 'walker2d', 'inverted_pendulum', 'inverted_double_pendulum',
+  if name in ('ant', 'humanoid', 'halfcheetah', 'hopper', 'walker2d', 'humanoidstandup', 'inverted_pendulum', 'inverted_double_pendulum',
               'reacher', 'swimmer'):
     return envs_assets.load(name)
   if name == 'two_trees':      # our own synthetic model (tests/synthetic_models.py): several free roots
@@ -131,7 +133,7 @@ def load(name):
 
 
 ENV_XML = {'ant.xml': 'ant', 'humanoid.xml': 'humanoid', 'half_cheetah.xml': 'halfcheetah', 'hopper.xml': 'hopper',
-           'walker2d.xml': 'walker2d', 'inverted_pendulum.xml': 'inverted_pendulum',
+           'walker2d.xml': 'walker2d', 'humanoidstandup.xml': 'humanoidstandup', 'inverted_pendulum.xml': 'inverted_pendulum',
            'inverted_double_pendulum.xml': 'inverted_double_pendulum', 'reacher.xml': 'reacher', 'swimmer.xml': 'swimmer'}
 
 
@@ -148,13 +150,15 @@ def env_golden(only=None):
   mjcf_stub.load = _mjcf_load
   from brax.envs import ant as ref_ant, half_cheetah as ref_hc, humanoid as ref_hum   # the reference
   from brax.envs import hopper as ref_hop, walker2d as ref_walk                       # the reference
+  from brax.envs import humanoidstandup as ref_hs
   from brax.envs import inverted_pendulum as ref_ip, inverted_double_pendulum as ref_idp, reacher as ref_re, swimmer as ref_sw
   from brax.envs.wrappers import training as ref_wrap                                 # the reference
   assert ref_wrap.__file__.startswith('/root/reference/')
   cases = {'ant': (ref_ant.Ant, 4, 7, 5), 'humanoid': (ref_hum.Humanoid, 3, 6, 4), 'halfcheetah': (ref_hc.Halfcheetah, 3, 5, 3),
            'hopper': (ref_hop.Hopper, 4, 6, 4), 'walker2d': (ref_walk.Walker2d, 3, 5, 4),
            'inverted_pendulum': (ref_ip.InvertedPendulum, 4, 6, 4), 'inverted_double_pendulum': (ref_idp.InvertedDoublePendulum, 4, 6, 4),
-           'reacher': (ref_re.Reacher, 3, 6, 4), 'swimmer': (ref_sw.Swimmer, 3, 6, 4)}
+           'reacher': (ref_re.Reacher, 3, 6, 4), 'swimmer': (ref_sw.Swimmer, 3, 6, 4),
+           'humanoidstandup': (ref_hs.HumanoidStandup, 2, 5, 3)}
   for name, (cls, n, steps, ep_len) in cases.items():
     if only is not None and f'env_{name}' not in only:
       continue

@@ -7,7 +7,7 @@ import torch
 from brax_b200 import envs_assets, native
 
 name = sys.argv[1]; n = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
-nf = int(sys.argv[3]) if len(sys.argv) > 3 else (4 if name in ('hopper', 'walker2d') else 5)
+nf = int(sys.argv[3]) if len(sys.argv) > 3 else {'hopper': 4, 'walker2d': 4, 'swimmer': 4, 'reacher': 2, 'inverted_pendulum': 2, 'inverted_double_pendulum': 2}.get(name, 5)
 dev = torch.device('cuda', 0)
 s = envs_assets.load(name)
 g = torch.Generator(device='cpu').manual_seed(0)
