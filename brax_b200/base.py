@@ -191,7 +191,9 @@ class ContactPairs:
   exclusion.  plane-sphere gives one contact per pair; plane-capsule gives two
   (the capsule's end spheres, +axis first), emitted after the plane-sphere group
   (mjx groups contacts by geom-type pair).  For capsules `frame` is only the
-  fallback: the tangent follows the capsule axis at run time.
+  fallback: the tangent follows the capsule axis at run time.  capsule-capsule
+  (kind 2, one contact between the closest points of the two segments) comes last;
+  both geoms may sit on moving links and geom1's shape is in the `a_*` fields.
   """
   geom1: np.ndarray        # (ncon,) plane geom
   geom2: np.ndarray        # (ncon,) sphere / capsule geom
@@ -208,6 +210,10 @@ class ContactPairs:
   friction: np.ndarray     # (ncon,) sliding friction mu = max(geom1, geom2)
   solref: np.ndarray       # (ncon,2)
   solimp: np.ndarray       # (ncon,5)
+  a_pos: np.ndarray = None     # (ncon,3) kind 2: geom1 centre in link_a frame
+  a_quat: np.ndarray = None    # (ncon,4) kind 2: geom1 orientation in link_a frame
+  a_half: np.ndarray = None    # (ncon,)  kind 2: geom1 half length
+  a_radius: np.ndarray = None  # (ncon,)  kind 2: geom1 radius
 
 
 @dataclasses.dataclass(frozen=True)
@@ -316,7 +322,7 @@ class System(Base):
   def contact_pairs(self) -> ContactPairs:
     """Enumerates colliding geom pairs (see ContactPairs)."""
     ng = 0 if self.geom_type is None else len(self.geom_type)
-    rows, caps = [], []
+    rows, caps, capcap = [], [], []
     for g1 in range(ng):
       for g2 in range(g1 + 1, ng):
         b1, b2 = int(self.geom_bodyid[g1]), int(self.geom_bodyid[g2])
@@ -332,10 +338,13 @@ class System(Base):
             self.link_parents[l1] == l2 or self.link_parents[l2] == l1):
           continue
         t1, t2 = int(self.geom_type[g1]), int(self.geom_type[g2])
+        if (t1, t2) == (3, 3):
+          capcap.append((g1, g2, l1, l2, 2, float(self.geom_size[g2][1])))
+          continue
         if (t1, t2) not in ((0, 2), (0, 3)):
           raise NotImplementedError(
-              f'collision pair type ({t1},{t2}) not supported: only plane-sphere and '
-              'plane-capsule (SURVEY.md section 8 a-11 / f-3)')
+              f'collision pair type ({t1},{t2}) not supported: only plane-sphere, plane-capsule '
+              'and capsule-capsule (SURVEY.md section 8 a-11 / f-3)')
         if l1 != -1:
           raise NotImplementedError('planes must be attached to the world')
         if t2 == 2:
@@ -344,7 +353,7 @@ class System(Base):
           half = float(self.geom_size[g2][1])
           caps.append((g1, g2, l1, l2, 1, half))
           caps.append((g1, g2, l1, l2, 1, -half))
-    rows = rows + caps
+    rows = rows + caps + capcap
     n = len(rows)
     f64 = np.float64
 
@@ -372,16 +381,22 @@ class System(Base):
         frame=np.zeros((n, 3, 3), np.float32),
         sphere_pos=np.zeros((n, 3), np.float32), radius=np.zeros(n, np.float32),
         friction=np.zeros(n, np.float32), solref=np.zeros((n, 2), np.float32),
-        solimp=np.zeros((n, 5), np.float32))
+        solimp=np.zeros((n, 5), np.float32),
+        a_pos=np.zeros((n, 3), np.float32), a_quat=np.tile(np.array([1, 0, 0, 0], np.float32), (n, 1)),
+        a_half=np.zeros(n, np.float32), a_radius=np.zeros(n, np.float32))
     for k, (g1, g2, l1, l2, kind, half) in enumerate(rows):
       cp['kind'][k], cp['half_len'][k] = kind, half
       cp['geom_quat'][k] = self.geom_quat[g2]
       nrm = quat_to_mat(np.asarray(self.geom_quat[g1], f64))[:, 2]
       cp['geom1'][k], cp['geom2'][k] = g1, g2
       cp['link_a'][k], cp['link_b'][k] = l1, l2
-      cp['plane_pos'][k] = self.geom_pos[g1]
-      cp['plane_normal'][k] = nrm
-      cp['frame'][k] = make_frame(nrm)
+      if kind == 2:
+        cp['a_pos'][k], cp['a_quat'][k] = self.geom_pos[g1], self.geom_quat[g1]
+        cp['a_half'][k], cp['a_radius'][k] = self.geom_size[g1][1], self.geom_size[g1][0]
+      else:
+        cp['plane_pos'][k] = self.geom_pos[g1]
+        cp['plane_normal'][k] = nrm
+        cp['frame'][k] = make_frame(nrm)
       cp['sphere_pos'][k] = self.geom_pos[g2]
       cp['radius'][k] = self.geom_size[g2][0]
       cp['friction'][k] = max(self.geom_friction[g1][0], self.geom_friction[g2][0])

@@ -242,7 +242,8 @@ int bxg_step(const BxgModel* m, int64_t n_env, int32_t n_frames, const BxgState*
 // what the kernel's env code assumes about the model for each env kind
 static const char* env_spec_error(const BxgModel* m, const BxgEnvSpec* spec) {
   const bxg::Dims& d = m->pm.d;
-  if (spec->kind < BXG_ENV_ROOT_VELOCITY || spec->kind > BXG_ENV_STANDUP) return "unknown env kind";
+  if (spec->kind < BXG_ENV_ROOT_VELOCITY || spec->kind > BXG_ENV_PUSHER) return "unknown env kind";
+  if (spec->kind == BXG_ENV_PUSHER && (d.nu > d.nq || d.nu > d.nv || spec->tip_link < 0 || spec->tip_link >= d.L || spec->target_link < 0 || spec->target_link >= d.L || spec->object_link < 0 || spec->object_link >= d.L)) return "pusher env kind needs tip, object and target links";
   if (spec->kind == BXG_ENV_CARTPOLE && d.nq < 2) return "cartpole env kind needs q = [x, angle, ...]";
   if (spec->kind == BXG_ENV_DOUBLE_CARTPOLE && (d.nv < 3 || spec->tip_link < 0 || spec->tip_link >= d.L)) return "double cartpole env kind needs nv >= 3 and a tip link";
   if (spec->kind == BXG_ENV_REACHER && (d.nq < 2 || spec->tip_link < 0 || spec->tip_link >= d.L || spec->target_link < 0 || spec->target_link >= d.L)) return "reacher env kind needs a tip link and a target link";

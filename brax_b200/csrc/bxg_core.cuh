@@ -1462,9 +1462,67 @@ BXG_HD void capsule_end(Q4 link_rot, Q4 geom_quat, float half_len, V3 n, V3* cen
   *t2 = cross(n, b);
 }
 
+// z column of math.quat_to_3x3(q): the axis of a capsule whose world orientation is q
+BXG_HD V3 capsule_axis(Q4 q) {
+  float dq = q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z, sc = 2.f / dq;
+  float xs = q.x * sc, ys = q.y * sc, zs = q.z * sc;
+  return V3{q.x * zs + q.w * ys, q.y * zs - q.w * xs, 1.f - (q.x * xs + q.y * ys)};
+}
+// mjx math.normalize_with_norm: x / (n + 1e-6 * (n == 0)), n the safe norm
+BXG_HD V3 normalize_with_norm(V3 v, float* norm) {
+  bool zero = fabsf(v.x) <= 1e-8f && fabsf(v.y) <= 1e-8f && fabsf(v.z) <= 1e-8f;
+  float n = zero ? 0.f : sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
+  float d = n + 1e-6f * (n == 0.f ? 1.f : 0.f);
+  *norm = n;
+  return V3{v.x / d, v.y / d, v.z / d};
+}
+// mjx math.closest_segment_point
+BXG_HD V3 closest_segment_point(V3 a, V3 b, V3 pt) {
+  V3 ab = b - a;
+  float t = dot(pt - a, ab) / (dot(ab, ab) + 1e-6f);
+  t = fmaxf(0.f, fminf(t, 1.f));
+  return a + ab * t;
+}
+// mjx collision_primitive.capsule_capsule: closest points of the two segments
+// (math.closest_segment_to_segment_points), then _sphere_sphere; frame = math.make_frame(n).
+// No reference test pins capsule-capsule numbers (parity unpinned for this pair type).
+BXG_HD_NOINLINE void capsule_capsule(V3 ca, V3 xa, float half_a, float rad_a, V3 cb, V3 xb, float half_b, float rad_b,
+                                     float* dist, V3* pos, V3* n_out, V3* t1, V3* t2) {
+  V3 a0 = ca - xa * half_a, a1 = ca + xa * half_a, b0 = cb - xb * half_b, b1 = cb + xb * half_b;
+  float len_a, len_b;
+  V3 dir_a = normalize_with_norm(a1 - a0, &len_a), dir_b = normalize_with_norm(b1 - b0, &len_b);
+  float ha = len_a * 0.5f, hb = len_b * 0.5f;
+  V3 a_mid = a0 + dir_a * ha, b_mid = b0 + dir_b * hb;
+  V3 trans = a_mid - b_mid;
+  float dab = dot(dir_a, dir_b), dat = dot(dir_a, trans), dbt = dot(dir_b, trans);
+  float denom = 1.f - dab * dab;
+  float orig_t_a = (-dat + dab * dbt) / (denom + 1e-6f);
+  float orig_t_b = dbt + orig_t_a * dab;
+  float t_a = fmaxf(-ha, fminf(orig_t_a, ha)), t_b = fmaxf(-hb, fminf(orig_t_b, hb));
+  V3 best_a = a_mid + dir_a * t_a, best_b = b_mid + dir_b * t_b;
+  V3 new_a = closest_segment_point(a0, a1, best_b), new_b = closest_segment_point(b0, b1, best_a);
+  V3 u = new_a - best_b, v = best_a - new_b;
+  if (dot(u, u) < dot(v, v)) best_a = new_a; else best_b = new_b;
+  float d;
+  V3 n = normalize_with_norm(best_b - best_a, &d);
+  if (d == 0.f) n = V3{1.f, 0.f, 0.f};
+  d = d - (rad_a + rad_b);
+  *dist = d;
+  *pos = best_a + n * (rad_a + d * 0.5f);
+  float nn;
+  V3 a = normalize_with_norm(n, &nn);
+  V3 b = (-0.5f < a.y && a.y < 0.5f) ? V3{0.f, 1.f, 0.f} : V3{0.f, 0.f, 1.f};
+  float ab = dot(a, b);
+  b = normalize_with_norm(V3{b.x - a.x * ab, b.y - a.y * ab, b.z - a.z * ab}, &nn);
+  *n_out = a; *t1 = b; *t2 = cross(a, b);
+}
+
 // ------------------------------------------------------- constraint.jacobian
-template <class X>
+template <class X, class Cfg>
 BXG_HD void con_jacobian(X& ex, const Ctx& c) {
+  // contacts between two moving links (capsule-capsule) are compiled into variant 5 and the
+  // generic variant only (bxg_model.h picks one of them for such models)
+  constexpr bool kTwoBody = Cfg::VC4 == 0 || Cfg::NC4 == 16;
   const Dims& D = *c.D; const float* mf = c.mf; const int* mi = c.mi; float* s = c.s;
   const int nv = D.nv, nvp = D.jld;
   float* J = s + D.s_J;
@@ -1480,8 +1538,20 @@ BXG_HD void con_jacobian(X& ex, const Ctx& c) {
     if (mi[D.m_con_kind + cc] == BXG_CON_PLANE_CAPSULE_END) capsule_end(ld4(s + D.s_x_rot + 4 * lb), ld4(mf + D.m_con_gquat + 4 * cc), mf[D.m_con_half + cc], n, &sp, &t1, &t2);
     float dist = dot(sp - ld3(mf + D.m_con_ppos + 3 * cc), n) - rad;
     V3 pos = sp - n * (rad + 0.5f * dist);
+    int la = -1; uint32_t alo = 0u, ahi = 0u;
+    if constexpr (kTwoBody) {
+      if (mi[D.m_con_kind + cc] == BXG_CON_CAPSULE_CAPSULE) {
+        la = mi[D.m_con_la + cc]; alo = (uint32_t)mi[D.m_con_anca_lo + cc]; ahi = (uint32_t)mi[D.m_con_anca_hi + cc];
+        V3 ca = ld3(mf + D.m_con_apos + 3 * cc); Q4 qa = ld4(mf + D.m_con_aquat + 4 * cc), qb = ld4(mf + D.m_con_gquat + 4 * cc);
+        if (la >= 0) { ca = ld3(s + D.s_x_pos + 3 * la) + rotate(ca, ld4(s + D.s_x_rot + 4 * la)); qa = qmul(ld4(s + D.s_x_rot + 4 * la), qa); }
+        qb = qmul(ld4(s + D.s_x_rot + 4 * lb), qb);
+        capsule_capsule(ca, capsule_axis(qa), mf[D.m_con_ahalf + cc], mf[D.m_con_arad + cc], sp, capsule_axis(qb), mf[D.m_con_half + cc], rad,
+                        &dist, &pos, &n, &t1, &t2);
+      }
+    }
     bool active = dist < 0.f;
     V3 off = pos - ld3(s + D.s_root_com + 3 * lb);
+    V3 off_a = la >= 0 ? pos - ld3(s + D.s_root_com + 3 * la) : V3{0.f, 0.f, 0.f};
     uint32_t lo = (uint32_t)mi[D.m_con_anc_lo + cc], hi = (uint32_t)mi[D.m_con_anc_hi + cc];
     V3 dir[4];
     for (int k = 0; k < 4; ++k) {
@@ -1498,6 +1568,16 @@ BXG_HD void con_jacobian(X& ex, const Ctx& c) {
           V3 df = v - cross(off, a);
           r0 = dot(df, dir[0]); r1 = dot(df, dir[1]); r2 = dot(df, dir[2]); r3 = dot(df, dir[3]);
         }
+        if constexpr (kTwoBody) {   // diff = J_b.vel - J_a.vel (constraint.py:158)
+          uint32_t abit = d < 32 ? (alo >> d) & 1u : (ahi >> (d - 32)) & 1u;
+          if (active && abit) {
+            V3 a = ld3(s + D.s_cdof_ang + 3 * d), v = ld3(s + D.s_cdof_vel + 3 * d);
+            V3 ja = v - cross(off_a, a);
+            V3 jb = bit ? v - cross(off, a) : V3{0.f, 0.f, 0.f};
+            V3 df = jb - ja;
+            r0 = dot(df, dir[0]); r1 = dot(df, dir[1]); r2 = dot(df, dir[2]); r3 = dot(df, dir[3]);
+          }
+        }
         J[(4 * cc + 0) * nvp + d] = r0; J[(4 * cc + 1) * nvp + d] = r1;
         J[(4 * cc + 2) * nvp + d] = r2; J[(4 * cc + 3) * nvp + d] = r3;
       }
@@ -1512,6 +1592,7 @@ BXG_HD void con_jacobian(X& ex, const Ctx& c) {
         float imp;
         imp_aref(mf + D.m_con_sp + kImpStride * cc, dist, vel, &imp, &aref);
         float tw = mf[D.m_link_invw + lb];  // link_a is the world: contributes 0
+        if constexpr (kTwoBody) { if (la >= 0) tw = mf[D.m_link_invw + la] + mf[D.m_link_invw + lb]; }   // invweight[a] * (a > -1) + invweight[b]
         diag = (tw + mu * mu * tw) * (2.f * mu * mu * (1.f - imp) / (imp + 1e-8f));
       }
       s[D.s_diag + row] = diag; s[D.s_aref + row] = aref; s[D.s_rowact + row] = active ? 1.f : 0.f;
@@ -1563,7 +1644,7 @@ BXG_HD void update_position_terms(X& ex, const Ctx& c, Stats* st, bool in_step) 
     else minv_newton_schulz<X, Cfg>(ex, c, st);
   }
   if (sl & 2) ex.cta_sync();
-  con_jacobian(ex, c);
+  con_jacobian<X, Cfg>(ex, c);
 }
 
 // pipeline.step (pipeline.py:78-94)
@@ -1618,6 +1699,11 @@ BXG_HD V3 env_tip(const Ctx& c, const BxgEnvSpec& sp) {
   const Dims& D = *c.D; const float* s = c.s;
   return ld3(s + D.s_x_pos + 3 * sp.tip_link) + rotate(V3{sp.tip_pos[0], sp.tip_pos[1], sp.tip_pos[2]}, ld4(s + D.s_x_rot + 4 * sp.tip_link));
 }
+// x.take(link).do(Transform.create(pos=inertia.transform.pos[link])).pos: the link's centre of mass
+BXG_HD V3 env_link_com(const Ctx& c, int l) {
+  const Dims& D = *c.D; const float* s = c.s;
+  return ld3(s + D.s_x_pos + 3 * l) + rotate(ld3(c.mf + D.m_in_pos + 3 * l), ld4(s + D.s_x_rot + 4 * l));
+}
 // math.safe_norm (brax/math.py:308-328)
 BXG_HD float env_safe_norm(V3 v) {
   bool zero = fabsf(v.x) <= 1e-8f && fabsf(v.y) <= 1e-8f && fabsf(v.z) <= 1e-8f;
@@ -1645,7 +1731,7 @@ BXG_HD void env_prologue(X& ex, const Ctx& c, const BxgEnvSpec& sp, const BxgSta
   ex.lanes([&](int lane) {
     for (int i = lane; i < L * 3; i += X::G) s[D.s_x_pos + i] = g.x_pos[e * L * 3 + i];
     for (int i = lane; i < L * 4; i += X::G) s[D.s_x_rot + i] = g.x_rot[e * L * 4 + i];
-    if (sp.kind == BXG_ENV_COM_VELOCITY || sp.kind == BXG_ENV_CARTPOLE || sp.kind == BXG_ENV_STANDUP) {
+    if (sp.kind == BXG_ENV_COM_VELOCITY || sp.kind == BXG_ENV_CARTPOLE || sp.kind == BXG_ENV_STANDUP || sp.kind == BXG_ENV_PUSHER) {
       // action = (a + 1) * (hi - lo) * 0.5 + lo   (envs/humanoid.py:260-262, inverted_pendulum.py:134-137)
       for (int a = lane; a < D.nu; a += X::G) {
         float lo = mf[D.m_act_clo + a], hi = mf[D.m_act_chi + a];
@@ -1655,6 +1741,11 @@ BXG_HD void env_prologue(X& ex, const Ctx& c, const BxgEnvSpec& sp, const BxgSta
   });
   V3 ref = sp.kind == BXG_ENV_COM_VELOCITY ? env_com(c) : ld3(s + D.s_x_pos);
   if (sp.kind == BXG_ENV_SWIMMER) ref = V3{s[D.s_q], s[D.s_q + 1], 0.f};   // pipeline_state0.q[:2] (envs/swimmer.py:165-167)
+  if (sp.kind == BXG_ENV_PUSHER) {
+    // reward_near / reward_dist come from the PRE-step state (envs/pusher.py:204-211: state.pipeline_state.x)
+    V3 obj = env_link_com(c, sp.object_link);
+    ref = V3{-env_safe_norm(obj - env_link_com(c, sp.tip_link)), -env_safe_norm(obj - env_link_com(c, sp.target_link)), 0.f};
+  }
   ex.lanes([&](int lane) { if (lane == 0) st3(s + D.s_red, ref); });
 }
 
@@ -1676,6 +1767,11 @@ BXG_HD void env_write_obs(X& ex, const Ctx& c, const BxgEnvSpec& sp, float* o) {
         o[i] = sn; o[na + i] = cs;
       }
       for (int i = lane; i < nv; i += G) o[1 + 2 * na + i] = fmaxf(-10.f, fminf(s[D.s_qd + i], 10.f));
+    } else if (sp.kind == BXG_ENV_PUSHER) {
+      // [q[:7], qd[:7], x_i.pos[tips_arm], x_i.pos[object], x_i.pos[goal]]  (envs/pusher.py:224-237)
+      const int na = D.nu;
+      for (int i = lane; i < na; i += G) { o[i] = s[D.s_q + i]; o[na + i] = s[D.s_qd + i]; }
+      if (lane < 3) st3(o + 2 * na + 3 * lane, env_link_com(c, lane == 0 ? sp.tip_link : (lane == 1 ? sp.object_link : sp.target_link)));
     } else if (sp.kind == BXG_ENV_REACHER) {
       // [cos(theta), sin(theta), q[2:], tip_vel[:2], tip_pos - target_pos]  (envs/reacher.py:215-239)
       if (lane == 0) {
@@ -1775,6 +1871,10 @@ BXG_HD void env_epilogue(X& ex, const Ctx& c, const BxgEnvSpec& sp, const BxgEnv
     V3 tt = env_tip(c, sp) - ld3(s + D.s_x_pos + 3 * sp.target_link);
     ms[0] = -env_safe_norm(tt); ms[1] = -sq;
     reward = ms[0] + ms[1]; done = 0.f;
+  } else if (sp.kind == BXG_ENV_PUSHER) {
+    // reward = reward_dist + 0.1 * reward_ctrl + 0.5 * reward_near  (envs/pusher.py:212-215); before = (near, dist) of the old state
+    ms[0] = before.y; ms[1] = -sq; ms[2] = before.x;
+    reward = (ms[0] + 0.1f * ms[1]) + 0.5f * ms[2]; done = 0.f;
   } else if (sp.kind == BXG_ENV_STANDUP) {
     // uph_cost = (z - 0) / dt; reward = uph_cost + 1 - 0.01 * sum(action^2)  (envs/humanoidstandup.py:227-236)
     float uph_cost = (z - 0.f) / sp.env_dt;

@@ -46,6 +46,9 @@ struct Dims {
   int m_con_kind, m_con_gquat, m_con_half;   // plane-capsule end points: kind 1, geom quaternion [ncon,4], signed half length
   int m_con_anc_lo, m_con_anc_hi;        // [ncon] bitmask of dofs that move link_b
   int m_fluid;                           // [L, 8] per-link fluid constants (pack_fluid), only when `fluid`
+  int two_body;                          // some contact has kind 2 (capsule-capsule, link_a may move)
+  int m_con_la, m_con_apos, m_con_aquat, m_con_ahalf, m_con_arad;   // kind 2: link and shape of the first capsule
+  int m_con_anca_lo, m_con_anca_hi;      // [ncon] bitmask of dofs that move link_a
   int model_words;
   // ---- per-env slab ----
   int s_q, s_qd, s_act, s_tau, s_qfs, s_qfc, s_qdd;
@@ -188,6 +191,12 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
   d.fluid = m.enable_fluid ? 1 : 0;
   if (d.fluid && vid >= 0 && variant(vid).VC4 != 0) return "fluid forces are compiled into the generic kernel variant only";
   if (d.fluid) vid = 3;   // the specialised variants carry no fluid code: they stay exactly as profiled
+  d.two_body = 0;
+  for (int c = 0; c < m.ncon; ++c) if (m.con_kind && m.con_kind[c] == BXG_CON_CAPSULE_CAPSULE) d.two_body = 1;
+  // two-body contacts are compiled into variant 5 and the generic one only
+  auto two_body_ok = [](int k) { return variant(k).VC4 == 0 || variant(k).NC4 == 16; };
+  if (d.two_body && vid >= 0 && !two_body_ok(vid)) return "capsule-capsule contacts are compiled into kernel variants 3 and 5 only";
+  if (d.two_body && vid < 0) vid = variant_fits(variant(5), L, m.nv, d.nc) ? 5 : 3;
   if (vid < 0) {
     for (int k : kAutoOrder) { vid = k; if (variant_fits(variant(k), L, m.nv, d.nc)) break; }
   }
@@ -277,8 +286,11 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
   d.m_act_flo = put_f(m.act_force_lo, nu1); d.m_act_fhi = put_f(m.act_force_hi, nu1);
   d.m_act_bq = put_f(m.act_bias_q, nu1); d.m_act_bqd = put_f(m.act_bias_qd, nu1);
   for (int c = 0; c < m.ncon; ++c) {
+    const bool cc2 = m.con_kind && m.con_kind[c] == BXG_CON_CAPSULE_CAPSULE;
     if (m.con_link_b[c] < 0 || m.con_link_b[c] >= L) return "con_link_b out of range";
-    if (m.con_link_a[c] != -1) return "plane must be attached to the world (link_a == -1)";
+    if (!cc2 && m.con_link_a[c] != -1) return "plane must be attached to the world (link_a == -1)";
+    if (cc2 && (m.con_link_a[c] < -1 || m.con_link_a[c] >= L)) return "con_link_a out of range";
+    if (cc2 && (!m.con_a_pos || !m.con_a_quat || !m.con_a_half || !m.con_a_radius || !m.con_geom_quat || !m.con_half_len)) return "capsule-capsule contact without its capsule shapes";
   }
   d.m_con_lb = put_ip(m.con_link_b, m.ncon);
   d.m_con_ppos = put_f(m.con_plane_pos, m.ncon * 3); d.m_con_frame = put_f(m.con_frame, m.ncon * 9);
@@ -299,10 +311,10 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
     std::vector<float> gq((m.ncon > 0 ? m.ncon : 1) * 4, 0.f), half(m.ncon > 0 ? m.ncon : 1, 0.f);
     for (int c = 0; c < m.ncon; ++c) {
       kind[c] = m.con_kind ? m.con_kind[c] : BXG_CON_PLANE_SPHERE;
-      if (kind[c] != BXG_CON_PLANE_SPHERE && kind[c] != BXG_CON_PLANE_CAPSULE_END) return "unknown contact kind";
+      if (kind[c] != BXG_CON_PLANE_SPHERE && kind[c] != BXG_CON_PLANE_CAPSULE_END && kind[c] != BXG_CON_CAPSULE_CAPSULE) return "unknown contact kind";
       if (kind[c] == BXG_CON_PLANE_CAPSULE_END && (!m.con_geom_quat || !m.con_half_len)) return "capsule contact without con_geom_quat / con_half_len";
       gq[4 * c] = 1.f;
-      if (kind[c] == BXG_CON_PLANE_CAPSULE_END) { for (int k = 0; k < 4; ++k) gq[4 * c + k] = m.con_geom_quat[4 * c + k]; half[c] = m.con_half_len[c]; }
+      if (kind[c] != BXG_CON_PLANE_SPHERE) { for (int k = 0; k < 4; ++k) gq[4 * c + k] = m.con_geom_quat[4 * c + k]; half[c] = m.con_half_len[c]; }
     }
     d.m_con_kind = put_i(kind); d.m_con_gquat = put_f(gq.data(), (int)gq.size()); d.m_con_half = put_f(half.data(), (int)half.size());
   }
@@ -313,6 +325,19 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
     clo[c] = (int)(uint32_t)(mask & 0xffffffffu); chi[c] = (int)(uint32_t)(mask >> 32);
   }
   d.m_con_anc_lo = put_i(clo); d.m_con_anc_hi = put_i(chi);
+  d.m_con_la = d.m_con_apos = d.m_con_aquat = d.m_con_ahalf = d.m_con_arad = d.m_con_anca_lo = d.m_con_anca_hi = (int)b.size();
+  if (d.two_body) {
+    std::vector<int> la(m.ncon), alo(m.ncon, 0), ahi(m.ncon, 0);
+    for (int c = 0; c < m.ncon; ++c) {
+      la[c] = m.con_link_a[c];
+      uint64_t mask = 0;
+      for (int j = 0; j < m.nv; ++j) if (la[c] >= 0 && is_anc(dof_link[j], la[c])) mask |= (uint64_t)1 << j;
+      alo[c] = (int)(uint32_t)(mask & 0xffffffffu); ahi[c] = (int)(uint32_t)(mask >> 32);
+    }
+    d.m_con_la = put_i(la); d.m_con_anca_lo = put_i(alo); d.m_con_anca_hi = put_i(ahi);
+    d.m_con_apos = put_f(m.con_a_pos, m.ncon * 3); d.m_con_aquat = put_f(m.con_a_quat, m.ncon * 4);
+    d.m_con_ahalf = put_f(m.con_a_half, m.ncon); d.m_con_arad = put_f(m.con_a_radius, m.ncon);
+  }
   d.m_fluid = (int)b.size();
   if (d.fluid) {
     std::vector<float> fl(L * kFluidStride, 0.f);
@@ -400,6 +425,7 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
 BXG_MODEL_HD int env_obs_size(const Dims& D, const BxgEnvSpec& sp) {
   int base = (D.nq - sp.obs_skip) + D.nv;
   if (sp.kind == BXG_ENV_DOUBLE_CARTPOLE) return 1 + 2 * (D.nq - 1) + D.nv;   // q[0], sin, cos of q[1:], qd
+  if (sp.kind == BXG_ENV_PUSHER) return 2 * D.nu + 9;                           // q[:nu], qd[:nu], three centres of mass
   if (sp.kind == BXG_ENV_REACHER) return 4 + (D.nq - 2) + 2 + 3;               // cos, sin of q[:2], q[2:], tip_vel[:2], tip - target
   return (sp.kind == BXG_ENV_COM_VELOCITY || sp.kind == BXG_ENV_STANDUP) ? base + 10 * D.L + 6 * D.L + D.nv : base;
 }

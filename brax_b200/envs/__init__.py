@@ -1,17 +1,17 @@
 """Environments in scope (reference `brax/envs/__init__.py:35-107`): ant, humanoid, halfcheetah, hopper, walker2d,
-inverted_pendulum, inverted_double_pendulum, reacher, swimmer, humanoidstandup (not yet: pusher, whose geoms collide with each other; fast is a toy without physics)."""
+inverted_pendulum, inverted_double_pendulum, reacher, swimmer, humanoidstandup, pusher (`fast` is a toy without physics and is not mirrored)."""
 from typing import Optional
 
 from brax_b200.envs.ant import Ant
 from brax_b200.envs.base import FusedEnv, State
-from brax_b200.envs.classic import HumanoidStandup, InvertedDoublePendulum, InvertedPendulum, Reacher, Swimmer
+from brax_b200.envs.classic import HumanoidStandup, InvertedDoublePendulum, InvertedPendulum, Pusher, Reacher, Swimmer
 from brax_b200.envs.half_cheetah import Halfcheetah
 from brax_b200.envs.hopper import Hopper, Walker2d
 from brax_b200.envs.humanoid import Humanoid
 
 _envs = {'ant': Ant, 'humanoid': Humanoid, 'halfcheetah': Halfcheetah, 'hopper': Hopper, 'walker2d': Walker2d,
          'inverted_pendulum': InvertedPendulum, 'inverted_double_pendulum': InvertedDoublePendulum,
-         'reacher': Reacher, 'swimmer': Swimmer, 'humanoidstandup': HumanoidStandup}
+         'reacher': Reacher, 'swimmer': Swimmer, 'humanoidstandup': HumanoidStandup, 'pusher': Pusher}
 
 
 def get_environment(env_name: str, **kwargs) -> FusedEnv:

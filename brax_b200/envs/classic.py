@@ -1,5 +1,5 @@
 """The small classic-control envs (reference `brax/envs/{inverted_pendulum, inverted_double_pendulum,
-reacher, swimmer}.py`, backend='generalized') and HumanoidStandup.
+reacher, swimmer}.py`, backend='generalized'), HumanoidStandup and Pusher.
 
 No contacts; slide joints (the carts), a 2-dof link (Reacher's target) and, for Swimmer, the fluid
 forces of `brax/fluid.py` (compiled into the generic kernel variant).  Each env has its own kind in
@@ -155,4 +155,34 @@ class HumanoidStandup(FusedEnv):
     init_q = torch.as_tensor(np.asarray(self.sys.init_q, np.float32), device=device)
     q = init_q[None] + sharding.uniform(env_begin, n, self.sys.nq, seed, 1, -0.01, 0.01, device)
     qd = sharding.uniform(env_begin, n, self.sys.nv, seed, 2, -0.01, 0.01, device)
+    return q.contiguous(), qd.contiguous()
+
+
+class Pusher(FusedEnv):
+  """Reference envs/pusher.py:143-237: a 7-dof arm pushes a capsule towards a goal on a table.  The
+  wrist capsules collide with the table (plane-capsule) and with the object (capsule-capsule, both
+  links moving).  Reward (from the state BEFORE the step): -|object - goal| - 0.1 * sum(action^2)
+  - 0.5 * |object - tips_arm|."""
+
+  def __init__(self, backend='generalized', n_frames=5, **kwargs):
+    _check_backend(backend)
+    sys = envs_assets.load('pusher')
+    names = list(sys.link_names)
+    spec = _spec(native.ENV_PUSHER)
+    # tips_arm is fused into r_wrist_roll_link; the reference uses the parent r_wrist_flex_link (pusher.py:158-160)
+    spec.tip_link, spec.object_link, spec.target_link = names.index('r_wrist_flex_link'), names.index('object'), names.index('goal')
+    super().__init__(sys, spec, ('reward_dist', 'reward_ctrl', 'reward_near'), n_frames, **kwargs)
+
+  def _reset_q_qd(self, env_begin, n, seed, device):
+    # cylinder_pos = [U(-0.3, -1e-6), U(-0.2, 0.2)], pushed out to >= 0.17 from the goal at the origin;
+    # q[-4:] = [cylinder_pos, goal_pos]; qd = U(-0.005, 0.005), qd[-4:] = 0   (pusher.py:166-188)
+    q = torch.as_tensor(np.asarray(self.sys.init_q, np.float32), device=device)[None].repeat(n, 1)
+    cyl = torch.cat([sharding.uniform(env_begin, n, 1, seed, 1, -0.3, -1e-6, device),
+                     sharding.uniform(env_begin, n, 1, seed, 2, -0.2, 0.2, device)], 1)
+    norm = torch.linalg.norm(cyl, dim=1, keepdim=True)
+    cyl = cyl * torch.where(norm < 0.17, 0.17 / norm, torch.ones_like(norm))
+    q[:, -4:-2] = cyl
+    q[:, -2:] = 0.0
+    qd = sharding.uniform(env_begin, n, self.sys.nv, seed, 3, -0.005, 0.005, device)
+    qd[:, -4:] = 0.0
     return q.contiguous(), qd.contiguous()

@@ -53,6 +53,7 @@ class ModelDesc(ctypes.Structure):
       ('con_solref', _pf), ('con_solimp', _pf),
       ('con_kind', _pi), ('con_geom_quat', _pf), ('con_half_len', _pf),
       ('enable_fluid', _i32), ('viscosity', _f32), ('density', _f32),
+      ('con_a_pos', _pf), ('con_a_quat', _pf), ('con_a_half', _pf), ('con_a_radius', _pf),
   ]
 
 
@@ -72,6 +73,7 @@ ENV_DOUBLE_CARTPOLE = 5
 ENV_REACHER = 6
 ENV_SWIMMER = 7
 ENV_STANDUP = 8
+ENV_PUSHER = 9
 ENV_NUM_METRICS = 10
 
 
@@ -82,7 +84,7 @@ class EnvSpecC(ctypes.Structure):
               ('healthy_z_min', _f32), ('healthy_z_max', _f32), ('env_dt', _f32),
               ('healthy_angle_min', _f32), ('healthy_angle_max', _f32),
               ('healthy_state_min', _f32), ('healthy_state_max', _f32),
-              ('tip_link', _i32), ('target_link', _i32), ('tip_pos', _f32 * 3)]
+              ('tip_link', _i32), ('target_link', _i32), ('tip_pos', _f32 * 3), ('object_link', _i32)]
 
 
 class EnvIOC(ctypes.Structure):
@@ -151,6 +153,7 @@ def make_desc(sys, minv_mode: int = MINV_NEWTON_SCHULZ) -> Tuple[ModelDesc, list
   d.con_kind = ip(cp.kind); d.con_geom_quat = fp(cp.geom_quat); d.con_half_len = fp(cp.half_len)
   d.enable_fluid = int(bool(sys.enable_fluid))
   d.viscosity, d.density = float(np.asarray(sys.viscosity)), float(np.asarray(sys.density))
+  d.con_a_pos = fp(cp.a_pos); d.con_a_quat = fp(cp.a_quat); d.con_a_half = fp(cp.a_half); d.con_a_radius = fp(cp.a_radius)
   return d, keep
 
 

@@ -59,6 +59,7 @@ enum {
 
 #define BXG_CON_PLANE_SPHERE 0
 #define BXG_CON_PLANE_CAPSULE_END 1
+#define BXG_CON_CAPSULE_CAPSULE 2   /* one contact between the closest points of two capsules; link_a may move */
 
 /* Model constants = the fields of brax.base.System the path reads
  * (brax/base.py:415-540).  Host pointers. */
@@ -103,9 +104,9 @@ typedef struct BxgModelDesc {
   const float* act_force_hi;
   const float* act_bias_q;
   const float* act_bias_qd;
-  /* plane-sphere / plane-capsule contacts [ncon] (brax/contact.py:28-67 + mjx collision).
+  /* plane-sphere / plane-capsule / capsule-capsule contacts [ncon] (brax/contact.py:28-67 + mjx collision).
    * A capsule contributes two contacts (its end spheres, +axis first). */
-  const int32_t* con_link_a;     /* plane link (-1 = world) */
+  const int32_t* con_link_a;     /* plane link (-1 = world); kind 2: link of the first capsule */
   const int32_t* con_link_b;     /* sphere / capsule link */
   const float* con_plane_pos;    /* [ncon,3] world */
   const float* con_frame;        /* [ncon,3,3] rows normal,t1,t2 (capsules: t1, t2 follow the axis at run time) */
@@ -120,6 +121,12 @@ typedef struct BxgModelDesc {
   /* fluid forces on the links' inertia boxes (brax/fluid.py:24-91, dynamics.py:198-211) */
   int32_t enable_fluid;          /* sys.enable_fluid = viscosity > 0 or density > 0 (io/mjcf.py:467) */
   float viscosity, density;      /* sys.viscosity, sys.density */
+  /* capsule-capsule pairs (kind 2): geom1's shape in the frame of con_link_a (which may be a moving link);
+   * geom2's is con_sphere_pos / con_geom_quat / con_half_len / con_radius.  NULL when no pair has kind 2. */
+  const float* con_a_pos;        /* [ncon,3] */
+  const float* con_a_quat;       /* [ncon,4] */
+  const float* con_a_half;       /* [ncon] half length */
+  const float* con_a_radius;     /* [ncon] */
 } BxgModelDesc;
 
 /* The generalized State (brax/generalized/base.py:25-92 + brax/base.py:396-412)
@@ -183,6 +190,10 @@ enum {
                                  reward = -|tip - target| - sum(action^2) */
   BXG_ENV_SWIMMER = 7,        /* Swimmer (envs/swimmer.py:157-194): velocity of q[:2]; obs = [q[skip:], qd];
                                  reward = forward_reward_weight * vx - ctrl_cost_weight * sum(action^2) */
+  BXG_ENV_PUSHER = 9,         /* Pusher (envs/pusher.py:195-237): action rescaled to the ctrl range; reward from the
+                                 PRE-step centres of mass of tip_link, object_link, target_link:
+                                 -|obj - goal| - 0.1 * sum(action^2) - 0.5 * |obj - tip|;
+                                 obs = [q[:nu], qd[:nu], com(tip), com(object), com(goal)] of the post-step state */
   BXG_ENV_STANDUP = 8         /* HumanoidStandup (envs/humanoidstandup.py:220-274): action rescaled to the ctrl range;
                                  obs as COM_VELOCITY; reward = z of link 0 / env_dt + healthy_reward
                                  - ctrl_cost_weight * sum(action^2); never done */
@@ -203,6 +214,7 @@ typedef struct BxgEnvSpec {
   float healthy_state_min, healthy_state_max;   /* BXG_ENV_PLANAR: range of every entry of [q[2:], qd] */
   int32_t tip_link, target_link;     /* BXG_ENV_DOUBLE_CARTPOLE / BXG_ENV_REACHER */
   float tip_pos[3];                  /* tip in the frame of tip_link */
+  int32_t object_link;               /* BXG_ENV_PUSHER */
 } BxgEnvSpec;
 
 /* Per-env arrays, device pointers.  metrics order:
@@ -214,6 +226,7 @@ typedef struct BxgEnvSpec {
  *  CARTPOLE, DOUBLE_CARTPOLE: none
  *  REACHER:       reward_dist, reward_ctrl
  *  STANDUP:       reward_linup, reward_quadctrl
+ *  PUSHER:        reward_dist, reward_ctrl, reward_near
  *  SWIMMER:       reward_fwd, -, reward_ctrl, -, x_position, y_position, distance_from_origin,
  *                 x_velocity, y_velocity, forward_reward (always 0: swimmer.py never updates it)  */
 typedef struct BxgEnvIO {

@@ -95,6 +95,8 @@ typedef struct {
   real con_half_len[MAXCON];         /* signed: end point = centre + axis * half_len */
   int32_t enable_fluid, pad2;        /* sys.enable_fluid (io/mjcf.py:467) */
   real viscosity, density;           /* sys.viscosity, sys.density */
+  /* capsule-capsule pairs (con_kind 2): shape of geom1 in the frame of link_a */
+  real con_a_pos[MAXCON][3], con_a_quat[MAXCON][4], con_a_half[MAXCON], con_a_radius[MAXCON];
 } OrcModel;
 
 /* per-environment working state (reference generalized/base.py:25-92) */
@@ -517,7 +519,83 @@ static void imp_aref(const real* prm, real pos, real vel, real* imp_out, real* a
  * geom pose as brax/contact.py:48-53: pos = x.pos + rotate(geom_pos, x.rot),
  * mat = quat_to_3x3(x.rot * geom_quat).  No reference test pins plane-capsule numbers
  * (parity unpinned for this pair type). */
+/* mjx math.normalize_with_norm: x / (n + 1e-6 * (n == 0)), n the safe norm */
+static real normalize_with_norm(real* x) {
+  real n = safe_norm(x, 3);
+  real d = n + (real)1e-6 * (n == 0 ? (real)1 : (real)0);
+  for (int i = 0; i < 3; i++) x[i] = x[i] / d;
+  return n;
+}
+/* mjx math.closest_segment_point */
+static void closest_segment_point(const real* a, const real* b, const real* pt, real* o) {
+  real ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, pa[3] = {pt[0] - a[0], pt[1] - a[1], pt[2] - a[2]};
+  real t = dot3(pa, ab) / (dot3(ab, ab) + (real)1e-6);
+  t = r_max((real)0, r_min(t, (real)1));
+  for (int i = 0; i < 3; i++) o[i] = a[i] + t * ab[i];
+}
+/* mjx math.closest_segment_to_segment_points */
+static void closest_segment_to_segment_points(const real* a0, const real* a1, const real* b0, const real* b1, real* best_a, real* best_b) {
+  real dir_a[3], dir_b[3], a_mid[3], b_mid[3], trans[3];
+  for (int i = 0; i < 3; i++) { dir_a[i] = a1[i] - a0[i]; dir_b[i] = b1[i] - b0[i]; }
+  real len_a = normalize_with_norm(dir_a), len_b = normalize_with_norm(dir_b);
+  real half_a = len_a * (real)0.5, half_b = len_b * (real)0.5;
+  for (int i = 0; i < 3; i++) { a_mid[i] = a0[i] + dir_a[i] * half_a; b_mid[i] = b0[i] + dir_b[i] * half_b; trans[i] = a_mid[i] - b_mid[i]; }
+  real dab = dot3(dir_a, dir_b), dat = dot3(dir_a, trans), dbt = dot3(dir_b, trans);
+  real denom = 1 - dab * dab;
+  real orig_t_a = (-dat + dab * dbt) / (denom + (real)1e-6);
+  real orig_t_b = dbt + orig_t_a * dab;
+  real t_a = r_max(-half_a, r_min(orig_t_a, half_a)), t_b = r_max(-half_b, r_min(orig_t_b, half_b));
+  real new_a[3], new_b[3], u[3], v[3];
+  for (int i = 0; i < 3; i++) { best_a[i] = a_mid[i] + dir_a[i] * t_a; best_b[i] = b_mid[i] + dir_b[i] * t_b; }
+  closest_segment_point(a0, a1, best_b, new_a);
+  closest_segment_point(b0, b1, best_a, new_b);
+  for (int i = 0; i < 3; i++) { u[i] = new_a[i] - best_b[i]; v[i] = best_a[i] - new_b[i]; }
+  if (dot3(u, u) < dot3(v, v)) { for (int i = 0; i < 3; i++) best_a[i] = new_a[i]; }
+  else { for (int i = 0; i < 3; i++) best_b[i] = new_b[i]; }
+}
+/* centre and axis (z column of the geom's world matrix) of a capsule attached to `link` */
+static void capsule_world(const Env* e, int link, const real* gpos, const real* gquat, real* centre, real* axis) {
+  real t[3], q[4], mat[9];
+  static const real world_pos[3] = {0, 0, 0}, world_rot[4] = {1, 0, 0, 0};   /* contact.py:48-53 appends the world at index -1 */
+  const real* xp = link >= 0 ? e->x_pos[link] : world_pos;
+  const real* xr = link >= 0 ? e->x_rot[link] : world_rot;
+  rotate(gpos, xr, t);
+  for (int i = 0; i < 3; i++) centre[i] = xp[i] + t[i];
+  quat_mul(xr, gquat, q);
+  quat_to_3x3(q, mat);
+  axis[0] = mat[2]; axis[1] = mat[5]; axis[2] = mat[8];
+}
+/* mjx collision_primitive.capsule_capsule -> _sphere_sphere on the closest points; frame = math.make_frame(n) */
+static void contact_capsule_capsule(const OrcModel* m, const Env* e, int c, real* dist, real* pos, real* frame) {
+  real ca[3], xa[3], cb[3], xb[3], a0[3], a1[3], b0[3], b1[3], pa[3], pb[3], n[3], b[3];
+  capsule_world(e, m->con_link_a[c], m->con_a_pos[c], m->con_a_quat[c], ca, xa);
+  capsule_world(e, m->con_link_b[c], m->con_sphere_pos[c], m->con_geom_quat[c], cb, xb);
+  for (int i = 0; i < 3; i++) {
+    real sa = xa[i] * m->con_a_half[c], sb = xb[i] * m->con_half_len[c];
+    a0[i] = ca[i] - sa; a1[i] = ca[i] + sa; b0[i] = cb[i] - sb; b1[i] = cb[i] + sb;
+  }
+  closest_segment_to_segment_points(a0, a1, b0, b1, pa, pb);
+  for (int i = 0; i < 3; i++) n[i] = pb[i] - pa[i];
+  real d = normalize_with_norm(n);
+  if (d == 0) { n[0] = 1; n[1] = 0; n[2] = 0; }
+  real r1 = m->con_a_radius[c], r2 = m->con_radius[c];
+  d = d - (r1 + r2);
+  *dist = d;
+  for (int i = 0; i < 3; i++) pos[i] = pa[i] + n[i] * (r1 + d * (real)0.5);
+  /* make_frame: a = normalize(n); b = y (or z when a is near +-y), made orthogonal to a and normalised */
+  real a[3] = {n[0], n[1], n[2]};
+  normalize(a, 3);
+  int use_y = (real)-0.5 < a[1] && a[1] < (real)0.5;
+  b[0] = 0; b[1] = use_y ? 1 : 0; b[2] = use_y ? 0 : 1;
+  real ab = dot3(a, b);
+  for (int i = 0; i < 3; i++) b[i] = b[i] - a[i] * ab;
+  normalize(b, 3);
+  for (int i = 0; i < 3; i++) { frame[i] = a[i]; frame[3 + i] = b[i]; }
+  cross3(a, b, frame + 6);
+}
+
 static void contact_get(const OrcModel* m, const Env* e, int c, real* dist, real* pos, real* frame) {
+  if (m->con_kind[c] == 2) { contact_capsule_capsule(m, e, c, dist, pos, frame); return; }
   int lb = m->con_link_b[c];
   real t[3], sp[3], d[3];
   rotate(m->con_sphere_pos[c], e->x_rot[lb], t);

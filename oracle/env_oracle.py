@@ -13,6 +13,7 @@ tests/test_reference_golden.py).  Follows, statement by statement, float32:
   brax/envs/reacher.py:199-239        Reacher.step / _get_obs
   brax/envs/swimmer.py:157-194        Swimmer.step / _get_obs
   brax/envs/humanoidstandup.py:220-274  HumanoidStandup.step / _get_obs
+  brax/envs/pusher.py:195-237         Pusher.step / _get_obs
   brax/envs/wrappers/training.py:98-158  EpisodeWrapper.step, AutoResetWrapper.step
   brax/actuator.py:23-57              to_tau (for Humanoid's qfrc_actuator)
 """
@@ -83,7 +84,20 @@ class EnvOracle:
   def _tip(self, st, link, p):
     return (st['x_pos'][:, link] + _rotate(np.asarray(p, f32)[None], st['x_rot'][:, link])).astype(f32)
 
+  def _pusher_links(self):
+    names = list(self.sys.link_names)
+    return names.index('r_wrist_flex_link'), names.index('object'), names.index('goal')
+
+  @staticmethod
+  def _safe_norm(v):
+    zero = np.all(np.abs(v) <= 1e-8, axis=1)
+    return np.where(zero, f32(0), np.sqrt(np.sum(np.where(zero[:, None], f32(1), v) ** 2, -1))).astype(f32)
+
   def obs(self, st, action):
+    if self.kind == 'pusher':   # [q[:7], qd[:7], x_i.pos[tips_arm], x_i.pos[object], x_i.pos[goal]]
+      tip, obj, goal = self._pusher_links()
+      x_i = (st['x_pos'] + _rotate(self.ipos[None], st['x_rot'])).astype(f32)
+      return np.concatenate([st['q'][:, :7], st['qd'][:, :7], x_i[:, tip], x_i[:, obj], x_i[:, goal]], 1).astype(f32)
     if self.kind == 'inverted_double_pendulum':   # [q[:1], sin(q[1:]), cos(q[1:]), clip(qd, -10, 10)]
       q = st['q']
       return np.concatenate([q[:, :1], np.sin(q[:, 1:]), np.cos(q[:, 1:]), np.clip(st['qd'], f32(-10), f32(10))], 1).astype(f32)
@@ -126,6 +140,20 @@ class EnvOracle:
     action = np.asarray(action, f32)
     if self.classic:
       return self._classic_step(ps0, action)
+    if self.kind == 'pusher':
+      lo, hi = self.sys.actuator.ctrl_range[:, 0], self.sys.actuator.ctrl_range[:, 1]
+      action = ((action + f32(1)) * (hi - lo) * f32(0.5) + lo).astype(f32)
+      ps = {k: v.copy() for k, v in ps0.items()}
+      self.o.step(ps, action, self.n_frames)
+      tip, obj, goal = self._pusher_links()
+      x_i = (ps0['x_pos'] + _rotate(self.ipos[None], ps0['x_rot'])).astype(f32)   # the PRE-step state (pusher.py:204-207)
+      near = -self._safe_norm(x_i[:, obj] - x_i[:, tip])
+      dist = -self._safe_norm(x_i[:, obj] - x_i[:, goal])
+      sq = np.zeros(action.shape[0], f32)
+      for a in range(action.shape[1]):
+        sq = (sq + action[:, a] * action[:, a]).astype(f32)
+      reward = ((dist + f32(0.1) * -sq).astype(f32) + f32(0.5) * near).astype(f32)
+      return ps, self.obs(ps, action), reward, np.zeros_like(reward), {'reward_dist': dist, 'reward_ctrl': -sq, 'reward_near': near}
     if self.kind == 'humanoidstandup':
       lo, hi = self.sys.actuator.ctrl_range[:, 0], self.sys.actuator.ctrl_range[:, 1]
       action = ((action + f32(1)) * (hi - lo) * f32(0.5) + lo).astype(f32)

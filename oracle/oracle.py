@@ -68,6 +68,7 @@ def _model_struct(ct):
       ('con_solimp', ct * (MAXCON * 5)),
       ('con_kind', i32 * MAXCON), ('con_geom_quat', ct * (MAXCON * 4)), ('con_half_len', ct * MAXCON),
       ('enable_fluid', i32), ('pad2', i32), ('viscosity', ct), ('density', ct),
+      ('con_a_pos', ct * (MAXCON * 3)), ('con_a_quat', ct * (MAXCON * 4)), ('con_a_half', ct * MAXCON), ('con_a_radius', ct * MAXCON),
   ]
 
 
@@ -164,6 +165,7 @@ class Oracle:
       put('con_sphere_pos', cp.sphere_pos); put('con_radius', cp.radius)
       put('con_friction', cp.friction); put('con_solref', cp.solref); put('con_solimp', cp.solimp)
       put('con_kind', cp.kind); put('con_geom_quat', cp.geom_quat); put('con_half_len', cp.half_len)
+      put('con_a_pos', cp.a_pos); put('con_a_quat', cp.a_quat); put('con_a_half', cp.a_half); put('con_a_radius', cp.a_radius)
 
   # ---------------------------------------------------------------- state
   def shapes(self) -> Dict[str, tuple]:

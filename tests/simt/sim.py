@@ -84,6 +84,8 @@ class SimEnv:
     self.obs_size = base + 16 * L + nv if env.spec.kind in (native.ENV_COM_VELOCITY, native.ENV_STANDUP) else base
     if env.spec.kind == native.ENV_DOUBLE_CARTPOLE:
       self.obs_size = 1 + 2 * (nq - 1) + nv
+    if env.spec.kind == native.ENV_PUSHER:
+      self.obs_size = 2 * env.sys.nu + 9
     if env.spec.kind == native.ENV_REACHER:
       self.obs_size = 4 + (nq - 2) + 2 + 3
 

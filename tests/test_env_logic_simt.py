@@ -4,11 +4,12 @@ restatement of the reference envs (oracle/env_oracle.py)."""
 import numpy as np
 import pytest
 
+from oracle import oracle as O
 from oracle.env_oracle import EnvOracle
 from tests.simt.sim import SimEnv
 
 
-CLASSIC = ('inverted_pendulum', 'inverted_double_pendulum', 'reacher', 'swimmer', 'humanoidstandup')
+CLASSIC = ('inverted_pendulum', 'inverted_double_pendulum', 'reacher', 'swimmer', 'humanoidstandup', 'pusher')
 
 
 class _EnvStub:
@@ -31,7 +32,7 @@ class _EnvStub:
       sp.healthy_state_min, sp.healthy_state_max = (-100.0, 100.0) if name == 'hopper' else (-3.0e38, 3.0e38)
     elif name in CLASSIC:
       sp.kind = {'inverted_pendulum': native.ENV_CARTPOLE, 'inverted_double_pendulum': native.ENV_DOUBLE_CARTPOLE,
-                 'reacher': native.ENV_REACHER, 'swimmer': native.ENV_SWIMMER, 'humanoidstandup': native.ENV_STANDUP}[name]
+                 'reacher': native.ENV_REACHER, 'swimmer': native.ENV_SWIMMER, 'humanoidstandup': native.ENV_STANDUP, 'pusher': native.ENV_PUSHER}[name]
       sp.forward_reward_weight, sp.ctrl_cost_weight, sp.healthy_reward = 1.0, (1e-4 if name == 'swimmer' else 0.0), 0.0
       sp.healthy_z_min, sp.healthy_z_max, sp.healthy_angle_max = -3.0e38, 3.0e38, 0.2
       if name == 'inverted_double_pendulum':
@@ -42,11 +43,14 @@ class _EnvStub:
         sp.tip_pos[0] = 0.11
       if name == 'humanoidstandup':
         sp.ctrl_cost_weight, sp.healthy_reward = 0.01, 1.0
+      if name == 'pusher':
+        names = list(self.sys.link_names)
+        sp.tip_link, sp.object_link, sp.target_link = names.index('r_wrist_flex_link'), names.index('object'), names.index('goal')
     else:
       sp.kind, sp.forward_reward_weight, sp.ctrl_cost_weight, sp.healthy_reward = native.ENV_COM_VELOCITY, 1.25, 0.1, 5.0
       sp.healthy_z_min, sp.healthy_z_max = 1.0, 2.0
     sp.obs_skip, sp.terminate_when_unhealthy = {'halfcheetah': (1, 0), 'hopper': (1, 1), 'walker2d': (1, 1), 'inverted_pendulum': (0, 0),
-                                                'inverted_double_pendulum': (0, 0), 'reacher': (0, 0), 'swimmer': (2, 0), 'humanoidstandup': (2, 0)}.get(name, (2, 1))
+                                                'inverted_double_pendulum': (0, 0), 'reacher': (0, 0), 'swimmer': (2, 0), 'humanoidstandup': (2, 0), 'pusher': (0, 0)}.get(name, (2, 1))
     sp.episode_length = episode_length or 0
     self.n_frames = 4 if name in ('hopper', 'walker2d', 'swimmer') else (2 if name in CLASSIC[:3] else 5)
     sp.env_dt = float(np.float32(self.sys.opt.timestep) * np.float32(self.n_frames))
@@ -56,7 +60,7 @@ class _EnvStub:
 def _oracle(name, sys, **kw):
   if name in CLASSIC:
     return EnvOracle(sys, name, ctrl_cost_weight=1e-4 if name == 'swimmer' else 0.0,
-                     n_frames={'swimmer': 4, 'humanoidstandup': 5}.get(name, 2), **kw)
+                     n_frames={'swimmer': 4, 'humanoidstandup': 5, 'pusher': 5}.get(name, 2), **kw)
   if name == 'ant':
     return EnvOracle(sys, 'ant', ctrl_cost_weight=0.5, healthy_reward=1.0, healthy_z_range=(0.2, 1.0), **kw)
   if name == 'hopper':
@@ -94,7 +98,7 @@ def test_reset_obs_and_step_outputs(name):
     qd = (noise * rng0.standard_normal((n, stub.sys.nv))).astype(np.float32)
   elif name in CLASSIC:   # reset noise of the reference envs; one pendulum env starts tipped over (terminates at once)
     rng0 = np.random.default_rng(3)
-    noise = {'inverted_pendulum': 0.01, 'inverted_double_pendulum': 0.01, 'reacher': 0.1, 'swimmer': 0.1, 'humanoidstandup': 0.01}[name]
+    noise = {'inverted_pendulum': 0.01, 'inverted_double_pendulum': 0.01, 'reacher': 0.1, 'swimmer': 0.1, 'humanoidstandup': 0.01, 'pusher': 0.005}[name]
     q = (np.asarray(stub.sys.init_q)[None] + rng0.uniform(-noise, noise, (n, stub.sys.nq))).astype(np.float32)
     qd = rng0.uniform(-noise, noise, (n, stub.sys.nv)).astype(np.float32)
     if name == 'inverted_pendulum':
@@ -103,6 +107,10 @@ def test_reset_obs_and_step_outputs(name):
       q[0, 1] = 1.5
     if name == 'reacher':
       qd[:, 2:] = 0.0
+    if name == 'pusher':   # arm lowered onto the table, the object next to the wrist (both contact kinds active for some envs)
+      q[:, 1] = 0.40 + 0.05 * rng0.uniform(size=n)
+      w = O.Oracle(stub.sys, np.float32).init(q, qd)['x_pos'][:, 6]
+      q[:, 7], q[:, 8] = w[:, 1] + 0.07, w[:, 0] - 0.40
   else:
     _, q, qd = workloads.reset(name, 0, n, 0, 'cpu')
     q, qd = q.numpy(), qd.numpy()

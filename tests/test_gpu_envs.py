@@ -6,14 +6,14 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-CLASSIC = ('inverted_pendulum', 'inverted_double_pendulum', 'reacher', 'swimmer', 'humanoidstandup')
+CLASSIC = ('inverted_pendulum', 'inverted_double_pendulum', 'reacher', 'swimmer', 'humanoidstandup', 'pusher')
 
 
 def _oracle(name, sys, **kw):
   from oracle.env_oracle import EnvOracle
   if name in CLASSIC:
     return EnvOracle(sys, name, ctrl_cost_weight=1e-4 if name == 'swimmer' else 0.0,
-                     n_frames={'swimmer': 4, 'humanoidstandup': 5}.get(name, 2), **kw)
+                     n_frames={'swimmer': 4, 'humanoidstandup': 5, 'pusher': 5}.get(name, 2), **kw)
   if name == 'ant':
     return EnvOracle(sys, 'ant', ctrl_cost_weight=0.5, healthy_reward=1.0, healthy_z_range=(0.2, 1.0), **kw)
   if name == 'hopper':
@@ -49,7 +49,7 @@ def test_env_reset_and_step_match_reference_restatement(name):
   env = envs.create(name, episode_length=1000, auto_reset=True, batch_size=n)
   assert env.action_size == env.sys.nu and env.observation_size == {
       'ant': 27, 'humanoid': 244, 'halfcheetah': 17, 'hopper': 11, 'walker2d': 17, 'inverted_pendulum': 4,
-      'inverted_double_pendulum': 8, 'reacher': 11, 'swimmer': 8, 'humanoidstandup': 244}[name]
+      'inverted_double_pendulum': 8, 'reacher': 11, 'swimmer': 8, 'humanoidstandup': 244, 'pusher': 23}[name]
   st = env.reset(0)
   dev = st.obs.device
   orc = _oracle(name, env.sys, episode_length=1000, auto_reset=True)

@@ -2,7 +2,7 @@
 
 Run in the build container (needs /root/reference for the MJCF sources):
     python tools/gen_assets.py
-Writes brax_b200/assets/{ant,humanoid,halfcheetah,hopper,walker2d,humanoidstandup,inverted_pendulum,inverted_double_pendulum,
+Writes brax_b200/assets/{ant,humanoid,halfcheetah,hopper,walker2d,humanoidstandup,pusher,inverted_pendulum,inverted_double_pendulum,
 reacher,swimmer}.json and the small pendulum fixtures under tests/golden/ that the known-answer tests use.  The XML files themselves
 are not copied into this repository; only the numbers the hot path consumes.
 """
@@ -21,6 +21,7 @@ ASSETS = {
     'halfcheetah': f'{REF}/envs/assets/half_cheetah.xml',
     'hopper': f'{REF}/envs/assets/hopper.xml',
     'walker2d': f'{REF}/envs/assets/walker2d.xml',
+    'pusher': f'{REF}/envs/assets/pusher.xml',   # capsule-capsule pairs between moving links
     'humanoidstandup': f'{REF}/envs/assets/humanoidstandup.xml',   # 15 contacts: 77 constraint rows (generic kernel variant)
 }
 FIXTURES = ['triple_pendulum', 'single_pendulum_motor', 'single_pendulum_position',

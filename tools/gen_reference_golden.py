@@ -95,7 +95,7 @@ LEAVES = {   # our flat State field -> accessor on the reference State
 
 # model -> (envs, steps, how far to drop the root towards the floor so that contacts are active)
 CASES = {'ant': (3, 6, 0.0), 'humanoid': (2, 6, 0.0), 'halfcheetah': (2, 5, 0.35), 'hopper': (2, 5, 0.04),
-         'walker2d': (2, 5, 0.05), 'humanoidstandup': (2, 4, 0.0), 'triple_pendulum_motor': (2, 4, 0.0), 'inverted_pendulum': (2, 4, 0.0),
+         'walker2d': (2, 5, 0.05), 'humanoidstandup': (2, 4, 0.0), 'pusher': (2, 5, 0.0), 'triple_pendulum_motor': (2, 4, 0.0), 'inverted_pendulum': (2, 4, 0.0),
          'inverted_double_pendulum': (2, 4, 0.0), 'reacher': (2, 4, 0.0), 'swimmer': (2, 4, 0.0), 'two_trees': (2, 6, 0.0)}
 
 
@@ -121,7 +121,7 @@ def inputs(s, name, n, steps, drop, seed=0):
 
 
 def load(name):
-  if name in ('ant', 'humanoid', 'halfcheetah', 'hopper', 'walker2d', 'humanoidstandup', 'inverted_pendulum', 'inverted_double_pendulum',
+  if name in ('ant', 'humanoid', 'halfcheetah', 'hopper', 'walker2d', 'humanoidstandup', 'pusher', 'inverted_pendulum', 'inverted_double_pendulum',
               'reacher', 'swimmer'):
     return envs_assets.load(name)
   if name == 'two_trees':      # our own synthetic model (tests/synthetic_models.py): several free roots
@@ -133,7 +133,7 @@ def load(name):
 
 
 ENV_XML = {'ant.xml': 'ant', 'humanoid.xml': 'humanoid', 'half_cheetah.xml': 'halfcheetah', 'hopper.xml': 'hopper',
-           'walker2d.xml': 'walker2d', 'humanoidstandup.xml': 'humanoidstandup', 'inverted_pendulum.xml': 'inverted_pendulum',
+           'walker2d.xml': 'walker2d', 'humanoidstandup.xml': 'humanoidstandup', 'pusher.xml': 'pusher', 'inverted_pendulum.xml': 'inverted_pendulum',
            'inverted_double_pendulum.xml': 'inverted_double_pendulum', 'reacher.xml': 'reacher', 'swimmer.xml': 'swimmer'}
 
 
@@ -150,7 +150,7 @@ def env_golden(only=None):
   mjcf_stub.load = _mjcf_load
   from brax.envs import ant as ref_ant, half_cheetah as ref_hc, humanoid as ref_hum   # the reference
   from brax.envs import hopper as ref_hop, walker2d as ref_walk                       # the reference
-  from brax.envs import humanoidstandup as ref_hs
+  from brax.envs import humanoidstandup as ref_hs, pusher as ref_pu
   from brax.envs import inverted_pendulum as ref_ip, inverted_double_pendulum as ref_idp, reacher as ref_re, swimmer as ref_sw
   from brax.envs.wrappers import training as ref_wrap                                 # the reference
   assert ref_wrap.__file__.startswith('/root/reference/')
@@ -158,13 +158,26 @@ def env_golden(only=None):
            'hopper': (ref_hop.Hopper, 4, 6, 4), 'walker2d': (ref_walk.Walker2d, 3, 5, 4),
            'inverted_pendulum': (ref_ip.InvertedPendulum, 4, 6, 4), 'inverted_double_pendulum': (ref_idp.InvertedDoublePendulum, 4, 6, 4),
            'reacher': (ref_re.Reacher, 3, 6, 4), 'swimmer': (ref_sw.Swimmer, 3, 6, 4),
-           'humanoidstandup': (ref_hs.HumanoidStandup, 2, 5, 3)}
+           'humanoidstandup': (ref_hs.HumanoidStandup, 2, 5, 3), 'pusher': (ref_pu.Pusher, 3, 6, 4)}
   for name, (cls, n, steps, ep_len) in cases.items():
     if only is not None and f'env_{name}' not in only:
       continue
     env = ref_wrap.wrap(cls(backend='generalized'), episode_length=ep_len, action_repeat=1)
     rng = np.random.default_rng(7)
     st = env.reset(jax.random.split(jax.random.PRNGKey(3), n))
+    if name == 'pusher':   # arm lowered onto the table, the object under the wrist: both contact kinds active
+      q = np.asarray(st.pipeline_state.q).copy()
+      inner = env.env.env.env
+      for e in range(n):
+        q[e, :7] = 0.0
+        q[e, 1] = (0.40, 0.44, 0.42)[e % 3]
+        w = np.asarray(inner.pipeline_init(jp.array(q[e]), st.pipeline_state.qd[e]).x.pos[6])
+        q[e, 7], q[e, 8] = w[1] + 0.07, w[0] - 0.40
+      q = q.astype(np.float32).astype(np.float64)
+      ps = jax.vmap(inner.pipeline_init)(jp.array(q), st.pipeline_state.qd)
+      obs = jax.vmap(inner._get_obs)(ps)
+      st = st.replace(pipeline_state=ps, obs=obs)
+      st.info['first_pipeline_state'], st.info['first_obs'] = ps, obs
     if name in ('ant', 'hopper', 'inverted_pendulum', 'inverted_double_pendulum'):
       # one env starts unhealthy (Ant: z too high; Hopper: root angle out of range; the pendulums: pole(s) tipped over): terminates at once
       q = np.asarray(st.pipeline_state.q).copy()
@@ -211,6 +224,13 @@ def main():
     mjx.PAIRS = s.contact_pairs() if s.geom_bodyid is not None and len(s.contact_pairs().geom1) else None
     rs = reference_system(s)
     q0, qd0, act = inputs(s, name, n, steps, drop)
+    if name == 'pusher':   # arm lowered until the wrist capsules touch the table, the object pushed under the wrist
+      for e in range(n):
+        q0[e, :] = 0.0
+        q0[e, 1] = (0.40, 0.44)[e % 2]
+        w = np.asarray(ref_pipeline.init(rs, jp.array(q0[e]), jp.array(qd0[e])).x.pos[6])
+        q0[e, 7], q0[e, 8] = w[1] + 0.07, w[0] - 0.40
+      q0 = q0.astype(np.float32).astype(np.float64)
     out = {'q0': q0, 'qd0': qd0, 'act': act}
     active = 0
     for e in range(n):
