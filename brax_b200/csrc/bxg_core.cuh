@@ -1239,20 +1239,21 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
   typename X::template LaneVec<AREG ? R * CW : 1> arow;
   typename X::template LaneVec<R> bi, xi, yi, gi, xni, resi;
   typename X::LaneF p0, p1, p2;
-  // ---- active set ---------------------------------------------------------
-  uint64_t am = 0;
+  // ---- active set (rows 0..63 in am, rows 64.. in am_hi for the widest variant) -------------
+  uint64_t am = 0, am_hi = 0;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     ex.lanes([&](int lane) {
       int i = lane + r * G;
       p0(lane) = i < nc ? s[D.s_rowact + i] : 0.f;   // set by constraint.jacobian (load_env for the incoming state)
     });
-    am |= (uint64_t)ex.ballot(p0) << (r * G);
+    if (r * G < 64) am |= (uint64_t)ex.ballot(p0) << (r * G);
+    else am_hi |= (uint64_t)ex.ballot(p0) << (r * G - 64);
   }
 #if defined(__CUDA_ARCH__)
-  const int na = __popcll(am);
+  const int na_lo = __popcll(am), na = na_lo + (CW > 64 ? __popcll(am_hi) : 0);
 #else
-  const int na = __builtin_popcountll(am);
+  const int na_lo = __builtin_popcountll(am), na = na_lo + (CW > 64 ? __builtin_popcountll(am_hi) : 0);
 #endif
   if (na == 0) {   // nothing active: the solver would return x = 0 after one trivial iteration
     ex.lanes([&](int lane) { for (int d = lane; d < nv; d += G) s[D.s_qfc + d] = 0.f; });
@@ -1263,7 +1264,10 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
   ex.lanes([&](int lane) {
     for (int i = lane; i < CW; i += G) { xs[i] = 0.f; ys[i] = 0.f; xns[i] = 0.f; ress[i] = 0.f; }
 #pragma unroll
-    for (int r = 0; r < R; ++r) { int p = lane + r * G; if (p < CW) orig[p] = p < na ? nth_set_bit(am, p) : -1; }
+    for (int r = 0; r < R; ++r) {
+      int p = lane + r * G;
+      if (p < CW) orig[p] = p < na ? (CW > 64 && p >= na_lo ? 64 + nth_set_bit(am_hi, p - na_lo) : nth_set_bit(am, p)) : -1;
+    }
   });
   // b = (J Minv) qf_smooth - aref;  A[p, q] = (J Minv)[orig p, :] . J[orig q, :] + diag,
   // four active columns at a time (rows of J are broadcast 128-bit loads feeding four

@@ -4,7 +4,7 @@
 #include "bxg_kernels.cuh"
 
 #ifndef BXG_VARIANT
-#error "compile with -DBXG_VARIANT=0..5"
+#error "compile with -DBXG_VARIANT=0..6"
 #endif
 
 namespace {
@@ -18,6 +18,8 @@ using Cfg = bxg::KernelCfg<32, 8, 8>;
 using Cfg = bxg::KernelCfg<16, 6, 7>;
 #elif BXG_VARIANT == 5
 using Cfg = bxg::KernelCfg<32, 4, 16>;
+#elif BXG_VARIANT == 6
+using Cfg = bxg::KernelCfg<32, 6, 20>;
 #else
 using Cfg = bxg::KernelCfg<32, 0, 0>;
 #endif

@@ -84,9 +84,9 @@ inline int row_stride(int w) { int c = w / 4; return 4 * (c | 1); }
 // Kernel variants that are compiled (bxg_kernels.cu).  A model takes the first
 // variant it fits; the last one is the generic any-size kernel.
 struct Variant { int G, VC4, NC4, max_links, max_nv, max_nc; };
-constexpr int kNumVariantsAll = 6;
+constexpr int kNumVariantsAll = 7;
 // order in which a model is offered to the variants (first fit); 3 is the generic kernel, 4 is forced only
-constexpr int kAutoOrder[] = {0, 1, 2, 5, 3};
+constexpr int kAutoOrder[] = {0, 1, 2, 5, 6, 3};
 inline Variant variant(int id) {
   switch (id) {
     case 0: return {16, 4, 6, 16, 16, 24};   // Ant class: half-warp per env
@@ -94,6 +94,7 @@ inline Variant variant(int id) {
     case 2: return {32, 8, 8, 32, 32, 32};
     case 4: return {16, 6, 7, 16, 24, 28};   // Humanoid class on a half-warp (6x6 tiles); forced only
     case 5: return {32, 4, 16, 32, 16, 64};  // few dofs, many constraint rows (Walker2d, HalfCheetah): rows of A stay in shared memory
+    case 6: return {32, 6, 20, 32, 24, 80};  // Humanoid-size tree with up to 80 constraint rows (HumanoidStandup: 15 contacts); 128-bit active mask
     default: return {32, 0, 0, 32, 64, 128}; // generic
   }
 }

@@ -121,6 +121,7 @@ int dispatch(const BxgModelDesc* desc, int vid, A... a) {
     case 3: return run<bxg::KernelCfg<32, 0, 0>>(desc, vid, a...);
     case 4: return run<bxg::KernelCfg<16, 6, 7, true>>(desc, vid, a...);
     case 5: return run<bxg::KernelCfg<32, 4, 16, true>>(desc, vid, a...);
+    case 6: return run<bxg::KernelCfg<32, 6, 20, true>>(desc, vid, a...);
   }
   return 3;
 }

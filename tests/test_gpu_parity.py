@@ -325,10 +325,10 @@ def test_full_size_properties_ant_1m():
   assert torch.equal(again.q, again2.q)
 
 
-@pytest.mark.parametrize('n_legs', [3, 5, 7])
+@pytest.mark.parametrize('n_legs', [3, 5, 7, 10])
 def test_other_kernel_variants_on_gpu(n_legs):
   """Synthetic multi-leg models reach the kernel variants Ant / Humanoid do not
-  (5 legs: 32-lane 4x8-tile variant; 7 legs: generic any-size kernel)."""
+  (5 legs: 32-lane 4x8-tile variant; 7 legs: the 24-dof / 80-row variant; 10 legs: generic any-size kernel)."""
   from brax_b200.generalized import pipeline
   from brax_b200.io import mjcf
   from oracle import oracle as O

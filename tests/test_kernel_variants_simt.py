@@ -17,10 +17,11 @@ def _build():
   g.build()
 
 
-@pytest.mark.parametrize('n_legs,variant', [(3, 0), (5, 2), (7, 3)])
+@pytest.mark.parametrize('n_legs,variant', [(3, 0), (5, 2), (7, 6), (10, 3)])
 def test_variant_selection_and_parity(n_legs, variant):
   """3 legs: half-warp Ant class; 5 legs: nc = 30 -> the 32/32 tile variant (4x8 tiles);
-  7 legs: nc = 42 > 32 -> generic any-size kernel."""
+  7 legs: nv = 20, nc = 42 -> the 24-dof / 80-row variant (rows of A in shared memory, 128-bit active mask);
+  10 legs: nv = 26 > 24 -> generic any-size kernel."""
   _build()
   s = mjcf.loads(centipede_xml(n_legs))
   plan = native.plan(s)
