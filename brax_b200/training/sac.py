@@ -101,6 +101,7 @@ class ReplayBuffer:
     self.obs = torch.empty((capacity, obs_size), **f); self.next_obs = torch.empty((capacity, obs_size), **f)
     self.action = torch.empty((capacity, act_size), **f)
     self.reward = torch.empty(capacity, **f); self.discount = torch.empty(capacity, **f); self.truncation = torch.empty(capacity, **f)
+    self.size_t = torch.zeros((), **f)     # `size` on the device: the sampler inside a CUDA graph reads it
 
   def insert(self, obs, action, reward, discount, next_obs, truncation):
     n = obs.shape[0]
@@ -109,9 +110,11 @@ class ReplayBuffer:
     self.discount[idx], self.next_obs[idx], self.truncation[idx] = discount, next_obs, truncation
     self.pos = (self.pos + n) % self.capacity
     self.size = min(self.size + n, self.capacity)
+    self.size_t.fill_(float(self.size))
 
   def sample(self, batch_size: int):
-    idx = torch.randint(0, self.size, (batch_size,), device=self.obs.device)
+    # floor(U[0,1) * size): graph-capturable (the bound is a device scalar, not a Python int)
+    idx = (torch.rand(batch_size, device=self.obs.device) * self.size_t).long().clamp_(max=self.capacity - 1)
     return {'obs': self.obs[idx], 'action': self.action[idx], 'reward': self.reward[idx], 'discount': self.discount[idx],
             'next_obs': self.next_obs[idx], 'truncation': self.truncation[idx]}
 
@@ -145,7 +148,7 @@ def losses(net: SACNetworks, tr: Dict[str, torch.Tensor], reward_scaling: float,
 def train(env_name: str = 'ant', num_timesteps: int = 1_000_000, episode_length: int = 1000, num_envs: int = 128,
           learning_rate: float = 1e-4, discounting: float = 0.9, seed: int = 0, batch_size: int = 256,
           normalize_observations: bool = False, reward_scaling: float = 1.0, tau: float = 0.005, min_replay_size: int = 0,
-          max_replay_size: Optional[int] = None, grad_updates_per_step: int = 1, device=None,
+          max_replay_size: Optional[int] = None, grad_updates_per_step: int = 1, device=None, use_cuda_graph: bool = True,
           progress_fn: Optional[Callable[[int, Dict[str, float]], None]] = None, progress_every: int = 100):
   """Returns (networks, metrics).  metrics['sps'] = env-steps/sec including acting and learning."""
   world = dist.get_world_size() if dist.is_initialized() else 1
@@ -161,9 +164,10 @@ def train(env_name: str = 'ant', num_timesteps: int = 1_000_000, episode_length:
     for p in net.parameters():
       dist.broadcast(p.data, 0)
     net.target_q.load_state_dict(net.q.state_dict())
-  policy_opt = torch.optim.Adam(net.policy.parameters(), lr=learning_rate)
-  q_opt = torch.optim.Adam(net.q.parameters(), lr=learning_rate)
-  alpha_opt = torch.optim.Adam([net.log_alpha], lr=3e-4)        # reference train.py:233
+  graphed = use_cuda_graph and world == 1       # (several ranks: eager updates around the NCCL all-reduce)
+  policy_opt = torch.optim.Adam(net.policy.parameters(), lr=learning_rate, capturable=graphed)
+  q_opt = torch.optim.Adam(net.q.parameters(), lr=learning_rate, capturable=graphed)
+  alpha_opt = torch.optim.Adam([net.log_alpha], lr=3e-4, capturable=graphed)        # reference train.py:233
   buf = ReplayBuffer((max_replay_size or num_timesteps) // world, env.observation_size, env.action_size, device)
   state = env.reset(seed)
   ep_reward = torch.zeros(num_envs, device=device)
@@ -195,26 +199,54 @@ def train(env_name: str = 'ant', num_timesteps: int = 1_000_000, episode_length:
   torch.cuda.synchronize()
   t0, it, metrics = time.perf_counter(), 0, {}
   q_params, pi_params = list(net.q.parameters()), list(net.policy.parameters())
+  static_losses = torch.zeros(3, device=device)
+
+  def update():
+    """One gradient update (reference train.py:262-327): sample, three losses, three Adam steps, polyak."""
+    tr = buf.sample(batch_size)
+    a_loss, c_loss, p_loss = losses(net, tr, reward_scaling, discounting, env.action_size)
+    alpha_opt.zero_grad(set_to_none=True); q_opt.zero_grad(set_to_none=True); policy_opt.zero_grad(set_to_none=True)
+    a_loss.backward(inputs=[net.log_alpha])
+    c_loss.backward(inputs=q_params)
+    p_loss.backward(inputs=pi_params)
+    all_reduce_grads([net.log_alpha]); all_reduce_grads(q_params); all_reduce_grads(pi_params)
+    alpha_opt.step(); q_opt.step(); policy_opt.step()
+    with torch.no_grad():      # polyak: target = target * (1 - tau) + q * tau (train.py:306-309)
+      for tp, p in zip(net.target_q.parameters(), net.q.parameters()):
+        tp.mul_(1 - tau).add_(p, alpha=tau)
+      static_losses.copy_(torch.stack([a_loss.detach(), c_loss.detach(), p_loss.detach()]))
+
+  update_graph = None
+  if graphed:
+    # the learner is launch-bound (three small MLPs, ~200 kernels per update): one CUDA graph per update
+    if buf.size == 0:
+      state = actor_step(state, False); total += num_envs
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+      for _ in range(3):      # warm-up outside capture (allocations, cuBLAS handles, Adam state)
+        update()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    update_graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(update_graph):
+      update()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
   while total < num_timesteps:
     state = actor_step(state, False)
     total += num_envs * world
     for _ in range(grad_updates_per_step):
-      tr = buf.sample(batch_size)
-      a_loss, c_loss, p_loss = losses(net, tr, reward_scaling, discounting, env.action_size)
-      alpha_opt.zero_grad(set_to_none=True); q_opt.zero_grad(set_to_none=True); policy_opt.zero_grad(set_to_none=True)
-      a_loss.backward(inputs=[net.log_alpha])
-      c_loss.backward(inputs=q_params)
-      p_loss.backward(inputs=pi_params)
-      all_reduce_grads([net.log_alpha]); all_reduce_grads(q_params); all_reduce_grads(pi_params)
-      alpha_opt.step(); q_opt.step(); policy_opt.step()
-      with torch.no_grad():      # polyak: target = target * (1 - tau) + q * tau (train.py:306-309)
-        for tp, p in zip(net.target_q.parameters(), net.q.parameters()):
-          tp.mul_(1 - tau).add_(p, alpha=tau)
+      if update_graph is not None:
+        update_graph.replay()
+      else:
+        update()
     it += 1
     if it % progress_every == 0 or total >= num_timesteps:
       torch.cuda.synchronize()
-      metrics = {'sps': (total - min_replay_size * world) / (time.perf_counter() - t0), 'critic_loss': float(c_loss), 'actor_loss': float(p_loss),
-                 'alpha': float(net.log_alpha.exp()), 'episode_reward': float(finished_sum) / max(float(finished_n), 1.0),
+      a_l, c_l, p_l = static_losses.tolist()
+      metrics = {'sps': (total - min_replay_size * world) / (time.perf_counter() - t0), 'alpha_loss': a_l, 'critic_loss': c_l, 'actor_loss': p_l,
+                 'alpha': float(net.log_alpha.detach().exp()), 'episode_reward': float(finished_sum) / max(float(finished_n), 1.0),
                  'env_steps': total, 'iterations': it}
       if progress_fn and rank == 0:
         progress_fn(total, metrics)
