@@ -23,6 +23,5 @@ def create(env_name: str, episode_length: int = 1000, action_repeat: int = 1, au
            batch_size: Optional[int] = None, **kwargs) -> FusedEnv:
   """reference envs/__init__.py:76-107.  The Episode / Vmap / AutoReset wrappers
   are not separate objects here: their arithmetic is fused into the step kernel."""
-  if action_repeat != 1:
-    raise NotImplementedError('action_repeat != 1 is not fused; loop env.step instead')
-  return _envs[env_name](episode_length=episode_length, auto_reset=auto_reset, batch_size=batch_size, **kwargs)
+  return _envs[env_name](episode_length=episode_length, auto_reset=auto_reset, batch_size=batch_size,
+                         action_repeat=action_repeat, **kwargs)

@@ -40,7 +40,8 @@ class FusedEnv:
 
   def __init__(self, sys: base.System, spec: native.EnvSpecC, metric_names, n_frames: int,
                episode_length: Optional[int] = None, auto_reset: bool = False,
-               batch_size: Optional[int] = None, device=None, env_id_offset: int = 0, metric_slots=None):
+               batch_size: Optional[int] = None, device=None, env_id_offset: int = 0, metric_slots=None,
+               action_repeat: int = 1):
     self.sys = sys
     self.spec = spec
     self.metric_names = tuple(metric_names)
@@ -49,6 +50,7 @@ class FusedEnv:
     self._n_frames = int(n_frames)
     self.episode_length = episode_length
     self.auto_reset = auto_reset
+    self.action_repeat = int(action_repeat)   # EpisodeWrapper's scan over env.step (wrappers/training.py:99-104)
     self.batch_size = batch_size
     self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
     self.env_id_offset = int(env_id_offset)   # global id of env 0 (sharding across ranks)
@@ -112,7 +114,24 @@ class FusedEnv:
       first = {k: v.contiguous() for k, v in state.info['first_pipeline_state'].to_flat().items()}
       first_obs = state.info['first_obs'].contiguous()
     bufs = {k: v.contiguous() for k, v in state.pipeline_state.to_flat().items()}
+    reward_sum = None
+    if self.action_repeat > 1:
+      # EpisodeWrapper.step (wrappers/training.py:98-112): the inner env steps `action_repeat` times with one action,
+      # rewards are summed, `steps` advances by action_repeat and the episode / auto-reset logic runs once, on the
+      # last inner step.  The first action_repeat - 1 steps are bare env steps (no episode bookkeeping, no reset).
+      bare = type(self.spec).from_buffer_copy(self.spec)
+      bare.episode_length = 0
+      scratch = {'obs': io['obs'], 'reward': torch.empty_like(io['reward']), 'done': torch.zeros_like(io['done']), 'metrics': io['metrics']}
+      reward_sum = torch.zeros_like(io['reward'])
+      for _ in range(self.action_repeat - 1):
+        bufs = model.env_step(bare, bufs, action, self._n_frames, scratch)
+        reward_sum += scratch['reward']
+      if io['steps'] is not None:   # the kernel adds 1 after its own reset-on-previous-done: hand it that reset already applied
+        io['steps'] = torch.where(io['done'] != 0, torch.zeros_like(io['steps']), io['steps']) + float(self.action_repeat - 1)
+        io['done'] = torch.zeros_like(io['done'])
     out = model.env_step(self.spec, bufs, action, self._n_frames, io, first=first, first_obs=first_obs)
+    if reward_sum is not None:
+      io['reward'] = reward_sum + io['reward']
     metrics = {k: io['metrics'][:, self._metric_slots[k]] for k in self.metric_names}
     info = dict(state.info)
     if io['steps'] is not None:

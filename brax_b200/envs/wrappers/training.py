@@ -12,8 +12,6 @@ from brax_b200.envs.base import FusedEnv
 def wrap(env: FusedEnv, episode_length: int = 1000, action_repeat: int = 1, randomization_fn=None,
          batch_size: Optional[int] = None) -> FusedEnv:
   """Episode bookkeeping + auto-reset, as training.wrap applies them (reference :28-57)."""
-  if action_repeat != 1:
-    raise NotImplementedError('action_repeat != 1 is not fused; loop env.step instead')
   if randomization_fn is not None:
     raise NotImplementedError('domain randomisation needs a per-env System, which the kernel does not take')
   out = copy.copy(env)
@@ -21,6 +19,7 @@ def wrap(env: FusedEnv, episode_length: int = 1000, action_repeat: int = 1, rand
   out.episode_length = int(episode_length)
   out.spec.episode_length = int(episode_length)
   out.auto_reset = True
+  out.action_repeat = int(action_repeat)
   if batch_size is not None:
     out.batch_size = batch_size
   return out

@@ -121,3 +121,27 @@ def test_env_step_equals_pipeline_step_plus_obs():
   st2 = env.step(st, act)
   assert torch.equal(st2.pipeline_state.q, ps.q) and torch.equal(st2.pipeline_state.mass_mx_inv, ps.mass_mx_inv)
   assert torch.equal(st2.obs, torch.cat([ps.q[:, 2:], ps.qd], 1))
+
+
+def test_action_repeat_is_the_episode_wrappers_scan():
+  """action_repeat = 2 (EpisodeWrapper, reference wrappers/training.py:98-112): two inner env steps with one
+  action, rewards summed, `steps` advanced by 2, episode logic applied once."""
+  import torch
+  from brax_b200 import envs
+  n = 64
+  a = envs.create('ant', episode_length=5, action_repeat=2, auto_reset=True, batch_size=n)
+  b = envs.create('ant', episode_length=1000, action_repeat=1, auto_reset=True, batch_size=n)
+  sa, sb = a.reset(2), b.reset(2)
+  gen = torch.Generator(device='cpu').manual_seed(1)
+  for k in range(3):
+    act = (torch.rand((n, 8), generator=gen) * 2 - 1).to(sa.obs.device)
+    sb1 = b.step(sb, act); sb = b.step(sb1, act)
+    sa = a.step(sa, act)
+    assert float(sb1.done.sum()) == 0          # (healthy start: no termination between the two inner steps)
+    torch.testing.assert_close(sa.reward, sb1.reward + sb.reward)
+    if k < 2:
+      assert torch.equal(sa.pipeline_state.q, sb.pipeline_state.q) and torch.equal(sa.obs, sb.obs)
+      assert (sa.info['steps'] == 2 * (k + 1)).all() and (sa.done == sb.done).all()
+  # third call: steps = 6 >= episode_length = 5 -> truncated, state snaps back to the first state
+  assert (sa.done == 1).all() and (sa.info['truncation'] == 1 - sb.done).all() and (sa.info['steps'] == 6).all()
+  assert torch.equal(sa.obs, sa.info['first_obs'])
