@@ -133,15 +133,17 @@ def test_action_repeat_is_the_episode_wrappers_scan():
   b = envs.create('ant', episode_length=1000, action_repeat=1, auto_reset=True, batch_size=n)
   sa, sb = a.reset(2), b.reset(2)
   gen = torch.Generator(device='cpu').manual_seed(1)
+  ok = torch.ones(n, dtype=torch.bool, device=sa.obs.device)   # envs the reference env never terminated (b resets those at once, a after the pair)
   for k in range(3):
-    act = (torch.rand((n, 8), generator=gen) * 2 - 1).to(sa.obs.device)
+    act = 0.3 * (torch.rand((n, 8), generator=gen) * 2 - 1).to(sa.obs.device)
     sb1 = b.step(sb, act); sb = b.step(sb1, act)
     sa = a.step(sa, act)
-    assert float(sb1.done.sum()) == 0          # (healthy start: no termination between the two inner steps)
-    torch.testing.assert_close(sa.reward, sb1.reward + sb.reward)
+    ok &= (sb1.done == 0) & ((sb.done == 0) | (k == 2))
+    torch.testing.assert_close(sa.reward[ok], (sb1.reward + sb.reward)[ok])
     if k < 2:
-      assert torch.equal(sa.pipeline_state.q, sb.pipeline_state.q) and torch.equal(sa.obs, sb.obs)
-      assert (sa.info['steps'] == 2 * (k + 1)).all() and (sa.done == sb.done).all()
+      assert torch.equal(sa.pipeline_state.q[ok], sb.pipeline_state.q[ok]) and torch.equal(sa.obs[ok], sb.obs[ok])
+      assert (sa.info['steps'][ok] == 2 * (k + 1)).all() and (sa.done[ok] == sb.done[ok]).all()
+  assert ok.sum() >= n // 2
   # third call: steps = 6 >= episode_length = 5 -> truncated, state snaps back to the first state
-  assert (sa.done == 1).all() and (sa.info['truncation'] == 1 - sb.done).all() and (sa.info['steps'] == 6).all()
-  assert torch.equal(sa.obs, sa.info['first_obs'])
+  assert (sa.done[ok] == 1).all() and (sa.info['truncation'][ok] == (1 - sb.done)[ok]).all() and (sa.info['steps'][ok] == 6).all()
+  assert torch.equal(sa.obs[ok], sa.info['first_obs'][ok])
