@@ -2002,7 +2002,8 @@ BXG_HD void load_env(X& ex, const Ctx& c, const BxgState& g, const float* act, i
     const int G = X::G, jld = D.jld;
     for (int i = lane; i < nc; i += G) {
       bool nz = s[D.s_diag + i] != 0.f || s[D.s_aref + i] != 0.f;
-      for (int k = 0; k < jld && !nz; ++k) { int kk = k + i; kk = kk >= jld ? kk - jld : kk; kk = kk >= jld ? kk - jld : kk; nz = s[D.s_J + i * jld + kk] != 0.f; }
+      const int i0 = i % jld;   // (models with more than 2 * jld rows: the start column must wrap as often as needed)
+      for (int k = 0; k < jld && !nz; ++k) { int kk = k + i0; kk = kk >= jld ? kk - jld : kk; nz = s[D.s_J + i * jld + kk] != 0.f; }
       s[D.s_rowact + i] = nz ? 1.f : 0.f;
     }
   });

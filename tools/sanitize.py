@@ -29,4 +29,17 @@ for model in ('hopper', 'halfcheetah'):   # plane-capsule contacts: half-warp va
     st = pipeline.step(sys_, st, torch.zeros((29, sys_.nu), device=dev), n_frames=5)
   torch.cuda.synchronize()
   assert torch.isfinite(st.q).all()
+# fluid forces (generic variant), capsule-capsule contacts (variant 5), the 80-row variant, the classic-control env kinds
+for model in ('swimmer', 'pusher', 'humanoidstandup', 'reacher', 'inverted_pendulum', 'inverted_double_pendulum'):
+  env = envs.create(model, episode_length=2, auto_reset=True, batch_size=23)
+  es = env.reset(0)
+  if model == 'pusher':   # arm lowered onto the table, the object under the wrist: both contact kinds active
+    q = es.pipeline_state.q.clone(); q[:, :7] = 0.0; q[:, 1] = 0.42
+    w = pipeline.init(env.sys, q, es.pipeline_state.qd).x.pos[:, 6]
+    q[:, 7], q[:, 8] = w[:, 1] + 0.07, w[:, 0] - 0.40
+    es = es.replace(pipeline_state=pipeline.init(env.sys, q.contiguous(), es.pipeline_state.qd))
+  for k in range(3):
+    es = env.step(es, 0.5 * torch.ones((23, env.action_size), device=dev))
+  torch.cuda.synchronize()
+  assert torch.isfinite(es.obs).all() and torch.isfinite(es.pipeline_state.q).all(), model
 print('sanitize rollout ok')
