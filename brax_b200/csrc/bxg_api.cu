@@ -20,7 +20,7 @@ inline int envs_per_cta(const Dims& d, const Variant& var) {
   int n = (int)(avail / (sizeof(uint32_t) * (size_t)d.env_words));
   int per_warp = 32 / G;
   n -= n % per_warp;
-  int cap = variant_max_threads(var.G, var.VC4) / G;
+  int cap = variant_max_threads(var.G, var.VC4, var.NC4) / G;
   if (const char* e = getenv("BXG_MAX_ENVS_PER_CTA")) { int v = atoi(e); if (v >= per_warp && v < cap) cap = v - v % per_warp; }   // tuning knob
   return n > cap ? cap : n;
 }

@@ -129,7 +129,7 @@ struct Stats { int pg_iters, pg_trials, ns_accepts, ns_cold; };
 template <int G_, int VC4_, int NC4_, bool GENERIC_TOO_ = false>
 struct KernelCfg {
   static constexpr int G = G_, VC4 = VC4_, NC4 = NC4_;
-  static constexpr int MAX_THREADS = variant_max_threads(G_, VC4_);
+  static constexpr int MAX_THREADS = variant_max_threads(G_, VC4_, NC4_);
   static constexpr bool GENERIC_TOO = GENERIC_TOO_ || VC4_ == 0;
 };
 

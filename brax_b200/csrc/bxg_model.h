@@ -108,7 +108,8 @@ inline int mat_stride(const Variant& v, int w) { return v.VC4 == 6 ? w : row_str
 #ifndef BXG_G32_MAXT
 #define BXG_G32_MAXT 608
 #endif
-constexpr int variant_max_threads(int G, int VC4) { return G == 16 ? (VC4 == 6 ? 320 : 416) : BXG_G32_MAXT; }
+// (the 80-row variant holds few envs per SM: small CTAs, so each thread may keep up to 255 registers)
+constexpr int variant_max_threads(int G, int VC4, int NC4 = 0) { return G == 16 ? (VC4 == 6 ? 320 : 416) : (NC4 >= 20 ? 256 : BXG_G32_MAXT); }
 inline bool variant_fits(const Variant& v, int L, int nv, int nc) { return L <= v.max_links && nv <= v.max_nv && nc <= v.max_nc; }
 
 struct PackedModel {
