@@ -8,6 +8,8 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include <string>
 #include <vector>
@@ -108,8 +110,11 @@ inline int mat_stride(const Variant& v, int w) { return v.VC4 == 6 ? w : row_str
 #ifndef BXG_G32_MAXT
 #define BXG_G32_MAXT 608
 #endif
+#ifndef BXG_G16_MAXT
+#define BXG_G16_MAXT 480   // 30 Ant envs per SM at 128 registers per thread
+#endif
 // (the 80-row variant holds few envs per SM: small CTAs, so each thread may keep up to 255 registers)
-constexpr int variant_max_threads(int G, int VC4, int NC4 = 0) { return G == 16 ? (VC4 == 6 ? 320 : 416) : (NC4 >= 20 ? 256 : BXG_G32_MAXT); }
+constexpr int variant_max_threads(int G, int VC4, int NC4 = 0) { return G == 16 ? (VC4 == 6 ? 320 : BXG_G16_MAXT) : (NC4 >= 20 ? 256 : BXG_G32_MAXT); }
 inline bool variant_fits(const Variant& v, int L, int nv, int nc) { return L <= v.max_links && nv <= v.max_nv && nc <= v.max_nc; }
 
 struct PackedModel {
@@ -359,16 +364,23 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
   const int nvv = m.nv, nc = d.nc, ncz = nc > 0 ? nc : 1;
   d.s_q = take1(m.nq); d.s_qd = take1(nvv); d.s_act = take1(m.nu > 0 ? m.nu : 1);
   d.s_qfc = take1(nvv); d.s_qdd = take1(nvv);
-  d.s_x_pos = take1(L * 3); d.s_x_rot = take1(L * 4); d.s_xd_ang = take1(L * 3); d.s_xd_vel = take1(L * 3);
-  d.s_root_com = take1(L * 3);
-  d.s_cinr_pos = take1(L * 3); d.s_cinr_rot = take1(L * 4); d.s_cinr_i = take1(L * 9); d.s_cinr_mass = take1(L);
-  d.s_cd_ang = take1(L * 3); d.s_cd_vel = take1(L * 3);
-  d.s_cdof_ang = take1(nvv * 3); d.s_cdof_vel = take1(nvv * 3);
-  d.s_cdofd_ang = take1(nvv * 3); d.s_cdofd_vel = take1(nvv * 3);
-  d.s_diag = take1(ncz); d.s_aref = take1(ncz);
-  d.s_qfs = take(d.nvw);
   // (the Cholesky mode shares them too: its factor lives in the Newton-Schulz buffer's slot)
   const bool shared_slots = var.VC4 > 0 && m.matrix_inv_iterations > 0;
+  // Everything kinematics.forward and dynamics.transform_com produce (x, xd, root_com, cinr, cd, cdof, cdofd).
+  // It is dead from the end of dynamics.forward until kinematics recomputes it after integrate, i.e. for the
+  // whole of constraint.force: in the specialised variants the part of A that does not fit M's slot spills
+  // over this block, which therefore sits directly behind that slot (see below).
+  auto take_kin_block = [&]() {
+    d.s_x_pos = take1(L * 3); d.s_x_rot = take1(L * 4); d.s_xd_ang = take1(L * 3); d.s_xd_vel = take1(L * 3);
+    d.s_root_com = take1(L * 3);
+    d.s_cinr_pos = take1(L * 3); d.s_cinr_rot = take1(L * 4); d.s_cinr_i = take1(L * 9); d.s_cinr_mass = take1(L);
+    d.s_cd_ang = take1(L * 3); d.s_cd_vel = take1(L * 3);
+    d.s_cdof_ang = take1(nvv * 3); d.s_cdof_vel = take1(nvv * 3);
+    d.s_cdofd_ang = take1(nvv * 3); d.s_cdofd_vel = take1(nvv * 3);
+  };
+  if (!shared_slots) take_kin_block();
+  d.s_diag = take1(ncz); d.s_aref = take1(ncz);
+  d.s_qfs = take(d.nvw);
   // union of phase-local temporaries: kinematics / RNE / com temps, composite
   // inertias (CRBA) and the constraint-solver vectors never live at the same time.
   // tau (actuator.to_tau) lives from the start of dynamics to qf_smooth and, for the
@@ -398,7 +410,12 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
   auto mx = [](int a, int b) { return a > b ? a : b; };
   d.s_Minv = take(mat_v);
   if (shared_slots) {
-    int s0 = take(mx(mat_v, mat_a)), s1 = take(mx(mat_v, mat_j));
+    // slot1 {Newton-Schulz buffer | J}, then slot0 {M | A}: M takes mat_v words, A runs on into the kinematics
+    // block behind it (dead while A lives), plus padding only if even that is too small
+    int s1 = take(mx(mat_v, mat_j));
+    int s0 = take(mat_v);
+    take_kin_block();
+    if (o - s0 < mat_a) o = s0 + mat_a;
     d.s_M = s0; d.s_A = s0; d.s_Xn = s1; d.s_B = s1; d.s_J = s1;
     d.s_JM = s0; d.s_scr = s1;  // unused by the specialised kernels
   } else {
@@ -415,6 +432,10 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
   // two envs' broadcast row loads (64 B each) never share a bank
   if (var.G == 16) while (o % 32 != 16) o += 4;
   d.env_words = o;
+  if (getenv("BXG_DEBUG_LAYOUT"))   // tuning aid: where the slab's words go
+    fprintf(stderr, "slab: q %d qd %d act %d qfc %d qdd %d diag %d aref %d qfs %d t_ang %d j_rot %d b %d Minv %d slot1 %d slot0 %d x_pos %d cdofd_vel %d dist %d rowact %d red %d end %d (mat_v %d mat_a %d mat_j %d)\n",
+            d.s_q, d.s_qd, d.s_act, d.s_qfc, d.s_qdd, d.s_diag, d.s_aref, d.s_qfs, d.s_t_ang, d.s_j_rot, d.s_b, d.s_Minv, d.s_Xn, d.s_M, d.s_x_pos,
+            d.s_cdofd_vel, d.s_dist, d.s_rowact, d.s_red, o, mat_v, mat_a, mat_j);
   return "";
 }
 
