@@ -131,7 +131,11 @@ def train(env_name: str = 'ant', num_envs: int = 2048, episode_length: int = 100
   if world > 1:
     for p in agent.parameters():
       dist.broadcast(p.data, 0)
-  opt = torch.optim.Adam(agent.parameters(), lr=learning_rate, capturable=use_cuda_graph)
+  # the learner's GEMMs run on the tensor cores in TF32, as XLA's default precision does for the reference's
+  # float32 dots on GPU; the physics step is untouched by this switch (plain FP32 FMA)
+  torch.backends.cuda.matmul.allow_tf32 = True
+  torch.backends.cudnn.allow_tf32 = True
+  opt = torch.optim.Adam(agent.parameters(), lr=learning_rate, capturable=use_cuda_graph, fused=True)
   sgd_graph = step_graph = static_mb = static_loss = static_flat = None
   state = env.reset(seed)
   # one training step consumes batch_size * num_minibatches trajectories of unroll_length steps
