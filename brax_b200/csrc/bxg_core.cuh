@@ -133,6 +133,9 @@ struct KernelCfg {
   static constexpr bool GENERIC_TOO = GENERIC_TOO_ || VC4_ == 0;
 };
 
+// one byte per constraint row: 1 where the row is active (else J, diag and aref of the row are all zero)
+BXG_HD uint8_t* row_active(float* s, const Dims& D) { return reinterpret_cast<uint8_t*>(s + D.s_rowact); }
+
 // constraint._imp_aref (brax/generalized/constraint.py:29-65); prm as packed by pack_impedance
 // (bxg_model.h): the row-constant quotients are precomputed on the host
 BXG_HD_NOINLINE void imp_aref(const float* prm, float pos, float vel, float* imp_out, float* aref_out) {
@@ -1245,7 +1248,7 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
   for (int r = 0; r < R; ++r) {
     ex.lanes([&](int lane) {
       int i = lane + r * G;
-      p0(lane) = i < nc ? s[D.s_rowact + i] : 0.f;   // set by constraint.jacobian (load_env for the incoming state)
+      p0(lane) = i < nc && row_active(s, D)[i] ? 1.f : 0.f;   // set by constraint.jacobian (load_env for the incoming state)
     });
     if (r * G < 64) am |= (uint64_t)ex.ballot(p0) << (r * G);
     else am_hi |= (uint64_t)ex.ballot(p0) << (r * G - 64);
@@ -1599,7 +1602,7 @@ BXG_HD void con_jacobian(X& ex, const Ctx& c) {
         if constexpr (kTwoBody) { if (la >= 0) tw = mf[D.m_link_invw + la] + mf[D.m_link_invw + lb]; }   // invweight[a] * (a > -1) + invweight[b]
         diag = (tw + mu * mu * tw) * (2.f * mu * mu * (1.f - imp) / (imp + 1e-8f));
       }
-      s[D.s_diag + row] = diag; s[D.s_aref + row] = aref; s[D.s_rowact + row] = active ? 1.f : 0.f;
+      s[D.s_diag + row] = diag; s[D.s_aref + row] = aref; row_active(s, D)[row] = active ? 1 : 0;
     });
   }
   if (D.nlim > 0) {
@@ -1618,7 +1621,7 @@ BXG_HD void con_jacobian(X& ex, const Ctx& c) {
           diag = mf[D.m_dof_invw + d] * (1.f - imp) / (imp + 1e-8f);
         }
         J[row * nvp + d] = side;
-        s[D.s_diag + row] = diag; s[D.s_aref + row] = aref; s[D.s_rowact + row] = active ? 1.f : 0.f;
+        s[D.s_diag + row] = diag; s[D.s_aref + row] = aref; row_active(s, D)[row] = active ? 1 : 0;
       }
     });
   }
@@ -2004,7 +2007,7 @@ BXG_HD void load_env(X& ex, const Ctx& c, const BxgState& g, const float* act, i
       bool nz = s[D.s_diag + i] != 0.f || s[D.s_aref + i] != 0.f;
       const int i0 = i % jld;   // (models with more than 2 * jld rows: the start column must wrap as often as needed)
       for (int k = 0; k < jld && !nz; ++k) { int kk = k + i0; kk = kk >= jld ? kk - jld : kk; nz = s[D.s_J + i * jld + kk] != 0.f; }
-      s[D.s_rowact + i] = nz ? 1.f : 0.f;
+      row_active(s, D)[i] = nz ? 1 : 0;
     }
   });
 }

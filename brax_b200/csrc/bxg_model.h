@@ -72,8 +72,8 @@ struct Dims {
   int s_scr;                   // generic path / Cholesky scratch (2 matrices)
   int s_diag, s_aref, s_b, s_px, s_py, s_pg, s_pres, s_pxn;  // solver vectors (b..pxn) alias the t/f temporaries
   int s_dist;                  // [ncon]
-  int s_rowact;                // [nc] 1.0 where the constraint row is active (else J, diag, aref of the row are all zero)
-  int s_red;                   // [8] scalars
+  int s_rowact;                // [nc] BYTES: 1 where the constraint row is active (else J, diag, aref of the row are all zero)
+  int s_red;                   // [4] scalars (the env's pre-step reference point)
   int env_words;
 };
 
@@ -108,7 +108,7 @@ inline int mat_stride(const Variant& v, int w) { return v.VC4 == 6 ? w : row_str
 // Largest CTA a variant is launched with (its __launch_bounds__): half-warp variants
 // fill an SM's shared memory with fewer threads and can keep more registers each.
 #ifndef BXG_G32_MAXT
-#define BXG_G32_MAXT 608
+#define BXG_G32_MAXT 640
 #endif
 #ifndef BXG_G16_MAXT
 #define BXG_G16_MAXT 480   // 30 Ant envs per SM at 128 registers per thread
@@ -425,8 +425,8 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
     d.s_A = take(mat_a); d.s_JM = take(mat_j);
   }
   d.s_dist = take1(m.ncon > 0 ? m.ncon : 1);
-  d.s_rowact = take1(ncz);
-  d.s_red = take1(8);
+  d.s_rowact = take1((ncz + 3) / 4);   // one byte per row
+  d.s_red = take1(4);
   o = (o + 3) & ~3;
   // half-warp variants put two envs in one warp: offset their slabs by 16 banks so that the
   // two envs' broadcast row loads (64 B each) never share a bank
