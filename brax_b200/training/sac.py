@@ -165,9 +165,12 @@ def train(env_name: str = 'ant', num_timesteps: int = 1_000_000, episode_length:
       dist.broadcast(p.data, 0)
     net.target_q.load_state_dict(net.q.state_dict())
   graphed = use_cuda_graph and world == 1       # (several ranks: eager updates around the NCCL all-reduce)
-  policy_opt = torch.optim.Adam(net.policy.parameters(), lr=learning_rate, capturable=graphed)
-  q_opt = torch.optim.Adam(net.q.parameters(), lr=learning_rate, capturable=graphed)
-  alpha_opt = torch.optim.Adam([net.log_alpha], lr=3e-4, capturable=graphed)        # reference train.py:233
+  # learner GEMMs in TF32 on the tensor cores (XLA's default precision for the reference's float32 dots on GPU);
+  # the physics step is plain FP32 and unaffected
+  torch.backends.cuda.matmul.allow_tf32 = True
+  policy_opt = torch.optim.Adam(net.policy.parameters(), lr=learning_rate, capturable=graphed, fused=True)
+  q_opt = torch.optim.Adam(net.q.parameters(), lr=learning_rate, capturable=graphed, fused=True)
+  alpha_opt = torch.optim.Adam([net.log_alpha], lr=3e-4, capturable=graphed, fused=True)        # reference train.py:233
   buf = ReplayBuffer((max_replay_size or num_timesteps) // world, env.observation_size, env.action_size, device)
   state = env.reset(seed)
   ep_reward = torch.zeros(num_envs, device=device)
