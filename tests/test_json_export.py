@@ -25,3 +25,16 @@ def test_schema_and_shapes(ant):
   bad = [types.SimpleNamespace(x=types.SimpleNamespace(pos=st['x_pos'], rot=st['x_rot']))]   # batched: rejected
   with pytest.raises(RuntimeError):
     bjson.dumps(ant, bad)
+
+
+@pytest.mark.parametrize('name', ['pusher', 'swimmer', 'humanoidstandup', 'reacher', 'inverted_pendulum',
+                                  'inverted_double_pendulum', 'hopper', 'walker2d', 'halfcheetah', 'humanoid'])
+def test_every_shipped_model_exports(name):
+  from brax_b200 import envs_assets
+  from brax_b200.io import json as bjson
+  s = envs_assets.load(name)
+  n = s.num_links()
+  frame = types.SimpleNamespace(x=types.SimpleNamespace(pos=np.zeros((n, 3), np.float32),
+                                                        rot=np.tile(np.array([1, 0, 0, 0], np.float32), (n, 1))))
+  d = json.loads(bjson.dumps(s, [frame]))
+  assert len(d['states']['x']) == 1 and sum(len(g) for g in d['geoms'].values()) == len(s.geom_type)
