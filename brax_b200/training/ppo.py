@@ -255,10 +255,12 @@ def train(env_name: str = 'ant', num_envs: int = 2048, episode_length: int = 100
           opt.step()
     for _ in range(num_update_epochs):
       perm = torch.randperm(n_traj, device=device)
-      for mb in perm[:mb_size * num_minibatches].view(num_minibatches, mb_size):
+      if sgd_graph is not None:   # one gather per leaf and epoch; the minibatches are then plain slices
+        shuffled = {k: torch.index_select(v, 1, perm[:mb_size * num_minibatches]) for k, v in td.items()}
+      for i, mb in enumerate(perm[:mb_size * num_minibatches].view(num_minibatches, mb_size)):
         if sgd_graph is not None:
-          for k, v in td.items():
-            torch.index_select(v, 1, mb, out=static_mb[k])
+          for k, v in shuffled.items():
+            static_mb[k].copy_(v[:, i * mb_size:(i + 1) * mb_size])
           sgd_graph.replay()
           if world > 1:
             dist.all_reduce(static_flat)
