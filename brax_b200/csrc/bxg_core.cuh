@@ -1597,7 +1597,9 @@ BXG_HD void con_jacobian(X& ex, const Ctx& c) {
         float vel = 0.f;
         for (int d = 0; d < nv; ++d) vel += J[row * nvp + d] * s[D.s_qd + d];
         float imp;
-        imp_aref(mf + D.m_con_sp + kImpStride * cc, dist, vel, &imp, &aref);
+        int spi = cc;
+        if constexpr (Cfg::NC4 >= 20) spi = mi[D.m_con_sp_idx + cc];   // 80-row variant: distinct parameter sets stored once
+        imp_aref(mf + D.m_con_sp + kImpStride * spi, dist, vel, &imp, &aref);
         float tw = mf[D.m_link_invw + lb];  // link_a is the world: contributes 0
         if constexpr (kTwoBody) { if (la >= 0) tw = mf[D.m_link_invw + la] + mf[D.m_link_invw + lb]; }   // invweight[a] * (a > -1) + invweight[b]
         diag = (tw + mu * mu * tw) * (2.f * mu * mu * (1.f - imp) / (imp + 1e-8f));
@@ -1617,7 +1619,9 @@ BXG_HD void con_jacobian(X& ex, const Ctx& c) {
         float diag = 0.f, aref = 0.f;
         if (active) {
           float imp;
-          imp_aref(mf + D.m_dof_sp + kImpStride * d, pos, side * s[D.s_qd + d], &imp, &aref);
+          int spi = d;
+          if constexpr (Cfg::NC4 >= 20) spi = mi[D.m_dof_sp_idx + d];
+          imp_aref(mf + D.m_dof_sp + kImpStride * spi, pos, side * s[D.s_qd + d], &imp, &aref);
           diag = mf[D.m_dof_invw + d] * (1.f - imp) / (imp + 1e-8f);
         }
         J[row * nvp + d] = side;

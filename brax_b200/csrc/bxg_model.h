@@ -10,6 +10,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <string>
 #include <vector>
@@ -48,6 +49,9 @@ struct Dims {
   int m_con_kind, m_con_gquat, m_con_half;   // plane-capsule end points: kind 1, geom quaternion [ncon,4], signed half length
   int m_con_anc_lo, m_con_anc_hi;        // [ncon] bitmask of dofs that move link_b
   int m_fluid;                           // [L, 8] per-link fluid constants (pack_fluid), only when `fluid`
+  // 80-row variant only: impedance rows stored once per distinct parameter set (most models have one or two),
+  // m_dof_sp_idx [nv] / m_con_sp_idx [ncon] pick the row: a smaller blob means one more env per SM there
+  int sp_dedup, m_dof_sp_idx, m_con_sp_idx;
   int two_body;                          // some contact has kind 2 (capsule-capsule, link_a may move)
   int m_con_la, m_con_apos, m_con_aquat, m_con_ahalf, m_con_arad;   // kind 2: link and shape of the first capsule
   int m_con_anca_lo, m_con_anca_hi;      // [ncon] bitmask of dofs that move link_a
@@ -163,6 +167,18 @@ inline void pack_fluid(const float* inertia_i9, float mass, float viscosity, flo
   const float p4[3] = {p2[0] * p2[0], p2[1] * p2[1], p2[2] * p2[2]};
   const float bma[3] = {box[0] * (p4[1] + p4[2]), box[1] * (p4[0] + p4[2]), box[2] * (p4[0] + p4[1])};
   for (int i = 0; i < 3; ++i) { o8[2 + i] = -0.5f * density * bmv[i]; o8[5 + i] = -1.0f * density * bma[i]; }
+}
+
+// distinct rows (bitwise) of an [n, kImpStride] table and the row each entry maps to
+inline void dedup_rows(const std::vector<float>& rows, int n, std::vector<float>* uniq, std::vector<int>* idx) {
+  uniq->clear(); idx->assign(n, 0);
+  for (int i = 0; i < n; ++i) {
+    int found = -1;
+    for (int u = 0; u < (int)uniq->size() / kImpStride && found < 0; ++u)
+      if (memcmp(uniq->data() + u * kImpStride, rows.data() + i * kImpStride, sizeof(float) * kImpStride) == 0) found = u;
+    if (found < 0) { found = (int)uniq->size() / kImpStride; uniq->insert(uniq->end(), rows.begin() + i * kImpStride, rows.begin() + (i + 1) * kImpStride); }
+    (*idx)[i] = found;
+  }
 }
 
 // Returns empty string on success, else an error message.
@@ -284,7 +300,16 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
   d.m_dof_invw = put_f(m.dof_invweight, m.nv); {
     std::vector<float> dsp(m.nv * kImpStride, 0.f);
     for (int i = 0; i < m.nv; ++i) pack_impedance(m.dof_solver_params + 7 * i, dsp.data() + kImpStride * i);
-    d.m_dof_sp = put_f(dsp.data(), m.nv * kImpStride);
+    d.sp_dedup = var.NC4 >= 20 ? 1 : 0;
+    d.m_dof_sp_idx = d.m_con_sp_idx = (int)b.size();
+    if (d.sp_dedup) {
+      std::vector<int> idx; std::vector<float> uniq;
+      dedup_rows(dsp, m.nv, &uniq, &idx);
+      d.m_dof_sp_idx = put_i(idx);
+      d.m_dof_sp = put_f(uniq.data(), (int)uniq.size());
+    } else {
+      d.m_dof_sp = put_f(dsp.data(), m.nv * kImpStride);
+    }
   }
   int nu1 = m.nu > 0 ? m.nu : 0;
   d.m_act_qid = put_ip(m.act_q_id, nu1); d.m_act_did = put_ip(m.act_qd_id, nu1);
@@ -311,7 +336,15 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
   {
     std::vector<float> csp(m.ncon * kImpStride + 1, 0.f);
     for (int c = 0; c < m.ncon; ++c) pack_impedance(sp.data() + 7 * c, csp.data() + kImpStride * c);
-    d.m_con_sp = put_f(csp.data(), m.ncon * kImpStride);
+    if (d.sp_dedup && m.ncon > 0) {
+      std::vector<int> idx; std::vector<float> uniq;
+      csp.resize(m.ncon * kImpStride);
+      dedup_rows(csp, m.ncon, &uniq, &idx);
+      d.m_con_sp_idx = put_i(idx);
+      d.m_con_sp = put_f(uniq.data(), (int)uniq.size());
+    } else {
+      d.m_con_sp = put_f(csp.data(), m.ncon * kImpStride);
+    }
   }
   {
     std::vector<int> kind(m.ncon > 0 ? m.ncon : 1, 0);
