@@ -942,6 +942,7 @@ template <> struct Tile<16, 24> { static constexpr int RG = 4, CG = 4, TM = 6, T
 template <> struct Tile<16, 16> { static constexpr int RG = 4, CG = 4, TM = 4, TN = 4; static constexpr bool PIPE = true; };
 template <> struct Tile<32, 32> { static constexpr int RG = 8, CG = 4, TM = 4, TN = 8; static constexpr bool PIPE = false; };
 template <> struct Tile<32, 16> { static constexpr int RG = 8, CG = 4, TM = 2, TN = 4; static constexpr bool PIPE = true; };
+template <> struct Tile<4, 4>   { static constexpr int RG = 2, CG = 2, TM = 2, TN = 2; static constexpr bool PIPE = false; };
 struct alignas(8) F2 { float x, y; };
 
 template <int TN>

@@ -4,7 +4,7 @@
 #include "bxg_kernels.cuh"
 
 #ifndef BXG_VARIANT
-#error "compile with -DBXG_VARIANT=0..6"
+#error "compile with -DBXG_VARIANT=0..7"
 #endif
 
 namespace {
@@ -20,6 +20,8 @@ using Cfg = bxg::KernelCfg<16, 6, 7>;
 using Cfg = bxg::KernelCfg<32, 4, 16>;
 #elif BXG_VARIANT == 6
 using Cfg = bxg::KernelCfg<32, 6, 20>;
+#elif BXG_VARIANT == 7
+using Cfg = bxg::KernelCfg<4, 1, 1>;
 #else
 using Cfg = bxg::KernelCfg<32, 0, 0>;
 #endif

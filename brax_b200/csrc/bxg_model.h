@@ -90,9 +90,9 @@ inline int row_stride(int w) { int c = w / 4; return 4 * (c | 1); }
 // Kernel variants that are compiled (bxg_kernels.cu).  A model takes the first
 // variant it fits; the last one is the generic any-size kernel.
 struct Variant { int G, VC4, NC4, max_links, max_nv, max_nc; };
-constexpr int kNumVariantsAll = 7;
+constexpr int kNumVariantsAll = 8;
 // order in which a model is offered to the variants (first fit); 3 is the generic kernel, 4 is forced only
-constexpr int kAutoOrder[] = {0, 1, 2, 5, 6, 3};
+constexpr int kAutoOrder[] = {7, 0, 1, 2, 5, 6, 3};
 inline Variant variant(int id) {
   switch (id) {
     case 0: return {16, 4, 6, 16, 16, 24};   // Ant class: half-warp per env
@@ -100,6 +100,7 @@ inline Variant variant(int id) {
     case 2: return {32, 8, 8, 32, 32, 32};
     case 4: return {16, 6, 7, 16, 24, 28};   // Humanoid class on a half-warp (6x6 tiles); forced only
     case 5: return {32, 4, 16, 32, 16, 64};  // few dofs, many constraint rows (Walker2d, HalfCheetah): rows of A stay in shared memory
+    case 7: return {4, 1, 1, 4, 4, 4};       // classic-control size (pendulums, Reacher): 4 lanes per env, eight envs per warp
     case 6: return {32, 6, 20, 32, 24, 80};  // Humanoid-size tree with up to 80 constraint rows (HumanoidStandup: 15 contacts); 128-bit active mask
     default: return {32, 0, 0, 32, 64, 128}; // generic
   }
@@ -445,7 +446,7 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
   if (shared_slots) {
     // slot1 {Newton-Schulz buffer | J}, then slot0 {M | A}: M takes mat_v words, A runs on into the kinematics
     // block behind it (dead while A lives), plus padding only if even that is too small
-    int s1 = take(mx(mat_v, mat_j));
+    int s1 = take(mx(mx(mat_v, mat_j), 6 * nvv));   // (mass.matrix parks crb * cdof, 6 floats per dof, in the Newton-Schulz buffer)
     int s0 = take(mat_v);
     take_kin_block();
     if (o - s0 < mat_a) o = s0 + mat_a;
@@ -453,7 +454,7 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
     d.s_JM = s0; d.s_scr = s1;  // unused by the specialised kernels
   } else {
     d.s_M = take(mat_v); d.s_J = take(mat_j);
-    d.s_scr = take(2 * mat_v);            // Cholesky: dst/Lm; generic Newton-Schulz: candidate, I + r
+    d.s_scr = take(mat_v + mx(mat_v, 6 * nvv));   // Cholesky: dst/Lm; generic Newton-Schulz: candidate, I + r (also mass.matrix's 6 floats per dof)
     d.s_Xn = d.s_scr; d.s_B = d.s_scr + mat_v;
     d.s_A = take(mat_a); d.s_JM = take(mat_j);
   }

@@ -72,3 +72,40 @@ def test_models_beyond_the_limits_are_rejected():
   assert rc == 3 and b'not supported' in lib.bxg_last_error()
   ok = mjcf.loads(centipede_xml(10))        # 21 links, nv = 26, nc = 60: the generic kernel takes it
   assert native.plan(ok)['variant'] == 3
+
+
+@pytest.mark.parametrize('model', ['inverted_pendulum', 'inverted_double_pendulum', 'reacher'])
+def test_four_lane_variant(model):
+  """Classic-control models (<= 4 links / dofs / rows) take the 4-lane variant: eight envs per warp, 4 x 4
+  register tiles.  Parity with the oracle as one-substep maps, forward and reverse lane order."""
+  _build()
+  from brax_b200 import envs_assets
+  s = envs_assets.load(model)
+  plan = native.plan(s)
+  assert plan['variant'] == 7 and plan['lanes_per_env'] == 4, plan
+  rng = np.random.default_rng(0)
+  n = 11                                   # not a multiple of the eight envs of a warp
+  q = (np.asarray(s.init_q)[None] + rng.uniform(-0.3, 0.3, (n, s.nq))).astype(np.float32)
+  if model == 'inverted_double_pendulum':
+    q[:, 1] = 1.6 * rng.uniform(-1, 1, n)  # beyond the joint range (+-1.57?): limit rows active for some envs
+  qd = rng.standard_normal((n, s.nv)).astype(np.float32)
+  sim, o = Sim(s), O.Oracle(s)
+  a, b = sim.init(q, qd), o.init(q, qd)
+  for f in O.STATE_FIELDS:
+    np.testing.assert_allclose(a[f], b[f], rtol=1e-5, atol=1e-6 * max(1.0, float(np.abs(b[f]).max()) if b[f].size else 1.0), err_msg=f)
+  inside = []
+  for k in range(8):
+    act = rng.uniform(-1, 1, (n, s.nu)).astype(np.float32)
+    st_in = {f: b[f].copy() for f in O.STATE_FIELDS}
+    a = sim.step(st_in, act, 1)
+    o.step(b, act, 1)
+    e = np.zeros(n)
+    for f in ('q', 'qd', 'x_pos', 'x_rot', 'xd_ang', 'xd_vel'):
+      e = np.maximum(e, (np.abs(a[f] - b[f]) / (1e-5 + 1e-4 * np.abs(b[f]))).reshape(n, -1).max(1))
+    inside.append(e <= 1.0)
+  assert np.mean(inside) >= 0.9, np.mean(inside)
+  r = Sim(s, reverse=True)
+  z = np.zeros((n, s.nu), np.float32)
+  x, y = sim.step(sim.init(q, qd), z, 3), r.step(r.init(q, qd), z, 3)
+  for f in O.STATE_FIELDS:
+    assert np.array_equal(x[f], y[f]), f
