@@ -233,8 +233,8 @@ template <class X, class Cfg>
 BXG_HD void dyn_forces(X& ex, const Ctx& c) {
   const Dims& D = *c.D; const float* mf = c.mf; const int* mi = c.mi; float* s = c.s;
   const int L = D.L, nv = D.nv;
-  // fluid models always run on the generic variant (bxg_model.h): the specialised ones carry no fluid code
-  constexpr bool kFluidCode = Cfg::VC4 == 0;
+  // fluid models run on the generic variant or on the small 8-wide one (bxg_model.h): the others carry no fluid code
+  constexpr bool kFluidCode = Cfg::VC4 == 0 || (Cfg::G == 4 && Cfg::VC4 == 2);
   if constexpr (kFluidCode) { if (D.fluid) fluid_passive(ex, c); }
   actuator_tau(ex, c);
   // RNE forward scan: cdd, then cfrc_flat (lanes <-> links, one tree level at a time)
@@ -943,6 +943,7 @@ template <> struct Tile<16, 16> { static constexpr int RG = 4, CG = 4, TM = 4, T
 template <> struct Tile<32, 32> { static constexpr int RG = 8, CG = 4, TM = 4, TN = 8; static constexpr bool PIPE = false; };
 template <> struct Tile<32, 16> { static constexpr int RG = 8, CG = 4, TM = 2, TN = 4; static constexpr bool PIPE = true; };
 template <> struct Tile<4, 4>   { static constexpr int RG = 2, CG = 2, TM = 2, TN = 2; static constexpr bool PIPE = false; };
+template <> struct Tile<4, 8>   { static constexpr int RG = 2, CG = 2, TM = 4, TN = 4; static constexpr bool PIPE = false; };
 struct alignas(8) F2 { float x, y; };
 
 template <int TN>

@@ -4,7 +4,7 @@
 #include "bxg_kernels.cuh"
 
 #ifndef BXG_VARIANT
-#error "compile with -DBXG_VARIANT=0..7"
+#error "compile with -DBXG_VARIANT=0..8"
 #endif
 
 namespace {
@@ -22,6 +22,8 @@ using Cfg = bxg::KernelCfg<32, 4, 16>;
 using Cfg = bxg::KernelCfg<32, 6, 20>;
 #elif BXG_VARIANT == 7
 using Cfg = bxg::KernelCfg<4, 1, 1>;
+#elif BXG_VARIANT == 8
+using Cfg = bxg::KernelCfg<4, 2, 2>;
 #else
 using Cfg = bxg::KernelCfg<32, 0, 0>;
 #endif

@@ -123,6 +123,7 @@ int dispatch(const BxgModelDesc* desc, int vid, A... a) {
     case 5: return run<bxg::KernelCfg<32, 4, 16, true>>(desc, vid, a...);
     case 6: return run<bxg::KernelCfg<32, 6, 20, true>>(desc, vid, a...);
     case 7: return run<bxg::KernelCfg<4, 1, 1, true>>(desc, vid, a...);
+    case 8: return run<bxg::KernelCfg<4, 2, 2, true>>(desc, vid, a...);
   }
   return 3;
 }

@@ -101,7 +101,7 @@ def test_fluid_drag_of_a_translating_box():
   </worldbody>
 </mujoco>'''
   s = mjcf.loads(xml)
-  assert s.enable_fluid and native.plan(s)['variant'] == 3
+  assert s.enable_fluid and native.plan(s)['variant'] in (3, 8)      # the only variants that carry the fluid forces
   o = O.Oracle(s, np.float64)
   v = 0.7
   st = o.init(np.array([[0, 0, 1.0, 1, 0, 0, 0]]), np.array([[v, 0, 0, 0, 0, 0]]))
