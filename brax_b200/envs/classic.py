@@ -2,7 +2,7 @@
 reacher, swimmer}.py`, backend='generalized'), HumanoidStandup and Pusher.
 
 No contacts; slide joints (the carts), a 2-dof link (Reacher's target) and, for Swimmer, the fluid
-forces of `brax/fluid.py` (compiled into the generic kernel variant).  Each env has its own kind in
+forces of `brax/fluid.py` (compiled into the generic kernel variant and the small 4-lane one Swimmer runs on).  Each env has its own kind in
 the kernel's env epilogue (include/bxg.h BXG_ENV_CARTPOLE ... BXG_ENV_SWIMMER)."""
 import math
 
