@@ -27,22 +27,22 @@ inline int envs_per_cta(const Dims& d, const Variant& var) {
 }
 
 extern "C" {
-const void* bxg_step_kernel_v0(); const void* bxg_step_kernel_v1(); const void* bxg_step_kernel_v2(); const void* bxg_step_kernel_v3(); const void* bxg_step_kernel_v4(); const void* bxg_step_kernel_v5(); const void* bxg_step_kernel_v6(); const void* bxg_step_kernel_v7(); const void* bxg_step_kernel_v8();
-const void* bxg_init_kernel_v0(); const void* bxg_init_kernel_v1(); const void* bxg_init_kernel_v2(); const void* bxg_init_kernel_v3(); const void* bxg_init_kernel_v4(); const void* bxg_init_kernel_v5(); const void* bxg_init_kernel_v6(); const void* bxg_init_kernel_v7(); const void* bxg_init_kernel_v8();
+const void* bxg_step_kernel_v0(); const void* bxg_step_kernel_v1(); const void* bxg_step_kernel_v2(); const void* bxg_step_kernel_v3(); const void* bxg_step_kernel_v4(); const void* bxg_step_kernel_v5(); const void* bxg_step_kernel_v6(); const void* bxg_step_kernel_v7(); const void* bxg_step_kernel_v8(); const void* bxg_step_kernel_v9();
+const void* bxg_init_kernel_v0(); const void* bxg_init_kernel_v1(); const void* bxg_init_kernel_v2(); const void* bxg_init_kernel_v3(); const void* bxg_init_kernel_v4(); const void* bxg_init_kernel_v5(); const void* bxg_init_kernel_v6(); const void* bxg_init_kernel_v7(); const void* bxg_init_kernel_v8(); const void* bxg_init_kernel_v9();
 }
 extern "C" {
 const void* bxg_step_chol_kernel_v0(); const void* bxg_step_chol_kernel_v1(); const void* bxg_step_chol_kernel_v2();
-const void* bxg_step_chol_kernel_v3(); const void* bxg_step_chol_kernel_v4(); const void* bxg_step_chol_kernel_v5(); const void* bxg_step_chol_kernel_v6(); const void* bxg_step_chol_kernel_v7(); const void* bxg_step_chol_kernel_v8();
+const void* bxg_step_chol_kernel_v3(); const void* bxg_step_chol_kernel_v4(); const void* bxg_step_chol_kernel_v5(); const void* bxg_step_chol_kernel_v6(); const void* bxg_step_chol_kernel_v7(); const void* bxg_step_chol_kernel_v8(); const void* bxg_step_chol_kernel_v9();
 }
 static const void* step_chol_kernel_of(int v) {
   switch (v) { case 0: return bxg_step_chol_kernel_v0(); case 1: return bxg_step_chol_kernel_v1(); case 2: return bxg_step_chol_kernel_v2();
-               case 4: return bxg_step_chol_kernel_v4(); case 5: return bxg_step_chol_kernel_v5(); case 6: return bxg_step_chol_kernel_v6(); case 7: return bxg_step_chol_kernel_v7(); case 8: return bxg_step_chol_kernel_v8(); default: return bxg_step_chol_kernel_v3(); }
+               case 4: return bxg_step_chol_kernel_v4(); case 5: return bxg_step_chol_kernel_v5(); case 6: return bxg_step_chol_kernel_v6(); case 7: return bxg_step_chol_kernel_v7(); case 8: return bxg_step_chol_kernel_v8(); case 9: return bxg_step_chol_kernel_v9(); default: return bxg_step_chol_kernel_v3(); }
 }
 static const void* step_kernel_of(int v) {
-  switch (v) { case 0: return bxg_step_kernel_v0(); case 1: return bxg_step_kernel_v1(); case 2: return bxg_step_kernel_v2(); case 4: return bxg_step_kernel_v4(); case 5: return bxg_step_kernel_v5(); case 6: return bxg_step_kernel_v6(); case 7: return bxg_step_kernel_v7(); case 8: return bxg_step_kernel_v8(); default: return bxg_step_kernel_v3(); }
+  switch (v) { case 0: return bxg_step_kernel_v0(); case 1: return bxg_step_kernel_v1(); case 2: return bxg_step_kernel_v2(); case 4: return bxg_step_kernel_v4(); case 5: return bxg_step_kernel_v5(); case 6: return bxg_step_kernel_v6(); case 7: return bxg_step_kernel_v7(); case 8: return bxg_step_kernel_v8(); case 9: return bxg_step_kernel_v9(); default: return bxg_step_kernel_v3(); }
 }
 static const void* init_kernel_of(int v) {
-  switch (v) { case 0: return bxg_init_kernel_v0(); case 1: return bxg_init_kernel_v1(); case 2: return bxg_init_kernel_v2(); case 4: return bxg_init_kernel_v4(); case 5: return bxg_init_kernel_v5(); case 6: return bxg_init_kernel_v6(); case 7: return bxg_init_kernel_v7(); case 8: return bxg_init_kernel_v8(); default: return bxg_init_kernel_v3(); }
+  switch (v) { case 0: return bxg_init_kernel_v0(); case 1: return bxg_init_kernel_v1(); case 2: return bxg_init_kernel_v2(); case 4: return bxg_init_kernel_v4(); case 5: return bxg_init_kernel_v5(); case 6: return bxg_init_kernel_v6(); case 7: return bxg_init_kernel_v7(); case 8: return bxg_init_kernel_v8(); case 9: return bxg_init_kernel_v9(); default: return bxg_init_kernel_v3(); }
 }
 
 struct BxgModel {

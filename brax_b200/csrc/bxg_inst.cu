@@ -4,7 +4,7 @@
 #include "bxg_kernels.cuh"
 
 #ifndef BXG_VARIANT
-#error "compile with -DBXG_VARIANT=0..8"
+#error "compile with -DBXG_VARIANT=0..9"
 #endif
 
 namespace {
@@ -24,6 +24,8 @@ using Cfg = bxg::KernelCfg<32, 6, 20>;
 using Cfg = bxg::KernelCfg<4, 1, 1>;
 #elif BXG_VARIANT == 8
 using Cfg = bxg::KernelCfg<4, 2, 2>;
+#elif BXG_VARIANT == 9
+using Cfg = bxg::KernelCfg<4, 2, 4>;
 #else
 using Cfg = bxg::KernelCfg<32, 0, 0>;
 #endif

@@ -90,9 +90,9 @@ inline int row_stride(int w) { int c = w / 4; return 4 * (c | 1); }
 // Kernel variants that are compiled (bxg_kernels.cu).  A model takes the first
 // variant it fits; the last one is the generic any-size kernel.
 struct Variant { int G, VC4, NC4, max_links, max_nv, max_nc; };
-constexpr int kNumVariantsAll = 9;
+constexpr int kNumVariantsAll = 10;
 // order in which a model is offered to the variants (first fit); 3 is the generic kernel, 4 is forced only
-constexpr int kAutoOrder[] = {7, 8, 0, 1, 2, 5, 6, 3};
+constexpr int kAutoOrder[] = {7, 8, 9, 0, 1, 2, 5, 6, 3};
 inline Variant variant(int id) {
   switch (id) {
     case 0: return {16, 4, 6, 16, 16, 24};   // Ant class: half-warp per env
@@ -100,6 +100,7 @@ inline Variant variant(int id) {
     case 2: return {32, 8, 8, 32, 32, 32};
     case 4: return {16, 6, 7, 16, 24, 28};   // Humanoid class on a half-warp (6x6 tiles); forced only
     case 5: return {32, 4, 16, 32, 16, 64};  // few dofs, many constraint rows (Walker2d, HalfCheetah): rows of A stay in shared memory
+    case 9: return {4, 2, 4, 4, 8, 16};      // four links with contacts (Hopper: 6 dofs, 14 rows)
     case 8: return {4, 2, 2, 4, 8, 8};       // as 7 with 8-wide matrices; carries the fluid forces (Swimmer: 3 links, 5 dofs)
     case 7: return {4, 1, 1, 4, 4, 4};       // classic-control size (pendulums, Reacher): 4 lanes per env, eight envs per warp
     case 6: return {32, 6, 20, 32, 24, 80};  // Humanoid-size tree with up to 80 constraint rows (HumanoidStandup: 15 contacts); 128-bit active mask
@@ -214,10 +215,10 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
   if (d.nc > 128) return "more than 128 constraint rows not supported";
   int vid = force_variant;
   d.fluid = m.enable_fluid ? 1 : 0;
-  // fluid forces are compiled into variant 8 and the generic one; the other specialised variants stay exactly as profiled
-  auto fluid_ok = [](int k) { return variant(k).VC4 == 0 || k == 8; };
-  if (d.fluid && vid >= 0 && !fluid_ok(vid)) return "fluid forces are compiled into kernel variants 3 and 8 only";
-  if (d.fluid && vid < 0) vid = variant_fits(variant(8), L, m.nv, d.nc) ? 8 : 3;
+  // fluid forces are compiled into the small 8-wide variants (8, 9) and the generic one; the other specialised variants stay exactly as profiled
+  auto fluid_ok = [](int k) { return variant(k).VC4 == 0 || (variant(k).G == 4 && variant(k).VC4 == 2); };
+  if (d.fluid && vid >= 0 && !fluid_ok(vid)) return "fluid forces are compiled into kernel variants 3, 8 and 9 only";
+  if (d.fluid && vid < 0) vid = variant_fits(variant(8), L, m.nv, d.nc) ? 8 : (variant_fits(variant(9), L, m.nv, d.nc) ? 9 : 3);
   d.two_body = 0;
   for (int c = 0; c < m.ncon; ++c) if (m.con_kind && m.con_kind[c] == BXG_CON_CAPSULE_CAPSULE) d.two_body = 1;
   // two-body contacts are compiled into variant 5 and the generic one only

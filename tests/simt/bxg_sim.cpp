@@ -124,6 +124,7 @@ int dispatch(const BxgModelDesc* desc, int vid, A... a) {
     case 6: return run<bxg::KernelCfg<32, 6, 20, true>>(desc, vid, a...);
     case 7: return run<bxg::KernelCfg<4, 1, 1, true>>(desc, vid, a...);
     case 8: return run<bxg::KernelCfg<4, 2, 2, true>>(desc, vid, a...);
+    case 9: return run<bxg::KernelCfg<4, 2, 4, true>>(desc, vid, a...);
   }
   return 3;
 }
