@@ -49,34 +49,68 @@
 #define BXG_PRAGMA_(x) _Pragma(#x)
 #define BXG_PRAGMA_UNROLL(n) BXG_PRAGMA_(unroll n)
 
+// Scalar type of the algorithm.  The product (device) build is float, the only type the
+// reference computes in (fp32).  The host emulator (tests/simt/) also
+// instantiates the SAME source with BXG_REAL = double, so that the kernel logic of every
+// variant can be compared leaf by leaf, to 1e-9, with the reference-source goldens, which
+// are float64 (tools/gen_reference_golden.py): no percentile, no float32 noise floor.
+#ifndef BXG_REAL
+#define BXG_REAL float
+#endif
+#define R(x) ((::bxg::real)(x))   // a literal of the scalar type: R(1e-8) is exactly 1e-8f in the float build
+
 namespace bxg {
 
+using real = BXG_REAL;
+#if defined(__CUDA_ARCH__)
+static_assert(sizeof(real) == 4, "device code is float only");
+#endif
+
+BXG_HD float r_abs(float x) { return fabsf(x); }
+BXG_HD float r_sqrt(float x) { return sqrtf(x); }
+BXG_HD float r_max(float a, float b) { return fmaxf(a, b); }
+BXG_HD float r_min(float a, float b) { return fminf(a, b); }
+BXG_HD float r_pow(float a, float b) { return powf(a, b); }
+BXG_HD float r_fma(float a, float b, float c) { return fmaf(a, b, c); }
+BXG_HD void r_sincos(float x, float* s, float* c) { sincosf(x, s, c); }
+#if !defined(__CUDA_ARCH__)
+inline double r_abs(double x) { return fabs(x); }
+inline double r_sqrt(double x) { return sqrt(x); }
+inline double r_max(double a, double b) { return fmax(a, b); }
+inline double r_min(double a, double b) { return fmin(a, b); }
+inline double r_pow(double a, double b) { return pow(a, b); }
+inline double r_fma(double a, double b, double c) { return fma(a, b, c); }
+inline void r_sincos(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
+#endif
+// machine epsilon of the scalar type (jaxopt's line search adds jnp.finfo(dtype).eps)
+BXG_HD real r_eps() { return sizeof(real) == 4 ? (real)1.1920929e-07 : (real)2.220446049250313e-16; }
+
 // ------------------------------------------------------------------ algebra
-struct V3 { float x, y, z; };
-struct Q4 { float w, x, y, z; };
+struct V3 { real x, y, z; };
+struct Q4 { real w, x, y, z; };
 
-struct alignas(16) F4 { float x, y, z, w; };
+struct alignas(16) F4 { real x, y, z, w; };
 // 128-bit shared-memory access (LDS.128 / STS.128 on device); p must be 16-byte aligned
-BXG_HD F4 ldv4(const float* p) { return *reinterpret_cast<const F4*>(p); }
-BXG_HD void stv4(float* p, F4 v) { *reinterpret_cast<F4*>(p) = v; }
+BXG_HD F4 ldv4(const real* p) { return *reinterpret_cast<const F4*>(p); }
+BXG_HD void stv4(real* p, F4 v) { *reinterpret_cast<F4*>(p) = v; }
 
-BXG_HD V3 ld3(const float* p) { return V3{p[0], p[1], p[2]}; }
-BXG_HD void st3(float* p, V3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
-BXG_HD Q4 ld4(const float* p) { return Q4{p[0], p[1], p[2], p[3]}; }
-BXG_HD void st4(float* p, Q4 q) { p[0] = q.w; p[1] = q.x; p[2] = q.y; p[3] = q.z; }
+BXG_HD V3 ld3(const real* p) { return V3{p[0], p[1], p[2]}; }
+BXG_HD void st3(real* p, V3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+BXG_HD Q4 ld4(const real* p) { return Q4{p[0], p[1], p[2], p[3]}; }
+BXG_HD void st4(real* p, Q4 q) { p[0] = q.w; p[1] = q.x; p[2] = q.y; p[3] = q.z; }
 BXG_HD V3 operator+(V3 a, V3 b) { return V3{a.x + b.x, a.y + b.y, a.z + b.z}; }
 BXG_HD V3 operator-(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
-BXG_HD V3 operator*(V3 a, float s) { return V3{a.x * s, a.y * s, a.z * s}; }
-BXG_HD float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+BXG_HD V3 operator*(V3 a, real s) { return V3{a.x * s, a.y * s, a.z * s}; }
+BXG_HD real dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 BXG_HD V3 cross(V3 a, V3 b) { return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
 
 // math.rotate (brax/math.py:25-41)
 BXG_HD V3 rotate(V3 v, Q4 q) {
   V3 u{q.x, q.y, q.z};
-  float s = q.w, d = dot(u, v), k = s * s - dot(u, u);
+  real s = q.w, d = dot(u, v), k = s * s - dot(u, u);
   V3 c = cross(u, v);
-  V3 r{2.f * (d * u.x) + k * v.x, 2.f * (d * u.y) + k * v.y, 2.f * (d * u.z) + k * v.z};
-  float s2 = 2.f * s;
+  V3 r{R(2.) * (d * u.x) + k * v.x, R(2.) * (d * u.y) + k * v.y, R(2.) * (d * u.z) + k * v.z};
+  real s2 = R(2.) * s;
   return V3{r.x + s2 * c.x, r.y + s2 * c.y, r.z + s2 * c.z};
 }
 // math.quat_mul (brax/math.py:86-101)
@@ -89,15 +123,15 @@ BXG_HD Q4 qmul(Q4 u, Q4 v) {
 // math.normalize on a quaternion incl. safe_norm's all-close-to-zero rule
 // (brax/math.py:308-345)
 BXG_HD Q4 qnormalize(Q4 q) {
-  bool zero = fabsf(q.w) <= 1e-8f && fabsf(q.x) <= 1e-8f && fabsf(q.y) <= 1e-8f && fabsf(q.z) <= 1e-8f;
-  float n = zero ? 0.f : sqrtf(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
-  float d = n + 1e-6f * (n == 0.f ? 1.f : 0.f);
+  bool zero = r_abs(q.w) <= R(1e-8) && r_abs(q.x) <= R(1e-8) && r_abs(q.y) <= R(1e-8) && r_abs(q.z) <= R(1e-8);
+  real n = zero ? R(0.) : r_sqrt(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+  real d = n + R(1e-6) * (n == R(0.) ? R(1.) : R(0.));
   return Q4{q.w / d, q.x / d, q.y / d, q.z / d};
 }
 // normalize(quat_rot_axis(axis, angle)) (brax/math.py:133-147)
-BXG_HD Q4 axis_quat(V3 axis, float angle) {
-  float sn, cs;
-  sincosf(angle * 0.5f, &sn, &cs);
+BXG_HD Q4 axis_quat(V3 axis, real angle) {
+  real sn, cs;
+  r_sincos(angle * R(0.5), &sn, &cs);
   return qnormalize(Q4{cs, axis.x * sn, axis.y * sn, axis.z * sn});
 }
 // Transform.do(Transform) (brax/base.py:557-562)
@@ -106,7 +140,7 @@ BXG_HD void tf_do(V3 ap, Q4 ar, V3 bp, Q4 br, V3* op, Q4* orr) {
   *orr = qmul(ar, br);
 }
 // Inertia.mul(Motion) -> Force (brax/base.py:297-302); im row-major 3x3
-BXG_HD void inertia_mul(V3 ipos, const float* im, float mass, V3 mang, V3 mvel, V3* fang, V3* fvel) {
+BXG_HD void inertia_mul(V3 ipos, const real* im, real mass, V3 mang, V3 mvel, V3* fang, V3* fvel) {
   V3 c1 = cross(ipos, mvel), c2 = cross(ipos, mang);
   fang->x = (im[0] * mang.x + im[1] * mang.y + im[2] * mang.z) + c1.x;
   fang->y = (im[3] * mang.x + im[4] * mang.y + im[5] * mang.z) + c1.y;
@@ -116,9 +150,9 @@ BXG_HD void inertia_mul(V3 ipos, const float* im, float mass, V3 mang, V3 mvel, 
 
 struct Ctx {
   const Dims* D;
-  const float* mf;  // model blob viewed as float
+  const real* mf;  // model blob viewed as float
   const int* mi;    // model blob viewed as int32
-  float* s;         // this env's slab
+  real* s;         // this env's slab
 };
 
 struct Stats { int pg_iters, pg_trials, ns_accepts, ns_cold; };
@@ -134,28 +168,28 @@ struct KernelCfg {
 };
 
 // one byte per constraint row: 1 where the row is active (else J, diag and aref of the row are all zero)
-BXG_HD uint8_t* row_active(float* s, const Dims& D) { return reinterpret_cast<uint8_t*>(s + D.s_rowact); }
+BXG_HD uint8_t* row_active(real* s, const Dims& D) { return reinterpret_cast<uint8_t*>(s + D.s_rowact); }
 
 // constraint._imp_aref (brax/generalized/constraint.py:29-65); prm as packed by pack_impedance
 // (bxg_model.h): the row-constant quotients are precomputed on the host
-BXG_HD_NOINLINE void imp_aref(const float* prm, float pos, float vel, float* imp_out, float* aref_out) {
-  const float dmin = prm[0], dmax = prm[1], width = prm[2], mid = prm[3], power = prm[4];
-  const float inv_a = prm[5], inv_b = prm[6], b = prm[7], k = prm[8];
-  float imp_x = fabsf(pos) / width;
-  float imp_a, imp_b;
-  if (power == 2.f) {
+BXG_HD_NOINLINE void imp_aref(const real* prm, real pos, real vel, real* imp_out, real* aref_out) {
+  const real dmin = prm[0], dmax = prm[1], width = prm[2], mid = prm[3], power = prm[4];
+  const real inv_a = prm[5], inv_b = prm[6], b = prm[7], k = prm[8];
+  real imp_x = r_abs(pos) / width;
+  real imp_a, imp_b;
+  if (power == R(2.)) {
     // x^2 is an exact operation: no transcendental needed (MuJoCo's default solimp power;
     // XLA's simplifier lowers pow(x, 2) to x * x as well)
     imp_a = inv_a * (imp_x * imp_x);
-    imp_b = 1.f - inv_b * ((1.f - imp_x) * (1.f - imp_x));
+    imp_b = R(1.) - inv_b * ((R(1.) - imp_x) * (R(1.) - imp_x));
   } else {
-    imp_a = inv_a * powf(imp_x, power);
-    imp_b = 1.f - inv_b * powf(1.f - imp_x, power);
+    imp_a = inv_a * r_pow(imp_x, power);
+    imp_b = R(1.) - inv_b * r_pow(R(1.) - imp_x, power);
   }
-  float imp_y = imp_x < mid ? imp_a : imp_b;
-  float imp = dmin + imp_y * (dmax - dmin);
-  imp = fmaxf(dmin, fminf(imp, dmax));
-  if (imp_x > 1.0f) imp = dmax;
+  real imp_y = imp_x < mid ? imp_a : imp_b;
+  real imp = dmin + imp_y * (dmax - dmin);
+  imp = r_max(dmin, r_min(imp, dmax));
+  if (imp_x > R(1.0)) imp = dmax;
   *imp_out = imp;
   *aref_out = -b * vel - k * imp * pos;
 }
@@ -164,19 +198,19 @@ BXG_HD_NOINLINE void imp_aref(const float* prm, float pos, float vel, float* imp
 // actuator.to_tau (brax/actuator.py:23-57), lanes <-> dofs, into s_tau
 template <class X>
 BXG_HD void actuator_tau(X& ex, const Ctx& c) {
-  const Dims& D = *c.D; const float* mf = c.mf; const int* mi = c.mi; float* s = c.s;
+  const Dims& D = *c.D; const real* mf = c.mf; const int* mi = c.mi; real* s = c.s;
   const int nv = D.nv;
   ex.lanes([&](int lane) {
     for (int d = lane; d < nv; d += X::G) {
-      float tau = 0.f;
+      real tau = R(0.);
       for (int k = mi[D.m_dof_act_start + d]; k < mi[D.m_dof_act_start + d + 1]; ++k) {
         int a = mi[D.m_dof_act_list + k];
-        float qv = s[D.s_q + mi[D.m_act_qid + a]], qdv = s[D.s_qd + mi[D.m_act_did + a]];
-        float ctrl = fmaxf(mf[D.m_act_clo + a], fminf(s[D.s_act + a], mf[D.m_act_chi + a]));
-        float gear = mf[D.m_act_gear + a];
-        float bias = gear * (qv * mf[D.m_act_bq + a] + qdv * mf[D.m_act_bqd + a]);
-        float f = mf[D.m_act_gain + a] * ctrl + bias;
-        f = fmaxf(mf[D.m_act_flo + a], fminf(f, mf[D.m_act_fhi + a]));
+        real qv = s[D.s_q + mi[D.m_act_qid + a]], qdv = s[D.s_qd + mi[D.m_act_did + a]];
+        real ctrl = r_max(mf[D.m_act_clo + a], r_min(s[D.s_act + a], mf[D.m_act_chi + a]));
+        real gear = mf[D.m_act_gear + a];
+        real bias = gear * (qv * mf[D.m_act_bq + a] + qdv * mf[D.m_act_bqd + a]);
+        real f = mf[D.m_act_gain + a] * ctrl + bias;
+        f = r_max(mf[D.m_act_flo + a], r_min(f, mf[D.m_act_fhi + a]));
         tau += f * gear;
       }
       s[D.s_tau + d] = tau;
@@ -191,7 +225,7 @@ BXG_HD void actuator_tau(X& ex, const Ctx& c) {
 // assembly of qf_smooth.  Runs before the RNE passes, which reuse the same temporaries.
 template <class X>
 BXG_HD void fluid_passive(X& ex, const Ctx& c) {
-  const Dims& D = *c.D; const float* mf = c.mf; const int* mi = c.mi; float* s = c.s;
+  const Dims& D = *c.D; const real* mf = c.mf; const int* mi = c.mi; real* s = c.s;
   const int L = D.L, nv = D.nv;
   ex.lanes([&](int lane) {
     for (int l = lane; l < L; l += X::G) {
@@ -202,11 +236,11 @@ BXG_HD void fluid_passive(X& ex, const Ctx& c) {
       V3 cda = ld3(s + D.s_cd_ang + 3 * l);
       V3 ang = rotate(cda, rinv);
       V3 vel = rotate(ld3(s + D.s_cd_vel + 3 * l) - cross(off, cda), rinv);
-      const float* k = mf + D.m_fluid + kFluidStride * l;
-      V3 fa{k[0] * ang.x + k[5] * fabsf(ang.x) * ang.x / 64.0f, k[0] * ang.y + k[6] * fabsf(ang.y) * ang.y / 64.0f,
-            k[0] * ang.z + k[7] * fabsf(ang.z) * ang.z / 64.0f};
-      V3 fv{k[1] * vel.x + k[2] * fabsf(vel.x) * vel.x, k[1] * vel.y + k[3] * fabsf(vel.y) * vel.y,
-            k[1] * vel.z + k[4] * fabsf(vel.z) * vel.z};
+      const real* k = mf + D.m_fluid + kFluidStride * l;
+      V3 fa{k[0] * ang.x + k[5] * r_abs(ang.x) * ang.x / R(64.0), k[0] * ang.y + k[6] * r_abs(ang.y) * ang.y / R(64.0),
+            k[0] * ang.z + k[7] * r_abs(ang.z) * ang.z / R(64.0)};
+      V3 fv{k[1] * vel.x + k[2] * r_abs(vel.x) * vel.x, k[1] * vel.y + k[3] * r_abs(vel.y) * vel.y,
+            k[1] * vel.z + k[4] * r_abs(vel.z) * vel.z};
       st3(s + D.s_t_vel + 3 * l, rotate(fv, xi_rot));
       st3(s + D.s_t_ang + 3 * l, rotate(fa, xi_rot));
       st3(s + D.s_f_ang + 3 * l, off);
@@ -216,7 +250,7 @@ BXG_HD void fluid_passive(X& ex, const Ctx& c) {
     for (int d = lane; d < nv; d += X::G) {
       const int dl = mi[D.m_dof_link + d];
       V3 ca = ld3(s + D.s_cdof_ang + 3 * d), cv = ld3(s + D.s_cdof_vel + 3 * d);
-      float acc = 0.f;
+      real acc = R(0.);
       for (int l = dl; l < L; ++l) {
         int p = l;
         while (p > dl) p = mi[D.m_link_parent + p];   // parents precede their children
@@ -231,7 +265,7 @@ BXG_HD void fluid_passive(X& ex, const Ctx& c) {
 
 template <class X, class Cfg>
 BXG_HD void dyn_forces(X& ex, const Ctx& c) {
-  const Dims& D = *c.D; const float* mf = c.mf; const int* mi = c.mi; float* s = c.s;
+  const Dims& D = *c.D; const real* mf = c.mf; const int* mi = c.mi; real* s = c.s;
   const int L = D.L, nv = D.nv;
   // fluid models run on the generic variant or on the small 8-wide one (bxg_model.h): the others carry no fluid code
   constexpr bool kFluidCode = Cfg::VC4 == 0 || (Cfg::G == 4 && Cfg::VC4 == 2);
@@ -243,10 +277,10 @@ BXG_HD void dyn_forces(X& ex, const Ctx& c) {
       if (l >= L || mi[D.m_link_depth + l] != lvl) return;
       int p = mi[D.m_link_parent + l], da = mi[D.m_link_dadr + l], nd = mi[D.m_link_ndof + l];
       nd = nd == 0 ? 6 : nd;
-      V3 ca = p >= 0 ? ld3(s + D.s_t_ang + 3 * p) : V3{0.f, 0.f, 0.f};
+      V3 ca = p >= 0 ? ld3(s + D.s_t_ang + 3 * p) : V3{R(0.), R(0.), R(0.)};
       V3 cv = p >= 0 ? ld3(s + D.s_t_vel + 3 * p) : V3{-D.gx, -D.gy, -D.gz};
       for (int k = 0; k < nd; ++k) {
-        float qd = s[D.s_qd + da + k];
+        real qd = s[D.s_qd + da + k];
         ca = ca + ld3(s + D.s_cdofd_ang + 3 * (da + k)) * qd;
         cv = cv + ld3(s + D.s_cdofd_vel + 3 * (da + k)) * qd;
       }
@@ -258,7 +292,7 @@ BXG_HD void dyn_forces(X& ex, const Ctx& c) {
     ex.lanes([&](int l) {
       if (l >= L) return;
       V3 ca = ld3(s + D.s_t_ang + 3 * l), cv = ld3(s + D.s_t_vel + 3 * l);
-      V3 ip = ld3(s + D.s_cinr_pos + 3 * l); const float* im = s + D.s_cinr_i + 9 * l; float mass = s[D.s_cinr_mass + l];
+      V3 ip = ld3(s + D.s_cinr_pos + 3 * l); const real* im = s + D.s_cinr_i + 9 * l; real mass = s[D.s_cinr_mass + l];
       V3 cda = ld3(s + D.s_cd_ang + 3 * l), cdv = ld3(s + D.s_cd_vel + 3 * l);
       V3 fa, fv, ga, gv;
       inertia_mul(ip, im, mass, ca, cv, &fa, &fv);
@@ -284,10 +318,10 @@ BXG_HD void dyn_forces(X& ex, const Ctx& c) {
   ex.lanes([&](int lane) {
     for (int d = lane; d < nv; d += X::G) {
       int l = mi[D.m_dof_link + d], qi = mi[D.m_dof_qidx + d];
-      float bias = dot(ld3(s + D.s_cdof_vel + 3 * d), ld3(s + D.s_f_vel + 3 * l)) +
+      real bias = dot(ld3(s + D.s_cdof_vel + 3 * d), ld3(s + D.s_f_vel + 3 * l)) +
                    dot(ld3(s + D.s_cdof_ang + 3 * d), ld3(s + D.s_f_ang + 3 * l));
-      float qd = s[D.s_qd + d];
-      float passive = qi < 0 ? 0.f : -s[D.s_q + qi] * mf[D.m_stiff + d];
+      real qd = s[D.s_qd + d];
+      real passive = qi < 0 ? R(0.) : -s[D.s_q + qi] * mf[D.m_stiff + d];
       passive = passive - mf[D.m_damp + d] * qd;
       if constexpr (kFluidCode) { if (D.fluid) passive = passive + s[D.s_qfs + d]; }
       s[D.s_qfs + d] = (passive - bias) + s[D.s_tau + d];
@@ -298,93 +332,93 @@ BXG_HD void dyn_forces(X& ex, const Ctx& c) {
 // --------------------------------------- constraint.force + projected gradient
 template <class X>
 BXG_HD void con_force_generic(X& ex, const Ctx& c, Stats* st) {
-  const Dims& D = *c.D; float* s = c.s;
+  const Dims& D = *c.D; real* s = c.s;
   const int nv = D.nv, nc = D.nc, nvp = D.nvp, ncp = D.ncp;
   if (nc == 0) {
-    ex.lanes([&](int lane) { for (int d = lane; d < nv; d += X::G) s[D.s_qfc + d] = 0.f; });
+    ex.lanes([&](int lane) { for (int d = lane; d < nv; d += X::G) s[D.s_qfc + d] = R(0.); });
     return;
   }
-  float* J = s + D.s_J; float* Mi = s + D.s_Minv; const int jld = D.jld;
-  float* JM = s + D.s_JM; float* A = s + D.s_A;
-  float* b = s + D.s_b; float* x = s + D.s_px; float* y = s + D.s_py; float* g = s + D.s_pg;
-  float* res = s + D.s_pres; float* xn = s + D.s_pxn;
+  real* J = s + D.s_J; real* Mi = s + D.s_Minv; const int jld = D.jld;
+  real* JM = s + D.s_JM; real* A = s + D.s_A;
+  real* b = s + D.s_b; real* x = s + D.s_px; real* y = s + D.s_py; real* g = s + D.s_pg;
+  real* res = s + D.s_pres; real* xn = s + D.s_pxn;
   // A = J Minv J^T + diag, b = J Minv qf_smooth - aref   (lanes <-> rows)
   ex.lanes([&](int lane) {
     for (int i = lane; i < nc; i += X::G) {
       for (int j = 0; j < nv; ++j) {
-        float acc = 0.f;
+        real acc = R(0.);
         for (int k = 0; k < nv; ++k) acc += J[i * jld + k] * Mi[k * nvp + j];
         JM[i * jld + j] = acc;
       }
       for (int j = 0; j < nc; ++j) {
-        float acc = 0.f;
+        real acc = R(0.);
         for (int k = 0; k < nv; ++k) acc += JM[i * jld + k] * J[j * jld + k];
-        A[i * ncp + j] = acc + (i == j ? s[D.s_diag + i] : 0.f);
+        A[i * ncp + j] = acc + (i == j ? s[D.s_diag + i] : R(0.));
       }
-      float acc = 0.f;
+      real acc = R(0.);
       for (int k = 0; k < nv; ++k) acc += JM[i * jld + k] * s[D.s_qfs + k];
       b[i] = acc - s[D.s_aref + i];
-      x[i] = 0.f; y[i] = 0.f;
+      x[i] = R(0.); y[i] = R(0.);
     }
   });
-  float t = 1.f, stepsize = 1.f, error = INFINITY;
-  const float tol = 1e-3f, eps = 1.1920929e-07f;
+  real t = R(1.), stepsize = R(1.), error = INFINITY;
+  const real tol = R(1e-3), eps = r_eps();
   int it = 0;
   while (it < D.solver_iterations && (it == 0 || error > tol)) {
     ex.lanes([&](int lane) {
       for (int i = lane; i < nc; i += X::G) {
-        float acc = 0.f;
+        real acc = R(0.);
         for (int j = 0; j < nc; ++j) acc += A[i * ncp + j] * y[j];
         res[i] = acc + b[i];
       }
     });
-    float fy = 0.f;
-    for (int i = 0; i < nc; ++i) fy += 0.5f * (res[i] * res[i]);
+    real fy = R(0.);
+    for (int i = 0; i < nc; ++i) fy += R(0.5) * (res[i] * res[i]);
     ex.lanes([&](int lane) {
       for (int j = lane; j < nc; j += X::G) {
-        float acc = 0.f;
+        real acc = R(0.);
         for (int i = 0; i < nc; ++i) acc += A[i * ncp + j] * res[i];
         g[j] = acc;
       }
     });   // (writes g only: no hazard with the redundant reads of res above)
-    float sz = stepsize;
+    real sz = stepsize;
     for (int ls = 0;; ++ls) {
-      ex.lanes([&](int lane) { for (int i = lane; i < nc; i += X::G) xn[i] = fmaxf(y[i] - sz * g[i], 0.f); });
+      ex.lanes([&](int lane) { for (int i = lane; i < nc; i += X::G) xn[i] = r_max(y[i] - sz * g[i], R(0.)); });
       ex.lanes([&](int lane) {
         for (int i = lane; i < nc; i += X::G) {
-          float acc = 0.f;
+          real acc = R(0.);
           for (int j = 0; j < nc; ++j) acc += A[i * ncp + j] * xn[j];
           res[i] = acc + b[i];
         }
       });
-      float sqdist = 0.f, vd = 0.f, fn = 0.f;
-      for (int i = 0; i < nc; ++i) { float dlt = xn[i] - y[i]; sqdist += dlt * dlt; }
-      for (int i = 0; i < nc; ++i) { float dlt = xn[i] - y[i]; vd += dlt * g[i]; }
-      for (int i = 0; i < nc; ++i) fn += 0.5f * (res[i] * res[i]);
+      real sqdist = R(0.), vd = R(0.), fn = R(0.);
+      for (int i = 0; i < nc; ++i) { real dlt = xn[i] - y[i]; sqdist += dlt * dlt; }
+      for (int i = 0; i < nc; ++i) { real dlt = xn[i] - y[i]; vd += dlt * g[i]; }
+      for (int i = 0; i < nc; ++i) fn += R(0.5) * (res[i] * res[i]);
       st->pg_trials++;
       ex.sync();   // every lane finished its redundant reads of xn / res before they are rewritten
-      float fun_decrease = sz * (fn - fy);
-      float condition = sz * vd + 0.5f * sqdist;
+      real fun_decrease = sz * (fn - fy);
+      real condition = sz * vd + R(0.5) * sqdist;
       if (!(fun_decrease > condition + eps) || ls >= D.solver_maxls) break;
-      sz = sz * 0.5f;
+      sz = sz * R(0.5);
     }
-    stepsize = sz <= 1e-6f ? 1.f : sz / 0.5f;
-    float tn = 0.5f * (1.f + sqrtf(1.f + 4.f * (t * t)));
-    float mom = (t - 1.f) / tn;
+    stepsize = sz <= R(1e-6) ? R(1.) : sz / R(0.5);
+    real tn = R(0.5) * (R(1.) + r_sqrt(R(1.) + R(4.) * (t * t)));
+    real mom = (t - R(1.)) / tn;
     // res now holds A x+ + b: reuse it for the error gradient
     ex.lanes([&](int lane) {
       for (int j = lane; j < nc; j += X::G) {
-        float acc = 0.f;
+        real acc = R(0.);
         for (int i = 0; i < nc; ++i) acc += A[i * ncp + j] * res[i];
         g[j] = acc;
-        float dlt = xn[j] - x[j];
+        real dlt = xn[j] - x[j];
         y[j] = xn[j] + mom * dlt;
         x[j] = xn[j];
       }
     });
-    float err2 = 0.f;
-    for (int i = 0; i < nc; ++i) { float dlt = fmaxf(xn[i] - g[i], 0.f) - xn[i]; err2 += dlt * dlt; }
-    error = sqrtf(err2);
+    real err2 = R(0.);
+    for (int i = 0; i < nc; ++i) { real dlt = r_max(xn[i] - g[i], R(0.)) - xn[i]; err2 += dlt * dlt; }
+    error = r_sqrt(err2);
     t = tn;
     ++it;
     st->pg_iters++;
@@ -393,7 +427,7 @@ BXG_HD void con_force_generic(X& ex, const Ctx& c, Stats* st) {
   // qf_constraint = J^T x
   ex.lanes([&](int lane) {
     for (int j = lane; j < nv; j += X::G) {
-      float acc = 0.f;
+      real acc = R(0.);
       for (int i = 0; i < nc; ++i) acc += J[i * jld + j] * x[i];
       s[D.s_qfc + j] = acc;
     }
@@ -404,17 +438,17 @@ BXG_HD void con_force_generic(X& ex, const Ctx& c, Stats* st) {
 // Used by init (mass.py:103-104), integrate's implicit-damping branch
 // (integrator.py:58-60) and BXG_MINV_CHOLESKY.
 template <class X>
-BXG_HD void spd_inverse(X& ex, const Ctx& c, const float* src, float* dst, float* Lm, const float* add_diag, float diag_scale) {
+BXG_HD void spd_inverse(X& ex, const Ctx& c, const real* src, real* dst, real* Lm, const real* add_diag, real diag_scale) {
   const Dims& D = *c.D;
   const int n = D.nv, nvp = D.nvp;
   for (int j = 0; j < n; ++j) {
     ex.lanes([&](int lane) {
-      float sd = src[j * nvp + j] + (add_diag ? add_diag[j] * diag_scale : 0.f);
+      real sd = src[j * nvp + j] + (add_diag ? add_diag[j] * diag_scale : R(0.));
       for (int k = 0; k < j; ++k) sd -= Lm[j * nvp + k] * Lm[j * nvp + k];
-      float dg = sqrtf(sd);
+      real dg = r_sqrt(sd);
       for (int i = j + lane; i < n; i += X::G) {
         if (i == j) { Lm[j * nvp + j] = dg; continue; }
-        float tt = src[i * nvp + j];
+        real tt = src[i * nvp + j];
         for (int k = 0; k < j; ++k) tt -= Lm[i * nvp + k] * Lm[j * nvp + k];
         Lm[i * nvp + j] = tt / dg;
       }
@@ -423,12 +457,12 @@ BXG_HD void spd_inverse(X& ex, const Ctx& c, const float* src, float* dst, float
   ex.lanes([&](int lane) {
     for (int col = lane; col < n; col += X::G) {
       for (int i = 0; i < n; ++i) {
-        float tt = i == col ? 1.f : 0.f;
+        real tt = i == col ? R(1.) : R(0.);
         for (int k = 0; k < i; ++k) tt -= Lm[i * nvp + k] * dst[k * nvp + col];
         dst[i * nvp + col] = tt / Lm[i * nvp + i];
       }
       for (int i = n - 1; i >= 0; --i) {
-        float tt = dst[i * nvp + col];
+        real tt = dst[i * nvp + col];
         for (int k = i + 1; k < n; ++k) tt -= Lm[k * nvp + i] * dst[k * nvp + col];
         dst[i * nvp + col] = tt / Lm[i * nvp + i];
       }
@@ -443,7 +477,7 @@ BXG_HD void spd_inverse(X& ex, const Ctx& c, const float* src, float* dst, float
 // so that the back substitution reads rows too.  Solve: lane c owns column c of the
 // inverse in registers.  W = nvw.
 template <class X, int W>
-BXG_HD void spd_inverse_rows(X& ex, const Ctx& c, const float* src, float* dst, float* Lm) {
+BXG_HD void spd_inverse_rows(X& ex, const Ctx& c, const real* src, real* dst, real* Lm) {
   const Dims& D = *c.D;
   const int n = D.nv, ld = D.nvp;
   typename X::template LaneVec<W> lrow;
@@ -451,20 +485,20 @@ BXG_HD void spd_inverse_rows(X& ex, const Ctx& c, const float* src, float* dst, 
   for (int j = 0; j < W; ++j) {
     if (j < n) {
       ex.lanes([&](int i) {
-        float lj[W > 1 ? W : 1];
+        real lj[W > 1 ? W : 1];
 #pragma unroll
         for (int k4 = 0; k4 < j; k4 += 4) { F4 t = ldv4(Lm + j * ld + k4); lj[k4] = t.x; if (k4 + 1 < W) lj[k4 + 1] = t.y; if (k4 + 2 < W) lj[k4 + 2] = t.z; if (k4 + 3 < W) lj[k4 + 3] = t.w; }
-        float sd = src[j * ld + j];
+        real sd = src[j * ld + j];
 #pragma unroll
         for (int k = 0; k < j; ++k) sd -= lj[k] * lj[k];
-        const float dg = sqrtf(sd);
+        const real dg = r_sqrt(sd);
         if (i == j) {
           lrow(i)[j] = dg; Lm[j * ld + j] = dg;
         } else if (i > j && i < n) {
-          float tt = src[i * ld + j];
+          real tt = src[i * ld + j];
 #pragma unroll
           for (int k = 0; k < j; ++k) tt -= lrow(i)[k] * lj[k];
-          const float v = tt / dg;
+          const real v = tt / dg;
           lrow(i)[j] = v; Lm[i * ld + j] = v; Lm[j * ld + i] = v;
         }
       });
@@ -472,14 +506,14 @@ BXG_HD void spd_inverse_rows(X& ex, const Ctx& c, const float* src, float* dst, 
   }
   ex.lanes([&](int col) {
     if (col >= n) return;
-    float y[W];
+    real y[W];
 #pragma unroll
     for (int i = 0; i < W; ++i) {
       if (i < n) {
-        float li[W];
+        real li[W];
 #pragma unroll
         for (int k4 = 0; k4 <= i; k4 += 4) { F4 t = ldv4(Lm + i * ld + k4); li[k4] = t.x; if (k4 + 1 < W) li[k4 + 1] = t.y; if (k4 + 2 < W) li[k4 + 2] = t.z; if (k4 + 3 < W) li[k4 + 3] = t.w; }
-        float tt = i == col ? 1.f : 0.f;
+        real tt = i == col ? R(1.) : R(0.);
 #pragma unroll
         for (int k = 0; k < i; ++k) tt -= li[k] * y[k];
         y[i] = tt / li[i];
@@ -488,10 +522,10 @@ BXG_HD void spd_inverse_rows(X& ex, const Ctx& c, const float* src, float* dst, 
 #pragma unroll
     for (int i = W - 1; i >= 0; --i) {
       if (i < n) {
-        float li[W];
+        real li[W];
 #pragma unroll
         for (int k4 = (i / 4) * 4; k4 < W; k4 += 4) { F4 t = ldv4(Lm + i * ld + k4); li[k4] = t.x; if (k4 + 1 < W) li[k4 + 1] = t.y; if (k4 + 2 < W) li[k4 + 2] = t.z; if (k4 + 3 < W) li[k4 + 3] = t.w; }
-        float tt = y[i];
+        real tt = y[i];
 #pragma unroll
         for (int k = i + 1; k < W; ++k) if (k < n) tt -= li[k] * y[k];
         y[i] = tt / li[i];
@@ -505,18 +539,18 @@ BXG_HD void spd_inverse_rows(X& ex, const Ctx& c, const float* src, float* dst, 
 // ------------------------------------------------------ integrator.integrate
 template <class X>
 BXG_HD void integrate(X& ex, const Ctx& c) {
-  const Dims& D = *c.D; const float* mf = c.mf; const int* mi = c.mi; float* s = c.s;
+  const Dims& D = *c.D; const real* mf = c.mf; const int* mi = c.mi; real* s = c.s;
   const int nv = D.nv, nvp = D.nvp, L = D.L;
-  const float dt = D.dt;
-  const float* Mi = s + D.s_Minv;
+  const real dt = D.dt;
+  const real* Mi = s + D.s_Minv;
   if (D.ns_iters == 0) {
-    float* tmp = s + D.s_scr;  // dst
+    real* tmp = s + D.s_scr;  // dst
     spd_inverse(ex, c, s + D.s_M, tmp, s + D.s_scr + D.nvw * nvp, mf + D.m_damp, dt);
     Mi = tmp;
   }
   ex.lanes([&](int lane) {
     for (int i = lane; i < nv; i += X::G) {
-      float acc = 0.f;
+      real acc = R(0.);
       for (int j = 0; j < nv; ++j) acc += Mi[i * nvp + j] * (s[D.s_qfs + j] + s[D.s_qfc + j]);
       s[D.s_qdd + i] = acc;
     }
@@ -530,12 +564,12 @@ BXG_HD void integrate(X& ex, const Ctx& c) {
     if (nd == 0) {
       Q4 rot = ld4(s + D.s_q + qa + 3);
       V3 ang = ld3(s + D.s_qd + da + 3);
-      float ang_norm = sqrtf(ang.x * ang.x + ang.y * ang.y + ang.z * ang.z) + 1e-8f;
+      real ang_norm = r_sqrt(ang.x * ang.x + ang.y * ang.y + ang.z * ang.z) + R(1e-8);
       V3 axis{ang.x / ang_norm, ang.y / ang_norm, ang.z / ang_norm};
-      float sn, cs;
-      sincosf((dt * ang_norm) * 0.5f, &sn, &cs);
+      real sn, cs;
+      r_sincos((dt * ang_norm) * R(0.5), &sn, &cs);
       Q4 nr = qmul(rot, Q4{cs, axis.x * sn, axis.y * sn, axis.z * sn});
-      float n = sqrtf(nr.w * nr.w + nr.x * nr.x + nr.y * nr.y + nr.z * nr.z);
+      real n = r_sqrt(nr.w * nr.w + nr.x * nr.x + nr.y * nr.y + nr.z * nr.z);
       st4(s + D.s_q + qa + 3, Q4{nr.w / n, nr.x / n, nr.y / n, nr.z / n});
       for (int i = 0; i < 3; ++i) s[D.s_q + qa + i] = s[D.s_q + qa + i] + s[D.s_qd + da + i] * dt;
     } else {
@@ -547,9 +581,9 @@ BXG_HD void integrate(X& ex, const Ctx& c) {
 // -------------------------------------------------------- kinematics.forward
 template <class X>
 BXG_HD void kinematics(X& ex, const Ctx& c) {
-  const Dims& D = *c.D; const float* mf = c.mf; const int* mi = c.mi; float* s = c.s;
+  const Dims& D = *c.D; const real* mf = c.mf; const int* mi = c.mi; real* s = c.s;
   const int L = D.L;
-  float* jpos = s + D.s_f_ang; float* jrot = s + D.s_j_rot; float* jdang = s + D.s_t_ang; float* jdvel = s + D.s_t_vel;
+  real* jpos = s + D.s_f_ang; real* jrot = s + D.s_j_rot; real* jdang = s + D.s_t_ang; real* jdvel = s + D.s_t_vel;
   ex.lanes([&](int l) {
     if (l >= L) return;
     int qa = mi[D.m_link_qadr + l], da = mi[D.m_link_dadr + l], nd = mi[D.m_link_ndof + l];
@@ -560,7 +594,7 @@ BXG_HD void kinematics(X& ex, const Ctx& c) {
     } else {
       p = V3{0, 0, 0}; a = p; v = p; r = Q4{1, 0, 0, 0};
       for (int k = 0; k < nd; ++k) {
-        int d = da + k; float qk = s[D.s_q + qa + k], qdk = s[D.s_qd + d];
+        int d = da + k; real qk = s[D.s_q + qa + k], qdk = s[D.s_qd + d];
         V3 mang = ld3(mf + D.m_dof_ang + 3 * d), mvel = ld3(mf + D.m_dof_vel + 3 * d);
         Q4 sr = axis_quat(mang, qk);
         V3 sp = mvel * qk, sa = mang * qdk, sv = mvel * qdk;
@@ -610,9 +644,9 @@ BXG_HD void kinematics(X& ex, const Ctx& c) {
 // ---------------------------------------------------- dynamics.transform_com
 template <class X>
 BXG_HD void transform_com(X& ex, const Ctx& c) {
-  const Dims& D = *c.D; const float* mf = c.mf; const int* mi = c.mi; float* s = c.s;
+  const Dims& D = *c.D; const real* mf = c.mf; const int* mi = c.mi; real* s = c.s;
   const int L = D.L;
-  float* xi_pos = s + D.s_t_ang;
+  real* xi_pos = s + D.s_t_ang;
   ex.lanes([&](int l) {
     if (l >= L) return;
     V3 xp; Q4 xr;
@@ -623,38 +657,38 @@ BXG_HD void transform_com(X& ex, const Ctx& c) {
     if (l >= L) return;
     // root_com: mass-weighted mean over the links of this tree (index order)
     int root = mi[D.m_link_root + l];
-    V3 msum{0, 0, 0}; float mtot = 0.f;
+    V3 msum{0, 0, 0}; real mtot = R(0.);
     for (int k = 0; k < L; ++k) {
       if (mi[D.m_link_root + k] != root) continue;
-      float mk = mf[D.m_in_mass + k];
+      real mk = mf[D.m_in_mass + k];
       msum = msum + ld3(xi_pos + 3 * k) * mk; mtot += mk;
     }
     V3 com{msum.x / mtot, msum.y / mtot, msum.z / mtot};
     st3(s + D.s_root_com + 3 * l, com);
     // cinr = Transform(x_i.pos - com, x_i.rot).do(inertia)  (base.py:588-594)
-    float mass = mf[D.m_in_mass + l];
+    real mass = mf[D.m_in_mass + l];
     V3 p = ld3(xi_pos + 3 * l) - com;
     Q4 q = ld4(s + D.s_cinr_rot + 4 * l);
-    float R[9];
+    real R[9];
     {
-      float dq = q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z, sc = 2.f / dq;
-      float xs = q.x * sc, ys = q.y * sc, zs = q.z * sc;
-      float wx = q.w * xs, wy = q.w * ys, wz = q.w * zs, xx = q.x * xs, xy = q.x * ys, xz = q.x * zs;
-      float yy = q.y * ys, yz = q.y * zs, zz = q.z * zs;
-      R[0] = 1.f - (yy + zz); R[1] = xy - wz; R[2] = xz + wy;
-      R[3] = xy + wz; R[4] = 1.f - (xx + zz); R[5] = yz - wx;
-      R[6] = xz - wy; R[7] = yz + wx; R[8] = 1.f - (xx + yy);
+      real dq = q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z, sc = R(2.) / dq;
+      real xs = q.x * sc, ys = q.y * sc, zs = q.z * sc;
+      real wx = q.w * xs, wy = q.w * ys, wz = q.w * zs, xx = q.x * xs, xy = q.x * ys, xz = q.x * zs;
+      real yy = q.y * ys, yz = q.y * zs, zz = q.z * zs;
+      R[0] = R(1.) - (yy + zz); R[1] = xy - wz; R[2] = xz + wy;
+      R[3] = xy + wz; R[4] = R(1.) - (xx + zz); R[5] = yz - wx;
+      R[6] = xz - wy; R[7] = yz + wx; R[8] = R(1.) - (xx + yy);
     }
-    const float* I0 = mf + D.m_in_i + 9 * l;
-    float T[9];
+    const real* I0 = mf + D.m_in_i + 9 * l;
+    real T[9];
     for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) {
-      float acc = 0.f;
+      real acc = R(0.);
       for (int k = 0; k < 3; ++k) acc += R[3 * a + k] * I0[3 * k + b];
       T[3 * a + b] = acc;
     }
-    float h[9] = {0.f, -p.z, p.y, p.z, 0.f, -p.x, -p.y, p.x, 0.f};
+    real h[9] = {R(0.), -p.z, p.y, p.z, R(0.), -p.x, -p.y, p.x, R(0.)};
     for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) {
-      float acc = 0.f, hh = 0.f;
+      real acc = R(0.), hh = R(0.);
       for (int k = 0; k < 3; ++k) acc += T[3 * a + k] * R[3 * b + k];
       for (int k = 0; k < 3; ++k) hh += h[3 * a + k] * h[3 * b + k];
       s[D.s_cinr_i + 9 * l + 3 * a + b] = acc + hh * mass;
@@ -684,7 +718,7 @@ BXG_HD void transform_com(X& ex, const Ctx& c) {
         V3 mang = ld3(mf + D.m_dof_ang + 3 * d), mvel = ld3(mf + D.m_dof_vel + 3 * d);
         V3 a = rotate(mang, lr);
         V3 v = rotate(mvel, lr) + cross(lp, a);
-        float qk = s[D.s_q + qa + k];
+        real qk = s[D.s_q + qa + k];
         V3 np_; Q4 nr;
         tf_do(lp, lr, mvel * qk, axis_quat(mang, qk), &np_, &nr);
         lp = np_; lr = nr;
@@ -702,7 +736,7 @@ BXG_HD void transform_com(X& ex, const Ctx& c) {
       V3 ca = p >= 0 ? ld3(s + D.s_cd_ang + 3 * p) : V3{0, 0, 0};
       V3 cv = p >= 0 ? ld3(s + D.s_cd_vel + 3 * p) : V3{0, 0, 0};
       for (int k = 0; k < nd; ++k) {
-        float qd = s[D.s_qd + da + k];
+        real qd = s[D.s_qd + da + k];
         ca = ca + ld3(s + D.s_cdof_ang + 3 * (da + k)) * qd;
         cv = cv + ld3(s + D.s_cdof_vel + 3 * (da + k)) * qd;
       }
@@ -716,7 +750,7 @@ BXG_HD void transform_com(X& ex, const Ctx& c) {
     if (nd == 0) {
       V3 ca{0, 0, 0}, cv{0, 0, 0};
       for (int k = 0; k < 3; ++k) {
-        float qd = s[D.s_qd + da + k];
+        real qd = s[D.s_qd + da + k];
         ca = ca + ld3(s + D.s_cdof_ang + 3 * (da + k)) * qd;
         cv = cv + ld3(s + D.s_cdof_vel + 3 * (da + k)) * qd;
       }
@@ -734,7 +768,7 @@ BXG_HD void transform_com(X& ex, const Ctx& c) {
         V3 da_ = ld3(s + D.s_cdof_ang + 3 * d), dv_ = ld3(s + D.s_cdof_vel + 3 * d);
         st3(s + D.s_cdofd_vel + 3 * d, cross(ca, dv_) + cross(cv, da_));
         st3(s + D.s_cdofd_ang + 3 * d, cross(ca, da_));
-        float qd = s[D.s_qd + d];
+        real qd = s[D.s_qd + d];
         ca = ca + da_ * qd; cv = cv + dv_ * qd;
       }
     }
@@ -744,16 +778,16 @@ BXG_HD void transform_com(X& ex, const Ctx& c) {
 // --------------------------------------------------------------- mass.matrix
 template <class X>
 BXG_HD void mass_matrix(X& ex, const Ctx& c) {
-  const Dims& D = *c.D; const float* mf = c.mf; const int* mi = c.mi; float* s = c.s;
+  const Dims& D = *c.D; const real* mf = c.mf; const int* mi = c.mi; real* s = c.s;
   const int L = D.L, nv = D.nv, nvp = D.nvp;
-  float* M = s + D.s_M;
+  real* M = s + D.s_M;
   ex.lanes([&](int lane) {
     if (lane < L) {
       for (int i = 0; i < 3; ++i) s[D.s_crb_pos + 3 * lane + i] = s[D.s_cinr_pos + 3 * lane + i];
       for (int i = 0; i < 9; ++i) s[D.s_crb_i + 9 * lane + i] = s[D.s_cinr_i + 9 * lane + i];
       s[D.s_crb_mass + lane] = s[D.s_cinr_mass + lane];
     }
-    for (int i = 4 * lane; i < D.nvw * nvp; i += 4 * X::G) stv4(M + i, F4{0.f, 0.f, 0.f, 0.f});   // incl. padding rows (slot shared with A)
+    for (int i = 4 * lane; i < D.nvw * nvp; i += 4 * X::G) stv4(M + i, F4{R(0.), R(0.), R(0.), R(0.)});   // incl. padding rows (slot shared with A)
   });
   for (int lvl = D.max_depth - 1; lvl >= 0; --lvl) {
     ex.lanes([&](int l) {
@@ -768,7 +802,7 @@ BXG_HD void mass_matrix(X& ex, const Ctx& c) {
   }
   // f[i] = crb[link(i)] * cdof[i] per dof, parked in the Newton-Schulz buffer (J is dead
   // between constraint.force and constraint.jacobian); then one lane per non-zero (i, j <= i)
-  float* fbuf = s + D.s_B;
+  real* fbuf = s + D.s_B;
   ex.lanes([&](int lane) {
     for (int i = lane; i < nv; i += X::G) {
       int li = mi[D.m_dof_link + i];
@@ -781,7 +815,7 @@ BXG_HD void mass_matrix(X& ex, const Ctx& c) {
   ex.lanes([&](int lane) {
     for (int p = lane; p < D.n_mm_pairs; p += X::G) {
       const int ij = mi[D.m_mm_pairs + p], i = ij & 255, j = ij >> 8;
-      float v = dot(ld3(s + D.s_cdof_vel + 3 * j), ld3(fbuf + 6 * i)) + dot(ld3(s + D.s_cdof_ang + 3 * j), ld3(fbuf + 6 * i + 3));
+      real v = dot(ld3(s + D.s_cdof_vel + 3 * j), ld3(fbuf + 6 * i)) + dot(ld3(s + D.s_cdof_ang + 3 * j), ld3(fbuf + 6 * i + 3));
       if (i == j) v += mf[D.m_arm + i];
       M[i * nvp + j] = v;
       M[j * nvp + i] = v;
@@ -792,49 +826,49 @@ BXG_HD void mass_matrix(X& ex, const Ctx& c) {
 // ------------------------------------------------------ math.inv_approximate
 template <class X>
 BXG_HD void minv_newton_schulz_generic(X& ex, const Ctx& c, Stats* st) {
-  const Dims& D = *c.D; float* s = c.s;
+  const Dims& D = *c.D; real* s = c.s;
   const int n = D.nv, nvp = D.nvp;
-  const float* M = s + D.s_M;
-  float* Xc = s + D.s_Minv;   // current estimate
-  float* Xn = s + D.s_Xn;     // candidate
-  float* RB = s + D.s_B;      // residual r, then I + r in place
+  const real* M = s + D.s_M;
+  real* Xc = s + D.s_Minv;   // current estimate
+  real* Xn = s + D.s_Xn;     // candidate
+  real* RB = s + D.s_B;      // residual r, then I + r in place
   typename X::LaneF p_sum, p_max;
   // r0 = I - M X
   ex.lanes([&](int lane) {
-    float ss = 0.f, mx = 0.f;
+    real ss = R(0.), mx = R(0.);
     for (int i = lane; i < n; i += X::G) {
       for (int j = 0; j < n; ++j) {
-        float acc = 0.f;
+        real acc = R(0.);
         for (int k = 0; k < n; ++k) acc += M[i * nvp + k] * Xc[k * nvp + j];
-        float r = (i == j ? 1.f : 0.f) - acc;
+        real r = (i == j ? R(1.) : R(0.)) - acc;
         RB[i * nvp + j] = r;
-        ss += r * r; mx = fmaxf(mx, fabsf(r));
+        ss += r * r; mx = r_max(mx, r_abs(r));
       }
     }
     p_sum(lane) = ss; p_max(lane) = mx;
   });
-  float ss = ex.sum(p_sum), mx = ex.max(p_max);
-  float nrm0 = mx <= 1e-8f ? 0.f : sqrtf(ss);
-  if (nrm0 > 1.f) {
+  real ss = ex.sum(p_sum), mx = ex.max(p_max);
+  real nrm0 = mx <= R(1e-8) ? R(0.) : r_sqrt(ss);
+  if (nrm0 > R(1.)) {
     ex.lanes([&](int lane) {
-      float tr = 0.f;
+      real tr = R(0.);
       for (int i = lane; i < n; i += X::G) for (int k = 0; k < n; ++k) tr += M[i * nvp + k] * M[i * nvp + k];
       p_sum(lane) = tr;
     });
-    float tr = ex.sum(p_sum);
+    real tr = ex.sum(p_sum);
     ex.lanes([&](int lane) {
-      for (int i = lane; i < n; i += X::G) for (int j = 0; j < n; ++j) Xc[i * nvp + j] = 0.5f * M[j * nvp + i] / tr;
+      for (int i = lane; i < n; i += X::G) for (int j = 0; j < n; ++j) Xc[i * nvp + j] = R(0.5) * M[j * nvp + i] / tr;
     });
     st->ns_cold++;
   }
-  float err = 1.f;
+  real err = R(1.);
   for (int it = 0; it < D.ns_iters; ++it) {
     // RB <- I + r ; Xn = Xc (I + r)
-    ex.lanes([&](int lane) { for (int i = lane; i < n; i += X::G) RB[i * nvp + i] = 1.f + RB[i * nvp + i]; });
+    ex.lanes([&](int lane) { for (int i = lane; i < n; i += X::G) RB[i * nvp + i] = R(1.) + RB[i * nvp + i]; });
     ex.lanes([&](int lane) {
       for (int i = lane; i < n; i += X::G) {
         for (int j = 0; j < n; ++j) {
-          float acc = 0.f;
+          real acc = R(0.);
           for (int k = 0; k < n; ++k) acc += Xc[i * nvp + k] * RB[k * nvp + j];
           Xn[i * nvp + j] = acc;
         }
@@ -842,20 +876,20 @@ BXG_HD void minv_newton_schulz_generic(X& ex, const Ctx& c, Stats* st) {
     });
     // r' = I - M Xn
     ex.lanes([&](int lane) {
-      float s2 = 0.f, m2 = 0.f;
+      real s2 = R(0.), m2 = R(0.);
       for (int i = lane; i < n; i += X::G) {
         for (int j = 0; j < n; ++j) {
-          float acc = 0.f;
+          real acc = R(0.);
           for (int k = 0; k < n; ++k) acc += M[i * nvp + k] * Xn[k * nvp + j];
-          float r = (i == j ? 1.f : 0.f) - acc;
+          real r = (i == j ? R(1.) : R(0.)) - acc;
           RB[i * nvp + j] = r;
-          s2 += r * r; m2 = fmaxf(m2, fabsf(r));
+          s2 += r * r; m2 = r_max(m2, r_abs(r));
         }
       }
       p_sum(lane) = s2; p_max(lane) = m2;
     });
-    float s2 = ex.sum(p_sum), m2 = ex.max(p_max);
-    float err_next = m2 <= 1e-8f ? 0.f : sqrtf(s2);
+    real s2 = ex.sum(p_sum), m2 = ex.max(p_max);
+    real err_next = m2 <= R(1e-8) ? R(0.) : r_sqrt(s2);
     if (err_next < err) {
       ex.lanes([&](int lane) { for (int i = lane; i < n * nvp; i += X::G) Xc[i] = Xn[i]; });
       st->ns_accepts++;
@@ -871,12 +905,12 @@ BXG_HD void minv_newton_schulz_generic(X& ex, const Ctx& c, Stats* st) {
 // read the same address: one wavefront), so one LDS.128 feeds four FFMA per lane.
 // acc[0..4*C4) = sum_k a[k] * B[k][0..4*C4), k ascending (same order as the oracle).
 template <int K, int C4>
-BXG_HD void row_times_mat(const float* a, const float* B, int ldb, float* acc) {
+BXG_HD void row_times_mat(const real* a, const real* B, int ldb, real* acc) {
 #pragma unroll
-  for (int j = 0; j < 4 * C4; ++j) acc[j] = 0.f;
+  for (int j = 0; j < 4 * C4; ++j) acc[j] = R(0.);
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    const float ak = a[k];
+    const real ak = a[k];
 #pragma unroll
     for (int cc = 0; cc < C4; ++cc) {
       F4 b = ldv4(B + k * ldb + 4 * cc);
@@ -888,15 +922,15 @@ BXG_HD void row_times_mat(const float* a, const float* B, int ldb, float* acc) {
 // Same product with the left row read from shared memory (own row, 128-bit
 // chunks) and the k loop rolled: small code, no register-resident left operand.
 template <int K, int C4>
-BXG_HD void smem_row_times_mat(const float* arow_sm, const float* B, int ldb, float* acc) {
+BXG_HD void smem_row_times_mat(const real* arow_sm, const real* B, int ldb, real* acc) {
 #pragma unroll
-  for (int j = 0; j < 4 * C4; ++j) acc[j] = 0.f;
+  for (int j = 0; j < 4 * C4; ++j) acc[j] = R(0.);
 #pragma unroll 1
   for (int k0 = 0; k0 < K; k0 += 4) {
     const F4 a4 = ldv4(arow_sm + k0);
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
-      const float ak = kk == 0 ? a4.x : kk == 1 ? a4.y : kk == 2 ? a4.z : a4.w;
+      const real ak = kk == 0 ? a4.x : kk == 1 ? a4.y : kk == 2 ? a4.z : a4.w;
 #pragma unroll
       for (int cc = 0; cc < C4; ++cc) {
         F4 b = ldv4(B + (k0 + kk) * ldb + 4 * cc);
@@ -907,19 +941,19 @@ BXG_HD void smem_row_times_mat(const float* arow_sm, const float* B, int ldb, fl
   }
 }
 template <int C4>
-BXG_HD void load_row(const float* p, float* r) {
+BXG_HD void load_row(const real* p, real* r) {
 #pragma unroll
   for (int cc = 0; cc < C4; ++cc) { F4 v = ldv4(p + 4 * cc); r[4 * cc] = v.x; r[4 * cc + 1] = v.y; r[4 * cc + 2] = v.z; r[4 * cc + 3] = v.w; }
 }
 template <int C4>
-BXG_HD void store_row(float* p, const float* r) {
+BXG_HD void store_row(real* p, const real* r) {
 #pragma unroll
   for (int cc = 0; cc < C4; ++cc) stv4(p + 4 * cc, F4{r[4 * cc], r[4 * cc + 1], r[4 * cc + 2], r[4 * cc + 3]});
 }
 // dot of a register row with a shared-memory vector (broadcast 128-bit loads)
 template <int C4>
-BXG_HD float row_dot(const float* a, const float* v) {
-  float acc = 0.f;
+BXG_HD real row_dot(const real* a, const real* v) {
+  real acc = R(0.);
 #pragma unroll
   for (int cc = 0; cc < C4; ++cc) {
     F4 b = ldv4(v + 4 * cc);
@@ -944,10 +978,10 @@ template <> struct Tile<32, 32> { static constexpr int RG = 8, CG = 4, TM = 4, T
 template <> struct Tile<32, 16> { static constexpr int RG = 8, CG = 4, TM = 2, TN = 4; static constexpr bool PIPE = true; };
 template <> struct Tile<4, 4>   { static constexpr int RG = 2, CG = 2, TM = 2, TN = 2; static constexpr bool PIPE = false; };
 template <> struct Tile<4, 8>   { static constexpr int RG = 2, CG = 2, TM = 4, TN = 4; static constexpr bool PIPE = false; };
-struct alignas(8) F2 { float x, y; };
+struct alignas(8) F2 { real x, y; };
 
 template <int TN>
-BXG_HD void load_cols(const float* p, float* v) {
+BXG_HD void load_cols(const real* p, real* v) {
   if constexpr (TN % 4 == 0) {
 #pragma unroll
     for (int c = 0; c < TN / 4; ++c) { F4 t = ldv4(p + 4 * c); v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w; }
@@ -957,7 +991,7 @@ BXG_HD void load_cols(const float* p, float* v) {
   }
 }
 template <int TN>
-BXG_HD void store_cols(float* p, const float* v) {
+BXG_HD void store_cols(real* p, const real* v) {
   if constexpr (TN % 4 == 0) {
 #pragma unroll
     for (int c = 0; c < TN / 4; ++c) stv4(p + 4 * c, F4{v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]});
@@ -970,9 +1004,9 @@ BXG_HD void store_cols(float* p, const float* v) {
 // acc[r * TN + c] = sum_k A[row0 + r][k] * B[k][col0 + c], k ascending; NEG accumulates
 // the negated products instead (rounding is symmetric: exactly -(A B), no extra operation)
 template <class T, int W, bool NEG = false>
-BXG_HD void tile_matmul(int lane, const float* A, const float* B, int ld, float* acc) {
+BXG_HD void tile_matmul(int lane, const real* A, const real* B, int ld, real* acc) {
   const int rg = lane / T::CG, cg = lane - rg * T::CG;
-  const float* a0 = A + rg * T::TM * ld;
+  const real* a0 = A + rg * T::TM * ld;
 #if defined(__CUDA_ARCH__)
   // sm_100a packed FP32: one FFMA2 = two fused multiply-adds per lane (same
   // rounding as two scalar FFMA), halving the issue slots of the inner product
@@ -980,17 +1014,17 @@ BXG_HD void tile_matmul(int lane, const float* A, const float* B, int ld, float*
 #pragma unroll
   for (int r = 0; r < T::TM; ++r)
 #pragma unroll
-    for (int cc = 0; cc < T::TN / 2; ++cc) acc2[r][cc] = make_float2(0.f, 0.f);
+    for (int cc = 0; cc < T::TN / 2; ++cc) acc2[r][cc] = make_float2(R(0.), R(0.));
   if constexpr (T::PIPE) {
   // explicit software pipeline: the operands of k-block k0 + 4 are requested before the FMAs of block k0
-  F4 a_nxt[T::TM]; float b_nxt[4][T::TN];
+  F4 a_nxt[T::TM]; real b_nxt[4][T::TN];
 #pragma unroll
   for (int r = 0; r < T::TM; ++r) a_nxt[r] = ldv4(a0 + r * ld);
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) load_cols<T::TN>(B + kk * ld + cg * T::TN, b_nxt[kk]);
   BXG_PRAGMA_UNROLL(BXG_PIPE16_UNROLL)
   for (int k0 = 0; k0 < W; k0 += 4) {
-    F4 a[T::TM]; float bv[4][T::TN];
+    F4 a[T::TM]; real bv[4][T::TN];
 #pragma unroll
     for (int r = 0; r < T::TM; ++r) a[r] = a_nxt[r];
 #pragma unroll
@@ -1007,8 +1041,8 @@ BXG_HD void tile_matmul(int lane, const float* A, const float* B, int ld, float*
     for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
       for (int r = 0; r < T::TM; ++r) {
-        const float ap = kk == 0 ? a[r].x : kk == 1 ? a[r].y : kk == 2 ? a[r].z : a[r].w;
-        const float av = NEG ? -ap : ap;
+        const real ap = kk == 0 ? a[r].x : kk == 1 ? a[r].y : kk == 2 ? a[r].z : a[r].w;
+        const real av = NEG ? -ap : ap;
         const float2 av2 = make_float2(av, av);
 #pragma unroll
         for (int cc = 0; cc < T::TN / 2; ++cc)
@@ -1024,12 +1058,12 @@ BXG_HD void tile_matmul(int lane, const float* A, const float* B, int ld, float*
     for (int r = 0; r < T::TM; ++r) a[r] = ldv4(a0 + r * ld + k0);
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
-      float bv[T::TN];
+      real bv[T::TN];
       load_cols<T::TN>(B + (k0 + kk) * ld + cg * T::TN, bv);
 #pragma unroll
       for (int r = 0; r < T::TM; ++r) {
-        const float ap = kk == 0 ? a[r].x : kk == 1 ? a[r].y : kk == 2 ? a[r].z : a[r].w;
-        const float av = NEG ? -ap : ap;
+        const real ap = kk == 0 ? a[r].x : kk == 1 ? a[r].y : kk == 2 ? a[r].z : a[r].w;
+        const real av = NEG ? -ap : ap;
         const float2 av2 = make_float2(av, av);
 #pragma unroll
         for (int cc = 0; cc < T::TN / 2; ++cc)
@@ -1046,7 +1080,7 @@ BXG_HD void tile_matmul(int lane, const float* A, const float* B, int ld, float*
 #pragma unroll
   for (int r = 0; r < T::TM; ++r)
 #pragma unroll
-    for (int cc = 0; cc < T::TN; ++cc) acc[r * T::TN + cc] = 0.f;
+    for (int cc = 0; cc < T::TN; ++cc) acc[r * T::TN + cc] = R(0.);
 #pragma unroll 1
   for (int k0 = 0; k0 < W; k0 += 4) {
     F4 a[T::TM];
@@ -1054,12 +1088,12 @@ BXG_HD void tile_matmul(int lane, const float* A, const float* B, int ld, float*
     for (int r = 0; r < T::TM; ++r) a[r] = ldv4(a0 + r * ld + k0);
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
-      float bv[T::TN];
+      real bv[T::TN];
       load_cols<T::TN>(B + (k0 + kk) * ld + cg * T::TN, bv);
 #pragma unroll
       for (int r = 0; r < T::TM; ++r) {
-        const float ap = kk == 0 ? a[r].x : kk == 1 ? a[r].y : kk == 2 ? a[r].z : a[r].w;
-        const float av = NEG ? -ap : ap;
+        const real ap = kk == 0 ? a[r].x : kk == 1 ? a[r].y : kk == 2 ? a[r].z : a[r].w;
+        const real av = NEG ? -ap : ap;
 #pragma unroll
         for (int cc = 0; cc < T::TN; ++cc) acc[r * T::TN + cc] += av * bv[cc];
       }
@@ -1094,14 +1128,14 @@ BXG_HD void tile_diagonal(int lane, int n, F f) {
   }
 }
 template <class T>
-BXG_HD void residual_tile(int lane, int n, float* acc, float* ss, float* mx) {
-  tile_diagonal<T>(lane, n, [&](int e) { acc[e] = 1.f + acc[e]; });     // r = I - M X
+BXG_HD void residual_tile(int lane, int n, real* acc, real* ss, real* mx) {
+  tile_diagonal<T>(lane, n, [&](int e) { acc[e] = R(1.) + acc[e]; });     // r = I - M X
 #pragma unroll
-  for (int e = 0; e < T::TM * T::TN; ++e) { *ss += acc[e] * acc[e]; *mx = fmaxf(*mx, fabsf(acc[e])); }
-  tile_diagonal<T>(lane, n, [&](int e) { acc[e] = 1.f + acc[e]; });     // I + r
+  for (int e = 0; e < T::TM * T::TN; ++e) { *ss += acc[e] * acc[e]; *mx = r_max(*mx, r_abs(acc[e])); }
+  tile_diagonal<T>(lane, n, [&](int e) { acc[e] = R(1.) + acc[e]; });     // I + r
 }
 template <class T>
-BXG_HD void store_tile(int lane, float* C, int ld, const float* acc) {
+BXG_HD void store_tile(int lane, real* C, int ld, const real* acc) {
   const int rg = lane / T::CG, cg = lane - rg * T::CG;
 #pragma unroll
   for (int r = 0; r < T::TM; ++r) store_cols<T::TN>(C + (rg * T::TM + r) * ld + cg * T::TN, acc + r * T::TN);
@@ -1116,65 +1150,65 @@ BXG_HD void store_tile(int lane, float* C, int ld, const float* acc) {
 template <class X, int W>
 BXG_HD void minv_newton_schulz_tiles(X& ex, const Ctx& c, Stats* st) {
   using T = Tile<X::G, W>;
-  const Dims& D = *c.D; float* s = c.s;
+  const Dims& D = *c.D; real* s = c.s;
   const int n = D.nv, ld = D.nvp;
-  const float* M = s + D.s_M;
-  float* Xa = s + D.s_Minv;
-  float* Xc = Xa;                      // current estimate
-  float* Q = s + D.s_B;                // I + r, then the candidate
+  const real* M = s + D.s_M;
+  real* Xa = s + D.s_Minv;
+  real* Xc = Xa;                      // current estimate
+  real* Q = s + D.s_B;                // I + r, then the candidate
   typename X::LaneF p_sum, p_max;
   typename X::template LaneVec<T::TM * T::TN> tile;
   // r0 = I - M X
   ex.lanes([&](int lane) {
-    float* acc = tile(lane); float ss = 0.f, mx = 0.f;
+    real* acc = tile(lane); real ss = R(0.), mx = R(0.);
     tile_matmul<T, W, true>(lane, M, Xc, ld, acc);
     residual_tile<T>(lane, n, acc, &ss, &mx);
     store_tile<T>(lane, Q, ld, acc);
     p_sum(lane) = ss; p_max(lane) = mx;
   });
-  float ss0, mx0;
+  real ss0, mx0;
   ex.sum_max(p_sum, p_max, &ss0, &mx0);
-  float nrm0 = mx0 <= 1e-8f ? 0.f : sqrtf(ss0);
-  if (nrm0 > 1.f) {
+  real nrm0 = mx0 <= R(1e-8) ? R(0.) : r_sqrt(ss0);
+  if (nrm0 > R(1.)) {
     // cold start 0.5 M^T / tr(M M^T); M is exactly symmetric
     ex.lanes([&](int lane) {
-      float tr = 0.f;
+      real tr = R(0.);
       for (int i = lane; i < W * ld; i += X::G) tr += M[i] * M[i];
       p_sum(lane) = tr;
     });
-    const float tr = ex.sum(p_sum);
+    const real tr = ex.sum(p_sum);
     // x / tr with one shared reciprocal: q = x * (1/tr) corrected by its own remainder
     // (the correctly rounded quotient whenever 1/tr is; three operations per element
     // instead of a division sequence each)
-    const float rinv = 1.f / tr;
+    const real rinv = R(1.) / tr;
     ex.lanes([&](int lane) {
       for (int i = 4 * lane; i < W * ld; i += 4 * X::G) {
         F4 m = ldv4(M + i);
-        float x[4] = {0.5f * m.x, 0.5f * m.y, 0.5f * m.z, 0.5f * m.w}, q[4];
+        real x[4] = {R(0.5) * m.x, R(0.5) * m.y, R(0.5) * m.z, R(0.5) * m.w}, q[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { q[u] = x[u] * rinv; q[u] = fmaf(fmaf(-tr, q[u], x[u]), rinv, q[u]); }
+        for (int u = 0; u < 4; ++u) { q[u] = x[u] * rinv; q[u] = r_fma(r_fma(-tr, q[u], x[u]), rinv, q[u]); }
         stv4(Xc + i, F4{q[0], q[1], q[2], q[3]});
       }
     });
     st->ns_cold++;
   }
-  float err = 1.f;
+  real err = R(1.);
   for (int it = 0; it < D.ns_iters; ++it) {
     ex.lanes([&](int lane) { tile_matmul<T, W>(lane, Xc, Q, ld, tile(lane)); });   // candidate = X (I + r)
     ex.lanes([&](int lane) { store_tile<T>(lane, Q, ld, tile(lane)); });           // ... replaces I + r
     ex.lanes([&](int lane) {       // r' = I - M candidate
-      float* acc = tile(lane); float ss = 0.f, mx = 0.f;
+      real* acc = tile(lane); real ss = R(0.), mx = R(0.);
       tile_matmul<T, W, true>(lane, M, Q, ld, acc);
       residual_tile<T>(lane, n, acc, &ss, &mx);
       p_sum(lane) = ss; p_max(lane) = mx;
     });
-    float s2, m2;
+    real s2, m2;
     ex.sum_max(p_sum, p_max, &s2, &m2);
-    float err_next = m2 <= 1e-8f ? 0.f : sqrtf(s2);
+    real err_next = m2 <= R(1e-8) ? R(0.) : r_sqrt(s2);
     const bool accept = err_next < err;
-    float* dst = accept ? Xc : Q;     // I + r' replaces the loser
+    real* dst = accept ? Xc : Q;     // I + r' replaces the loser
     ex.lanes([&](int lane) { store_tile<T>(lane, dst, ld, tile(lane)); });
-    if (accept) { float* t = Xc; Xc = Q; Q = t; st->ns_accepts++; }
+    if (accept) { real* t = Xc; Xc = Q; Q = t; st->ns_accepts++; }
     err = err_next;
   }
   if (Xc != Xa) ex.lanes([&](int lane) { for (int i = lane; i < W * ld; i += X::G) Xa[i] = Xc[i]; });
@@ -1190,8 +1224,8 @@ BXG_HD void minv_newton_schulz(X& ex, const Ctx& c, Stats* st) {
 
 // dot of a register row with a shared-memory vector, first `chunks` float4 chunks
 template <int C4>
-BXG_HD float row_dot_n(const float* a, const float* v, int chunks) {
-  float acc = 0.f;
+BXG_HD real row_dot_n(const real* a, const real* v, int chunks) {
+  real acc = R(0.);
 #pragma unroll
   for (int cc = 0; cc < C4; ++cc) {
     if (cc < chunks) {
@@ -1211,8 +1245,8 @@ BXG_HD int nth_set_bit(uint64_t m, int n) {
 #endif
 }
 // dot of a row of A kept in shared memory (128-bit loads of the lane's own row) with a vector
-BXG_HD float smem_row_dot(const float* arow_sm, const float* v, int chunks) {
-  float acc = 0.f;
+BXG_HD real smem_row_dot(const real* arow_sm, const real* v, int chunks) {
+  real acc = R(0.);
   for (int cc = 0; cc < chunks; ++cc) {
     F4 a = ldv4(arow_sm + 4 * cc), b = ldv4(v + 4 * cc);
     acc += a.x * b.x; acc += a.y * b.y; acc += a.z * b.z; acc += a.w * b.w;
@@ -1235,11 +1269,11 @@ template <class X, int VC4, int NC4, int R>
 BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
   constexpr int VW = 4 * VC4, CW = 4 * NC4, G = X::G;
   constexpr bool AREG = R * CW <= 56;
-  const Dims& D = *c.D; float* s = c.s;
+  const Dims& D = *c.D; real* s = c.s;
   const int nv = D.nv, nc = D.nc, ldv = D.nvp, ldj = D.jld, ldc = D.ncp;
-  const float* J = s + D.s_J; const float* Mi = s + D.s_Minv;
-  float* A = s + D.s_A;
-  float* xs = s + D.s_px; float* ys = s + D.s_py; float* ress = s + D.s_pres; float* xns = s + D.s_pxn;
+  const real* J = s + D.s_J; const real* Mi = s + D.s_Minv;
+  real* A = s + D.s_A;
+  real* xs = s + D.s_px; real* ys = s + D.s_py; real* ress = s + D.s_pres; real* xns = s + D.s_pxn;
   int* orig = reinterpret_cast<int*>(s + D.s_pg);   // compact row -> row of J
   typename X::template LaneVec<AREG ? R * CW : 1> arow;
   typename X::template LaneVec<R> bi, xi, yi, gi, xni, resi;
@@ -1250,7 +1284,7 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
   for (int r = 0; r < R; ++r) {
     ex.lanes([&](int lane) {
       int i = lane + r * G;
-      p0(lane) = i < nc && row_active(s, D)[i] ? 1.f : 0.f;   // set by constraint.jacobian (load_env for the incoming state)
+      p0(lane) = i < nc && row_active(s, D)[i] ? R(1.) : R(0.);   // set by constraint.jacobian (load_env for the incoming state)
     });
     if (r * G < 64) am |= (uint64_t)ex.ballot(p0) << (r * G);
     else am_hi |= (uint64_t)ex.ballot(p0) << (r * G - 64);
@@ -1261,13 +1295,13 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
   const int na_lo = __builtin_popcountll(am), na = na_lo + (CW > 64 ? __builtin_popcountll(am_hi) : 0);
 #endif
   if (na == 0) {   // nothing active: the solver would return x = 0 after one trivial iteration
-    ex.lanes([&](int lane) { for (int d = lane; d < nv; d += G) s[D.s_qfc + d] = 0.f; });
+    ex.lanes([&](int lane) { for (int d = lane; d < nv; d += G) s[D.s_qfc + d] = R(0.); });
     st->pg_iters++; st->pg_trials++;
     return;
   }
   const int nch = (na + 3) >> 2;           // float4 chunks that hold active columns
   ex.lanes([&](int lane) {
-    for (int i = lane; i < CW; i += G) { xs[i] = 0.f; ys[i] = 0.f; xns[i] = 0.f; ress[i] = 0.f; }
+    for (int i = lane; i < CW; i += G) { xs[i] = R(0.); ys[i] = R(0.); xns[i] = R(0.); ress[i] = R(0.); }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       int p = lane + r * G;
@@ -1282,40 +1316,40 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       int p = lane + r * G;
-      float* ar = arow(lane) + (AREG ? r * CW : 0);
+      real* ar = arow(lane) + (AREG ? r * CW : 0);
       if constexpr (AREG) {
 #pragma unroll
-        for (int j = 0; j < CW; ++j) ar[j] = 0.f;
+        for (int j = 0; j < CW; ++j) ar[j] = R(0.);
       }
-      bi(lane)[r] = 0.f;
+      bi(lane)[r] = R(0.);
       if (p < na) {
         const int i = orig[p];
-        float jm[VW];
+        real jm[VW];
         smem_row_times_mat<VW, VC4>(J + i * ldj, Mi, ldv, jm);        // (J Minv)[i, :]
-        float bacc = 0.f;
+        real bacc = R(0.);
 #pragma unroll
         for (int cc = 0; cc < VC4; ++cc) {
           F4 f = ldv4(s + D.s_qfs + 4 * cc);
           bacc += jm[4 * cc] * f.x; bacc += jm[4 * cc + 1] * f.y; bacc += jm[4 * cc + 2] * f.z; bacc += jm[4 * cc + 3] * f.w;
         }
         bi(lane)[r] = bacc - s[D.s_aref + i];
-        const float dg = s[D.s_diag + i];
-        float* arow_sm = A + p * ldc;
+        const real dg = s[D.s_diag + i];
+        real* arow_sm = A + p * ldc;
 #pragma unroll 1
         for (int qc = 0; qc < nch; ++qc) {
-          float a4[4];
+          real a4[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int q = 4 * qc + u, iq = orig[q];
-            const float* jq = J + (iq < 0 ? i : iq) * ldj;
-            float acc = 0.f;
+            const real* jq = J + (iq < 0 ? i : iq) * ldj;
+            real acc = R(0.);
 #pragma unroll
             for (int cc = 0; cc < VC4; ++cc) {
               F4 b = ldv4(jq + 4 * cc);
               acc += jm[4 * cc] * b.x; acc += jm[4 * cc + 1] * b.y; acc += jm[4 * cc + 2] * b.z; acc += jm[4 * cc + 3] * b.w;
             }
             if (q == p) acc += dg;
-            a4[u] = iq < 0 ? 0.f : acc;
+            a4[u] = iq < 0 ? R(0.) : acc;
           }
           stv4(arow_sm + 4 * qc, F4{a4[0], a4[1], a4[2], a4[3]});
         }
@@ -1326,98 +1360,98 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
           }
         }
       }
-      xi(lane)[r] = 0.f; yi(lane)[r] = 0.f; gi(lane)[r] = 0.f; xni(lane)[r] = 0.f; resi(lane)[r] = 0.f;
+      xi(lane)[r] = R(0.); yi(lane)[r] = R(0.); gi(lane)[r] = R(0.); xni(lane)[r] = R(0.); resi(lane)[r] = R(0.);
     }
   });
-  float t = 1.f, stepsize = 1.f, error = INFINITY;
-  const float tol = 1e-3f, eps = 1.1920929e-07f;
+  real t = R(1.), stepsize = R(1.), error = INFINITY;
+  const real tol = R(1e-3), eps = r_eps();
   int it = 0;
   while (it < D.solver_iterations && (it == 0 || error > tol)) {
     // value and gradient at y
     ex.lanes([&](int lane) {
-      float f = 0.f;
+      real f = R(0.);
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         int p = lane + r * G;
         if (p < na) {
-          float rv = (AREG ? row_dot_n<NC4>(arow(lane) + (AREG ? r * CW : 0), ys, nch) : smem_row_dot(A + p * ldc, ys, nch)) + bi(lane)[r];
+          real rv = (AREG ? row_dot_n<NC4>(arow(lane) + (AREG ? r * CW : 0), ys, nch) : smem_row_dot(A + p * ldc, ys, nch)) + bi(lane)[r];
           ress[p] = rv;
-          f += 0.5f * (rv * rv);
+          f += R(0.5) * (rv * rv);
         }
       }
       p0(lane) = f;
     });
-    float fy = ex.sum(p0);
+    real fy = ex.sum(p0);
     ex.lanes([&](int lane) {
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         int j = lane + r * G;
         if (j < na) {
-          float acc = 0.f;
+          real acc = R(0.);
 #pragma unroll 4
           for (int i = 0; i < na; ++i) acc += A[i * ldc + j] * ress[i];
           gi(lane)[r] = acc;
         }
       }
     });
-    float sz = stepsize;
+    real sz = stepsize;
     for (int ls = 0;; ++ls) {
       ex.lanes([&](int lane) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           int p = lane + r * G;
-          if (p < na) { float v = fmaxf(yi(lane)[r] - sz * gi(lane)[r], 0.f); xni(lane)[r] = v; xns[p] = v; }
+          if (p < na) { real v = r_max(yi(lane)[r] - sz * gi(lane)[r], R(0.)); xni(lane)[r] = v; xns[p] = v; }
         }
       });
       ex.lanes([&](int lane) {
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        real a0 = R(0.), a1 = R(0.), a2 = R(0.);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           int p = lane + r * G;
           if (p < na) {
-            float rv = (AREG ? row_dot_n<NC4>(arow(lane) + (AREG ? r * CW : 0), xns, nch) : smem_row_dot(A + p * ldc, xns, nch)) + bi(lane)[r];
+            real rv = (AREG ? row_dot_n<NC4>(arow(lane) + (AREG ? r * CW : 0), xns, nch) : smem_row_dot(A + p * ldc, xns, nch)) + bi(lane)[r];
             resi(lane)[r] = rv;
-            float dlt = xni(lane)[r] - yi(lane)[r];
-            a0 += dlt * dlt; a1 += dlt * gi(lane)[r]; a2 += 0.5f * (rv * rv);
+            real dlt = xni(lane)[r] - yi(lane)[r];
+            a0 += dlt * dlt; a1 += dlt * gi(lane)[r]; a2 += R(0.5) * (rv * rv);
           }
         }
         p0(lane) = a0; p1(lane) = a1; p2(lane) = a2;
       });
-      float sqdist, vd, fn;
+      real sqdist, vd, fn;
       ex.sum3(p0, p1, p2, &sqdist, &vd, &fn);
       st->pg_trials++;
-      float fun_decrease = sz * (fn - fy);
-      float condition = sz * vd + 0.5f * sqdist;
+      real fun_decrease = sz * (fn - fy);
+      real condition = sz * vd + R(0.5) * sqdist;
       if (!(fun_decrease > condition + eps) || ls >= D.solver_maxls) break;
-      sz = sz * 0.5f;
+      sz = sz * R(0.5);
     }
-    stepsize = sz <= 1e-6f ? 1.f : sz / 0.5f;
-    float tn = 0.5f * (1.f + sqrtf(1.f + 4.f * (t * t)));
-    float mom = (t - 1.f) / tn;
+    stepsize = sz <= R(1e-6) ? R(1.) : sz / R(0.5);
+    real tn = R(0.5) * (R(1.) + r_sqrt(R(1.) + R(4.) * (t * t)));
+    real mom = (t - R(1.)) / tn;
     ex.lanes([&](int lane) {
 #pragma unroll
       for (int r = 0; r < R; ++r) { int p = lane + r * G; if (p < na) ress[p] = resi(lane)[r]; }
     });
     ex.lanes([&](int lane) {
-      float e2 = 0.f;
+      real e2 = R(0.);
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         int j = lane + r * G;
         if (j < na) {
-          float acc = 0.f;
+          real acc = R(0.);
 #pragma unroll 4
           for (int i = 0; i < na; ++i) acc += A[i * ldc + j] * ress[i];
-          float xn = xni(lane)[r];
-          float dlt = fmaxf(xn - acc, 0.f) - xn;
+          real xn = xni(lane)[r];
+          real dlt = r_max(xn - acc, R(0.)) - xn;
           e2 += dlt * dlt;
-          float yv = xn + mom * (xn - xi(lane)[r]);
+          real yv = xn + mom * (xn - xi(lane)[r]);
           yi(lane)[r] = yv; ys[j] = yv;
           xi(lane)[r] = xn; xs[j] = xn;
         }
       }
       p0(lane) = e2;
     });
-    error = sqrtf(ex.sum(p0));
+    error = r_sqrt(ex.sum(p0));
     t = tn;
     ++it;
     st->pg_iters++;
@@ -1425,7 +1459,7 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
   // qf_constraint = J^T x over the active rows (lanes read consecutive columns of J)
   ex.lanes([&](int lane) {
     for (int j = lane; j < nv; j += G) {
-      float acc = 0.f;
+      real acc = R(0.);
 #pragma unroll 4
       for (int p = 0; p < na; ++p) acc += J[orig[p] * ldj + j] * xs[p];
       s[D.s_qfc + j] = acc;
@@ -1437,7 +1471,7 @@ template <class X, class Cfg>
 BXG_HD void con_force(X& ex, const Ctx& c, Stats* st) {
   const Dims& D = *c.D;
   if (D.nc == 0) {
-    ex.lanes([&](int lane) { for (int d = lane; d < D.nv; d += X::G) c.s[D.s_qfc + d] = 0.f; });
+    ex.lanes([&](int lane) { for (int d = lane; d < D.nv; d += X::G) c.s[D.s_qfc + d] = R(0.); });
     return;
   }
   if constexpr (Cfg::VC4 > 0 && Cfg::NC4 > 0) {
@@ -1454,74 +1488,74 @@ BXG_HD void con_force(X& ex, const Ctx& c, Stats* st) {
 // capsule axis (third column of the geom's world rotation, brax/contact.py:48-53 with
 // math.quat_to_3x3), and the contact frame's first tangent follows the axis projected
 // into the plane (falls back to y or z when the capsule stands upright).
-BXG_HD void capsule_end(Q4 link_rot, Q4 geom_quat, float half_len, V3 n, V3* centre, V3* t1, V3* t2) {
+BXG_HD void capsule_end(Q4 link_rot, Q4 geom_quat, real half_len, V3 n, V3* centre, V3* t1, V3* t2) {
   Q4 q = qmul(link_rot, geom_quat);
-  float dq = q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z, sc = 2.f / dq;
-  float xs = q.x * sc, ys = q.y * sc, zs = q.z * sc;
-  V3 axis{q.x * zs + q.w * ys, q.y * zs - q.w * xs, 1.f - (q.x * xs + q.y * ys)};
+  real dq = q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z, sc = R(2.) / dq;
+  real xs = q.x * sc, ys = q.y * sc, zs = q.z * sc;
+  V3 axis{q.x * zs + q.w * ys, q.y * zs - q.w * xs, R(1.) - (q.x * xs + q.y * ys)};
   *centre = *centre + axis * half_len;
-  float na = dot(n, axis);
+  real na = dot(n, axis);
   V3 b{axis.x - n.x * na, axis.y - n.y * na, axis.z - n.z * na};
-  bool zero = fabsf(b.x) <= 1e-8f && fabsf(b.y) <= 1e-8f && fabsf(b.z) <= 1e-8f;     // math.safe_norm
-  float bn = zero ? 0.f : sqrtf(b.x * b.x + b.y * b.y + b.z * b.z);
-  float d = bn + 1e-6f * (bn == 0.f ? 1.f : 0.f);
+  bool zero = r_abs(b.x) <= R(1e-8) && r_abs(b.y) <= R(1e-8) && r_abs(b.z) <= R(1e-8);     // math.safe_norm
+  real bn = zero ? R(0.) : r_sqrt(b.x * b.x + b.y * b.y + b.z * b.z);
+  real d = bn + R(1e-6) * (bn == R(0.) ? R(1.) : R(0.));
   b = V3{b.x / d, b.y / d, b.z / d};
-  if (bn < 0.5f) b = (-0.5f < n.y && n.y < 0.5f) ? V3{0.f, 1.f, 0.f} : V3{0.f, 0.f, 1.f};
+  if (bn < R(0.5)) b = (-R(0.5) < n.y && n.y < R(0.5)) ? V3{R(0.), R(1.), R(0.)} : V3{R(0.), R(0.), R(1.)};
   *t1 = b;
   *t2 = cross(n, b);
 }
 
 // z column of math.quat_to_3x3(q): the axis of a capsule whose world orientation is q
 BXG_HD V3 capsule_axis(Q4 q) {
-  float dq = q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z, sc = 2.f / dq;
-  float xs = q.x * sc, ys = q.y * sc, zs = q.z * sc;
-  return V3{q.x * zs + q.w * ys, q.y * zs - q.w * xs, 1.f - (q.x * xs + q.y * ys)};
+  real dq = q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z, sc = R(2.) / dq;
+  real xs = q.x * sc, ys = q.y * sc, zs = q.z * sc;
+  return V3{q.x * zs + q.w * ys, q.y * zs - q.w * xs, R(1.) - (q.x * xs + q.y * ys)};
 }
 // mjx math.normalize_with_norm: x / (n + 1e-6 * (n == 0)), n the safe norm
-BXG_HD V3 normalize_with_norm(V3 v, float* norm) {
-  bool zero = fabsf(v.x) <= 1e-8f && fabsf(v.y) <= 1e-8f && fabsf(v.z) <= 1e-8f;
-  float n = zero ? 0.f : sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
-  float d = n + 1e-6f * (n == 0.f ? 1.f : 0.f);
+BXG_HD V3 normalize_with_norm(V3 v, real* norm) {
+  bool zero = r_abs(v.x) <= R(1e-8) && r_abs(v.y) <= R(1e-8) && r_abs(v.z) <= R(1e-8);
+  real n = zero ? R(0.) : r_sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
+  real d = n + R(1e-6) * (n == R(0.) ? R(1.) : R(0.));
   *norm = n;
   return V3{v.x / d, v.y / d, v.z / d};
 }
 // mjx math.closest_segment_point
 BXG_HD V3 closest_segment_point(V3 a, V3 b, V3 pt) {
   V3 ab = b - a;
-  float t = dot(pt - a, ab) / (dot(ab, ab) + 1e-6f);
-  t = fmaxf(0.f, fminf(t, 1.f));
+  real t = dot(pt - a, ab) / (dot(ab, ab) + R(1e-6));
+  t = r_max(R(0.), r_min(t, R(1.)));
   return a + ab * t;
 }
 // mjx collision_primitive.capsule_capsule: closest points of the two segments
 // (math.closest_segment_to_segment_points), then _sphere_sphere; frame = math.make_frame(n).
 // No reference test pins capsule-capsule numbers (parity unpinned for this pair type).
-BXG_HD_NOINLINE void capsule_capsule(V3 ca, V3 xa, float half_a, float rad_a, V3 cb, V3 xb, float half_b, float rad_b,
-                                     float* dist, V3* pos, V3* n_out, V3* t1, V3* t2) {
+BXG_HD_NOINLINE void capsule_capsule(V3 ca, V3 xa, real half_a, real rad_a, V3 cb, V3 xb, real half_b, real rad_b,
+                                     real* dist, V3* pos, V3* n_out, V3* t1, V3* t2) {
   V3 a0 = ca - xa * half_a, a1 = ca + xa * half_a, b0 = cb - xb * half_b, b1 = cb + xb * half_b;
-  float len_a, len_b;
+  real len_a, len_b;
   V3 dir_a = normalize_with_norm(a1 - a0, &len_a), dir_b = normalize_with_norm(b1 - b0, &len_b);
-  float ha = len_a * 0.5f, hb = len_b * 0.5f;
+  real ha = len_a * R(0.5), hb = len_b * R(0.5);
   V3 a_mid = a0 + dir_a * ha, b_mid = b0 + dir_b * hb;
   V3 trans = a_mid - b_mid;
-  float dab = dot(dir_a, dir_b), dat = dot(dir_a, trans), dbt = dot(dir_b, trans);
-  float denom = 1.f - dab * dab;
-  float orig_t_a = (-dat + dab * dbt) / (denom + 1e-6f);
-  float orig_t_b = dbt + orig_t_a * dab;
-  float t_a = fmaxf(-ha, fminf(orig_t_a, ha)), t_b = fmaxf(-hb, fminf(orig_t_b, hb));
+  real dab = dot(dir_a, dir_b), dat = dot(dir_a, trans), dbt = dot(dir_b, trans);
+  real denom = R(1.) - dab * dab;
+  real orig_t_a = (-dat + dab * dbt) / (denom + R(1e-6));
+  real orig_t_b = dbt + orig_t_a * dab;
+  real t_a = r_max(-ha, r_min(orig_t_a, ha)), t_b = r_max(-hb, r_min(orig_t_b, hb));
   V3 best_a = a_mid + dir_a * t_a, best_b = b_mid + dir_b * t_b;
   V3 new_a = closest_segment_point(a0, a1, best_b), new_b = closest_segment_point(b0, b1, best_a);
   V3 u = new_a - best_b, v = best_a - new_b;
   if (dot(u, u) < dot(v, v)) best_a = new_a; else best_b = new_b;
-  float d;
+  real d;
   V3 n = normalize_with_norm(best_b - best_a, &d);
-  if (d == 0.f) n = V3{1.f, 0.f, 0.f};
+  if (d == R(0.)) n = V3{R(1.), R(0.), R(0.)};
   d = d - (rad_a + rad_b);
   *dist = d;
-  *pos = best_a + n * (rad_a + d * 0.5f);
-  float nn;
+  *pos = best_a + n * (rad_a + d * R(0.5));
+  real nn;
   V3 a = normalize_with_norm(n, &nn);
-  V3 b = (-0.5f < a.y && a.y < 0.5f) ? V3{0.f, 1.f, 0.f} : V3{0.f, 0.f, 1.f};
-  float ab = dot(a, b);
+  V3 b = (-R(0.5) < a.y && a.y < R(0.5)) ? V3{R(0.), R(1.), R(0.)} : V3{R(0.), R(0.), R(1.)};
+  real ab = dot(a, b);
   b = normalize_with_norm(V3{b.x - a.x * ab, b.y - a.y * ab, b.z - a.z * ab}, &nn);
   *n_out = a; *t1 = b; *t2 = cross(a, b);
 }
@@ -1532,21 +1566,21 @@ BXG_HD void con_jacobian(X& ex, const Ctx& c) {
   // contacts between two moving links (capsule-capsule) are compiled into variant 5 and the
   // generic variant only (bxg_model.h picks one of them for such models)
   constexpr bool kTwoBody = Cfg::VC4 == 0 || Cfg::NC4 == 16;
-  const Dims& D = *c.D; const float* mf = c.mf; const int* mi = c.mi; float* s = c.s;
+  const Dims& D = *c.D; const real* mf = c.mf; const int* mi = c.mi; real* s = c.s;
   const int nv = D.nv, nvp = D.jld;
-  float* J = s + D.s_J;
+  real* J = s + D.s_J;
   // J shares its slot with Newton-Schulz scratch: clear it (limit rows and the
   // padding columns rely on zeros)
-  ex.lanes([&](int lane) { for (int i = lane; i < D.nc * nvp; i += X::G) J[i] = 0.f; });
+  ex.lanes([&](int lane) { for (int i = lane; i < D.nc * nvp; i += X::G) J[i] = R(0.); });
   for (int cc = 0; cc < D.ncon; ++cc) {
     int lb = mi[D.m_con_lb + cc];
     // contact.get, plane-sphere / plane-capsule (contact.py:28-67 + mjx): every lane redundantly
     V3 n = ld3(mf + D.m_con_frame + 9 * cc), t1 = ld3(mf + D.m_con_frame + 9 * cc + 3), t2 = ld3(mf + D.m_con_frame + 9 * cc + 6);
-    float rad = mf[D.m_con_rad + cc], mu = mf[D.m_con_mu + cc];
+    real rad = mf[D.m_con_rad + cc], mu = mf[D.m_con_mu + cc];
     V3 sp = ld3(s + D.s_x_pos + 3 * lb) + rotate(ld3(mf + D.m_con_spos + 3 * cc), ld4(s + D.s_x_rot + 4 * lb));
     if (mi[D.m_con_kind + cc] == BXG_CON_PLANE_CAPSULE_END) capsule_end(ld4(s + D.s_x_rot + 4 * lb), ld4(mf + D.m_con_gquat + 4 * cc), mf[D.m_con_half + cc], n, &sp, &t1, &t2);
-    float dist = dot(sp - ld3(mf + D.m_con_ppos + 3 * cc), n) - rad;
-    V3 pos = sp - n * (rad + 0.5f * dist);
+    real dist = dot(sp - ld3(mf + D.m_con_ppos + 3 * cc), n) - rad;
+    V3 pos = sp - n * (rad + R(0.5) * dist);
     int la = -1; uint32_t alo = 0u, ahi = 0u;
     if constexpr (kTwoBody) {
       if (mi[D.m_con_kind + cc] == BXG_CON_CAPSULE_CAPSULE) {
@@ -1558,20 +1592,20 @@ BXG_HD void con_jacobian(X& ex, const Ctx& c) {
                         &dist, &pos, &n, &t1, &t2);
       }
     }
-    bool active = dist < 0.f;
+    bool active = dist < R(0.);
     V3 off = pos - ld3(s + D.s_root_com + 3 * lb);
-    V3 off_a = la >= 0 ? pos - ld3(s + D.s_root_com + 3 * la) : V3{0.f, 0.f, 0.f};
+    V3 off_a = la >= 0 ? pos - ld3(s + D.s_root_com + 3 * la) : V3{R(0.), R(0.), R(0.)};
     uint32_t lo = (uint32_t)mi[D.m_con_anc_lo + cc], hi = (uint32_t)mi[D.m_con_anc_hi + cc];
     V3 dir[4];
     for (int k = 0; k < 4; ++k) {
-      V3 tt = k < 2 ? t1 : t2; float f = (k & 1) ? mu : -mu;
+      V3 tt = k < 2 ? t1 : t2; real f = (k & 1) ? mu : -mu;
       dir[k] = V3{(-tt.x) * f + n.x, (-tt.y) * f + n.y, (-tt.z) * f + n.z};
     }
     ex.lanes([&](int lane) {
       if (lane == 0) s[D.s_dist + cc] = dist;
       for (int d = lane; d < nv; d += X::G) {
         uint32_t bit = d < 32 ? (lo >> d) & 1u : (hi >> (d - 32)) & 1u;
-        float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+        real r0 = R(0.), r1 = R(0.), r2 = R(0.), r3 = R(0.);
         if (active && bit) {
           V3 a = ld3(s + D.s_cdof_ang + 3 * d), v = ld3(s + D.s_cdof_vel + 3 * d);
           V3 df = v - cross(off, a);
@@ -1582,7 +1616,7 @@ BXG_HD void con_jacobian(X& ex, const Ctx& c) {
           if (active && abit) {
             V3 a = ld3(s + D.s_cdof_ang + 3 * d), v = ld3(s + D.s_cdof_vel + 3 * d);
             V3 ja = v - cross(off_a, a);
-            V3 jb = bit ? v - cross(off, a) : V3{0.f, 0.f, 0.f};
+            V3 jb = bit ? v - cross(off, a) : V3{R(0.), R(0.), R(0.)};
             V3 df = jb - ja;
             r0 = dot(df, dir[0]); r1 = dot(df, dir[1]); r2 = dot(df, dir[2]); r3 = dot(df, dir[3]);
           }
@@ -1594,17 +1628,17 @@ BXG_HD void con_jacobian(X& ex, const Ctx& c) {
     ex.lanes([&](int lane) {
       if (lane >= 4) return;
       int row = 4 * cc + lane;
-      float diag = 0.f, aref = 0.f;
+      real diag = R(0.), aref = R(0.);
       if (active) {
-        float vel = 0.f;
+        real vel = R(0.);
         for (int d = 0; d < nv; ++d) vel += J[row * nvp + d] * s[D.s_qd + d];
-        float imp;
+        real imp;
         int spi = cc;
         if constexpr (Cfg::NC4 >= 20) spi = mi[D.m_con_sp_idx + cc];   // 80-row variant: distinct parameter sets stored once
         imp_aref(mf + D.m_con_sp + kImpStride * spi, dist, vel, &imp, &aref);
-        float tw = mf[D.m_link_invw + lb];  // link_a is the world: contributes 0
+        real tw = mf[D.m_link_invw + lb];  // link_a is the world: contributes 0
         if constexpr (kTwoBody) { if (la >= 0) tw = mf[D.m_link_invw + la] + mf[D.m_link_invw + lb]; }   // invweight[a] * (a > -1) + invweight[b]
-        diag = (tw + mu * mu * tw) * (2.f * mu * mu * (1.f - imp) / (imp + 1e-8f));
+        diag = (tw + mu * mu * tw) * (R(2.) * mu * mu * (R(1.) - imp) / (imp + R(1e-8)));
       }
       s[D.s_diag + row] = diag; s[D.s_aref + row] = aref; row_active(s, D)[row] = active ? 1 : 0;
     });
@@ -1613,18 +1647,18 @@ BXG_HD void con_jacobian(X& ex, const Ctx& c) {
     ex.lanes([&](int lane) {
       for (int r = lane; r < D.nlim; r += X::G) {
         int d = mi[D.m_lim_dof + r], row = 4 * D.ncon + r;
-        float q = s[D.s_q + mi[D.m_dof_qidx + d]];
-        float pos_min = q - mf[D.m_lim_lo + d], pos_max = mf[D.m_lim_hi + d] - q;
-        float pos = fminf(fminf(pos_min, pos_max), 0.f);
-        bool active = pos < 0.f;
-        float side = active ? (pos_min < pos_max ? 1.f : -1.f) : 0.f;
-        float diag = 0.f, aref = 0.f;
+        real q = s[D.s_q + mi[D.m_dof_qidx + d]];
+        real pos_min = q - mf[D.m_lim_lo + d], pos_max = mf[D.m_lim_hi + d] - q;
+        real pos = r_min(r_min(pos_min, pos_max), R(0.));
+        bool active = pos < R(0.);
+        real side = active ? (pos_min < pos_max ? R(1.) : -R(1.)) : R(0.);
+        real diag = R(0.), aref = R(0.);
         if (active) {
-          float imp;
+          real imp;
           int spi = d;
           if constexpr (Cfg::NC4 >= 20) spi = mi[D.m_dof_sp_idx + d];
           imp_aref(mf + D.m_dof_sp + kImpStride * spi, pos, side * s[D.s_qd + d], &imp, &aref);
-          diag = mf[D.m_dof_invw + d] * (1.f - imp) / (imp + 1e-8f);
+          diag = mf[D.m_dof_invw + d] * (R(1.) - imp) / (imp + R(1e-8));
         }
         J[row * nvp + d] = side;
         s[D.s_diag + row] = diag; s[D.s_aref + row] = aref; row_active(s, D)[row] = active ? 1 : 0;
@@ -1651,9 +1685,9 @@ BXG_HD void update_position_terms(X& ex, const Ctx& c, Stats* st, bool in_step) 
     if constexpr (Cfg::VC4 > 0 && 4 * Cfg::VC4 <= X::G) {   // one lane per row / column
       if (!Cfg::GENERIC_TOO || !c.D->force_generic) { spd_inverse_rows<X, 4 * Cfg::VC4>(ex, c, c.s + c.D->s_M, c.s + c.D->s_Minv, c.s + c.D->s_scr); done = true; }
     }
-    if (!done) spd_inverse(ex, c, c.s + c.D->s_M, c.s + c.D->s_Minv, c.s + c.D->s_scr, nullptr, 0.f);
+    if (!done) spd_inverse(ex, c, c.s + c.D->s_M, c.s + c.D->s_Minv, c.s + c.D->s_scr, nullptr, R(0.));
   } else {
-    if (c.D->ns_iters == 0) spd_inverse(ex, c, c.s + c.D->s_M, c.s + c.D->s_Minv, c.s + c.D->s_scr, nullptr, 0.f);
+    if (c.D->ns_iters == 0) spd_inverse(ex, c, c.s + c.D->s_M, c.s + c.D->s_Minv, c.s + c.D->s_scr, nullptr, R(0.));
     else minv_newton_schulz<X, Cfg>(ex, c, st);
   }
   if (sl & 2) ex.cta_sync();
@@ -1678,10 +1712,10 @@ BXG_HD void substep(X& ex, const Ctx& c, Stats* st) {
 // pipeline.init (pipeline.py:51-61); q, qd already in the slab
 template <class X, class Cfg>
 BXG_HD void init_env(X& ex, const Ctx& c, Stats* st) {
-  const Dims& D = *c.D; float* s = c.s;
+  const Dims& D = *c.D; real* s = c.s;
   ex.lanes([&](int lane) {
-    for (int i = lane; i < D.nv; i += X::G) { s[D.s_qfs + i] = 0.f; s[D.s_qfc + i] = 0.f; s[D.s_qdd + i] = 0.f; }
-    for (int i = lane; i < (D.nc > 0 ? D.nc : 1) * D.jld; i += X::G) s[D.s_J + i] = 0.f;
+    for (int i = lane; i < D.nv; i += X::G) { s[D.s_qfs + i] = R(0.); s[D.s_qfc + i] = R(0.); s[D.s_qdd + i] = R(0.); }
+    for (int i = lane; i < (D.nc > 0 ? D.nc : 1) * D.jld; i += X::G) s[D.s_J + i] = R(0.);
   });
   update_position_terms<X, Cfg, 1>(ex, c, st, false);
 }
@@ -1690,15 +1724,15 @@ BXG_HD void init_env(X& ex, const Ctx& c, Stats* st) {
 // columns past nv / nc are read by compile-time-width loops and must contribute 0).
 template <class X>
 BXG_HD void prepare_env(X& ex, const Ctx& c) {
-  const Dims& D = *c.D; float* s = c.s;
+  const Dims& D = *c.D; real* s = c.s;
   const int ncz = D.nc > 0 ? D.nc : 1;
   ex.lanes([&](int lane) {
     const int G = X::G;
-    for (int i = lane; i < D.nvw * D.nvp; i += G) { s[D.s_M + i] = 0.f; s[D.s_Minv + i] = 0.f; }
-    for (int i = lane; i < ncz * D.jld; i += G) s[D.s_J + i] = 0.f;
-    for (int i = lane; i < D.nvw; i += G) s[D.s_qfs + i] = 0.f;   // read 128 bits at a time: the padding must be zero
-    for (int i = lane; i < D.nv; i += G) { s[D.s_qfc + i] = 0.f; s[D.s_qdd + i] = 0.f; }
-    for (int i = lane; i < D.ncw; i += G) { s[D.s_b + i] = 0.f; s[D.s_px + i] = 0.f; s[D.s_py + i] = 0.f; s[D.s_pg + i] = 0.f; s[D.s_pres + i] = 0.f; s[D.s_pxn + i] = 0.f; }
+    for (int i = lane; i < D.nvw * D.nvp; i += G) { s[D.s_M + i] = R(0.); s[D.s_Minv + i] = R(0.); }
+    for (int i = lane; i < ncz * D.jld; i += G) s[D.s_J + i] = R(0.);
+    for (int i = lane; i < D.nvw; i += G) s[D.s_qfs + i] = R(0.);   // read 128 bits at a time: the padding must be zero
+    for (int i = lane; i < D.nv; i += G) { s[D.s_qfc + i] = R(0.); s[D.s_qdd + i] = R(0.); }
+    for (int i = lane; i < D.ncw; i += G) { s[D.s_b + i] = R(0.); s[D.s_px + i] = R(0.); s[D.s_py + i] = R(0.); s[D.s_pg + i] = R(0.); s[D.s_pres + i] = R(0.); s[D.s_pxn + i] = R(0.); }
   });
 }
 
@@ -1709,27 +1743,27 @@ BXG_HD void prepare_env(X& ex, const Ctx& c) {
 // (Humanoid), stored in s_red[0..2] by env_prologue.
 // a point fixed in the frame of a link: x.take(link).do(Transform.create(pos=p)).pos
 BXG_HD V3 env_tip(const Ctx& c, const BxgEnvSpec& sp) {
-  const Dims& D = *c.D; const float* s = c.s;
+  const Dims& D = *c.D; const real* s = c.s;
   return ld3(s + D.s_x_pos + 3 * sp.tip_link) + rotate(V3{sp.tip_pos[0], sp.tip_pos[1], sp.tip_pos[2]}, ld4(s + D.s_x_rot + 4 * sp.tip_link));
 }
 // x.take(link).do(Transform.create(pos=inertia.transform.pos[link])).pos: the link's centre of mass
 BXG_HD V3 env_link_com(const Ctx& c, int l) {
-  const Dims& D = *c.D; const float* s = c.s;
+  const Dims& D = *c.D; const real* s = c.s;
   return ld3(s + D.s_x_pos + 3 * l) + rotate(ld3(c.mf + D.m_in_pos + 3 * l), ld4(s + D.s_x_rot + 4 * l));
 }
 // math.safe_norm (brax/math.py:308-328)
-BXG_HD float env_safe_norm(V3 v) {
-  bool zero = fabsf(v.x) <= 1e-8f && fabsf(v.y) <= 1e-8f && fabsf(v.z) <= 1e-8f;
-  return zero ? 0.f : sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
+BXG_HD real env_safe_norm(V3 v) {
+  bool zero = r_abs(v.x) <= R(1e-8) && r_abs(v.y) <= R(1e-8) && r_abs(v.z) <= R(1e-8);
+  return zero ? R(0.) : r_sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
 }
 
 // whole-model centre of mass from link poses in s_x_pos / s_x_rot
 // (envs/humanoid.py:339-354 `_com`); every lane computes it redundantly
 BXG_HD V3 env_com(const Ctx& c) {
-  const Dims& D = *c.D; const float* mf = c.mf; const float* s = c.s;
-  V3 msum{0, 0, 0}; float mtot = 0.f;
+  const Dims& D = *c.D; const real* mf = c.mf; const real* s = c.s;
+  V3 msum{0, 0, 0}; real mtot = R(0.);
   for (int l = 0; l < D.L; ++l) {
-    float m = mf[D.m_in_mass + l];
+    real m = mf[D.m_in_mass + l];
     V3 xi = ld3(s + D.s_x_pos + 3 * l) + rotate(ld3(mf + D.m_in_pos + 3 * l), ld4(s + D.s_x_rot + 4 * l));
     msum = msum + xi * m; mtot += m;
   }
@@ -1737,9 +1771,9 @@ BXG_HD V3 env_com(const Ctx& c) {
 }
 
 // captures the pre-step reference point and rescales the action (Humanoid)
-template <class X>
-BXG_HD void env_prologue(X& ex, const Ctx& c, const BxgEnvSpec& sp, const BxgState& g, int64_t e) {
-  const Dims& D = *c.D; const float* mf = c.mf; float* s = c.s;
+template <class X, class ST>
+BXG_HD void env_prologue(X& ex, const Ctx& c, const BxgEnvSpec& sp, const ST& g, int64_t e) {
+  const Dims& D = *c.D; const real* mf = c.mf; real* s = c.s;
   const int L = D.L;
   ex.lanes([&](int lane) {
     for (int i = lane; i < L * 3; i += X::G) s[D.s_x_pos + i] = g.x_pos[e * L * 3 + i];
@@ -1747,17 +1781,17 @@ BXG_HD void env_prologue(X& ex, const Ctx& c, const BxgEnvSpec& sp, const BxgSta
     if (sp.kind == BXG_ENV_COM_VELOCITY || sp.kind == BXG_ENV_CARTPOLE || sp.kind == BXG_ENV_STANDUP || sp.kind == BXG_ENV_PUSHER) {
       // action = (a + 1) * (hi - lo) * 0.5 + lo   (envs/humanoid.py:260-262, inverted_pendulum.py:134-137)
       for (int a = lane; a < D.nu; a += X::G) {
-        float lo = mf[D.m_act_clo + a], hi = mf[D.m_act_chi + a];
-        s[D.s_act + a] = (s[D.s_act + a] + 1.f) * (hi - lo) * 0.5f + lo;
+        real lo = mf[D.m_act_clo + a], hi = mf[D.m_act_chi + a];
+        s[D.s_act + a] = (s[D.s_act + a] + R(1.)) * (hi - lo) * R(0.5) + lo;
       }
     }
   });
   V3 ref = sp.kind == BXG_ENV_COM_VELOCITY ? env_com(c) : ld3(s + D.s_x_pos);
-  if (sp.kind == BXG_ENV_SWIMMER) ref = V3{s[D.s_q], s[D.s_q + 1], 0.f};   // pipeline_state0.q[:2] (envs/swimmer.py:165-167)
+  if (sp.kind == BXG_ENV_SWIMMER) ref = V3{s[D.s_q], s[D.s_q + 1], R(0.)};   // pipeline_state0.q[:2] (envs/swimmer.py:165-167)
   if (sp.kind == BXG_ENV_PUSHER) {
     // reward_near / reward_dist come from the PRE-step state (envs/pusher.py:204-211: state.pipeline_state.x)
     V3 obj = env_link_com(c, sp.object_link);
-    ref = V3{-env_safe_norm(obj - env_link_com(c, sp.tip_link)), -env_safe_norm(obj - env_link_com(c, sp.target_link)), 0.f};
+    ref = V3{-env_safe_norm(obj - env_link_com(c, sp.tip_link)), -env_safe_norm(obj - env_link_com(c, sp.target_link)), R(0.)};
   }
   ex.lanes([&](int lane) { if (lane == 0) st3(s + D.s_red, ref); });
 }
@@ -1765,8 +1799,8 @@ BXG_HD void env_prologue(X& ex, const Ctx& c, const BxgEnvSpec& sp, const BxgSta
 // _get_obs (envs/ant.py:271-279, envs/humanoid.py:301-337) from the slab; for the
 // COM kind s_tau must already hold actuator.to_tau at the current q, qd
 template <class X>
-BXG_HD void env_write_obs(X& ex, const Ctx& c, const BxgEnvSpec& sp, float* o) {
-  const Dims& D = *c.D; const float* mf = c.mf; float* s = c.s;
+BXG_HD void env_write_obs(X& ex, const Ctx& c, const BxgEnvSpec& sp, real* o) {
+  const Dims& D = *c.D; const real* mf = c.mf; real* s = c.s;
   const int L = D.L, nv = D.nv, nq = D.nq;
   ex.lanes([&](int lane) {
     const int G = X::G;
@@ -1776,10 +1810,10 @@ BXG_HD void env_write_obs(X& ex, const Ctx& c, const BxgEnvSpec& sp, float* o) {
       const int na = nq - 1;
       for (int i = lane; i < nq; i += G) {
         if (i == 0) { o[0] = s[D.s_q]; continue; }
-        float sn, cs; sincosf(s[D.s_q + i], &sn, &cs);
+        real sn, cs; r_sincos(s[D.s_q + i], &sn, &cs);
         o[i] = sn; o[na + i] = cs;
       }
-      for (int i = lane; i < nv; i += G) o[1 + 2 * na + i] = fmaxf(-10.f, fminf(s[D.s_qd + i], 10.f));
+      for (int i = lane; i < nv; i += G) o[1 + 2 * na + i] = r_max(-R(10.), r_min(s[D.s_qd + i], R(10.)));
     } else if (sp.kind == BXG_ENV_PUSHER) {
       // [q[:7], qd[:7], x_i.pos[tips_arm], x_i.pos[object], x_i.pos[goal]]  (envs/pusher.py:224-237)
       const int na = D.nu;
@@ -1788,27 +1822,27 @@ BXG_HD void env_write_obs(X& ex, const Ctx& c, const BxgEnvSpec& sp, float* o) {
     } else if (sp.kind == BXG_ENV_REACHER) {
       // [cos(theta), sin(theta), q[2:], tip_vel[:2], tip_pos - target_pos]  (envs/reacher.py:215-239)
       if (lane == 0) {
-        for (int i = 0; i < 2; ++i) { float sn, cs; sincosf(s[D.s_q + i], &sn, &cs); o[i] = cs; o[2 + i] = sn; }
+        for (int i = 0; i < 2; ++i) { real sn, cs; r_sincos(s[D.s_q + i], &sn, &cs); o[i] = cs; o[2 + i] = sn; }
         for (int i = 2; i < nq; ++i) o[2 + i] = s[D.s_q + i];
         // Transform.create(pos=tip).do(xd.take(tip_link)).vel = vel - tip x ang  (identity rotation, base.py:565-570)
         V3 tp{sp.tip_pos[0], sp.tip_pos[1], sp.tip_pos[2]};
         V3 tv = ld3(s + D.s_xd_vel + 3 * sp.tip_link) - cross(tp, ld3(s + D.s_xd_ang + 3 * sp.tip_link));
         V3 tt = env_tip(c, sp) - ld3(s + D.s_x_pos + 3 * sp.target_link);
-        float* t = o + 2 + nq;
+        real* t = o + 2 + nq;
         t[0] = tv.x; t[1] = tv.y; t[2] = tt.x; t[3] = tt.y; t[4] = tt.z;
       }
     } else if (sp.kind == BXG_ENV_PLANAR) {
       // position = q.at[1].set(x.pos[0, 2]); velocity = clip(qd, -10, 10)  (envs/hopper.py:266-276, walker2d.py:263-273)
       for (int i = lane; i < np; i += G) o[i] = sp.obs_skip + i == 1 ? s[D.s_x_pos + 2] : s[D.s_q + sp.obs_skip + i];
-      for (int i = lane; i < nv; i += G) o[np + i] = fmaxf(-10.f, fminf(s[D.s_qd + i], 10.f));
+      for (int i = lane; i < nv; i += G) o[np + i] = r_max(-R(10.), r_min(s[D.s_qd + i], R(10.)));
     } else {
       for (int i = lane; i < np; i += G) o[i] = s[D.s_q + sp.obs_skip + i];
       for (int i = lane; i < nv; i += G) o[np + i] = s[D.s_qd + i];
     }
     if (sp.kind == BXG_ENV_COM_VELOCITY || sp.kind == BXG_ENV_STANDUP) {
-      float mass_sum = 0.f;
+      real mass_sum = R(0.);
       for (int l = 0; l < L; ++l) mass_sum += mf[D.m_in_mass + l];
-      float* oi = o + np + nv; float* ov = oi + 10 * L; float* of = ov + 6 * L;
+      real* oi = o + np + nv; real* ov = oi + 10 * L; real* of = ov + 6 * L;
       // com_inertia = [cinr.i (9), mass]: x_i - com is what transform_com used (one tree)
       for (int i = lane; i < L * 10; i += G) { int l = i / 10, k = i - 10 * l; oi[i] = k < 9 ? s[D.s_cinr_i + 9 * l + k] : mf[D.m_in_mass + l]; }
       // com_velocity = [m * (xd.vel - (x_i - x) x xd.ang) / mass_sum, xd.ang]  (humanoid.py:316-323)
@@ -1817,7 +1851,7 @@ BXG_HD void env_write_obs(X& ex, const Ctx& c, const BxgEnvSpec& sp, float* o) {
         V3 off = (xp + rotate(ld3(mf + D.m_in_pos + 3 * l), ld4(s + D.s_x_rot + 4 * l))) - xp;
         V3 ang = ld3(s + D.s_xd_ang + 3 * l);
         V3 v = ld3(s + D.s_xd_vel + 3 * l) - cross(off, ang);
-        float m = mf[D.m_in_mass + l];
+        real m = mf[D.m_in_mass + l];
         ov[6 * l + 0] = m * v.x / mass_sum; ov[6 * l + 1] = m * v.y / mass_sum; ov[6 * l + 2] = m * v.z / mass_sum;
         ov[6 * l + 3] = ang.x; ov[6 * l + 4] = ang.y; ov[6 * l + 5] = ang.z;
       }
@@ -1828,86 +1862,86 @@ BXG_HD void env_write_obs(X& ex, const Ctx& c, const BxgEnvSpec& sp, float* o) {
 
 // observation of a freshly initialised state: action = zeros (humanoid.py:241)
 template <class X>
-BXG_HD void env_reset_obs(X& ex, const Ctx& c, const BxgEnvSpec& sp, float* o) {
-  const Dims& D = *c.D; float* s = c.s;
-  ex.lanes([&](int lane) { for (int a = lane; a < D.nu; a += X::G) s[D.s_act + a] = 0.f; });
+BXG_HD void env_reset_obs(X& ex, const Ctx& c, const BxgEnvSpec& sp, real* o) {
+  const Dims& D = *c.D; real* s = c.s;
+  ex.lanes([&](int lane) { for (int a = lane; a < D.nu; a += X::G) s[D.s_act + a] = R(0.); });
   if (sp.kind == BXG_ENV_COM_VELOCITY || sp.kind == BXG_ENV_STANDUP) actuator_tau(ex, c);
   env_write_obs(ex, c, sp, o);
 }
 
-template <class X>
-BXG_HD void env_epilogue(X& ex, const Ctx& c, const BxgEnvSpec& sp, const BxgEnvIO& io, int64_t e, bool valid, bool* done_out) {
-  const Dims& D = *c.D; const float* mf = c.mf; float* s = c.s;
+template <class X, class IO>
+BXG_HD void env_epilogue(X& ex, const Ctx& c, const BxgEnvSpec& sp, const IO& io, int64_t e, bool valid, bool* done_out) {
+  const Dims& D = *c.D; const real* mf = c.mf; real* s = c.s;
   const int L = D.L, nv = D.nv, nq = D.nq;
   const bool com_kind = sp.kind == BXG_ENV_COM_VELOCITY;
   if (com_kind || sp.kind == BXG_ENV_STANDUP) actuator_tau(ex, c);   // qfrc_actuator at the post-step q, qd (humanoid.py:325-327)
   // ---- reward / done / metrics: every lane redundantly (uniform scalars) ----
   V3 before = ld3(s + D.s_red);
   V3 after = com_kind ? env_com(c) : ld3(s + D.s_x_pos);
-  if (sp.kind == BXG_ENV_SWIMMER) after = V3{s[D.s_q], s[D.s_q + 1], 0.f};   // xy_position = q[:2] (envs/swimmer.py:164)
+  if (sp.kind == BXG_ENV_SWIMMER) after = V3{s[D.s_q], s[D.s_q + 1], R(0.)};   // xy_position = q[:2] (envs/swimmer.py:164)
   V3 vel{(after.x - before.x) / sp.env_dt, (after.y - before.y) / sp.env_dt, (after.z - before.z) / sp.env_dt};
-  float forward_reward = sp.forward_reward_weight * vel.x;   // Ant has no weight (envs/ant.py:240): its spec carries 1.0, exact
-  float z = s[D.s_x_pos + 2];
-  float is_healthy = z < sp.healthy_z_min ? 0.f : 1.f;
-  if (z > sp.healthy_z_max) is_healthy = 0.f;
+  real forward_reward = sp.forward_reward_weight * vel.x;   // Ant has no weight (envs/ant.py:240): its spec carries 1.0, exact
+  real z = s[D.s_x_pos + 2];
+  real is_healthy = z < sp.healthy_z_min ? R(0.) : R(1.);
+  if (z > sp.healthy_z_max) is_healthy = R(0.);
   if (sp.kind == BXG_ENV_PLANAR) {
     // strict ranges on z, the root angle q[2] and every entry of [q[2:], qd]
     // (envs/hopper.py:233-244; walker2d.py:215-219 is the same test without the state range)
-    const float angle = s[D.s_q + 2];
+    const real angle = s[D.s_q + 2];
     bool ok = sp.healthy_z_min < z && z < sp.healthy_z_max && sp.healthy_angle_min < angle && angle < sp.healthy_angle_max;
     for (int i = 2; i < nq; ++i) ok = ok && sp.healthy_state_min < s[D.s_q + i] && s[D.s_q + i] < sp.healthy_state_max;
     for (int i = 0; i < nv; ++i) ok = ok && sp.healthy_state_min < s[D.s_qd + i] && s[D.s_qd + i] < sp.healthy_state_max;
-    is_healthy = ok ? 1.f : 0.f;
+    is_healthy = ok ? R(1.) : R(0.);
   }
-  float healthy_reward = sp.terminate_when_unhealthy ? sp.healthy_reward : sp.healthy_reward * is_healthy;
-  float sq = 0.f;
+  real healthy_reward = sp.terminate_when_unhealthy ? sp.healthy_reward : sp.healthy_reward * is_healthy;
+  real sq = R(0.);
   for (int a = 0; a < D.nu; ++a) sq += s[D.s_act + a] * s[D.s_act + a];
-  float ctrl_cost = sp.ctrl_cost_weight * sq;
-  float reward = com_kind ? (forward_reward + healthy_reward) - ctrl_cost : ((forward_reward + healthy_reward) - ctrl_cost) - 0.f;
-  float done = sp.terminate_when_unhealthy ? 1.f - is_healthy : 0.f;
+  real ctrl_cost = sp.ctrl_cost_weight * sq;
+  real reward = com_kind ? (forward_reward + healthy_reward) - ctrl_cost : ((forward_reward + healthy_reward) - ctrl_cost) - R(0.);
+  real done = sp.terminate_when_unhealthy ? R(1.) - is_healthy : R(0.);
   // the small classic-control envs: their own reward / done; metrics (if any) in ms[]
   const bool simple_kind = sp.kind >= BXG_ENV_CARTPOLE;
-  float ms[BXG_ENV_NUM_METRICS] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  real ms[BXG_ENV_NUM_METRICS] = {R(0.), R(0.), R(0.), R(0.), R(0.), R(0.), R(0.), R(0.), R(0.), R(0.)};
   if (sp.kind == BXG_ENV_CARTPOLE) {
     // reward = 1.0; done = |obs[1]| > 0.2  (envs/inverted_pendulum.py:141-142)
-    reward = 1.0f; done = fabsf(s[D.s_q + 1]) > sp.healthy_angle_max ? 1.f : 0.f;
+    reward = R(1.0); done = r_abs(s[D.s_q + 1]) > sp.healthy_angle_max ? R(1.) : R(0.);
   } else if (sp.kind == BXG_ENV_DOUBLE_CARTPOLE) {
     // envs/inverted_double_pendulum.py:164-177
     V3 tip = env_tip(c, sp);
-    const float x = tip.x, y = tip.z, v1 = s[D.s_qd + 1], v2 = s[D.s_qd + 2];
-    float dist_penalty = 0.01f * (x * x) + (y - 2.f) * (y - 2.f);
-    float vel_penalty = 1e-3f * (v1 * v1) + 5e-3f * (v2 * v2);
-    done = y <= sp.healthy_z_min ? 1.f : 0.f;
-    reward = ((1.f - done) * sp.healthy_reward - dist_penalty) - vel_penalty;
+    const real x = tip.x, y = tip.z, v1 = s[D.s_qd + 1], v2 = s[D.s_qd + 2];
+    real dist_penalty = R(0.01) * (x * x) + (y - R(2.)) * (y - R(2.));
+    real vel_penalty = R(1e-3) * (v1 * v1) + R(5e-3) * (v2 * v2);
+    done = y <= sp.healthy_z_min ? R(1.) : R(0.);
+    reward = ((R(1.) - done) * sp.healthy_reward - dist_penalty) - vel_penalty;
   } else if (sp.kind == BXG_ENV_REACHER) {
     // reward_dist = -safe_norm(obs[-3:]); reward_ctrl = -sum(action^2)  (envs/reacher.py:203-207)
     V3 tt = env_tip(c, sp) - ld3(s + D.s_x_pos + 3 * sp.target_link);
     ms[0] = -env_safe_norm(tt); ms[1] = -sq;
-    reward = ms[0] + ms[1]; done = 0.f;
+    reward = ms[0] + ms[1]; done = R(0.);
   } else if (sp.kind == BXG_ENV_PUSHER) {
     // reward = reward_dist + 0.1 * reward_ctrl + 0.5 * reward_near  (envs/pusher.py:212-215); before = (near, dist) of the old state
     ms[0] = before.y; ms[1] = -sq; ms[2] = before.x;
-    reward = (ms[0] + 0.1f * ms[1]) + 0.5f * ms[2]; done = 0.f;
+    reward = (ms[0] + R(0.1) * ms[1]) + R(0.5) * ms[2]; done = R(0.);
   } else if (sp.kind == BXG_ENV_STANDUP) {
     // uph_cost = (z - 0) / dt; reward = uph_cost + 1 - 0.01 * sum(action^2)  (envs/humanoidstandup.py:227-236)
-    float uph_cost = (z - 0.f) / sp.env_dt;
-    reward = (uph_cost + sp.healthy_reward) - ctrl_cost; done = 0.f;
+    real uph_cost = (z - R(0.)) / sp.env_dt;
+    reward = (uph_cost + sp.healthy_reward) - ctrl_cost; done = R(0.);
     ms[0] = uph_cost; ms[1] = -ctrl_cost;
   } else if (sp.kind == BXG_ENV_SWIMMER) {
     // envs/swimmer.py:168-183 (jp.linalg.norm, not safe_norm; 'forward_reward' is never updated)
-    reward = forward_reward - ctrl_cost; done = 0.f;
+    reward = forward_reward - ctrl_cost; done = R(0.);
     ms[0] = forward_reward; ms[2] = -ctrl_cost; ms[4] = after.x; ms[5] = after.y;
-    ms[6] = sqrtf(after.x * after.x + after.y * after.y); ms[7] = vel.x; ms[8] = vel.y;
+    ms[6] = r_sqrt(after.x * after.x + after.y * after.y); ms[7] = vel.x; ms[8] = vel.y;
   }
   // EpisodeWrapper (wrappers/training.py:98-135) after AutoResetWrapper's step reset (:141-146)
-  float trunc = 0.f;
+  real trunc = R(0.);
   if (io.steps && valid) {
-    float steps = io.done[e] != 0.f ? 0.f : io.steps[e];
-    steps += 1.f;
-    if (sp.episode_length > 0 && steps >= (float)sp.episode_length) { trunc = 1.f - done; done = 1.f; }
+    real steps = io.done[e] != R(0.) ? R(0.) : io.steps[e];
+    steps += R(1.);
+    if (sp.episode_length > 0 && steps >= (real)sp.episode_length) { trunc = R(1.) - done; done = R(1.); }
     ex.lanes([&](int lane) { if (lane == 0) { io.steps[e] = steps; if (io.truncation) io.truncation[e] = trunc; } });
   }
-  *done_out = done != 0.f;
+  *done_out = done != R(0.);
   if (!valid) return;
   const int osz = env_obs_size(D, sp);
   const bool use_first = *done_out && io.first_state != nullptr;
@@ -1915,23 +1949,23 @@ BXG_HD void env_epilogue(X& ex, const Ctx& c, const BxgEnvSpec& sp, const BxgEnv
     const int G = X::G;
     if (lane == 0) {
       io.reward[e] = reward; io.done[e] = done;
-      float* m = io.metrics + e * BXG_ENV_NUM_METRICS;
-      float dist;
+      real* m = io.metrics + e * BXG_ENV_NUM_METRICS;
+      real dist;
       if (simple_kind) {
         for (int i = 0; i < BXG_ENV_NUM_METRICS; ++i) m[i] = ms[i];
       } else if (com_kind) {
-        dist = sqrtf(after.x * after.x + after.y * after.y + after.z * after.z);
+        dist = r_sqrt(after.x * after.x + after.y * after.y + after.z * after.z);
         m[0] = forward_reward; m[1] = forward_reward; m[2] = -ctrl_cost; m[3] = healthy_reward;
-        m[4] = after.x; m[5] = after.y; m[6] = dist; m[7] = vel.x; m[8] = vel.y; m[9] = 0.f;
+        m[4] = after.x; m[5] = after.y; m[6] = dist; m[7] = vel.x; m[8] = vel.y; m[9] = R(0.);
       } else {
-        bool zero = fabsf(after.x) <= 1e-8f && fabsf(after.y) <= 1e-8f && fabsf(after.z) <= 1e-8f;  // math.safe_norm
-        dist = zero ? 0.f : sqrtf(after.x * after.x + after.y * after.y + after.z * after.z);
-        m[0] = forward_reward; m[1] = healthy_reward; m[2] = -ctrl_cost; m[3] = -0.f;
+        bool zero = r_abs(after.x) <= R(1e-8) && r_abs(after.y) <= R(1e-8) && r_abs(after.z) <= R(1e-8);  // math.safe_norm
+        dist = zero ? R(0.) : r_sqrt(after.x * after.x + after.y * after.y + after.z * after.z);
+        m[0] = forward_reward; m[1] = healthy_reward; m[2] = -ctrl_cost; m[3] = -R(0.);
         m[4] = after.x; m[5] = after.y; m[6] = dist; m[7] = vel.x; m[8] = vel.y; m[9] = forward_reward;
       }
     }
     if (use_first) {   // AutoResetWrapper: obs = where(done, first_obs, obs)
-      float* o = io.obs + e * osz;
+      real* o = io.obs + e * osz;
       for (int i = lane; i < osz; i += G) o[i] = io.first_obs[e * osz + i];
     }
   });
@@ -1939,13 +1973,13 @@ BXG_HD void env_epilogue(X& ex, const Ctx& c, const BxgEnvSpec& sp, const BxgEnv
 }
 
 // AutoResetWrapper for the pipeline state: copy first_state's leaves for a done env
-template <class X>
-BXG_HD void store_first_state(X& ex, const Ctx& c, const BxgState& g, const BxgState& f, int64_t e) {
+template <class X, class ST>
+BXG_HD void store_first_state(X& ex, const Ctx& c, const ST& g, const ST& f, int64_t e) {
   const Dims& D = *c.D;
   const int L = D.L, nv = D.nv, nq = D.nq, nc = D.nc;
   ex.lanes([&](int lane) {
     const int G = X::G;
-    auto cp = [&](float* dst, const float* src, int n) { for (int i = lane; i < n; i += G) dst[e * n + i] = src[e * n + i]; };
+    auto cp = [&](real* dst, const real* src, int n) { for (int i = lane; i < n; i += G) dst[e * n + i] = src[e * n + i]; };
     cp(g.q, f.q, nq); cp(g.qd, f.qd, nv); cp(g.x_pos, f.x_pos, L * 3); cp(g.x_rot, f.x_rot, L * 4);
     cp(g.xd_ang, f.xd_ang, L * 3); cp(g.xd_vel, f.xd_vel, L * 3); cp(g.root_com, f.root_com, L * 3);
     cp(g.cinr_pos, f.cinr_pos, L * 3); cp(g.cinr_rot, f.cinr_rot, L * 4); cp(g.cinr_i, f.cinr_i, L * 9); cp(g.cinr_mass, f.cinr_mass, L);
@@ -1964,9 +1998,10 @@ BXG_HD void io_vec(X& ex, int n, F f) {
 }
 
 // Loads the State leaves pipeline.step reads.
-template <class X>
-BXG_HD void load_env(X& ex, const Ctx& c, const BxgState& g, const float* act, int64_t e) {
-  const Dims& D = *c.D; float* s = c.s;
+// ST: BxgState (include/bxg.h), or the emulator's double-precision twin with the same member names
+template <class X, class ST>
+BXG_HD void load_env(X& ex, const Ctx& c, const ST& g, const real* act, int64_t e) {
+  const Dims& D = *c.D; real* s = c.s;
   const int L = D.L, nv = D.nv, nq = D.nq, nc = D.nc, nvp = D.nvp;
   ex.lanes([&](int lane) {
     const int G = X::G;
@@ -2010,26 +2045,26 @@ BXG_HD void load_env(X& ex, const Ctx& c, const BxgState& g, const float* act, i
   ex.lanes([&](int lane) {
     const int G = X::G, jld = D.jld;
     for (int i = lane; i < nc; i += G) {
-      bool nz = s[D.s_diag + i] != 0.f || s[D.s_aref + i] != 0.f;
+      bool nz = s[D.s_diag + i] != R(0.) || s[D.s_aref + i] != R(0.);
       const int i0 = i % jld;   // (models with more than 2 * jld rows: the start column must wrap as often as needed)
-      for (int k = 0; k < jld && !nz; ++k) { int kk = k + i0; kk = kk >= jld ? kk - jld : kk; nz = s[D.s_J + i * jld + kk] != 0.f; }
+      for (int k = 0; k < jld && !nz; ++k) { int kk = k + i0; kk = kk >= jld ? kk - jld : kk; nz = s[D.s_J + i * jld + kk] != R(0.); }
       row_active(s, D)[i] = nz ? 1 : 0;
     }
   });
 }
 
 template <class X>
-BXG_HD void load_env_qqd(X& ex, const Ctx& c, const float* q, const float* qd, int64_t e) {
-  const Dims& D = *c.D; float* s = c.s;
+BXG_HD void load_env_qqd(X& ex, const Ctx& c, const real* q, const real* qd, int64_t e) {
+  const Dims& D = *c.D; real* s = c.s;
   ex.lanes([&](int lane) {
     for (int i = lane; i < D.nq; i += X::G) s[D.s_q + i] = q[e * D.nq + i];
     for (int i = lane; i < D.nv; i += X::G) s[D.s_qd + i] = qd[e * D.nv + i];
   });
 }
 
-template <class X>
-BXG_HD void store_env(X& ex, const Ctx& c, const BxgState& g, int64_t e, const BxgDiag* dg, const Stats& st) {
-  const Dims& D = *c.D; const float* s = c.s;
+template <class X, class ST>
+BXG_HD void store_env(X& ex, const Ctx& c, const ST& g, int64_t e, const BxgDiag* dg, const Stats& st) {
+  const Dims& D = *c.D; const real* s = c.s;
   const int L = D.L, nv = D.nv, nq = D.nq, nc = D.nc, nvp = D.nvp;
   ex.lanes([&](int lane) {
     const int G = X::G;

@@ -124,11 +124,17 @@ inline int mat_stride(const Variant& v, int w) { return v.VC4 == 6 ? w : row_str
 constexpr int variant_max_threads(int G, int VC4, int NC4 = 0) { return G == 16 ? (VC4 == 6 ? 320 : BXG_G16_MAXT) : (NC4 >= 20 ? 256 : BXG_G32_MAXT); }
 inline bool variant_fits(const Variant& v, int L, int nv, int nc) { return L <= v.max_links && nv <= v.max_nv && nc <= v.max_nc; }
 
-struct PackedModel {
+// blob: the 32-bit words the kernel stages into shared memory (integers and float bit patterns).
+// blob_r: only for R != float (the host emulator's double instantiation, tests/simt/): the same
+// words as values of type R, index for index; the integer view is then `blob`.
+template <class R>
+struct PackedModelT {
   Dims d;
   int variant_id = -1;
   std::vector<uint32_t> blob;
+  std::vector<R> blob_r;
 };
+using PackedModel = PackedModelT<float>;
 
 // Impedance parameters of one constraint row as the kernel reads them: from
 // [timeconst, dampratio, dmin, dmax, width, mid, power] (solref ++ solimp) to
@@ -136,15 +142,20 @@ struct PackedModel {
 // row-constant subexpressions of constraint._imp_aref (constraint.py:40-61), evaluated here in
 // float with the same operations the oracle applies, instead of four divisions per call.
 constexpr int kImpStride = 9;
-inline void pack_impedance(const float* p7, float* o9) {
-  const float tc = p7[0], dr = p7[1], dmin = p7[2], dmax = p7[3], width = p7[4], mid = p7[5], power = p7[6];
+inline float m_pow(float a, float b) { return powf(a, b); }
+inline double m_pow(double a, double b) { return pow(a, b); }
+inline float m_sqrt(float a) { return sqrtf(a); }
+inline double m_sqrt(double a) { return sqrt(a); }
+template <class R>
+inline void pack_impedance(const float* p7, R* o9) {
+  const R tc = p7[0], dr = p7[1], dmin = p7[2], dmax = p7[3], width = p7[4], mid = p7[5], power = p7[6];
   o9[0] = dmin; o9[1] = dmax; o9[2] = width; o9[3] = mid; o9[4] = power;
-  o9[5] = 1.0f / powf(mid, power - 1.f);
-  o9[6] = 1.0f / powf(1.f - mid, power - 1.f);
-  float b = 2.f / (dmax * tc);
-  float k = 1.f / (dmax * dmax * tc * tc * dr * dr);
-  if (dr <= 0.f) b = -dr / dmax;
-  if (tc <= 0.f) k = -tc / (dmax * dmax);
+  o9[5] = R(1) / m_pow(mid, power - R(1));
+  o9[6] = R(1) / m_pow(R(1) - mid, power - R(1));
+  R b = R(2) / (dmax * tc);
+  R k = R(1) / (dmax * dmax * tc * tc * dr * dr);
+  if (dr <= R(0)) b = -dr / dmax;
+  if (tc <= R(0)) k = -tc / (dmax * dmax);
   o9[7] = b; o9[8] = k;
 }
 
@@ -152,43 +163,48 @@ inline void pack_impedance(const float* p7, float* o9) {
 // operations the oracle applies: [ang_scale, vel_scale, cv[3], ca[3]] with
 // frc.ang = ang_scale * w + ca * |w| * w / 64,  frc.vel = vel_scale * v + cv * |v| * v
 constexpr int kFluidStride = 8;
-inline void pack_fluid(const float* inertia_i9, float mass, float viscosity, float density, float* o8) {
-  const float dg[3] = {inertia_i9[0], inertia_i9[4], inertia_i9[8]};
-  float box[3];
+template <class R>
+inline void pack_fluid(const float* inertia_i9, R mass, R viscosity, R density, R* o8) {
+  const R dg[3] = {inertia_i9[0], inertia_i9[4], inertia_i9[8]};
+  R box[3];
   for (int i = 0; i < 3; ++i) {
-    float sum = 0.f;
-    for (int j = 0; j < 3; ++j) sum += dg[j] * (i == j ? -1.f : 1.f);
-    sum = 6.f * (sum > 1e-12f ? sum : 1e-12f);
-    box[i] = sqrtf(sum / mass);
+    R sum = R(0);
+    for (int j = 0; j < 3; ++j) sum += dg[j] * (i == j ? R(-1) : R(1));
+    sum = R(6) * (sum > R(1e-12) ? sum : R(1e-12));
+    box[i] = m_sqrt(sum / mass);
   }
-  const float pi = 3.14159265358979323846f;
-  const float diam = (box[0] + box[1] + box[2]) / 3.f;
+  const R pi = R(3.14159265358979323846);
+  const R diam = (box[0] + box[1] + box[2]) / R(3);
   o8[0] = -pi * (diam * diam * diam) * viscosity;
-  o8[1] = (float)(-3.0 * 3.14159265358979323846) * diam * viscosity;
-  const float bmv[3] = {box[1] * box[2], box[0] * box[2], box[0] * box[1]};
-  const float p2[3] = {box[0] * box[0], box[1] * box[1], box[2] * box[2]};
-  const float p4[3] = {p2[0] * p2[0], p2[1] * p2[1], p2[2] * p2[2]};
-  const float bma[3] = {box[0] * (p4[1] + p4[2]), box[1] * (p4[0] + p4[2]), box[2] * (p4[0] + p4[1])};
-  for (int i = 0; i < 3; ++i) { o8[2 + i] = -0.5f * density * bmv[i]; o8[5 + i] = -1.0f * density * bma[i]; }
+  o8[1] = (R)(-3.0 * 3.14159265358979323846) * diam * viscosity;
+  const R bmv[3] = {box[1] * box[2], box[0] * box[2], box[0] * box[1]};
+  const R p2[3] = {box[0] * box[0], box[1] * box[1], box[2] * box[2]};
+  const R p4[3] = {p2[0] * p2[0], p2[1] * p2[1], p2[2] * p2[2]};
+  const R bma[3] = {box[0] * (p4[1] + p4[2]), box[1] * (p4[0] + p4[2]), box[2] * (p4[0] + p4[1])};
+  for (int i = 0; i < 3; ++i) { o8[2 + i] = R(-0.5) * density * bmv[i]; o8[5 + i] = R(-1.0) * density * bma[i]; }
 }
 
 // distinct rows (bitwise) of an [n, kImpStride] table and the row each entry maps to
-inline void dedup_rows(const std::vector<float>& rows, int n, std::vector<float>* uniq, std::vector<int>* idx) {
+template <class R>
+inline void dedup_rows(const std::vector<R>& rows, int n, std::vector<R>* uniq, std::vector<int>* idx) {
   uniq->clear(); idx->assign(n, 0);
   for (int i = 0; i < n; ++i) {
     int found = -1;
     for (int u = 0; u < (int)uniq->size() / kImpStride && found < 0; ++u)
-      if (memcmp(uniq->data() + u * kImpStride, rows.data() + i * kImpStride, sizeof(float) * kImpStride) == 0) found = u;
+      if (memcmp(uniq->data() + u * kImpStride, rows.data() + i * kImpStride, sizeof(R) * kImpStride) == 0) found = u;
     if (found < 0) { found = (int)uniq->size() / kImpStride; uniq->insert(uniq->end(), rows.begin() + i * kImpStride, rows.begin() + (i + 1) * kImpStride); }
     (*idx)[i] = found;
   }
 }
 
 // Returns empty string on success, else an error message.
-inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force_variant = -1) {
+template <class R>
+inline std::string pack_model_t(const BxgModelDesc& m, PackedModelT<R>* out, int force_variant = -1) {
   Dims& d = out->d;
   std::vector<uint32_t>& b = out->blob;
-  b.clear();
+  std::vector<R>& br = out->blob_r;
+  constexpr bool kWide = sizeof(R) != sizeof(float);
+  b.clear(); br.clear();
   if (m.abi_version != BXG_ABI_VERSION) return "abi_version mismatch";
   if (m.num_links < 1 || m.nv < 1 || m.nq < 1) return "empty model";
   if (m.num_links > 32) return "num_links > 32 not supported";
@@ -217,16 +233,17 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
   d.fluid = m.enable_fluid ? 1 : 0;
   // fluid forces are compiled into the small 8-wide variants (8, 9) and the generic one; the other specialised variants stay exactly as profiled
   auto fluid_ok = [](int k) { return variant(k).VC4 == 0 || (variant(k).G == 4 && variant(k).VC4 == 2); };
-  if (d.fluid && vid >= 0 && !fluid_ok(vid)) return "fluid forces are compiled into kernel variants 3, 8 and 9 only";
-  if (d.fluid && vid < 0) vid = variant_fits(variant(8), L, m.nv, d.nc) ? 8 : (variant_fits(variant(9), L, m.nv, d.nc) ? 9 : 3);
   d.two_body = 0;
   for (int c = 0; c < m.ncon; ++c) if (m.con_kind && m.con_kind[c] == BXG_CON_CAPSULE_CAPSULE) d.two_body = 1;
   // two-body contacts are compiled into variant 5 and the generic one only
   auto two_body_ok = [](int k) { return variant(k).VC4 == 0 || variant(k).NC4 == 16; };
-  if (d.two_body && vid >= 0 && !two_body_ok(vid)) return "capsule-capsule contacts are compiled into kernel variants 3 and 5 only";
-  if (d.two_body && vid < 0) vid = variant_fits(variant(5), L, m.nv, d.nc) ? 5 : 3;
+  // a variant is allowed when it carries every optional code path the model needs; a model is offered to the
+  // allowed variants in kAutoOrder (first fit).  Only an explicitly forced variant can be rejected here.
+  auto allowed = [&](int k) { return (!d.fluid || fluid_ok(k)) && (!d.two_body || two_body_ok(k)); };
+  if (vid >= 0 && vid < kNumVariantsAll && d.fluid && !fluid_ok(vid)) return "fluid forces are compiled into kernel variants 3, 8 and 9 only";
+  if (vid >= 0 && vid < kNumVariantsAll && d.two_body && !two_body_ok(vid)) return "capsule-capsule contacts are compiled into kernel variants 3 and 5 only";
   if (vid < 0) {
-    for (int k : kAutoOrder) { vid = k; if (variant_fits(variant(k), L, m.nv, d.nc)) break; }
+    for (int k : kAutoOrder) { if (!allowed(k)) continue; vid = k; if (variant_fits(variant(k), L, m.nv, d.nc)) break; }
   }
   if (vid >= kNumVariantsAll || !variant_fits(variant(vid), L, m.nv, d.nc)) return "model does not fit the requested kernel variant";
   out->variant_id = vid;
@@ -243,13 +260,18 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
   d.ns_iters = m.matrix_inv_iterations; d.minv_mode = m.minv_mode; d.force_generic = 0; d.sync_level = 1; d.phase_groups = 1;
   d.dt = m.dt; d.gx = m.gravity[0]; d.gy = m.gravity[1]; d.gz = m.gravity[2];
 
-  auto put_i = [&](const std::vector<int>& v) { int o = (int)b.size(); for (int x : v) b.push_back((uint32_t)x); return o; };
-  auto put_f = [&](const float* p, int n) {
+  auto put_i = [&](const std::vector<int>& v) { int o = (int)b.size(); for (int x : v) { b.push_back((uint32_t)x); if (kWide) br.push_back(R(0)); } return o; };
+  auto put_f = [&](const float* p, int n) {   // model constants: float32 values (exact in R)
     int o = (int)b.size();
-    for (int i = 0; i < n; ++i) { union { float f; uint32_t u; } c; c.f = p ? p[i] : 0.f; b.push_back(c.u); }
+    for (int i = 0; i < n; ++i) { union { float f; uint32_t u; } c; c.f = p ? p[i] : 0.f; b.push_back(c.u); if (kWide) br.push_back((R)c.f); }
     return o;
   };
-  auto put_ip = [&](const int32_t* p, int n) { int o = (int)b.size(); for (int i = 0; i < n; ++i) b.push_back((uint32_t)p[i]); return o; };
+  auto put_r = [&](const R* p, int n) {       // constants derived on the host in the scalar type R
+    int o = (int)b.size();
+    for (int i = 0; i < n; ++i) { union { float f; uint32_t u; } c; c.f = (float)p[i]; b.push_back(c.u); if (kWide) br.push_back(p[i]); }
+    return o;
+  };
+  auto put_ip = [&](const int32_t* p, int n) { int o = (int)b.size(); for (int i = 0; i < n; ++i) { b.push_back((uint32_t)p[i]); if (kWide) br.push_back(R(0)); } return o; };
 
   d.m_link_parent = put_ip(m.link_parent, L);
   d.m_link_ndof = put_ip(m.link_ndof, L);
@@ -303,17 +325,17 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
   d.m_lim_lo = put_f(m.has_limit ? m.dof_limit_lo : nullptr, m.nv);
   d.m_lim_hi = put_f(m.has_limit ? m.dof_limit_hi : nullptr, m.nv);
   d.m_dof_invw = put_f(m.dof_invweight, m.nv); {
-    std::vector<float> dsp(m.nv * kImpStride, 0.f);
-    for (int i = 0; i < m.nv; ++i) pack_impedance(m.dof_solver_params + 7 * i, dsp.data() + kImpStride * i);
+    std::vector<R> dsp(m.nv * kImpStride, R(0));
+    for (int i = 0; i < m.nv; ++i) pack_impedance<R>(m.dof_solver_params + 7 * i, dsp.data() + kImpStride * i);
     d.sp_dedup = var.NC4 >= 20 ? 1 : 0;
     d.m_dof_sp_idx = d.m_con_sp_idx = (int)b.size();
     if (d.sp_dedup) {
-      std::vector<int> idx; std::vector<float> uniq;
-      dedup_rows(dsp, m.nv, &uniq, &idx);
+      std::vector<int> idx; std::vector<R> uniq;
+      dedup_rows<R>(dsp, m.nv, &uniq, &idx);
       d.m_dof_sp_idx = put_i(idx);
-      d.m_dof_sp = put_f(uniq.data(), (int)uniq.size());
+      d.m_dof_sp = put_r(uniq.data(), (int)uniq.size());
     } else {
-      d.m_dof_sp = put_f(dsp.data(), m.nv * kImpStride);
+      d.m_dof_sp = put_r(dsp.data(), m.nv * kImpStride);
     }
   }
   int nu1 = m.nu > 0 ? m.nu : 0;
@@ -339,16 +361,16 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
     for (int k = 0; k < 5; ++k) sp[c * 7 + 2 + k] = m.con_solimp[c * 5 + k];
   }
   {
-    std::vector<float> csp(m.ncon * kImpStride + 1, 0.f);
-    for (int c = 0; c < m.ncon; ++c) pack_impedance(sp.data() + 7 * c, csp.data() + kImpStride * c);
+    std::vector<R> csp(m.ncon * kImpStride + 1, R(0));
+    for (int c = 0; c < m.ncon; ++c) pack_impedance<R>(sp.data() + 7 * c, csp.data() + kImpStride * c);
     if (d.sp_dedup && m.ncon > 0) {
-      std::vector<int> idx; std::vector<float> uniq;
+      std::vector<int> idx; std::vector<R> uniq;
       csp.resize(m.ncon * kImpStride);
-      dedup_rows(csp, m.ncon, &uniq, &idx);
+      dedup_rows<R>(csp, m.ncon, &uniq, &idx);
       d.m_con_sp_idx = put_i(idx);
-      d.m_con_sp = put_f(uniq.data(), (int)uniq.size());
+      d.m_con_sp = put_r(uniq.data(), (int)uniq.size());
     } else {
-      d.m_con_sp = put_f(csp.data(), m.ncon * kImpStride);
+      d.m_con_sp = put_r(csp.data(), m.ncon * kImpStride);
     }
   }
   {
@@ -385,11 +407,11 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
   }
   d.m_fluid = (int)b.size();
   if (d.fluid) {
-    std::vector<float> fl(L * kFluidStride, 0.f);
-    for (int l = 0; l < L; ++l) pack_fluid(m.inertia_i + 9 * l, m.inertia_mass[l], m.viscosity, m.density, fl.data() + kFluidStride * l);
-    d.m_fluid = put_f(fl.data(), L * kFluidStride);
+    std::vector<R> fl(L * kFluidStride, R(0));
+    for (int l = 0; l < L; ++l) pack_fluid<R>(m.inertia_i + 9 * l, (R)m.inertia_mass[l], (R)m.viscosity, (R)m.density, fl.data() + kFluidStride * l);
+    d.m_fluid = put_r(fl.data(), L * kFluidStride);
   }
-  while (b.size() % 4) b.push_back(0);
+  while (b.size() % 4) { b.push_back(0); if (kWide) br.push_back(R(0)); }
   d.model_words = (int)b.size();
 
   // ---- per-env slab ----
@@ -476,6 +498,7 @@ inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force
             d.s_cdofd_vel, d.s_dist, d.s_rowact, d.s_red, o, mat_v, mat_a, mat_j);
   return "";
 }
+inline std::string pack_model(const BxgModelDesc& m, PackedModel* out, int force_variant = -1) { return pack_model_t<float>(m, out, force_variant); }
 
 // Length of one observation vector (shared by the kernels and the C ABI).
 #if defined(__CUDACC__)

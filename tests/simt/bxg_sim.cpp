@@ -8,6 +8,13 @@
 // two orders exposes an intra-phase cross-lane dependency (a race on device).
 // mode bit 0 = reverse lane order, bit 1 = force the generic (non register-row) kernels.
 //
+// Built twice (tests/simt/sim.py): libbxg_sim.so with the product's scalar type (float), and
+// libbxg_sim_f64.so with -DBXG_REAL=double: the same algorithm source in double precision,
+// State leaves as double arrays, so that every variant's LOGIC can be held against the
+// reference-source goldens (float64) to 1e-9 on every leaf (tests/test_kernel_logic_f64.py).
+// The double build carries the physics path only (init / step), not the env epilogue, whose
+// reference constants are Python floats (float64) that BxgEnvSpec holds as float.
+//
 // This is not a CPU fallback: it lives under tests/, is never built by the
 // package and nothing in brax_b200/ can load it.
 #include <string.h>
@@ -19,18 +26,30 @@
 
 namespace {
 
+using bxg::real;
+constexpr bool kF64 = sizeof(real) == 8;
+
+// BxgState with leaves of the scalar type (same member names and order: the Python side passes
+// one struct of 25 pointers either way)
+struct SimState {
+  real *q, *qd, *x_pos, *x_rot, *xd_ang, *xd_vel, *root_com, *cinr_pos, *cinr_rot, *cinr_i, *cinr_mass, *cd_ang, *cd_vel,
+       *cdof_ang, *cdof_vel, *cdofd_ang, *cdofd_vel, *mass_mx, *mass_mx_inv, *con_jac, *con_diag, *con_aref,
+       *qf_smooth, *qf_constraint, *qdd;
+};
+static_assert(sizeof(SimState) == sizeof(BxgState), "SimState mirrors BxgState");
+
 template <int G_>
 struct HostExec {
   static constexpr int G = G_;
   bool reverse = false;
   struct LaneF {
-    float v[G_];
-    float& operator()(int l) { return v[l]; }
+    real v[G_];
+    real& operator()(int l) { return v[l]; }
   };
   template <int N>
   struct LaneVec {
-    float v[G_][N];
-    float* operator()(int l) { return v[l]; }
+    real v[G_][N];
+    real* operator()(int l) { return v[l]; }
   };
   void sync() {}
   void cta_sync() {}
@@ -39,42 +58,43 @@ struct HostExec {
     if (!reverse) for (int l = 0; l < G; ++l) f(l);
     else for (int l = G - 1; l >= 0; --l) f(l);
   }
-  float sum(LaneF& p) {  // same pairing as the xor-shuffle butterfly
-    float a[G_], b[G_];
+  real sum(LaneF& p) {  // same pairing as the xor-shuffle butterfly
+    real a[G_], b[G_];
     memcpy(a, p.v, sizeof a);
     for (int o = G / 2; o >= 1; o >>= 1) { for (int l = 0; l < G; ++l) b[l] = a[l] + a[l ^ o]; memcpy(a, b, sizeof a); }
     return a[0];
   }
-  void sum_max(LaneF& ps, LaneF& pm, float* s_out, float* m_out) { *s_out = sum(ps); *m_out = max(pm); }
-  void sum3(LaneF& p0, LaneF& p1, LaneF& p2, float* o0, float* o1, float* o2) { *o0 = sum(p0); *o1 = sum(p1); *o2 = sum(p2); }
+  void sum_max(LaneF& ps, LaneF& pm, real* s_out, real* m_out) { *s_out = sum(ps); *m_out = max(pm); }
+  void sum3(LaneF& p0, LaneF& p1, LaneF& p2, real* o0, real* o1, real* o2) { *o0 = sum(p0); *o1 = sum(p1); *o2 = sum(p2); }
   uint32_t ballot(LaneF& p) {
     uint32_t b = 0;
-    for (int l = 0; l < G; ++l) if (p.v[l] != 0.f) b |= 1u << l;
+    for (int l = 0; l < G; ++l) if (p.v[l] != real(0)) b |= 1u << l;
     return b;
   }
-  float max(LaneF& p) {
-    float m = p.v[0];
-    for (int l = 1; l < G; ++l) m = fmaxf(m, p.v[l]);
+  real max(LaneF& p) {
+    real m = p.v[0];
+    for (int l = 1; l < G; ++l) m = bxg::r_max(m, p.v[l]);
     return m;
   }
 };
 
 template <class Cfg>
-int run(const BxgModelDesc* desc, int vid, int mode, bool init, int64_t n_env, int n_frames, const float* q, const float* qd,
-        const BxgState* in, const float* act, const BxgState* out, int flags, const BxgDiag* diag,
+int run(const BxgModelDesc* desc, int vid, int mode, bool init, int64_t n_env, int n_frames, const real* q, const real* qd,
+        const SimState* in, const real* act, const SimState* out, int flags, const BxgDiag* diag,
         const BxgEnvSpec* env = nullptr, const BxgEnvIO* eio = nullptr) {
   constexpr int G = Cfg::G;
-  bxg::PackedModel pm;
-  std::string err = bxg::pack_model(*desc, &pm, vid);
+  bxg::PackedModelT<real> pm;
+  std::string err = bxg::pack_model_t<real>(*desc, &pm, vid);
   if (!err.empty()) return 3;
   const bool reverse = mode & 1;
   pm.d.force_generic = (mode & 2) ? 1 : 0;
-  std::vector<float> slab_store(pm.d.env_words + 4);
-  float* slab_base = slab_store.data();
+  std::vector<real> slab_store(pm.d.env_words + 4);
+  real* slab_base = slab_store.data();
   while (reinterpret_cast<uintptr_t>(slab_base) % 16) ++slab_base;
   bxg::Ctx c;
   c.D = &pm.d;
-  c.mf = reinterpret_cast<const float*>(pm.blob.data());
+  if constexpr (kF64) c.mf = reinterpret_cast<const real*>(pm.blob_r.data());
+  else c.mf = reinterpret_cast<const real*>(pm.blob.data());
   c.mi = reinterpret_cast<const int*>(pm.blob.data());
   c.s = slab_base;
   HostExec<G> ex;
@@ -87,19 +107,21 @@ int run(const BxgModelDesc* desc, int vid, int mode, bool init, int64_t n_env, i
     if (init) {
       bxg::load_env_qqd(ex, c, q, qd, e);
       bxg::init_env<HostExec<G>, Cfg>(ex, c, &st);
-      if (env) bxg::env_reset_obs(ex, c, *env, eio->obs + e * bxg::env_obs_size(pm.d, *env));
+      if constexpr (!kF64) { if (env) bxg::env_reset_obs(ex, c, *env, eio->obs + e * bxg::env_obs_size(pm.d, *env)); }
       bxg::store_env(ex, c, *out, e, nullptr, st);
     } else {
       bxg::load_env(ex, c, *in, act, e);
-      if (env) bxg::env_prologue(ex, c, *env, *in, e);
+      if constexpr (!kF64) { if (env) bxg::env_prologue(ex, c, *env, *in, e); }
       for (int f = 0; f < n_frames; ++f) {
         if (pm.d.minv_mode == BXG_MINV_CHOLESKY) bxg::substep<HostExec<G>, Cfg, 1>(ex, c, &st);
         else bxg::substep<HostExec<G>, Cfg, 0>(ex, c, &st);
       }
       bool done = false;
-      if (env) bxg::env_epilogue(ex, c, *env, *eio, e, true, &done);
-      if (done && eio && eio->first_state) bxg::store_first_state(ex, c, *out, *eio->first_state, e);
-      else bxg::store_env(ex, c, *out, e, (flags & BXG_STEP_DIAGNOSTICS) ? diag : nullptr, st);
+      if constexpr (!kF64) {
+        if (env) bxg::env_epilogue(ex, c, *env, *eio, e, true, &done);
+        if (done && eio && eio->first_state) { bxg::store_first_state(ex, c, *out, *reinterpret_cast<const SimState*>(eio->first_state), e); continue; }
+      }
+      bxg::store_env(ex, c, *out, e, (flags & BXG_STEP_DIAGNOSTICS) ? diag : nullptr, st);
     }
   }
   return 0;
@@ -130,25 +152,28 @@ int dispatch(const BxgModelDesc* desc, int vid, A... a) {
 }
 
 extern "C" {
+int sim_sizeof_real() { return (int)sizeof(real); }
 // variant: -1 = the one the library would pick, else a forced kernel variant id
-int sim_init(const BxgModelDesc* desc, int variant, int mode, int64_t n_env, const float* q, const float* qd, const BxgState* out) {
-  return dispatch(desc, variant, mode, true, n_env, 0, q, qd, (const BxgState*)nullptr, (const float*)nullptr, out, 0, (const BxgDiag*)nullptr,
+int sim_init(const BxgModelDesc* desc, int variant, int mode, int64_t n_env, const real* q, const real* qd, const SimState* out) {
+  return dispatch(desc, variant, mode, true, n_env, 0, q, qd, (const SimState*)nullptr, (const real*)nullptr, out, 0, (const BxgDiag*)nullptr,
                   (const BxgEnvSpec*)nullptr, (const BxgEnvIO*)nullptr);
 }
-int sim_step(const BxgModelDesc* desc, int variant, int mode, int64_t n_env, int n_frames, const BxgState* in, const float* act,
-             const BxgState* out, int flags, const BxgDiag* diag) {
-  return dispatch(desc, variant, mode, false, n_env, n_frames, (const float*)nullptr, (const float*)nullptr, in, act, out, flags, diag,
+int sim_step(const BxgModelDesc* desc, int variant, int mode, int64_t n_env, int n_frames, const SimState* in, const real* act,
+             const SimState* out, int flags, const BxgDiag* diag) {
+  return dispatch(desc, variant, mode, false, n_env, n_frames, (const real*)nullptr, (const real*)nullptr, in, act, out, flags, diag,
                   (const BxgEnvSpec*)nullptr, (const BxgEnvIO*)nullptr);
 }
-int sim_env_reset(const BxgModelDesc* desc, int variant, int mode, const BxgEnvSpec* spec, int64_t n_env, const float* q,
-                  const float* qd, const BxgState* out, float* obs) {
+#if !defined(BXG_SIM_F64)
+int sim_env_reset(const BxgModelDesc* desc, int variant, int mode, const BxgEnvSpec* spec, int64_t n_env, const real* q,
+                  const real* qd, const SimState* out, real* obs) {
   BxgEnvIO io{}; io.obs = obs;
-  return dispatch(desc, variant, mode, true, n_env, 0, q, qd, (const BxgState*)nullptr, (const float*)nullptr, out, 0,
+  return dispatch(desc, variant, mode, true, n_env, 0, q, qd, (const SimState*)nullptr, (const real*)nullptr, out, 0,
                   (const BxgDiag*)nullptr, spec, (const BxgEnvIO*)&io);
 }
 int sim_env_step(const BxgModelDesc* desc, int variant, int mode, const BxgEnvSpec* spec, int64_t n_env, int n_frames,
-                 const BxgState* in, const float* action, const BxgState* out, const BxgEnvIO* io) {
-  return dispatch(desc, variant, mode, false, n_env, n_frames, (const float*)nullptr, (const float*)nullptr, in, action, out, 0,
+                 const SimState* in, const real* action, const SimState* out, const BxgEnvIO* io) {
+  return dispatch(desc, variant, mode, false, n_env, n_frames, (const real*)nullptr, (const real*)nullptr, in, action, out, 0,
                   (const BxgDiag*)nullptr, spec, io);
 }
+#endif
 }

@@ -10,23 +10,31 @@ from brax_b200 import native
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, 'libbxg_sim.so')
+_SO64 = os.path.join(_HERE, 'libbxg_sim_f64.so')   # the same source with BXG_REAL = double (kernel logic vs the float64 goldens)
 _SRC = os.path.join(_HERE, 'bxg_sim.cpp')
 _CSRC = os.path.join(os.path.dirname(os.path.dirname(_HERE)), 'brax_b200', 'csrc')
 
 
 def build(force=False):
   deps = [_SRC] + [os.path.join(_CSRC, f) for f in ('bxg_core.cuh', 'bxg_model.h')]
-  if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps):
-    return
-  subprocess.run(['g++', '-O2', '-ffp-contract=off', '-fPIC', '-shared', '-std=c++17', '-Wno-unknown-pragmas', _SRC, '-o', _SO], check=True)
+  jobs = []
+  for so, extra in ((_SO, []), (_SO64, ['-DBXG_REAL=double', '-DBXG_SIM_F64'])):
+    if not force and os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(d) for d in deps):
+      continue
+    jobs.append(subprocess.Popen(['g++', '-O2', '-ffp-contract=off', '-fPIC', '-shared', '-std=c++17', '-Wno-unknown-pragmas'] + extra + [_SRC, '-o', so]))
+  for j in jobs:
+    if j.wait() != 0:
+      raise RuntimeError('g++ failed for the host emulator')
 
 
 class Sim:
-  def __init__(self, sys, variant=-1, reverse=False, minv_mode=native.MINV_NEWTON_SCHULZ, generic=False):
+  def __init__(self, sys, variant=-1, reverse=False, minv_mode=native.MINV_NEWTON_SCHULZ, generic=False, dtype=np.float32):
     """variant: -1 auto, 0 = (G16, nv<=16, nc<=24), 1 = (G32, nv<=24, nc<=28),
     2 = (G32, nv<=32, nc<=32), 3 = generic kernel, 4 = (G16, nv<=24, nc<=28), 5 = (G32, nv<=16, nc<=64)."""
     build()
-    self.lib = ctypes.CDLL(_SO)
+    self.dtype = np.dtype(dtype)
+    self.lib = ctypes.CDLL(_SO if self.dtype == np.float32 else _SO64)
+    assert self.lib.sim_sizeof_real() == self.dtype.itemsize
     self.sys = sys
     self.desc, self._keep = native.make_desc(sys, minv_mode)
     self.G, self.reverse = int(variant), int(reverse) | (2 if generic else 0)
@@ -34,21 +42,21 @@ class Sim:
     self.ncon = len(sys.contact_pairs().geom1)
 
   def alloc(self, n):
-    return {k: np.zeros((n,) + s, np.float32) for k, s in self.shapes.items()}
+    return {k: np.zeros((n,) + s, self.dtype) for k, s in self.shapes.items()}
 
   @staticmethod
-  def _cstate(b):
+  def _cstate(b, dtype=np.float32):
     cs = native.StateC()
     for f in native.STATE_FIELDS:
-      assert b[f].dtype == np.float32 and b[f].flags['C_CONTIGUOUS'], f
+      assert b[f].dtype == dtype and b[f].flags['C_CONTIGUOUS'], f
       setattr(cs, f, b[f].ctypes.data)
     return cs
 
   def init(self, q, qd):
-    q = np.ascontiguousarray(np.atleast_2d(q), np.float32); qd = np.ascontiguousarray(np.atleast_2d(qd), np.float32)
+    q = np.ascontiguousarray(np.atleast_2d(q), self.dtype); qd = np.ascontiguousarray(np.atleast_2d(qd), self.dtype)
     n = q.shape[0]
     out = self.alloc(n)
-    cs = self._cstate(out)
+    cs = self._cstate(out, self.dtype)
     rc = self.lib.sim_init(ctypes.byref(self.desc), self.G, self.reverse, ctypes.c_int64(n),
                            q.ctypes.data_as(ctypes.c_void_p), qd.ctypes.data_as(ctypes.c_void_p), ctypes.byref(cs))
     assert rc == 0, rc
@@ -56,9 +64,10 @@ class Sim:
 
   def step(self, st, act, n_frames=1, diag=False):
     n = st['q'].shape[0]
-    act = np.ascontiguousarray(np.atleast_2d(act), np.float32)
+    act = np.ascontiguousarray(np.atleast_2d(act), self.dtype)
+    st = {k: np.ascontiguousarray(st[k], self.dtype) for k in native.STATE_FIELDS}
     out = self.alloc(n)
-    cin, cout = self._cstate(st), self._cstate(out)
+    cin, cout = self._cstate(st, self.dtype), self._cstate(out, self.dtype)
     dg = native.DiagC()
     con_dist = np.zeros((n, max(self.ncon, 1)), np.float32); stats = np.zeros((n, 4), np.int32)
     dg.con_dist = con_dist.ctypes.data; dg.stats = stats.ctypes.data

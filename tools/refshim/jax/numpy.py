@@ -101,9 +101,15 @@ def take(x, indices, axis=None, mode=None, **kw):
   return _wrap(_np.take(_np.asarray(x), indices, axis=axis, mode=mode or 'raise'))
 
 
+WHERE_HOOK = None   # tools/gen_reference_golden_big.py: observes the reference's branch selections (it never alters them)
+
+
 def where(c, a=None, b=None):
   if a is None:
     return _wrap(_np.where(c))
+  if WHERE_HOOK is not None:
+    import sys as _sys
+    WHERE_HOOK(_sys._getframe(1).f_code.co_name, c)
   return _wrap(_np.where(c, a, b))
 
 
