@@ -132,63 +132,50 @@ class ClockSampler:
             'samples': len(sm), 'reasons': sorted(reasons), 'source': 'nvidia-smi'}
 
 
-def cpu_port_throughput(model, n_frames, seconds_target=12.0, seed=0):
-  """Times the C oracle (a port, NOT the JAX reference) on the host cores on a
-  bounded sample of the same workload.  Returns (env_steps_per_s, cores, sample)."""
-  import numpy as np
-  import torch
-  from brax_b200 import workloads
-  from oracle import oracle as O
-  cores = os.cpu_count() or 1
-  sys_, q, qd = workloads.reset(model, 0, 64 * cores, seed, 'cpu')
-  o = O.Oracle(sys_, np.float32)
-  st = o.init(q.numpy(), qd.numpy())
-  n = q.shape[0]
-  act = workloads.action(model, 0, n, seed, 0, 'cpu').numpy()
-  o.step(st, act, n_frames)  # warm-up
-  t0 = time.perf_counter(); o.step(st, act, n_frames); dt1 = time.perf_counter() - t0
-  reps = max(1, min(200, int(seconds_target / max(dt1, 1e-6))))
-  t0 = time.perf_counter()
-  for k in range(reps):
-    act = workloads.action(model, 0, n, seed, 1 + k, 'cpu').numpy()
-    o.step(st, act, n_frames)
-  dt = time.perf_counter() - t0
-  return n * reps / dt, cores, f'{model}: {n} envs x {reps} env-steps, C oracle -O2 + OpenMP'
-
-
-def run_reference(args, rank, world):
-  """--impl reference: the reference's CPU implementation of the path.  JAX /
-  jaxopt / mujoco are not installable here, so this arm times the
-  oracle port on all host threads, bounded sample per step."""
-  if rank != 0:
-    return
-  model, n_env = WORKLOADS[args.workload]
+def cpu_reference(model, steps, warmup, seconds_target=None, seed=0):
+  """The reference arm AND the cpu_baseline leg: the C oracle (a port of the reference's algorithm, NOT JAX: jax /
+  jaxopt / mujoco are absent from the image and from the GPU box, profiles/r02_probe_reference.log) on the host
+  cores, OpenMP over envs with an EXPLICIT thread count (launchers export OMP_NUM_THREADS=1), on a bounded sample
+  of the workload: 32 envs per thread.  With `seconds_target` the number of timed env-steps is chosen so that the
+  run takes about that long.  Returns a dict."""
   import numpy as np
   from brax_b200 import workloads
   from oracle import oracle as O
   cores = os.cpu_count() or 1
   n = 32 * cores
-  sys_, q, qd = workloads.reset(model, 0, n, 0, 'cpu')
-  o = O.Oracle(sys_, np.float32)
+  sys_, q, qd = workloads.reset(model, 0, n, seed, 'cpu')
+  o = O.Oracle(sys_, np.float32, threads=cores)
   st = o.init(q.numpy(), qd.numpy())
   nf = workloads.N_FRAMES[model]
-  for w in range(args.warmup):
-    o.step(st, workloads.action(model, 0, n, 0, w, 'cpu').numpy(), nf)
-  acts = [workloads.action(model, 0, n, 0, 100 + k, 'cpu').numpy() for k in range(args.steps)]
   t0 = time.perf_counter()
-  for k in range(args.steps):
-    o.step(st, acts[k], nf)
+  for w in range(max(warmup, 1)):
+    o.step(st, workloads.action(model, 0, n, seed, w, 'cpu').numpy(), nf)
+  per_step = (time.perf_counter() - t0) / max(warmup, 1)
+  if seconds_target is not None:
+    steps = max(1, min(400, int(seconds_target / max(per_step, 1e-6))))
+  acts = [workloads.action(model, 0, n, seed, 100 + k, 'cpu').numpy() for k in range(min(steps, 16))]
+  t0 = time.perf_counter()
+  for k in range(steps):
+    o.step(st, acts[k % len(acts)], nf)
   dt = time.perf_counter() - t0
-  val = n * args.steps / dt
-  sample = f'{n} envs x {args.steps} env-steps of {args.workload} per run (bounded sample)'
+  return {'value': n * steps / dt, 'ms_per_step': 1e3 * dt / steps, 'cores': o.threads, 'n_env': n, 'steps': steps, 'nf': nf,
+          'sample': f'{model}: {n} envs x {steps} env-steps, C oracle (-O2, no FMA contraction), OpenMP {o.threads} threads'}
+
+
+def run_reference(args, rank, world):
+  """--impl reference: the reference's CPU implementation of the path (the oracle port: see cpu_reference)."""
+  if rank != 0:
+    return
+  model, n_env = WORKLOADS[args.workload]
+  r = cpu_reference(model, args.steps, args.warmup)
   line = {
-      'impl': 'reference', 'metric': 'env-steps/sec', 'value': val, 'unit': 'env-steps/s', 'n_gpus': args.gpus,
-      'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
+      'impl': 'reference', 'metric': 'env-steps/sec', 'value': r['value'], 'unit': 'env-steps/s', 'n_gpus': args.gpus,
+      'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': r['ms_per_step'],
       'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-      'config': {'workload': args.workload, 'model': model, 'envs_per_gpu': n_env, 'n_frames': nf,
-                 'note': 'CPU restatement (C oracle port), not JAX: jax/jaxopt/mujoco unavailable offline'},
-      'cpu_baseline': {'value': val, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
-      'e2e': {'value': val, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+      'config': {'workload': args.workload, 'model': model, 'envs_per_gpu': n_env, 'n_frames': r['nf'],
+                 'note': 'CPU restatement (C oracle port), not JAX: jax/jaxopt/mujoco unavailable offline; host threads set explicitly'},
+      'cpu_baseline': {'value': r['value'], 'unit': 'env-steps/s', 'cores': r['cores'], 'kind': 'port', 'sample': r['sample']},
+      'e2e': {'value': r['value'], 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
   }
   print(json.dumps(line), flush=True)
 
@@ -204,6 +191,8 @@ def main():
   ap.add_argument('--minv', default='newton_schulz', choices=['newton_schulz', 'cholesky'])
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-extra', action='store_true', help='skip the secondary workload lines')
+  ap.add_argument('--no-ppo', action='store_true', help='skip the end-to-end PPO line (config 5)')
+  ap.add_argument('--ppo-timesteps', type=int, default=6_000_000, help='env-steps per GPU of the PPO line')
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
@@ -245,7 +234,7 @@ def main():
 
   def measure(workload, steps, warmup, with_clocks, minv=minv):
     model, n_env = WORKLOADS[workload]
-    if args.envs:
+    if args.envs and workload == args.workload:
       n_env = args.envs
     nf = workloads.N_FRAMES[model]
     begin = rank * n_env  # weak scaling: every rank has n_env envs; ids are global
@@ -290,7 +279,7 @@ def main():
         'model': model, 'n_env': n_env, 'nf': nf, 'value': total_envs / (kern_avg_ms * 1e-3),
         'ms_per_step': kern_avg_ms, 'kern_avg_ms': kern_avg_ms, 'wall_ms_per_step': 1e3 * wall / steps,
         'ms_per_step_incl_flush': dev_ms_total / steps,
-        'launches': launches, 'clocks': clocks, 'flush': flush, 'nm': nm, 'state': a, 'spare': b, 'acts': acts, 'nonfinite': nonfinite,
+        'launches': launches, 'clocks': clocks, 'flush': flush, 'nm': nm, 'minv': minv, 'state': a, 'spare': b, 'acts': acts, 'nonfinite': nonfinite,
         'begin': begin,
     }
 
@@ -319,73 +308,108 @@ def main():
     return {'value': n_env * world * steps / (ms * 1e-3), 'unit': 'env-steps/s',
             'h2d_bytes_per_step': n_env * sys_.nu * 4, 'd2h_bytes_per_step': n_env * (sys_.nq + sys_.nv) * 4}
 
+  def flops_per_env_step(sysm, nf):
+    # algorithmic FLOPs per env-step at the reference iteration counts: Newton-Schulz
+    # (2*iters + 1 products of 2 nv^3), A = J Minv J^T, ~6.6 matvecs per solver iteration, O(L) terms
+    nv_, nc_ = sysm.nv, native.num_constraints(sysm)
+    per_sub = ((2 * sysm.matrix_inv_iterations + 1) * 2 * nv_ ** 3 + 2 * nc_ * nv_ ** 2 + 2 * nc_ ** 2 * nv_
+               + sysm.solver_iterations * 6.6 * 2 * nc_ ** 2 + 20e3)
+    return per_sub * nf
+
+  def static_traffic(workload, n_env):
+    """DRAM bytes per launch from the committed ncu capture of this workload (profiles/traffic.json): a constant of
+    the kernel's I/O layout (full State in, full State out), NOT measured in this run."""
+    tp = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tp):
+      with open(tp) as f:
+        tj = json.load(f)
+      if workload in tj:
+        return tj[workload]['dram_bytes_per_env_step'] * n_env
+    return None
+
+  def summarize(workload, r, e2e):
+    model = r['model']
+    achieved = workloads.ALGO_BYTES[model] * r['n_env'] / (r['kern_avg_ms'] * 1e-3) / 1e9     # per launch = per rank per step
+    fl = flops_per_env_step(r['nm'].sys, r['nf'])
+    tf = fl * r['n_env'] / (r['kern_avg_ms'] * 1e-3) / 1e12
+    plan = native.plan(r['nm'].sys, r['minv'])
+    shape = r['nm'].launch_shape(r['n_env'])
+    return {
+        'value': r['value'], 'unit': 'env-steps/s', 'ms_per_step': r['ms_per_step'], 'e2e': e2e,
+        'launch': {'variant': plan['variant'], 'lanes_per_env': plan['lanes_per_env'], 'grid': shape['grid'],
+                   'threads_per_cta': shape['threads_per_cta'], 'envs_per_cta': shape['envs_per_cta'],
+                   'smem_bytes_per_cta': shape['smem_bytes_per_cta'], 'envs_per_cta_max': plan['envs_per_cta']},
+        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
+                     'traffic': static_traffic(workload, r['n_env']),
+                     'traffic_source': 'static: ncu dram__bytes of the committed capture (profiles/traffic.json), not measured in this run',
+                     'peak_source': peak_src, 'algorithmic_bytes_per_env_step': workloads.ALGO_BYTES[model],
+                     'note': 'the step is bound on-chip (shared-memory operand delivery and FMA issue of the Newton-Schulz products, '
+                             'then latency), not by HBM (SURVEY 8d); see profiles/ for pipe utilisation'},
+        'fp32': {'achieved': tf, 'peak': FP32_PEAK_TFLOPS, 'unit': 'TFLOP/s', 'frac': tf / FP32_PEAK_TFLOPS, 'flops_per_env_step': fl,
+                 'note': 'theoretical non-tensor FP32 FMA peak (148 SMs x 128 lanes x 2 x 1.965 GHz), not in MEASURED_PEAKS.json; '
+                         'the dense work is fp32 by the parity requirement'},
+        'l2': 'flushed between steps (256 MiB write, outside the per-step event intervals)' if r['flush'] else 'state >> L2, no flush',
+        'nonfinite_envs': r['nonfinite'],
+    }
+
   r = measure(args.workload, args.steps, args.warmup, with_clocks=True)
   e2e = measure_e2e(r, args.steps)
   model = r['model']
-  plan = native.plan(r['nm'].sys, minv)
-  algo_bytes = workloads.ALGO_BYTES[model] * r['n_env']          # per launch (= per rank per step)
-  achieved = algo_bytes / (r['kern_avg_ms'] * 1e-3) / 1e9
-  traffic = None
-  tp = os.path.join(ROOT, 'profiles', 'traffic.json')
-  if os.path.exists(tp):
-    with open(tp) as f:
-      tj = json.load(f)
-    if args.workload in tj:
-      traffic = tj[args.workload]['dram_bytes_per_env_step'] * r['n_env']
-
-  # algorithmic FLOPs per env-step at the reference iteration counts: Newton-Schulz
-  # (2*iters + 1 products of 2 nv^3), A = J Minv J^T, ~6.6 matvecs per solver iteration, O(L) terms
-  sysm = r['nm'].sys
-  nv_, nc_ = sysm.nv, native.num_constraints(sysm)
-  per_sub = ((2 * sysm.matrix_inv_iterations + 1) * 2 * nv_ ** 3 + 2 * nc_ * nv_ ** 2 + 2 * nc_ ** 2 * nv_
-             + sysm.solver_iterations * 6.6 * 2 * nc_ ** 2 + 20e3)
-  flops_per_env_step = per_sub * r['nf']
-  fp32_tflops = flops_per_env_step * r['n_env'] / (r['kern_avg_ms'] * 1e-3) / 1e12
-
+  sm = summarize(args.workload, r, e2e)
   line = {
       'metric': 'env-steps/sec', 'value': r['value'], 'unit': 'env-steps/s', 'n_gpus': world,
       'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': r['ms_per_step'],
       'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
       'config': {'workload': args.workload, 'model': model, 'envs_per_gpu': r['n_env'], 'n_frames': r['nf'],
                  'minv': args.minv, 'parallelism': f'env-shard x{world}, no collective',
-                 'launch': {k: plan[k] for k in ('variant', 'lanes_per_env', 'envs_per_cta', 'smem_bytes_per_cta')},
-                 'l2': 'flushed between steps (256 MiB write, outside the per-step event intervals)' if r['flush'] else 'state >> L2, no flush'},
-      'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
-                   'traffic': traffic, 'peak_source': peak_src,
-                   'algorithmic_bytes_per_env_step': workloads.ALGO_BYTES[model],
-                   'note': 'the step is bound on-chip (Newton-Schulz products: issue / register-bandwidth bound at 53% of FMA peak; then '
-                           'latency), not by HBM (SURVEY 8d); see profiles/ for pipe utilisation'},
-      'fp32': {'achieved': fp32_tflops, 'peak': FP32_PEAK_TFLOPS, 'unit': 'TFLOP/s', 'frac': fp32_tflops / FP32_PEAK_TFLOPS,
-               'flops_per_env_step': flops_per_env_step,
-               'note': 'non-tensor FP32 FMA peak at max clock; the dense work is fp32 by the parity requirement'},
+                 'launch': sm['launch'], 'l2': sm['l2']},
+      'roofline': sm['roofline'], 'fp32': sm['fp32'],
       'e2e': e2e, 'gpu_launches': r['launches'], 'clocks': r['clocks'],
       'kernel_ms': r['kern_avg_ms'], 'wall_ms_per_step': r['wall_ms_per_step'],
       'ms_per_step_incl_l2_flush': r['ms_per_step_incl_flush'], 'nonfinite_envs': r['nonfinite'],
   }
 
-  if not args.no_extra and world == 1:
+  if not args.no_extra:
+    # The metric's other configurations, at EVERY N (BASELINE configs 3 and 4: Ant 1 M envs per GPU; Humanoid 512 k
+    # envs per GPU = 4 M over 8 GPUs, randomised falls), each with its own e2e leg and both roofline fractions; then
+    # the exact-inverse mode on the default workload (north_star's per-env Cholesky solve: NOT the reference's
+    # Newton-Schulz numerics, DESIGN.md section 2); then config 5 (end-to-end PPO on Ant).
     extra = []
-    del r['state'], r['spare']
-    # the other headline configuration, and the exact-inverse mode (north_star's per-env Cholesky solve: NOT
-    # the reference's Newton-Schulz numerics) on the default workload
-    for wl, st_, mv in (('ant_1m', 5, minv), (args.workload, 10, native.MINV_CHOLESKY)):
+    del r['state'], r['spare'], r['nm'], r['acts']
+    for wl, st_, mv in (('ant_1m', 5, minv), ('humanoid_512k', 5, minv), (args.workload, 10, native.MINV_CHOLESKY)):
       if wl == args.workload and mv == minv:
         continue
       try:
         torch.cuda.empty_cache()
         x = measure(wl, st_, 3, with_clocks=False, minv=mv)
-        ab = workloads.ALGO_BYTES[x['model']] * x['n_env'] / (x['kern_avg_ms'] * 1e-3) / 1e9
-        extra.append({'workload': wl, 'minv': 'cholesky' if mv == native.MINV_CHOLESKY else 'newton_schulz',
-                      'value': x['value'], 'unit': 'env-steps/s', 'ms_per_step': x['ms_per_step'],
-                      'steps': st_, 'roofline_frac_hbm': ab / hbm_peak})
+        xe = measure_e2e(x, st_)
+        ent = {'workload': wl, 'model': x['model'], 'envs_per_gpu': x['n_env'], 'n_gpus': world, 'steps': st_,
+               'minv': 'cholesky' if mv == native.MINV_CHOLESKY else 'newton_schulz'}
+        ent.update(summarize(wl, x, xe))
+        extra.append(ent)
         del x
       except Exception as ex:  # report, do not hide
         extra.append({'workload': wl, 'error': repr(ex)})
+    if not args.no_ppo:
+      try:
+        torch.cuda.empty_cache()
+        from brax_b200.training import ppo
+        # notebooks/training.ipynb:250 hyper-parameters (SURVEY 8d config 5); a bounded number of env-steps
+        _, pm = ppo.train('ant', num_envs=4096, episode_length=1000, num_timesteps=args.ppo_timesteps * world, unroll_length=5,
+                          batch_size=2048, num_minibatches=32, num_update_epochs=4, reward_scaling=10.0, entropy_cost=1e-2,
+                          discounting=0.97, learning_rate=3e-4, seed=1, device=dev)
+        extra.append({'workload': 'ppo_ant', 'config': 'BASELINE configs[4]: end-to-end PPO on Ant, 4096 envs per GPU, unroll 5, 32 minibatches x 2048, '
+                      '4 epochs; env-steps/s include policy inference and the learner; gradients and normaliser statistics all-reduced over NCCL',
+                      'n_gpus': world, 'value': max_over_ranks(-pm['sps_steady']) * -1.0, 'unit': 'env-steps/s',
+                      'value_incl_graph_capture': pm['sps'], 'env_steps': pm['env_steps'], 'iterations': pm['iterations'],
+                      'episode_reward': pm['episode_reward']})
+      except Exception as ex:
+        extra.append({'workload': 'ppo_ant', 'error': repr(ex)})
     line['other_workloads'] = extra
 
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
-    v, cores, sample = cpu_port_throughput(model, workloads.N_FRAMES[model])
-    line['cpu_baseline'] = {'value': v, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample}
+    c = cpu_reference(model, 0, 2, seconds_target=12.0)
+    line['cpu_baseline'] = {'value': c['value'], 'unit': 'env-steps/s', 'cores': c['cores'], 'kind': 'port', 'sample': c['sample']}
 
   if rank == 0:
     print(json.dumps(line), flush=True)

@@ -202,6 +202,13 @@ static LaunchShape launch_shape(const BxgModel* m, int64_t n_env) {
   return ls;
 }
 
+int bxg_launch_shape(const BxgModel* m, int64_t n_env, int32_t info[4]) {
+  if (!m || !info || n_env <= 0) return fail(BXG_E_INVALID, "null model or empty batch");
+  LaunchShape ls = launch_shape(m, n_env);
+  info[0] = ls.grid; info[1] = ls.threads; info[2] = (int32_t)ls.smem; info[3] = ls.threads / m->lanes;
+  return BXG_OK;
+}
+
 int bxg_init(const BxgModel* m, int64_t n_env, const float* q, const float* qd, const BxgState* out, void* stream) {
   if (!m) return fail(BXG_E_INVALID, "null model");
   if (n_env <= 0) return n_env == 0 ? BXG_OK : fail(BXG_E_INVALID, "n_env < 0");

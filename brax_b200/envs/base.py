@@ -53,6 +53,8 @@ class FusedEnv:
     self.action_repeat = int(action_repeat)   # EpisodeWrapper's scan over env.step (wrappers/training.py:99-104)
     self.batch_size = batch_size
     self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    if self.device.type == 'cuda' and self.device.index is None:   # 'cuda' means the CURRENT device, not device 0
+      self.device = torch.device('cuda', torch.cuda.current_device())
     self.env_id_offset = int(env_id_offset)   # global id of env 0 (sharding across ranks)
     spec.episode_length = int(episode_length) if episode_length else 0
     spec.env_dt = float(np.float32(sys.opt.timestep) * np.float32(self._n_frames))
@@ -79,7 +81,7 @@ class FusedEnv:
     return self
 
   def _model(self) -> native.NativeModel:
-    return native.model_for(self.sys, self.device.index or 0)
+    return native.model_for(self.sys, self.device.index)
 
   # -- API --------------------------------------------------------------------
   def reset(self, rng) -> State:
@@ -93,6 +95,9 @@ class FusedEnv:
     info: Dict[str, Any] = {}
     if self.episode_length:
       info['steps'] = zeros(); info['truncation'] = zeros()
+      # EpisodeWrapper.reset (wrappers/training.py:83-96)
+      info['episode_done'] = zeros()
+      info['episode_metrics'] = {k: zeros() for k in ('sum_reward', 'length') + self.metric_names}
     if self.auto_reset:
       info['first_pipeline_state'] = PipelineState.from_flat(bufs)
       info['first_obs'] = obs
@@ -136,6 +141,15 @@ class FusedEnv:
     info = dict(state.info)
     if io['steps'] is not None:
       info['steps'] = io['steps']; info['truncation'] = io['truncation']
+    if 'episode_metrics' in state.info:
+      # EpisodeWrapper.step (wrappers/training.py:114-127): episode sums restart after an episode that ended
+      keep = 1.0 - state.info['episode_done']
+      em = state.info['episode_metrics']
+      new = {'sum_reward': em['sum_reward'] * keep + io['reward'], 'length': em['length'] * keep + float(self.action_repeat)}
+      for k in self.metric_names:
+        new[k] = (em[k] * keep + metrics[k]) if k != 'reward' else em[k]
+      info['episode_metrics'] = new
+      info['episode_done'] = io['done']
     return State(PipelineState.from_flat(out), io['obs'], io['reward'], io['done'], metrics, info)
 
   def _reset_q_qd(self, env_begin, n, seed, device):

@@ -197,6 +197,7 @@ def lib() -> ctypes.CDLL:
       l.bxg_model_destroy.argtypes = [ctypes.c_void_p]
       l.bxg_model_num_constraints.argtypes = [ctypes.c_void_p]
       l.bxg_plan.argtypes = [ctypes.POINTER(ModelDesc), ctypes.POINTER(ctypes.c_int32)]
+      l.bxg_launch_shape.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int32)]
       l.bxg_init.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                              ctypes.POINTER(StateC), ctypes.c_void_p]
       l.bxg_step.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(StateC),
@@ -257,18 +258,25 @@ class NativeModel:
     if h is not None and _lib is not None:
       _lib.bxg_model_destroy(h)
 
+  def launch_shape(self, n: int) -> dict:
+    """The launch a batch of n envs actually gets (grid, threads, shared memory, envs per CTA)."""
+    info = (ctypes.c_int32 * 4)()
+    _check(lib().bxg_launch_shape(self._h, n, info), 'bxg_launch_shape')
+    return dict(zip(('grid', 'threads_per_cta', 'smem_bytes_per_cta', 'envs_per_cta'), list(info)))
+
   # -- buffers ---------------------------------------------------------------
   def alloc(self, n: int) -> Dict[str, 'torch.Tensor']:
     import torch
     dev = torch.device('cuda', self.device)
     return {k: torch.empty((n,) + s, dtype=torch.float32, device=dev) for k, s in self.shapes.items()}
 
-  @staticmethod
-  def _cstate(bufs) -> StateC:
+  def _cstate(self, bufs) -> StateC:
     cs = StateC()
     for f in STATE_FIELDS:
       t = bufs[f]
       assert t.is_cuda and t.is_contiguous() and t.dtype.is_floating_point and t.element_size() == 4, f
+      # the model's constants live on self.device and the kernel is launched there: a leaf on another GPU is a bug
+      assert t.device.index == self.device, f'{f} is on cuda:{t.device.index}, the model on cuda:{self.device}'
       setattr(cs, f, t.data_ptr())
     return cs
 

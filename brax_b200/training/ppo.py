@@ -27,7 +27,7 @@ from brax_b200 import envs
 
 class Agent(nn.Module):
   def __init__(self, obs_size: int, act_size: int, hidden=(64, 64), entropy_cost=1e-2, discounting=0.97,
-               reward_scaling=10.0, lambda_=0.95, epsilon=0.3):
+               reward_scaling=10.0, lambda_=0.95, epsilon=0.3, normalize_advantage=True, clip_obs=None):
     super().__init__()
     def mlp(sizes):
       layers = []
@@ -36,25 +36,46 @@ class Agent(nn.Module):
       return nn.Sequential(*layers[:-1])
     self.policy = mlp([obs_size, *hidden, 2 * act_size])
     self.value = mlp([obs_size, *hidden, 1])
+    # running_statistics.RunningStatisticsState (acme/running_statistics.py:62-68): count, mean, summed_variance, std
     self.register_buffer('num_steps', torch.zeros(()))
     self.register_buffer('running_mean', torch.zeros(obs_size))
-    self.register_buffer('running_var', torch.zeros(obs_size))
+    self.register_buffer('running_var', torch.zeros(obs_size))     # summed_variance
+    self.register_buffer('running_std', torch.ones(obs_size))
     self.entropy_cost, self.discounting, self.reward_scaling = entropy_cost, discounting, reward_scaling
     self.lambda_, self.epsilon = lambda_, epsilon
+    self.normalize_advantage = normalize_advantage
+    self.clip_obs = clip_obs
 
   @torch.no_grad()
-  def update_normalization(self, obs):
-    n = obs.shape[0] * obs.shape[1]
-    flat = obs.reshape(n, -1)
-    total = self.num_steps + n
-    delta = flat - self.running_mean
-    self.running_mean += delta.sum(0) / total
-    self.running_var += (delta * (flat - self.running_mean)).sum(0)
-    self.num_steps.copy_(total)
+  def update_normalization(self, obs, group=None):
+    """running_statistics.update (acme/running_statistics.py:120-300, Welford branch) with
+    `pmap_axis_name` = the process group: the step increment, the mean update and the variance
+    update are summed over ranks (`jax.lax.psum`, :174, :262-264, :270-271), so every rank ends
+    with identical statistics.  `group=None` uses the default group when torch.distributed is
+    initialised with more than one rank."""
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    flat = obs.reshape(-1, obs.shape[-1])
+    inc = torch.tensor(float(flat.shape[0]), device=flat.device)
+    if multi:
+      dist.all_reduce(inc, group=group)
+    count = self.num_steps + inc
+    diff_to_old_mean = flat - self.running_mean
+    mean_update = diff_to_old_mean.sum(0) / count
+    if multi:
+      dist.all_reduce(mean_update, group=group)
+    mean = self.running_mean + mean_update
+    variance_update = (diff_to_old_mean * (flat - mean)).sum(0)
+    if multi:
+      dist.all_reduce(variance_update, group=group)
+    self.running_mean.copy_(mean)
+    self.running_var.add_(variance_update)
+    self.num_steps.copy_(count)
+    self.running_std.copy_(torch.clip(torch.sqrt(torch.clamp(self.running_var, min=0) / count), 1e-6, 1e6))
 
   def normalize(self, obs):
-    var = self.running_var / (self.num_steps + 1.0)
-    return torch.clip((obs - self.running_mean) / (var.sqrt() + 1e-6), -5, 5)
+    """running_statistics.normalize (acme/running_statistics.py:303-328)."""
+    out = (obs - self.running_mean) / self.running_std
+    return out if self.clip_obs is None else torch.clip(out, -self.clip_obs, self.clip_obs)
 
   @staticmethod
   def dist_create(logits):
@@ -68,9 +89,11 @@ class Agent(nn.Module):
     return lp.sum(-1)
 
   @staticmethod
-  def dist_entropy(loc, scale):
+  def dist_entropy(loc, scale, noise=None):
+    """ParametricDistribution.entropy (distribution.py:84-91): Gaussian entropy plus the tanh
+    log-det-jacobian at one sample; `noise` stands for the sample's standard normal draw."""
     ent = 0.5 + 0.5 * math.log(2 * math.pi) + torch.log(scale)
-    sample = loc + scale * torch.randn_like(loc)
+    sample = loc + scale * (torch.randn_like(loc) if noise is None else noise)
     ent = ent + 2 * (math.log(2) - sample - torch.nn.functional.softplus(-2 * sample))
     return ent.sum(-1)
 
@@ -96,7 +119,8 @@ class Agent(nn.Module):
     adv = (reward + self.discounting * (1 - termination) * vs_t1 - values) * mask
     return vs, adv
 
-  def loss(self, td: Dict[str, torch.Tensor]):
+  def loss(self, td: Dict[str, torch.Tensor], entropy_noise=None, parts: bool = False):
+    """compute_ppo_loss (agents/ppo/losses.py:143-303) on time-major data."""
     obs = self.normalize(td['obs'])                       # [T+1, B, obs]
     values = self.value(obs).squeeze(-1)
     logits = self.policy(obs[:-1])
@@ -107,16 +131,20 @@ class Agent(nn.Module):
     reward = td['reward'] * self.reward_scaling
     termination = td['done'] * (1 - td['truncation'])
     vs, adv = self.gae(td['truncation'], termination, reward, values[:-1].detach(), values[-1].detach())
+    if self.normalize_advantage:                           # losses.py:236-237 (jnp.std: population standard deviation)
+      adv = (adv - adv.mean()) / (adv.std(unbiased=False) + 1e-8)
     rho = torch.exp(lp - blp)
     policy_loss = -torch.minimum(rho * adv, rho.clip(1 - self.epsilon, 1 + self.epsilon) * adv).mean()
-    v_loss = 0.25 * ((vs - values[:-1]) ** 2).mean()
-    ent_loss = -self.entropy_cost * self.dist_entropy(loc, scale).mean()
-    return policy_loss + v_loss + ent_loss
+    v_loss = 0.25 * ((vs - values[:-1]) ** 2).mean()       # mean(v_error^2) * 0.5 * vf_coefficient(0.5), losses.py:258-270
+    ent_loss = -self.entropy_cost * self.dist_entropy(loc, scale, entropy_noise).mean()
+    total = policy_loss + v_loss + ent_loss
+    return (total, policy_loss, v_loss, ent_loss) if parts else total
 
 
 def train(env_name: str = 'ant', num_envs: int = 2048, episode_length: int = 1000, num_timesteps: int = 1_000_000,
           unroll_length: int = 5, batch_size: int = 1024, num_minibatches: int = 32, num_update_epochs: int = 4,
           reward_scaling: float = 10.0, entropy_cost: float = 1e-2, discounting: float = 0.97, learning_rate: float = 3e-4,
+          normalize_advantage: bool = True,
           seed: int = 0, device=None, use_cuda_graph: bool = True, progress_fn: Optional[Callable[[int, Dict[str, float]], None]] = None):
   """Returns (agent, metrics).  metrics['sps'] = env-steps/sec including policy
   inference and learning (the figure BASELINE config 5 asks for)."""
@@ -127,7 +155,7 @@ def train(env_name: str = 'ant', num_envs: int = 2048, episode_length: int = 100
                     env_id_offset=rank * num_envs)
   torch.manual_seed(seed + rank)
   agent = Agent(env.observation_size, env.action_size, entropy_cost=entropy_cost, discounting=discounting,
-                reward_scaling=reward_scaling).to(device)
+                reward_scaling=reward_scaling, normalize_advantage=normalize_advantage).to(device)
   if world > 1:
     for p in agent.parameters():
       dist.broadcast(p.data, 0)
@@ -188,6 +216,7 @@ def train(env_name: str = 'ant', num_envs: int = 2048, episode_length: int = 100
 
   torch.cuda.synchronize()
   t0 = time.perf_counter()
+  t_steady, total_steady = None, 0     # from the end of the first iteration on (it captures the learner's CUDA graphs)
   while total < num_timesteps:
     obs_l, logit_l, pre_l, rew_l, done_l, trunc_l = [], [], [], [], [], []
     for _ in range(rollouts_per_step):
@@ -280,7 +309,11 @@ def train(env_name: str = 'ant', num_envs: int = 2048, episode_length: int = 100
     total += steps_per_train_step
     it += 1
     torch.cuda.synchronize()
-    metrics = {'sps': total / (time.perf_counter() - t0), 'loss': float(loss.detach()),
+    now = time.perf_counter()
+    if t_steady is None:
+      t_steady, total_steady = now, total
+    steady = (total - total_steady) / (now - t_steady) if total > total_steady else total / (now - t0)
+    metrics = {'sps': total / (now - t0), 'sps_steady': steady, 'loss': float(loss.detach()),
                'episode_reward': float(finished_sum) / max(float(finished_n), 1.0), 'env_steps': total, 'iterations': it}
     if progress_fn and rank == 0:
       progress_fn(total, metrics)

@@ -55,10 +55,22 @@ class SACNetworks(nn.Module):
   def update_normalization(self, obs):
     if not self.normalize_observations:
       return
-    total = self.num_steps + obs.shape[0]
+    # running_statistics.update with pmap_axis_name (acme/running_statistics.py:174,262-271): the increment, the mean
+    # update and the variance update are summed over ranks, so every rank holds the statistics of the global batch
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    inc = torch.tensor(float(obs.shape[0]), device=obs.device)
+    if multi:
+      dist.all_reduce(inc)
+    total = self.num_steps + inc
     delta = obs - self.running_mean
-    self.running_mean += delta.sum(0) / total
-    self.running_var += (delta * (obs - self.running_mean)).sum(0)
+    mean_update = delta.sum(0) / total
+    if multi:
+      dist.all_reduce(mean_update)
+    self.running_mean += mean_update
+    var_update = (delta * (obs - self.running_mean)).sum(0)
+    if multi:
+      dist.all_reduce(var_update)
+    self.running_var += var_update
     self.num_steps.copy_(total)
 
   def normalize(self, obs):

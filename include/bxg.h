@@ -256,6 +256,11 @@ int bxg_model_num_constraints(const BxgModel* model);
  * [2] = model words, [3] = per-env slab words, [4] = envs per CTA,
  * [5] = dynamic shared memory bytes per CTA, [6] = nc, [7] = reserved. */
 int bxg_plan(const BxgModelDesc* desc, int32_t info[8]);
+/* The launch a batch of n_env envs gets on this model's device (the persistent kernel picks
+ * the number of envs per CTA per call: small or awkward batches use smaller CTAs).
+ * info[0] = grid (CTAs), [1] = threads per CTA, [2] = dynamic shared memory bytes per CTA,
+ * [3] = envs per CTA. */
+int bxg_launch_shape(const BxgModel* model, int64_t n_env, int32_t info[4]);
 
 /* generalized.pipeline.init over a batch (pipeline.py:32-61):
  * q [n,nq], qd [n,nv] -> every leaf of `out`. */

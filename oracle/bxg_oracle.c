@@ -991,6 +991,14 @@ static void env_store(const OrcModel* m, OrcState* s, long i, const Env* e) {
 int orc_sizeof_real(void) { return (int)sizeof(real); }
 int orc_sizeof_model(void) { return (int)sizeof(OrcModel); }
 int orc_max_links(void) { return MAXL; }
+/* Threads of the batch loops below, set explicitly: launchers such as torch.distributed.run
+ * export OMP_NUM_THREADS=1, which would silently serialise the CPU baseline. Returns the count in effect. */
+#ifdef _OPENMP
+#include <omp.h>
+int orc_set_threads(int n) { if (n > 0) omp_set_num_threads(n); return omp_get_max_threads(); }
+#else
+int orc_set_threads(int n) { (void)n; return 1; }
+#endif
 
 /* pipeline.init over a batch: q [n,nq], qd [n,nv] -> full state */
 int orc_init(const OrcModel* m, long n_env, const real* q, const real* qd, OrcState* out) {

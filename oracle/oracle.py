@@ -96,8 +96,8 @@ class Oracle:
     self.sys = sys
     self.model = Model()
     self._fill(sys)
-    if threads is not None:
-      os.environ['OMP_NUM_THREADS'] = str(threads)
+    # explicit thread count (never inherited from OMP_NUM_THREADS, which launchers set to 1)
+    self.threads = int(self.lib.orc_set_threads(int(threads) if threads is not None else (os.cpu_count() or 1)))
     self.lib.orc_step.argtypes = [ctypes.c_void_p, ctypes.c_long, ctypes.c_int,
                                   ctypes.c_void_p, ctypes.c_void_p]
     self.lib.orc_init.argtypes = [ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p,

@@ -4,10 +4,17 @@ import functools
 import numpy as _np
 
 from jax import numpy  # noqa: F401  (jax.numpy)
-from jax import lax, ops, random, scipy, tree, tree_util, typing  # noqa: F401
+from jax import lax, nn, ops, random, scipy, tree, tree_util, typing  # noqa: F401
 from jax.tree_util import tree_map as _tree_map, tree_leaves as _tree_leaves
 
 Array = _np.ndarray
+
+
+class _Config:   # the stand-in computes in float64 (tools/refshim/README.md)
+  jax_enable_x64 = True
+
+
+config = _Config()
 
 
 class custom_jvp:   # forward evaluation only

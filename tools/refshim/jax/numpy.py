@@ -126,6 +126,8 @@ def __getattr__(name):   # everything else: the NumPy function of the same name,
   f = getattr(_np, name)
   if callable(f) and not isinstance(f, type):
     def g(*a, **k):
+      if isinstance(k.get('axis'), range):   # jax accepts any sequence of axes
+        k['axis'] = tuple(k['axis'])
       return _wrap(f(*a, **k))
     g.__name__ = name
     return g

@@ -49,3 +49,16 @@ def tree_flatten(tree, is_leaf=None):
 def tree_unflatten(treedef, leaves):
   it = iter(leaves)
   return tree_map(lambda _: next(it), treedef)
+
+
+def tree_structure(tree):
+  """A comparable description of the container structure (leaves replaced by '*')."""
+  if tree is None:
+    return None
+  if isinstance(tree, (tuple, list)):
+    return (type(tree).__name__, tuple(tree_structure(t) for t in tree))
+  if isinstance(tree, dict):
+    return ('dict', tuple((k, tree_structure(v)) for k, v in sorted(tree.items())))
+  if type(tree) in _registered:
+    return (type(tree).__name__, tuple((fl.name, tree_structure(getattr(tree, fl.name))) for fl in _node_fields(tree)))
+  return '*'
