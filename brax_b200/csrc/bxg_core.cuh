@@ -72,7 +72,27 @@ BXG_HD float r_max(float a, float b) { return fmaxf(a, b); }
 BXG_HD float r_min(float a, float b) { return fminf(a, b); }
 BXG_HD float r_pow(float a, float b) { return powf(a, b); }
 BXG_HD float r_fma(float a, float b, float c) { return fmaf(a, b, c); }
-BXG_HD void r_sincos(float x, float* s, float* c) { sincosf(x, s, c); }
+// sin and cos in float from ONE source for host and device (libm's and CUDA's sincosf differ in the last bit):
+// Cody-Waite reduction by pi/2 in three parts with fused multiply-adds, then the Cephes minimax polynomials on
+// [-pi/4, pi/4].  Measured against float64: <= 1.5 ulp for |x| <= 100, <= 2.4 ulp (sin) up to 1e4
+// (tests/test_kernel_math.py); the angles here are joint angles and dt * |omega| / 2.
+BXG_HD void r_sincos(float x, float* s, float* c) {
+  const float k = rintf(x * 0.636619747f);                       // x * 2/pi, to nearest even
+  float r = fmaf(k, -1.57079637050628662109e+00f, x);
+  r = fmaf(k, 4.37113882867379288655e-08f, r);
+  r = fmaf(k, 1.77635683940025046468e-15f, r);
+  r = r < -1.0f ? -1.0f : (r > 1.0f ? 1.0f : r);                  // no-op in range (|r| <= pi/4 + rounding); keeps the result bounded for |x| > ~1e6, NaN stays NaN
+  const float z = r * r;
+  float sp = fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f);
+  sp = fmaf(sp, z, -1.6666654611e-1f);
+  const float sn = fmaf(sp * z, r, r);
+  float cp = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  cp = fmaf(cp, z, 4.166664568298827e-2f);
+  const float cs = fmaf(cp * z, z, fmaf(z, -0.5f, 1.0f));
+  const int q = (int)fminf(fmaxf(k, -1.0e9f), 1.0e9f) & 3;       // (far outside the reduction's range the result is only bounded)
+  *s = q == 0 ? sn : q == 1 ? cs : q == 2 ? -sn : -cs;
+  *c = q == 0 ? cs : q == 1 ? -sn : q == 2 ? -cs : sn;
+}
 #if !defined(__CUDA_ARCH__)
 inline double r_abs(double x) { return fabs(x); }
 inline double r_sqrt(double x) { return sqrt(x); }
@@ -101,30 +121,35 @@ BXG_HD void st4(real* p, Q4 q) { p[0] = q.w; p[1] = q.x; p[2] = q.y; p[3] = q.z;
 BXG_HD V3 operator+(V3 a, V3 b) { return V3{a.x + b.x, a.y + b.y, a.z + b.z}; }
 BXG_HD V3 operator-(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
 BXG_HD V3 operator*(V3 a, real s) { return V3{a.x * s, a.y * s, a.z * s}; }
-BXG_HD real dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-BXG_HD V3 cross(V3 a, V3 b) { return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+// Fused multiply-adds are written out (r_fma): the device code is compiled with -fmad=false and the host
+// emulator with -ffp-contract=off, so the SOURCE fixes every rounding and both produce the same bits
+// (tests/test_gpu_bitexact.py).  s * a + b on vectors:
+BXG_HD V3 fmav(V3 a, real s, V3 b) { return V3{r_fma(a.x, s, b.x), r_fma(a.y, s, b.y), r_fma(a.z, s, b.z)}; }
+BXG_HD real dot(V3 a, V3 b) { return r_fma(a.z, b.z, r_fma(a.y, b.y, a.x * b.x)); }
+BXG_HD V3 cross(V3 a, V3 b) { return V3{r_fma(a.y, b.z, -(a.z * b.y)), r_fma(a.z, b.x, -(a.x * b.z)), r_fma(a.x, b.y, -(a.y * b.x))}; }
 
 // math.rotate (brax/math.py:25-41)
 BXG_HD V3 rotate(V3 v, Q4 q) {
   V3 u{q.x, q.y, q.z};
-  real s = q.w, d = dot(u, v), k = s * s - dot(u, u);
+  real s = q.w, d = dot(u, v), k = r_fma(s, s, -dot(u, u));
   V3 c = cross(u, v);
-  V3 r{R(2.) * (d * u.x) + k * v.x, R(2.) * (d * u.y) + k * v.y, R(2.) * (d * u.z) + k * v.z};
+  const real d2 = R(2.) * d;
+  V3 r{r_fma(k, v.x, d2 * u.x), r_fma(k, v.y, d2 * u.y), r_fma(k, v.z, d2 * u.z)};
   real s2 = R(2.) * s;
-  return V3{r.x + s2 * c.x, r.y + s2 * c.y, r.z + s2 * c.z};
+  return V3{r_fma(s2, c.x, r.x), r_fma(s2, c.y, r.y), r_fma(s2, c.z, r.z)};
 }
 // math.quat_mul (brax/math.py:86-101)
 BXG_HD Q4 qmul(Q4 u, Q4 v) {
-  return Q4{u.w * v.w - u.x * v.x - u.y * v.y - u.z * v.z,
-            u.w * v.x + u.x * v.w + u.y * v.z - u.z * v.y,
-            u.w * v.y - u.x * v.z + u.y * v.w + u.z * v.x,
-            u.w * v.z + u.x * v.y - u.y * v.x + u.z * v.w};
+  return Q4{r_fma(-u.z, v.z, r_fma(-u.y, v.y, r_fma(-u.x, v.x, u.w * v.w))),
+            r_fma(-u.z, v.y, r_fma(u.y, v.z, r_fma(u.x, v.w, u.w * v.x))),
+            r_fma(u.z, v.x, r_fma(u.y, v.w, r_fma(-u.x, v.z, u.w * v.y))),
+            r_fma(u.z, v.w, r_fma(-u.y, v.x, r_fma(u.x, v.y, u.w * v.z)))};
 }
 // math.normalize on a quaternion incl. safe_norm's all-close-to-zero rule
 // (brax/math.py:308-345)
 BXG_HD Q4 qnormalize(Q4 q) {
   bool zero = r_abs(q.w) <= R(1e-8) && r_abs(q.x) <= R(1e-8) && r_abs(q.y) <= R(1e-8) && r_abs(q.z) <= R(1e-8);
-  real n = zero ? R(0.) : r_sqrt(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+  real n = zero ? R(0.) : r_sqrt(r_fma(q.z, q.z, r_fma(q.y, q.y, r_fma(q.x, q.x, q.w * q.w))));
   real d = n + R(1e-6) * (n == R(0.) ? R(1.) : R(0.));
   return Q4{q.w / d, q.x / d, q.y / d, q.z / d};
 }
@@ -142,10 +167,10 @@ BXG_HD void tf_do(V3 ap, Q4 ar, V3 bp, Q4 br, V3* op, Q4* orr) {
 // Inertia.mul(Motion) -> Force (brax/base.py:297-302); im row-major 3x3
 BXG_HD void inertia_mul(V3 ipos, const real* im, real mass, V3 mang, V3 mvel, V3* fang, V3* fvel) {
   V3 c1 = cross(ipos, mvel), c2 = cross(ipos, mang);
-  fang->x = (im[0] * mang.x + im[1] * mang.y + im[2] * mang.z) + c1.x;
-  fang->y = (im[3] * mang.x + im[4] * mang.y + im[5] * mang.z) + c1.y;
-  fang->z = (im[6] * mang.x + im[7] * mang.y + im[8] * mang.z) + c1.z;
-  *fvel = mvel * mass - c2;
+  fang->x = r_fma(im[2], mang.z, r_fma(im[1], mang.y, im[0] * mang.x)) + c1.x;
+  fang->y = r_fma(im[5], mang.z, r_fma(im[4], mang.y, im[3] * mang.x)) + c1.y;
+  fang->z = r_fma(im[8], mang.z, r_fma(im[7], mang.y, im[6] * mang.x)) + c1.z;
+  *fvel = V3{r_fma(mvel.x, mass, -c2.x), r_fma(mvel.y, mass, -c2.y), r_fma(mvel.z, mass, -c2.z)};
 }
 
 struct Ctx {
@@ -211,7 +236,7 @@ BXG_HD void actuator_tau(X& ex, const Ctx& c) {
         real bias = gear * (qv * mf[D.m_act_bq + a] + qdv * mf[D.m_act_bqd + a]);
         real f = mf[D.m_act_gain + a] * ctrl + bias;
         f = r_max(mf[D.m_act_flo + a], r_min(f, mf[D.m_act_fhi + a]));
-        tau += f * gear;
+        tau = r_fma(f, gear, tau);
       }
       s[D.s_tau + d] = tau;
     }
@@ -281,8 +306,8 @@ BXG_HD void dyn_forces(X& ex, const Ctx& c) {
       V3 cv = p >= 0 ? ld3(s + D.s_t_vel + 3 * p) : V3{-D.gx, -D.gy, -D.gz};
       for (int k = 0; k < nd; ++k) {
         real qd = s[D.s_qd + da + k];
-        ca = ca + ld3(s + D.s_cdofd_ang + 3 * (da + k)) * qd;
-        cv = cv + ld3(s + D.s_cdofd_vel + 3 * (da + k)) * qd;
+        ca = fmav(ld3(s + D.s_cdofd_ang + 3 * (da + k)), qd, ca);
+        cv = fmav(ld3(s + D.s_cdofd_vel + 3 * (da + k)), qd, cv);
       }
       st3(s + D.s_t_ang + 3 * l, ca); st3(s + D.s_t_vel + 3 * l, cv);
     });
@@ -322,7 +347,7 @@ BXG_HD void dyn_forces(X& ex, const Ctx& c) {
                    dot(ld3(s + D.s_cdof_ang + 3 * d), ld3(s + D.s_f_ang + 3 * l));
       real qd = s[D.s_qd + d];
       real passive = qi < 0 ? R(0.) : -s[D.s_q + qi] * mf[D.m_stiff + d];
-      passive = passive - mf[D.m_damp + d] * qd;
+      passive = r_fma(-mf[D.m_damp + d], qd, passive);
       if constexpr (kFluidCode) { if (D.fluid) passive = passive + s[D.s_qfs + d]; }
       s[D.s_qfs + d] = (passive - bias) + s[D.s_tau + d];
     }
@@ -347,16 +372,16 @@ BXG_HD void con_force_generic(X& ex, const Ctx& c, Stats* st) {
     for (int i = lane; i < nc; i += X::G) {
       for (int j = 0; j < nv; ++j) {
         real acc = R(0.);
-        for (int k = 0; k < nv; ++k) acc += J[i * jld + k] * Mi[k * nvp + j];
+        for (int k = 0; k < nv; ++k) acc = r_fma(J[i * jld + k], Mi[k * nvp + j], acc);
         JM[i * jld + j] = acc;
       }
       for (int j = 0; j < nc; ++j) {
         real acc = R(0.);
-        for (int k = 0; k < nv; ++k) acc += JM[i * jld + k] * J[j * jld + k];
+        for (int k = 0; k < nv; ++k) acc = r_fma(JM[i * jld + k], J[j * jld + k], acc);
         A[i * ncp + j] = acc + (i == j ? s[D.s_diag + i] : R(0.));
       }
       real acc = R(0.);
-      for (int k = 0; k < nv; ++k) acc += JM[i * jld + k] * s[D.s_qfs + k];
+      for (int k = 0; k < nv; ++k) acc = r_fma(JM[i * jld + k], s[D.s_qfs + k], acc);
       b[i] = acc - s[D.s_aref + i];
       x[i] = R(0.); y[i] = R(0.);
     }
@@ -368,16 +393,16 @@ BXG_HD void con_force_generic(X& ex, const Ctx& c, Stats* st) {
     ex.lanes([&](int lane) {
       for (int i = lane; i < nc; i += X::G) {
         real acc = R(0.);
-        for (int j = 0; j < nc; ++j) acc += A[i * ncp + j] * y[j];
+        for (int j = 0; j < nc; ++j) acc = r_fma(A[i * ncp + j], y[j], acc);
         res[i] = acc + b[i];
       }
     });
     real fy = R(0.);
-    for (int i = 0; i < nc; ++i) fy += R(0.5) * (res[i] * res[i]);
+    for (int i = 0; i < nc; ++i) fy = r_fma(R(0.5), (res[i] * res[i]), fy);
     ex.lanes([&](int lane) {
       for (int j = lane; j < nc; j += X::G) {
         real acc = R(0.);
-        for (int i = 0; i < nc; ++i) acc += A[i * ncp + j] * res[i];
+        for (int i = 0; i < nc; ++i) acc = r_fma(A[i * ncp + j], res[i], acc);
         g[j] = acc;
       }
     });   // (writes g only: no hazard with the redundant reads of res above)
@@ -387,14 +412,14 @@ BXG_HD void con_force_generic(X& ex, const Ctx& c, Stats* st) {
       ex.lanes([&](int lane) {
         for (int i = lane; i < nc; i += X::G) {
           real acc = R(0.);
-          for (int j = 0; j < nc; ++j) acc += A[i * ncp + j] * xn[j];
+          for (int j = 0; j < nc; ++j) acc = r_fma(A[i * ncp + j], xn[j], acc);
           res[i] = acc + b[i];
         }
       });
       real sqdist = R(0.), vd = R(0.), fn = R(0.);
-      for (int i = 0; i < nc; ++i) { real dlt = xn[i] - y[i]; sqdist += dlt * dlt; }
-      for (int i = 0; i < nc; ++i) { real dlt = xn[i] - y[i]; vd += dlt * g[i]; }
-      for (int i = 0; i < nc; ++i) fn += R(0.5) * (res[i] * res[i]);
+      for (int i = 0; i < nc; ++i) { real dlt = xn[i] - y[i]; sqdist = r_fma(dlt, dlt, sqdist); }
+      for (int i = 0; i < nc; ++i) { real dlt = xn[i] - y[i]; vd = r_fma(dlt, g[i], vd); }
+      for (int i = 0; i < nc; ++i) fn = r_fma(R(0.5), (res[i] * res[i]), fn);
       st->pg_trials++;
       ex.sync();   // every lane finished its redundant reads of xn / res before they are rewritten
       real fun_decrease = sz * (fn - fy);
@@ -409,7 +434,7 @@ BXG_HD void con_force_generic(X& ex, const Ctx& c, Stats* st) {
     ex.lanes([&](int lane) {
       for (int j = lane; j < nc; j += X::G) {
         real acc = R(0.);
-        for (int i = 0; i < nc; ++i) acc += A[i * ncp + j] * res[i];
+        for (int i = 0; i < nc; ++i) acc = r_fma(A[i * ncp + j], res[i], acc);
         g[j] = acc;
         real dlt = xn[j] - x[j];
         y[j] = xn[j] + mom * dlt;
@@ -417,7 +442,7 @@ BXG_HD void con_force_generic(X& ex, const Ctx& c, Stats* st) {
       }
     });
     real err2 = R(0.);
-    for (int i = 0; i < nc; ++i) { real dlt = r_max(xn[i] - g[i], R(0.)) - xn[i]; err2 += dlt * dlt; }
+    for (int i = 0; i < nc; ++i) { real dlt = r_max(xn[i] - g[i], R(0.)) - xn[i]; err2 = r_fma(dlt, dlt, err2); }
     error = r_sqrt(err2);
     t = tn;
     ++it;
@@ -428,7 +453,7 @@ BXG_HD void con_force_generic(X& ex, const Ctx& c, Stats* st) {
   ex.lanes([&](int lane) {
     for (int j = lane; j < nv; j += X::G) {
       real acc = R(0.);
-      for (int i = 0; i < nc; ++i) acc += J[i * jld + j] * x[i];
+      for (int i = 0; i < nc; ++i) acc = r_fma(J[i * jld + j], x[i], acc);
       s[D.s_qfc + j] = acc;
     }
   });
@@ -551,12 +576,12 @@ BXG_HD void integrate(X& ex, const Ctx& c) {
   ex.lanes([&](int lane) {
     for (int i = lane; i < nv; i += X::G) {
       real acc = R(0.);
-      for (int j = 0; j < nv; ++j) acc += Mi[i * nvp + j] * (s[D.s_qfs + j] + s[D.s_qfc + j]);
+      for (int j = 0; j < nv; ++j) acc = r_fma(Mi[i * nvp + j], (s[D.s_qfs + j] + s[D.s_qfc + j]), acc);
       s[D.s_qdd + i] = acc;
     }
   });
   ex.lanes([&](int lane) {
-    for (int i = lane; i < nv; i += X::G) s[D.s_qd + i] = s[D.s_qd + i] + s[D.s_qdd + i] * dt;
+    for (int i = lane; i < nv; i += X::G) s[D.s_qd + i] = r_fma(s[D.s_qdd + i], dt, s[D.s_qd + i]);
   });
   ex.lanes([&](int l) {
     if (l >= L) return;
@@ -571,9 +596,9 @@ BXG_HD void integrate(X& ex, const Ctx& c) {
       Q4 nr = qmul(rot, Q4{cs, axis.x * sn, axis.y * sn, axis.z * sn});
       real n = r_sqrt(nr.w * nr.w + nr.x * nr.x + nr.y * nr.y + nr.z * nr.z);
       st4(s + D.s_q + qa + 3, Q4{nr.w / n, nr.x / n, nr.y / n, nr.z / n});
-      for (int i = 0; i < 3; ++i) s[D.s_q + qa + i] = s[D.s_q + qa + i] + s[D.s_qd + da + i] * dt;
+      for (int i = 0; i < 3; ++i) s[D.s_q + qa + i] = r_fma(s[D.s_qd + da + i], dt, s[D.s_q + qa + i]);
     } else {
-      for (int k = 0; k < nd; ++k) s[D.s_q + qa + k] = s[D.s_q + qa + k] + s[D.s_qd + da + k] * dt;
+      for (int k = 0; k < nd; ++k) s[D.s_q + qa + k] = r_fma(s[D.s_qd + da + k], dt, s[D.s_q + qa + k]);
     }
   });
 }
@@ -661,7 +686,7 @@ BXG_HD void transform_com(X& ex, const Ctx& c) {
     for (int k = 0; k < L; ++k) {
       if (mi[D.m_link_root + k] != root) continue;
       real mk = mf[D.m_in_mass + k];
-      msum = msum + ld3(xi_pos + 3 * k) * mk; mtot += mk;
+      msum = fmav(ld3(xi_pos + 3 * k), mk, msum); mtot += mk;
     }
     V3 com{msum.x / mtot, msum.y / mtot, msum.z / mtot};
     st3(s + D.s_root_com + 3 * l, com);
@@ -683,15 +708,15 @@ BXG_HD void transform_com(X& ex, const Ctx& c) {
     real T[9];
     for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) {
       real acc = R(0.);
-      for (int k = 0; k < 3; ++k) acc += R[3 * a + k] * I0[3 * k + b];
+      for (int k = 0; k < 3; ++k) acc = r_fma(R[3 * a + k], I0[3 * k + b], acc);
       T[3 * a + b] = acc;
     }
     real h[9] = {R(0.), -p.z, p.y, p.z, R(0.), -p.x, -p.y, p.x, R(0.)};
     for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) {
       real acc = R(0.), hh = R(0.);
-      for (int k = 0; k < 3; ++k) acc += T[3 * a + k] * R[3 * b + k];
-      for (int k = 0; k < 3; ++k) hh += h[3 * a + k] * h[3 * b + k];
-      s[D.s_cinr_i + 9 * l + 3 * a + b] = acc + hh * mass;
+      for (int k = 0; k < 3; ++k) acc = r_fma(T[3 * a + k], R[3 * b + k], acc);
+      for (int k = 0; k < 3; ++k) hh = r_fma(h[3 * a + k], h[3 * b + k], hh);
+      s[D.s_cinr_i + 9 * l + 3 * a + b] = r_fma(hh, mass, acc);
     }
     st3(s + D.s_cinr_pos + 3 * l, p * mass);
     s[D.s_cinr_mass + l] = mass;
@@ -737,8 +762,8 @@ BXG_HD void transform_com(X& ex, const Ctx& c) {
       V3 cv = p >= 0 ? ld3(s + D.s_cd_vel + 3 * p) : V3{0, 0, 0};
       for (int k = 0; k < nd; ++k) {
         real qd = s[D.s_qd + da + k];
-        ca = ca + ld3(s + D.s_cdof_ang + 3 * (da + k)) * qd;
-        cv = cv + ld3(s + D.s_cdof_vel + 3 * (da + k)) * qd;
+        ca = fmav(ld3(s + D.s_cdof_ang + 3 * (da + k)), qd, ca);
+        cv = fmav(ld3(s + D.s_cdof_vel + 3 * (da + k)), qd, cv);
       }
       st3(s + D.s_cd_ang + 3 * l, ca); st3(s + D.s_cd_vel + 3 * l, cv);
     });
@@ -751,8 +776,8 @@ BXG_HD void transform_com(X& ex, const Ctx& c) {
       V3 ca{0, 0, 0}, cv{0, 0, 0};
       for (int k = 0; k < 3; ++k) {
         real qd = s[D.s_qd + da + k];
-        ca = ca + ld3(s + D.s_cdof_ang + 3 * (da + k)) * qd;
-        cv = cv + ld3(s + D.s_cdof_vel + 3 * (da + k)) * qd;
+        ca = fmav(ld3(s + D.s_cdof_ang + 3 * (da + k)), qd, ca);
+        cv = fmav(ld3(s + D.s_cdof_vel + 3 * (da + k)), qd, cv);
       }
       for (int k = 0; k < 6; ++k) {
         V3 da_ = ld3(s + D.s_cdof_ang + 3 * (da + k)), dv_ = ld3(s + D.s_cdof_vel + 3 * (da + k));
@@ -769,7 +794,7 @@ BXG_HD void transform_com(X& ex, const Ctx& c) {
         st3(s + D.s_cdofd_vel + 3 * d, cross(ca, dv_) + cross(cv, da_));
         st3(s + D.s_cdofd_ang + 3 * d, cross(ca, da_));
         real qd = s[D.s_qd + d];
-        ca = ca + da_ * qd; cv = cv + dv_ * qd;
+        ca = fmav(da_, qd, ca); cv = fmav(dv_, qd, cv);
       }
     }
   });
@@ -839,10 +864,10 @@ BXG_HD void minv_newton_schulz_generic(X& ex, const Ctx& c, Stats* st) {
     for (int i = lane; i < n; i += X::G) {
       for (int j = 0; j < n; ++j) {
         real acc = R(0.);
-        for (int k = 0; k < n; ++k) acc += M[i * nvp + k] * Xc[k * nvp + j];
+        for (int k = 0; k < n; ++k) acc = r_fma(M[i * nvp + k], Xc[k * nvp + j], acc);
         real r = (i == j ? R(1.) : R(0.)) - acc;
         RB[i * nvp + j] = r;
-        ss += r * r; mx = r_max(mx, r_abs(r));
+        ss = r_fma(r, r, ss); mx = r_max(mx, r_abs(r));
       }
     }
     p_sum(lane) = ss; p_max(lane) = mx;
@@ -852,7 +877,7 @@ BXG_HD void minv_newton_schulz_generic(X& ex, const Ctx& c, Stats* st) {
   if (nrm0 > R(1.)) {
     ex.lanes([&](int lane) {
       real tr = R(0.);
-      for (int i = lane; i < n; i += X::G) for (int k = 0; k < n; ++k) tr += M[i * nvp + k] * M[i * nvp + k];
+      for (int i = lane; i < n; i += X::G) for (int k = 0; k < n; ++k) tr = r_fma(M[i * nvp + k], M[i * nvp + k], tr);
       p_sum(lane) = tr;
     });
     real tr = ex.sum(p_sum);
@@ -869,7 +894,7 @@ BXG_HD void minv_newton_schulz_generic(X& ex, const Ctx& c, Stats* st) {
       for (int i = lane; i < n; i += X::G) {
         for (int j = 0; j < n; ++j) {
           real acc = R(0.);
-          for (int k = 0; k < n; ++k) acc += Xc[i * nvp + k] * RB[k * nvp + j];
+          for (int k = 0; k < n; ++k) acc = r_fma(Xc[i * nvp + k], RB[k * nvp + j], acc);
           Xn[i * nvp + j] = acc;
         }
       }
@@ -880,10 +905,10 @@ BXG_HD void minv_newton_schulz_generic(X& ex, const Ctx& c, Stats* st) {
       for (int i = lane; i < n; i += X::G) {
         for (int j = 0; j < n; ++j) {
           real acc = R(0.);
-          for (int k = 0; k < n; ++k) acc += M[i * nvp + k] * Xn[k * nvp + j];
+          for (int k = 0; k < n; ++k) acc = r_fma(M[i * nvp + k], Xn[k * nvp + j], acc);
           real r = (i == j ? R(1.) : R(0.)) - acc;
           RB[i * nvp + j] = r;
-          s2 += r * r; m2 = r_max(m2, r_abs(r));
+          s2 = r_fma(r, r, s2); m2 = r_max(m2, r_abs(r));
         }
       }
       p_sum(lane) = s2; p_max(lane) = m2;
@@ -914,8 +939,8 @@ BXG_HD void row_times_mat(const real* a, const real* B, int ldb, real* acc) {
 #pragma unroll
     for (int cc = 0; cc < C4; ++cc) {
       F4 b = ldv4(B + k * ldb + 4 * cc);
-      acc[4 * cc + 0] += ak * b.x; acc[4 * cc + 1] += ak * b.y;
-      acc[4 * cc + 2] += ak * b.z; acc[4 * cc + 3] += ak * b.w;
+      acc[4 * cc + 0] = r_fma(ak, b.x, acc[4 * cc + 0]); acc[4 * cc + 1] = r_fma(ak, b.y, acc[4 * cc + 1]);
+      acc[4 * cc + 2] = r_fma(ak, b.z, acc[4 * cc + 2]); acc[4 * cc + 3] = r_fma(ak, b.w, acc[4 * cc + 3]);
     }
   }
 }
@@ -934,8 +959,8 @@ BXG_HD void smem_row_times_mat(const real* arow_sm, const real* B, int ldb, real
 #pragma unroll
       for (int cc = 0; cc < C4; ++cc) {
         F4 b = ldv4(B + (k0 + kk) * ldb + 4 * cc);
-        acc[4 * cc + 0] += ak * b.x; acc[4 * cc + 1] += ak * b.y;
-        acc[4 * cc + 2] += ak * b.z; acc[4 * cc + 3] += ak * b.w;
+        acc[4 * cc + 0] = r_fma(ak, b.x, acc[4 * cc + 0]); acc[4 * cc + 1] = r_fma(ak, b.y, acc[4 * cc + 1]);
+        acc[4 * cc + 2] = r_fma(ak, b.z, acc[4 * cc + 2]); acc[4 * cc + 3] = r_fma(ak, b.w, acc[4 * cc + 3]);
       }
     }
   }
@@ -957,7 +982,7 @@ BXG_HD real row_dot(const real* a, const real* v) {
 #pragma unroll
   for (int cc = 0; cc < C4; ++cc) {
     F4 b = ldv4(v + 4 * cc);
-    acc += a[4 * cc] * b.x; acc += a[4 * cc + 1] * b.y; acc += a[4 * cc + 2] * b.z; acc += a[4 * cc + 3] * b.w;
+    acc = r_fma(a[4 * cc], b.x, acc); acc = r_fma(a[4 * cc + 1], b.y, acc); acc = r_fma(a[4 * cc + 2], b.z, acc); acc = r_fma(a[4 * cc + 3], b.w, acc);
   }
   return acc;
 }
@@ -1095,7 +1120,7 @@ BXG_HD void tile_matmul(int lane, const real* A, const real* B, int ld, real* ac
         const real ap = kk == 0 ? a[r].x : kk == 1 ? a[r].y : kk == 2 ? a[r].z : a[r].w;
         const real av = NEG ? -ap : ap;
 #pragma unroll
-        for (int cc = 0; cc < T::TN; ++cc) acc[r * T::TN + cc] += av * bv[cc];
+        for (int cc = 0; cc < T::TN; ++cc) acc[r * T::TN + cc] = r_fma(av, bv[cc], acc[r * T::TN + cc]);
       }
     }
   }
@@ -1131,7 +1156,7 @@ template <class T>
 BXG_HD void residual_tile(int lane, int n, real* acc, real* ss, real* mx) {
   tile_diagonal<T>(lane, n, [&](int e) { acc[e] = R(1.) + acc[e]; });     // r = I - M X
 #pragma unroll
-  for (int e = 0; e < T::TM * T::TN; ++e) { *ss += acc[e] * acc[e]; *mx = r_max(*mx, r_abs(acc[e])); }
+  for (int e = 0; e < T::TM * T::TN; ++e) { *ss = r_fma(acc[e], acc[e], *ss); *mx = r_max(*mx, r_abs(acc[e])); }
   tile_diagonal<T>(lane, n, [&](int e) { acc[e] = R(1.) + acc[e]; });     // I + r
 }
 template <class T>
@@ -1230,7 +1255,7 @@ BXG_HD real row_dot_n(const real* a, const real* v, int chunks) {
   for (int cc = 0; cc < C4; ++cc) {
     if (cc < chunks) {
       F4 b = ldv4(v + 4 * cc);
-      acc += a[4 * cc] * b.x; acc += a[4 * cc + 1] * b.y; acc += a[4 * cc + 2] * b.z; acc += a[4 * cc + 3] * b.w;
+      acc = r_fma(a[4 * cc], b.x, acc); acc = r_fma(a[4 * cc + 1], b.y, acc); acc = r_fma(a[4 * cc + 2], b.z, acc); acc = r_fma(a[4 * cc + 3], b.w, acc);
     }
   }
   return acc;
@@ -1249,7 +1274,7 @@ BXG_HD real smem_row_dot(const real* arow_sm, const real* v, int chunks) {
   real acc = R(0.);
   for (int cc = 0; cc < chunks; ++cc) {
     F4 a = ldv4(arow_sm + 4 * cc), b = ldv4(v + 4 * cc);
-    acc += a.x * b.x; acc += a.y * b.y; acc += a.z * b.z; acc += a.w * b.w;
+    acc = r_fma(a.x, b.x, acc); acc = r_fma(a.y, b.y, acc); acc = r_fma(a.z, b.z, acc); acc = r_fma(a.w, b.w, acc);
   }
   return acc;
 }
@@ -1330,7 +1355,7 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
 #pragma unroll
         for (int cc = 0; cc < VC4; ++cc) {
           F4 f = ldv4(s + D.s_qfs + 4 * cc);
-          bacc += jm[4 * cc] * f.x; bacc += jm[4 * cc + 1] * f.y; bacc += jm[4 * cc + 2] * f.z; bacc += jm[4 * cc + 3] * f.w;
+          bacc = r_fma(jm[4 * cc], f.x, bacc); bacc = r_fma(jm[4 * cc + 1], f.y, bacc); bacc = r_fma(jm[4 * cc + 2], f.z, bacc); bacc = r_fma(jm[4 * cc + 3], f.w, bacc);
         }
         bi(lane)[r] = bacc - s[D.s_aref + i];
         const real dg = s[D.s_diag + i];
@@ -1346,7 +1371,7 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
 #pragma unroll
             for (int cc = 0; cc < VC4; ++cc) {
               F4 b = ldv4(jq + 4 * cc);
-              acc += jm[4 * cc] * b.x; acc += jm[4 * cc + 1] * b.y; acc += jm[4 * cc + 2] * b.z; acc += jm[4 * cc + 3] * b.w;
+              acc = r_fma(jm[4 * cc], b.x, acc); acc = r_fma(jm[4 * cc + 1], b.y, acc); acc = r_fma(jm[4 * cc + 2], b.z, acc); acc = r_fma(jm[4 * cc + 3], b.w, acc);
             }
             if (q == p) acc += dg;
             a4[u] = iq < 0 ? R(0.) : acc;
@@ -1376,7 +1401,7 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
         if (p < na) {
           real rv = (AREG ? row_dot_n<NC4>(arow(lane) + (AREG ? r * CW : 0), ys, nch) : smem_row_dot(A + p * ldc, ys, nch)) + bi(lane)[r];
           ress[p] = rv;
-          f += R(0.5) * (rv * rv);
+          f = r_fma(R(0.5), (rv * rv), f);
         }
       }
       p0(lane) = f;
@@ -1389,7 +1414,7 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
         if (j < na) {
           real acc = R(0.);
 #pragma unroll 4
-          for (int i = 0; i < na; ++i) acc += A[i * ldc + j] * ress[i];
+          for (int i = 0; i < na; ++i) acc = r_fma(A[i * ldc + j], ress[i], acc);
           gi(lane)[r] = acc;
         }
       }
@@ -1412,7 +1437,7 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
             real rv = (AREG ? row_dot_n<NC4>(arow(lane) + (AREG ? r * CW : 0), xns, nch) : smem_row_dot(A + p * ldc, xns, nch)) + bi(lane)[r];
             resi(lane)[r] = rv;
             real dlt = xni(lane)[r] - yi(lane)[r];
-            a0 += dlt * dlt; a1 += dlt * gi(lane)[r]; a2 += R(0.5) * (rv * rv);
+            a0 = r_fma(dlt, dlt, a0); a1 = r_fma(dlt, gi(lane)[r], a1); a2 = r_fma(R(0.5), (rv * rv), a2);
           }
         }
         p0(lane) = a0; p1(lane) = a1; p2(lane) = a2;
@@ -1440,10 +1465,10 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
         if (j < na) {
           real acc = R(0.);
 #pragma unroll 4
-          for (int i = 0; i < na; ++i) acc += A[i * ldc + j] * ress[i];
+          for (int i = 0; i < na; ++i) acc = r_fma(A[i * ldc + j], ress[i], acc);
           real xn = xni(lane)[r];
           real dlt = r_max(xn - acc, R(0.)) - xn;
-          e2 += dlt * dlt;
+          e2 = r_fma(dlt, dlt, e2);
           real yv = xn + mom * (xn - xi(lane)[r]);
           yi(lane)[r] = yv; ys[j] = yv;
           xi(lane)[r] = xn; xs[j] = xn;
@@ -1461,7 +1486,7 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
     for (int j = lane; j < nv; j += G) {
       real acc = R(0.);
 #pragma unroll 4
-      for (int p = 0; p < na; ++p) acc += J[orig[p] * ldj + j] * xs[p];
+      for (int p = 0; p < na; ++p) acc = r_fma(J[orig[p] * ldj + j], xs[p], acc);
       s[D.s_qfc + j] = acc;
     }
   });
@@ -1631,7 +1656,7 @@ BXG_HD void con_jacobian(X& ex, const Ctx& c) {
       real diag = R(0.), aref = R(0.);
       if (active) {
         real vel = R(0.);
-        for (int d = 0; d < nv; ++d) vel += J[row * nvp + d] * s[D.s_qd + d];
+        for (int d = 0; d < nv; ++d) vel = r_fma(J[row * nvp + d], s[D.s_qd + d], vel);
         real imp;
         int spi = cc;
         if constexpr (Cfg::NC4 >= 20) spi = mi[D.m_con_sp_idx + cc];   // 80-row variant: distinct parameter sets stored once
@@ -1765,7 +1790,7 @@ BXG_HD V3 env_com(const Ctx& c) {
   for (int l = 0; l < D.L; ++l) {
     real m = mf[D.m_in_mass + l];
     V3 xi = ld3(s + D.s_x_pos + 3 * l) + rotate(ld3(mf + D.m_in_pos + 3 * l), ld4(s + D.s_x_rot + 4 * l));
-    msum = msum + xi * m; mtot += m;
+    msum = fmav(xi, m, msum); mtot += m;
   }
   return V3{msum.x / mtot, msum.y / mtot, msum.z / mtot};
 }
@@ -1895,7 +1920,7 @@ BXG_HD void env_epilogue(X& ex, const Ctx& c, const BxgEnvSpec& sp, const IO& io
   }
   real healthy_reward = sp.terminate_when_unhealthy ? sp.healthy_reward : sp.healthy_reward * is_healthy;
   real sq = R(0.);
-  for (int a = 0; a < D.nu; ++a) sq += s[D.s_act + a] * s[D.s_act + a];
+  for (int a = 0; a < D.nu; ++a) sq = r_fma(s[D.s_act + a], s[D.s_act + a], sq);
   real ctrl_cost = sp.ctrl_cost_weight * sq;
   real reward = com_kind ? (forward_reward + healthy_reward) - ctrl_cost : ((forward_reward + healthy_reward) - ctrl_cost) - R(0.);
   real done = sp.terminate_when_unhealthy ? R(1.) - is_healthy : R(0.);

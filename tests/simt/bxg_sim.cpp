@@ -153,6 +153,8 @@ int dispatch(const BxgModelDesc* desc, int vid, A... a) {
 
 extern "C" {
 int sim_sizeof_real() { return (int)sizeof(real); }
+// the kernel's sine / cosine (bxg_core.cuh r_sincos) on n values: tests/test_kernel_math.py
+void sim_sincos(const real* x, int n, real* s, real* c) { for (int i = 0; i < n; ++i) bxg::r_sincos(x[i], s + i, c + i); }
 // variant: -1 = the one the library would pick, else a forced kernel variant id
 int sim_init(const BxgModelDesc* desc, int variant, int mode, int64_t n_env, const real* q, const real* qd, const SimState* out) {
   return dispatch(desc, variant, mode, true, n_env, 0, q, qd, (const SimState*)nullptr, (const real*)nullptr, out, 0, (const BxgDiag*)nullptr,

@@ -17,11 +17,16 @@ _CSRC = os.path.join(os.path.dirname(os.path.dirname(_HERE)), 'brax_b200', 'csrc
 
 def build(force=False):
   deps = [_SRC] + [os.path.join(_CSRC, f) for f in ('bxg_core.cuh', 'bxg_model.h')]
+  # explicit fmaf() calls become one instruction where the CPU has FMA (same result as libm's software fmaf)
+  try:
+    hw_fma = ' fma ' in open('/proc/cpuinfo').read()
+  except OSError:
+    hw_fma = False
   jobs = []
   for so, extra in ((_SO, []), (_SO64, ['-DBXG_REAL=double', '-DBXG_SIM_F64'])):
     if not force and os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(d) for d in deps):
       continue
-    jobs.append(subprocess.Popen(['g++', '-O2', '-ffp-contract=off', '-fPIC', '-shared', '-std=c++17', '-Wno-unknown-pragmas'] + extra + [_SRC, '-o', so]))
+    jobs.append(subprocess.Popen(['g++', '-O2', '-ffp-contract=off', '-fPIC', '-shared', '-std=c++17', '-Wno-unknown-pragmas'] + (['-mfma'] if hw_fma else []) + extra + [_SRC, '-o', so]))
   for j in jobs:
     if j.wait() != 0:
       raise RuntimeError('g++ failed for the host emulator')
