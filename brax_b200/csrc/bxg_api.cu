@@ -34,6 +34,24 @@ extern "C" {
 const void* bxg_step_chol_kernel_v0(); const void* bxg_step_chol_kernel_v1(); const void* bxg_step_chol_kernel_v2();
 const void* bxg_step_chol_kernel_v3(); const void* bxg_step_chol_kernel_v4(); const void* bxg_step_chol_kernel_v5(); const void* bxg_step_chol_kernel_v6(); const void* bxg_step_chol_kernel_v7(); const void* bxg_step_chol_kernel_v8(); const void* bxg_step_chol_kernel_v9();
 }
+extern "C" {
+const void* bxg_step_lean_kernel_v0(); const void* bxg_step_lean_kernel_v1(); const void* bxg_step_lean_kernel_v2(); const void* bxg_step_lean_kernel_v3(); const void* bxg_step_lean_kernel_v4(); const void* bxg_step_lean_kernel_v5(); const void* bxg_step_lean_kernel_v6(); const void* bxg_step_lean_kernel_v7(); const void* bxg_step_lean_kernel_v8(); const void* bxg_step_lean_kernel_v9();
+const void* bxg_step_chol_lean_kernel_v0(); const void* bxg_step_chol_lean_kernel_v1(); const void* bxg_step_chol_lean_kernel_v2(); const void* bxg_step_chol_lean_kernel_v3(); const void* bxg_step_chol_lean_kernel_v4(); const void* bxg_step_chol_lean_kernel_v5(); const void* bxg_step_chol_lean_kernel_v6(); const void* bxg_step_chol_lean_kernel_v7(); const void* bxg_step_chol_lean_kernel_v8(); const void* bxg_step_chol_lean_kernel_v9();
+}
+static const void* step_lean_kernel_of(int v, bool chol) {
+  switch (v) {
+    case 0: return chol ? bxg_step_chol_lean_kernel_v0() : bxg_step_lean_kernel_v0();
+    case 1: return chol ? bxg_step_chol_lean_kernel_v1() : bxg_step_lean_kernel_v1();
+    case 2: return chol ? bxg_step_chol_lean_kernel_v2() : bxg_step_lean_kernel_v2();
+    case 4: return chol ? bxg_step_chol_lean_kernel_v4() : bxg_step_lean_kernel_v4();
+    case 5: return chol ? bxg_step_chol_lean_kernel_v5() : bxg_step_lean_kernel_v5();
+    case 6: return chol ? bxg_step_chol_lean_kernel_v6() : bxg_step_lean_kernel_v6();
+    case 7: return chol ? bxg_step_chol_lean_kernel_v7() : bxg_step_lean_kernel_v7();
+    case 8: return chol ? bxg_step_chol_lean_kernel_v8() : bxg_step_lean_kernel_v8();
+    case 9: return chol ? bxg_step_chol_lean_kernel_v9() : bxg_step_lean_kernel_v9();
+    default: return chol ? bxg_step_chol_lean_kernel_v3() : bxg_step_lean_kernel_v3();
+  }
+}
 static const void* step_chol_kernel_of(int v) {
   switch (v) { case 0: return bxg_step_chol_kernel_v0(); case 1: return bxg_step_chol_kernel_v1(); case 2: return bxg_step_chol_kernel_v2();
                case 4: return bxg_step_chol_kernel_v4(); case 5: return bxg_step_chol_kernel_v5(); case 6: return bxg_step_chol_kernel_v6(); case 7: return bxg_step_chol_kernel_v7(); case 8: return bxg_step_chol_kernel_v8(); case 9: return bxg_step_chol_kernel_v9(); default: return bxg_step_chol_kernel_v3(); }
@@ -79,6 +97,10 @@ struct DeviceGuard {
   ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
 };
 
+// BXG_STEP_LEAN: only the leaves that mode touches
+bool state_ok_lean(const BxgState* s) {
+  return s && s->q && s->qd && s->x_pos && s->x_rot && s->xd_ang && s->xd_vel && s->mass_mx_inv;
+}
 bool state_ok(const BxgState* s, int nc) {
   if (!s) return false;
   const float* const* p = reinterpret_cast<const float* const*>(s);
@@ -135,8 +157,9 @@ int bxg_model_create(const BxgModelDesc* desc, int device, BxgModel** out) {
   // raise it to the device maximum, never to this model's own size
   const void* ks = m->pm.d.minv_mode == BXG_MINV_CHOLESKY ? step_chol_kernel_of(m->pm.variant_id) : step_kernel_of(m->pm.variant_id);
   const void* ki = init_kernel_of(m->pm.variant_id);
+  const void* kl = step_lean_kernel_of(m->pm.variant_id, m->pm.d.minv_mode == BXG_MINV_CHOLESKY);
   // (dynamic + the kernel's few bytes of static shared memory must fit the opt-in limit)
-  for (const void* k : {ks, ki}) {
+  for (const void* k : {ks, ki, kl}) {
     cudaFuncAttributes fa;
     if ((ce = cudaFuncGetAttributes(&fa, k)) != cudaSuccess) return cleanup(cuda_fail(ce, "cudaFuncGetAttributes"));
     const int dyn_max = (int)prop.sharedMemPerBlockOptin - (int)fa.sharedSizeBytes;
@@ -229,9 +252,10 @@ int bxg_step(const BxgModel* m, int64_t n_env, int32_t n_frames, const BxgState*
   if (!m) return fail(BXG_E_INVALID, "null model");
   if (n_frames < 0) return fail(BXG_E_INVALID, "n_frames < 0");
   if (n_env <= 0) return n_env == 0 ? BXG_OK : fail(BXG_E_INVALID, "n_env < 0");
-  if (!state_ok(in, m->pm.d.nc) || !state_ok(out, m->pm.d.nc)) return fail(BXG_E_INVALID, "null argument");
+  const bool lean = flags & BXG_STEP_LEAN;
+  if (lean ? (!state_ok_lean(in) || !state_ok_lean(out)) : (!state_ok(in, m->pm.d.nc) || !state_ok(out, m->pm.d.nc))) return fail(BXG_E_INVALID, "null argument");
   if (m->pm.d.nu > 0 && !act) return fail(BXG_E_INVALID, "act is NULL but the model has actuators");
-  BxgDiag dg{nullptr, nullptr};
+  BxgDiag dg{nullptr, nullptr, nullptr};
   if ((flags & BXG_STEP_DIAGNOSTICS) && diag) dg = *diag;
   cudaStream_t st = (cudaStream_t)stream;
   DeviceGuard guard(m->device);
@@ -240,7 +264,9 @@ int bxg_step(const BxgModel* m, int64_t n_env, int32_t n_frames, const BxgState*
   BxgEnvSpec env{}; BxgEnvIO eio{}; BxgState first{};
   void* args[] = {(void*)&m->pm.d, (void*)&m->d_blob, (void*)in, (void*)&act, (void*)out, (void*)&n_env, (void*)&nf, (void*)&fl, (void*)&dg,
                   (void*)&env, (void*)&eio, (void*)&first};
-  BXG_CUDA(cudaLaunchKernel(m->pm.d.minv_mode == BXG_MINV_CHOLESKY ? step_chol_kernel_of(m->pm.variant_id) : step_kernel_of(m->pm.variant_id), dim3(ls.grid), dim3(ls.threads), args, ls.smem, st));
+  const bool chol = m->pm.d.minv_mode == BXG_MINV_CHOLESKY;
+  const void* kern = lean ? step_lean_kernel_of(m->pm.variant_id, chol) : (chol ? step_chol_kernel_of(m->pm.variant_id) : step_kernel_of(m->pm.variant_id));
+  BXG_CUDA(cudaLaunchKernel(kern, dim3(ls.grid), dim3(ls.threads), args, ls.smem, st));
   g_launches.fetch_add(1);
   BXG_CUDA(cudaGetLastError());
   return BXG_OK;
@@ -288,20 +314,23 @@ int bxg_env_step(const BxgModel* m, const BxgEnvSpec* spec, int64_t n_env, int32
   if (spec->kind == BXG_ENV_PLANAR && m->pm.d.nq < 3) return fail(BXG_E_INVALID, "planar env kind needs q = [x, z, angle, ...]");
   if (n_frames < 1) return fail(BXG_E_INVALID, "n_frames < 1");
   if (n_env <= 0) return n_env == 0 ? BXG_OK : fail(BXG_E_INVALID, "n_env < 0");
-  if (!state_ok(in, m->pm.d.nc) || !state_ok(out, m->pm.d.nc)) return fail(BXG_E_INVALID, "null state leaf");
+  const bool lean = io->flags & BXG_STEP_LEAN;
+  if (lean ? (!state_ok_lean(in) || !state_ok_lean(out)) : (!state_ok(in, m->pm.d.nc) || !state_ok(out, m->pm.d.nc))) return fail(BXG_E_INVALID, "null state leaf");
   if (!io->obs || !io->reward || !io->done || !io->metrics) return fail(BXG_E_INVALID, "null env output");
-  if (io->first_state && (!state_ok(io->first_state, m->pm.d.nc) || !io->first_obs)) return fail(BXG_E_INVALID, "null first_state leaf");
+  if (io->first_state && (!(lean ? state_ok_lean(io->first_state) : state_ok(io->first_state, m->pm.d.nc)) || !io->first_obs)) return fail(BXG_E_INVALID, "null first_state leaf");
   if (m->pm.d.nu > 0 && !action) return fail(BXG_E_INVALID, "action is NULL but the model has actuators");
   cudaStream_t st = (cudaStream_t)stream;
   DeviceGuard guard(m->device);
   LaunchShape ls = launch_shape(m, n_env);
-  int nf = n_frames, fl = 0;
-  BxgDiag dg{nullptr, nullptr};
+  int nf = n_frames, fl = io->flags & BXG_STEP_LEAN;
+  BxgDiag dg{nullptr, nullptr, nullptr};
   BxgEnvSpec env = *spec; BxgEnvIO eio = *io; BxgState first{};
   if (io->first_state) first = *io->first_state;
   void* args[] = {(void*)&m->pm.d, (void*)&m->d_blob, (void*)in, (void*)&action, (void*)out, (void*)&n_env, (void*)&nf, (void*)&fl, (void*)&dg,
                   (void*)&env, (void*)&eio, (void*)&first};
-  BXG_CUDA(cudaLaunchKernel(m->pm.d.minv_mode == BXG_MINV_CHOLESKY ? step_chol_kernel_of(m->pm.variant_id) : step_kernel_of(m->pm.variant_id), dim3(ls.grid), dim3(ls.threads), args, ls.smem, st));
+  const bool chol = m->pm.d.minv_mode == BXG_MINV_CHOLESKY;
+  const void* kern = lean ? step_lean_kernel_of(m->pm.variant_id, chol) : (chol ? step_chol_kernel_of(m->pm.variant_id) : step_kernel_of(m->pm.variant_id));
+  BXG_CUDA(cudaLaunchKernel(kern, dim3(ls.grid), dim3(ls.threads), args, ls.smem, st));
   g_launches.fetch_add(1);
   BXG_CUDA(cudaGetLastError());
   return BXG_OK;

@@ -180,7 +180,22 @@ struct Ctx {
   real* s;         // this env's slab
 };
 
-struct Stats { int pg_iters, pg_trials, ns_accepts, ns_cold; };
+struct Stats {
+  int pg_iters, pg_trials, ns_accepts, ns_cold;
+#if defined(BXG_PHASE_TIMERS)
+  long long t_last;                  // tuning builds: start of the current phase (clock64)
+  unsigned long long* phase_cycles;  // BxgDiag.phase_cycles: lane 0 of every warp adds its cycles at each phase end
+#endif
+};
+// phases: 0 load, 1 dynamics, 2 constraint.force, 12 the CTA barrier behind it, 3 integrate, 4 kinematics, 5 transform_com,
+// 6 mass.matrix, 7 matrix_inv, 8 constraint.jacobian, 9 env prologue / epilogue, 10 store, 11 lean entry
+#if defined(BXG_PHASE_TIMERS) && defined(__CUDA_ARCH__)
+#define BXG_PHASE_BEGIN(st) ((st)->t_last = clock64())
+#define BXG_PHASE_END(st, k) do { long long t__ = clock64(); if ((st)->phase_cycles && (threadIdx.x & 31) == 0) atomicAdd((st)->phase_cycles + (k), (unsigned long long)(t__ - (st)->t_last)); (st)->t_last = clock64(); } while (0)
+#else
+#define BXG_PHASE_BEGIN(st) ((void)0)
+#define BXG_PHASE_END(st, k) ((void)0)
+#endif
 
 // Compile-time kernel configuration: lanes per env and register-row widths.
 // GENERIC_TOO keeps the any-size code reachable next to the specialised kernels
@@ -317,7 +332,7 @@ BXG_HD void dyn_forces(X& ex, const Ctx& c) {
     ex.lanes([&](int l) {
       if (l >= L) return;
       V3 ca = ld3(s + D.s_t_ang + 3 * l), cv = ld3(s + D.s_t_vel + 3 * l);
-      V3 ip = ld3(s + D.s_cinr_pos + 3 * l); const real* im = s + D.s_cinr_i + 9 * l; real mass = s[D.s_cinr_mass + l];
+      V3 ip = ld3(s + D.s_cinr_pos + 3 * l); const real* im = s + D.s_cinr_i + 9 * l; real mass = mf[D.m_in_mass + l];
       V3 cda = ld3(s + D.s_cd_ang + 3 * l), cdv = ld3(s + D.s_cd_vel + 3 * l);
       V3 fa, fv, ga, gv;
       inertia_mul(ip, im, mass, ca, cv, &fa, &fv);
@@ -604,31 +619,44 @@ BXG_HD void integrate(X& ex, const Ctx& c) {
 }
 
 // -------------------------------------------------------- kinematics.forward
-template <class X>
+// VEL = false: link poses x only.  Nothing in the physics reads the link velocities xd (they are an output leaf and
+// an input of some env observations), so the substeps skip them; finish_env() runs the full function once, after
+// the last substep, and xd then lives in the t_ang / t_vel temporaries (dead by then) instead of its own slab words.
+// The joint transform / motion of a link is produced and consumed by the same lane: it stays in registers.
+template <class X, bool VEL>
 BXG_HD void kinematics(X& ex, const Ctx& c) {
   const Dims& D = *c.D; const real* mf = c.mf; const int* mi = c.mi; real* s = c.s;
   const int L = D.L;
-  real* jpos = s + D.s_f_ang; real* jrot = s + D.s_j_rot; real* jdang = s + D.s_t_ang; real* jdvel = s + D.s_t_vel;
+#if BXG_KIN_REGS
+  typename X::template LaneVec<VEL ? 13 : 7> jt;   // [pos 3, rot 4, (ang 3, vel 3)] of this lane's link
+#else
+  typename X::template LaneVec<VEL ? 6 : 1> jdv;   // joint motion (ang 3, vel 3) of this lane's link; the joint transform goes through shared memory
+  real* jpos = s + D.s_f_ang; real* jrot = s + D.s_j_rot;
+#endif
   ex.lanes([&](int l) {
     if (l >= L) return;
     int qa = mi[D.m_link_qadr + l], da = mi[D.m_link_dadr + l], nd = mi[D.m_link_ndof + l];
-    V3 p, a, v; Q4 r;
+    V3 p, a{0, 0, 0}, v{0, 0, 0}; Q4 r;
     if (nd == 0) {
       p = ld3(s + D.s_q + qa); r = ld4(s + D.s_q + qa + 3);
-      v = ld3(s + D.s_qd + da); a = ld3(s + D.s_qd + da + 3);
+      if constexpr (VEL) { v = ld3(s + D.s_qd + da); a = ld3(s + D.s_qd + da + 3); }
     } else {
-      p = V3{0, 0, 0}; a = p; v = p; r = Q4{1, 0, 0, 0};
+      p = V3{0, 0, 0}; r = Q4{1, 0, 0, 0};
       for (int k = 0; k < nd; ++k) {
-        int d = da + k; real qk = s[D.s_q + qa + k], qdk = s[D.s_qd + d];
+        int d = da + k; real qk = s[D.s_q + qa + k];
         V3 mang = ld3(mf + D.m_dof_ang + 3 * d), mvel = ld3(mf + D.m_dof_vel + 3 * d);
         Q4 sr = axis_quat(mang, qk);
-        V3 sp = mvel * qk, sa = mang * qdk, sv = mvel * qdk;
+        V3 sp = mvel * qk;
+        V3 sa{0, 0, 0}, sv{0, 0, 0};
+        if constexpr (VEL) { real qdk = s[D.s_qd + d]; sa = mang * qdk; sv = mvel * qdk; }
         if (k == 0) { p = sp; r = sr; a = sa; v = sv; }
         else {
           V3 np_; Q4 nr;
           tf_do(p, r, sp, sr, &np_, &nr);
-          a = a + rotate(sa, sr);
-          v = v + rotate(sv + cross(sp, sa), sr);
+          if constexpr (VEL) {
+            a = a + rotate(sa, sr);
+            v = v + rotate(sv + cross(sp, sa), sr);
+          }
           p = np_; r = nr;
         }
       }
@@ -638,25 +666,42 @@ BXG_HD void kinematics(X& ex, const Ctx& c) {
     p = (p + jp) - anc;
     V3 tp; Q4 tr;
     tf_do(ld3(mf + D.m_tf_pos + 3 * l), ld4(mf + D.m_tf_rot + 4 * l), p, r, &tp, &tr);
-    st3(jpos + 3 * l, tp); st4(jrot + 4 * l, tr); st3(jdang + 3 * l, a); st3(jdvel + 3 * l, v);
+#if BXG_KIN_REGS
+    real* j = jt(l);
+    st3(j, tp); st4(j + 3, tr);
+    if constexpr (VEL) { st3(j + 7, a); st3(j + 10, v); }
+#else
+    st3(jpos + 3 * l, tp); st4(jrot + 4 * l, tr);
+    if constexpr (VEL) { st3(jdv(l), a); st3(jdv(l) + 3, v); }
+#endif
   });
   for (int lvl = 0; lvl <= D.max_depth; ++lvl) {
     ex.lanes([&](int l) {
       if (l >= L || mi[D.m_link_depth + l] != lvl) return;
       int p = mi[D.m_link_parent + l];
-      V3 jp = ld3(jpos + 3 * l), ja = ld3(jdang + 3 * l), jv = ld3(jdvel + 3 * l); Q4 jr = ld4(jrot + 4 * l);
+      V3 ja{0, 0, 0}, jv{0, 0, 0};
+#if BXG_KIN_REGS
+      const real* j = jt(l);
+      V3 jp = ld3(j); Q4 jr = ld4(j + 3);
+      if constexpr (VEL) { ja = ld3(j + 7); jv = ld3(j + 10); }
+#else
+      V3 jp = ld3(jpos + 3 * l); Q4 jr = ld4(jrot + 4 * l);
+      if constexpr (VEL) { ja = ld3(jdv(l)); jv = ld3(jdv(l) + 3); }
+#endif
       if (p < 0) {
         st3(s + D.s_x_pos + 3 * l, jp); st4(s + D.s_x_rot + 4 * l, jr);
-        st3(s + D.s_xd_ang + 3 * l, rotate(ja, jr)); st3(s + D.s_xd_vel + 3 * l, jv);
+        if constexpr (VEL) { st3(s + D.s_xd_ang + 3 * l, rotate(ja, jr)); st3(s + D.s_xd_vel + 3 * l, jv); }
       } else {
         V3 pp = ld3(s + D.s_x_pos + 3 * p); Q4 pr = ld4(s + D.s_x_rot + 4 * p);
-        V3 pa = ld3(s + D.s_xd_ang + 3 * p), pv = ld3(s + D.s_xd_vel + 3 * p);
         V3 xp; Q4 xr;
         tf_do(pp, pr, jp, jr, &xp, &xr);
-        V3 vel = (pv + cross(pa, xp - pp)) + rotate(jv, pr);
-        V3 ang = pa + rotate(ja, xr);
         st3(s + D.s_x_pos + 3 * l, xp); st4(s + D.s_x_rot + 4 * l, xr);
-        st3(s + D.s_xd_ang + 3 * l, ang); st3(s + D.s_xd_vel + 3 * l, vel);
+        if constexpr (VEL) {
+          V3 pa = ld3(s + D.s_xd_ang + 3 * p), pv = ld3(s + D.s_xd_vel + 3 * p);
+          V3 vel = (pv + cross(pa, xp - pp)) + rotate(jv, pr);
+          V3 ang = pa + rotate(ja, xr);
+          st3(s + D.s_xd_ang + 3 * l, ang); st3(s + D.s_xd_vel + 3 * l, vel);
+        }
       }
     });
   }
@@ -664,6 +709,14 @@ BXG_HD void kinematics(X& ex, const Ctx& c) {
     if (l >= L) return;
     st4(s + D.s_x_rot + 4 * l, qnormalize(ld4(s + D.s_x_rot + 4 * l)));
   });
+}
+// After the last substep (and after init): kinematics.forward in full.  x comes out as it already is (same inputs,
+// same code), xd is produced here, into the t_ang / t_vel temporaries (bxg_model.h: s_xd_* alias them).
+template <class X>
+BXG_HD void finish_env(X& ex, const Ctx& c) {
+#if BXG_XD_TAIL
+  kinematics<X, true>(ex, c);
+#endif
 }
 
 // ---------------------------------------------------- dynamics.transform_com
@@ -719,7 +772,6 @@ BXG_HD void transform_com(X& ex, const Ctx& c) {
       s[D.s_cinr_i + 9 * l + 3 * a + b] = r_fma(hh, mass, acc);
     }
     st3(s + D.s_cinr_pos + 3 * l, p * mass);
-    s[D.s_cinr_mass + l] = mass;
     // joint frame j = parent.do(link.transform).do(link.joint)  (dynamics.py:47-52)
     int nd = mi[D.m_link_ndof + l], qa = mi[D.m_link_qadr + l], da = mi[D.m_link_dadr + l];
     int pi = nd == 0 ? l : mi[D.m_link_parent + l];
@@ -810,7 +862,7 @@ BXG_HD void mass_matrix(X& ex, const Ctx& c) {
     if (lane < L) {
       for (int i = 0; i < 3; ++i) s[D.s_crb_pos + 3 * lane + i] = s[D.s_cinr_pos + 3 * lane + i];
       for (int i = 0; i < 9; ++i) s[D.s_crb_i + 9 * lane + i] = s[D.s_cinr_i + 9 * lane + i];
-      s[D.s_crb_mass + lane] = s[D.s_cinr_mass + lane];
+      s[D.s_crb_mass + lane] = mf[D.m_in_mass + lane];
     }
     for (int i = 4 * lane; i < D.nvw * nvp; i += 4 * X::G) stv4(M + i, F4{R(0.), R(0.), R(0.), R(0.)});   // incl. padding rows (slot shared with A)
   });
@@ -1700,10 +1752,13 @@ BXG_HD void con_jacobian(X& ex, const Ctx& c) {
 template <class X, class Cfg, int INV>
 BXG_HD void update_position_terms(X& ex, const Ctx& c, Stats* st, bool in_step) {
   const int sl = in_step ? c.D->sync_level : 0;
-  kinematics(ex, c);
+  kinematics<X, !BXG_XD_TAIL>(ex, c);
+  BXG_PHASE_END(st, 4);
   transform_com(ex, c);
+  BXG_PHASE_END(st, 5);
   if (sl & 8) ex.cta_sync();
   mass_matrix(ex, c);
+  BXG_PHASE_END(st, 6);
   if (sl & 16) ex.cta_sync();
   if constexpr (INV == 1) {
     bool done = false;
@@ -1715,8 +1770,10 @@ BXG_HD void update_position_terms(X& ex, const Ctx& c, Stats* st, bool in_step) 
     if (c.D->ns_iters == 0) spd_inverse(ex, c, c.s + c.D->s_M, c.s + c.D->s_Minv, c.s + c.D->s_scr, nullptr, R(0.));
     else minv_newton_schulz<X, Cfg>(ex, c, st);
   }
+  BXG_PHASE_END(st, 7);
   if (sl & 2) ex.cta_sync();
   con_jacobian<X, Cfg>(ex, c);
+  BXG_PHASE_END(st, 8);
 }
 
 // pipeline.step (pipeline.py:78-94)
@@ -1725,12 +1782,17 @@ BXG_HD void substep(X& ex, const Ctx& c, Stats* st) {
   // CTA-wide phase alignment keeps the warps of a CTA on the same straight-line
   // code (instruction-cache locality); sync_level trades that against barrier waits
   const int sl = c.D->sync_level;
+  BXG_PHASE_BEGIN(st);
   if (sl & 4) ex.cta_sync();
   dyn_forces<X, Cfg>(ex, c);
+  BXG_PHASE_END(st, 1);
   if (sl & 32) ex.cta_sync();
   con_force<X, Cfg>(ex, c, st);
+  BXG_PHASE_END(st, 2);
   if (sl & 1) ex.cta_sync();
+  BXG_PHASE_END(st, 12);
   integrate(ex, c);
+  BXG_PHASE_END(st, 3);
   update_position_terms<X, Cfg, INV>(ex, c, st, true);
 }
 
@@ -2038,7 +2100,6 @@ BXG_HD void load_env(X& ex, const Ctx& c, const ST& g, const real* act, int64_t 
       s[D.s_cd_ang + i] = g.cd_ang[e * L * 3 + i]; s[D.s_cd_vel + i] = g.cd_vel[e * L * 3 + i];
     }
     for (int i = lane; i < L * 9; i += G) s[D.s_cinr_i + i] = g.cinr_i[e * L * 9 + i];
-    for (int i = lane; i < L; i += G) s[D.s_cinr_mass + i] = g.cinr_mass[e * L + i];
     if (D.fluid) {   // fluid.force reads x and root_com of the incoming state (dynamics.py:199-206)
       for (int i = lane; i < L * 3; i += G) { s[D.s_x_pos + i] = g.x_pos[e * L * 3 + i]; s[D.s_root_com + i] = g.root_com[e * L * 3 + i]; }
       for (int i = lane; i < L * 4; i += G) s[D.s_x_rot + i] = g.x_rot[e * L * 4 + i];
@@ -2078,6 +2139,74 @@ BXG_HD void load_env(X& ex, const Ctx& c, const ST& g, const real* act, int64_t 
   });
 }
 
+// ---- lean state I/O (BXG_STEP_LEAN) ------------------------------------------------
+// q, qd, act and mass_mx_inv are the step's only independent inputs: every other leaf it reads is a function of
+// (q, qd) that the previous step (or init) computed with the code below, so recomputing it at entry gives the
+// same bits.  x of the incoming state is read by the env prologue (pre-step reference point).
+template <class X, class ST>
+BXG_HD void load_env_lean(X& ex, const Ctx& c, const ST& g, const real* act, int64_t e) {
+  const Dims& D = *c.D; real* s = c.s;
+  const int nv = D.nv, nq = D.nq, nvp = D.nvp;
+  ex.lanes([&](int lane) {
+    const int G = X::G;
+    for (int i = lane; i < nq; i += G) s[D.s_q + i] = g.q[e * nq + i];
+    for (int i = lane; i < nv; i += G) s[D.s_qd + i] = g.qd[e * nv + i];
+    for (int i = lane; i < D.nu; i += G) s[D.s_act + i] = act[e * D.nu + i];
+    const int dq = G / nv, dr = G - dq * nv;
+    int r = lane / nv, cc = lane - r * nv;
+    for (int i = lane; i < nv * nv; i += G) {
+      s[D.s_Minv + r * nvp + cc] = g.mass_mx_inv[e * nv * nv + i];
+      r += dq; cc += dr; if (cc >= nv) { cc -= nv; ++r; }
+    }
+  });
+}
+// what update_position_terms leaves behind, minus the Newton-Schulz run that produced the incoming mass_mx_inv
+template <class X, class Cfg>
+BXG_HD void lean_entry(X& ex, const Ctx& c) {
+  kinematics<X, !BXG_XD_TAIL>(ex, c);
+  transform_com(ex, c);
+  if (c.D->ns_iters == 0) mass_matrix(ex, c);   // integrate's implicit-damping solve reads M (integrator.py:58-60)
+  con_jacobian<X, Cfg>(ex, c);
+}
+template <class X, class ST>
+BXG_HD void store_env_lean(X& ex, const Ctx& c, const ST& g, int64_t e, const BxgDiag* dg, const Stats& st) {
+  const Dims& D = *c.D; const real* s = c.s;
+  const int L = D.L, nv = D.nv, nq = D.nq, nvp = D.nvp;
+  ex.lanes([&](int lane) {
+    const int G = X::G;
+    for (int i = lane; i < nq; i += G) g.q[e * nq + i] = s[D.s_q + i];
+    for (int i = lane; i < nv; i += G) g.qd[e * nv + i] = s[D.s_qd + i];
+    for (int i = lane; i < L * 3; i += G) {
+      g.x_pos[e * L * 3 + i] = s[D.s_x_pos + i]; g.xd_ang[e * L * 3 + i] = s[D.s_xd_ang + i]; g.xd_vel[e * L * 3 + i] = s[D.s_xd_vel + i];
+    }
+    for (int i = lane; i < L * 4; i += G) g.x_rot[e * L * 4 + i] = s[D.s_x_rot + i];
+    const int dq = G / nv, dr = G - dq * nv;
+    int r = lane / nv, cc = lane - r * nv;
+    for (int i = lane; i < nv * nv; i += G) {
+      g.mass_mx_inv[e * nv * nv + i] = s[D.s_Minv + r * nvp + cc];
+      r += dq; cc += dr; if (cc >= nv) { cc -= nv; ++r; }
+    }
+    if (dg) {
+      if (dg->con_dist) for (int i = lane; i < D.ncon; i += G) dg->con_dist[e * D.ncon + i] = s[D.s_dist + i];
+      if (dg->stats && lane == 0) {
+        int32_t* o = dg->stats + e * 4;
+        o[0] += st.pg_iters; o[1] += st.pg_trials; o[2] += st.ns_accepts; o[3] += st.ns_cold;
+      }
+    }
+  });
+}
+template <class X, class ST>
+BXG_HD void store_first_state_lean(X& ex, const Ctx& c, const ST& g, const ST& f, int64_t e) {
+  const Dims& D = *c.D;
+  const int L = D.L, nv = D.nv, nq = D.nq;
+  ex.lanes([&](int lane) {
+    const int G = X::G;
+    auto cp = [&](real* dst, const real* src, int n) { for (int i = lane; i < n; i += G) dst[e * n + i] = src[e * n + i]; };
+    cp(g.q, f.q, nq); cp(g.qd, f.qd, nv); cp(g.x_pos, f.x_pos, L * 3); cp(g.x_rot, f.x_rot, L * 4);
+    cp(g.xd_ang, f.xd_ang, L * 3); cp(g.xd_vel, f.xd_vel, L * 3); cp(g.mass_mx_inv, f.mass_mx_inv, nv * nv);
+  });
+}
+
 template <class X>
 BXG_HD void load_env_qqd(X& ex, const Ctx& c, const real* q, const real* qd, int64_t e) {
   const Dims& D = *c.D; real* s = c.s;
@@ -2105,7 +2234,7 @@ BXG_HD void store_env(X& ex, const Ctx& c, const ST& g, int64_t e, const BxgDiag
     }
     for (int i = lane; i < L * 4; i += G) { g.x_rot[e * L * 4 + i] = s[D.s_x_rot + i]; g.cinr_rot[e * L * 4 + i] = s[D.s_cinr_rot + i]; }
     for (int i = lane; i < L * 9; i += G) g.cinr_i[e * L * 9 + i] = s[D.s_cinr_i + i];
-    for (int i = lane; i < L; i += G) g.cinr_mass[e * L + i] = s[D.s_cinr_mass + i];
+    for (int i = lane; i < L; i += G) g.cinr_mass[e * L + i] = c.mf[D.m_in_mass + i];   // cinr.mass is the link's mass (base.py:588-594)
     for (int i = lane; i < nv * 3; i += G) {
       g.cdof_ang[e * nv * 3 + i] = s[D.s_cdof_ang + i]; g.cdof_vel[e * nv * 3 + i] = s[D.s_cdof_vel + i];
       g.cdofd_ang[e * nv * 3 + i] = s[D.s_cdofd_ang + i]; g.cdofd_vel[e * nv * 3 + i] = s[D.s_cdofd_vel + i];

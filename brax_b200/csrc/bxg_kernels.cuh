@@ -105,7 +105,9 @@ __device__ __forceinline__ void stage_model(const Dims& D, const uint32_t* __res
   __syncthreads();
 }
 
-template <class Cfg, int INV>
+// LEAN (BXG_STEP_LEAN, include/bxg.h) is a compile-time mode: with the lean entry code in the same kernel the
+// default path loses 4 % (Ant) to the larger register / code footprint (profiles/r02_ab_lean_code.txt).
+template <class Cfg, int INV, bool LEAN>
 __global__ void __launch_bounds__(Cfg::MAX_THREADS)
 step_kernel(const Dims D, const uint32_t* __restrict__ model, const BxgState in, const float* __restrict__ act,
             const BxgState out, int64_t n_env, int n_frames, int flags, const BxgDiag diag,
@@ -128,17 +130,33 @@ step_kernel(const Dims D, const uint32_t* __restrict__ model, const BxgState in,
     int64_t e = p * per_pass + (int64_t)blockIdx.x * groups + group;
     const bool valid = e < n_env;
     if (!valid) e = n_env - 1;
-    Stats st{0, 0, 0, 0};
+    Stats st{};
+#if defined(BXG_PHASE_TIMERS)
+    st.phase_cycles = valid ? diag.phase_cycles : nullptr;
+#endif
+    constexpr bool lean = LEAN;
+    BXG_PHASE_BEGIN(&st);
     prepare_env(ex, c);
-    load_env(ex, c, in, act, e);
-    if (env.kind) env_prologue(ex, c, env, in, e);
+    if constexpr (lean) load_env_lean(ex, c, in, act, e);
+    else load_env(ex, c, in, act, e);
+    BXG_PHASE_END(&st, 0);
+    if constexpr (lean) { lean_entry<DevExec<G>, Cfg>(ex, c); BXG_PHASE_END(&st, 11); }
+    if (env.kind) { env_prologue(ex, c, env, in, e); BXG_PHASE_END(&st, 9); }
     for (int f = 0; f < n_frames; ++f) substep<DevExec<G>, Cfg, INV>(ex, c, &st);
     bool done = false;
-    if (env.kind) env_epilogue(ex, c, env, eio, e, valid, &done);
+    BXG_PHASE_BEGIN(&st);
+    finish_env(ex, c);      // link velocities xd (once, not per substep)
+    BXG_PHASE_END(&st, 4);
+    if (env.kind) { env_epilogue(ex, c, env, eio, e, valid, &done); BXG_PHASE_END(&st, 9); }
     if (valid) {
-      if (done && eio.first_state) store_first_state(ex, c, out, first, e);   // AutoResetWrapper
-      else store_env(ex, c, out, e, (flags & BXG_STEP_DIAGNOSTICS) ? &diag : nullptr, st);
+      const BxgDiag* dg = (flags & BXG_STEP_DIAGNOSTICS) ? &diag : nullptr;
+      if (done && eio.first_state) {   // AutoResetWrapper
+        if constexpr (lean) store_first_state_lean(ex, c, out, first, e); else store_first_state(ex, c, out, first, e);
+      } else {
+        if constexpr (lean) store_env_lean(ex, c, out, e, dg, st); else store_env(ex, c, out, e, dg, st);
+      }
     }
+    BXG_PHASE_END(&st, 10);
   }
 }
 
@@ -162,10 +180,11 @@ init_kernel(const Dims D, const uint32_t* __restrict__ model, const float* __res
     int64_t e = p * per_pass + (int64_t)blockIdx.x * groups + group;
     const bool valid = e < n_env;
     if (!valid) e = n_env - 1;
-    Stats st{0, 0, 0, 0};
+    Stats st{};
     prepare_env(ex, c);
     load_env_qqd(ex, c, q, qd, e);
     init_env<DevExec<G>, Cfg>(ex, c, &st);
+    finish_env(ex, c);
     if (env.kind && valid) env_reset_obs(ex, c, env, obs + e * env_obs_size(D, env));
     if (valid) store_env(ex, c, out, e, nullptr, st);
   }

@@ -81,6 +81,15 @@ struct Dims {
   int env_words;
 };
 
+// Tuning switches (A/B builds, tools/build_alt.py).  XD_TAIL: link velocities once per launch (finish_env), their
+// slab words aliased to dead temporaries.  KIN_REGS: the joint transform of kinematics.forward stays in registers.
+#ifndef BXG_XD_TAIL
+#define BXG_XD_TAIL 1
+#endif
+#ifndef BXG_KIN_REGS
+#define BXG_KIN_REGS 0
+#endif
+
 // Row widths the register-row kernels are instantiated for (bxg_core.cuh).
 // Row stride: a multiple of 4 floats (16-byte rows for 128-bit shared loads) whose
 // chunk count is odd, so that lanes reading "their own row" with 128-bit
@@ -118,7 +127,7 @@ inline int mat_stride(const Variant& v, int w) { return v.VC4 == 6 ? w : row_str
 #define BXG_G32_MAXT 640
 #endif
 #ifndef BXG_G16_MAXT
-#define BXG_G16_MAXT 480   // 30 Ant envs per SM at 128 registers per thread
+#define BXG_G16_MAXT 512   // 32 Ant envs per SM (16 warps: four per scheduler) at 128 registers per thread
 #endif
 // (the 80-row variant holds few envs per SM: small CTAs, so each thread may keep up to 255 registers)
 constexpr int variant_max_threads(int G, int VC4, int NC4 = 0) { return G == 16 ? (VC4 == 6 ? 320 : BXG_G16_MAXT) : (NC4 >= 20 ? 256 : BXG_G32_MAXT); }
@@ -431,9 +440,10 @@ inline std::string pack_model_t(const BxgModelDesc& m, PackedModelT<R>* out, int
   // whole of constraint.force: in the specialised variants the part of A that does not fit M's slot spills
   // over this block, which therefore sits directly behind that slot (see below).
   auto take_kin_block = [&]() {
-    d.s_x_pos = take1(L * 3); d.s_x_rot = take1(L * 4); d.s_xd_ang = take1(L * 3); d.s_xd_vel = take1(L * 3);
+    d.s_x_pos = take1(L * 3); d.s_x_rot = take1(L * 4);   // (xd: see s_xd_* below)
+    if (!BXG_XD_TAIL) { d.s_xd_ang = take1(L * 3); d.s_xd_vel = take1(L * 3); }
     d.s_root_com = take1(L * 3);
-    d.s_cinr_pos = take1(L * 3); d.s_cinr_rot = take1(L * 4); d.s_cinr_i = take1(L * 9); d.s_cinr_mass = take1(L);
+    d.s_cinr_pos = take1(L * 3); d.s_cinr_rot = take1(L * 4); d.s_cinr_i = take1(L * 9); d.s_cinr_mass = -1;   // cinr.mass is the model's link mass: never stored per env
     d.s_cd_ang = take1(L * 3); d.s_cd_vel = take1(L * 3);
     d.s_cdof_ang = take1(nvv * 3); d.s_cdof_vel = take1(nvv * 3);
     d.s_cdofd_ang = take1(nvv * 3); d.s_cdofd_vel = take1(nvv * 3);
@@ -450,6 +460,9 @@ inline std::string pack_model_t(const BxgModelDesc& m, PackedModelT<R>* out, int
     o = (o + 3) & ~3;
     int base = o;
     d.s_t_ang = take1(L * 3); d.s_t_vel = take1(L * 3); d.s_f_ang = take1(L * 3); d.s_f_vel = take1(L * 3);
+    // The link velocities xd are written once per launch, by finish_env after the last substep, and read only by
+    // the env epilogue and store_env: they live in the (then dead) t_ang / t_vel temporaries.
+    if (BXG_XD_TAIL) { d.s_xd_ang = d.s_t_ang; d.s_xd_vel = d.s_t_vel; }
     d.s_j_rot = take1(L * 4 > nvv ? L * 4 : nvv);
     d.s_tau = d.s_j_rot;
     int end_tf = o;

@@ -41,8 +41,11 @@ class FusedEnv:
   def __init__(self, sys: base.System, spec: native.EnvSpecC, metric_names, n_frames: int,
                episode_length: Optional[int] = None, auto_reset: bool = False,
                batch_size: Optional[int] = None, device=None, env_id_offset: int = 0, metric_slots=None,
-               action_repeat: int = 1):
+               action_repeat: int = 1, lean: bool = False):
     self.sys = sys
+    # lean: the pipeline state carries q, qd, x, xd and mass_mx_inv only (BXG_STEP_LEAN): the step recomputes the
+    # rest in shared memory, bit-identically; a quarter of the State in HBM, what a trainer's rollout wants
+    self.lean = bool(lean)
     self.spec = spec
     self.metric_names = tuple(metric_names)
     # slot of each metric in the kernel's per-env metrics row (default: in order)
@@ -90,6 +93,8 @@ class FusedEnv:
     seed = int(rng)
     q, qd = self._reset_q_qd(self.env_id_offset, n, seed, self.device)
     bufs, obs = self._model().env_reset(self.spec, q, qd)
+    if self.lean:
+      bufs = {k: v for k, v in bufs.items() if k in native.LEAN_FIELDS}
     zeros = lambda: torch.zeros(n, dtype=torch.float32, device=self.device)
     metrics = {k: zeros() for k in self.metric_names}
     info: Dict[str, Any] = {}
@@ -116,9 +121,9 @@ class FusedEnv:
     }
     first = first_obs = None
     if 'first_pipeline_state' in state.info:
-      first = {k: v.contiguous() for k, v in state.info['first_pipeline_state'].to_flat().items()}
+      first = {k: v.contiguous() for k, v in state.info['first_pipeline_state'].to_flat().items() if v is not None}
       first_obs = state.info['first_obs'].contiguous()
-    bufs = {k: v.contiguous() for k, v in state.pipeline_state.to_flat().items()}
+    bufs = {k: v.contiguous() for k, v in state.pipeline_state.to_flat().items() if v is not None}
     reward_sum = None
     if self.action_repeat > 1:
       # EpisodeWrapper.step (wrappers/training.py:98-112): the inner env steps `action_repeat` times with one action,
@@ -129,12 +134,12 @@ class FusedEnv:
       scratch = {'obs': io['obs'], 'reward': torch.empty_like(io['reward']), 'done': torch.zeros_like(io['done']), 'metrics': io['metrics']}
       reward_sum = torch.zeros_like(io['reward'])
       for _ in range(self.action_repeat - 1):
-        bufs = model.env_step(bare, bufs, action, self._n_frames, scratch)
+        bufs = model.env_step(bare, bufs, action, self._n_frames, scratch, lean=self.lean)
         reward_sum += scratch['reward']
       if io['steps'] is not None:   # the kernel adds 1 after its own reset-on-previous-done: hand it that reset already applied
         io['steps'] = torch.where(io['done'] != 0, torch.zeros_like(io['steps']), io['steps']) + float(self.action_repeat - 1)
         io['done'] = torch.zeros_like(io['done'])
-    out = model.env_step(self.spec, bufs, action, self._n_frames, io, first=first, first_obs=first_obs)
+    out = model.env_step(self.spec, bufs, action, self._n_frames, io, first=first, first_obs=first_obs, lean=self.lean)
     if reward_sum is not None:
       io['reward'] = reward_sum + io['reward']
     metrics = {k: io['metrics'][:, self._metric_slots[k]] for k in self.metric_names}

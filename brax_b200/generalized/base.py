@@ -31,20 +31,22 @@ class State(base.State):
   # ---- flat <-> nested ----------------------------------------------------
   @classmethod
   def from_flat(cls, b: Dict[str, Any], contact=None) -> 'State':
+    # a lean state (BXG_STEP_LEAN, include/bxg.h) carries q, qd, x, xd and mass_mx_inv only: the other leaves are None
+    g = b.get
     return cls(
         q=b['q'], qd=b['qd'],
         x=Transform(pos=b['x_pos'], rot=b['x_rot']),
         xd=Motion(ang=b['xd_ang'], vel=b['xd_vel']),
         contact=contact,
-        root_com=b['root_com'],
-        cinr=Inertia(transform=Transform(pos=b['cinr_pos'], rot=b['cinr_rot']),
-                     i=b['cinr_i'], mass=b['cinr_mass']),
-        cd=Motion(ang=b['cd_ang'], vel=b['cd_vel']),
-        cdof=Motion(ang=b['cdof_ang'], vel=b['cdof_vel']),
-        cdofd=Motion(ang=b['cdofd_ang'], vel=b['cdofd_vel']),
-        mass_mx=b['mass_mx'], mass_mx_inv=b['mass_mx_inv'],
-        con_jac=b['con_jac'], con_diag=b['con_diag'], con_aref=b['con_aref'],
-        qf_smooth=b['qf_smooth'], qf_constraint=b['qf_constraint'], qdd=b['qdd'])
+        root_com=g('root_com'),
+        cinr=Inertia(transform=Transform(pos=g('cinr_pos'), rot=g('cinr_rot')),
+                     i=g('cinr_i'), mass=g('cinr_mass')),
+        cd=Motion(ang=g('cd_ang'), vel=g('cd_vel')),
+        cdof=Motion(ang=g('cdof_ang'), vel=g('cdof_vel')),
+        cdofd=Motion(ang=g('cdofd_ang'), vel=g('cdofd_vel')),
+        mass_mx=g('mass_mx'), mass_mx_inv=b['mass_mx_inv'],
+        con_jac=g('con_jac'), con_diag=g('con_diag'), con_aref=g('con_aref'),
+        qf_smooth=g('qf_smooth'), qf_constraint=g('qf_constraint'), qdd=g('qdd'))
 
   def to_flat(self) -> Dict[str, Any]:
     return {

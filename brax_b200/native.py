@@ -19,6 +19,9 @@ LIB_PATH = os.path.join(_HERE, 'libbxg.so')
 MINV_NEWTON_SCHULZ = 0
 MINV_CHOLESKY = 1
 STEP_DIAGNOSTICS = 1
+STEP_LEAN = 2          # BXG_STEP_LEAN: q, qd, x, mass_mx_inv in; q, qd, x, xd, mass_mx_inv out
+NUM_PHASES = 16
+LEAN_FIELDS = ('q', 'qd', 'x_pos', 'x_rot', 'xd_ang', 'xd_vel', 'mass_mx_inv')
 
 STATE_FIELDS = (
     'q', 'qd', 'x_pos', 'x_rot', 'xd_ang', 'xd_vel', 'root_com',
@@ -62,7 +65,7 @@ class StateC(ctypes.Structure):
 
 
 class DiagC(ctypes.Structure):
-  _fields_ = [('con_dist', ctypes.c_void_p), ('stats', ctypes.c_void_p)]
+  _fields_ = [('con_dist', ctypes.c_void_p), ('stats', ctypes.c_void_p), ('phase_cycles', ctypes.c_void_p)]
 
 
 ENV_ROOT_VELOCITY = 1
@@ -91,7 +94,7 @@ class EnvIOC(ctypes.Structure):
   """Mirror of BxgEnvIO (include/bxg.h)."""
   _fields_ = [('obs', ctypes.c_void_p), ('reward', ctypes.c_void_p), ('done', ctypes.c_void_p),
               ('metrics', ctypes.c_void_p), ('steps', ctypes.c_void_p), ('truncation', ctypes.c_void_p),
-              ('first_state', ctypes.POINTER(StateC)), ('first_obs', ctypes.c_void_p)]
+              ('first_state', ctypes.POINTER(StateC)), ('first_obs', ctypes.c_void_p), ('flags', _i32)]
 
 
 def make_desc(sys, minv_mode: int = MINV_NEWTON_SCHULZ) -> Tuple[ModelDesc, list]:
@@ -114,7 +117,7 @@ def make_desc(sys, minv_mode: int = MINV_NEWTON_SCHULZ) -> Tuple[ModelDesc, list
 
   cp = sys.contact_pairs()
   d = ModelDesc()
-  d.abi_version = 3
+  d.abi_version = 4
   d.num_links, d.nq, d.nv, d.nu = sys.num_links(), sys.nq, sys.nv, sys.nu
   d.ncon = len(cp.geom1)
   d.has_limit = 0 if sys.dof.limit is None else 1
@@ -209,7 +212,7 @@ def lib() -> ctypes.CDLL:
       l.bxg_env_step.argtypes = [ctypes.c_void_p, ctypes.POINTER(EnvSpecC), ctypes.c_int64, ctypes.c_int32,
                                  ctypes.POINTER(StateC), ctypes.c_void_p, ctypes.POINTER(StateC),
                                  ctypes.POINTER(EnvIOC), ctypes.c_void_p]
-      if l.bxg_abi_version() != 3:
+      if l.bxg_abi_version() != 4:
         raise RuntimeError('libbxg.so ABI version mismatch')
       _lib = l
     return _lib
@@ -265,14 +268,14 @@ class NativeModel:
     return dict(zip(('grid', 'threads_per_cta', 'smem_bytes_per_cta', 'envs_per_cta'), list(info)))
 
   # -- buffers ---------------------------------------------------------------
-  def alloc(self, n: int) -> Dict[str, 'torch.Tensor']:
+  def alloc(self, n: int, lean: bool = False) -> Dict[str, 'torch.Tensor']:
     import torch
     dev = torch.device('cuda', self.device)
-    return {k: torch.empty((n,) + s, dtype=torch.float32, device=dev) for k, s in self.shapes.items()}
+    return {k: torch.empty((n,) + s, dtype=torch.float32, device=dev) for k, s in self.shapes.items() if not lean or k in LEAN_FIELDS}
 
-  def _cstate(self, bufs) -> StateC:
+  def _cstate(self, bufs, lean: bool = False) -> StateC:
     cs = StateC()
-    for f in STATE_FIELDS:
+    for f in (LEAN_FIELDS if lean else STATE_FIELDS):
       t = bufs[f]
       assert t.is_cuda and t.is_contiguous() and t.dtype.is_floating_point and t.element_size() == 4, f
       # the model's constants live on self.device and the kernel is launched there: a leaf on another GPU is a bug
@@ -293,7 +296,8 @@ class NativeModel:
     return out
 
   def step(self, bufs: dict, act, n_frames: int = 1, out: Optional[dict] = None,
-           diag: Optional[dict] = None) -> dict:
+           diag: Optional[dict] = None, lean: bool = False) -> dict:
+    """lean: BXG_STEP_LEAN (include/bxg.h): `bufs` / `out` need only native.LEAN_FIELDS."""
     import torch
     n = bufs['q'].shape[0]
     if self.sys.nu:
@@ -302,14 +306,15 @@ class NativeModel:
       act_ptr = act.data_ptr()
     else:
       act_ptr = None
-    out = self.alloc(n) if out is None else out
-    cin, cout = self._cstate(bufs), self._cstate(out)
-    flags, dg = 0, None
+    out = self.alloc(n, lean) if out is None else out
+    cin, cout = self._cstate(bufs, lean), self._cstate(out, lean)
+    flags, dg = (STEP_LEAN if lean else 0), None
     if diag is not None:
-      flags = STEP_DIAGNOSTICS
+      flags |= STEP_DIAGNOSTICS
       dg = DiagC()
       dg.con_dist = diag['con_dist'].data_ptr() if self.ncon else None
       dg.stats = diag['stats'].data_ptr()
+      dg.phase_cycles = diag['phase_cycles'].data_ptr() if 'phase_cycles' in diag else None
     stream = torch.cuda.current_stream(bufs['q'].device).cuda_stream
     _check(lib().bxg_step(self._h, n, int(n_frames), ctypes.byref(cin), act_ptr, ctypes.byref(cout),
                           flags, ctypes.byref(dg) if dg is not None else None, stream), 'bxg_step')
@@ -333,16 +338,17 @@ class NativeModel:
     return out, obs
 
   def env_step(self, spec: EnvSpecC, bufs: dict, action, n_frames: int, io: dict, out: Optional[dict] = None,
-               first: Optional[dict] = None, first_obs=None) -> dict:
+               first: Optional[dict] = None, first_obs=None, lean: bool = False) -> dict:
     """AutoReset(Episode(env)).step over the batch.  `io` holds the per-env arrays
     obs, reward, done, metrics (+ optional steps, truncation), updated in place."""
     import torch
     n = bufs['q'].shape[0]
     action = action.contiguous().float()
     assert action.shape == (n, self.sys.nu), action.shape
-    out = self.alloc(n) if out is None else out
-    cin, cout = self._cstate(bufs), self._cstate(out)
+    out = self.alloc(n, lean) if out is None else out
+    cin, cout = self._cstate(bufs, lean), self._cstate(out, lean)
     eio = EnvIOC()
+    eio.flags = STEP_LEAN if lean else 0
     for k in ('obs', 'reward', 'done', 'metrics'):
       t = io[k]
       assert t.is_cuda and t.is_contiguous() and t.dtype == torch.float32, k
@@ -351,7 +357,7 @@ class NativeModel:
     eio.truncation = io['truncation'].data_ptr() if io.get('truncation') is not None else None
     cfirst = None
     if first is not None:
-      cfirst = self._cstate(first)
+      cfirst = self._cstate(first, lean)
       eio.first_state = ctypes.pointer(cfirst)
       eio.first_obs = first_obs.data_ptr()
     stream = torch.cuda.current_stream(action.device).cuda_stream
@@ -363,7 +369,8 @@ class NativeModel:
     import torch
     dev = torch.device('cuda', self.device)
     return {'con_dist': torch.zeros((n, max(self.ncon, 1)), dtype=torch.float32, device=dev),
-            'stats': torch.zeros((n, 4), dtype=torch.int32, device=dev)}
+            'stats': torch.zeros((n, 4), dtype=torch.int32, device=dev),
+            'phase_cycles': torch.zeros(NUM_PHASES, dtype=torch.int64, device=dev)}
 
 
 def model_for(sys, device: int, minv_mode: int = MINV_NEWTON_SCHULZ) -> NativeModel:

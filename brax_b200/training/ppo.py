@@ -151,8 +151,9 @@ def train(env_name: str = 'ant', num_envs: int = 2048, episode_length: int = 100
   world = dist.get_world_size() if dist.is_initialized() else 1
   rank = dist.get_rank() if dist.is_initialized() else 0
   device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+  # lean pipeline state: the rollout never reads the derived State leaves, the step recomputes them on chip
   env = envs.create(env_name, episode_length=episode_length, auto_reset=True, batch_size=num_envs, device=device,
-                    env_id_offset=rank * num_envs)
+                    env_id_offset=rank * num_envs, lean=True)
   torch.manual_seed(seed + rank)
   agent = Agent(env.observation_size, env.action_size, entropy_cost=entropy_cost, discounting=discounting,
                 reward_scaling=reward_scaling, normalize_advantage=normalize_advantage).to(device)

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BXG_ABI_VERSION 3
+#define BXG_ABI_VERSION 4
 
 enum {
   BXG_OK = 0,
@@ -46,7 +46,13 @@ enum {
 enum {
   BXG_STEP_DEFAULT = 0,
   /* also write the per-contact penetration distance and solver statistics */
-  BXG_STEP_DIAGNOSTICS = 1
+  BXG_STEP_DIAGNOSTICS = 1,
+  /* Lean state I/O.  Of `in` only q, qd, x_pos, x_rot and mass_mx_inv are read: every other leaf is a pure
+   * function of (q, qd) (pipeline.py:51-61,86-93) and is recomputed in shared memory at entry by the code that
+   * would have produced it; of `out` only q, qd, x_pos, x_rot, xd_ang, xd_vel and mass_mx_inv are written (the
+   * other leaves may be NULL).  Those leaves are bit-identical to a default step's: a rollout needs about a
+   * quarter of the State in HBM (Ant 1.4 KB instead of 5.5 KB per env) and half of the DRAM traffic. */
+  BXG_STEP_LEAN = 2
 };
 
 /* How mass_mx_inv is produced inside step (reference mass.py:86-106).
@@ -165,7 +171,10 @@ typedef struct BxgDiag {
   float* con_dist;      /* [n, ncon]  contact.dist after the last substep   */
   int32_t* stats;       /* [n, 4]  accumulated: pg iterations, line-search
                            evaluations, Newton-Schulz accepts, cold starts  */
+  unsigned long long* phase_cycles;  /* [BXG_NUM_PHASES] per-warp cycles summed per phase of the step; written
+                           only by tuning builds (-DBXG_PHASE_TIMERS, tools/build_alt.py); may be NULL */
 } BxgDiag;
+#define BXG_NUM_PHASES 16
 
 /* ---- environment step ---------------------------------
  * The env arithmetic the reference does around pipeline_step, fused after the
@@ -238,6 +247,7 @@ typedef struct BxgEnvIO {
   float* truncation;          /* [n] out     info['truncation']; may be NULL */
   const BxgState* first_state; /* AutoResetWrapper source; NULL disables auto-reset */
   const float* first_obs;      /* [n, obs_size] */
+  int32_t flags;               /* BXG_STEP_LEAN or 0 */
 } BxgEnvIO;
 
 typedef struct BxgModel BxgModel;

@@ -102,26 +102,35 @@ int run(const BxgModelDesc* desc, int vid, int mode, bool init, int64_t n_env, i
   for (int64_t e = 0; e < n_env; ++e) {
     // poison the slab so stale-data bugs show up as NaN
     for (int i = 0; i < pm.d.env_words; ++i) slab_base[i] = NAN;
-    bxg::Stats st{0, 0, 0, 0};
+    bxg::Stats st{};
     bxg::prepare_env(ex, c);
     if (init) {
       bxg::load_env_qqd(ex, c, q, qd, e);
       bxg::init_env<HostExec<G>, Cfg>(ex, c, &st);
+      bxg::finish_env(ex, c);
       if constexpr (!kF64) { if (env) bxg::env_reset_obs(ex, c, *env, eio->obs + e * bxg::env_obs_size(pm.d, *env)); }
       bxg::store_env(ex, c, *out, e, nullptr, st);
     } else {
-      bxg::load_env(ex, c, *in, act, e);
+      const bool lean = (flags & BXG_STEP_LEAN) || (eio && (eio->flags & BXG_STEP_LEAN));
+      if (lean) { bxg::load_env_lean(ex, c, *in, act, e); bxg::lean_entry<HostExec<G>, Cfg>(ex, c); }
+      else bxg::load_env(ex, c, *in, act, e);
       if constexpr (!kF64) { if (env) bxg::env_prologue(ex, c, *env, *in, e); }
       for (int f = 0; f < n_frames; ++f) {
         if (pm.d.minv_mode == BXG_MINV_CHOLESKY) bxg::substep<HostExec<G>, Cfg, 1>(ex, c, &st);
         else bxg::substep<HostExec<G>, Cfg, 0>(ex, c, &st);
       }
       bool done = false;
+      bxg::finish_env(ex, c);
       if constexpr (!kF64) {
         if (env) bxg::env_epilogue(ex, c, *env, *eio, e, true, &done);
-        if (done && eio && eio->first_state) { bxg::store_first_state(ex, c, *out, *reinterpret_cast<const SimState*>(eio->first_state), e); continue; }
+        if (done && eio && eio->first_state) {
+          if (lean) bxg::store_first_state_lean(ex, c, *out, *reinterpret_cast<const SimState*>(eio->first_state), e);
+          else bxg::store_first_state(ex, c, *out, *reinterpret_cast<const SimState*>(eio->first_state), e);
+          continue;
+        }
       }
-      bxg::store_env(ex, c, *out, e, (flags & BXG_STEP_DIAGNOSTICS) ? diag : nullptr, st);
+      if (lean) bxg::store_env_lean(ex, c, *out, e, (flags & BXG_STEP_DIAGNOSTICS) ? diag : nullptr, st);
+      else bxg::store_env(ex, c, *out, e, (flags & BXG_STEP_DIAGNOSTICS) ? diag : nullptr, st);
     }
   }
   return 0;

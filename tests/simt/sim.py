@@ -67,18 +67,24 @@ class Sim:
     assert rc == 0, rc
     return out
 
-  def step(self, st, act, n_frames=1, diag=False):
+  def step(self, st, act, n_frames=1, diag=False, lean=False):
     n = st['q'].shape[0]
     act = np.ascontiguousarray(np.atleast_2d(act), self.dtype)
-    st = {k: np.ascontiguousarray(st[k], self.dtype) for k in native.STATE_FIELDS}
+    if lean:   # the other leaves are neither read nor written: poison them so that a stray read shows
+      st = {k: (np.ascontiguousarray(st[k], self.dtype) if k in native.LEAN_FIELDS else np.full((n,) + self.shapes[k], np.nan, self.dtype)) for k in native.STATE_FIELDS}
+    else:
+      st = {k: np.ascontiguousarray(st[k], self.dtype) for k in native.STATE_FIELDS}
     out = self.alloc(n)
+    if lean:
+      for k in out:
+        out[k][...] = np.nan
     cin, cout = self._cstate(st, self.dtype), self._cstate(out, self.dtype)
     dg = native.DiagC()
     con_dist = np.zeros((n, max(self.ncon, 1)), np.float32); stats = np.zeros((n, 4), np.int32)
     dg.con_dist = con_dist.ctypes.data; dg.stats = stats.ctypes.data
     rc = self.lib.sim_step(ctypes.byref(self.desc), self.G, self.reverse, ctypes.c_int64(n), int(n_frames),
                            ctypes.byref(cin), act.ctypes.data_as(ctypes.c_void_p), ctypes.byref(cout),
-                           1 if diag else 0, ctypes.byref(dg))
+                           (1 if diag else 0) | (native.STEP_LEAN if lean else 0), ctypes.byref(dg))
     assert rc == 0, rc
     if diag:
       out['con_dist'] = con_dist; out['stats'] = stats

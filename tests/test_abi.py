@@ -31,7 +31,7 @@ def test_loads_and_fails_loudly_without_cuda(ant):
   _build()
   from brax_b200 import native
   lib = native.lib()
-  assert lib.bxg_abi_version() == 3
+  assert lib.bxg_abi_version() == 4
   import torch
   if torch.cuda.is_available():
     pytest.skip('CUDA present: the no-device error path is exercised on CPU boxes')

@@ -125,3 +125,45 @@ def test_fused_env_step_equals_host_emulation_bit_for_bit(name):
     _assert_same_bits(st.pipeline_state.q.cpu().numpy(), hs['q'], f'{name} step {k} q')
     _assert_same_bits(st.pipeline_state.mass_mx_inv.cpu().numpy(), hs['mass_mx_inv'], f'{name} step {k} mass_mx_inv')
   assert saw_done
+
+
+@pytest.mark.parametrize('name', ['ant', 'humanoid', 'hopper', 'swimmer', 'pusher'])
+def test_lean_state_io_gives_the_same_bits(name):
+  """BXG_STEP_LEAN (include/bxg.h): only q, qd, x and mass_mx_inv are read, the derived leaves are recomputed on
+  chip; q, qd, x, xd, mass_mx_inv come out bit-identical to the default step, the other leaves are never touched."""
+  import torch
+  from brax_b200 import native
+  n = 70
+  s, q, qd, acts, nf = _inputs(name, n, seed=9)
+  dev = torch.device('cuda', 0)
+  nm = native.NativeModel(s, 0)
+  full = nm.init(torch.as_tensor(q, device=dev), torch.as_tensor(qd, device=dev))
+  lean = {k: full[k].clone() for k in native.LEAN_FIELDS}
+  for act in acts:
+    a = torch.as_tensor(act, device=dev)
+    full = nm.step(full, a, nf)
+    poisoned = {k: torch.full_like(v, float('nan')) for k, v in nm.alloc(n).items() if k not in native.LEAN_FIELDS}
+    out = dict(poisoned, **nm.alloc(n, lean=True))
+    nm.step(dict(poisoned, **lean), a, nf, out=out, lean=True)      # derived input leaves are garbage: never read
+    for k in native.LEAN_FIELDS:
+      assert torch.equal(out[k], full[k]), (name, k)
+    assert all(torch.isnan(out[k]).all() for k in poisoned)           # and never written
+    lean = {k: out[k] for k in native.LEAN_FIELDS}
+
+
+@pytest.mark.parametrize('name', ['ant', 'humanoid'])
+def test_lean_fused_env_gives_the_same_bits(name):
+  import torch
+  from brax_b200 import envs
+  n = 96
+  e_full = envs.create(name, episode_length=4, auto_reset=True, batch_size=n)
+  e_lean = envs.create(name, episode_length=4, auto_reset=True, batch_size=n, lean=True)
+  a, b = e_full.reset(2), e_lean.reset(2)
+  assert b.pipeline_state.cdof.ang is None and torch.equal(a.obs, b.obs)
+  gen = torch.Generator(device='cpu').manual_seed(0)
+  for k in range(7):
+    act = (torch.rand((n, e_full.action_size), generator=gen) * 2 - 1).to(a.obs.device)
+    a, b = e_full.step(a, act), e_lean.step(b, act)
+    for x, y in ((a.obs, b.obs), (a.reward, b.reward), (a.done, b.done), (a.pipeline_state.q, b.pipeline_state.q),
+                 (a.pipeline_state.x.rot, b.pipeline_state.x.rot), (a.info['steps'], b.info['steps'])):
+      assert torch.equal(x, y), (name, k)
