@@ -191,6 +191,7 @@ def main():
   ap.add_argument('--minv', default='newton_schulz', choices=['newton_schulz', 'cholesky'])
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-extra', action='store_true', help='skip the secondary workload lines')
+  ap.add_argument('--lean', action='store_true', help='BXG_STEP_LEAN state I/O (q, qd, x, xd, mass_mx_inv only) for the main workload')
   ap.add_argument('--no-ppo', action='store_true', help='skip the end-to-end PPO line (config 5)')
   ap.add_argument('--ppo-timesteps', type=int, default=6_000_000, help='env-steps per GPU of the PPO line')
   args = ap.parse_args()
@@ -232,7 +233,7 @@ def main():
   hbm_peak, peak_src = peaks()
   flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-  def measure(workload, steps, warmup, with_clocks, minv=minv):
+  def measure(workload, steps, warmup, with_clocks, minv=minv, lean=False):
     model, n_env = WORKLOADS[workload]
     if args.envs and workload == args.workload:
       n_env = args.envs
@@ -240,12 +241,14 @@ def main():
     begin = rank * n_env  # weak scaling: every rank has n_env envs; ids are global
     sys_, q, qd = workloads.reset(model, begin, n_env, 0, dev)
     nm = native.model_for(sys_, local_rank, minv)
-    a, b = nm.init(q, qd), nm.alloc(n_env)
+    a, b = nm.init(q, qd), nm.alloc(n_env, lean)
+    if lean:   # the derived State leaves are neither read nor written in this mode: drop them
+      a = {k: a[k] for k in native.LEAN_FIELDS}
     acts = [workloads.action(model, begin, n_env, 0, k, dev) for k in range(min(steps + warmup, 8))]
     state_bytes = sum(t.numel() * 4 for t in a.values())
     flush = state_bytes < (512 << 20)
     for w in range(warmup):
-      nm.step(a, acts[w % len(acts)], nf, out=b); a, b = b, a
+      nm.step(a, acts[w % len(acts)], nf, out=b, lean=lean); a, b = b, a
     sampler = ClockSampler(local_rank) if with_clocks else None
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     barrier()
@@ -257,7 +260,7 @@ def main():
       if flush:
         flush_buf.fill_(k & 0xff)
       ev[k][0].record()
-      nm.step(a, acts[(warmup + k) % len(acts)], nf, out=b)
+      nm.step(a, acts[(warmup + k) % len(acts)], nf, out=b, lean=lean)
       ev[k][1].record()
       a, b = b, a
     barrier()
@@ -279,7 +282,7 @@ def main():
         'model': model, 'n_env': n_env, 'nf': nf, 'value': total_envs / (kern_avg_ms * 1e-3),
         'ms_per_step': kern_avg_ms, 'kern_avg_ms': kern_avg_ms, 'wall_ms_per_step': 1e3 * wall / steps,
         'ms_per_step_incl_flush': dev_ms_total / steps,
-        'launches': launches, 'clocks': clocks, 'flush': flush, 'nm': nm, 'minv': minv, 'state': a, 'spare': b, 'acts': acts, 'nonfinite': nonfinite,
+        'launches': launches, 'clocks': clocks, 'flush': flush, 'nm': nm, 'minv': minv, 'lean': lean, 'state_bytes': state_bytes, 'state': a, 'spare': b, 'acts': acts, 'nonfinite': nonfinite,
         'begin': begin,
     }
 
@@ -298,7 +301,7 @@ def main():
     e0.record()
     for k in range(steps):
       d_act.copy_(h_act[k % len(h_act)], non_blocking=True)
-      nm.step(a, d_act, nf, out=b)
+      nm.step(a, d_act, nf, out=b, lean=r['lean'])
       a, b = b, a
       h_q.copy_(a['q'], non_blocking=True); h_qd.copy_(a['qd'], non_blocking=True)
       torch.cuda.current_stream().synchronize()  # the caller consumes the result every step
@@ -329,6 +332,7 @@ def main():
 
   def summarize(workload, r, e2e):
     model = r['model']
+    tkey = workload + ('_lean' if r['lean'] else '')
     achieved = workloads.ALGO_BYTES[model] * r['n_env'] / (r['kern_avg_ms'] * 1e-3) / 1e9     # per launch = per rank per step
     fl = flops_per_env_step(r['nm'].sys, r['nf'])
     tf = fl * r['n_env'] / (r['kern_avg_ms'] * 1e-3) / 1e12
@@ -340,7 +344,7 @@ def main():
                    'threads_per_cta': shape['threads_per_cta'], 'envs_per_cta': shape['envs_per_cta'],
                    'smem_bytes_per_cta': shape['smem_bytes_per_cta'], 'envs_per_cta_max': plan['envs_per_cta']},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
-                     'traffic': static_traffic(workload, r['n_env']),
+                     'traffic': static_traffic(tkey, r['n_env']),
                      'traffic_source': 'static: ncu dram__bytes of the committed capture (profiles/traffic.json), not measured in this run',
                      'peak_source': peak_src, 'algorithmic_bytes_per_env_step': workloads.ALGO_BYTES[model],
                      'note': 'the step is bound on-chip (shared-memory operand delivery and FMA issue of the Newton-Schulz products, '
@@ -350,9 +354,11 @@ def main():
                          'the dense work is fp32 by the parity requirement'},
         'l2': 'flushed between steps (256 MiB write, outside the per-step event intervals)' if r['flush'] else 'state >> L2, no flush',
         'nonfinite_envs': r['nonfinite'],
+        'state_io': 'lean (q, qd, x, xd, mass_mx_inv; BXG_STEP_LEAN)' if r['lean'] else 'full generalized.State (25 leaves, drop-in)',
+        'state_bytes_per_env': r['state_bytes'] // r['n_env'],
     }
 
-  r = measure(args.workload, args.steps, args.warmup, with_clocks=True)
+  r = measure(args.workload, args.steps, args.warmup, with_clocks=True, lean=args.lean)
   e2e = measure_e2e(r, args.steps)
   model = r['model']
   sm = summarize(args.workload, r, e2e)
@@ -362,7 +368,7 @@ def main():
       'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
       'config': {'workload': args.workload, 'model': model, 'envs_per_gpu': r['n_env'], 'n_frames': r['nf'],
                  'minv': args.minv, 'parallelism': f'env-shard x{world}, no collective',
-                 'launch': sm['launch'], 'l2': sm['l2']},
+                 'launch': sm['launch'], 'l2': sm['l2'], 'state_io': sm['state_io']},
       'roofline': sm['roofline'], 'fp32': sm['fp32'],
       'e2e': e2e, 'gpu_launches': r['launches'], 'clocks': r['clocks'],
       'kernel_ms': r['kern_avg_ms'], 'wall_ms_per_step': r['wall_ms_per_step'],
@@ -376,12 +382,13 @@ def main():
     # Newton-Schulz numerics); then config 5 (end-to-end PPO on Ant).
     extra = []
     del r['state'], r['spare'], r['nm'], r['acts']
-    for wl, st_, mv in (('ant_1m', 5, minv), ('humanoid_512k', 5, minv), (args.workload, 10, native.MINV_CHOLESKY)):
-      if wl == args.workload and mv == minv:
+    for wl, st_, mv, ln in (('ant_1m', 5, minv, False), ('humanoid_512k', 5, minv, False), ('ant_1m', 5, minv, True),
+                            (args.workload, 10, minv, True), (args.workload, 10, native.MINV_CHOLESKY, False)):
+      if wl == args.workload and mv == minv and ln == args.lean:
         continue
       try:
         torch.cuda.empty_cache()
-        x = measure(wl, st_, 3, with_clocks=False, minv=mv)
+        x = measure(wl, st_, 3, with_clocks=False, minv=mv, lean=ln)
         xe = measure_e2e(x, st_)
         ent = {'workload': wl, 'model': x['model'], 'envs_per_gpu': x['n_env'], 'n_gpus': world, 'steps': st_,
                'minv': 'cholesky' if mv == native.MINV_CHOLESKY else 'newton_schulz'}

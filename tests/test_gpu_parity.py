@@ -1,7 +1,14 @@
 """Parity of the CUDA path (through the C ABI, via brax_b200.generalized.pipeline)
-against the oracle on the same seeded inputs.  Tolerances are the ones
+against the float32 ORACLE on the same seeded inputs.  Tolerances are the ones
 BASELINE.json `north_star` states: 1e-4 relative / 1e-5 absolute for q, qd, x, xd
-(fp32), contact active set exact except within 1e-6 of the threshold."""
+(fp32), contact active set exact except within 1e-6 of the threshold.
+
+These are float32-vs-float32 comparisons of two different evaluation orders of an algorithm that
+amplifies rounding, so they are statistical by nature; the gates sit at the
+measured values (gpurun_out/parity_report.json).  The EXACT checks live elsewhere: the kernel source
+in double precision equals the reference-source goldens on every leaf (tests/test_kernel_logic_f64.py),
+and the CUDA path equals the float32 host emulation of that source bit for bit
+(tests/test_gpu_bitexact.py)."""
 import json
 import os
 
@@ -114,8 +121,8 @@ def test_single_substep_map_is_within_stated_tolerance(model):
                                       'median_scaled_err': float(np.median(errs)), 'p99_scaled_err': float(np.percentile(errs, 99)),
                                       'solver_branch_flips': flips, 'contact_mask_mismatch_beyond_1e-6': mask_mismatch})
   assert mask_mismatch == 0, f'contact active set differs beyond the 1e-6 band: {mask_mismatch}'
-  assert frac_ok >= 0.95, frac_ok
-  assert np.median(errs) <= 0.05
+  assert frac_ok >= 0.97, frac_ok          # measured 0.976 (Ant) / 0.978 (Humanoid)
+  assert np.median(errs) <= 0.02           # measured 0.009 / 0.008
 
 
 @pytest.mark.parametrize('model', ['ant', 'humanoid'])
@@ -159,7 +166,7 @@ def test_one_env_step_map_vs_fp32_noise_floor(model):
       'contact_mask_mismatch_on_in_tolerance_envs': mask_mismatch})
   assert mask_mismatch == 0
   assert pg[0] <= 0.2, pg                       # median env is far inside the tolerance
-  assert (e_gpu <= 1).mean() >= 0.8, (e_gpu <= 1).mean()
+  assert (e_gpu <= 1).mean() >= {'ant': 0.85, 'humanoid': 0.92}[model], (e_gpu <= 1).mean()   # measured 0.871 / 0.944
   assert (e_gpu <= 1).mean() >= (e_floor <= 1).mean() - 0.05
   for a, b in zip(pg, pf):
     assert a <= 4.0 * b + 0.05, (pg, pf)          # not worse than fp32's own noise floor
@@ -458,4 +465,4 @@ def test_cuda_path_against_reference_source_golden(name):
       np.testing.assert_allclose(out[f], r, rtol=2e-3, atol=2e-4 * max(1.0, float(np.abs(r).max()) if r.size else 1.0), err_msg=f'{name} step {k} {f}')
   frac = float(np.mean(inside))
   _report(f'reference_golden_{name}', {'envs_x_steps': int(n * steps), 'frac_inside_1e-4_1e-5': frac})
-  assert frac >= 0.75, (name, frac)
+  assert frac >= 0.9, (name, frac)          # measured 1.0 everywhere except Humanoid 11 / 12
