@@ -9,6 +9,8 @@
 #include <string>
 
 #include "bxg_model.h"
+#include "gen/bxg_dims_ant.h"
+#include "gen/bxg_dims_humanoid.h"
 
 namespace bxg {
 constexpr size_t kSmemBudget = 227 * 1024;  // usable shared memory per SM on sm_100
@@ -27,16 +29,16 @@ inline int envs_per_cta(const Dims& d, const Variant& var) {
 }
 
 extern "C" {
-const void* bxg_step_kernel_v0(); const void* bxg_step_kernel_v1(); const void* bxg_step_kernel_v2(); const void* bxg_step_kernel_v3(); const void* bxg_step_kernel_v4(); const void* bxg_step_kernel_v5(); const void* bxg_step_kernel_v6(); const void* bxg_step_kernel_v7(); const void* bxg_step_kernel_v8(); const void* bxg_step_kernel_v9();
-const void* bxg_init_kernel_v0(); const void* bxg_init_kernel_v1(); const void* bxg_init_kernel_v2(); const void* bxg_init_kernel_v3(); const void* bxg_init_kernel_v4(); const void* bxg_init_kernel_v5(); const void* bxg_init_kernel_v6(); const void* bxg_init_kernel_v7(); const void* bxg_init_kernel_v8(); const void* bxg_init_kernel_v9();
+const void* bxg_step_kernel_v0(); const void* bxg_step_kernel_v1(); const void* bxg_step_kernel_v2(); const void* bxg_step_kernel_v3(); const void* bxg_step_kernel_v4(); const void* bxg_step_kernel_v5(); const void* bxg_step_kernel_v6(); const void* bxg_step_kernel_v7(); const void* bxg_step_kernel_v8(); const void* bxg_step_kernel_v9(); const void* bxg_step_kernel_v10(); const void* bxg_step_kernel_v11();
+const void* bxg_init_kernel_v0(); const void* bxg_init_kernel_v1(); const void* bxg_init_kernel_v2(); const void* bxg_init_kernel_v3(); const void* bxg_init_kernel_v4(); const void* bxg_init_kernel_v5(); const void* bxg_init_kernel_v6(); const void* bxg_init_kernel_v7(); const void* bxg_init_kernel_v8(); const void* bxg_init_kernel_v9(); const void* bxg_init_kernel_v10(); const void* bxg_init_kernel_v11();
 }
 extern "C" {
 const void* bxg_step_chol_kernel_v0(); const void* bxg_step_chol_kernel_v1(); const void* bxg_step_chol_kernel_v2();
-const void* bxg_step_chol_kernel_v3(); const void* bxg_step_chol_kernel_v4(); const void* bxg_step_chol_kernel_v5(); const void* bxg_step_chol_kernel_v6(); const void* bxg_step_chol_kernel_v7(); const void* bxg_step_chol_kernel_v8(); const void* bxg_step_chol_kernel_v9();
+const void* bxg_step_chol_kernel_v3(); const void* bxg_step_chol_kernel_v4(); const void* bxg_step_chol_kernel_v5(); const void* bxg_step_chol_kernel_v6(); const void* bxg_step_chol_kernel_v7(); const void* bxg_step_chol_kernel_v8(); const void* bxg_step_chol_kernel_v9(); const void* bxg_step_chol_kernel_v10(); const void* bxg_step_chol_kernel_v11();
 }
 extern "C" {
-const void* bxg_step_lean_kernel_v0(); const void* bxg_step_lean_kernel_v1(); const void* bxg_step_lean_kernel_v2(); const void* bxg_step_lean_kernel_v3(); const void* bxg_step_lean_kernel_v4(); const void* bxg_step_lean_kernel_v5(); const void* bxg_step_lean_kernel_v6(); const void* bxg_step_lean_kernel_v7(); const void* bxg_step_lean_kernel_v8(); const void* bxg_step_lean_kernel_v9();
-const void* bxg_step_chol_lean_kernel_v0(); const void* bxg_step_chol_lean_kernel_v1(); const void* bxg_step_chol_lean_kernel_v2(); const void* bxg_step_chol_lean_kernel_v3(); const void* bxg_step_chol_lean_kernel_v4(); const void* bxg_step_chol_lean_kernel_v5(); const void* bxg_step_chol_lean_kernel_v6(); const void* bxg_step_chol_lean_kernel_v7(); const void* bxg_step_chol_lean_kernel_v8(); const void* bxg_step_chol_lean_kernel_v9();
+const void* bxg_step_lean_kernel_v0(); const void* bxg_step_lean_kernel_v1(); const void* bxg_step_lean_kernel_v2(); const void* bxg_step_lean_kernel_v3(); const void* bxg_step_lean_kernel_v4(); const void* bxg_step_lean_kernel_v5(); const void* bxg_step_lean_kernel_v6(); const void* bxg_step_lean_kernel_v7(); const void* bxg_step_lean_kernel_v8(); const void* bxg_step_lean_kernel_v9(); const void* bxg_step_lean_kernel_v10(); const void* bxg_step_lean_kernel_v11();
+const void* bxg_step_chol_lean_kernel_v0(); const void* bxg_step_chol_lean_kernel_v1(); const void* bxg_step_chol_lean_kernel_v2(); const void* bxg_step_chol_lean_kernel_v3(); const void* bxg_step_chol_lean_kernel_v4(); const void* bxg_step_chol_lean_kernel_v5(); const void* bxg_step_chol_lean_kernel_v6(); const void* bxg_step_chol_lean_kernel_v7(); const void* bxg_step_chol_lean_kernel_v8(); const void* bxg_step_chol_lean_kernel_v9(); const void* bxg_step_chol_lean_kernel_v10(); const void* bxg_step_chol_lean_kernel_v11();
 }
 static const void* step_lean_kernel_of(int v, bool chol) {
   switch (v) {
@@ -49,22 +51,25 @@ static const void* step_lean_kernel_of(int v, bool chol) {
     case 7: return chol ? bxg_step_chol_lean_kernel_v7() : bxg_step_lean_kernel_v7();
     case 8: return chol ? bxg_step_chol_lean_kernel_v8() : bxg_step_lean_kernel_v8();
     case 9: return chol ? bxg_step_chol_lean_kernel_v9() : bxg_step_lean_kernel_v9();
+    case 10: return chol ? bxg_step_chol_lean_kernel_v10() : bxg_step_lean_kernel_v10();
+    case 11: return chol ? bxg_step_chol_lean_kernel_v11() : bxg_step_lean_kernel_v11();
     default: return chol ? bxg_step_chol_lean_kernel_v3() : bxg_step_lean_kernel_v3();
   }
 }
 static const void* step_chol_kernel_of(int v) {
   switch (v) { case 0: return bxg_step_chol_kernel_v0(); case 1: return bxg_step_chol_kernel_v1(); case 2: return bxg_step_chol_kernel_v2();
-               case 4: return bxg_step_chol_kernel_v4(); case 5: return bxg_step_chol_kernel_v5(); case 6: return bxg_step_chol_kernel_v6(); case 7: return bxg_step_chol_kernel_v7(); case 8: return bxg_step_chol_kernel_v8(); case 9: return bxg_step_chol_kernel_v9(); default: return bxg_step_chol_kernel_v3(); }
+               case 4: return bxg_step_chol_kernel_v4(); case 5: return bxg_step_chol_kernel_v5(); case 6: return bxg_step_chol_kernel_v6(); case 7: return bxg_step_chol_kernel_v7(); case 8: return bxg_step_chol_kernel_v8(); case 9: return bxg_step_chol_kernel_v9(); case 10: return bxg_step_chol_kernel_v10(); case 11: return bxg_step_chol_kernel_v11(); default: return bxg_step_chol_kernel_v3(); }
 }
 static const void* step_kernel_of(int v) {
-  switch (v) { case 0: return bxg_step_kernel_v0(); case 1: return bxg_step_kernel_v1(); case 2: return bxg_step_kernel_v2(); case 4: return bxg_step_kernel_v4(); case 5: return bxg_step_kernel_v5(); case 6: return bxg_step_kernel_v6(); case 7: return bxg_step_kernel_v7(); case 8: return bxg_step_kernel_v8(); case 9: return bxg_step_kernel_v9(); default: return bxg_step_kernel_v3(); }
+  switch (v) { case 0: return bxg_step_kernel_v0(); case 1: return bxg_step_kernel_v1(); case 2: return bxg_step_kernel_v2(); case 4: return bxg_step_kernel_v4(); case 5: return bxg_step_kernel_v5(); case 6: return bxg_step_kernel_v6(); case 7: return bxg_step_kernel_v7(); case 8: return bxg_step_kernel_v8(); case 9: return bxg_step_kernel_v9(); case 10: return bxg_step_kernel_v10(); case 11: return bxg_step_kernel_v11(); default: return bxg_step_kernel_v3(); }
 }
 static const void* init_kernel_of(int v) {
-  switch (v) { case 0: return bxg_init_kernel_v0(); case 1: return bxg_init_kernel_v1(); case 2: return bxg_init_kernel_v2(); case 4: return bxg_init_kernel_v4(); case 5: return bxg_init_kernel_v5(); case 6: return bxg_init_kernel_v6(); case 7: return bxg_init_kernel_v7(); case 8: return bxg_init_kernel_v8(); case 9: return bxg_init_kernel_v9(); default: return bxg_init_kernel_v3(); }
+  switch (v) { case 0: return bxg_init_kernel_v0(); case 1: return bxg_init_kernel_v1(); case 2: return bxg_init_kernel_v2(); case 4: return bxg_init_kernel_v4(); case 5: return bxg_init_kernel_v5(); case 6: return bxg_init_kernel_v6(); case 7: return bxg_init_kernel_v7(); case 8: return bxg_init_kernel_v8(); case 9: return bxg_init_kernel_v9(); case 10: return bxg_init_kernel_v10(); case 11: return bxg_init_kernel_v11(); default: return bxg_init_kernel_v3(); }
 }
 
 struct BxgModel {
   bxg::PackedModel pm;
+  int kernel_id = 0;       // pm.variant_id, or 10 / 11: that variant compiled for exactly this model's packed layout
   int device = 0;
   int lanes = 32;          // G
   int sm_count = 0;
@@ -101,6 +106,16 @@ struct DeviceGuard {
 bool state_ok_lean(const BxgState* s) {
   return s && s->q && s->qd && s->x_pos && s->x_rot && s->xd_ang && s->xd_vel && s->mass_mx_inv;
 }
+// Kernel id for a packed model: its variant, or the model-specialised build of that variant (constexpr Dims:
+// kernel ids 10 = Ant layout on variant 0, 11 = Humanoid layout on variant 1) when the packed layout, sizes and
+// solver settings are IDENTICAL to the ones that build was compiled for.  Any other model keeps the generic kernel.
+int specialised_kernel_id(const bxg::PackedModel& pm) {
+  if (getenv("BXG_NO_SPECIALISE")) return pm.variant_id;
+  auto same = [&](bxg::Dims c) { c.minv_mode = pm.d.minv_mode; return memcmp(&c, &pm.d, sizeof c) == 0; };
+  if (pm.variant_id == 0 && same(bxg::const_dims_ant())) return 10;
+  if (pm.variant_id == 1 && same(bxg::const_dims_humanoid())) return 11;
+  return pm.variant_id;
+}
 bool state_ok(const BxgState* s, int nc) {
   if (!s) return false;
   const float* const* p = reinterpret_cast<const float* const*>(s);
@@ -127,6 +142,8 @@ int bxg_model_create(const BxgModelDesc* desc, int device, BxgModel** out) {
   if (const char* fv = getenv("BXG_FORCE_VARIANT")) force_variant = atoi(fv);   // tuning knob (e.g. 4: Humanoid class on half-warps)
   std::string err = bxg::pack_model(*desc, &m->pm, force_variant);
   if (!err.empty()) { delete m; return fail(BXG_E_UNSUPPORTED, err); }
+  m->kernel_id = force_variant >= 0 ? m->pm.variant_id : specialised_kernel_id(m->pm);   // (before the tuning knobs below change Dims)
+  if (getenv("BXG_SYNC_LEVEL") || getenv("BXG_PHASE_GROUPS")) m->kernel_id = m->pm.variant_id;
   if (const char* sl = getenv("BXG_SYNC_LEVEL")) m->pm.d.sync_level = atoi(sl);   // tuning knobs
   if (const char* pg = getenv("BXG_PHASE_GROUPS")) m->pm.d.phase_groups = atoi(pg);
   int ndev = 0;
@@ -155,9 +172,9 @@ int bxg_model_create(const BxgModelDesc* desc, int device, BxgModel** out) {
     return cleanup(cuda_fail(ce, "cudaMemcpy(model)"));
   // the attribute is per function (shared by every model of this variant): always
   // raise it to the device maximum, never to this model's own size
-  const void* ks = m->pm.d.minv_mode == BXG_MINV_CHOLESKY ? step_chol_kernel_of(m->pm.variant_id) : step_kernel_of(m->pm.variant_id);
-  const void* ki = init_kernel_of(m->pm.variant_id);
-  const void* kl = step_lean_kernel_of(m->pm.variant_id, m->pm.d.minv_mode == BXG_MINV_CHOLESKY);
+  const void* ks = m->pm.d.minv_mode == BXG_MINV_CHOLESKY ? step_chol_kernel_of(m->kernel_id) : step_kernel_of(m->kernel_id);
+  const void* ki = init_kernel_of(m->kernel_id);
+  const void* kl = step_lean_kernel_of(m->kernel_id, m->pm.d.minv_mode == BXG_MINV_CHOLESKY);
   // (dynamic + the kernel's few bytes of static shared memory must fit the opt-in limit)
   for (const void* k : {ks, ki, kl}) {
     cudaFuncAttributes fa;
@@ -196,7 +213,7 @@ int bxg_plan(const BxgModelDesc* desc, int32_t info[8]) {
   const int G = bxg::variant(pm.variant_id).G, groups = bxg::envs_per_cta(pm.d, bxg::variant(pm.variant_id));
   info[0] = pm.variant_id; info[1] = G; info[2] = pm.d.model_words; info[3] = pm.d.env_words; info[4] = groups;
   info[5] = (int32_t)(sizeof(uint32_t) * ((size_t)pm.d.model_words + (size_t)groups * pm.d.env_words));
-  info[6] = pm.d.nc; info[7] = 0;
+  info[6] = pm.d.nc; info[7] = specialised_kernel_id(pm);
   return BXG_OK;
 }
 
@@ -241,7 +258,7 @@ int bxg_init(const BxgModel* m, int64_t n_env, const float* q, const float* qd, 
   LaunchShape ls = launch_shape(m, n_env);
   BxgEnvSpec env{}; float* obs = nullptr;
   void* args[] = {(void*)&m->pm.d, (void*)&m->d_blob, (void*)&q, (void*)&qd, (void*)out, (void*)&n_env, (void*)&env, (void*)&obs};
-  BXG_CUDA(cudaLaunchKernel(init_kernel_of(m->pm.variant_id), dim3(ls.grid), dim3(ls.threads), args, ls.smem, st));
+  BXG_CUDA(cudaLaunchKernel(init_kernel_of(m->kernel_id), dim3(ls.grid), dim3(ls.threads), args, ls.smem, st));
   g_launches.fetch_add(1);
   BXG_CUDA(cudaGetLastError());
   return BXG_OK;
@@ -265,7 +282,7 @@ int bxg_step(const BxgModel* m, int64_t n_env, int32_t n_frames, const BxgState*
   void* args[] = {(void*)&m->pm.d, (void*)&m->d_blob, (void*)in, (void*)&act, (void*)out, (void*)&n_env, (void*)&nf, (void*)&fl, (void*)&dg,
                   (void*)&env, (void*)&eio, (void*)&first};
   const bool chol = m->pm.d.minv_mode == BXG_MINV_CHOLESKY;
-  const void* kern = lean ? step_lean_kernel_of(m->pm.variant_id, chol) : (chol ? step_chol_kernel_of(m->pm.variant_id) : step_kernel_of(m->pm.variant_id));
+  const void* kern = lean ? step_lean_kernel_of(m->kernel_id, chol) : (chol ? step_chol_kernel_of(m->kernel_id) : step_kernel_of(m->kernel_id));
   BXG_CUDA(cudaLaunchKernel(kern, dim3(ls.grid), dim3(ls.threads), args, ls.smem, st));
   g_launches.fetch_add(1);
   BXG_CUDA(cudaGetLastError());
@@ -300,7 +317,7 @@ int bxg_env_reset(const BxgModel* m, const BxgEnvSpec* spec, int64_t n_env, cons
   LaunchShape ls = launch_shape(m, n_env);
   BxgEnvSpec env = *spec;
   void* args[] = {(void*)&m->pm.d, (void*)&m->d_blob, (void*)&q, (void*)&qd, (void*)out, (void*)&n_env, (void*)&env, (void*)&obs};
-  BXG_CUDA(cudaLaunchKernel(init_kernel_of(m->pm.variant_id), dim3(ls.grid), dim3(ls.threads), args, ls.smem, st));
+  BXG_CUDA(cudaLaunchKernel(init_kernel_of(m->kernel_id), dim3(ls.grid), dim3(ls.threads), args, ls.smem, st));
   g_launches.fetch_add(1);
   BXG_CUDA(cudaGetLastError());
   return BXG_OK;
@@ -329,7 +346,7 @@ int bxg_env_step(const BxgModel* m, const BxgEnvSpec* spec, int64_t n_env, int32
   void* args[] = {(void*)&m->pm.d, (void*)&m->d_blob, (void*)in, (void*)&action, (void*)out, (void*)&n_env, (void*)&nf, (void*)&fl, (void*)&dg,
                   (void*)&env, (void*)&eio, (void*)&first};
   const bool chol = m->pm.d.minv_mode == BXG_MINV_CHOLESKY;
-  const void* kern = lean ? step_lean_kernel_of(m->pm.variant_id, chol) : (chol ? step_chol_kernel_of(m->pm.variant_id) : step_kernel_of(m->pm.variant_id));
+  const void* kern = lean ? step_lean_kernel_of(m->kernel_id, chol) : (chol ? step_chol_kernel_of(m->kernel_id) : step_kernel_of(m->kernel_id));
   BXG_CUDA(cudaLaunchKernel(kern, dim3(ls.grid), dim3(ls.threads), args, ls.smem, st));
   g_launches.fetch_add(1);
   BXG_CUDA(cudaGetLastError());

@@ -30,6 +30,20 @@
 
 #include "bxg_model.h"
 
+// Model-specialised translation units (bxg_inst.cu, kernel ids 10 and 11): BXG_CONST_DIMS names a generated header
+// (tools/gen_const_dims.py) with the packed Dims of ONE model as a constexpr function BXG_CONST_DIMS_FN, so every
+// size, slab offset, blob offset and loop bound of the step is a compile-time constant -- what jit gives the
+// reference, whose tree scans unroll at trace time (scan.py:87-134).  The generic kernels read the same fields from
+// the kernel parameter; bxg_model_create picks the specialised kernel only when the model's packed Dims are identical.
+#if defined(BXG_CONST_DIMS)
+#include BXG_CONST_DIMS
+#define BXG_GET_DIMS(c) constexpr ::bxg::Dims D = ::bxg::BXG_CONST_DIMS_FN()
+#define BXG_DIMS_OF(c) (::bxg::BXG_CONST_DIMS_FN())
+#else
+#define BXG_GET_DIMS(c) const ::bxg::Dims& D = *(c).D
+#define BXG_DIMS_OF(c) (*(c).D)
+#endif
+
 #if defined(__CUDACC__)
 #define BXG_HD __host__ __device__ __forceinline__
 #define BXG_HD_NOINLINE static __host__ __device__ __noinline__   // one copy: keeps the per-substep code footprint small
@@ -242,7 +256,7 @@ BXG_HD_NOINLINE void imp_aref(const real* prm, real pos, real vel, real* imp_out
 // actuator.to_tau (brax/actuator.py:23-57), lanes <-> dofs, into s_tau
 template <class X>
 BXG_HD void actuator_tau(X& ex, const Ctx& c) {
-  const Dims& D = *c.D; const real* mf = c.mf; const int* mi = c.mi; real* s = c.s;
+  BXG_GET_DIMS(c); const real* mf = c.mf; const int* mi = c.mi; real* s = c.s;
   const int nv = D.nv;
   ex.lanes([&](int lane) {
     for (int d = lane; d < nv; d += X::G) {
@@ -269,7 +283,7 @@ BXG_HD void actuator_tau(X& ex, const Ctx& c) {
 // assembly of qf_smooth.  Runs before the RNE passes, which reuse the same temporaries.
 template <class X>
 BXG_HD void fluid_passive(X& ex, const Ctx& c) {
-  const Dims& D = *c.D; const real* mf = c.mf; const int* mi = c.mi; real* s = c.s;
+  BXG_GET_DIMS(c); const real* mf = c.mf; const int* mi = c.mi; real* s = c.s;
   const int L = D.L, nv = D.nv;
   ex.lanes([&](int lane) {
     for (int l = lane; l < L; l += X::G) {
@@ -309,7 +323,7 @@ BXG_HD void fluid_passive(X& ex, const Ctx& c) {
 
 template <class X, class Cfg>
 BXG_HD void dyn_forces(X& ex, const Ctx& c) {
-  const Dims& D = *c.D; const real* mf = c.mf; const int* mi = c.mi; real* s = c.s;
+  BXG_GET_DIMS(c); const real* mf = c.mf; const int* mi = c.mi; real* s = c.s;
   const int L = D.L, nv = D.nv;
   // fluid models run on the generic variant or on the small 8-wide one (bxg_model.h): the others carry no fluid code
   constexpr bool kFluidCode = Cfg::VC4 == 0 || (Cfg::G == 4 && Cfg::VC4 == 2);
@@ -376,7 +390,7 @@ BXG_HD void dyn_forces(X& ex, const Ctx& c) {
 // --------------------------------------- constraint.force + projected gradient
 template <class X>
 BXG_HD void con_force_generic(X& ex, const Ctx& c, Stats* st) {
-  const Dims& D = *c.D; real* s = c.s;
+  BXG_GET_DIMS(c); real* s = c.s;
   const int nv = D.nv, nc = D.nc, nvp = D.nvp, ncp = D.ncp;
   if (nc == 0) {
     ex.lanes([&](int lane) { for (int d = lane; d < nv; d += X::G) s[D.s_qfc + d] = R(0.); });
@@ -483,7 +497,7 @@ BXG_HD void con_force_generic(X& ex, const Ctx& c, Stats* st) {
 // (integrator.py:58-60) and BXG_MINV_CHOLESKY.
 template <class X>
 BXG_HD void spd_inverse(X& ex, const Ctx& c, const real* src, real* dst, real* Lm, const real* add_diag, real diag_scale) {
-  const Dims& D = *c.D;
+  BXG_GET_DIMS(c);
   const int n = D.nv, nvp = D.nvp;
   for (int j = 0; j < n; ++j) {
     ex.lanes([&](int lane) {
@@ -522,7 +536,7 @@ BXG_HD void spd_inverse(X& ex, const Ctx& c, const real* src, real* dst, real* L
 // inverse in registers.  W = nvw.
 template <class X, int W>
 BXG_HD void spd_inverse_rows(X& ex, const Ctx& c, const real* src, real* dst, real* Lm) {
-  const Dims& D = *c.D;
+  BXG_GET_DIMS(c);
   const int n = D.nv, ld = D.nvp;
   typename X::template LaneVec<W> lrow;
 #pragma unroll
@@ -583,7 +597,7 @@ BXG_HD void spd_inverse_rows(X& ex, const Ctx& c, const real* src, real* dst, re
 // ------------------------------------------------------ integrator.integrate
 template <class X>
 BXG_HD void integrate(X& ex, const Ctx& c) {
-  const Dims& D = *c.D; const real* mf = c.mf; const int* mi = c.mi; real* s = c.s;
+  BXG_GET_DIMS(c); const real* mf = c.mf; const int* mi = c.mi; real* s = c.s;
   const int nv = D.nv, nvp = D.nvp, L = D.L;
   const real dt = D.dt;
   const real* Mi = s + D.s_Minv;
@@ -629,7 +643,7 @@ BXG_HD void integrate(X& ex, const Ctx& c) {
 // The joint transform / motion of a link is produced and consumed by the same lane: it stays in registers.
 template <class X, bool VEL>
 BXG_HD void kinematics(X& ex, const Ctx& c) {
-  const Dims& D = *c.D; const real* mf = c.mf; const int* mi = c.mi; real* s = c.s;
+  BXG_GET_DIMS(c); const real* mf = c.mf; const int* mi = c.mi; real* s = c.s;
   const int L = D.L;
 #if BXG_KIN_REGS
   typename X::template LaneVec<VEL ? 13 : 7> jt;   // [pos 3, rot 4, (ang 3, vel 3)] of this lane's link
@@ -726,7 +740,7 @@ BXG_HD void finish_env(X& ex, const Ctx& c) {
 // ---------------------------------------------------- dynamics.transform_com
 template <class X>
 BXG_HD void transform_com(X& ex, const Ctx& c) {
-  const Dims& D = *c.D; const real* mf = c.mf; const int* mi = c.mi; real* s = c.s;
+  BXG_GET_DIMS(c); const real* mf = c.mf; const int* mi = c.mi; real* s = c.s;
   const int L = D.L;
   real* xi_pos = s + D.s_t_ang;
   ex.lanes([&](int l) {
@@ -859,7 +873,7 @@ BXG_HD void transform_com(X& ex, const Ctx& c) {
 // --------------------------------------------------------------- mass.matrix
 template <class X>
 BXG_HD void mass_matrix(X& ex, const Ctx& c) {
-  const Dims& D = *c.D; const real* mf = c.mf; const int* mi = c.mi; real* s = c.s;
+  BXG_GET_DIMS(c); const real* mf = c.mf; const int* mi = c.mi; real* s = c.s;
   const int L = D.L, nv = D.nv, nvp = D.nvp;
   real* M = s + D.s_M;
   ex.lanes([&](int lane) {
@@ -907,7 +921,7 @@ BXG_HD void mass_matrix(X& ex, const Ctx& c) {
 // ------------------------------------------------------ math.inv_approximate
 template <class X>
 BXG_HD void minv_newton_schulz_generic(X& ex, const Ctx& c, Stats* st) {
-  const Dims& D = *c.D; real* s = c.s;
+  BXG_GET_DIMS(c); real* s = c.s;
   const int n = D.nv, nvp = D.nvp;
   const real* M = s + D.s_M;
   real* Xc = s + D.s_Minv;   // current estimate
@@ -1231,7 +1245,7 @@ BXG_HD void store_tile(int lane, real* C, int ld, const real* acc) {
 template <class X, int W>
 BXG_HD void minv_newton_schulz_tiles(X& ex, const Ctx& c, Stats* st) {
   using T = Tile<X::G, W>;
-  const Dims& D = *c.D; real* s = c.s;
+  BXG_GET_DIMS(c); real* s = c.s;
   const int n = D.nv, ld = D.nvp;
   const real* M = s + D.s_M;
   real* Xa = s + D.s_Minv;
@@ -1298,7 +1312,7 @@ BXG_HD void minv_newton_schulz_tiles(X& ex, const Ctx& c, Stats* st) {
 template <class X, class Cfg>
 BXG_HD void minv_newton_schulz(X& ex, const Ctx& c, Stats* st) {
   if constexpr (Cfg::VC4 > 0) {
-    if (!Cfg::GENERIC_TOO || !c.D->force_generic) { minv_newton_schulz_tiles<X, 4 * Cfg::VC4>(ex, c, st); return; }
+    if (!Cfg::GENERIC_TOO || !BXG_DIMS_OF(c).force_generic) { minv_newton_schulz_tiles<X, 4 * Cfg::VC4>(ex, c, st); return; }
   }
   if constexpr (Cfg::GENERIC_TOO) minv_newton_schulz_generic(ex, c, st);
 }
@@ -1350,7 +1364,7 @@ template <class X, int VC4, int NC4, int R>
 BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
   constexpr int VW = 4 * VC4, CW = 4 * NC4, G = X::G;
   constexpr bool AREG = R * CW <= 56;
-  const Dims& D = *c.D; real* s = c.s;
+  BXG_GET_DIMS(c); real* s = c.s;
   const int nv = D.nv, nc = D.nc, ldv = D.nvp, ldj = D.jld, ldc = D.ncp;
   const real* J = s + D.s_J; const real* Mi = s + D.s_Minv;
   real* A = s + D.s_A;
@@ -1550,7 +1564,7 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
 
 template <class X, class Cfg>
 BXG_HD void con_force(X& ex, const Ctx& c, Stats* st) {
-  const Dims& D = *c.D;
+  BXG_GET_DIMS(c);
   if (D.nc == 0) {
     ex.lanes([&](int lane) { for (int d = lane; d < D.nv; d += X::G) c.s[D.s_qfc + d] = R(0.); });
     return;
@@ -1647,7 +1661,7 @@ BXG_HD void con_jacobian(X& ex, const Ctx& c) {
   // contacts between two moving links (capsule-capsule) are compiled into variant 5 and the
   // generic variant only (bxg_model.h picks one of them for such models)
   constexpr bool kTwoBody = Cfg::VC4 == 0 || Cfg::NC4 == 16;
-  const Dims& D = *c.D; const real* mf = c.mf; const int* mi = c.mi; real* s = c.s;
+  BXG_GET_DIMS(c); const real* mf = c.mf; const int* mi = c.mi; real* s = c.s;
   const int nv = D.nv, nvp = D.jld;
   real* J = s + D.s_J;
   // J shares its slot with Newton-Schulz scratch: clear it (limit rows and the
@@ -1755,7 +1769,7 @@ BXG_HD void con_jacobian(X& ex, const Ctx& c) {
 //   1  exact SPD inverse by Cholesky (pipeline.init; BXG_MINV_CHOLESKY steps)
 template <class X, class Cfg, int INV>
 BXG_HD void update_position_terms(X& ex, const Ctx& c, Stats* st, bool in_step) {
-  const int sl = in_step ? c.D->sync_level : 0;
+  const int sl = in_step ? BXG_DIMS_OF(c).sync_level : 0;
   kinematics<X, !BXG_XD_TAIL>(ex, c);
   BXG_PHASE_END(st, 4);
   transform_com(ex, c);
@@ -1767,11 +1781,11 @@ BXG_HD void update_position_terms(X& ex, const Ctx& c, Stats* st, bool in_step) 
   if constexpr (INV == 1) {
     bool done = false;
     if constexpr (Cfg::VC4 > 0 && 4 * Cfg::VC4 <= X::G) {   // one lane per row / column
-      if (!Cfg::GENERIC_TOO || !c.D->force_generic) { spd_inverse_rows<X, 4 * Cfg::VC4>(ex, c, c.s + c.D->s_M, c.s + c.D->s_Minv, c.s + c.D->s_scr); done = true; }
+      if (!Cfg::GENERIC_TOO || !BXG_DIMS_OF(c).force_generic) { spd_inverse_rows<X, 4 * Cfg::VC4>(ex, c, c.s + BXG_DIMS_OF(c).s_M, c.s + BXG_DIMS_OF(c).s_Minv, c.s + BXG_DIMS_OF(c).s_scr); done = true; }
     }
-    if (!done) spd_inverse(ex, c, c.s + c.D->s_M, c.s + c.D->s_Minv, c.s + c.D->s_scr, nullptr, R(0.));
+    if (!done) spd_inverse(ex, c, c.s + BXG_DIMS_OF(c).s_M, c.s + BXG_DIMS_OF(c).s_Minv, c.s + BXG_DIMS_OF(c).s_scr, nullptr, R(0.));
   } else {
-    if (c.D->ns_iters == 0) spd_inverse(ex, c, c.s + c.D->s_M, c.s + c.D->s_Minv, c.s + c.D->s_scr, nullptr, R(0.));
+    if (BXG_DIMS_OF(c).ns_iters == 0) spd_inverse(ex, c, c.s + BXG_DIMS_OF(c).s_M, c.s + BXG_DIMS_OF(c).s_Minv, c.s + BXG_DIMS_OF(c).s_scr, nullptr, R(0.));
     else minv_newton_schulz<X, Cfg>(ex, c, st);
   }
   BXG_PHASE_END(st, 7);
@@ -1785,7 +1799,7 @@ template <class X, class Cfg, int INV>
 BXG_HD void substep(X& ex, const Ctx& c, Stats* st) {
   // CTA-wide phase alignment keeps the warps of a CTA on the same straight-line
   // code (instruction-cache locality); sync_level trades that against barrier waits
-  const int sl = c.D->sync_level;
+  const int sl = BXG_DIMS_OF(c).sync_level;
   BXG_PHASE_BEGIN(st);
   if (sl & 4) ex.cta_sync();
   dyn_forces<X, Cfg>(ex, c);
@@ -1803,7 +1817,7 @@ BXG_HD void substep(X& ex, const Ctx& c, Stats* st) {
 // pipeline.init (pipeline.py:51-61); q, qd already in the slab
 template <class X, class Cfg>
 BXG_HD void init_env(X& ex, const Ctx& c, Stats* st) {
-  const Dims& D = *c.D; real* s = c.s;
+  BXG_GET_DIMS(c); real* s = c.s;
   ex.lanes([&](int lane) {
     for (int i = lane; i < D.nv; i += X::G) { s[D.s_qfs + i] = R(0.); s[D.s_qfc + i] = R(0.); s[D.s_qdd + i] = R(0.); }
     for (int i = lane; i < (D.nc > 0 ? D.nc : 1) * D.jld; i += X::G) s[D.s_J + i] = R(0.);
@@ -1815,7 +1829,7 @@ BXG_HD void init_env(X& ex, const Ctx& c, Stats* st) {
 // columns past nv / nc are read by compile-time-width loops and must contribute 0).
 template <class X>
 BXG_HD void prepare_env(X& ex, const Ctx& c) {
-  const Dims& D = *c.D; real* s = c.s;
+  BXG_GET_DIMS(c); real* s = c.s;
   const int ncz = D.nc > 0 ? D.nc : 1;
   ex.lanes([&](int lane) {
     const int G = X::G;
@@ -1834,12 +1848,12 @@ BXG_HD void prepare_env(X& ex, const Ctx& c) {
 // (Humanoid), stored in s_red[0..2] by env_prologue.
 // a point fixed in the frame of a link: x.take(link).do(Transform.create(pos=p)).pos
 BXG_HD V3 env_tip(const Ctx& c, const BxgEnvSpec& sp) {
-  const Dims& D = *c.D; const real* s = c.s;
+  BXG_GET_DIMS(c); const real* s = c.s;
   return ld3(s + D.s_x_pos + 3 * sp.tip_link) + rotate(V3{sp.tip_pos[0], sp.tip_pos[1], sp.tip_pos[2]}, ld4(s + D.s_x_rot + 4 * sp.tip_link));
 }
 // x.take(link).do(Transform.create(pos=inertia.transform.pos[link])).pos: the link's centre of mass
 BXG_HD V3 env_link_com(const Ctx& c, int l) {
-  const Dims& D = *c.D; const real* s = c.s;
+  BXG_GET_DIMS(c); const real* s = c.s;
   return ld3(s + D.s_x_pos + 3 * l) + rotate(ld3(c.mf + D.m_in_pos + 3 * l), ld4(s + D.s_x_rot + 4 * l));
 }
 // math.safe_norm (brax/math.py:308-328)
@@ -1851,7 +1865,7 @@ BXG_HD real env_safe_norm(V3 v) {
 // whole-model centre of mass from link poses in s_x_pos / s_x_rot
 // (envs/humanoid.py:339-354 `_com`); every lane computes it redundantly
 BXG_HD V3 env_com(const Ctx& c) {
-  const Dims& D = *c.D; const real* mf = c.mf; const real* s = c.s;
+  BXG_GET_DIMS(c); const real* mf = c.mf; const real* s = c.s;
   V3 msum{0, 0, 0}; real mtot = R(0.);
   for (int l = 0; l < D.L; ++l) {
     real m = mf[D.m_in_mass + l];
@@ -1864,7 +1878,7 @@ BXG_HD V3 env_com(const Ctx& c) {
 // captures the pre-step reference point and rescales the action (Humanoid)
 template <class X, class ST>
 BXG_HD void env_prologue(X& ex, const Ctx& c, const BxgEnvSpec& sp, const ST& g, int64_t e) {
-  const Dims& D = *c.D; const real* mf = c.mf; real* s = c.s;
+  BXG_GET_DIMS(c); const real* mf = c.mf; real* s = c.s;
   const int L = D.L;
   ex.lanes([&](int lane) {
     for (int i = lane; i < L * 3; i += X::G) s[D.s_x_pos + i] = g.x_pos[e * L * 3 + i];
@@ -1891,7 +1905,7 @@ BXG_HD void env_prologue(X& ex, const Ctx& c, const BxgEnvSpec& sp, const ST& g,
 // COM kind s_tau must already hold actuator.to_tau at the current q, qd
 template <class X>
 BXG_HD void env_write_obs(X& ex, const Ctx& c, const BxgEnvSpec& sp, real* o) {
-  const Dims& D = *c.D; const real* mf = c.mf; real* s = c.s;
+  BXG_GET_DIMS(c); const real* mf = c.mf; real* s = c.s;
   const int L = D.L, nv = D.nv, nq = D.nq;
   ex.lanes([&](int lane) {
     const int G = X::G;
@@ -1954,7 +1968,7 @@ BXG_HD void env_write_obs(X& ex, const Ctx& c, const BxgEnvSpec& sp, real* o) {
 // observation of a freshly initialised state: action = zeros (humanoid.py:241)
 template <class X>
 BXG_HD void env_reset_obs(X& ex, const Ctx& c, const BxgEnvSpec& sp, real* o) {
-  const Dims& D = *c.D; real* s = c.s;
+  BXG_GET_DIMS(c); real* s = c.s;
   ex.lanes([&](int lane) { for (int a = lane; a < D.nu; a += X::G) s[D.s_act + a] = R(0.); });
   if (sp.kind == BXG_ENV_COM_VELOCITY || sp.kind == BXG_ENV_STANDUP) actuator_tau(ex, c);
   env_write_obs(ex, c, sp, o);
@@ -1962,7 +1976,7 @@ BXG_HD void env_reset_obs(X& ex, const Ctx& c, const BxgEnvSpec& sp, real* o) {
 
 template <class X, class IO>
 BXG_HD void env_epilogue(X& ex, const Ctx& c, const BxgEnvSpec& sp, const IO& io, int64_t e, bool valid, bool* done_out) {
-  const Dims& D = *c.D; const real* mf = c.mf; real* s = c.s;
+  BXG_GET_DIMS(c); const real* mf = c.mf; real* s = c.s;
   const int L = D.L, nv = D.nv, nq = D.nq;
   const bool com_kind = sp.kind == BXG_ENV_COM_VELOCITY;
   if (com_kind || sp.kind == BXG_ENV_STANDUP) actuator_tau(ex, c);   // qfrc_actuator at the post-step q, qd (humanoid.py:325-327)
@@ -2066,7 +2080,7 @@ BXG_HD void env_epilogue(X& ex, const Ctx& c, const BxgEnvSpec& sp, const IO& io
 // AutoResetWrapper for the pipeline state: copy first_state's leaves for a done env
 template <class X, class ST>
 BXG_HD void store_first_state(X& ex, const Ctx& c, const ST& g, const ST& f, int64_t e) {
-  const Dims& D = *c.D;
+  BXG_GET_DIMS(c);
   const int L = D.L, nv = D.nv, nq = D.nq, nc = D.nc;
   ex.lanes([&](int lane) {
     const int G = X::G;
@@ -2092,7 +2106,7 @@ BXG_HD void io_vec(X& ex, int n, F f) {
 // ST: BxgState (include/bxg.h), or the emulator's double-precision twin with the same member names
 template <class X, class ST>
 BXG_HD void load_env(X& ex, const Ctx& c, const ST& g, const real* act, int64_t e) {
-  const Dims& D = *c.D; real* s = c.s;
+  BXG_GET_DIMS(c); real* s = c.s;
   const int L = D.L, nv = D.nv, nq = D.nq, nc = D.nc, nvp = D.nvp;
   ex.lanes([&](int lane) {
     const int G = X::G;
@@ -2149,7 +2163,7 @@ BXG_HD void load_env(X& ex, const Ctx& c, const ST& g, const real* act, int64_t 
 // same bits.  x of the incoming state is read by the env prologue (pre-step reference point).
 template <class X, class ST>
 BXG_HD void load_env_lean(X& ex, const Ctx& c, const ST& g, const real* act, int64_t e) {
-  const Dims& D = *c.D; real* s = c.s;
+  BXG_GET_DIMS(c); real* s = c.s;
   const int nv = D.nv, nq = D.nq, nvp = D.nvp;
   ex.lanes([&](int lane) {
     const int G = X::G;
@@ -2169,12 +2183,12 @@ template <class X, class Cfg>
 BXG_HD void lean_entry(X& ex, const Ctx& c) {
   kinematics<X, !BXG_XD_TAIL>(ex, c);
   transform_com(ex, c);
-  if (c.D->ns_iters == 0) mass_matrix(ex, c);   // integrate's implicit-damping solve reads M (integrator.py:58-60)
+  if (BXG_DIMS_OF(c).ns_iters == 0) mass_matrix(ex, c);   // integrate's implicit-damping solve reads M (integrator.py:58-60)
   con_jacobian<X, Cfg>(ex, c);
 }
 template <class X, class ST>
 BXG_HD void store_env_lean(X& ex, const Ctx& c, const ST& g, int64_t e, const BxgDiag* dg, const Stats& st) {
-  const Dims& D = *c.D; const real* s = c.s;
+  BXG_GET_DIMS(c); const real* s = c.s;
   const int L = D.L, nv = D.nv, nq = D.nq, nvp = D.nvp;
   ex.lanes([&](int lane) {
     const int G = X::G;
@@ -2201,7 +2215,7 @@ BXG_HD void store_env_lean(X& ex, const Ctx& c, const ST& g, int64_t e, const Bx
 }
 template <class X, class ST>
 BXG_HD void store_first_state_lean(X& ex, const Ctx& c, const ST& g, const ST& f, int64_t e) {
-  const Dims& D = *c.D;
+  BXG_GET_DIMS(c);
   const int L = D.L, nv = D.nv, nq = D.nq;
   ex.lanes([&](int lane) {
     const int G = X::G;
@@ -2213,7 +2227,7 @@ BXG_HD void store_first_state_lean(X& ex, const Ctx& c, const ST& g, const ST& f
 
 template <class X>
 BXG_HD void load_env_qqd(X& ex, const Ctx& c, const real* q, const real* qd, int64_t e) {
-  const Dims& D = *c.D; real* s = c.s;
+  BXG_GET_DIMS(c); real* s = c.s;
   ex.lanes([&](int lane) {
     for (int i = lane; i < D.nq; i += X::G) s[D.s_q + i] = q[e * D.nq + i];
     for (int i = lane; i < D.nv; i += X::G) s[D.s_qd + i] = qd[e * D.nv + i];
@@ -2222,7 +2236,7 @@ BXG_HD void load_env_qqd(X& ex, const Ctx& c, const real* q, const real* qd, int
 
 template <class X, class ST>
 BXG_HD void store_env(X& ex, const Ctx& c, const ST& g, int64_t e, const BxgDiag* dg, const Stats& st) {
-  const Dims& D = *c.D; const real* s = c.s;
+  BXG_GET_DIMS(c); const real* s = c.s;
   const int L = D.L, nv = D.nv, nq = D.nq, nc = D.nc, nvp = D.nvp;
   ex.lanes([&](int lane) {
     const int G = X::G;

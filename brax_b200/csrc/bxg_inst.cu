@@ -1,16 +1,24 @@
 // bxg_inst.cu -- one kernel variant per translation unit (-DBXG_VARIANT=k) so
 // the variants compile in parallel.  Exposes the two entry points of variant k
 // to bxg_api.cu as plain function pointers.
+// kernel ids 10 and 11: variants 0 and 1 specialised for the packed layout of Ant / Humanoid (constexpr Dims)
+#if BXG_VARIANT == 10
+#define BXG_CONST_DIMS "gen/bxg_dims_ant.h"
+#define BXG_CONST_DIMS_FN const_dims_ant
+#elif BXG_VARIANT == 11
+#define BXG_CONST_DIMS "gen/bxg_dims_humanoid.h"
+#define BXG_CONST_DIMS_FN const_dims_humanoid
+#endif
 #include "bxg_kernels.cuh"
 
 #ifndef BXG_VARIANT
-#error "compile with -DBXG_VARIANT=0..9"
+#error "compile with -DBXG_VARIANT=0..11"
 #endif
 
 namespace {
-#if BXG_VARIANT == 0
+#if BXG_VARIANT == 0 || BXG_VARIANT == 10
 using Cfg = bxg::KernelCfg<16, 4, 6>;
-#elif BXG_VARIANT == 1
+#elif BXG_VARIANT == 1 || BXG_VARIANT == 11
 using Cfg = bxg::KernelCfg<32, 6, 7>;
 #elif BXG_VARIANT == 2
 using Cfg = bxg::KernelCfg<32, 8, 8>;

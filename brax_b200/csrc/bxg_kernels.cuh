@@ -109,15 +109,20 @@ __device__ __forceinline__ void stage_model(const Dims& D, const uint32_t* __res
 // default path loses 4 % (Ant) to the larger register / code footprint (profiles/r02_ab_lean_code.txt).
 template <class Cfg, int INV, bool LEAN>
 __global__ void __launch_bounds__(Cfg::MAX_THREADS)
-step_kernel(const Dims D, const uint32_t* __restrict__ model, const BxgState in, const float* __restrict__ act,
+step_kernel(const Dims Dparam, const uint32_t* __restrict__ model, const BxgState in, const float* __restrict__ act,
             const BxgState out, int64_t n_env, int n_frames, int flags, const BxgDiag diag,
             const BxgEnvSpec env, const BxgEnvIO eio, const BxgState first) {
   extern __shared__ __align__(16) uint32_t smem_u[];
   constexpr int G = Cfg::G;
+#if defined(BXG_CONST_DIMS)
+  constexpr Dims D = BXG_CONST_DIMS_FN();   // (the launch passes the same values in Dparam: bxg_api.cu checked them at model creation)
+#else
+  const Dims& D = Dparam;
+#endif
   stage_model(D, model, smem_u);
   const int groups = blockDim.x / G, group = threadIdx.x / G;
   Ctx c;
-  c.D = &D;
+  c.D = &Dparam;
   c.mf = reinterpret_cast<const float*>(smem_u);
   c.mi = reinterpret_cast<const int*>(smem_u);
   c.s = reinterpret_cast<float*>(smem_u) + D.model_words + group * D.env_words;
@@ -162,14 +167,19 @@ step_kernel(const Dims D, const uint32_t* __restrict__ model, const BxgState in,
 
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::MAX_THREADS)
-init_kernel(const Dims D, const uint32_t* __restrict__ model, const float* __restrict__ q, const float* __restrict__ qd,
+init_kernel(const Dims Dparam, const uint32_t* __restrict__ model, const float* __restrict__ q, const float* __restrict__ qd,
             const BxgState out, int64_t n_env, const BxgEnvSpec env, float* __restrict__ obs) {
   extern __shared__ __align__(16) uint32_t smem_u[];
   constexpr int G = Cfg::G;
+#if defined(BXG_CONST_DIMS)
+  constexpr Dims D = BXG_CONST_DIMS_FN();   // (the launch passes the same values in Dparam: bxg_api.cu checked them at model creation)
+#else
+  const Dims& D = Dparam;
+#endif
   stage_model(D, model, smem_u);
   const int groups = blockDim.x / G, group = threadIdx.x / G;
   Ctx c;
-  c.D = &D;
+  c.D = &Dparam;
   c.mf = reinterpret_cast<const float*>(smem_u);
   c.mi = reinterpret_cast<const int*>(smem_u);
   c.s = reinterpret_cast<float*>(smem_u) + D.model_words + group * D.env_words;

@@ -223,8 +223,8 @@ def plan(sys, minv_mode: int = MINV_NEWTON_SCHULZ) -> dict:
   desc, keep = make_desc(sys, minv_mode)
   info = (ctypes.c_int32 * 8)()
   _check(lib().bxg_plan(ctypes.byref(desc), info), 'bxg_plan')
-  names = ('variant', 'lanes_per_env', 'model_words', 'env_words', 'envs_per_cta', 'smem_bytes_per_cta', 'nc')
-  return dict(zip(names, list(info)[:7]))
+  names = ('variant', 'lanes_per_env', 'model_words', 'env_words', 'envs_per_cta', 'smem_bytes_per_cta', 'nc', 'kernel_id')
+  return dict(zip(names, list(info)[:8]))
 
 
 def launch_count() -> int:

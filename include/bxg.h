@@ -264,7 +264,9 @@ int bxg_model_num_constraints(const BxgModel* model);
 /* Host-only planning query (no CUDA needed): which kernel variant a model maps
  * to and its shared-memory footprint.  info[0] = variant id, [1] = lanes per env,
  * [2] = model words, [3] = per-env slab words, [4] = envs per CTA,
- * [5] = dynamic shared memory bytes per CTA, [6] = nc, [7] = reserved. */
+ * [5] = dynamic shared memory bytes per CTA, [6] = nc, [7] = kernel id: the variant id, or 10 / 11 when the
+ * model's packed layout is exactly the one a model-specialised build of that variant was compiled for
+ * (Ant on variant 0, Humanoid on variant 1: sizes and offsets are compile-time constants there). */
 int bxg_plan(const BxgModelDesc* desc, int32_t info[8]);
 /* The launch a batch of n_env envs gets on this model's device (the persistent kernel picks
  * the number of envs per CTA per call: small or awkward batches use smaller CTAs).

@@ -17,6 +17,8 @@
 //
 // This is not a CPU fallback: it lives under tests/, is never built by the
 // package and nothing in brax_b200/ can load it.
+#include <stddef.h>
+#include <stdio.h>
 #include <string.h>
 
 #include <string>
@@ -162,6 +164,25 @@ int dispatch(const BxgModelDesc* desc, int vid, A... a) {
 
 extern "C" {
 int sim_sizeof_real() { return (int)sizeof(real); }
+// The packed Dims of a model as a C++ aggregate initializer (bxg_model.h field order): input of
+// tools/gen_const_dims.py, which writes the headers the model-specialised kernel variants are compiled with.
+int sim_dims_initializer(const BxgModelDesc* desc, int variant, char* buf, int cap) {
+  bxg::PackedModel pm;
+  if (!bxg::pack_model(*desc, &pm, variant).empty()) return -1;
+  static_assert(sizeof(bxg::Dims) % 4 == 0, "Dims is a sequence of 4-byte fields");
+  const size_t f0 = offsetof(bxg::Dims, dt) / 4, f1 = offsetof(bxg::Dims, gz) / 4;
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(&pm.d);
+  std::string out = "{";
+  for (size_t i = 0; i < sizeof(bxg::Dims) / 4; ++i) {
+    char tmp[64];
+    if (i >= f0 && i <= f1) { float f; memcpy(&f, w + i, 4); snprintf(tmp, sizeof tmp, "%af", (double)f); }
+    else snprintf(tmp, sizeof tmp, "%d", (int)w[i]);
+    out += tmp; out += i + 1 < sizeof(bxg::Dims) / 4 ? ", " : "}";
+  }
+  if ((int)out.size() + 1 > cap) return -2;
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return pm.variant_id;
+}
 // the kernel's sine / cosine (bxg_core.cuh r_sincos) on n values: tests/test_kernel_math.py
 void sim_sincos(const real* x, int n, real* s, real* c) { for (int i = 0; i < n; ++i) bxg::r_sincos(x[i], s + i, c + i); }
 // variant: -1 = the one the library would pick, else a forced kernel variant id

@@ -167,3 +167,29 @@ def test_lean_fused_env_gives_the_same_bits(name):
     for x, y in ((a.obs, b.obs), (a.reward, b.reward), (a.done, b.done), (a.pipeline_state.q, b.pipeline_state.q),
                  (a.pipeline_state.x.rot, b.pipeline_state.x.rot), (a.info['steps'], b.info['steps'])):
       assert torch.equal(x, y), (name, k)
+
+
+@pytest.mark.parametrize('name', ['ant', 'humanoid'])
+def test_model_specialised_kernels_equal_the_generic_ones_bit_for_bit(name):
+  """Kernel ids 10 / 11 (constexpr Dims, bxg_inst.cu) are what Ant / Humanoid run on; BXG_NO_SPECIALISE keeps the
+  blob-driven kernel of the variant.  Same source, same arithmetic: identical bits."""
+  import os
+  import torch
+  from brax_b200 import native
+  n = 50
+  s, q, qd, acts, nf = _inputs(name, n, seed=4)
+  assert native.plan(s)['kernel_id'] == {'ant': 10, 'humanoid': 11}[name]
+  dev = torch.device('cuda', 0)
+  spec = native.NativeModel(s, 0)
+  os.environ['BXG_NO_SPECIALISE'] = '1'
+  try:
+    gen = native.NativeModel(s, 0)
+  finally:
+    del os.environ['BXG_NO_SPECIALISE']
+  a = spec.init(torch.as_tensor(q, device=dev), torch.as_tensor(qd, device=dev))
+  b = gen.init(torch.as_tensor(q, device=dev), torch.as_tensor(qd, device=dev))
+  for act in acts:
+    t = torch.as_tensor(act, device=dev)
+    a, b = spec.step(a, t, nf), gen.step(b, t, nf)
+    for f in native.STATE_FIELDS:
+      assert torch.equal(a[f], b[f]), (name, f)
