@@ -204,6 +204,7 @@ void bxg_model_destroy(BxgModel* m) {
 }
 
 int bxg_model_num_constraints(const BxgModel* m) { return m ? m->pm.d.nc : -1; }
+int bxg_model_kernel_id(const BxgModel* m) { return m ? m->kernel_id : -1; }
 
 int bxg_plan(const BxgModelDesc* desc, int32_t info[8]) {
   if (!desc || !info) return fail(BXG_E_INVALID, "null argument");

@@ -43,8 +43,8 @@ using Cfg = bxg::KernelCfg<32, 0, 0>;
 #define BXG_CAT(a, b) BXG_CAT2(a, b)
 // two step kernels per variant: Newton-Schulz (the reference's matrix_inv) and exact Cholesky inverse
 // and each of them with lean state I/O (BXG_STEP_LEAN)
-extern "C" const void* BXG_CAT(bxg_step_kernel_v, BXG_VARIANT)() { return (const void*)bxg::step_kernel<Cfg, 0, false>; }
-extern "C" const void* BXG_CAT(bxg_step_chol_kernel_v, BXG_VARIANT)() { return (const void*)bxg::step_kernel<Cfg, 1, false>; }
-extern "C" const void* BXG_CAT(bxg_step_lean_kernel_v, BXG_VARIANT)() { return (const void*)bxg::step_kernel<Cfg, 0, true>; }
-extern "C" const void* BXG_CAT(bxg_step_chol_lean_kernel_v, BXG_VARIANT)() { return (const void*)bxg::step_kernel<Cfg, 1, true>; }
-extern "C" const void* BXG_CAT(bxg_init_kernel_v, BXG_VARIANT)() { return (const void*)bxg::init_kernel<Cfg>; }
+extern "C" const void* BXG_CAT(bxg_step_kernel_v, BXG_VARIANT)() { return (const void*)bxg::step_kernel<Cfg, 0, false, BXG_VARIANT>; }
+extern "C" const void* BXG_CAT(bxg_step_chol_kernel_v, BXG_VARIANT)() { return (const void*)bxg::step_kernel<Cfg, 1, false, BXG_VARIANT>; }
+extern "C" const void* BXG_CAT(bxg_step_lean_kernel_v, BXG_VARIANT)() { return (const void*)bxg::step_kernel<Cfg, 0, true, BXG_VARIANT>; }
+extern "C" const void* BXG_CAT(bxg_step_chol_lean_kernel_v, BXG_VARIANT)() { return (const void*)bxg::step_kernel<Cfg, 1, true, BXG_VARIANT>; }
+extern "C" const void* BXG_CAT(bxg_init_kernel_v, BXG_VARIANT)() { return (const void*)bxg::init_kernel<Cfg, BXG_VARIANT>; }

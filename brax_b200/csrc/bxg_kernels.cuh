@@ -107,7 +107,9 @@ __device__ __forceinline__ void stage_model(const Dims& D, const uint32_t* __res
 
 // LEAN (BXG_STEP_LEAN, include/bxg.h) is a compile-time mode: with the lean entry code in the same kernel the
 // default path loses 4 % (Ant) to the larger register / code footprint (profiles/r02_ab_lean_code.txt).
-template <class Cfg, int INV, bool LEAN>
+// ID: the kernel id of the translation unit (bxg_inst.cu).  It makes every instantiation a distinct symbol: ids 10 / 11
+// use the same Cfg as variants 0 / 1 and would otherwise be ONE weak symbol for two different kernels.
+template <class Cfg, int INV, bool LEAN, int ID>
 __global__ void __launch_bounds__(Cfg::MAX_THREADS)
 step_kernel(const Dims Dparam, const uint32_t* __restrict__ model, const BxgState in, const float* __restrict__ act,
             const BxgState out, int64_t n_env, int n_frames, int flags, const BxgDiag diag,
@@ -165,7 +167,7 @@ step_kernel(const Dims Dparam, const uint32_t* __restrict__ model, const BxgStat
   }
 }
 
-template <class Cfg>
+template <class Cfg, int ID>
 __global__ void __launch_bounds__(Cfg::MAX_THREADS)
 init_kernel(const Dims Dparam, const uint32_t* __restrict__ model, const float* __restrict__ q, const float* __restrict__ qd,
             const BxgState out, int64_t n_env, const BxgEnvSpec env, float* __restrict__ obs) {

@@ -199,6 +199,7 @@ def lib() -> ctypes.CDLL:
       l.bxg_model_create.argtypes = [ctypes.POINTER(ModelDesc), ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
       l.bxg_model_destroy.argtypes = [ctypes.c_void_p]
       l.bxg_model_num_constraints.argtypes = [ctypes.c_void_p]
+      l.bxg_model_kernel_id.argtypes = [ctypes.c_void_p]
       l.bxg_plan.argtypes = [ctypes.POINTER(ModelDesc), ctypes.POINTER(ctypes.c_int32)]
       l.bxg_launch_shape.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int32)]
       l.bxg_init.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
@@ -254,6 +255,7 @@ class NativeModel:
     h = ctypes.c_void_p()
     _check(lib().bxg_model_create(ctypes.byref(desc), self.device, ctypes.byref(h)), 'bxg_model_create')
     self._h = h
+    self.kernel_id = int(lib().bxg_model_kernel_id(h))
     del keep
 
   def __del__(self):

@@ -261,6 +261,8 @@ int bxg_model_create(const BxgModelDesc* desc, int device, BxgModel** out);
 void bxg_model_destroy(BxgModel* model);
 /* nc for this model (rows of con_jac). */
 int bxg_model_num_constraints(const BxgModel* model);
+/* The kernel id this model's launches use (bxg_plan info[7]). */
+int bxg_model_kernel_id(const BxgModel* model);
 /* Host-only planning query (no CUDA needed): which kernel variant a model maps
  * to and its shared-memory footprint.  info[0] = variant id, [1] = lanes per env,
  * [2] = model words, [3] = per-env slab words, [4] = envs per CTA,
