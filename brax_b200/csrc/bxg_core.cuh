@@ -1063,6 +1063,7 @@ BXG_HD real row_dot(const real* a, const real* v) {
 // issues TM 128-bit loads of A and 4*TN/2 64-bit (or TN/4 128-bit) loads of B for
 // 4*TM*TN FFMA, which balances the shared-memory pipe against the FMA pipe; the
 // k loop stays rolled so the body lives in the instruction cache.
+template <int N> struct IntC { static constexpr int value = N; };
 template <int G, int W> struct Tile;
 // PIPE: request the operands of the next k-block before the FMAs of the current one, explicitly.  Pays where
 // registers allow (4x4 tiles: Ant +2.4 %); with the 3x6 tiles at 96 registers it costs 5 % (profiles/r01_sweep_r1i.json)
@@ -1098,10 +1099,14 @@ BXG_HD void store_cols(real* p, const real* v) {
 
 // acc[r * TN + c] = sum_k A[row0 + r][k] * B[k][col0 + c], k ascending; NEG accumulates
 // the negated products instead (rounding is symmetric: exactly -(A B), no extra operation)
-template <class T, int W, bool NEG = false>
+// K <= W: the k range that can hold non-zeros (columns of A / rows of B past it are zero padding).  Only the
+// model-specialised builds know it at compile time (K = nv): their products skip the padded k steps, exact zeros
+// whose omission leaves every sum unchanged (Ant: 14 of 16, one eighth of the multiply-adds; Humanoid: 23 of 24).
+template <class T, int W, bool NEG = false, int K = W>
 BXG_HD void tile_matmul(int lane, const real* A, const real* B, int ld, real* acc) {
   const int rg = lane / T::CG, cg = lane - rg * T::CG;
   const real* a0 = A + rg * T::TM * ld;
+  constexpr int KB = (K / 4) * 4, KT = K - KB;   // k steps in full blocks of four, and in the tail block
 #if defined(__CUDA_ARCH__)
   // sm_100a packed FP32: one FFMA2 = two fused multiply-adds per lane (same
   // rounding as two scalar FFMA), halving the issue slots of the inner product
@@ -1117,23 +1122,9 @@ BXG_HD void tile_matmul(int lane, const real* A, const real* B, int ld, real* ac
   for (int r = 0; r < T::TM; ++r) a_nxt[r] = ldv4(a0 + r * ld);
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) load_cols<T::TN>(B + kk * ld + cg * T::TN, b_nxt[kk]);
-  BXG_PRAGMA_UNROLL(BXG_PIPE16_UNROLL)
-  for (int k0 = 0; k0 < W; k0 += 4) {
-    F4 a[T::TM]; real bv[4][T::TN];
+  auto block = [&](const F4* a, const real (*bv)[T::TN], auto nk) {
 #pragma unroll
-    for (int r = 0; r < T::TM; ++r) a[r] = a_nxt[r];
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk)
-#pragma unroll
-      for (int cc = 0; cc < T::TN; ++cc) bv[kk][cc] = b_nxt[kk][cc];
-    if (k0 + 4 < W) {
-#pragma unroll
-      for (int r = 0; r < T::TM; ++r) a_nxt[r] = ldv4(a0 + r * ld + k0 + 4);
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) load_cols<T::TN>(B + (k0 + 4 + kk) * ld + cg * T::TN, b_nxt[kk]);
-    }
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
+    for (int kk = 0; kk < decltype(nk)::value; ++kk) {
 #pragma unroll
       for (int r = 0; r < T::TM; ++r) {
         const real ap = kk == 0 ? a[r].x : kk == 1 ? a[r].y : kk == 2 ? a[r].z : a[r].w;
@@ -1144,15 +1135,32 @@ BXG_HD void tile_matmul(int lane, const real* A, const real* B, int ld, real* ac
           acc2[r][cc] = __ffma2_rn(av2, make_float2(bv[kk][2 * cc], bv[kk][2 * cc + 1]), acc2[r][cc]);
       }
     }
+  };
+  BXG_PRAGMA_UNROLL(BXG_PIPE16_UNROLL)
+  for (int k0 = 0; k0 < KB; k0 += 4) {
+    F4 a[T::TM]; real bv[4][T::TN];
+#pragma unroll
+    for (int r = 0; r < T::TM; ++r) a[r] = a_nxt[r];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+      for (int cc = 0; cc < T::TN; ++cc) bv[kk][cc] = b_nxt[kk][cc];
+    if (k0 + 4 < K) {
+#pragma unroll
+      for (int r = 0; r < T::TM; ++r) a_nxt[r] = ldv4(a0 + r * ld + k0 + 4);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) if (k0 + 4 + kk < K) load_cols<T::TN>(B + (k0 + 4 + kk) * ld + cg * T::TN, b_nxt[kk]);
+    }
+    block(a, bv, IntC<4>{});
   }
+  if constexpr (KT > 0) block(a_nxt, b_nxt, IntC<KT>{});   // tail block: the real k steps only
   } else {
-  BXG_PRAGMA_UNROLL(BXG_TILE_UNROLL)
-  for (int k0 = 0; k0 < W; k0 += 4) {
+  auto block = [&](int k0, auto nk) {
     F4 a[T::TM];
 #pragma unroll
     for (int r = 0; r < T::TM; ++r) a[r] = ldv4(a0 + r * ld + k0);
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
+    for (int kk = 0; kk < decltype(nk)::value; ++kk) {
       real bv[T::TN];
       load_cols<T::TN>(B + (k0 + kk) * ld + cg * T::TN, bv);
 #pragma unroll
@@ -1165,7 +1173,10 @@ BXG_HD void tile_matmul(int lane, const real* A, const real* B, int ld, real* ac
           acc2[r][cc] = __ffma2_rn(av2, make_float2(bv[2 * cc], bv[2 * cc + 1]), acc2[r][cc]);
       }
     }
-  }
+  };
+  BXG_PRAGMA_UNROLL(BXG_TILE_UNROLL)
+  for (int k0 = 0; k0 < KB; k0 += 4) block(k0, IntC<4>{});
+  if constexpr (KT > 0) block(KB, IntC<KT>{});   // tail block: the real k steps only
   }
 #pragma unroll
   for (int r = 0; r < T::TM; ++r)
@@ -1177,12 +1188,13 @@ BXG_HD void tile_matmul(int lane, const real* A, const real* B, int ld, real* ac
 #pragma unroll
     for (int cc = 0; cc < T::TN; ++cc) acc[r * T::TN + cc] = R(0.);
 #pragma unroll 1
-  for (int k0 = 0; k0 < W; k0 += 4) {
+  for (int k0 = 0; k0 < K; k0 += 4) {
     F4 a[T::TM];
 #pragma unroll
     for (int r = 0; r < T::TM; ++r) a[r] = ldv4(a0 + r * ld + k0);
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
+      if (k0 + kk >= K) break;
       real bv[T::TN];
       load_cols<T::TN>(B + (k0 + kk) * ld + cg * T::TN, bv);
 #pragma unroll
@@ -1247,6 +1259,11 @@ BXG_HD void minv_newton_schulz_tiles(X& ex, const Ctx& c, Stats* st) {
   using T = Tile<X::G, W>;
   BXG_GET_DIMS(c); real* s = c.s;
   const int n = D.nv, ld = D.nvp;
+#if defined(BXG_CONST_DIMS)
+  constexpr int K = D.nv;      // model-specialised build: the padded k steps are skipped (tile_matmul)
+#else
+  constexpr int K = W;
+#endif
   const real* M = s + D.s_M;
   real* Xa = s + D.s_Minv;
   real* Xc = Xa;                      // current estimate
@@ -1256,7 +1273,7 @@ BXG_HD void minv_newton_schulz_tiles(X& ex, const Ctx& c, Stats* st) {
   // r0 = I - M X
   ex.lanes([&](int lane) {
     real* acc = tile(lane); real ss = R(0.), mx = R(0.);
-    tile_matmul<T, W, true>(lane, M, Xc, ld, acc);
+    tile_matmul<T, W, true, K>(lane, M, Xc, ld, acc);
     residual_tile<T>(lane, n, acc, &ss, &mx);
     store_tile<T>(lane, Q, ld, acc);
     p_sum(lane) = ss; p_max(lane) = mx;
@@ -1289,11 +1306,11 @@ BXG_HD void minv_newton_schulz_tiles(X& ex, const Ctx& c, Stats* st) {
   }
   real err = R(1.);
   for (int it = 0; it < D.ns_iters; ++it) {
-    ex.lanes([&](int lane) { tile_matmul<T, W>(lane, Xc, Q, ld, tile(lane)); });   // candidate = X (I + r)
+    ex.lanes([&](int lane) { tile_matmul<T, W, false, K>(lane, Xc, Q, ld, tile(lane)); });   // candidate = X (I + r)
     ex.lanes([&](int lane) { store_tile<T>(lane, Q, ld, tile(lane)); });           // ... replaces I + r
     ex.lanes([&](int lane) {       // r' = I - M candidate
       real* acc = tile(lane); real ss = R(0.), mx = R(0.);
-      tile_matmul<T, W, true>(lane, M, Q, ld, acc);
+      tile_matmul<T, W, true, K>(lane, M, Q, ld, acc);
       residual_tile<T>(lane, n, acc, &ss, &mx);
       p_sum(lane) = ss; p_max(lane) = mx;
     });
