@@ -1475,6 +1475,7 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
       xi(lane)[r] = R(0.); yi(lane)[r] = R(0.); gi(lane)[r] = R(0.); xni(lane)[r] = R(0.); resi(lane)[r] = R(0.);
     }
   });
+  BXG_PHASE_END(st, 13);   // (tuning builds) active set + A, b built
   real t = R(1.), stepsize = R(1.), error = INFINITY;
   const real tol = R(1e-3), eps = r_eps();
   int it = 0;
@@ -1568,6 +1569,7 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
     ++it;
     st->pg_iters++;
   }
+  BXG_PHASE_END(st, 14);   // (tuning builds) FISTA iterations + line searches
   // qf_constraint = J^T x over the active rows (lanes read consecutive columns of J)
   ex.lanes([&](int lane) {
     for (int j = lane; j < nv; j += G) {

@@ -213,6 +213,10 @@ def lib() -> ctypes.CDLL:
       l.bxg_env_step.argtypes = [ctypes.c_void_p, ctypes.POINTER(EnvSpecC), ctypes.c_int64, ctypes.c_int32,
                                  ctypes.POINTER(StateC), ctypes.c_void_p, ctypes.POINTER(StateC),
                                  ctypes.POINTER(EnvIOC), ctypes.c_void_p]
+      _f, _vp = ctypes.c_float, ctypes.c_void_p
+      l.bxg_gae.argtypes = [_vp, _vp, _vp, _vp, _vp, ctypes.c_int32, ctypes.c_int64, _f, _f, _vp, _vp, _vp]
+      l.bxg_policy_act.argtypes = [_vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int64, ctypes.c_int32,
+                                   ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _f, _vp, _vp, _vp, _vp]
       if l.bxg_abi_version() != 4:
         raise RuntimeError('libbxg.so ABI version mismatch')
       _lib = l

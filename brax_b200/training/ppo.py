@@ -23,6 +23,7 @@ import torch.distributed as dist
 from torch import nn
 
 from brax_b200 import envs
+from brax_b200.training import fused
 
 
 class Agent(nn.Module):
@@ -99,6 +100,10 @@ class Agent(nn.Module):
 
   @torch.no_grad()
   def act(self, obs):
+    if obs.is_cuda and obs.dtype == torch.float32 and fused.supports(self.policy):
+      # one hand-written launch: normalise, MLP, sample, tanh (brax_b200/csrc/bxg_train.cu)
+      noise = torch.randn((obs.shape[0], self.policy[-1].out_features // 2), device=obs.device)
+      return fused.policy_act(self.policy, self.running_mean, self.running_std, obs, noise, clip=self.clip_obs)
     logits = self.policy(self.normalize(obs))
     loc, scale = self.dist_create(logits)
     pre = loc + scale * torch.randn_like(loc)
@@ -106,6 +111,13 @@ class Agent(nn.Module):
 
   @torch.no_grad()
   def gae(self, truncation, termination, reward, values, bootstrap):
+    if reward.is_cuda and reward.dtype == torch.float32:
+      return fused.gae(truncation, termination, reward, values, bootstrap, self.lambda_, self.discounting)   # one launch
+    return self.gae_reference(truncation, termination, reward, values, bootstrap)
+
+  @torch.no_grad()
+  def gae_reference(self, truncation, termination, reward, values, bootstrap):
+    """compute_gae (agents/ppo/losses.py:38-101) in framework ops: the statement the kernel is tested against."""
     mask = 1.0 - truncation
     values_t1 = torch.cat([values[1:], bootstrap[None]], 0)
     deltas = (reward + self.discounting * (1 - termination) * values_t1 - values) * mask

@@ -302,6 +302,20 @@ int bxg_env_reset(const BxgModel* model, const BxgEnvSpec* spec, int64_t n_env,
                   const float* q, const float* qd, const BxgState* out, float* obs,
                   void* stream);
 
+/* ---- the two launch-bound pieces of the PPO loop -------------------------------
+ * compute_gae (agents/ppo/losses.py:38-101) on time-major [T, B] arrays; bootstrap [B]; writes vs and advantages. */
+int bxg_gae(const float* truncation, const float* termination, const float* reward, const float* values,
+            const float* bootstrap, int32_t T, int64_t B, float lambda, float discount, float* vs, float* advantages,
+            void* stream);
+/* The policy's inference step of the rollout (training/acting.py:33-53 with agents/ppo/networks.py:66-88):
+ * normalise obs with (mean, std) (acme/running_statistics.py:303-328; clip <= 0: no clipping), MLP
+ * [obs, h1, h2, 2 act] with swish (torch Linear layout: W [out, in]), loc / scale = softplus + min_std, raw action
+ * = loc + scale * noise, action = tanh(raw).  Compiled for h1 = h2 = 64; other widths return BXG_E_UNSUPPORTED. */
+int bxg_policy_act(const float* obs, const float* mean, const float* std, float clip, const float* W1, const float* b1,
+                   const float* W2, const float* b2, const float* W3, const float* b3, const float* noise, int64_t n,
+                   int32_t obs_size, int32_t h1, int32_t h2, int32_t act_size, float min_std, float* logits, float* pre,
+                   float* action, void* stream);
+
 /* Number of kernel launches issued by this library so far in this process
  * (bench.py reports the delta over the timed region as gpu_launches). */
 int64_t bxg_launch_count(void);

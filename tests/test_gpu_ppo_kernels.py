@@ -1,0 +1,58 @@
+"""The hand-written PPO kernels (bxg_gae, bxg_policy_act) against the framework-op statements of the same functions,
+which tests/test_ppo_reference.py pins to the reference's own source."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_gae_kernel_matches_compute_gae():
+  import torch
+  from brax_b200.training import fused, ppo
+  dev = torch.device('cuda', 0)
+  g = torch.Generator(device='cpu').manual_seed(0)
+  for T, B in ((5, 2048), (1, 7), (20, 333)):
+    trunc = (torch.rand((T, B), generator=g) < 0.15).float()
+    done = torch.maximum(trunc, (torch.rand((T, B), generator=g) < 0.2).float())
+    term = done * (1 - trunc)
+    rew, val, boot = torch.randn((T, B), generator=g), torch.randn((T, B), generator=g), torch.randn((B,), generator=g)
+    a = ppo.Agent(27, 8)
+    vs_ref, adv_ref = a.gae_reference(trunc, term, rew, val, boot)
+    vs, adv = fused.gae(*(t.to(dev) for t in (trunc, term, rew, val, boot)), a.lambda_, a.discounting)
+    np.testing.assert_allclose(vs.cpu().numpy(), vs_ref.numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(adv.cpu().numpy(), adv_ref.numpy(), rtol=1e-5, atol=1e-5)
+  # the golden vectors of the reference source too
+  import os
+  from tests.conftest import ROOT
+  G = np.load(os.path.join(ROOT, 'tests', 'golden', 'ref_ppo.npz'))
+  f = lambda k: torch.as_tensor(G[k], dtype=torch.float32, device=dev)   # noqa: E731
+  vs, adv = fused.gae(f('gae_truncation'), f('gae_termination'), f('gae_rewards'), f('gae_values'), f('gae_bootstrap'), 0.95, 0.97)
+  np.testing.assert_allclose(vs.cpu().numpy(), G['gae_vs'], rtol=1e-5, atol=1e-5)
+  np.testing.assert_allclose(adv.cpu().numpy(), G['gae_advantages'], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize('obs_size,act_size', [(27, 8), (244, 17), (11, 3)])
+def test_policy_act_kernel_matches_the_framework_ops(obs_size, act_size):
+  import torch
+  from brax_b200.training import fused, ppo
+  dev = torch.device('cuda', 0)
+  torch.manual_seed(1)
+  a = ppo.Agent(obs_size, act_size).to(dev)
+  a.update_normalization(torch.randn((5, 64, obs_size), device=dev) * 3 + 1)
+  assert fused.supports(a.policy)
+  for n in (1, 63, 4096):
+    obs = torch.randn((n, obs_size), device=dev) * 3 + 1
+    noise = torch.randn((n, act_size), device=dev)
+    act, logits, pre = fused.policy_act(a.policy, a.running_mean, a.running_std, obs, noise)
+    ref_logits = a.policy(a.normalize(obs))
+    loc, scale = a.dist_create(ref_logits)
+    ref_pre = loc + scale * noise
+    np.testing.assert_allclose(logits.cpu().numpy(), ref_logits.detach().cpu().numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(pre.cpu().numpy(), ref_pre.detach().cpu().numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(act.cpu().numpy(), torch.tanh(ref_pre).detach().cpu().numpy(), rtol=1e-4, atol=1e-5)
+  # a clipped normaliser and a policy the kernel is not compiled for
+  a.clip_obs = 5.0
+  obs = torch.randn((33, obs_size), device=dev) * 30
+  act, logits, _ = fused.policy_act(a.policy, a.running_mean, a.running_std, obs, torch.zeros((33, act_size), device=dev), clip=5.0)
+  np.testing.assert_allclose(logits.cpu().numpy(), a.policy(a.normalize(obs)).detach().cpu().numpy(), rtol=1e-4, atol=1e-4)
+  assert not fused.supports(ppo.Agent(obs_size, act_size, hidden=(32, 32)).to(dev).policy)

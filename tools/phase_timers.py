@@ -13,7 +13,7 @@ import torch  # noqa: E402
 from brax_b200 import native, workloads  # noqa: E402
 
 NAMES = ['load', 'dynamics (tau, RNE)', 'constraint.force', 'integrate', 'kinematics', 'transform_com', 'mass.matrix',
-         'matrix_inv (Newton-Schulz)', 'constraint.jacobian', 'env prologue / epilogue', 'store', 'lean entry', 'CTA barrier after constraint.force']
+         'matrix_inv (Newton-Schulz)', 'constraint.jacobian', 'env prologue / epilogue', 'store', 'lean entry', 'CTA barrier after constraint.force', 'constraint.force: active set, A, b', 'constraint.force: FISTA + line search']
 
 
 def main():
