@@ -61,6 +61,9 @@
 #define BXG_PIPE16_UNROLL 1
 #endif
 // explicit software pipeline in the 6x6 tile product of the half-warp 24-wide variant (320-thread CTAs: registers to spare)
+#ifndef BXG_PIPE_3X6
+#define BXG_PIPE_3X6 false    // (with the 3x6 tiles at 96 registers the explicit pipeline costs 5 %: profiles/r01_sweep_r1i.json)
+#endif
 #ifndef BXG_PIPE_6X6
 #define BXG_PIPE_6X6 true
 #endif
@@ -1067,7 +1070,7 @@ template <int N> struct IntC { static constexpr int value = N; };
 template <int G, int W> struct Tile;
 // PIPE: request the operands of the next k-block before the FMAs of the current one, explicitly.  Pays where
 // registers allow (4x4 tiles: Ant +2.4 %); with the 3x6 tiles at 96 registers it costs 5 % (profiles/r01_sweep_r1i.json)
-template <> struct Tile<32, 24> { static constexpr int RG = 8, CG = 4, TM = 3, TN = 6; static constexpr bool PIPE = false; };
+template <> struct Tile<32, 24> { static constexpr int RG = 8, CG = 4, TM = 3, TN = 6; static constexpr bool PIPE = BXG_PIPE_3X6; };
 template <> struct Tile<16, 24> { static constexpr int RG = 4, CG = 4, TM = 6, TN = 6; static constexpr bool PIPE = BXG_PIPE_6X6; };
 template <> struct Tile<16, 16> { static constexpr int RG = 4, CG = 4, TM = 4, TN = 4; static constexpr bool PIPE = true; };
 template <> struct Tile<32, 32> { static constexpr int RG = 8, CG = 4, TM = 4, TN = 8; static constexpr bool PIPE = false; };

@@ -1,0 +1,7 @@
+mkdir -p gpurun_out
+for rep in 1 2; do for name in "$@"; do
+  lib=brax_b200/libbxg_$name.so; [ $name = main ] && lib=brax_b200/libbxg.so
+  for wl in humanoid_8192 humanoid_512k; do
+    BXG_LIB=$lib python bench.py --workload $wl --steps 10 --no-extra --no-cpu-baseline 2>> gpurun_out/ab.err | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$name', d['config']['workload'], round(d['value']))"
+  done
+done; done
