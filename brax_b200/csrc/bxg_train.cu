@@ -98,6 +98,97 @@ __global__ void __launch_bounds__(64) policy_act_kernel(const float* __restrict_
   }
 }
 
+
+// ---- PPO loss head (compute_ppo_loss, agents/ppo/losses.py:143-303, from the network outputs on) ----------------
+// pass 1: per trajectory, termination / reward scaling / compute_gae; sum and sum of squares of the advantages
+__global__ void ppo_gae_stats_kernel(const float* __restrict__ values, const float* __restrict__ reward, const float* __restrict__ done,
+                                     const float* __restrict__ trunc, int T, int64_t B, float reward_scaling, float lambda, float discount,
+                                     float* __restrict__ vs, float* __restrict__ adv, double* __restrict__ stats) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double s1 = 0.0, s2 = 0.0;
+  if (b < B) {
+    float acc = 0.f, v_next = values[(int64_t)T * B + b], vs_next = v_next;
+    for (int t = T - 1; t >= 0; --t) {
+      const int64_t i = (int64_t)t * B + b;
+      const float tr = trunc[i], mask = 1.f - tr, tm = done[i] * (1.f - tr), r = reward[i] * reward_scaling, v = values[i];
+      const float delta = (r + discount * (1.f - tm) * v_next - v) * mask;
+      acc = delta + discount * (1.f - tm) * mask * lambda * acc;
+      const float vs_t = acc + v;
+      const float a = (r + discount * (1.f - tm) * vs_next - v) * mask;
+      adv[i] = a; vs[i] = vs_t;
+      s1 += a; s2 += (double)a * a;
+      v_next = v; vs_next = vs_t;
+    }
+  }
+  for (int o = 16; o >= 1; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(stats, s1); atomicAdd(stats + 1, s2); }
+}
+
+__device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + expf(-x)); }
+
+// pass 2: one thread per (t, b): the three loss terms and their gradients wrt the policy logits and the values
+__global__ void ppo_head_kernel(const float* __restrict__ logits, const float* __restrict__ values, const float* __restrict__ beh,
+                                const float* __restrict__ pre, const float* __restrict__ noise, const float* __restrict__ vs,
+                                const float* __restrict__ adv, const double* __restrict__ stats, int T, int64_t B, int A,
+                                float eps_clip, float entropy_cost, int normalize_adv, float min_std, float* __restrict__ loss,
+                                float* __restrict__ dlogits, float* __restrict__ dvalues) {
+  const int64_t N = (int64_t)T * B;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float lp_loss = 0.f, lv_loss = 0.f, le_loss = 0.f;
+  if (i < N) {
+    const float inv_n = 1.f / (float)N;
+    float a = adv[i];
+    if (normalize_adv) {
+      const double mean = stats[0] / (double)N;
+      double var = stats[1] / (double)N - mean * mean;
+      var = var > 0.0 ? var : 0.0;
+      a = (float)(((double)a - mean) / (sqrt(var) + 1e-8));
+    }
+    // log-prob difference (the tanh log-det-jacobian of the raw action is common to both and cancels) and the entropy
+    float dl = 0.f, ent = 0.f;
+    for (int j = 0; j < A; ++j) {
+      const float mu = logits[i * 2 * A + j], raw = logits[i * 2 * A + A + j];
+      const float sg = softplus(raw) + min_std;
+      const float mub = beh[i * 2 * A + j], sgb = softplus(beh[i * 2 * A + A + j]) + min_std;
+      const float p = pre[i * A + j];
+      const float z = (p - mu) / sg, zb = (p - mub) / sgb;
+      dl += (-0.5f * z * z - logf(sg)) - (-0.5f * zb * zb - logf(sgb));
+      const float sm = mu + sg * noise[i * A + j];
+      ent += 0.5f + 0.9189385332f + logf(sg) + 2.f * (0.6931471806f - sm - softplus(-2.f * sm));
+    }
+    const float rho = expf(dl);
+    const float lo = 1.f - eps_clip, hi = 1.f + eps_clip;
+    const float rc = fminf(fmaxf(rho, lo), hi);
+    const float s1 = rho * a, s2 = rc * a;
+    lp_loss = -fminf(s1, s2) * inv_n;
+    const float in_range = (rho >= lo && rho <= hi) ? 1.f : 0.f;
+    // d(-min(s1, s2)) / d rho, torch.minimum's convention (the smaller takes the gradient, a tie splits it)
+    float dmin_drho = s1 < s2 ? a : (s1 > s2 ? a * in_range : 0.5f * a + 0.5f * a * in_range);
+    const float dlp = -dmin_drho * rho * inv_n;         // d loss / d log-prob
+    le_loss = -entropy_cost * ent * inv_n;
+    for (int j = 0; j < A; ++j) {
+      const float mu = logits[i * 2 * A + j], raw = logits[i * 2 * A + A + j];
+      const float sg = softplus(raw) + min_std;
+      const float p = pre[i * A + j], nz = noise[i * A + j];
+      const float d = p - mu;
+      const float th = tanhf(mu + sg * nz);
+      const float g_mu = dlp * (d / (sg * sg)) + (-entropy_cost * inv_n) * (-2.f * th);
+      const float g_sg = dlp * (d * d / (sg * sg * sg) - 1.f / sg) + (-entropy_cost * inv_n) * (1.f / sg - 2.f * th * nz);
+      dlogits[i * 2 * A + j] = g_mu;
+      dlogits[i * 2 * A + A + j] = g_sg * sigmoidf(raw);
+    }
+    const float ve = vs[i] - values[i];
+    lv_loss = 0.25f * ve * ve * inv_n;
+    dvalues[i] = -0.5f * ve * inv_n;
+  } else if (i < N + B) {
+    dvalues[i] = 0.f;                                   // the bootstrap value enters through stop_gradient only
+  }
+  for (int o = 16; o >= 1; o >>= 1) {
+    lp_loss += __shfl_xor_sync(0xffffffffu, lp_loss, o); lv_loss += __shfl_xor_sync(0xffffffffu, lv_loss, o); le_loss += __shfl_xor_sync(0xffffffffu, le_loss, o);
+  }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(loss + 1, lp_loss); atomicAdd(loss + 2, lv_loss); atomicAdd(loss + 3, le_loss); atomicAdd(loss, lp_loss + lv_loss + le_loss); }
+}
+
 }  // namespace
 
 extern "C" {
@@ -127,6 +218,25 @@ int bxg_policy_act(const float* obs, const float* mean, const float* std, float 
   const int threads = 64;
   policy_act_kernel<64, 64><<<(unsigned)((n + threads - 1) / threads), threads, smem, (cudaStream_t)stream>>>(
       obs, mean, std, clip, W1, b1, W2, b2, W3, b3, noise, n, obs_size, act_size, min_std, logits, pre, action);
+  return cudaGetLastError() == cudaSuccess ? BXG_OK : BXG_E_CUDA;
+}
+
+int bxg_ppo_head(const float* logits, const float* values, const float* behaviour_logits, const float* raw_action,
+                 const float* reward, const float* done, const float* truncation, const float* entropy_noise, int32_t T, int64_t B,
+                 int32_t act_size, float reward_scaling, float lambda, float discount, float clip_epsilon, float entropy_cost,
+                 int32_t normalize_advantage, float min_std, float* vs_scratch, float* adv_scratch, double* stats_scratch,
+                 float* loss4, float* dlogits, float* dvalues, void* stream) {
+  if (!logits || !values || !behaviour_logits || !raw_action || !reward || !done || !truncation || !entropy_noise || !vs_scratch ||
+      !adv_scratch || !stats_scratch || !loss4 || !dlogits || !dvalues || T < 1 || B < 1 || act_size < 1) return BXG_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(stats_scratch, 0, 2 * sizeof(double), st) != cudaSuccess || cudaMemsetAsync(loss4, 0, 4 * sizeof(float), st) != cudaSuccess) return BXG_E_CUDA;
+  const int threads = 128;
+  ppo_gae_stats_kernel<<<(unsigned)((B + threads - 1) / threads), threads, 0, st>>>(values, reward, done, truncation, T, B, reward_scaling, lambda,
+                                                                                   discount, vs_scratch, adv_scratch, stats_scratch);
+  const int64_t n = (int64_t)T * B + B;
+  ppo_head_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(logits, values, behaviour_logits, raw_action, entropy_noise, vs_scratch,
+                                                                              adv_scratch, stats_scratch, T, B, act_size, clip_epsilon, entropy_cost,
+                                                                              normalize_advantage, min_std, loss4, dlogits, dvalues);
   return cudaGetLastError() == cudaSuccess ? BXG_OK : BXG_E_CUDA;
 }
 

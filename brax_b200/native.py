@@ -217,6 +217,7 @@ def lib() -> ctypes.CDLL:
       l.bxg_gae.argtypes = [_vp, _vp, _vp, _vp, _vp, ctypes.c_int32, ctypes.c_int64, _f, _f, _vp, _vp, _vp]
       l.bxg_policy_act.argtypes = [_vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int64, ctypes.c_int32,
                                    ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _f, _vp, _vp, _vp, _vp]
+      l.bxg_ppo_head.argtypes = [_vp] * 8 + [ctypes.c_int32, ctypes.c_int64, ctypes.c_int32, _f, _f, _f, _f, _f, ctypes.c_int32, _f] + [_vp] * 7
       if l.bxg_abi_version() != 4:
         raise RuntimeError('libbxg.so ABI version mismatch')
       _lib = l

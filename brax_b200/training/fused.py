@@ -50,3 +50,38 @@ def policy_act(policy: torch.nn.Sequential, mean, std, obs, noise, clip=None, mi
         _ptr(l2.bias), _ptr(l3.weight), _ptr(l3.bias), _ptr(noise.contiguous()), n, no, l1.out_features, l2.out_features, na,
         float(min_std), _ptr(logits), _ptr(pre), _ptr(action), stream), 'bxg_policy_act')
   return action, logits, pre
+
+
+class _PPOHead(torch.autograd.Function):
+  """compute_ppo_loss from the network outputs on, forward and backward in two hand-written launches
+  (bxg_ppo_head).  The gradient wrt the logits and the values is produced in the forward pass."""
+
+  @staticmethod
+  def forward(ctx, logits, values, beh_logits, pre, reward, done, trunc, noise, cfg):
+    T, B, A2 = logits.shape
+    dev = logits.device
+    args = [t.contiguous() for t in (logits, values, beh_logits, pre, reward, done, trunc, noise)]
+    vs, adv = torch.empty((T, B), device=dev), torch.empty((T, B), device=dev)
+    stats = torch.empty(2, dtype=torch.float64, device=dev)
+    loss4 = torch.empty(4, device=dev)
+    dlogits, dvalues = torch.empty_like(args[0]), torch.empty_like(args[1])
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+      native._check(native.lib().bxg_ppo_head(
+          *[_ptr(t) for t in args], T, B, A2 // 2, float(cfg['reward_scaling']), float(cfg['lambda_']), float(cfg['discounting']),
+          float(cfg['epsilon']), float(cfg['entropy_cost']), int(bool(cfg['normalize_advantage'])), float(cfg.get('min_std', 0.001)),
+          _ptr(vs), _ptr(adv), stats.data_ptr(), _ptr(loss4), _ptr(dlogits), _ptr(dvalues), stream), 'bxg_ppo_head')
+    ctx.save_for_backward(dlogits, dvalues)
+    ctx.mark_non_differentiable()
+    return loss4
+
+  @staticmethod
+  def backward(ctx, g):
+    dlogits, dvalues = ctx.saved_tensors
+    # loss4 = (total, policy, value, entropy): the gradients stored are those of the total
+    return g[0] * dlogits, g[0] * dvalues, None, None, None, None, None, None, None
+
+
+def ppo_head(logits, values, beh_logits, pre, reward, done, trunc, noise, **cfg):
+  """-> tensor [total, policy_loss, v_loss, entropy_loss]; differentiate `[0]` (the total)."""
+  return _PPOHead.apply(logits, values, beh_logits, pre, reward, done, trunc, noise, cfg)

@@ -46,6 +46,7 @@ class Agent(nn.Module):
     self.lambda_, self.epsilon = lambda_, epsilon
     self.normalize_advantage = normalize_advantage
     self.clip_obs = clip_obs
+    self.fused_head = True      # CUDA float32: the loss head runs as bxg_ppo_head (the framework-op statement below otherwise)
 
   @torch.no_grad()
   def update_normalization(self, obs, group=None):
@@ -136,6 +137,13 @@ class Agent(nn.Module):
     obs = self.normalize(td['obs'])                       # [T+1, B, obs]
     values = self.value(obs).squeeze(-1)
     logits = self.policy(obs[:-1])
+    if self.fused_head and logits.is_cuda and logits.dtype == torch.float32:
+      # everything from the network outputs on, forward and backward, in two hand-written launches (bxg_ppo_head)
+      noise = torch.randn_like(td['pre']) if entropy_noise is None else entropy_noise
+      l4 = fused.ppo_head(logits, values, td['logits'], td['pre'], td['reward'], td['done'], td['truncation'], noise,
+                          reward_scaling=self.reward_scaling, lambda_=self.lambda_, discounting=self.discounting, epsilon=self.epsilon,
+                          entropy_cost=self.entropy_cost, normalize_advantage=self.normalize_advantage)
+      return (l4[0], l4[1], l4[2], l4[3]) if parts else l4[0]
     loc, scale = self.dist_create(logits)
     beh_loc, beh_scale = self.dist_create(td['logits'])
     lp = self.dist_log_prob(loc, scale, td['pre'])

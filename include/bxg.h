@@ -316,6 +316,16 @@ int bxg_policy_act(const float* obs, const float* mean, const float* std, float 
                    int32_t obs_size, int32_t h1, int32_t h2, int32_t act_size, float min_std, float* logits, float* pre,
                    float* action, void* stream);
 
+/* compute_ppo_loss from the network outputs on (agents/ppo/losses.py:186-303): termination, reward scaling,
+ * compute_gae, advantage normalisation, tanh-normal log-probs, clipped surrogate, value loss (x 0.5 x vf 0.5), sampled
+ * entropy -- and the gradients of the total loss wrt the policy logits [T, B, 2 act] and the values [T + 1, B]
+ * (row T is the bootstrap value: zero gradient), in two launches.  loss4 = (total, policy, value, entropy). */
+int bxg_ppo_head(const float* logits, const float* values, const float* behaviour_logits, const float* raw_action,
+                 const float* reward, const float* done, const float* truncation, const float* entropy_noise, int32_t T, int64_t B,
+                 int32_t act_size, float reward_scaling, float lambda, float discount, float clip_epsilon, float entropy_cost,
+                 int32_t normalize_advantage, float min_std, float* vs_scratch, float* adv_scratch, double* stats_scratch,
+                 float* loss4, float* dlogits, float* dvalues, void* stream);
+
 /* Number of kernel launches issued by this library so far in this process
  * (bench.py reports the delta over the timed region as gpu_launches). */
 int64_t bxg_launch_count(void);

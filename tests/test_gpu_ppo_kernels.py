@@ -56,3 +56,37 @@ def test_policy_act_kernel_matches_the_framework_ops(obs_size, act_size):
   act, logits, _ = fused.policy_act(a.policy, a.running_mean, a.running_std, obs, torch.zeros((33, act_size), device=dev), clip=5.0)
   np.testing.assert_allclose(logits.cpu().numpy(), a.policy(a.normalize(obs)).detach().cpu().numpy(), rtol=1e-4, atol=1e-4)
   assert not fused.supports(ppo.Agent(obs_size, act_size, hidden=(32, 32)).to(dev).policy)
+
+
+@pytest.mark.parametrize('normalize_advantage', [True, False])
+def test_ppo_head_kernel_matches_the_framework_loss_and_its_autograd_gradients(normalize_advantage):
+  """bxg_ppo_head against Agent.loss in framework ops (which tests/test_ppo_reference.py pins to compute_ppo_loss run
+  from the reference source): loss terms and the gradient of every network parameter."""
+  import torch
+  from brax_b200.training import ppo
+  dev = torch.device('cuda', 0)
+  torch.manual_seed(3)
+  T, B, OBS, ACT = 5, 1536, 27, 8
+  a = ppo.Agent(OBS, ACT, normalize_advantage=normalize_advantage).to(dev)
+  a.update_normalization(torch.randn((T, B, OBS), device=dev) * 2 + 1)
+  obs = torch.randn((T + 1, B, OBS), device=dev) * 2 + 1
+  with torch.no_grad():
+    beh = a.policy(a.normalize(obs[:-1])) + 0.05 * torch.randn((T, B, 2 * ACT), device=dev)
+    loc, scale = a.dist_create(beh)
+    pre = loc + scale * torch.randn_like(loc)
+  trunc = (torch.rand((T, B), device=dev) < 0.15).float()
+  done = torch.maximum(trunc, (torch.rand((T, B), device=dev) < 0.2).float())
+  td = {'obs': obs, 'logits': beh, 'pre': pre, 'reward': torch.randn((T, B), device=dev), 'done': done, 'truncation': trunc}
+  noise = torch.randn((T, B, ACT), device=dev)
+  res = {}
+  for fused_head in (False, True):
+    a.fused_head = fused_head
+    a.zero_grad(set_to_none=True)
+    parts = a.loss(td, entropy_noise=noise, parts=True)
+    parts[0].backward()
+    res[fused_head] = ([float(p.detach()) for p in parts], [p.grad.detach().clone() for p in a.parameters()])
+  for x, y in zip(*[res[k][0] for k in (False, True)]):
+    assert abs(x - y) <= 2e-5 * max(1.0, abs(x)), (res[False][0], res[True][0])
+  for gx, gy in zip(res[False][1], res[True][1]):
+    scale = float(gx.abs().max()) + 1e-12
+    assert float((gx - gy).abs().max()) <= 2e-4 * scale + 1e-7, (float((gx - gy).abs().max()), scale)
