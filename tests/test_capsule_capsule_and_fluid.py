@@ -152,3 +152,24 @@ def test_kernel_source_matches_oracle(model):
   x, y = sim.step(sim.init(q, qd), z, 3), r.step(r.init(q, qd), z, 3)
   for f in O.STATE_FIELDS:
     assert np.array_equal(x[f], y[f]), f
+
+
+def test_plan_for_a_model_with_fluid_forces_and_two_body_contacts():
+  """Variant selection (bxg_model.h): a model needing BOTH optional code paths goes to the generic variant, which
+  carries both, instead of being rejected; a forced variant lacking one of them is still an error."""
+  import ctypes
+  import numpy as np
+  from brax_b200 import envs_assets, native
+  pusher = envs_assets.load('pusher')                       # capsule-capsule contacts between moving links
+  assert native.plan(pusher)['variant'] == 5
+  both = pusher.replace(enable_fluid=True, viscosity=np.float32(0.1), density=np.float32(1.2))
+  p = native.plan(both)
+  assert p['variant'] == 3 and p['kernel_id'] == 3          # the generic any-size kernel: fluid + two-body rows
+  swimmer = envs_assets.load('swimmer')                     # fluid only: the small 8-wide variant
+  assert native.plan(swimmer)['variant'] == 8
+  # the host emulator runs it (same selection code), finite results
+  from tests.simt.sim import Sim
+  sim = Sim(both)
+  q = np.asarray(both.init_q, np.float32)[None].repeat(2, 0); qd = np.full((2, both.nv), 0.1, np.float32)
+  st = sim.step(sim.init(q, qd), np.zeros((2, both.nu), np.float32), 2)
+  assert all(np.isfinite(v).all() for v in st.values())

@@ -147,3 +147,33 @@ def test_action_repeat_is_the_episode_wrappers_scan():
   # third call: steps = 6 >= episode_length = 5 -> truncated, state snaps back to the first state
   assert (sa.done[ok] == 1).all() and (sa.info['truncation'][ok] == (1 - sb.done)[ok]).all() and (sa.info['steps'][ok] == 6).all()
   assert torch.equal(sa.obs[ok], sa.info['first_obs'][ok])
+
+
+@pytest.mark.parametrize('name', ['ant', 'hopper'])
+def test_episode_metrics_follow_the_episode_wrapper(name):
+  """info['episode_done'] / info['episode_metrics'] as EpisodeWrapper maintains them (wrappers/training.py:83-127):
+  sums restart after an episode that ended, `length` counts steps, every env metric is accumulated."""
+  import torch
+  from brax_b200 import envs
+  n, ep_len = 32, 3
+  env = envs.create(name, episode_length=ep_len, auto_reset=True, batch_size=n)
+  st = env.reset(1)
+  em = st.info['episode_metrics']
+  assert set(em) == {'sum_reward', 'length', *env.metric_names} and float(st.info['episode_done'].sum()) == 0
+  exp = {k: np.zeros(n) for k in em}
+  prev_done = np.zeros(n)
+  gen = torch.Generator(device='cpu').manual_seed(0)
+  for k in range(8):
+    act = (torch.rand((n, env.action_size), generator=gen) * 2 - 1).to(st.obs.device)
+    st = env.step(st, act)
+    keep = 1.0 - prev_done
+    exp['sum_reward'] = exp['sum_reward'] * keep + st.reward.cpu().numpy()
+    exp['length'] = exp['length'] * keep + 1
+    for m in env.metric_names:
+      if m != 'reward':
+        exp[m] = exp[m] * keep + st.metrics[m].cpu().numpy()
+    prev_done = st.done.cpu().numpy()
+    for m, v in exp.items():
+      np.testing.assert_allclose(st.info['episode_metrics'][m].cpu().numpy(), v, rtol=1e-5, atol=1e-5, err_msg=f'{name} step {k} {m}')
+    np.testing.assert_array_equal(st.info['episode_done'].cpu().numpy(), prev_done)
+  assert float(st.info['episode_metrics']['length'].max()) <= ep_len

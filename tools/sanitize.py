@@ -43,3 +43,32 @@ for model in ('swimmer', 'pusher', 'humanoidstandup', 'reacher', 'inverted_pendu
   torch.cuda.synchronize()
   assert torch.isfinite(es.obs).all() and torch.isfinite(es.pipeline_state.q).all(), model
 print('sanitize rollout ok')
+# round 2: lean state I/O (separate kernels), the model-specialised kernels (ids 10 / 11: Ant and Humanoid above run on
+# them; BXG_NO_SPECIALISE covers their generic twins) and the PPO kernels
+from brax_b200 import native
+from brax_b200.training import fused, ppo
+for model in ('ant', 'humanoid'):
+  env = envs.create(model, episode_length=2, auto_reset=True, batch_size=19, lean=True)
+  es = env.reset(0)
+  for k in range(3):
+    es = env.step(es, torch.zeros((19, env.action_size), device=dev))
+  torch.cuda.synchronize()
+  assert torch.isfinite(es.obs).all()
+os.environ['BXG_NO_SPECIALISE'] = '1'
+for model in ('ant', 'humanoid'):
+  sys_, q, qd = workloads.reset(model, 0, 37, 0, dev)
+  nm = native.NativeModel(sys_, 0)
+  assert nm.kernel_id == native.plan(sys_)['variant']
+  st = nm.init(q, qd)
+  st = nm.step(st, workloads.action(model, 0, 37, 0, 0, dev), 5)
+  torch.cuda.synchronize()
+  assert torch.isfinite(st['q']).all()
+del os.environ['BXG_NO_SPECIALISE']
+a = ppo.Agent(27, 8).to(dev)
+act, logits, pre = a.act(torch.randn((77, 27), device=dev))
+T, B = 5, 130
+td = {'obs': torch.randn((T + 1, B, 27), device=dev), 'logits': torch.randn((T, B, 16), device=dev), 'pre': torch.randn((T, B, 8), device=dev),
+      'reward': torch.randn((T, B), device=dev), 'done': torch.zeros((T, B), device=dev), 'truncation': torch.zeros((T, B), device=dev)}
+a.loss(td).backward()
+torch.cuda.synchronize()
+print('sanitize: done')
