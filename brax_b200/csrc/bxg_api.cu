@@ -111,7 +111,7 @@ bool state_ok_lean(const BxgState* s) {
 // solver settings are IDENTICAL to the ones that build was compiled for.  Any other model keeps the generic kernel.
 int specialised_kernel_id(const bxg::PackedModel& pm) {
   if (getenv("BXG_NO_SPECIALISE")) return pm.variant_id;
-  auto same = [&](bxg::Dims c) { c.minv_mode = pm.d.minv_mode; return memcmp(&c, &pm.d, sizeof c) == 0; };
+  auto same = [&](bxg::Dims c) { c.minv_mode = pm.d.minv_mode; c.phase_groups = pm.d.phase_groups; return memcmp(&c, &pm.d, sizeof c) == 0; };   // (phase_groups: a tuning value of the build)
   if (pm.variant_id == 0 && same(bxg::const_dims_ant())) return 10;
   if (pm.variant_id == 1 && same(bxg::const_dims_humanoid())) return 11;
   return pm.variant_id;

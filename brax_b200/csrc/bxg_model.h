@@ -89,6 +89,9 @@ struct Dims {
 #ifndef BXG_DEFAULT_SYNC_LEVEL
 #define BXG_DEFAULT_SYNC_LEVEL 1   // one CTA-wide phase alignment per substep, behind constraint.force (Dims::sync_level)
 #endif
+#ifndef BXG_DEFAULT_PHASE_GROUPS
+#define BXG_DEFAULT_PHASE_GROUPS 1 // the warps of a CTA align their phases in this many independent groups (Dims::phase_groups)
+#endif
 #ifndef BXG_KIN_REGS
 #define BXG_KIN_REGS 0
 #endif
@@ -269,7 +272,7 @@ inline std::string pack_model_t(const BxgModelDesc& m, PackedModelT<R>* out, int
   d.max_depth = 0;
   for (int l = 0; l < L; ++l) d.max_depth = depth[l] > d.max_depth ? depth[l] : d.max_depth;
   d.solver_iterations = m.solver_iterations; d.solver_maxls = m.solver_maxls;
-  d.ns_iters = m.matrix_inv_iterations; d.minv_mode = m.minv_mode; d.force_generic = 0; d.sync_level = BXG_DEFAULT_SYNC_LEVEL; d.phase_groups = 1;
+  d.ns_iters = m.matrix_inv_iterations; d.minv_mode = m.minv_mode; d.force_generic = 0; d.sync_level = BXG_DEFAULT_SYNC_LEVEL; d.phase_groups = BXG_DEFAULT_PHASE_GROUPS;
   d.dt = m.dt; d.gx = m.gravity[0]; d.gy = m.gravity[1]; d.gz = m.gravity[2];
 
   auto put_i = [&](const std::vector<int>& v) { int o = (int)b.size(); for (int x : v) { b.push_back((uint32_t)x); if (kWide) br.push_back(R(0)); } return o; };

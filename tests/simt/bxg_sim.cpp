@@ -166,9 +166,10 @@ extern "C" {
 int sim_sizeof_real() { return (int)sizeof(real); }
 // The packed Dims of a model as a C++ aggregate initializer (bxg_model.h field order): input of
 // tools/gen_const_dims.py, which writes the headers the model-specialised kernel variants are compiled with.
-int sim_dims_initializer(const BxgModelDesc* desc, int variant, char* buf, int cap) {
+int sim_dims_initializer(const BxgModelDesc* desc, int variant, int phase_groups, char* buf, int cap) {
   bxg::PackedModel pm;
   if (!bxg::pack_model(*desc, &pm, variant).empty()) return -1;
+  if (phase_groups > 0) pm.d.phase_groups = phase_groups;   // a tuning value of the specialised build, not part of the model's layout
   static_assert(sizeof(bxg::Dims) % 4 == 0, "Dims is a sequence of 4-byte fields");
   const size_t f0 = offsetof(bxg::Dims, dt) / 4, f1 = offsetof(bxg::Dims, gz) / 4;
   const uint32_t* w = reinterpret_cast<const uint32_t*>(&pm.d);
