@@ -6,6 +6,18 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _exact_fp32_framework_gemms():
+  """The trainer switches the framework's GEMMs to TF32 (ppo.train); the statements these kernels are compared with
+  must run in plain float32."""
+  import torch
+  old = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+  torch.backends.cuda.matmul.allow_tf32 = False
+  torch.backends.cudnn.allow_tf32 = False
+  yield
+  torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
 def test_gae_kernel_matches_compute_gae():
   import torch
   from brax_b200.training import fused, ppo
