@@ -52,6 +52,47 @@ def tree_leaves(tree) -> List[Any]:
   return out
 
 
+def unbatch(tree_v, in_axes) -> list:
+  """The n unbatched trees a batched tree stands for: leaf i of result e is `leaf[e]` where `in_axes` holds 0 and the
+  shared leaf where it holds None.  This is what `jax.vmap(f, in_axes=[in_axes, ...])(tree_v, ...)` hands to `f` for
+  env e (reference envs/wrappers/training.py:223-260: a System with domain-randomised leaves).  `in_axes` has the
+  structure of `tree_v`; a None at a node stands for None at every leaf below it."""
+  sizes = set()
+
+  def scan(t, ax):
+    if t is None or ax is None:
+      return
+    if _is_node(t):
+      for f in dataclasses.fields(t):
+        if not f.metadata.get('static', False):
+          scan(getattr(t, f.name), getattr(ax, f.name) if _is_node(ax) else ax)
+    elif isinstance(t, (tuple, list)):
+      for i, v in enumerate(t):
+        scan(v, ax[i] if isinstance(ax, (tuple, list)) else ax)
+    else:
+      if ax != 0:
+        raise NotImplementedError(f'in_axes entries must be 0 or None, got {ax!r}')
+      sizes.add(int(np.shape(t)[0]))
+  scan(tree_v, in_axes)
+  if len(sizes) != 1:
+    raise ValueError(f'batched leaves must share one leading size, got {sorted(sizes)}')
+  n = sizes.pop()
+
+  def pick(t, ax, e):
+    if t is None or ax is None:
+      return t
+    if _is_node(t):
+      kw = {}
+      for f in dataclasses.fields(t):
+        v = getattr(t, f.name)
+        kw[f.name] = v if f.metadata.get('static', False) else pick(v, getattr(ax, f.name) if _is_node(ax) else ax, e)
+      return type(t)(**kw)
+    if isinstance(t, (tuple, list)):
+      return type(t)(pick(v, ax[i] if isinstance(ax, (tuple, list)) else ax, e) for i, v in enumerate(t))
+    return t[e]
+  return [pick(tree_v, in_axes, e) for e in range(n)]
+
+
 def static(default=dataclasses.MISSING, **kw):
   if default is dataclasses.MISSING:
     return dataclasses.field(metadata={'static': True}, **kw)

@@ -40,6 +40,22 @@ extern "C" {
 const void* bxg_step_lean_kernel_v0(); const void* bxg_step_lean_kernel_v1(); const void* bxg_step_lean_kernel_v2(); const void* bxg_step_lean_kernel_v3(); const void* bxg_step_lean_kernel_v4(); const void* bxg_step_lean_kernel_v5(); const void* bxg_step_lean_kernel_v6(); const void* bxg_step_lean_kernel_v7(); const void* bxg_step_lean_kernel_v8(); const void* bxg_step_lean_kernel_v9(); const void* bxg_step_lean_kernel_v10(); const void* bxg_step_lean_kernel_v11();
 const void* bxg_step_chol_lean_kernel_v0(); const void* bxg_step_chol_lean_kernel_v1(); const void* bxg_step_chol_lean_kernel_v2(); const void* bxg_step_chol_lean_kernel_v3(); const void* bxg_step_chol_lean_kernel_v4(); const void* bxg_step_chol_lean_kernel_v5(); const void* bxg_step_chol_lean_kernel_v6(); const void* bxg_step_chol_lean_kernel_v7(); const void* bxg_step_chol_lean_kernel_v8(); const void* bxg_step_chol_lean_kernel_v9(); const void* bxg_step_chol_lean_kernel_v10(); const void* bxg_step_chol_lean_kernel_v11();
 }
+extern "C" {
+const void* bxg_step_perenv_kernel_v0(); const void* bxg_step_perenv_kernel_v1(); const void* bxg_step_perenv_kernel_v3();
+const void* bxg_step_perenv_lean_kernel_v0(); const void* bxg_step_perenv_lean_kernel_v1(); const void* bxg_step_perenv_lean_kernel_v3();
+const void* bxg_init_perenv_kernel_v0(); const void* bxg_init_perenv_kernel_v1(); const void* bxg_init_perenv_kernel_v3();
+}
+// per-env models run on variants 0, 1 and 3 (bxg_inst.cu)
+static const void* step_perenv_kernel_of(int v, bool lean) {
+  switch (v) {
+    case 0: return lean ? bxg_step_perenv_lean_kernel_v0() : bxg_step_perenv_kernel_v0();
+    case 1: return lean ? bxg_step_perenv_lean_kernel_v1() : bxg_step_perenv_kernel_v1();
+    default: return lean ? bxg_step_perenv_lean_kernel_v3() : bxg_step_perenv_kernel_v3();
+  }
+}
+static const void* init_perenv_kernel_of(int v) {
+  switch (v) { case 0: return bxg_init_perenv_kernel_v0(); case 1: return bxg_init_perenv_kernel_v1(); default: return bxg_init_perenv_kernel_v3(); }
+}
 static const void* step_lean_kernel_of(int v, bool chol) {
   switch (v) {
     case 0: return chol ? bxg_step_chol_lean_kernel_v0() : bxg_step_lean_kernel_v0();
@@ -76,6 +92,7 @@ struct BxgModel {
   int groups = 0;          // envs per CTA
   int threads = 0;         // CTA size
   uint32_t* d_blob = nullptr;
+  int64_t n_models = 0;    // 0: one model for every env; n: env e of an n-env batch reads row e of d_blob ([n][model_words])
   size_t smem_bytes = 0;
   int blocks_per_sm_step = 1, blocks_per_sm_init = 1;
 };
@@ -134,18 +151,8 @@ int bxg_abi_version(void) { return BXG_ABI_VERSION; }
 const char* bxg_last_error(void) { return g_err.c_str(); }
 int64_t bxg_launch_count(void) { return g_launches.load(); }
 
-int bxg_model_create(const BxgModelDesc* desc, int device, BxgModel** out) {
-  if (!desc || !out) return fail(BXG_E_INVALID, "null argument");
-  *out = nullptr;
-  BxgModel* m = new BxgModel();
-  int force_variant = -1;
-  if (const char* fv = getenv("BXG_FORCE_VARIANT")) force_variant = atoi(fv);   // tuning knob (e.g. 4: Humanoid class on half-warps)
-  std::string err = bxg::pack_model(*desc, &m->pm, force_variant);
-  if (!err.empty()) { delete m; return fail(BXG_E_UNSUPPORTED, err); }
-  m->kernel_id = force_variant >= 0 ? m->pm.variant_id : specialised_kernel_id(m->pm);   // (before the tuning knobs below change Dims)
-  if (getenv("BXG_SYNC_LEVEL") || getenv("BXG_PHASE_GROUPS")) m->kernel_id = m->pm.variant_id;
-  if (const char* sl = getenv("BXG_SYNC_LEVEL")) m->pm.d.sync_level = atoi(sl);   // tuning knobs
-  if (const char* pg = getenv("BXG_PHASE_GROUPS")) m->pm.d.phase_groups = atoi(pg);
+// device side of model creation: upload `blob` (one model, or n_models of them back to back) and configure the kernels
+static int model_upload(BxgModel* m, int device, const std::vector<uint32_t>& blob) {
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
   if (ce != cudaSuccess || ndev == 0) { delete m; return fail(BXG_E_CUDA, "no CUDA device: this library has no CPU fallback"); }
@@ -167,14 +174,15 @@ int bxg_model_create(const BxgModelDesc* desc, int device, BxgModel** out) {
   m->smem_bytes = sizeof(uint32_t) * ((size_t)D.model_words + (size_t)groups * D.env_words);
   if (m->smem_bytes > (size_t)prop.sharedMemPerBlockOptin)
     return cleanup(fail(BXG_E_UNSUPPORTED, "model needs more shared memory per CTA than the device offers"));
-  if ((ce = cudaMalloc(&m->d_blob, m->pm.blob.size() * sizeof(uint32_t))) != cudaSuccess) return cleanup(cuda_fail(ce, "cudaMalloc(model)"));
-  if ((ce = cudaMemcpy(m->d_blob, m->pm.blob.data(), m->pm.blob.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess)
+  if ((ce = cudaMalloc(&m->d_blob, blob.size() * sizeof(uint32_t))) != cudaSuccess) return cleanup(cuda_fail(ce, "cudaMalloc(model)"));
+  if ((ce = cudaMemcpy(m->d_blob, blob.data(), blob.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess)
     return cleanup(cuda_fail(ce, "cudaMemcpy(model)"));
   // the attribute is per function (shared by every model of this variant): always
   // raise it to the device maximum, never to this model's own size
-  const void* ks = m->pm.d.minv_mode == BXG_MINV_CHOLESKY ? step_chol_kernel_of(m->kernel_id) : step_kernel_of(m->kernel_id);
-  const void* ki = init_kernel_of(m->kernel_id);
-  const void* kl = step_lean_kernel_of(m->kernel_id, m->pm.d.minv_mode == BXG_MINV_CHOLESKY);
+  const bool chol = m->pm.d.minv_mode == BXG_MINV_CHOLESKY;
+  const void* ks = m->n_models ? step_perenv_kernel_of(m->kernel_id, false) : (chol ? step_chol_kernel_of(m->kernel_id) : step_kernel_of(m->kernel_id));
+  const void* ki = m->n_models ? init_perenv_kernel_of(m->kernel_id) : init_kernel_of(m->kernel_id);
+  const void* kl = m->n_models ? step_perenv_kernel_of(m->kernel_id, true) : step_lean_kernel_of(m->kernel_id, chol);
   // (dynamic + the kernel's few bytes of static shared memory must fit the opt-in limit)
   for (const void* k : {ks, ki, kl}) {
     cudaFuncAttributes fa;
@@ -187,6 +195,55 @@ int bxg_model_create(const BxgModelDesc* desc, int device, BxgModel** out) {
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m->blocks_per_sm_init, ki, m->threads, m->smem_bytes);
   if (m->blocks_per_sm_step < 1 || m->blocks_per_sm_init < 1) return cleanup(fail(BXG_E_UNSUPPORTED, "kernel does not fit on an SM"));
   cudaSetDevice(prev);
+  return BXG_OK;
+}
+
+int bxg_model_create(const BxgModelDesc* desc, int device, BxgModel** out) {
+  if (!desc || !out) return fail(BXG_E_INVALID, "null argument");
+  *out = nullptr;
+  BxgModel* m = new BxgModel();
+  int force_variant = -1;
+  if (const char* fv = getenv("BXG_FORCE_VARIANT")) force_variant = atoi(fv);   // tuning knob (e.g. 4: Humanoid class on half-warps)
+  std::string err = bxg::pack_model(*desc, &m->pm, force_variant);
+  if (!err.empty()) { delete m; return fail(BXG_E_UNSUPPORTED, err); }
+  m->kernel_id = force_variant >= 0 ? m->pm.variant_id : specialised_kernel_id(m->pm);   // (before the tuning knobs below change Dims)
+  if (getenv("BXG_SYNC_LEVEL") || getenv("BXG_PHASE_GROUPS")) m->kernel_id = m->pm.variant_id;
+  if (const char* sl = getenv("BXG_SYNC_LEVEL")) m->pm.d.sync_level = atoi(sl);   // tuning knobs
+  if (const char* pg = getenv("BXG_PHASE_GROUPS")) m->pm.d.phase_groups = atoi(pg);
+  int rc = model_upload(m, device, m->pm.blob);
+  if (rc != BXG_OK) return rc;
+  *out = m;
+  return BXG_OK;
+}
+
+// n models of ONE topology (same links, dofs, actuators, contact pairs, solver settings), different constants: env e of
+// every n-env batch uses descs[e].  The packed layout (Dims) depends on the topology only and must come out identical.
+int bxg_model_create_batched(const BxgModelDesc* descs, int64_t n, int device, BxgModel** out) {
+  if (!descs || !out || n < 1) return fail(BXG_E_INVALID, "null argument or n < 1");
+  *out = nullptr;
+  if (descs[0].minv_mode == BXG_MINV_CHOLESKY) return fail(BXG_E_UNSUPPORTED, "per-env models run the reference's Newton-Schulz mode only");
+  BxgModel* m = new BxgModel();
+  // the variant the nominal model gets, if it carries the per-env kernels (0, 1, 3), else the generic one
+  std::string err = bxg::pack_model(descs[0], &m->pm, -1);
+  if (err.empty() && m->pm.variant_id != 0 && m->pm.variant_id != 1 && m->pm.variant_id != 3) err = bxg::pack_model(descs[0], &m->pm, 3);
+  if (!err.empty()) { delete m; return fail(BXG_E_UNSUPPORTED, err); }
+  const int vid = m->pm.variant_id;
+  m->kernel_id = vid; m->n_models = n;
+  const size_t words = m->pm.blob.size();
+  std::vector<uint32_t> all(words * (size_t)n);
+  memcpy(all.data(), m->pm.blob.data(), words * sizeof(uint32_t));
+  bxg::PackedModel pe{};
+  for (int64_t e = 1; e < n; ++e) {
+    err = bxg::pack_model(descs[e], &pe, vid);
+    if (!err.empty()) { delete m; return fail(BXG_E_UNSUPPORTED, "model " + std::to_string(e) + ": " + err); }
+    if (memcmp(&pe.d, &m->pm.d, sizeof(bxg::Dims)) != 0 || pe.blob.size() != words) {
+      delete m;
+      return fail(BXG_E_UNSUPPORTED, "model " + std::to_string(e) + " differs from model 0 in topology, sizes, time step, gravity or solver settings: only constants stored in the model blob may vary per env");
+    }
+    memcpy(all.data() + words * (size_t)e, pe.blob.data(), words * sizeof(uint32_t));
+  }
+  int rc = model_upload(m, device, all);
+  if (rc != BXG_OK) return rc;
   *out = m;
   return BXG_OK;
 }
@@ -205,6 +262,7 @@ void bxg_model_destroy(BxgModel* m) {
 
 int bxg_model_num_constraints(const BxgModel* m) { return m ? m->pm.d.nc : -1; }
 int bxg_model_kernel_id(const BxgModel* m) { return m ? m->kernel_id : -1; }
+int64_t bxg_model_num_models(const BxgModel* m) { return m ? m->n_models : -1; }
 
 int bxg_plan(const BxgModelDesc* desc, int32_t info[8]) {
   if (!desc || !info) return fail(BXG_E_INVALID, "null argument");
@@ -253,13 +311,14 @@ int bxg_launch_shape(const BxgModel* m, int64_t n_env, int32_t info[4]) {
 int bxg_init(const BxgModel* m, int64_t n_env, const float* q, const float* qd, const BxgState* out, void* stream) {
   if (!m) return fail(BXG_E_INVALID, "null model");
   if (n_env <= 0) return n_env == 0 ? BXG_OK : fail(BXG_E_INVALID, "n_env < 0");
+  if (m->n_models && n_env != m->n_models) return fail(BXG_E_INVALID, "a batched model takes exactly one env per model: n_env != number of models");
   if (!q || !qd || !state_ok(out, m->pm.d.nc)) return fail(BXG_E_INVALID, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
   DeviceGuard guard(m->device);
   LaunchShape ls = launch_shape(m, n_env);
   BxgEnvSpec env{}; float* obs = nullptr;
   void* args[] = {(void*)&m->pm.d, (void*)&m->d_blob, (void*)&q, (void*)&qd, (void*)out, (void*)&n_env, (void*)&env, (void*)&obs};
-  BXG_CUDA(cudaLaunchKernel(init_kernel_of(m->kernel_id), dim3(ls.grid), dim3(ls.threads), args, ls.smem, st));
+  BXG_CUDA(cudaLaunchKernel(m->n_models ? init_perenv_kernel_of(m->kernel_id) : init_kernel_of(m->kernel_id), dim3(ls.grid), dim3(ls.threads), args, ls.smem, st));
   g_launches.fetch_add(1);
   BXG_CUDA(cudaGetLastError());
   return BXG_OK;
@@ -270,6 +329,7 @@ int bxg_step(const BxgModel* m, int64_t n_env, int32_t n_frames, const BxgState*
   if (!m) return fail(BXG_E_INVALID, "null model");
   if (n_frames < 0) return fail(BXG_E_INVALID, "n_frames < 0");
   if (n_env <= 0) return n_env == 0 ? BXG_OK : fail(BXG_E_INVALID, "n_env < 0");
+  if (m->n_models && n_env != m->n_models) return fail(BXG_E_INVALID, "a batched model takes exactly one env per model: n_env != number of models");
   const bool lean = flags & BXG_STEP_LEAN;
   if (lean ? (!state_ok_lean(in) || !state_ok_lean(out)) : (!state_ok(in, m->pm.d.nc) || !state_ok(out, m->pm.d.nc))) return fail(BXG_E_INVALID, "null argument");
   if (m->pm.d.nu > 0 && !act) return fail(BXG_E_INVALID, "act is NULL but the model has actuators");
@@ -283,7 +343,7 @@ int bxg_step(const BxgModel* m, int64_t n_env, int32_t n_frames, const BxgState*
   void* args[] = {(void*)&m->pm.d, (void*)&m->d_blob, (void*)in, (void*)&act, (void*)out, (void*)&n_env, (void*)&nf, (void*)&fl, (void*)&dg,
                   (void*)&env, (void*)&eio, (void*)&first};
   const bool chol = m->pm.d.minv_mode == BXG_MINV_CHOLESKY;
-  const void* kern = lean ? step_lean_kernel_of(m->kernel_id, chol) : (chol ? step_chol_kernel_of(m->kernel_id) : step_kernel_of(m->kernel_id));
+  const void* kern = m->n_models ? step_perenv_kernel_of(m->kernel_id, lean) : lean ? step_lean_kernel_of(m->kernel_id, chol) : (chol ? step_chol_kernel_of(m->kernel_id) : step_kernel_of(m->kernel_id));
   BXG_CUDA(cudaLaunchKernel(kern, dim3(ls.grid), dim3(ls.threads), args, ls.smem, st));
   g_launches.fetch_add(1);
   BXG_CUDA(cudaGetLastError());
@@ -312,13 +372,14 @@ int bxg_env_reset(const BxgModel* m, const BxgEnvSpec* spec, int64_t n_env, cons
   if (!m || !spec) return fail(BXG_E_INVALID, "null argument");
   if (const char* why = env_spec_error(m, spec)) return fail(BXG_E_INVALID, why);
   if (n_env <= 0) return n_env == 0 ? BXG_OK : fail(BXG_E_INVALID, "n_env < 0");
+  if (m->n_models && n_env != m->n_models) return fail(BXG_E_INVALID, "a batched model takes exactly one env per model: n_env != number of models");
   if (!q || !qd || !obs || !state_ok(out, m->pm.d.nc)) return fail(BXG_E_INVALID, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
   DeviceGuard guard(m->device);
   LaunchShape ls = launch_shape(m, n_env);
   BxgEnvSpec env = *spec;
   void* args[] = {(void*)&m->pm.d, (void*)&m->d_blob, (void*)&q, (void*)&qd, (void*)out, (void*)&n_env, (void*)&env, (void*)&obs};
-  BXG_CUDA(cudaLaunchKernel(init_kernel_of(m->kernel_id), dim3(ls.grid), dim3(ls.threads), args, ls.smem, st));
+  BXG_CUDA(cudaLaunchKernel(m->n_models ? init_perenv_kernel_of(m->kernel_id) : init_kernel_of(m->kernel_id), dim3(ls.grid), dim3(ls.threads), args, ls.smem, st));
   g_launches.fetch_add(1);
   BXG_CUDA(cudaGetLastError());
   return BXG_OK;
@@ -332,6 +393,7 @@ int bxg_env_step(const BxgModel* m, const BxgEnvSpec* spec, int64_t n_env, int32
   if (spec->kind == BXG_ENV_PLANAR && m->pm.d.nq < 3) return fail(BXG_E_INVALID, "planar env kind needs q = [x, z, angle, ...]");
   if (n_frames < 1) return fail(BXG_E_INVALID, "n_frames < 1");
   if (n_env <= 0) return n_env == 0 ? BXG_OK : fail(BXG_E_INVALID, "n_env < 0");
+  if (m->n_models && n_env != m->n_models) return fail(BXG_E_INVALID, "a batched model takes exactly one env per model: n_env != number of models");
   const bool lean = io->flags & BXG_STEP_LEAN;
   if (lean ? (!state_ok_lean(in) || !state_ok_lean(out)) : (!state_ok(in, m->pm.d.nc) || !state_ok(out, m->pm.d.nc))) return fail(BXG_E_INVALID, "null state leaf");
   if (!io->obs || !io->reward || !io->done || !io->metrics) return fail(BXG_E_INVALID, "null env output");
@@ -347,7 +409,7 @@ int bxg_env_step(const BxgModel* m, const BxgEnvSpec* spec, int64_t n_env, int32
   void* args[] = {(void*)&m->pm.d, (void*)&m->d_blob, (void*)in, (void*)&action, (void*)out, (void*)&n_env, (void*)&nf, (void*)&fl, (void*)&dg,
                   (void*)&env, (void*)&eio, (void*)&first};
   const bool chol = m->pm.d.minv_mode == BXG_MINV_CHOLESKY;
-  const void* kern = lean ? step_lean_kernel_of(m->kernel_id, chol) : (chol ? step_chol_kernel_of(m->kernel_id) : step_kernel_of(m->kernel_id));
+  const void* kern = m->n_models ? step_perenv_kernel_of(m->kernel_id, lean) : lean ? step_lean_kernel_of(m->kernel_id, chol) : (chol ? step_chol_kernel_of(m->kernel_id) : step_kernel_of(m->kernel_id));
   BXG_CUDA(cudaLaunchKernel(kern, dim3(ls.grid), dim3(ls.threads), args, ls.smem, st));
   g_launches.fetch_add(1);
   BXG_CUDA(cudaGetLastError());

@@ -48,3 +48,9 @@ extern "C" const void* BXG_CAT(bxg_step_chol_kernel_v, BXG_VARIANT)() { return (
 extern "C" const void* BXG_CAT(bxg_step_lean_kernel_v, BXG_VARIANT)() { return (const void*)bxg::step_kernel<Cfg, 0, true, BXG_VARIANT>; }
 extern "C" const void* BXG_CAT(bxg_step_chol_lean_kernel_v, BXG_VARIANT)() { return (const void*)bxg::step_kernel<Cfg, 1, true, BXG_VARIANT>; }
 extern "C" const void* BXG_CAT(bxg_init_kernel_v, BXG_VARIANT)() { return (const void*)bxg::init_kernel<Cfg, BXG_VARIANT>; }
+// per-env models (bxg_model_create_batched): Newton-Schulz only, on the Ant-class, Humanoid-class and generic variants
+#if BXG_VARIANT == 0 || BXG_VARIANT == 1 || BXG_VARIANT == 3
+extern "C" const void* BXG_CAT(bxg_step_perenv_kernel_v, BXG_VARIANT)() { return (const void*)bxg::step_kernel<Cfg, 0, false, BXG_VARIANT, true>; }
+extern "C" const void* BXG_CAT(bxg_step_perenv_lean_kernel_v, BXG_VARIANT)() { return (const void*)bxg::step_kernel<Cfg, 0, true, BXG_VARIANT, true>; }
+extern "C" const void* BXG_CAT(bxg_init_perenv_kernel_v, BXG_VARIANT)() { return (const void*)bxg::init_kernel<Cfg, BXG_VARIANT, true>; }
+#endif

@@ -109,7 +109,11 @@ __device__ __forceinline__ void stage_model(const Dims& D, const uint32_t* __res
 // default path loses 4 % (Ant) to the larger register / code footprint (profiles/r02_ab_lean_code.txt).
 // ID: the kernel id of the translation unit (bxg_inst.cu).  It makes every instantiation a distinct symbol: ids 10 / 11
 // use the same Cfg as variants 0 / 1 and would otherwise be ONE weak symbol for two different kernels.
-template <class Cfg, int INV, bool LEAN, int ID>
+// PERENV: one model per env (bxg_model_create_batched: the reference's DomainRandomizationVmapWrapper, a System with
+// batched leaves, envs/wrappers/training.py:223-260).  `model` is then [n_env][model_words] in global memory and env e
+// reads its constants from its own row (through L1 / L2) instead of the CTA's shared-memory copy; the slab layout is
+// unchanged.  A compile-time mode: the default kernels keep their shared-memory addressing.
+template <class Cfg, int INV, bool LEAN, int ID, bool PERENV = false>
 __global__ void __launch_bounds__(Cfg::MAX_THREADS)
 step_kernel(const Dims Dparam, const uint32_t* __restrict__ model, const BxgState in, const float* __restrict__ act,
             const BxgState out, int64_t n_env, int n_frames, int flags, const BxgDiag diag,
@@ -121,7 +125,7 @@ step_kernel(const Dims Dparam, const uint32_t* __restrict__ model, const BxgStat
 #else
   const Dims& D = Dparam;
 #endif
-  stage_model(D, model, smem_u);
+  if constexpr (!PERENV) stage_model(D, model, smem_u);
   const int groups = blockDim.x / G, group = threadIdx.x / G;
   Ctx c;
   c.D = &Dparam;
@@ -137,6 +141,10 @@ step_kernel(const Dims Dparam, const uint32_t* __restrict__ model, const BxgStat
     int64_t e = p * per_pass + (int64_t)blockIdx.x * groups + group;
     const bool valid = e < n_env;
     if (!valid) e = n_env - 1;
+    if constexpr (PERENV) {
+      const uint32_t* mb = model + e * (int64_t)D.model_words;
+      c.mf = reinterpret_cast<const float*>(mb); c.mi = reinterpret_cast<const int*>(mb);
+    }
     Stats st{};
 #if defined(BXG_PHASE_TIMERS)
     st.phase_cycles = valid ? diag.phase_cycles : nullptr;
@@ -167,7 +175,7 @@ step_kernel(const Dims Dparam, const uint32_t* __restrict__ model, const BxgStat
   }
 }
 
-template <class Cfg, int ID>
+template <class Cfg, int ID, bool PERENV = false>
 __global__ void __launch_bounds__(Cfg::MAX_THREADS)
 init_kernel(const Dims Dparam, const uint32_t* __restrict__ model, const float* __restrict__ q, const float* __restrict__ qd,
             const BxgState out, int64_t n_env, const BxgEnvSpec env, float* __restrict__ obs) {
@@ -178,7 +186,7 @@ init_kernel(const Dims Dparam, const uint32_t* __restrict__ model, const float* 
 #else
   const Dims& D = Dparam;
 #endif
-  stage_model(D, model, smem_u);
+  if constexpr (!PERENV) stage_model(D, model, smem_u);
   const int groups = blockDim.x / G, group = threadIdx.x / G;
   Ctx c;
   c.D = &Dparam;
@@ -192,6 +200,10 @@ init_kernel(const Dims Dparam, const uint32_t* __restrict__ model, const float* 
     int64_t e = p * per_pass + (int64_t)blockIdx.x * groups + group;
     const bool valid = e < n_env;
     if (!valid) e = n_env - 1;
+    if constexpr (PERENV) {
+      const uint32_t* mb = model + e * (int64_t)D.model_words;
+      c.mf = reinterpret_cast<const float*>(mb); c.mi = reinterpret_cast<const int*>(mb);
+    }
     Stats st{};
     prepare_env(ex, c);
     load_env_qqd(ex, c, q, qd, e);

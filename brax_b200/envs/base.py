@@ -43,6 +43,7 @@ class FusedEnv:
                batch_size: Optional[int] = None, device=None, env_id_offset: int = 0, metric_slots=None,
                action_repeat: int = 1, lean: bool = False):
     self.sys = sys
+    self.systems = None   # one System per env (DomainRandomizationVmapWrapper, envs/wrappers/training.py), else None
     # lean: the pipeline state carries q, qd, x, xd and mass_mx_inv only (BXG_STEP_LEAN): the step recomputes the
     # rest in shared memory, bit-identically; a quarter of the State in HBM, what a trainer's rollout wants
     self.lean = bool(lean)
@@ -84,6 +85,11 @@ class FusedEnv:
     return self
 
   def _model(self) -> native.NativeModel:
+    if self.systems is not None:   # domain randomisation: env e steps with systems[e]
+      m = self._batched_models.get(self.device.index)
+      if m is None:
+        m = self._batched_models[self.device.index] = native.BatchedNativeModel(self.systems, self.device.index)
+      return m
     return native.model_for(self.sys, self.device.index)
 
   # -- API --------------------------------------------------------------------

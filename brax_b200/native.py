@@ -97,25 +97,32 @@ class EnvIOC(ctypes.Structure):
               ('first_state', ctypes.POINTER(StateC)), ('first_obs', ctypes.c_void_p), ('flags', _i32)]
 
 
-def make_desc(sys, minv_mode: int = MINV_NEWTON_SCHULZ) -> Tuple[ModelDesc, list]:
-  """System -> BxgModelDesc.  Returns (desc, keepalive arrays)."""
+def make_desc(sys, minv_mode: int = MINV_NEWTON_SCHULZ, cp=None, cache: Optional[dict] = None) -> Tuple[ModelDesc, list]:
+  """System -> BxgModelDesc.  Returns (desc, keepalive arrays).  cp: `sys.contact_pairs()` if the caller has it.
+  cache: conversions keyed by the identity of the source leaf, shared between the descs of a batched System (whose
+  unmapped leaves are the same objects in every env's System): each shared leaf is converted once."""
   keep = []
 
-  def fp(a):
-    a = np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(-1))
-    if a.size == 0:
-      a = np.zeros(1, np.float32)
-    keep.append(a)
-    return a.ctypes.data_as(_pf)
+  def conv(a, dtype, ptr_t, key):
+    k = (id(a) if key is None else key, dtype)
+    if cache is not None and k in cache:
+      return cache[k][1]
+    arr = np.ascontiguousarray(np.asarray(a, dtype=dtype).reshape(-1))
+    if arr.size == 0:
+      arr = np.zeros(1, dtype)
+    p = arr.ctypes.data_as(ptr_t)
+    if cache is not None:
+      cache[k] = (a, p, arr)    # (the source object stays alive, so its id is not reused)
+    keep.append(arr)
+    return p
 
-  def ip(a):
-    a = np.ascontiguousarray(np.asarray(a, dtype=np.int32).reshape(-1))
-    if a.size == 0:
-      a = np.zeros(1, np.int32)
-    keep.append(a)
-    return a.ctypes.data_as(_pi)
+  def fp(a, key=None):
+    return conv(a, np.float32, _pf, key)
 
-  cp = sys.contact_pairs()
+  def ip(a, key=None):
+    return conv(a, np.int32, _pi, key)
+
+  cp = sys.contact_pairs() if cp is None else cp
   d = ModelDesc()
   d.abi_version = 4
   d.num_links, d.nq, d.nv, d.nu = sys.num_links(), sys.nq, sys.nv, sys.nu
@@ -128,8 +135,8 @@ def make_desc(sys, minv_mode: int = MINV_NEWTON_SCHULZ) -> Tuple[ModelDesc, list
   d.dt = float(sys.opt.timestep)
   for i in range(3):
     d.gravity[i] = float(sys.gravity[i])
-  d.link_parent = ip(sys.link_parents)
-  d.link_ndof = ip([0 if t == 'f' else int(t) for t in sys.link_types])
+  d.link_parent = ip(sys.link_parents, key=('parents', sys.link_parents))
+  d.link_ndof = ip([0 if t == 'f' else int(t) for t in sys.link_types], key=('ndof', sys.link_types))
   d.link_tf_pos = fp(sys.link.transform.pos); d.link_tf_rot = fp(sys.link.transform.rot)
   d.link_joint_pos = fp(sys.link.joint.pos)
   d.inertia_pos = fp(sys.link.inertia.transform.pos); d.inertia_rot = fp(sys.link.inertia.transform.rot)
@@ -146,8 +153,8 @@ def make_desc(sys, minv_mode: int = MINV_NEWTON_SCHULZ) -> Tuple[ModelDesc, list
   d.act_gain = fp(a.gain); d.act_gear = fp(a.gear)
   cr = np.asarray(a.ctrl_range, np.float32).reshape(-1, 2)
   fr = np.asarray(a.force_range, np.float32).reshape(-1, 2)
-  d.act_ctrl_lo = fp(cr[:, 0]); d.act_ctrl_hi = fp(cr[:, 1])
-  d.act_force_lo = fp(fr[:, 0]); d.act_force_hi = fp(fr[:, 1])
+  d.act_ctrl_lo = fp(cr[:, 0], key=('clo', id(a.ctrl_range))); d.act_ctrl_hi = fp(cr[:, 1], key=('chi', id(a.ctrl_range)))
+  d.act_force_lo = fp(fr[:, 0], key=('flo', id(a.force_range))); d.act_force_hi = fp(fr[:, 1], key=('fhi', id(a.force_range)))
   d.act_bias_q = fp(a.bias_q); d.act_bias_qd = fp(a.bias_qd)
   d.con_link_a = ip(cp.link_a); d.con_link_b = ip(cp.link_b)
   d.con_plane_pos = fp(cp.plane_pos); d.con_frame = fp(cp.frame)
@@ -200,6 +207,9 @@ def lib() -> ctypes.CDLL:
       l.bxg_model_destroy.argtypes = [ctypes.c_void_p]
       l.bxg_model_num_constraints.argtypes = [ctypes.c_void_p]
       l.bxg_model_kernel_id.argtypes = [ctypes.c_void_p]
+      l.bxg_model_create_batched.argtypes = [ctypes.POINTER(ModelDesc), ctypes.c_int64, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+      l.bxg_model_num_models.argtypes = [ctypes.c_void_p]
+      l.bxg_model_num_models.restype = ctypes.c_int64
       l.bxg_plan.argtypes = [ctypes.POINTER(ModelDesc), ctypes.POINTER(ctypes.c_int32)]
       l.bxg_launch_shape.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int32)]
       l.bxg_init.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
@@ -378,6 +388,44 @@ class NativeModel:
     return {'con_dist': torch.zeros((n, max(self.ncon, 1)), dtype=torch.float32, device=dev),
             'stats': torch.zeros((n, 4), dtype=torch.int32, device=dev),
             'phase_cycles': torch.zeros(NUM_PHASES, dtype=torch.int64, device=dev)}
+
+
+class BatchedNativeModel(NativeModel):
+  """One System per env (bxg_model_create_batched): what the reference's DomainRandomizationVmapWrapper reaches with
+  `jax.vmap` over a System with batched leaves (envs/wrappers/training.py:223-260).  `systems[e]` is env e's System;
+  all share one topology.  Every call on this model takes exactly len(systems) envs."""
+
+  def __init__(self, systems, device: int):
+    import torch
+    if not torch.cuda.is_available():
+      raise RuntimeError('no CUDA device: brax_b200 has no CPU fallback')
+    systems = list(systems)
+    assert systems, 'no Systems'
+    sys = systems[0]
+    self.sys = sys
+    self.systems = systems
+    self.device = int(device)
+    self.minv_mode = MINV_NEWTON_SCHULZ
+    self.shapes = state_shapes(sys)
+    self.nc = num_constraints(sys)
+    self.ncon = len(sys.contact_pairs().geom1)
+    descs = (ModelDesc * len(systems))()
+    keep = []
+    geom = ('geom_pos', 'geom_quat', 'geom_size', 'geom_friction', 'geom_solref', 'geom_solimp')
+    cp0 = sys.contact_pairs()
+    cache = {}
+    for e, s in enumerate(systems):
+      # the contact pairs derive from the geom leaves only: shared (the same arrays) unless those are randomised
+      same_geoms = all(getattr(s, f) is getattr(sys, f) for f in geom)
+      d, k = make_desc(s, MINV_NEWTON_SCHULZ, cp0 if same_geoms else None, cache)
+      ctypes.memmove(ctypes.byref(descs, e * ctypes.sizeof(ModelDesc)), ctypes.byref(d), ctypes.sizeof(ModelDesc))
+      keep.append(k)
+    h = ctypes.c_void_p()
+    _check(lib().bxg_model_create_batched(descs, len(systems), self.device, ctypes.byref(h)), 'bxg_model_create_batched')
+    self._h = h
+    self.kernel_id = int(lib().bxg_model_kernel_id(h))
+    self.num_models = int(lib().bxg_model_num_models(h))
+    del keep
 
 
 def model_for(sys, device: int, minv_mode: int = MINV_NEWTON_SCHULZ) -> NativeModel:

@@ -18,6 +18,7 @@ import math
 import time
 from typing import Callable, Dict, Optional
 
+import numpy as np
 import torch
 import torch.distributed as dist
 from torch import nn
@@ -164,16 +165,26 @@ class Agent(nn.Module):
 def train(env_name: str = 'ant', num_envs: int = 2048, episode_length: int = 1000, num_timesteps: int = 1_000_000,
           unroll_length: int = 5, batch_size: int = 1024, num_minibatches: int = 32, num_update_epochs: int = 4,
           reward_scaling: float = 10.0, entropy_cost: float = 1e-2, discounting: float = 0.97, learning_rate: float = 3e-4,
-          normalize_advantage: bool = True,
+          normalize_advantage: bool = True, randomization_fn: Optional[Callable] = None,
           seed: int = 0, device=None, use_cuda_graph: bool = True, progress_fn: Optional[Callable[[int, Dict[str, float]], None]] = None):
   """Returns (agent, metrics).  metrics['sps'] = env-steps/sec including policy
-  inference and learning (the figure BASELINE config 5 asks for)."""
+  inference and learning (the figure BASELINE config 5 asks for).
+
+  randomization_fn: `fn(sys, rng) -> (sys_v, in_axes)` as in the reference trainer (agents/ppo/train.py:88-90, 268-276):
+  `rng` holds one integer seed per env of this rank (the reference passes one PRNG key per env), `sys_v` the System
+  with a leading env axis on the randomised leaves, `in_axes` 0 at those leaves and None elsewhere."""
   world = dist.get_world_size() if dist.is_initialized() else 1
   rank = dist.get_rank() if dist.is_initialized() else 0
   device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
   # lean pipeline state: the rollout never reads the derived State leaves, the step recomputes them on chip
   env = envs.create(env_name, episode_length=episode_length, auto_reset=True, batch_size=num_envs, device=device,
                     env_id_offset=rank * num_envs, lean=True)
+  if randomization_fn is not None:
+    import functools
+    from brax_b200.envs.wrappers import training as wrappers
+    env_seeds = np.random.SeedSequence([seed, rank]).generate_state(num_envs)
+    env = wrappers.DomainRandomizationVmapWrapper(env, functools.partial(randomization_fn, rng=env_seeds))
+    assert env.batch_size == num_envs, 'randomization_fn must return one System per env'
   torch.manual_seed(seed + rank)
   agent = Agent(env.observation_size, env.action_size, entropy_cost=entropy_cost, discounting=discounting,
                 reward_scaling=reward_scaling, normalize_advantage=normalize_advantage).to(device)

@@ -263,6 +263,16 @@ void bxg_model_destroy(BxgModel* model);
 int bxg_model_num_constraints(const BxgModel* model);
 /* The kernel id this model's launches use (bxg_plan info[7]). */
 int bxg_model_kernel_id(const BxgModel* model);
+/* A batched System: n models of ONE topology whose constants differ, env e of every launch uses descs[e].  Replaces
+ * `jax.vmap(step, in_axes=[sys_in_axes, 0, 0])(sys_v, state, action)` of the reference's DomainRandomizationVmapWrapper
+ * (envs/wrappers/training.py:223-260).  What may differ: every float array of BxgModelDesc (link / inertia / dof /
+ * actuator / contact constants, solver parameters), viscosity and density.  What must be equal (BXG_E_UNSUPPORTED
+ * otherwise): sizes, link_parent / link_ndof, actuator and contact index arrays, dt, gravity, iteration counts.
+ * Launches on the returned model require n_env == n (BXG_E_INVALID otherwise), run the reference's Newton-Schulz mode
+ * only and read each env's constants from global memory (kernel variants 0, 1 and 3). */
+int bxg_model_create_batched(const BxgModelDesc* descs, int64_t n, int device, BxgModel** out);
+/* n of bxg_model_create_batched, 0 for a model every env shares. */
+int64_t bxg_model_num_models(const BxgModel* model);
 /* Host-only planning query (no CUDA needed): which kernel variant a model maps
  * to and its shared-memory footprint.  info[0] = variant id, [1] = lanes per env,
  * [2] = model words, [3] = per-env slab words, [4] = envs per CTA,

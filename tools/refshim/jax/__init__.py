@@ -40,24 +40,40 @@ def _axes_for(in_axes, n):
   return [in_axes] * n
 
 
+def _prefix_apply(a, ax, leaf_fn):
+  """Walks `a` along the in_axes prefix tree `ax` (None: unmapped subtree, int: every leaf below mapped on that axis)."""
+  import dataclasses
+  from jax import tree_util as _tu
+  if ax is None:
+    return a
+  if isinstance(ax, int):
+    return _tree_map(lambda x: leaf_fn(x, ax), a)
+  if isinstance(a, (tuple, list)):
+    out = [_prefix_apply(t, ax[i], leaf_fn) for i, t in enumerate(a)]
+    return type(a)(*out) if hasattr(a, '_fields') else type(a)(out)
+  if isinstance(a, dict):
+    return {k: _prefix_apply(v, ax[k], leaf_fn) for k, v in a.items()}
+  if type(a) in _tu._registered:
+    return dataclasses.replace(a, **{fl.name: _prefix_apply(getattr(a, fl.name), getattr(ax, fl.name), leaf_fn)
+                                     for fl in _tu._node_fields(a)})
+  raise TypeError(f'in_axes prefix {ax!r} does not match argument {type(a)}')
+
+
 def vmap(fun, in_axes=0, out_axes=0):
-  """vmap as a Python loop over the mapped axis, outputs stacked along out_axes."""
+  """vmap as a Python loop over the mapped axis, outputs stacked along out_axes.  in_axes entries may be ints, None or
+  pytree prefixes of the argument (a System with 0 at its domain-randomised leaves: envs/wrappers/training.py:250-260)."""
   @functools.wraps(fun)
   def mapped(*args):
     axes = _axes_for(in_axes, len(args))
-    size = None
+    sizes = set()
     for a, ax in zip(args, axes):
-      if ax is None:
-        continue
-      assert isinstance(ax, int), 'pytree in_axes are not supported by this stand-in'
-      for leaf in _tree_leaves(a):
-        s = _np.shape(leaf)[ax]
-        assert size is None or size == s, 'vmap: inconsistent sizes'
-        size = s
-    assert size is not None and size > 0, 'vmap over an empty or unmapped batch'
+      _prefix_apply(a, ax, lambda x, k: sizes.add(_np.shape(x)[k]) or x)
+    assert len(sizes) == 1, f'vmap: inconsistent or missing mapped sizes {sizes}'
+    size = sizes.pop()
+    assert size > 0, 'vmap over an empty batch'
     outs = []
     for i in range(size):
-      sl = [a if ax is None else _tree_map(lambda x, ax=ax: numpy.take(x, i, axis=ax), a) for a, ax in zip(args, axes)]
+      sl = [_prefix_apply(a, ax, lambda x, k: numpy.take(x, i, axis=k)) for a, ax in zip(args, axes)]
       outs.append(fun(*sl))
     return _tree_map(lambda *xs: numpy.stack(xs, axis=out_axes), *outs)
   return mapped

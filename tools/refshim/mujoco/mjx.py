@@ -16,11 +16,24 @@ from jax import numpy as jp
 PAIRS = None   # brax_b200.base.ContactPairs of the model being run
 
 
+def _tree_replace_all(self, params):
+  """mjx's PyTreeNode.tree_replace ({'a.b.c': value}: nested `replace`), which brax.System inherits."""
+  def rep(node, attr, val):
+    if len(attr) == 1:
+      return node.replace(**{attr[0]: val})
+    return node.replace(**{attr[0]: rep(getattr(node, attr[0]), attr[1:], val)})
+  new = self
+  for k, v in params.items():
+    new = rep(new, k.split('.'), v)
+  return new
+
+
 class PyTreeNode:
   def __init_subclass__(cls, **kw):
     super().__init_subclass__(**kw)
     c = dataclasses.dataclass(frozen=True, kw_only=True)(cls)
     c.replace = lambda self, **upd: dataclasses.replace(self, **upd)
+    c.tree_replace = _tree_replace_all
     struct.register_dataclass(c)
 
 
