@@ -72,3 +72,26 @@ td = {'obs': torch.randn((T + 1, B, 27), device=dev), 'logits': torch.randn((T, 
 a.loss(td).backward()
 torch.cuda.synchronize()
 print('sanitize: done')
+# per-env models (domain randomisation): the kernels read each env's constants from global memory
+from brax_b200 import base
+for model in ('ant', 'humanoid', 'hopper'):   # variants 0, 1 and (hopper's own variant has no per-env build) the generic 3
+  sys_ = envs_assets.load(model)
+  n = 27
+  scale = np.random.default_rng(0).uniform(0.8, 1.25, (n, sys_.num_links())).astype(np.float32)
+  leaves = {'link.inertia.mass': np.asarray(sys_.link.inertia.mass, np.float32)[None] * scale,
+            'link.inertia.i': np.asarray(sys_.link.inertia.i, np.float32)[None] * scale[:, :, None, None]}
+  in_axes = base.tree_map(lambda x: None, sys_).tree_replace({k: 0 for k in leaves})
+  nm = native.BatchedNativeModel(base.unbatch(sys_.tree_replace(leaves), in_axes), 0)
+  assert nm.kernel_id == {'ant': 0, 'humanoid': 1, 'hopper': 3}[model], nm.kernel_id
+  q = torch.as_tensor(np.asarray(sys_.init_q, np.float32), device=dev)[None].repeat(n, 1).contiguous()
+  if model == 'hopper':
+    q[:, 1] -= 0.04
+  st = nm.init(q, torch.zeros((n, sys_.nv), device=dev))
+  lean = {k: st[k].clone() for k in native.LEAN_FIELDS}
+  for k in range(2):
+    a_ = 0.3 * torch.ones((n, sys_.nu), device=dev)
+    st = nm.step(st, a_, 5)
+    lean = nm.step(lean, a_, 5, lean=True)
+  torch.cuda.synchronize()
+  assert torch.isfinite(st['q']).all() and torch.equal(st['q'], lean['q']), model
+print('sanitize: per-env models done')
