@@ -15,9 +15,9 @@ procs, objs = [], []
 for v in range(g.N_VARIANTS):
   o = os.path.join(objdir, f'v{v}.o'); objs.append(o)
   procs.append(subprocess.Popen([nvcc] + flags + [f'-DBXG_VARIANT={v}', '-c', os.path.join(csrc, 'bxg_inst.cu'), '-o', o]))
-for name in ('api', 'train'):
-  o = os.path.join(objdir, f'{name}.o'); objs.append(o)
-  procs.append(subprocess.Popen([nvcc] + flags + ['-c', os.path.join(csrc, f'bxg_{name}.cu'), '-o', o]))
+for unit in ('api', 'train'):
+  o = os.path.join(objdir, f'{unit}.o'); objs.append(o)
+  procs.append(subprocess.Popen([nvcc] + flags + ['-c', os.path.join(csrc, f'bxg_{unit}.cu'), '-o', o]))
 assert all(p.wait() == 0 for p in procs)
 out = os.path.join(ROOT, 'brax_b200', f'libbxg_{name}.so')
 subprocess.run([nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '--shared', '-Xcompiler', '-fPIC'] + objs + ['-o', out], check=True)
