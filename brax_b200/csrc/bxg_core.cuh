@@ -209,7 +209,8 @@ struct Stats {
 #endif
 };
 // phases: 0 load, 1 dynamics, 2 constraint.force, 12 the CTA barrier behind it, 3 integrate, 4 kinematics, 5 transform_com,
-// 6 mass.matrix, 7 matrix_inv, 8 constraint.jacobian, 9 env prologue / epilogue, 10 store, 11 lean entry
+// 6 mass.matrix, 7 matrix_inv, 8 constraint.jacobian, 9 env prologue / epilogue, 10 store, 11 lean entry,
+// 13 / 14 / 15 inside constraint.force: active set + A + b, projected-gradient iterations without their line searches, line-search trials
 #if defined(BXG_PHASE_TIMERS) && defined(__CUDA_ARCH__)
 #define BXG_PHASE_BEGIN(st) ((st)->t_last = clock64())
 #define BXG_PHASE_END(st, k) do { long long t__ = clock64(); if ((st)->phase_cycles && (threadIdx.x & 31) == 0) atomicAdd((st)->phase_cycles + (k), (unsigned long long)(t__ - (st)->t_last)); (st)->t_last = clock64(); } while (0)
@@ -1510,8 +1511,14 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
         }
       }
     });
+    BXG_PHASE_END(st, 14);
     real sz = stepsize;
     for (int ls = 0;; ++ls) {
+      real sqdist, vd, fn;
+#if defined(BXG_LS_REPEAT)
+#pragma unroll 1
+      for (int rep = 0; rep < BXG_LS_REPEAT; ++rep) {     // tuning builds: every trial evaluated BXG_LS_REPEAT times (same result): what a trial costs
+#endif
       ex.lanes([&](int lane) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -1533,14 +1540,17 @@ BXG_HD void con_force_rows(X& ex, const Ctx& c, Stats* st) {
         }
         p0(lane) = a0; p1(lane) = a1; p2(lane) = a2;
       });
-      real sqdist, vd, fn;
       ex.sum3(p0, p1, p2, &sqdist, &vd, &fn);
+#if defined(BXG_LS_REPEAT)
+      }
+#endif
       st->pg_trials++;
       real fun_decrease = sz * (fn - fy);
       real condition = sz * vd + R(0.5) * sqdist;
       if (!(fun_decrease > condition + eps) || ls >= D.solver_maxls) break;
       sz = sz * R(0.5);
     }
+    BXG_PHASE_END(st, 15);   // (tuning builds) the line-search trials
     stepsize = sz <= R(1e-6) ? R(1.) : sz / R(0.5);
     real tn = R(0.5) * (R(1.) + r_sqrt(R(1.) + R(4.) * (t * t)));
     real mom = (t - R(1.)) / tn;

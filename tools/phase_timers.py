@@ -13,7 +13,7 @@ import torch  # noqa: E402
 from brax_b200 import native, workloads  # noqa: E402
 
 NAMES = ['load', 'dynamics (tau, RNE)', 'constraint.force', 'integrate', 'kinematics', 'transform_com', 'mass.matrix',
-         'matrix_inv (Newton-Schulz)', 'constraint.jacobian', 'env prologue / epilogue', 'store', 'lean entry', 'CTA barrier after constraint.force', 'constraint.force: active set, A, b', 'constraint.force: FISTA + line search']
+         'matrix_inv (Newton-Schulz)', 'constraint.jacobian', 'env prologue / epilogue', 'store', 'lean entry', 'CTA barrier after constraint.force', 'constraint.force: active set, A, b', 'constraint.force: FISTA iterations (without the line searches)', 'constraint.force: line-search trials']
 
 
 def main():
@@ -32,7 +32,14 @@ def main():
   torch.cuda.synchronize()
   cyc = diag['phase_cycles'].cpu().numpy().astype(float)
   tot = cyc.sum()
-  out = {'model': model, 'n_env': n, 'launch': nm.launch_shape(n), 'share_of_warp_cycles': {NAMES[i]: round(cyc[i] / tot, 4) for i in range(len(NAMES)) if cyc[i] > 0}}
+  ls_ = nm.launch_shape(n)
+  warp_substeps = ls_['grid'] * (ls_['threads_per_cta'] // 32) * -(-n // (ls_['grid'] * ls_['envs_per_cta'])) * 3 * nf
+  stats = diag['stats'].cpu().numpy().astype(float)      # counters accumulated over the three timed launches
+  out = {'model': model, 'n_env': n, 'launch': ls_, 'share_of_warp_cycles': {NAMES[i]: round(cyc[i] / tot, 4) for i in range(len(NAMES)) if cyc[i] > 0},
+         'cycles_per_warp_substep': {NAMES[i]: round(cyc[i] / warp_substeps) for i in range(len(NAMES)) if cyc[i] > 0},
+         'cycles_per_warp_substep_total': round(tot / warp_substeps),
+         'per_env_substep': {'pg_iterations': round(stats[:, 0].mean() / (3 * nf), 2), 'line_search_trials': round(stats[:, 1].mean() / (3 * nf), 2),
+                             'newton_schulz_accepts': round(stats[:, 2].mean() / (3 * nf), 2)}}
   print(json.dumps(out, indent=1))
 
 
