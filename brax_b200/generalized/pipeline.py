@@ -19,6 +19,7 @@ from typing import Optional
 
 import torch
 
+from brax_b200 import contact as contact_lib
 from brax_b200 import native
 from brax_b200.base import System
 from brax_b200.generalized.base import State
@@ -52,7 +53,7 @@ def init(
     sys: a brax_b200 System
     q: (n, q_size) or (q_size,) joint position vector(s), CUDA
     qd: (n, qd_size) or (qd_size,) joint velocity vector(s), CUDA
-    debug: if True, adds contact distances to the state for debugging
+    debug: if True, adds the contacts of the fresh state (`brax_b200.contact.Contact`) for debugging
   """
   _validate(sys)
   squeeze = q.dim() == 1
@@ -60,10 +61,9 @@ def init(
     q, qd = q[None], qd[None]
   model = native.model_for(sys, _device_index(q), minv_mode)
   bufs = model.init(q, qd)
-  contact = None
-  if debug:
-    contact = _contact_debug(model, bufs)
-  st = State.from_flat(bufs, contact)
+  st = State.from_flat(bufs, None)
+  if debug:   # reference pipeline.py:58-60: contact.get(sys, x)
+    st = st.replace(contact=contact_lib.get(sys, st.x))
   return _squeeze(st) if squeeze else st
 
 
@@ -81,7 +81,7 @@ def step(
     sys: a brax_b200 System
     state: physics state prior to step
     act: (n, act_size) or (act_size,) actuator input; None iff act_size == 0
-    debug: if True, adds contact distances to the state for debugging
+    debug: if True, adds the new state's contacts and the step's solver counters (`brax_b200.contact.Contact`)
   """
   squeeze = state.q.dim() == 1
   if squeeze:
@@ -91,32 +91,10 @@ def step(
   bufs = {k: v.contiguous() for k, v in state.to_flat().items()}
   diag = model.alloc_diag(bufs['q'].shape[0]) if debug else None
   out = model.step(bufs, act, n_frames=n_frames, diag=diag)
-  st = State.from_flat(out, diag if debug else None)
+  st = State.from_flat(out, None)
+  if debug:   # reference pipeline.py:91-92; the distances are the ones the kernel's colliders produced for this state
+    st = st.replace(contact=contact_lib.get(sys, st.x, kernel_dist=diag['con_dist'] if model.ncon else None, solver_stats=diag['stats']))
   return _squeeze(st) if squeeze else st
-
-
-def _contact_debug(model, bufs):
-  """debug=True after init: plane-sphere penetration distances of the fresh state
-  (brax/contact.py:28-67 + mjx plane-sphere).  Debug-only host-side torch ops; the
-  step kernel produces the same quantity itself (BXG_STEP_DIAGNOSTICS)."""
-  import numpy as np
-  n = bufs['q'].shape[0]
-  diag = model.alloc_diag(n)
-  cp = model.sys.contact_pairs()
-  if len(cp.geom1) == 0:
-    return diag
-  dev = bufs['q'].device
-  lb = torch.as_tensor(np.asarray(cp.link_b, np.int64), device=dev)
-  pos, rot = bufs['x_pos'][:, lb], bufs['x_rot'][:, lb]          # [n, ncon, 3|4]
-  v = torch.as_tensor(np.asarray(cp.sphere_pos, np.float32), device=dev)[None].expand_as(pos)
-  s_, u = rot[..., :1], rot[..., 1:]
-  r = 2 * ((u * v).sum(-1, keepdim=True) * u) + (s_ * s_ - (u * u).sum(-1, keepdim=True)) * v + 2 * s_ * torch.cross(u, v, dim=-1)
-  sp = pos + r
-  nrm = torch.as_tensor(np.asarray(cp.plane_normal, np.float32), device=dev)[None]
-  pp = torch.as_tensor(np.asarray(cp.plane_pos, np.float32), device=dev)[None]
-  rad = torch.as_tensor(np.asarray(cp.radius, np.float32), device=dev)[None]
-  diag['con_dist'] = (((sp - pp) * nrm).sum(-1) - rad).contiguous()
-  return diag
 
 
 def _squeeze(st: State) -> State:
