@@ -56,13 +56,18 @@
 #ifndef BXG_TILE_UNROLL
 #define BXG_TILE_UNROLL 2
 #endif
-// explicit software pipeline in the tile product of the half-warp 16-wide variant (unroll of its k-block loop)
+// explicit software pipeline in the tile product of the 16-wide variants: unroll of its k-block loop.  4 = the whole loop
+// (W = 16: four blocks; Ant's specialised build: three and the tail).  Rolled, the hand-over of the prefetched operands is
+// 41 register MOVs per 48 FFMA2 and the loop control on top: Ant 14.91 -> 15.8 M env-steps/s unrolled (pipelined or not)
 #ifndef BXG_PIPE16_UNROLL
-#define BXG_PIPE16_UNROLL 1
+#define BXG_PIPE16_UNROLL 4
 #endif
 // explicit software pipeline in the 6x6 tile product of the half-warp 24-wide variant (320-thread CTAs: registers to spare)
 #ifndef BXG_PIPE_3X6
 #define BXG_PIPE_3X6 false    // (with the 3x6 tiles at 96 registers the explicit pipeline costs 5 %: profiles/r01_sweep_r1i.json)
+#endif
+#ifndef BXG_PIPE_4X4
+#define BXG_PIPE_4X4 true
 #endif
 #ifndef BXG_PIPE_6X6
 #define BXG_PIPE_6X6 true
@@ -1073,7 +1078,7 @@ template <int G, int W> struct Tile;
 // registers allow (4x4 tiles: Ant +2.4 %); with the 3x6 tiles at 96 registers it costs 5 % (profiles/r01_sweep_r1i.json)
 template <> struct Tile<32, 24> { static constexpr int RG = 8, CG = 4, TM = 3, TN = 6; static constexpr bool PIPE = BXG_PIPE_3X6; };
 template <> struct Tile<16, 24> { static constexpr int RG = 4, CG = 4, TM = 6, TN = 6; static constexpr bool PIPE = BXG_PIPE_6X6; };
-template <> struct Tile<16, 16> { static constexpr int RG = 4, CG = 4, TM = 4, TN = 4; static constexpr bool PIPE = true; };
+template <> struct Tile<16, 16> { static constexpr int RG = 4, CG = 4, TM = 4, TN = 4; static constexpr bool PIPE = BXG_PIPE_4X4; };
 template <> struct Tile<32, 32> { static constexpr int RG = 8, CG = 4, TM = 4, TN = 8; static constexpr bool PIPE = false; };
 template <> struct Tile<32, 16> { static constexpr int RG = 8, CG = 4, TM = 2, TN = 4; static constexpr bool PIPE = true; };
 template <> struct Tile<4, 4>   { static constexpr int RG = 2, CG = 2, TM = 2, TN = 2; static constexpr bool PIPE = false; };
