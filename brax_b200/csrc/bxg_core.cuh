@@ -27,6 +27,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <type_traits>
 
 #include "bxg_model.h"
 
@@ -2139,6 +2140,58 @@ BXG_HD void io_vec(X& ex, int n, F f) {
   ex.lanes([&](int lane) { for (int i = lane; i < n; i += X::G) f(i); });
 }
 
+// ---- global -> shared copies with the loads in flight together ---------------------------------------------
+// A plain `for (i = lane; i < n; i += G) dst[i] = src[i]` compiles to load, wait, store, next: one DRAM / L2 latency
+// per element and lane (the load phase of a full State was ~48 such round trips: 26 k cycles per env pass, SM idle).
+// These helpers issue the loads of several leaves and several elements per lane first and store afterwards.
+#ifndef BXG_IO_BATCH
+#define BXG_IO_BATCH 4
+#endif
+template <class T>
+struct IoLeaf { real* dst; const T* src; int n; };
+// K leaves, each n <= any size: per round every lane fetches up to U elements of every leaf, then stores them
+template <int G, int U, int K, class T>
+BXG_HD void copy_in_many(const IoLeaf<T> (&lv)[K], int lane) {
+  int nmax = 0;
+#pragma unroll
+  for (int k = 0; k < K; ++k) nmax = lv[k].n > nmax ? lv[k].n : nmax;
+  for (int i0 = lane; i0 < nmax; i0 += G * U) {
+    real v[K][U];
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int u = 0; u < U; ++u) { const int i = i0 + u * G; v[k][u] = i < lv[k].n ? (real)lv[k].src[i] : R(0.); }
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int u = 0; u < U; ++u) { const int i = i0 + u * G; if (i < lv[k].n) lv[k].dst[i] = v[k][u]; }
+  }
+}
+// K row-major [rows][nv] matrices of one shape into shared-memory copies of row stride ld; the (row, column) of
+// element i advances incrementally (no integer division per element)
+template <int G, int U, int K, class T>
+BXG_HD void copy_in_matrices(const IoLeaf<T> (&lv)[K], int nv, int ld, int lane) {
+  const int n = lv[0].n;
+  const int dq = G / nv, dr = G - dq * nv;    // i += G  <=>  (r, cc) += (dq, dr) with one carry
+  int r = lane / nv, cc = lane - r * nv;
+  for (int i0 = lane; i0 < n; i0 += G * U) {
+    real v[K][U];
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int u = 0; u < U; ++u) { const int i = i0 + u * G; v[k][u] = i < n ? (real)lv[k].src[i] : R(0.); }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * G;
+      if (i < n) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) lv[k].dst[r * ld + cc] = v[k][u];
+      }
+      r += dq; cc += dr; if (cc >= nv) { cc -= nv; ++r; }
+    }
+  }
+}
+
 // Loads the State leaves pipeline.step reads.
 // ST: BxgState (include/bxg.h), or the emulator's double-precision twin with the same member names
 template <class X, class ST>
@@ -2146,40 +2199,33 @@ BXG_HD void load_env(X& ex, const Ctx& c, const ST& g, const real* act, int64_t 
   BXG_GET_DIMS(c); real* s = c.s;
   const int L = D.L, nv = D.nv, nq = D.nq, nc = D.nc, nvp = D.nvp;
   ex.lanes([&](int lane) {
-    const int G = X::G;
-    for (int i = lane; i < nq; i += G) s[D.s_q + i] = g.q[e * nq + i];
-    for (int i = lane; i < nv; i += G) s[D.s_qd + i] = g.qd[e * nv + i];
-    for (int i = lane; i < D.nu; i += G) s[D.s_act + i] = act[e * D.nu + i];
-    for (int i = lane; i < L * 3; i += G) {
-      s[D.s_cinr_pos + i] = g.cinr_pos[e * L * 3 + i];
-      s[D.s_cd_ang + i] = g.cd_ang[e * L * 3 + i]; s[D.s_cd_vel + i] = g.cd_vel[e * L * 3 + i];
-    }
-    for (int i = lane; i < L * 9; i += G) s[D.s_cinr_i + i] = g.cinr_i[e * L * 9 + i];
-    if (D.fluid) {   // fluid.force reads x and root_com of the incoming state (dynamics.py:199-206)
-      for (int i = lane; i < L * 3; i += G) { s[D.s_x_pos + i] = g.x_pos[e * L * 3 + i]; s[D.s_root_com + i] = g.root_com[e * L * 3 + i]; }
-      for (int i = lane; i < L * 4; i += G) s[D.s_x_rot + i] = g.x_rot[e * L * 4 + i];
-    }
-    for (int i = lane; i < nv * 3; i += G) {
-      s[D.s_cdof_ang + i] = g.cdof_ang[e * nv * 3 + i]; s[D.s_cdof_vel + i] = g.cdof_vel[e * nv * 3 + i];
-      s[D.s_cdofd_ang + i] = g.cdofd_ang[e * nv * 3 + i]; s[D.s_cdofd_vel + i] = g.cdofd_vel[e * nv * 3 + i];
-    }
-    // matrices: flat, fully coalesced reads; (row, column) of the re-strided shared-memory copy
-    // advance incrementally (no integer division by nv)
+    constexpr int G = X::G, U = BXG_IO_BATCH;
+    using T = typename std::remove_cv<typename std::remove_pointer<decltype(g.q)>::type>::type;
+    using Lf = IoLeaf<T>;
     {
-      const int dq = G / nv, dr = G - dq * nv;    // i += G  <=>  (r, cc) += (dq, dr) with one carry
-      int r = lane / nv, cc = lane - r * nv;
-      for (int i = lane; i < nv * nv; i += G) {
-        s[D.s_Minv + r * nvp + cc] = g.mass_mx_inv[e * nv * nv + i];
-        s[D.s_M + r * nvp + cc] = g.mass_mx[e * nv * nv + i];
-        r += dq; cc += dr; if (cc >= nv) { cc -= nv; ++r; }
-      }
-      r = lane / nv; cc = lane - r * nv;
-      for (int i = lane; i < nc * nv; i += G) {
-        s[D.s_J + r * D.jld + cc] = g.con_jac[e * nc * nv + i];
-        r += dq; cc += dr; if (cc >= nv) { cc -= nv; ++r; }
-      }
+      const Lf lv[8] = {{s + D.s_q, g.q + e * nq, nq}, {s + D.s_qd, g.qd + e * nv, nv}, {s + D.s_act, (const T*)act + e * D.nu, D.nu},
+                        {s + D.s_cinr_pos, g.cinr_pos + e * L * 3, L * 3}, {s + D.s_cd_ang, g.cd_ang + e * L * 3, L * 3},
+                        {s + D.s_cd_vel, g.cd_vel + e * L * 3, L * 3}, {s + D.s_diag, g.con_diag + e * nc, nc}, {s + D.s_aref, g.con_aref + e * nc, nc}};
+      copy_in_many<G, U, 8, T>(lv, lane);
     }
-    for (int i = lane; i < nc; i += G) { s[D.s_diag + i] = g.con_diag[e * nc + i]; s[D.s_aref + i] = g.con_aref[e * nc + i]; }
+    {
+      const Lf lv[5] = {{s + D.s_cinr_i, g.cinr_i + e * L * 9, L * 9}, {s + D.s_cdof_ang, g.cdof_ang + e * nv * 3, nv * 3}, {s + D.s_cdof_vel, g.cdof_vel + e * nv * 3, nv * 3},
+                        {s + D.s_cdofd_ang, g.cdofd_ang + e * nv * 3, nv * 3}, {s + D.s_cdofd_vel, g.cdofd_vel + e * nv * 3, nv * 3}};
+      copy_in_many<G, U, 5, T>(lv, lane);
+    }
+    if (D.fluid) {   // fluid.force reads x and root_com of the incoming state (dynamics.py:199-206)
+      const Lf lv[3] = {{s + D.s_x_pos, g.x_pos + e * L * 3, L * 3}, {s + D.s_root_com, g.root_com + e * L * 3, L * 3}, {s + D.s_x_rot, g.x_rot + e * L * 4, L * 4}};
+      copy_in_many<G, U, 3, T>(lv, lane);
+    }
+    // matrices: flat, fully coalesced reads into the re-strided shared-memory copies
+    {
+      const Lf lv[2] = {{s + D.s_Minv, g.mass_mx_inv + e * nv * nv, nv * nv}, {s + D.s_M, g.mass_mx + e * nv * nv, nv * nv}};
+      copy_in_matrices<G, U, 2, T>(lv, nv, nvp, lane);
+    }
+    {
+      const Lf lv[1] = {{s + D.s_J, g.con_jac + e * nc * nv, nc * nv}};
+      copy_in_matrices<G, 2 * U, 1, T>(lv, nv, D.jld, lane);
+    }
   });
   // active rows of the incoming jacobian: anything non-zero in the row (lane i starts its scan
   // at column i so that the lanes of a group read different banks)
@@ -2203,16 +2249,13 @@ BXG_HD void load_env_lean(X& ex, const Ctx& c, const ST& g, const real* act, int
   BXG_GET_DIMS(c); real* s = c.s;
   const int nv = D.nv, nq = D.nq, nvp = D.nvp;
   ex.lanes([&](int lane) {
-    const int G = X::G;
-    for (int i = lane; i < nq; i += G) s[D.s_q + i] = g.q[e * nq + i];
-    for (int i = lane; i < nv; i += G) s[D.s_qd + i] = g.qd[e * nv + i];
-    for (int i = lane; i < D.nu; i += G) s[D.s_act + i] = act[e * D.nu + i];
-    const int dq = G / nv, dr = G - dq * nv;
-    int r = lane / nv, cc = lane - r * nv;
-    for (int i = lane; i < nv * nv; i += G) {
-      s[D.s_Minv + r * nvp + cc] = g.mass_mx_inv[e * nv * nv + i];
-      r += dq; cc += dr; if (cc >= nv) { cc -= nv; ++r; }
-    }
+    constexpr int G = X::G, U = BXG_IO_BATCH;
+    using T = typename std::remove_cv<typename std::remove_pointer<decltype(g.q)>::type>::type;
+    using Lf = IoLeaf<T>;
+    const Lf lv[3] = {{s + D.s_q, g.q + e * nq, nq}, {s + D.s_qd, g.qd + e * nv, nv}, {s + D.s_act, (const T*)act + e * D.nu, D.nu}};
+    copy_in_many<G, U, 3, T>(lv, lane);
+    const Lf mv[1] = {{s + D.s_Minv, g.mass_mx_inv + e * nv * nv, nv * nv}};
+    copy_in_matrices<G, 2 * U, 1, T>(mv, nv, nvp, lane);
   });
 }
 // what update_position_terms leaves behind, minus the Newton-Schulz run that produced the incoming mass_mx_inv
