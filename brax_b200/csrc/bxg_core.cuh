@@ -1077,13 +1077,39 @@ template <int N> struct IntC { static constexpr int value = N; };
 template <int G, int W> struct Tile;
 // PIPE: request the operands of the next k-block before the FMAs of the current one, explicitly.  Pays where
 // registers allow (4x4 tiles: Ant +2.4 %); with the 3x6 tiles at 96 registers it costs 5 % (profiles/r01_sweep_r1i.json)
-template <> struct Tile<32, 24> { static constexpr int RG = 8, CG = 4, TM = 3, TN = 6; static constexpr bool PIPE = BXG_PIPE_3X6; };
-template <> struct Tile<16, 24> { static constexpr int RG = 4, CG = 4, TM = 6, TN = 6; static constexpr bool PIPE = BXG_PIPE_6X6; };
-template <> struct Tile<16, 16> { static constexpr int RG = 4, CG = 4, TM = 4, TN = 4; static constexpr bool PIPE = BXG_PIPE_4X4; };
-template <> struct Tile<32, 32> { static constexpr int RG = 8, CG = 4, TM = 4, TN = 8; static constexpr bool PIPE = false; };
-template <> struct Tile<32, 16> { static constexpr int RG = 8, CG = 4, TM = 2, TN = 4; static constexpr bool PIPE = true; };
-template <> struct Tile<4, 4>   { static constexpr int RG = 2, CG = 2, TM = 2, TN = 2; static constexpr bool PIPE = false; };
-template <> struct Tile<4, 8>   { static constexpr int RG = 2, CG = 2, TM = 4, TN = 4; static constexpr bool PIPE = false; };
+// Lane -> tile maps (MAP) and row ownership.  Measured on B200 (tools/microbench/lds128_patterns.cu,
+// profiles/r02_lds128_patterns.txt): a shared-memory load costs the LSU 4 bytes per lane and cycle (LDS.64: 2 cycles,
+// LDS.128: 4) UNLESS the two lanes of every adjacent pair (2i, 2i + 1) read the same address: then half (1.05 / 2.09).
+// Duplicate addresses further apart (lane l and l + 4) buy nothing, bank conflicts multiply.  So:
+//   MAP_PAIR_COLS (3x6 tiles, a warp per matrix): the lanes of a pair share the COLUMN group, i.e. the B operand, whose
+//     72 LDS.64 per product drop to 1 cycle each; the 18 LDS.128 of the A operand go from 2 to 4.  181 -> 148 LSU cycles
+//     per product and warp (the products are LSU-bound: 20 warps x 181 = 3630 of the 3900 cycles a product round took).
+//   ROWS_INTERLEAVED (4x4 tiles, two matrices per warp): row group rg owns rows rg, rg + RG, ... instead of TM consecutive
+//     ones.  With consecutive rows the four row groups' A loads sit 4 rows = 80 floats = 16 banks apart: groups 0 / 2 and
+//     1 / 3 and the other env's collide (4 cycles although adjacent quads share the address); interleaved they are 20 banks
+//     apart: conflict-free, 2 cycles.
+template <int RG_, int CG_, int TM_, int TN_, bool PIPE_, bool PAIR_COLS_ = false, bool ROWS_ILV_ = false>
+struct TileBase {
+  static constexpr int RG = RG_, CG = CG_, TM = TM_, TN = TN_;
+  static constexpr bool PIPE = PIPE_, PAIR_COLS = PAIR_COLS_, ROWS_ILV = ROWS_ILV_;
+  static_assert(!PAIR_COLS_ || (CG_ == 4 && RG_ == 8), "MAP_PAIR_COLS is written for an 8 x 4 lane grid");
+  BXG_HD static int rg(int lane) { return PAIR_COLS ? ((lane & 1) | ((lane >> 3) << 1)) : lane / CG; }
+  BXG_HD static int cg(int lane) { return PAIR_COLS ? ((lane >> 1) & 3) : lane - (lane / CG) * CG; }
+  BXG_HD static int row(int rg_, int r) { return ROWS_ILV ? rg_ + RG * r : rg_ * TM + r; }   // r-th row of row group rg_
+};
+#ifndef BXG_MAP_3X6
+#define BXG_MAP_3X6 true
+#endif
+#ifndef BXG_ILV_4X4
+#define BXG_ILV_4X4 true
+#endif
+template <> struct Tile<32, 24> : TileBase<8, 4, 3, 6, BXG_PIPE_3X6, BXG_MAP_3X6> {};
+template <> struct Tile<16, 24> : TileBase<4, 4, 6, 6, BXG_PIPE_6X6> {};
+template <> struct Tile<16, 16> : TileBase<4, 4, 4, 4, BXG_PIPE_4X4, false, BXG_ILV_4X4> {};
+template <> struct Tile<32, 32> : TileBase<8, 4, 4, 8, false> {};
+template <> struct Tile<32, 16> : TileBase<8, 4, 2, 4, true> {};
+template <> struct Tile<4, 4>   : TileBase<2, 2, 2, 2, false> {};
+template <> struct Tile<4, 8>   : TileBase<2, 2, 4, 4, false> {};
 struct alignas(8) F2 { real x, y; };
 
 template <int TN>
@@ -1114,8 +1140,9 @@ BXG_HD void store_cols(real* p, const real* v) {
 // whose omission leaves every sum unchanged (Ant: 14 of 16, one eighth of the multiply-adds; Humanoid: 23 of 24).
 template <class T, int W, bool NEG = false, int K = W>
 BXG_HD void tile_matmul(int lane, const real* A, const real* B, int ld, real* acc) {
-  const int rg = lane / T::CG, cg = lane - rg * T::CG;
-  const real* a0 = A + rg * T::TM * ld;
+  const int rg = T::rg(lane), cg = T::cg(lane);
+  const real* a0 = A + T::row(rg, 0) * ld;
+  const int rs = (T::row(rg, 1) - T::row(rg, 0)) * ld;      // distance between the lane's consecutive tile rows
   constexpr int KB = (K / 4) * 4, KT = K - KB;   // k steps in full blocks of four, and in the tail block
 #if defined(__CUDA_ARCH__)
   // sm_100a packed FP32: one FFMA2 = two fused multiply-adds per lane (same
@@ -1129,7 +1156,7 @@ BXG_HD void tile_matmul(int lane, const real* A, const real* B, int ld, real* ac
   // explicit software pipeline: the operands of k-block k0 + 4 are requested before the FMAs of block k0
   F4 a_nxt[T::TM]; real b_nxt[4][T::TN];
 #pragma unroll
-  for (int r = 0; r < T::TM; ++r) a_nxt[r] = ldv4(a0 + r * ld);
+  for (int r = 0; r < T::TM; ++r) a_nxt[r] = ldv4(a0 + r * rs);
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) load_cols<T::TN>(B + kk * ld + cg * T::TN, b_nxt[kk]);
   auto block = [&](const F4* a, const real (*bv)[T::TN], auto nk) {
@@ -1157,7 +1184,7 @@ BXG_HD void tile_matmul(int lane, const real* A, const real* B, int ld, real* ac
       for (int cc = 0; cc < T::TN; ++cc) bv[kk][cc] = b_nxt[kk][cc];
     if (k0 + 4 < K) {
 #pragma unroll
-      for (int r = 0; r < T::TM; ++r) a_nxt[r] = ldv4(a0 + r * ld + k0 + 4);
+      for (int r = 0; r < T::TM; ++r) a_nxt[r] = ldv4(a0 + r * rs + k0 + 4);
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) if (k0 + 4 + kk < K) load_cols<T::TN>(B + (k0 + 4 + kk) * ld + cg * T::TN, b_nxt[kk]);
     }
@@ -1168,7 +1195,7 @@ BXG_HD void tile_matmul(int lane, const real* A, const real* B, int ld, real* ac
   auto block = [&](int k0, auto nk) {
     F4 a[T::TM];
 #pragma unroll
-    for (int r = 0; r < T::TM; ++r) a[r] = ldv4(a0 + r * ld + k0);
+    for (int r = 0; r < T::TM; ++r) a[r] = ldv4(a0 + r * rs + k0);
 #pragma unroll
     for (int kk = 0; kk < decltype(nk)::value; ++kk) {
       real bv[T::TN];
@@ -1201,7 +1228,7 @@ BXG_HD void tile_matmul(int lane, const real* A, const real* B, int ld, real* ac
   for (int k0 = 0; k0 < K; k0 += 4) {
     F4 a[T::TM];
 #pragma unroll
-    for (int r = 0; r < T::TM; ++r) a[r] = ldv4(a0 + r * ld + k0);
+    for (int r = 0; r < T::TM; ++r) a[r] = ldv4(a0 + r * rs + k0);
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       if (k0 + kk >= K) break;
@@ -1229,8 +1256,17 @@ BXG_HD void tile_matmul(int lane, const real* A, const real* B, int ld, real* ac
 constexpr int tile_gcd(int a, int b) { return b == 0 ? a : tile_gcd(b, a % b); }
 template <class T, class F>
 BXG_HD void tile_diagonal(int lane, int n, F f) {
+  const int rg = T::rg(lane), cg = T::cg(lane);
+  if constexpr (T::ROWS_ILV) {
+    // rows rg + RG r, columns TN cg + c with TN == RG: the lane's one diagonal element is (r, c) = (cg, rg)
+    static_assert(T::TN == T::RG && T::TM == T::CG, "interleaved rows: square lane grid and tile");
+    const int row = rg + T::RG * cg;
+#pragma unroll
+    for (int r = 0; r < T::TM; ++r)
+#pragma unroll
+      for (int cc = 0; cc < T::TN; ++cc) if (r == cg && cc == rg && row < n) f(r * T::TN + cc);
+  } else {
   constexpr int S = tile_gcd(T::TM, T::TN);
-  const int rg = lane / T::CG, cg = lane - rg * T::CG;
   const int row0 = rg * T::TM, delta = row0 - cg * T::TN;     // diagonal elements: cc = r + delta
   if (delta > -T::TM && delta < T::TN) {
 #pragma unroll
@@ -1243,6 +1279,7 @@ BXG_HD void tile_diagonal(int lane, int n, F f) {
       }
     }
   }
+  }
 }
 template <class T>
 BXG_HD void residual_tile(int lane, int n, real* acc, real* ss, real* mx) {
@@ -1253,9 +1290,9 @@ BXG_HD void residual_tile(int lane, int n, real* acc, real* ss, real* mx) {
 }
 template <class T>
 BXG_HD void store_tile(int lane, real* C, int ld, const real* acc) {
-  const int rg = lane / T::CG, cg = lane - rg * T::CG;
+  const int rg = T::rg(lane), cg = T::cg(lane);
 #pragma unroll
-  for (int r = 0; r < T::TM; ++r) store_cols<T::TN>(C + (rg * T::TM + r) * ld + cg * T::TN, acc + r * T::TN);
+  for (int r = 0; r < T::TM; ++r) store_cols<T::TN>(C + T::row(rg, r) * ld + cg * T::TN, acc + r * T::TN);
 }
 
 // math.inv_approximate (brax/math.py:278-305) on W x W zero-padded matrices.
