@@ -1106,8 +1106,8 @@ struct TileBase {
 template <> struct Tile<32, 24> : TileBase<8, 4, 3, 6, BXG_PIPE_3X6, BXG_MAP_3X6> {};
 template <> struct Tile<16, 24> : TileBase<4, 4, 6, 6, BXG_PIPE_6X6> {};
 template <> struct Tile<16, 16> : TileBase<4, 4, 4, 4, BXG_PIPE_4X4, false, BXG_ILV_4X4> {};
-template <> struct Tile<32, 32> : TileBase<8, 4, 4, 8, false> {};
-template <> struct Tile<32, 16> : TileBase<8, 4, 2, 4, true> {};
+template <> struct Tile<32, 32> : TileBase<8, 4, 4, 8, false, BXG_MAP_3X6> {};
+template <> struct Tile<32, 16> : TileBase<8, 4, 2, 4, true, BXG_MAP_3X6> {};
 template <> struct Tile<4, 4>   : TileBase<2, 2, 2, 2, false> {};
 template <> struct Tile<4, 8>   : TileBase<2, 2, 4, 4, false> {};
 struct alignas(8) F2 { real x, y; };
