@@ -53,9 +53,12 @@
 #define BXG_HD_NOINLINE inline
 #endif
 
-// k-loop unroll of the register-tile product (in blocks of 4 k-steps)
+// k-loop unroll of the register-tile product (in blocks of 4 k-steps).  8 = the whole loop for every tile width.  While the
+// products were LSU-bound the unroll factor did not matter (1 / 2 / 3 / 5 within 1 %); with the pair-shared B operand
+// (TileBase::PAIR_COLS) the loop overhead and the accumulator hand-over MOVs of the peeled first block show:
+// Humanoid 8192 4.45 -> 4.59 / 4.67 / 4.68 M env-steps/s at unroll 3 / 4 / 5 (= full), 512 k 4.86 -> 5.10 M
 #ifndef BXG_TILE_UNROLL
-#define BXG_TILE_UNROLL 2
+#define BXG_TILE_UNROLL 8
 #endif
 // explicit software pipeline in the tile product of the 16-wide variants: unroll of its k-block loop.  4 = the whole loop
 // (W = 16: four blocks; Ant's specialised build: three and the tail).  Rolled, the hand-over of the prefetched operands is
